@@ -1,0 +1,118 @@
+"""Synthetic T1/T2/V2 block stores of a given molecular shape (there is no SCF/CCSD stack in scope).
+
+Two generators (SURVEY 7.2 / 8d "concrete synthetic inputs"):
+  * random_blocks  -- every stored block iid U(-1,1)*scale, seeded per block key (microbench, large shapes)
+  * physical       -- spatial t1/t2/(pq|rs) with the right permutational symmetry, spin-integrated and
+                      antisymmetrised into TCE spin-orbital blocks; gives tile-size-invariant E[T]/E(T).
+Block element order is TCE's: indices in key order, LAST index fastest (src/tce/sort/tce_sort4.F:31).
+"""
+from __future__ import annotations
+import dataclasses
+import numpy as np
+from . import tiling as tl
+
+
+@dataclasses.dataclass
+class BlockStores:
+    t: tl.Tiling
+    t1_hash: np.ndarray; t1: np.ndarray
+    t2_hash: np.ndarray; t2: np.ndarray
+    v2_hash: np.ndarray; v2: np.ndarray
+
+
+def _iter_hash(h):
+    n = int(h[0])
+    for i in range(n):
+        yield int(h[1 + i]), int(h[1 + n + i])
+
+
+def random_blocks(t: tl.Tiling, seed: int = 20240229, scale=(0.05, 0.02, 0.1)) -> BlockStores:
+    t1h, n1 = tl.t1_offset(t); t2h, n2 = tl.t2_offset(t); v2h, nv = tl.v2_offset(t)
+    rng = np.random.default_rng(seed)
+    t1 = rng.uniform(-1, 1, n1) * scale[0]
+    t2 = rng.uniform(-1, 1, n2) * scale[1]
+    v2 = rng.uniform(-1, 1, nv) * scale[2]
+    return BlockStores(t, t1h, t1, t2h, t2, v2h, v2)
+
+
+def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12) -> BlockStores:
+    """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts."""
+    assert t.restricted
+    no = int(sum(t.range[i] for i in range(t.noab) if t.spin[i] == 1))
+    nv = int(sum(t.range[i] for i in range(t.noab, t.noab + t.nvab) if t.spin[i] == 1))
+    n = no + nv
+    # irrep of each spatial orbital (from the alpha tiles)
+    irr = np.zeros(n, dtype=np.int64)
+    for b in range(t.noab + t.nvab):
+        if t.spin[b] == 1:
+            irr[t.members[b]] = t.sym[b]
+    rng = np.random.default_rng(seed)
+    # NOTE: draw in a tiling-independent order so different tilesizes see identical tensors
+    t1s = rng.uniform(-1, 1, (nv, no)) * 0.05
+    t2s = rng.uniform(-1, 1, (nv, nv, no, no)) * 0.02
+    t2s = 0.5 * (t2s + t2s.transpose(1, 0, 3, 2))
+    B = rng.uniform(-1, 1, (naux, n, n)) * 0.3
+    B = 0.5 * (B + B.transpose(0, 2, 1))
+    gam = rng.integers(0, int(irr.max()) + 1, naux)
+    pair = irr[:, None] ^ irr[None, :]
+    for L in range(naux):
+        B[L][pair != gam[L]] = 0.0
+    eri = np.einsum("Lpq,Lrs->pqrs", B, B)  # (pq|rs), 8-fold symmetric, irrep-0
+    io, iv = irr[:no], irr[no:]
+    t1s[(iv[:, None] ^ io[None, :]) != 0] = 0.0
+    m = iv[:, None, None, None] ^ iv[None, :, None, None] ^ io[None, None, :, None] ^ io[None, None, None, :]
+    t2s[m != 0] = 0.0
+
+    def so(b):  # spatial ids and spin of tile b (1-based)
+        return t.members[b - 1], int(t.spin[b - 1])
+
+    def v_block(g3b, g4b, g1b, g2b):
+        (a, sa), (b, sb), (c, sc), (d, sd) = so(g3b), so(g4b), so(g1b), so(g2b)
+        out = np.zeros((len(a), len(b), len(c), len(d)))
+        if sa == sc and sb == sd:  # <ab|cd> = (ac|bd)
+            out += eri[np.ix_(a, c, b, d)].transpose(0, 2, 1, 3)
+        if sa == sd and sb == sc:  # <ab|dc> = (ad|bc)
+            out -= eri[np.ix_(a, d, b, c)].transpose(0, 2, 3, 1)
+        return out
+
+    def t2_block(p1b, p2b, h3b, h4b):
+        (a, sa), (b, sb), (i, si), (j, sj) = so(p1b), so(p2b), so(h3b), so(h4b)
+        a, b = a - no, b - no
+        out = np.zeros((len(a), len(b), len(i), len(j)))
+        if sa == si and sb == sj:
+            out += t2s[np.ix_(a, b, i, j)]
+        if sa == sj and sb == si:
+            out -= t2s[np.ix_(a, b, j, i)].transpose(0, 1, 3, 2)
+        return out
+
+    t1h, n1 = tl.t1_offset(t); t2h, n2 = tl.t2_offset(t); v2h, nv2 = tl.v2_offset(t)
+    t1 = np.zeros(n1); t2 = np.zeros(n2); v2 = np.zeros(nv2)
+    for key, off in _iter_hash(t1h):
+        p5b, h6b = tl.decode_t1_key(t, key)
+        (a, _), (i, _) = so(p5b), so(h6b)
+        blk = t1s[np.ix_(a - no, i)]
+        t1[off:off + blk.size] = blk.ravel()
+    for key, off in _iter_hash(t2h):
+        blk = t2_block(*tl.decode_t2_key(t, key))
+        t2[off:off + blk.size] = blk.ravel()
+    for key, off in _iter_hash(v2h):
+        blk = v_block(*tl.decode_v2_key(t, key))
+        v2[off:off + blk.size] = blk.ravel()
+    return BlockStores(t, t1h, t1, t2h, t2, v2h, v2)
+
+
+# ---- named shapes of BASELINE.json's configs (alpha occ / alpha virt, C1 unless stated) ----
+SHAPES = {
+    # H2O cc-pVDZ on the exact QA tile table (tce_ccsd_t_h2o.out:644-659): irreps a1,a2,b1,b2 = 0,1,2,3
+    "h2o_ccpvdz_c2v": dict(occ=[3, 0, 1, 1], virt=[8, 2, 6, 3], tilesize=20),
+    "h2o_ccpvdz_c1": dict(occ=[5], virt=[19], tilesize=20),
+    "microbench_t40": dict(occ=[40], virt=[40], tilesize=40),
+    "uracil_augccpvdz": dict(occ=[21], virt=[191], tilesize=40),
+    "benzene_dimer_augccpvtz": dict(occ=[30], virt=[786], tilesize=40),
+    "h2o10_augccpvtz": dict(occ=[40], virt=[870], tilesize=40),
+}
+
+
+def shape_tiling(name: str, tilesize: int | None = None, seed: int = 20240229) -> tl.Tiling:
+    s = SHAPES[name]
+    return tl.make_tiling(s["occ"], s["virt"], tilesize or s["tilesize"], True, seed)

@@ -1,0 +1,191 @@
+"""Tile tables and TCE block-store offset tables for the (T) path (host-side integer state).
+
+Mirrors, for the state the (T) driver reads:
+  * tce_tile            src/tce/tce_tile.F:330-357 (tile split), :1279-1312 (k_spin/k_sym/k_range/k_offset/k_alpha)
+  * tce_t1_offset_new   src/tce/tce_t1_offset_new.F:40-53
+  * tce_t2_offset_new   src/tce/tce_t2_offset_new.F:45-68
+  * tce_mo2e_offset     src/tce/tce_mo2e_offset.F:45-67 (restricted here to the three V2 classes (T) reads)
+All tile ids are 1-based as in the reference; arrays are indexed [tile-1].
+"""
+from __future__ import annotations
+import dataclasses
+import numpy as np
+
+I64 = np.int64
+
+
+def tile_group(n: int, isize: int) -> list[int]:
+    """tce_tile.F:330-357: split n orbitals of one (spin, irrep) group into ceil(n/isize) near-equal tiles."""
+    if n <= 0:
+        return []
+    nblocks = n // isize
+    if n > isize * nblocks:
+        nblocks += 1
+    out, done = [], 0
+    for k in range(1, nblocks + 1):
+        r = k * n // nblocks - done
+        done += r
+        out.append(r)
+    return out
+
+
+@dataclasses.dataclass
+class Tiling:
+    noab: int
+    nvab: int
+    restricted: bool
+    spin: np.ndarray      # 1 alpha, 2 beta
+    sym: np.ndarray       # irrep bit code
+    range: np.ndarray
+    offset: np.ndarray    # into evl_sorted
+    alpha: np.ndarray     # 1-based id of the alpha twin (k_alpha)
+    evl_sorted: np.ndarray
+    # bookkeeping for synthetic generators: spatial orbital ids of each tile's members
+    members: list
+
+    @property
+    def ntiles(self) -> int:
+        return self.noab + self.nvab
+
+    def r(self, b: int) -> int:
+        return int(self.range[b - 1])
+
+
+def make_tiling(occ_by_irrep: list[int], virt_by_irrep: list[int], tilesize: int, restricted: bool = True,
+                seed: int = 20240229, evl: tuple | None = None) -> Tiling:
+    """RHF-style tiling: tile order h-alpha (by irrep), h-beta, p-alpha, p-beta (tce_tile.F:300-460).
+
+    Spatial orbital ids: occupied 0..no-1 grouped by irrep, virtual no..no+nv-1 grouped by irrep.
+    `evl` = optional (eps_occ, eps_virt) spatial arrays in that order; default seeded synthetic.
+    """
+    no, nv = sum(occ_by_irrep), sum(virt_by_irrep)
+    rng = np.random.default_rng(seed)
+    if evl is None:
+        eo = np.sort(rng.uniform(-2.0, -0.4, no))
+        ev = np.sort(rng.uniform(0.1, 3.0, nv))
+    else:
+        eo, ev = np.asarray(evl[0], float), np.asarray(evl[1], float)
+    spin, sym, rng_, members = [], [], [], []
+
+    def add_group(counts, base, sp):
+        start = base
+        n_tiles = 0
+        for irrep, n in enumerate(counts):
+            done = 0
+            for r in tile_group(n, tilesize):
+                spin.append(sp); sym.append(irrep); rng_.append(r)
+                members.append(np.arange(start + done, start + done + r))
+                done += r
+                n_tiles += 1
+            start += n
+        return n_tiles
+
+    noa = add_group(occ_by_irrep, 0, 1)
+    nob = add_group(occ_by_irrep, 0, 2)
+    nva = add_group(virt_by_irrep, no, 1)
+    nvb = add_group(virt_by_irrep, no, 2)
+    ntile = noa + nob + nva + nvb
+    rng_a = np.array(rng_, dtype=I64)
+    offset = np.zeros(ntile, dtype=I64)
+    offset[1:] = np.cumsum(rng_a)[:-1]
+    alpha = np.arange(1, ntile + 1, dtype=I64)
+    if restricted:  # tce_tile.F:1293-1306
+        alpha[noa:noa + nob] = np.arange(1, noa + 1)
+        alpha[noa + nob + nva:] = np.arange(noa + nob + 1, noa + nob + nva + 1)
+    eps_spatial = np.concatenate([eo, ev])
+    evl_sorted = np.concatenate([eps_spatial[m] for m in members]) if ntile else np.zeros(0)
+    return Tiling(noab=noa + nob, nvab=nva + nvb, restricted=restricted, spin=np.array(spin, dtype=I64),
+                  sym=np.array(sym, dtype=I64), range=rng_a, offset=offset, alpha=alpha,
+                  evl_sorted=np.ascontiguousarray(evl_sorted, dtype=np.float64), members=members)
+
+
+def _hash(keys: list[int], sizes: list[int]) -> tuple[np.ndarray, int]:
+    """TCE offset table: [n, keys..., offsets...]; keys come out ascending by construction."""
+    n = len(keys)
+    h = np.zeros(2 * n + 1, dtype=I64)
+    h[0] = n
+    h[1:n + 1] = keys
+    off = np.zeros(n, dtype=I64)
+    if n:
+        off[1:] = np.cumsum(np.array(sizes, dtype=I64))[:-1]
+    h[n + 1:] = off
+    assert np.all(np.diff(h[1:n + 1]) > 0), "TCE keys must be strictly ascending"
+    return h, int(sum(sizes))
+
+
+def t1_offset(t: Tiling, irrep: int = 0):
+    keys, sizes = [], []
+    for p5b in range(t.noab + 1, t.noab + t.nvab + 1):
+        for h6b in range(1, t.noab + 1):
+            if t.spin[p5b - 1] != t.spin[h6b - 1]:
+                continue
+            if (t.sym[p5b - 1] ^ t.sym[h6b - 1]) != irrep:
+                continue
+            if t.restricted and t.spin[p5b - 1] + t.spin[h6b - 1] == 4:
+                continue
+            keys.append(h6b - 1 + t.noab * (p5b - t.noab - 1))
+            sizes.append(t.r(p5b) * t.r(h6b))
+    return _hash(keys, sizes)
+
+
+def t2_offset(t: Tiling, irrep: int = 0):
+    keys, sizes = [], []
+    sp, sy = t.spin, t.sym
+    for p1b in range(t.noab + 1, t.noab + t.nvab + 1):
+        for p2b in range(p1b, t.noab + t.nvab + 1):
+            for h3b in range(1, t.noab + 1):
+                for h4b in range(h3b, t.noab + 1):
+                    if sp[p1b - 1] + sp[p2b - 1] != sp[h3b - 1] + sp[h4b - 1]:
+                        continue
+                    if (sy[p1b - 1] ^ sy[p2b - 1] ^ sy[h3b - 1] ^ sy[h4b - 1]) != irrep:
+                        continue
+                    if t.restricted and sp[p1b - 1] + sp[p2b - 1] + sp[h3b - 1] + sp[h4b - 1] == 8:
+                        continue
+                    keys.append(h4b - 1 + t.noab * (h3b - 1 + t.noab * (p2b - t.noab - 1 + t.nvab * (p1b - t.noab - 1))))
+                    sizes.append(t.r(p1b) * t.r(p2b) * t.r(h3b) * t.r(h4b))
+    return _hash(keys, sizes)
+
+
+def v2_offset(t: Tiling, irrep_v: int = 0, triples_only: bool = True):
+    """tce_mo2e_offset.F key order (g3b<=g4b, g1b<=g2b).  With triples_only the table holds only the
+    three classes the (T) path reads: <pp||hh>, <hp||hh>, <pp||hp>."""
+    keys, sizes = [], []
+    sp, sy = t.spin, t.sym
+    N = t.noab + t.nvab
+    is_p = lambda b: b > t.noab
+    for g3b in range(1, N + 1):
+        for g4b in range(g3b, N + 1):
+            for g1b in range(1, N + 1):
+                for g2b in range(g1b, N + 1):
+                    if triples_only:
+                        cls = (is_p(g3b), is_p(g4b), is_p(g1b), is_p(g2b))
+                        if cls not in ((True, True, False, False), (False, True, False, False), (True, True, False, True)):
+                            continue
+                    if sp[g3b - 1] + sp[g4b - 1] != sp[g1b - 1] + sp[g2b - 1]:
+                        continue
+                    if (sy[g3b - 1] ^ sy[g4b - 1] ^ sy[g1b - 1] ^ sy[g2b - 1]) != irrep_v:
+                        continue
+                    if t.restricted and sp[g3b - 1] + sp[g4b - 1] + sp[g1b - 1] + sp[g2b - 1] == 8:
+                        continue
+                    keys.append(g2b - 1 + N * (g1b - 1 + N * (g4b - 1 + N * (g3b - 1))))
+                    sizes.append(t.r(g3b) * t.r(g4b) * t.r(g1b) * t.r(g2b))
+    return _hash(keys, sizes)
+
+
+def decode_t1_key(t: Tiling, key: int):
+    return key // t.noab + t.noab + 1, key % t.noab + 1  # (p5b, h6b)
+
+
+def decode_t2_key(t: Tiling, key: int):
+    h4b = key % t.noab + 1; key //= t.noab
+    h3b = key % t.noab + 1; key //= t.noab
+    p2b = key % t.nvab + t.noab + 1; key //= t.nvab
+    return key + t.noab + 1, p2b, h3b, h4b  # (p1b,p2b,h3b,h4b)
+
+
+def decode_v2_key(t: Tiling, key: int):
+    N = t.noab + t.nvab
+    g2b = key % N + 1; key //= N
+    g1b = key % N + 1; key //= N
+    g4b = key % N + 1; key //= N
+    return key + 1, g4b, g1b, g2b  # (g3b,g4b,g1b,g2b)

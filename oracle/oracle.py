@@ -1,0 +1,144 @@
+"""ctypes binding of oracle/liboracle_triples.so -- TEST INFRASTRUCTURE ONLY (see triples_oracle.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle_triples.so")
+L = C.c_long
+PD = C.POINTER(C.c_double)
+PL = C.POINTER(C.c_long)
+
+
+def build(quiet=True):
+    subprocess.run(["make", "-C", HERE] + (["-s"] if quiet else []), check=True)
+
+
+class Ctx(C.Structure):
+    _fields_ = [("noab", L), ("nvab", L), ("restricted", L), ("irrep_t", L), ("irrep_v", L),
+                ("spin", PL), ("sym", PL), ("range", PL), ("offset", PL), ("alpha", PL), ("evl_sorted", PD),
+                ("t1_hash", PL), ("t1", PD), ("t2_hash", PL), ("t2", PD), ("v2_hash", PL), ("v2", PD)]
+
+
+class Counts(C.Structure):
+    _fields_ = [("flops_s1", C.c_double), ("flops_d1", C.c_double), ("flops_d2", C.c_double),
+                ("calls_s1", L), ("calls_d1", L), ("calls_d2", L)]
+
+    @property
+    def flops(self):
+        return self.flops_s1 + self.flops_d1 + self.flops_d2
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.ora_ccsd_t.restype = L
+        _lib.ora_ccsd_t_6tasks.restype = L
+        _lib.ora_tce_hash.restype = L
+        _lib.ora_tce_tile_group.restype = L
+        _lib.ora_ccsd_t_factor.restype = C.c_double
+    return _lib
+
+
+def _pl(a):
+    return a.ctypes.data_as(PL)
+
+
+def _pd(a):
+    return a.ctypes.data_as(PD)
+
+
+def make_ctx(st):
+    """st: nwchem_b200.synth.BlockStores.  Returns (Ctx, keepalive)."""
+    t = st.t
+    arrs = dict(spin=np.ascontiguousarray(t.spin, np.int64), sym=np.ascontiguousarray(t.sym, np.int64),
+                range=np.ascontiguousarray(t.range, np.int64), offset=np.ascontiguousarray(t.offset, np.int64),
+                alpha=np.ascontiguousarray(t.alpha, np.int64), evl=np.ascontiguousarray(t.evl_sorted, np.float64),
+                t1h=np.ascontiguousarray(st.t1_hash, np.int64), t1=np.ascontiguousarray(st.t1, np.float64),
+                t2h=np.ascontiguousarray(st.t2_hash, np.int64), t2=np.ascontiguousarray(st.t2, np.float64),
+                v2h=np.ascontiguousarray(st.v2_hash, np.int64), v2=np.ascontiguousarray(st.v2, np.float64))
+    c = Ctx(t.noab, t.nvab, int(t.restricted), 0, 0, _pl(arrs["spin"]), _pl(arrs["sym"]), _pl(arrs["range"]),
+            _pl(arrs["offset"]), _pl(arrs["alpha"]), _pd(arrs["evl"]), _pl(arrs["t1h"]), _pd(arrs["t1"]),
+            _pl(arrs["t2h"]), _pd(arrs["t2"]), _pl(arrs["v2h"]), _pd(arrs["v2"]))
+    return c, arrs
+
+
+def task_list(t):
+    l = lib()
+    spin = np.ascontiguousarray(t.spin, np.int64); sym = np.ascontiguousarray(t.sym, np.int64)
+    rng = np.ascontiguousarray(t.range, np.int64)
+    n = l.ora_ccsd_t_6tasks(L(int(t.restricted)), L(t.noab), L(t.nvab), _pl(spin), _pl(sym))
+    kl = np.zeros((max(n, 1), 7), np.int64)
+    l.ora_ccsd_t_neword(L(n), L(int(t.restricted)), L(t.noab), L(t.nvab), _pl(spin), _pl(sym), _pl(rng), _pl(kl))
+    return kl[:n]
+
+
+def ccsd_t(st, per_task=False, count=False):
+    """Whole (T) on the CPU: returns dict(e1, e2, tasks[, per_task, counts])."""
+    l = lib()
+    c, keep = make_ctx(st)
+    n = len(task_list(st.t))
+    e = np.zeros(2)
+    kl = np.zeros((max(n, 1), 7), np.int64)
+    pt = np.zeros((max(n, 1), 2))
+    cnt = Counts()
+    l.ora_ccsd_t(C.byref(c), _pd(e), _pl(kl), _pd(pt), C.byref(cnt))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return dict(e1=float(e[0]), e2=float(e[1]), tasks=kl[:n], per_task=pt[:n], counts=cnt)
+
+
+def tuple_tiles(st, tup):
+    """One tuple (p4b,p5b,p6b,h1b,h2b,h3b): returns (singles, doubles, e1, e2) with the t3 tiles as
+    arrays indexed [p4,p5,p6,h1,h2,h3] (C order == Fortran T3(h3,h2,h1,p6,p5,p4))."""
+    l = lib()
+    c, keep = make_ctx(st)
+    t = st.t
+    dims = [t.r(b) for b in tup]
+    size = int(np.prod(dims))
+    s = np.zeros(size); d = np.zeros(size); e = np.zeros(2)
+    tt = np.array(tup, np.int64)
+    cnt = Counts()
+    l.ora_ccsd_t_loop(C.byref(c), _pl(tt), _pd(s), _pd(d), _pd(e), C.byref(cnt))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return s.reshape(dims), d.reshape(dims), float(e[0]), float(e[1]), cnt
+
+
+def count_tuple(st_or_ctx, tup, keep=None):
+    l = lib()
+    c, keep = make_ctx(st_or_ctx) if keep is None else (st_or_ctx, keep)
+    cnt = Counts()
+    tt = np.array(tup, np.int64)
+    l.ora_ccsd_t_count(C.byref(c), _pl(tt), C.byref(cnt))
+    return cnt
+
+
+def kernel(family, k, dims_perm, kd, triplesx, tsub, v2sub):
+    """Call one of the 27 CPU kernels. dims_perm = (h3d,h2d,h1d,p6d,p5d,p4d) of the PERMUTED tuple."""
+    l = lib()
+    h3d, h2d, h1d, p6d, p5d, p4d = [int(x) for x in dims_perm]
+    l.ora_sd_t_kernel(L(family), L(k), L(h3d), L(h2d), L(h1d), L(p6d), L(p5d), L(p4d), L(int(kd)),
+                      _pd(triplesx), _pd(tsub), _pd(v2sub))
+
+
+def tile_group(n, isize):
+    l = lib()
+    out = np.zeros(max(n, 1), np.int64)
+    k = l.ora_tce_tile_group(L(n), L(isize), _pl(out))
+    return [int(x) for x in out[:k]]
+
+
+def num_threads():
+    return int(lib().ora_num_threads())

@@ -1,0 +1,740 @@
+/*
+ * oracle/triples_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C + OpenMP) of NWChem's TCE CCSD(T) perturbative-triples path,
+ * src/tce/ccsd_t.  It is the checker for the CUDA library and the "port" CPU baseline of
+ * bench.py; nothing in the product path (nwchem_b200/, libnwc_triples.so) may call it.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ * Arrays are Fortran column-major restated with explicit 0-based index arithmetic.
+ *
+ * PARITY PIN STATUS: the reference ships no kernel-level golden vectors for this path and
+ * its Fortran cannot be compiled in this image (no Fortran compiler, no GA/MPI).  The
+ * oracle is pinned by (i) the H2O/cc-pVDZ tile table of QA/tests/tce_ccsd_t_h2o
+ * (tce_ccsd_t_h2o.out:644-659), (ii) agreement of the 27 kernels + energy kernel with the
+ * reference's own CUDA implementation (sd_t_total.cu + memory.cu compiled unmodified into
+ * oracle/_ref, run on the GPU box), (iii) an independent second formulation
+ * (sort -> GEMM -> sortacc_6, ccsd_t_doubles.F:195-267) and (iv) tile-size invariance of
+ * E[T]/E(T) on antisymmetric synthetic amplitudes.  End-to-end energies of the QA outputs
+ * need converged CCSD amplitudes that nothing in scope can produce: that part is unpinned.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef long Integer; /* header.h:51 */
+
+#define RESTRICT __restrict__
+
+/* ------------------------------------------------------------------------------------ */
+/* 27 contraction kernels: src/tce/ccsd_t/ccsd_t_kernels_omp.F                           */
+/* Argument order is the CPU one: (h3d,h2d,h1d,p6d,p5d,p4d[,h7d|p7d],triplesx,t?sub,v2sub) */
+/* ------------------------------------------------------------------------------------ */
+#define T6(a, b, c, d, e, f, da, db, dc, dd, de) \
+  ((a) + (da) * ((b) + (db) * ((c) + (dc) * ((d) + (dd) * ((e) + (de) * (f))))))
+
+/* sd_t_s1_K: triplesx(A,B,C,D,E,F) SGN= t1sub(p4,h1)*v2sub(h3,h2,p6,p5)
+ * (ccsd_t_kernels_omp.F:5-360; declared layouts at :10,49,88,133,173,213,253,293,330) */
+#define DEF_S1(K, A, B, C, D, E, F, SGN)                                                       \
+  void ora_sd_t_s1_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,       \
+                       Integer p4d, double *RESTRICT triplesx, const double *RESTRICT t1sub,  \
+                       const double *RESTRICT v2sub) {                                        \
+    _Pragma("omp parallel for collapse(3) schedule(static)")                                  \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##=           \
+                    t1sub[p4 + p4d * h1] * v2sub[h3 + h3d * (h2 + h2d * (p6 + p6d * p5))];    \
+  }
+DEF_S1(1, h3, h2, h1, p6, p5, p4, +)
+DEF_S1(2, h3, h1, h2, p6, p5, p4, -)
+DEF_S1(3, h1, h3, h2, p6, p5, p4, +)
+DEF_S1(4, h3, h2, h1, p6, p4, p5, -)
+DEF_S1(5, h3, h1, h2, p6, p4, p5, +)
+DEF_S1(6, h1, h3, h2, p6, p4, p5, -)
+DEF_S1(7, h3, h2, h1, p4, p6, p5, +)
+DEF_S1(8, h3, h1, h2, p4, p6, p5, -)
+DEF_S1(9, h1, h3, h2, p4, p6, p5, +)
+
+/* sd_t_d1_K: triplesx(A..F) SGN= sum_h7 t2sub(h7,p4,p5,h1)*v2sub(h3,h2,p6,h7)
+ * (ccsd_t_kernels_omp.F:362-855).  Like the reference (:370-384) v2sub is first
+ * transposed into v2tmp(h7,h3,h2,p6) so the h7 sum is unit stride. */
+#define DEF_D1(K, A, B, C, D, E, F, SGN)                                                       \
+  void ora_sd_t_d1_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,       \
+                       Integer p4d, Integer h7d, double *RESTRICT triplesx,                   \
+                       const double *RESTRICT t2sub, const double *RESTRICT v2sub) {          \
+    double *v2tmp = (double *)malloc(sizeof(double) * (size_t)(h7d * h3d * h2d * p6d + 1));   \
+    _Pragma("omp parallel for collapse(3) schedule(static)")                                  \
+    for (Integer p6 = 0; p6 < p6d; p6++)                                                      \
+      for (Integer h7 = 0; h7 < h7d; h7++)                                                    \
+        for (Integer h2 = 0; h2 < h2d; h2++)                                                  \
+          for (Integer h3 = 0; h3 < h3d; h3++)                                                \
+            v2tmp[h7 + h7d * (h3 + h3d * (h2 + h2d * p6))] =                                  \
+                v2sub[h3 + h3d * (h2 + h2d * (p6 + p6d * h7))];                               \
+    _Pragma("omp parallel for collapse(3) schedule(static)")                                  \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++) {                                          \
+                const double *a = t2sub + h7d * (p4 + p4d * (p5 + p5d * h1));                 \
+                const double *b = v2tmp + h7d * (h3 + h3d * (h2 + h2d * p6));                 \
+                double s = 0.0;                                                               \
+                _Pragma("omp simd reduction(+:s)")                                            \
+                for (Integer h7 = 0; h7 < h7d; h7++) s += a[h7] * b[h7];                      \
+                triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##= s;        \
+              }                                                                               \
+    free(v2tmp);                                                                              \
+  }
+DEF_D1(1, h3, h2, h1, p6, p5, p4, -)
+DEF_D1(2, h3, h1, h2, p6, p5, p4, +)
+DEF_D1(3, h1, h3, h2, p6, p5, p4, -)
+DEF_D1(4, h3, h2, h1, p5, p4, p6, -)
+DEF_D1(5, h3, h1, h2, p5, p4, p6, +)
+DEF_D1(6, h1, h3, h2, p5, p4, p6, -)
+DEF_D1(7, h3, h2, h1, p5, p6, p4, +)
+DEF_D1(8, h3, h1, h2, p5, p6, p4, -)
+DEF_D1(9, h1, h3, h2, p5, p6, p4, +)
+
+/* sd_t_d2_K: triplesx(A..F) SGN= sum_p7 t2sub(p7,p4,h1,h2)*v2sub(p7,h3,p6,p5)
+ * (ccsd_t_kernels_omp.F:857-1198) */
+#define DEF_D2(K, A, B, C, D, E, F, SGN)                                                       \
+  void ora_sd_t_d2_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,       \
+                       Integer p4d, Integer p7d, double *RESTRICT triplesx,                   \
+                       const double *RESTRICT t2sub, const double *RESTRICT v2sub) {          \
+    _Pragma("omp parallel for collapse(3) schedule(static)")                                  \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++) {                                          \
+                const double *a = t2sub + p7d * (p4 + p4d * (h1 + h1d * h2));                 \
+                const double *b = v2sub + p7d * (h3 + h3d * (p6 + p6d * p5));                 \
+                double s = 0.0;                                                               \
+                _Pragma("omp simd reduction(+:s)")                                            \
+                for (Integer p7 = 0; p7 < p7d; p7++) s += a[p7] * b[p7];                      \
+                triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##= s;        \
+              }                                                                               \
+  }
+DEF_D2(1, h3, h2, h1, p6, p5, p4, -)
+DEF_D2(2, h2, h1, h3, p6, p5, p4, -)
+DEF_D2(3, h2, h3, h1, p6, p5, p4, +)
+DEF_D2(4, h3, h2, h1, p6, p4, p5, +)
+DEF_D2(5, h2, h1, h3, p6, p4, p5, +)
+DEF_D2(6, h2, h3, h1, p6, p4, p5, -)
+DEF_D2(7, h3, h2, h1, p4, p6, p5, -)
+DEF_D2(8, h2, h1, h3, p4, p6, p5, -)
+DEF_D2(9, h2, h3, h1, p4, p6, p5, +)
+
+typedef void (*s1_fn)(Integer, Integer, Integer, Integer, Integer, Integer, double *,
+                      const double *, const double *);
+typedef void (*d_fn)(Integer, Integer, Integer, Integer, Integer, Integer, Integer, double *,
+                     const double *, const double *);
+static const s1_fn S1[9] = {ora_sd_t_s1_1, ora_sd_t_s1_2, ora_sd_t_s1_3, ora_sd_t_s1_4, ora_sd_t_s1_5,
+                            ora_sd_t_s1_6, ora_sd_t_s1_7, ora_sd_t_s1_8, ora_sd_t_s1_9};
+static const d_fn D1[9] = {ora_sd_t_d1_1, ora_sd_t_d1_2, ora_sd_t_d1_3, ora_sd_t_d1_4, ora_sd_t_d1_5,
+                           ora_sd_t_d1_6, ora_sd_t_d1_7, ora_sd_t_d1_8, ora_sd_t_d1_9};
+static const d_fn D2[9] = {ora_sd_t_d2_1, ora_sd_t_d2_2, ora_sd_t_d2_3, ora_sd_t_d2_4, ora_sd_t_d2_5,
+                           ora_sd_t_d2_6, ora_sd_t_d2_7, ora_sd_t_d2_8, ora_sd_t_d2_9};
+
+/* generic entry points by (family, k): family 0 = s1, 1 = d1, 2 = d2; kd ignored for s1 */
+void ora_sd_t_kernel(Integer family, Integer k, Integer h3d, Integer h2d, Integer h1d, Integer p6d,
+                     Integer p5d, Integer p4d, Integer kd, double *triplesx, const double *tsub,
+                     const double *v2sub) {
+  if (family == 0) S1[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, triplesx, tsub, v2sub);
+  else if (family == 1) D1[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
+  else D2[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Energy: src/tce/ccsd_t/ccsd_t_dot.F:52-124                                            */
+/* ------------------------------------------------------------------------------------ */
+double ora_ccsd_t_factor(int restricted, Integer h1b, Integer h2b, Integer h3b, Integer p4b,
+                         Integer p5b, Integer p6b) {
+  double factor = restricted ? 2.0 : 1.0; /* :52-56 */
+  if (p4b == p5b && p5b == p6b) factor /= 6.0; /* :57-61 */
+  else if (p4b == p5b || p5b == p6b) factor /= 2.0;
+  if (h1b == h2b && h2b == h3b) factor /= 6.0; /* :62-66 */
+  else if (h1b == h2b || h2b == h3b) factor /= 2.0;
+  return factor;
+}
+
+void ora_ccsd_t_dot(const double *a_singles, const double *a_doubles, int restricted, Integer h1b,
+                    Integer h2b, Integer h3b, Integer p4b, Integer p5b, Integer p6b,
+                    const double *o_h1, const double *o_h2, const double *o_h3, const double *o_p4,
+                    const double *o_p5, const double *o_p6, Integer r_h1, Integer r_h2, Integer r_h3,
+                    Integer r_p4, Integer r_p5, Integer r_p6, double *energy1, double *energy2) {
+  const double factor = ora_ccsd_t_factor(restricted, h1b, h2b, h3b, p4b, p5b, p6b);
+  double e1 = 0.0, e2 = 0.0;
+#pragma omp parallel for collapse(3) schedule(static) reduction(+ : e1, e2)
+  for (Integer p4 = 0; p4 < r_p4; p4++)
+    for (Integer p5 = 0; p5 < r_p5; p5++)
+      for (Integer p6 = 0; p6 < r_p6; p6++) {
+        const double denom_0 = -(o_p4[p4] + o_p5[p5] + o_p6[p6]); /* :105 */
+        for (Integer h1 = 0; h1 < r_h1; h1++)
+          for (Integer h2 = 0; h2 < r_h2; h2++)
+            for (Integer h3 = 0; h3 < r_h3; h3++) {
+              const size_t i = T6(h3, h2, h1, p6, p5, p4, r_h3, r_h2, r_h1, r_p6, r_p5);
+              const double sing = a_singles[i], doub = a_doubles[i];
+              const double denom = doub * factor / (o_h1[h1] + o_h2[h2] + o_h3[h3] + denom_0); /* :114 */
+              e1 += denom * doub;          /* :115 */
+              e2 += denom * (doub + sing); /* :116 */
+            }
+      }
+  *energy1 += e1;
+  *energy2 += e2;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Block store helpers                                                                   */
+/* ------------------------------------------------------------------------------------ */
+/* tce_hash: src/tce/tce_hash.F:271-322.  hash[0]=n, hash[1..n]=sorted keys,
+ * hash[n+1..2n]=offsets.  Returns -1 (reference: errquit) if the key is absent. */
+Integer ora_tce_hash(const Integer *hash, Integer key) {
+  Integer length = hash[0], less = 1, more = length, middle;
+  for (;;) {
+    if (more - less <= 4) {
+      middle = -1;
+      for (Integer i = less; i <= more; i++)
+        if (hash[i] == key) middle = i;
+      if (middle == -1) return -1;
+      break;
+    }
+    middle = (less + more) / 2;
+    if (hash[middle] == key) break;
+    else if (hash[middle] > key) more = middle;
+    else less = middle;
+  }
+  return hash[length + middle];
+}
+
+static int g_error = 0;
+int ora_error(void) { int e = g_error; g_error = 0; return e; }
+
+/* get_hash_block (src/tce/get_hash_block.F:1-45) with the GA file replaced by host memory */
+static void get_hash_block(const double *d_file, double *array, Integer size, const Integer *hash,
+                           Integer key) {
+  Integer offset = ora_tce_hash(hash, key);
+  if (offset < 0) {
+    fprintf(stderr, "oracle: tce_hash: key not found %ld\n", key);
+    g_error = 1;
+    memset(array, 0, sizeof(double) * (size_t)size);
+    return;
+  }
+  memcpy(array, d_file + offset, sizeof(double) * (size_t)size);
+}
+
+/* tce_sort_2: src/tce/sort/new_sort2.F:4-30 (semantics of the plain algorithm):
+ * unsorted(a,b) row-major-with-last-index-fastest -> sorted in order (i,j) */
+void ora_tce_sort_2(const double *unsorted, double *sorted, Integer a, Integer b, Integer i, Integer j,
+                    double factor) {
+  Integer id[2], jd[2] = {a, b};
+  for (id[0] = 0; id[0] < a; id[0]++)
+    for (id[1] = 0; id[1] < b; id[1]++) {
+      Integer ia = id[1] + b * id[0];
+      Integer ib = id[j - 1] + jd[j - 1] * id[i - 1];
+      sorted[ib] = unsorted[ia] * factor;
+    }
+}
+
+/* tce_sort_4: src/tce/sort/tce_sort4.F:1-80 (new_sort4.F is a blocked version of the same map) */
+void ora_tce_sort_4(const double *unsorted, double *sorted, Integer a, Integer b, Integer c, Integer d,
+                    Integer i, Integer j, Integer k, Integer l, double factor) {
+  Integer jd[4] = {a, b, c, d};
+#pragma omp parallel for schedule(static)
+  for (Integer j1 = 0; j1 < a; j1++) {
+    Integer id[4];
+    id[0] = j1;
+    for (id[1] = 0; id[1] < b; id[1]++)
+      for (id[2] = 0; id[2] < c; id[2]++)
+        for (id[3] = 0; id[3] < d; id[3]++) {
+          Integer ia = id[3] + d * (id[2] + c * (id[1] + b * id[0]));
+          Integer ib = id[l - 1] + jd[l - 1] * (id[k - 1] + jd[k - 1] * (id[j - 1] + jd[j - 1] * id[i - 1]));
+          sorted[ib] = unsorted[ia] * factor;
+        }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Driver state (the common blocks of src/tce/include/tce.fh, tce_main.fh)              */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  Integer noab, nvab;            /* tce.fh:19-20 */
+  Integer restricted;            /* tce.fh:78 */
+  Integer irrep_t, irrep_v;      /* sym.fh; 0 for ground-state CC */
+  const Integer *spin;           /* k_spin  [noab+nvab], 1=alpha 2=beta */
+  const Integer *sym;            /* k_sym   irrep bit code */
+  const Integer *range;          /* k_range tile sizes */
+  const Integer *offset;         /* k_offset into evl_sorted */
+  const Integer *alpha;          /* k_alpha (1-based tile ids) */
+  const double *evl_sorted;      /* k_evl_sorted */
+  const Integer *t1_hash; const double *t1; /* tce_t1_offset_new.F */
+  const Integer *t2_hash; const double *t2; /* tce_t2_offset_new.F */
+  const Integer *v2_hash; const double *v2; /* tce_mo2e_offset.F   */
+} ora_ctx;
+
+#define SPIN(b) (c->spin[(b) - 1])
+#define SYM(b) (c->sym[(b) - 1])
+#define RANGE(b) (c->range[(b) - 1])
+
+/* tce_restricted_2/4: src/tce/tce_restricted.F:1-71 */
+static void restricted_2(const ora_ctx *c, Integer a1, Integer a2, Integer *b1, Integer *b2) {
+  if (c->restricted && SPIN(a1) + SPIN(a2) == 4) { *b1 = c->alpha[a1 - 1]; *b2 = c->alpha[a2 - 1]; }
+  else { *b1 = a1; *b2 = a2; }
+}
+static void restricted_4(const ora_ctx *c, Integer a1, Integer a2, Integer a3, Integer a4, Integer *b1,
+                         Integer *b2, Integer *b3, Integer *b4) {
+  if (c->restricted && SPIN(a1) + SPIN(a2) + SPIN(a3) + SPIN(a4) == 8) {
+    *b1 = c->alpha[a1 - 1]; *b2 = c->alpha[a2 - 1]; *b3 = c->alpha[a3 - 1]; *b4 = c->alpha[a4 - 1];
+  } else { *b1 = a1; *b2 = a2; *b3 = a3; *b4 = a4; }
+}
+
+/* de-duplication of the 9-row permutation table (ccsd_t_singles_l.F / ccsd_t_singles_gpu.F:166-182) */
+static void dedup_rows(Integer a3[9][6]) {
+  for (int ia = 0; ia < 8; ia++)
+    if (a3[ia][0] != 0)
+      for (int ja = ia + 1; ja < 9; ja++) {
+        int same = 1;
+        for (int q = 0; q < 6; q++) same &= (a3[ia][q] == a3[ja][q]);
+        if (same) for (int q = 0; q < 6; q++) a3[ja][q] = 0;
+      }
+}
+
+/* the four tuple-level filters shared by the three per-tuple drivers
+ * (e.g. ccsd_t_singles_gpu.F:203-211, offl_ccsd_t_doubles_l.F:281-290) */
+static int row_allowed(const ora_ctx *c, Integer p4b, Integer p5b, Integer p6b, Integer h1b, Integer h2b,
+                       Integer h3b) {
+  Integer ssum = SPIN(p4b) + SPIN(p5b) + SPIN(p6b) + SPIN(h1b) + SPIN(h2b) + SPIN(h3b);
+  if (c->restricted && ssum == 12) return 0;
+  if (SPIN(p4b) + SPIN(p5b) + SPIN(p6b) != SPIN(h1b) + SPIN(h2b) + SPIN(h3b)) return 0;
+  if ((SYM(p4b) ^ SYM(p5b) ^ SYM(p6b) ^ SYM(h1b) ^ SYM(h2b) ^ SYM(h3b)) != (c->irrep_v ^ c->irrep_t)) return 0;
+  return 1;
+}
+
+/* per-kernel flop / call counters filled by the drivers (dry-run capable) */
+typedef struct {
+  double flops_s1, flops_d1, flops_d2;
+  Integer calls_s1, calls_d1, calls_d2;
+} ora_counts;
+
+/* ------------------------------------------------------------------------------------ */
+/* Singles: ccsd_t_singles_l.F:30-463 == ccsd_t_singles_gpu.F:36-574                     */
+/* ------------------------------------------------------------------------------------ */
+void ora_ccsd_t_singles_l(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                          Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  /* P rows (p4|p5 p6): (p4,p5,p6),(p5,p4,p6),(p6,p4,p5); H rows: (h1,h2,h3),(h2,h1,h3),(h3,h1,h2)
+   * ccsd_t_singles_gpu.F:101-162 */
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+  static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+  Integer a3[9][6];
+  for (int ip = 0; ip < 3; ip++)
+    for (int ih = 0; ih < 3; ih++) {
+      Integer *r = a3[ip * 3 + ih];
+      r[0] = tp[P[ip][0]]; r[1] = tp[P[ip][1]]; r[2] = tp[P[ip][2]];
+      r[3] = th[H[ih][0]]; r[4] = th[H[ih][1]]; r[5] = th[H[ih][2]];
+    }
+  dedup_rows(a3);
+  const Integer N = c->noab + c->nvab;
+  for (int ia6 = 0; ia6 < 9; ia6++) {
+    const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2];
+    const Integer h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+    if (!(p5b <= p6b && h2b <= h3b && p4b != 0)) continue; /* :200 */
+    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue; /* :203-211 */
+    if (SPIN(p4b) != SPIN(h1b)) continue; /* :218 */
+    if ((SYM(p4b) ^ SYM(h1b)) != c->irrep_t) continue; /* :219 */
+    Integer p4b_1, h1b_1, p5b_2, p6b_2, h2b_2, h3b_2;
+    restricted_2(c, p4b, h1b, &p4b_1, &h1b_1); /* :221 */
+    restricted_4(c, p5b, p6b, h2b, h3b, &p5b_2, &p6b_2, &h2b_2, &h3b_2); /* :222 */
+    const Integer dima = RANGE(p4b) * RANGE(h1b);
+    const Integer dimb = RANGE(p5b) * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
+    if (!(dima > 0 && dimb > 0)) continue;
+    double *k_a = NULL, *k_a_sort = NULL, *k_b_sort = NULL;
+    if (!dryrun) {
+      k_a = (double *)malloc(sizeof(double) * dima);
+      k_a_sort = (double *)malloc(sizeof(double) * dima);
+      k_b_sort = (double *)malloc(sizeof(double) * dimb);
+      get_hash_block(c->t1, k_a, dima, c->t1_hash, h1b_1 - 1 + c->noab * (p4b_1 - c->noab - 1)); /* :234 */
+      ora_tce_sort_2(k_a, k_a_sort, RANGE(p4b), RANGE(h1b), 2, 1, 1.0); /* :237 */
+      get_hash_block(c->v2, k_b_sort, dimb, c->v2_hash,
+                     h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1)))); /* :246 */
+    }
+    /* nine dispatch tests (ccsd_t_singles_gpu.F:281,310,340,370,401,431,462,493,524):
+     * test K holds when (t_p4b,t_p5b,t_p6b) == row permuted by TP[K] and (t_h..) by TH[K] */
+    static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* t_p4b==p4b..; ==p5b,p4b,p6b; ==p5b,p6b,p4b */
+    static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* t_h1b==h1b..; ==h2b,h1b,h3b; ==h2b,h3b,h1b */
+    const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+    for (int kp = 0; kp < 3; kp++)
+      for (int kh = 0; kh < 3; kh++) {
+        if (!(t_p4b == rp[TP[kp][0]] && t_p5b == rp[TP[kp][1]] && t_p6b == rp[TP[kp][2]] &&
+              t_h1b == rh[TH[kh][0]] && t_h2b == rh[TH[kh][1]] && t_h3b == rh[TH[kh][2]]))
+          continue;
+        const int K = kp * 3 + kh; /* 0..8 -> sd_t_s1_{K+1} */
+        if (cnt) {
+          cnt->calls_s1++;
+          cnt->flops_s1 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) * RANGE(h3b);
+        }
+        if (!dryrun)
+          S1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort);
+      }
+    free(k_a); free(k_a_sort); free(k_b_sort);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* tce_hashnsort / tce_hashnsort_2: src/tce/ccsd_t/tce_hashnsort.F                       */
+/* ------------------------------------------------------------------------------------ */
+static int hashnsort(const ora_ctx *c, int dryrun, Integer p4b, Integer p5b, Integer h1b, Integer h7b,
+                     Integer p6b, Integer h2b, Integer h3b, double *t2sub, double *v2sub) {
+  if (!(SPIN(p4b) + SPIN(p5b) == SPIN(h1b) + SPIN(h7b) &&
+        (SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h7b)) == c->irrep_t)) return 0; /* :28-32 */
+  const Integer N = c->noab + c->nvab, noab = c->noab, nvab = c->nvab;
+  const Integer dim_common = RANGE(h7b);
+  const Integer dima = dim_common * RANGE(p4b) * RANGE(p5b) * RANGE(h1b);
+  const Integer dimb = dim_common * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
+  if (!dryrun && dima > 0 && dimb > 0) {
+    Integer p4b_1, p5b_1, h1b_1, h7b_1, p6b_2, h7b_2, h2b_2, h3b_2;
+    restricted_4(c, p4b, p5b, h1b, h7b, &p4b_1, &p5b_1, &h1b_1, &h7b_1);
+    restricted_4(c, p6b, h7b, h2b, h3b, &p6b_2, &h7b_2, &h2b_2, &h3b_2);
+    double *k_a = (double *)malloc(sizeof(double) * dima);
+    if (h7b < h1b) { /* :47-53 */
+      get_hash_block(c->t2, k_a, dima, c->t2_hash,
+                     h1b_1 - 1 + noab * (h7b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+      ora_tce_sort_4(k_a, t2sub, RANGE(p4b), RANGE(p5b), RANGE(h7b), RANGE(h1b), 4, 2, 1, 3, -1.0);
+    }
+    if (h1b <= h7b) { /* :55-62 */
+      get_hash_block(c->t2, k_a, dima, c->t2_hash,
+                     h7b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+      ora_tce_sort_4(k_a, t2sub, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h7b), 3, 2, 1, 4, 1.0);
+    }
+    free(k_a);
+    if (h7b <= p6b) /* :66-80 (always true: occupied tiles precede virtual tiles) */
+      get_hash_block(c->v2, v2sub, dimb, c->v2_hash,
+                     h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (h7b_2 - 1))));
+  }
+  return 1;
+}
+
+static int hashnsort_2(const ora_ctx *c, int dryrun, Integer p4b, Integer p7b, Integer h1b, Integer h2b,
+                       Integer p5b, Integer p6b, Integer h3b, double *t2sub, double *v2sub) {
+  if (!(SPIN(p4b) + SPIN(p7b) == SPIN(h1b) + SPIN(h2b) &&
+        (SYM(p4b) ^ SYM(p7b) ^ SYM(h1b) ^ SYM(h2b)) == c->irrep_t)) return 0; /* :111-114 */
+  const Integer N = c->noab + c->nvab, noab = c->noab, nvab = c->nvab;
+  const Integer dim_common = RANGE(p7b);
+  const Integer dima = dim_common * RANGE(p4b) * RANGE(h1b) * RANGE(h2b);
+  const Integer dimb = dim_common * RANGE(p5b) * RANGE(p6b) * RANGE(h3b);
+  if (!dryrun && dima > 0 && dimb > 0) {
+    Integer p4b_1, p7b_1, h1b_1, h2b_1, p5b_2, p6b_2, h3b_2, p7b_2;
+    restricted_4(c, p4b, p7b, h1b, h2b, &p4b_1, &p7b_1, &h1b_1, &h2b_1);
+    restricted_4(c, p5b, p6b, h3b, p7b, &p5b_2, &p6b_2, &h3b_2, &p7b_2);
+    double *k_a = (double *)malloc(sizeof(double) * dima);
+    if (p7b < p4b) { /* :129-135 */
+      get_hash_block(c->t2, k_a, dima, c->t2_hash,
+                     h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p4b_1 - noab - 1 + nvab * (p7b_1 - noab - 1))));
+      ora_tce_sort_4(k_a, t2sub, RANGE(p7b), RANGE(p4b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, -1.0);
+    }
+    if (p4b <= p7b) { /* :137-144 */
+      get_hash_block(c->t2, k_a, dima, c->t2_hash,
+                     h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p7b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+      ora_tce_sort_4(k_a, t2sub, RANGE(p4b), RANGE(p7b), RANGE(h1b), RANGE(h2b), 4, 3, 1, 2, 1.0);
+    }
+    free(k_a);
+    if (h3b <= p7b) /* :149-161 (always true) */
+      get_hash_block(c->v2, v2sub, dimb, c->v2_hash,
+                     p7b_2 - 1 + N * (h3b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1))));
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Doubles: offl_ccsd_t_doubles_l.F:72-1041 (ccsd_t_doubles_l_12)                        */
+/*          == ccsd_t_doubles_gpu.F:48-742 (_1) and :743-1345 (_2)                       */
+/* ------------------------------------------------------------------------------------ */
+void ora_ccsd_t_doubles_l(const ora_ctx *c, double *triplesx, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                          Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  const Integer noab = c->noab, nvab = c->nvab;
+  /* scratch sized as ccsd_t_v2t2lgth (ccsd_t_doubles_l.F:118-141): max tile^4 */
+  Integer maxr = 0;
+  for (Integer b = 1; b <= noab + nvab; b++) if (RANGE(b) > maxr) maxr = RANGE(b);
+  double *t2sub = NULL, *v2sub = NULL;
+  if (!dryrun) {
+    t2sub = (double *)malloc(sizeof(double) * (size_t)(maxr * maxr * maxr * maxr));
+    v2sub = (double *)malloc(sizeof(double) * (size_t)(maxr * maxr * maxr * maxr));
+  }
+  Integer a3[9][6];
+  /* ---- Sum(h7) family: rows offl_ccsd_t_doubles_l.F:176-237 ---- */
+  {
+    static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
+    static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (h1,h2,h3),(h2,h1,h3),(h3,h1,h2) */
+    for (int ip = 0; ip < 3; ip++)
+      for (int ih = 0; ih < 3; ih++) {
+        Integer *r = a3[ip * 3 + ih];
+        r[0] = tp[P[ip][0]]; r[1] = tp[P[ip][1]]; r[2] = tp[P[ip][2]];
+        r[3] = th[H[ih][0]]; r[4] = th[H[ih][1]]; r[5] = th[H[ih][2]];
+      }
+    dedup_rows(a3);
+    for (int ia6 = 0; ia6 < 9; ia6++) {
+      const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2];
+      const Integer h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+      if (!(p4b <= p5b && h2b <= h3b && p4b != 0)) continue; /* :281 */
+      if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue; /* :282-290 */
+      const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+      for (Integer h7b = 1; h7b <= noab; h7b++) { /* :325 (rotation by ga_nodeid only reorders) */
+        if (!hashnsort(c, dryrun, p4b, p5b, h1b, h7b, p6b, h2b, h3b, t2sub, v2sub)) continue;
+        /* dispatch tests ccsd_t_doubles_gpu.F:357,394,433,474,515,556,597,638,679 */
+        static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
+        static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==h1,h2,h3; ==h2,h1,h3; ==h2,h3,h1 */
+        for (int kp = 0; kp < 3; kp++)
+          for (int kh = 0; kh < 3; kh++) {
+            if (!(t_p4b == rp[TP[kp][0]] && t_p5b == rp[TP[kp][1]] && t_p6b == rp[TP[kp][2]] &&
+                  t_h1b == rh[TH[kh][0]] && t_h2b == rh[TH[kh][1]] && t_h3b == rh[TH[kh][2]]))
+              continue;
+            const int K = kp * 3 + kh;
+            if (cnt) {
+              cnt->calls_d1++;
+              cnt->flops_d1 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) *
+                               RANGE(h3b) * RANGE(h7b);
+            }
+            if (!dryrun)
+              D1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b),
+                    triplesx, t2sub, v2sub);
+          }
+      }
+    }
+  }
+  /* ---- Sum(p7) family: rows offl_ccsd_t_doubles_l.F:611-672 ---- */
+  {
+    static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
+    static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (h1,h2,h3),(h2,h3,h1),(h1,h3,h2) */
+    for (int ip = 0; ip < 3; ip++)
+      for (int ih = 0; ih < 3; ih++) {
+        Integer *r = a3[ip * 3 + ih];
+        r[0] = tp[P[ip][0]]; r[1] = tp[P[ip][1]]; r[2] = tp[P[ip][2]];
+        r[3] = th[H[ih][0]]; r[4] = th[H[ih][1]]; r[5] = th[H[ih][2]];
+      }
+    dedup_rows(a3);
+    for (int ia6 = 0; ia6 < 9; ia6++) {
+      const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2];
+      const Integer h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+      if (!(p5b <= p6b && h1b <= h2b && p4b != 0)) continue; /* :699 */
+      if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue; /* :700-708 */
+      const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+      for (Integer p7b = noab + 1; p7b <= noab + nvab; p7b++) { /* :739 */
+        if (!hashnsort_2(c, dryrun, p4b, p7b, h1b, h2b, p5b, p6b, h3b, t2sub, v2sub)) continue;
+        /* dispatch tests ccsd_t_doubles_gpu.F:998,1034,1070,1106,1142,1178,1214,1250,1286 */
+        static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==p4,p5,p6; ==p5,p4,p6; ==p5,p6,p4 */
+        static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==h1,h2,h3; ==h3,h1,h2; ==h1,h3,h2 */
+        for (int kp = 0; kp < 3; kp++)
+          for (int kh = 0; kh < 3; kh++) {
+            if (!(t_p4b == rp[TP[kp][0]] && t_p5b == rp[TP[kp][1]] && t_p6b == rp[TP[kp][2]] &&
+                  t_h1b == rh[TH[kh][0]] && t_h2b == rh[TH[kh][1]] && t_h3b == rh[TH[kh][2]]))
+              continue;
+            const int K = kp * 3 + kh;
+            if (cnt) {
+              cnt->calls_d2++;
+              cnt->flops_d2 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) *
+                               RANGE(h3b) * RANGE(p7b);
+            }
+            if (!dryrun)
+              D2[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b),
+                    triplesx, t2sub, v2sub);
+          }
+      }
+    }
+  }
+  free(t2sub); free(v2sub);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* One tuple: ccsd_t.F:358-456 (ccsd_t_loop)                                             */
+/* ------------------------------------------------------------------------------------ */
+void ora_ccsd_t_loop(const ora_ctx *c, const Integer *tuple /* p4b,p5b,p6b,h1b,h2b,h3b */, double *a_singles,
+                     double *a_doubles, double *energy /*[2], accumulated*/, ora_counts *cnt) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2];
+  const Integer t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  const Integer size = RANGE(t_p4b) * RANGE(t_p5b) * RANGE(t_p6b) * RANGE(t_h1b) * RANGE(t_h2b) * RANGE(t_h3b);
+  memset(a_singles, 0, sizeof(double) * (size_t)size); /* :421 */
+  memset(a_doubles, 0, sizeof(double) * (size_t)size); /* :422 */
+  ora_ccsd_t_singles_l(c, a_singles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, cnt); /* :435 */
+  ora_ccsd_t_doubles_l(c, a_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, cnt); /* :443 */
+  ora_ccsd_t_dot(a_singles, a_doubles, (int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b,
+                 c->evl_sorted + c->offset[t_h1b - 1], c->evl_sorted + c->offset[t_h2b - 1],
+                 c->evl_sorted + c->offset[t_h3b - 1], c->evl_sorted + c->offset[t_p4b - 1],
+                 c->evl_sorted + c->offset[t_p5b - 1], c->evl_sorted + c->offset[t_p6b - 1], RANGE(t_h1b),
+                 RANGE(t_h2b), RANGE(t_h3b), RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), &energy[0],
+                 &energy[1]); /* :447 */
+}
+
+/* dry run of one tuple: call and flop counts only (SURVEY 8d "algorithmic FLOPs") */
+void ora_ccsd_t_count(const ora_ctx *c, const Integer *tuple, ora_counts *cnt) {
+  ora_ccsd_t_singles_l(c, NULL, tuple[3], tuple[4], tuple[5], tuple[0], tuple[1], tuple[2], 1, cnt);
+  ora_ccsd_t_doubles_l(c, NULL, tuple[3], tuple[4], tuple[5], tuple[0], tuple[1], tuple[2], 1, cnt);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Task list: ccsd_t_neword.F:1-40 (ccsd_t_6tasks), :42-217 (ccsd_t_neword), :218 (sillysort) */
+/* ------------------------------------------------------------------------------------ */
+static int tuple_allowed(int restricted, const Integer *kspin, const Integer *ksym, Integer p4, Integer p5,
+                         Integer p6, Integer h1, Integer h2, Integer h3) {
+#define KS(b) kspin[(b) - 1]
+#define KY(b) ksym[(b) - 1]
+  if (KS(p4) + KS(p5) + KS(p6) != KS(h1) + KS(h2) + KS(h3)) return 0;
+  if (restricted && KS(p4) + KS(p5) + KS(p6) + KS(h1) + KS(h2) + KS(h3) > 8) return 0;
+  if ((KY(p4) ^ KY(p5) ^ KY(p6) ^ KY(h1) ^ KY(h2) ^ KY(h3)) != 0) return 0;
+  return 1;
+}
+
+Integer ora_ccsd_t_6tasks(Integer restricted, Integer noab, Integer nvab, const Integer *kspin,
+                          const Integer *ksym) {
+  Integer n = 0;
+  for (Integer p4 = noab + 1; p4 <= noab + nvab; p4++)
+    for (Integer p5 = p4; p5 <= noab + nvab; p5++)
+      for (Integer p6 = p5; p6 <= noab + nvab; p6++)
+        for (Integer h1 = 1; h1 <= noab; h1++)
+          for (Integer h2 = h1; h2 <= noab; h2++)
+            for (Integer h3 = h2; h3 <= noab; h3++)
+              if (tuple_allowed((int)restricted, kspin, ksym, p4, p5, p6, h1, h2, h3)) n++;
+  return n;
+}
+
+static void sillysort(Integer value, Integer *kaux, Integer *klist, Integer n, Integer *found) {
+  for (Integer m = 0; m < n; m++)
+    if (kaux[7 * m + 6] > value) {
+      for (int j = 0; j < 7; j++) klist[7 * (*found) + j] = kaux[7 * m + j];
+      (*found)++;
+      kaux[7 * m + 6] = -99;
+    }
+}
+
+/* klist(7,tot_task): 6 tile ids (p4b,p5b,p6b,h1b,h2b,h3b) + weight, heaviest first in 16 bands */
+void ora_ccsd_t_neword(Integer tot_task, Integer restricted, Integer noab, Integer nvab, const Integer *kspin,
+                       const Integer *ksym, const Integer *krange, Integer *klist) {
+  Integer *kaux = (Integer *)malloc(sizeof(Integer) * 7 * (size_t)(tot_task + 1));
+  Integer m = 0;
+  for (Integer p4 = noab + 1; p4 <= noab + nvab; p4++)
+    for (Integer p5 = p4; p5 <= noab + nvab; p5++)
+      for (Integer p6 = p5; p6 <= noab + nvab; p6++)
+        for (Integer h1 = 1; h1 <= noab; h1++)
+          for (Integer h2 = h1; h2 <= noab; h2++)
+            for (Integer h3 = h2; h3 <= noab; h3++)
+              if (tuple_allowed((int)restricted, kspin, ksym, p4, p5, p6, h1, h2, h3)) {
+                Integer *r = kaux + 7 * m;
+                r[0] = p4; r[1] = p5; r[2] = p6; r[3] = h1; r[4] = h2; r[5] = h3;
+                r[6] = krange[p4 - 1] * krange[p5 - 1] * krange[p6 - 1] * krange[h1 - 1] * krange[h2 - 1] *
+                       krange[h3 - 1];
+                m++;
+              }
+  Integer wl_max = 0, wl_min;
+  for (Integer i = 0; i < tot_task; i++) if (kaux[7 * i + 6] > wl_max) wl_max = kaux[7 * i + 6];
+  wl_min = wl_max;
+  for (Integer i = 0; i < tot_task; i++) if (kaux[7 * i + 6] < wl_min) wl_min = kaux[7 * i + 6];
+  if (tot_task == 0 || ((wl_max - wl_min) * 100.0) / wl_max < 1.0) { /* :136-143 */
+    memcpy(klist, kaux, sizeof(Integer) * 7 * (size_t)tot_task);
+    free(kaux);
+    return;
+  }
+  Integer found = 0;
+  const Integer nsplits = 16;
+  for (Integer ii = nsplits; ii >= 1; ii--) { /* :168-173 */
+    Integer w_in = wl_min + ((wl_max - wl_min) * (ii - 1)) / nsplits;
+    sillysort(w_in, kaux, klist, tot_task, &found);
+  }
+  sillysort(0, kaux, klist, tot_task, &found); /* :174 */
+  free(kaux);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Whole (T): ccsd_t.F:19-310 on one rank (the nxtask0 counter and ga_dgop are identity) */
+/* per_task (optional): 2*tot_task doubles receiving each tuple's (E1,E2)                */
+/* ------------------------------------------------------------------------------------ */
+Integer ora_ccsd_t(const ora_ctx *c, double *energy /*[2]*/, Integer *klist_out /*7*tot_task or NULL*/,
+                   double *per_task /*or NULL*/, ora_counts *cnt /*or NULL*/) {
+  const Integer tot = ora_ccsd_t_6tasks(c->restricted, c->noab, c->nvab, c->spin, c->sym);
+  Integer *klist = (Integer *)malloc(sizeof(Integer) * 7 * (size_t)(tot + 1));
+  ora_ccsd_t_neword(tot, c->restricted, c->noab, c->nvab, c->spin, c->sym, c->range, klist);
+  Integer range_p4 = 0, range_h1 = 0; /* ccsd_t.F:99-111 */
+  for (Integer b = c->noab + 1; b <= c->noab + c->nvab; b++) if (RANGE(b) > range_p4) range_p4 = RANGE(b);
+  for (Integer b = 1; b <= c->noab; b++) if (RANGE(b) > range_h1) range_h1 = RANGE(b);
+  const size_t size = (size_t)range_p4 * range_p4 * range_p4 * range_h1 * range_h1 * range_h1;
+  double *a_singles = (double *)malloc(sizeof(double) * (size + 8));
+  double *a_doubles = (double *)malloc(sizeof(double) * (size + 8));
+  energy[0] = energy[1] = 0.0;
+  for (Integer k = 0; k < tot; k++) {
+    double e[2] = {0.0, 0.0};
+    ora_ccsd_t_loop(c, klist + 7 * k, a_singles, a_doubles, e, cnt);
+    if (per_task) { per_task[2 * k] = e[0]; per_task[2 * k + 1] = e[1]; }
+    energy[0] += e[0];
+    energy[1] += e[1];
+  }
+  if (klist_out) memcpy(klist_out, klist, sizeof(Integer) * 7 * (size_t)tot);
+  free(a_singles); free(a_doubles); free(klist);
+  return tot;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Tiling: tce_tile.F:330-357 (one spin/irrep orbital group of n orbitals -> tile sizes) */
+/* returns the number of tiles, writes ranges[]                                          */
+/* ------------------------------------------------------------------------------------ */
+Integer ora_tce_tile_group(Integer n, Integer isize, Integer *ranges) {
+  if (n <= 0) return 0;
+  Integer nblocks = n / isize;
+  if (n > isize * nblocks) nblocks++;
+  Integer l = 0;
+  for (Integer k = 1; k <= nblocks; k++) {
+    ranges[k - 1] = k * n / nblocks - l;
+    l += ranges[k - 1];
+  }
+  return nblocks;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Second formulation (independent cross-check): ccsd_t_doubles.F:195-267                 */
+/* sort -> DGEMM('T','N') -> tce_sortacc_6, for ONE (row, p7b) pair of the Sum(p7) family */
+/* c_sort(dima_sort,dimb_sort) = a_sort(k,ia)^T b_sort(k,ib); then scattered with the     */
+/* permutation/sign of kernel K.  Used only by tests/test_oracle.py.                      */
+/* ------------------------------------------------------------------------------------ */
+void ora_tce_sortacc_6(const double *unsorted, double *sorted, Integer a, Integer b, Integer c, Integer d,
+                       Integer e, Integer f, Integer i, Integer j, Integer k, Integer l, Integer m, Integer n,
+                       double factor) { /* src/tce/sort/new_sort6.F semantics (tce_sortacc_6) */
+  Integer jd[6] = {a, b, c, d, e, f}, id[6];
+  for (id[0] = 0; id[0] < a; id[0]++)
+    for (id[1] = 0; id[1] < b; id[1]++)
+      for (id[2] = 0; id[2] < c; id[2]++)
+        for (id[3] = 0; id[3] < d; id[3]++)
+          for (id[4] = 0; id[4] < e; id[4]++)
+            for (id[5] = 0; id[5] < f; id[5]++) {
+              Integer ia = id[5] + f * (id[4] + e * (id[3] + d * (id[2] + c * (id[1] + b * id[0]))));
+              Integer ib = id[n - 1] + jd[n - 1] * (id[m - 1] + jd[m - 1] * (id[l - 1] + jd[l - 1] *
+                           (id[k - 1] + jd[k - 1] * (id[j - 1] + jd[j - 1] * id[i - 1]))));
+              sorted[ib] += unsorted[ia] * factor;
+            }
+}
+
+void ora_dgemm_tn(Integer m, Integer n, Integer k, const double *a /*k x m*/, const double *b /*k x n*/,
+                  double *cmat /*m x n col-major, accumulated*/) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (Integer j = 0; j < n; j++)
+    for (Integer i = 0; i < m; i++) {
+      double s = 0.0;
+      for (Integer q = 0; q < k; q++) s += a[q + k * i] * b[q + k * j];
+      cmat[i + m * j] += s;
+    }
+}
+
+int ora_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
