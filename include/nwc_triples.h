@@ -1,0 +1,151 @@
+/*
+ * libnwc_triples -- B200-native (sm_100a) CCSD(T) perturbative-triples kernels behind NWChem TCE's
+ * Fortran->C call surface for src/tce/ccsd_t.  Plain C ABI: pointers and sizes only.
+ *
+ * Tier 1 ("compat"): the exact symbols the reference's GPU driver binds
+ *   (ccsd_t_gpu.F, ccsd_t_singles_gpu.F, ccsd_t_doubles_gpu.F -> sd_t_total.cu, memory.cu, hybrid.c).
+ *   Fortran calling convention: lower case, one trailing underscore, every argument by reference,
+ *   integers are 64-bit (`typedef long Integer`, header.h:51).
+ *   Semantics differ from the reference in one documented way: execution is DEFERRED.  Each sd_t_*_cuda_
+ *   call copies its host operands to the device (they may be freed by the caller on return, as in
+ *   ccsd_t_doubles_gpu.F:723-726) and records the contraction; compute_en_ then runs ONE fused kernel
+ *   over everything recorded for the tuple and returns the two energies.  The t3 tile is never
+ *   materialised, so the host `triplesx` arguments are ignored exactly as in the reference.
+ *   Errors: print + exit(1) (header.h:27-37).
+ *
+ * Tier 2 ("native"): resident block stores, task partitioning and multi-GPU reduction, for hosts
+ *   that keep T1/T2/V2 in HBM (replaces the Global Arrays gets of get_block.F:79-81, the nxtask
+ *   counter of util_gnxtval.c:31 and the ga_dgop of ccsd_t.F:297).  Functions return 0 on success,
+ *   nonzero on error with a message available from nwc_triples_last_error().
+ */
+#ifndef NWC_TRIPLES_H
+#define NWC_TRIPLES_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long Integer; /* src/tce/ccsd_t/header.h:51 */
+
+/* ------------------------------------------------------------------------------------------
+ * Tier 1: drop-in symbols
+ * ---------------------------------------------------------------------------------------- */
+/* hybrid.c:24 -- 1 if this rank drives a GPU (rank-on-node < *icuda) */
+int check_device_(Integer *icuda);
+/* hybrid.c:31 -- bind the rank to a device; writes 30 to *cuda_device_number if the node has fewer
+ * than *icuda devices (ccsd_t_gpu.F:58-60 turns that into errquit) */
+int device_init_(Integer *icuda, Integer *cuda_device_number);
+/* memory.cu:70 / :165 -- pool life cycle (per tuple, ccsd_t_gpu.F:135,220) */
+void initmemmodule_(void);
+void finalizememmodule_(void);
+/* sd_t_total.cu:5392 / :12 -- open the singles / doubles part of a tuple; dims are the TASK tuple's ranges */
+void dev_mem_s_(Integer *h1d, Integer *h2d, Integer *h3d, Integer *p4d, Integer *p5d, Integer *p6d);
+void dev_mem_d_(Integer *h1d, Integer *h2d, Integer *h3d, Integer *p4d, Integer *p5d, Integer *p6d);
+/* sd_t_total.cu:24 */
+void dev_release_(void);
+
+/* sd_t_total.cu:5522.. (s1), :312.. (d1), :2885.. (d2).  dims are the PERMUTED tuple's ranges.
+ * t1sub(p4,h1), t2sub(h7,p4,p5,h1) | t2sub(p7,p4,h1,h2), v2sub(h3,h2,p6,p5) | (h3,h2,p6,h7) | (p7,h3,p6,p5),
+ * all Fortran column-major host arrays. */
+#define NWC_DECL_S1(K)                                                                                   \
+  void sd_t_s1_##K##_cuda_(Integer *h1d, Integer *h2d, Integer *h3d, Integer *p4d, Integer *p5d, Integer *p6d, \
+                           double *triplesx_unused, double *t1sub, double *v2sub);
+#define NWC_DECL_D1(K)                                                                                   \
+  void sd_t_d1_##K##_cuda_(Integer *h1d, Integer *h2d, Integer *h3d, Integer *h7d, Integer *p4d, Integer *p5d, \
+                           Integer *p6d, double *triplesx_unused, double *t2sub, double *v2sub);
+#define NWC_DECL_D2(K)                                                                                   \
+  void sd_t_d2_##K##_cuda_(Integer *h1d, Integer *h2d, Integer *h3d, Integer *p4d, Integer *p5d, Integer *p6d, \
+                           Integer *p7d, double *triplesx_unused, double *t2sub, double *v2sub);
+NWC_DECL_S1(1) NWC_DECL_S1(2) NWC_DECL_S1(3) NWC_DECL_S1(4) NWC_DECL_S1(5) NWC_DECL_S1(6) NWC_DECL_S1(7) NWC_DECL_S1(8) NWC_DECL_S1(9)
+NWC_DECL_D1(1) NWC_DECL_D1(2) NWC_DECL_D1(3) NWC_DECL_D1(4) NWC_DECL_D1(5) NWC_DECL_D1(6) NWC_DECL_D1(7) NWC_DECL_D1(8) NWC_DECL_D1(9)
+NWC_DECL_D2(1) NWC_DECL_D2(2) NWC_DECL_D2(3) NWC_DECL_D2(4) NWC_DECL_D2(5) NWC_DECL_D2(6) NWC_DECL_D2(7) NWC_DECL_D2(8) NWC_DECL_D2(9)
+
+/* sd_t_total.cu:5373 -- energy[0] = E[T] part, energy[1] = E(T) part of this tuple (ccsd_t_gpu.F:205-217) */
+void compute_en_(double *factor, double *energy, double *eval_h1, double *eval_h2, double *eval_h3, double *eval_p4,
+                 double *eval_p5, double *eval_p6, Integer *h1d, Integer *h2d, Integer *h3d, Integer *p4d,
+                 Integer *p5d, Integer *p6d, double *host_doubles_unused, double *host_singles_unused);
+
+/* not in the reference: tell the library this process's rank on its node when util_my_smp_index() is not linked */
+void nwc_triples_set_local_rank(Integer local_rank);
+/* validation aid: like compute_en_, but also writes the two t3 tiles T3(h3,h2,h1,p6,p5,p4) to host arrays */
+void nwc_compute_en_dump_(double *factor, double *energy, double *eval_h1, double *eval_h2, double *eval_h3,
+                          double *eval_p4, double *eval_p5, double *eval_p6, Integer *h1d, Integer *h2d, Integer *h3d,
+                          Integer *p4d, Integer *p5d, Integer *p6d, double *host_doubles, double *host_singles);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side driver (C++ restatement of the Fortran above the kernel boundary; stands in for
+ * ccsd_t_gpu.F + ccsd_t_singles_gpu.F + ccsd_t_doubles_gpu.F where no Fortran compiler exists).
+ * It fetches and sorts blocks on the HOST exactly like the reference and calls the Tier-1 symbols.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  Integer noab, nvab;      /* tce.fh:19-20 */
+  Integer restricted;      /* tce.fh:78   */
+  Integer irrep_t, irrep_v;
+  const Integer *spin;     /* k_spin   [noab+nvab], 1 alpha / 2 beta */
+  const Integer *sym;      /* k_sym    irrep bit code */
+  const Integer *range;    /* k_range */
+  const Integer *offset;   /* k_offset into evl_sorted */
+  const Integer *alpha;    /* k_alpha (1-based) */
+  const double *evl_sorted;
+  const Integer *t1_hash; const double *t1;  /* tce_t1_offset_new.F  : [n, keys.., offsets..] */
+  const Integer *t2_hash; const double *t2;  /* tce_t2_offset_new.F */
+  const Integer *v2_hash; const double *v2;  /* tce_mo2e_offset.F   */
+} nwc_tce_state;
+
+/* ccsd_t_gpu.F:2 -- whole (T) through the Tier-1 call surface on this rank; tasks dealt round-robin
+ * as `my_rank`-th of `nranks` (nranks=1: all).  energy[0]=E[T], energy[1]=E(T), unreduced. */
+int nwc_ccsd_t_gpu(const nwc_tce_state *st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
+                   double *per_task /* 2*ntasks or NULL */);
+/* one tuple through the Tier-1 surface; optional t3 tiles out (host, T3(h3,h2,h1,p6,p5,p4)) */
+int nwc_ccsd_t_gpu_tuple(const nwc_tce_state *st, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
+                         double *host_doubles, double *host_singles);
+
+/* host-only helpers (no device): task list of ccsd_t_neword.F and a dry run of one tuple's dispatch */
+Integer nwc_host_task_list(const nwc_tce_state *st, Integer *klist7, Integer capacity_tasks);
+int nwc_host_count_tuple(const nwc_tce_state *st, const Integer tuple_p4p5p6h1h2h3[6], Integer calls_s1_d1_d2[3],
+                         double flops_s1_d1_d2[3]);
+
+/* ------------------------------------------------------------------------------------------
+ * Tier 2: native API
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nwc_triples_ctx nwc_triples_ctx;
+
+typedef struct {
+  double fused_ms, repack_ms;          /* CUDA-event kernel time accumulated while timing is on */
+  long long fused_launches, repack_launches, reduce_launches;
+  long long work_items, descs, tuples;
+  double flops;                        /* algorithmic FLOPs of the tuples run */
+  double h2d_bytes, d2h_bytes;
+  double resident_bytes;               /* T1+T2+V2 in HBM */
+} nwc_triples_stats;
+
+const char *nwc_triples_last_error(void);
+int nwc_triples_create(nwc_triples_ctx **out, int device);
+int nwc_triples_destroy(nwc_triples_ctx *ctx);
+/* copies the tiling tables and uploads the three block stores into HBM (replicated per GPU) */
+int nwc_triples_set_state(nwc_triples_ctx *ctx, const nwc_tce_state *st);
+/* task list of ccsd_t_neword.F (7 Integers per task: p4b,p5b,p6b,h1b,h2b,h3b,weight), heaviest first */
+Integer nwc_triples_num_tasks(nwc_triples_ctx *ctx);
+int nwc_triples_task_list(nwc_triples_ctx *ctx, Integer *klist7);
+/* static partition replacing nxtask: tasks first, first+stride, ... (< ntasks).  energy[2] accumulates
+ * nothing across calls: it is set to this call's sums.  per_task: 2 doubles per task run, or NULL. */
+int nwc_triples_run(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
+                    double *per_task);
+/* one tuple, optionally materialising the t3 tiles (validation only) */
+int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
+                          double *host_doubles, double *host_singles);
+int nwc_triples_set_timing(nwc_triples_ctx *ctx, int on);
+int nwc_triples_get_stats(nwc_triples_ctx *ctx, nwc_triples_stats *out, int reset);
+/* panel arena budget per batch in bytes (default 8 GiB) */
+int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
+
+/* multi-GPU: one process per GPU.  The host distributes the 128-byte id (MPI/GA broadcast in NWChem,
+ * torch.distributed in bench.py), then every rank calls init; allreduce replaces ga_dgop (ccsd_t.F:297). */
+int nwc_triples_nccl_unique_id(char id128[128]);
+int nwc_triples_nccl_init(nwc_triples_ctx *ctx, const char id128[128], int rank, int nranks);
+int nwc_triples_allreduce_energy(nwc_triples_ctx *ctx, double energy[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

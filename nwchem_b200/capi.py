@@ -1,0 +1,261 @@
+"""ctypes binding of nwchem_b200/lib/libnwc_triples.so (include/nwc_triples.h).
+
+The library is the product; this module only marshals numpy arrays into its C ABI.  There is no CPU
+fallback: if the shared library is missing the import of this module raises.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libnwc_triples.so")
+L = C.c_long
+PL = C.POINTER(C.c_long)
+PD = C.POINTER(C.c_double)
+
+
+class TceState(C.Structure):  # nwc_tce_state
+    _fields_ = [("noab", L), ("nvab", L), ("restricted", L), ("irrep_t", L), ("irrep_v", L),
+                ("spin", PL), ("sym", PL), ("range", PL), ("offset", PL), ("alpha", PL), ("evl_sorted", PD),
+                ("t1_hash", PL), ("t1", PD), ("t2_hash", PL), ("t2", PD), ("v2_hash", PL), ("v2", PD)]
+
+
+class Stats(C.Structure):  # nwc_triples_stats
+    _fields_ = [("fused_ms", C.c_double), ("repack_ms", C.c_double), ("fused_launches", C.c_longlong),
+                ("repack_launches", C.c_longlong), ("reduce_launches", C.c_longlong), ("work_items", C.c_longlong),
+                ("descs", C.c_longlong), ("tuples", C.c_longlong), ("flops", C.c_double), ("h2d_bytes", C.c_double),
+                ("d2h_bytes", C.c_double), ("resident_bytes", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C nwchem_b200/csrc` "
+                               "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.nwc_triples_last_error.restype = C.c_char_p
+        _lib.nwc_triples_num_tasks.restype = L
+        _lib.nwc_triples_num_tasks.argtypes = [C.c_void_p]
+        _lib.nwc_triples_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        _lib.nwc_triples_destroy.argtypes = [C.c_void_p]
+        _lib.nwc_triples_set_state.argtypes = [C.c_void_p, C.POINTER(TceState)]
+        _lib.nwc_triples_task_list.argtypes = [C.c_void_p, PL]
+        _lib.nwc_triples_run.argtypes = [C.c_void_p, L, L, L, PD, PD]
+        _lib.nwc_triples_run_tuple.argtypes = [C.c_void_p, PL, PD, PD, PD]
+        _lib.nwc_triples_set_timing.argtypes = [C.c_void_p, C.c_int]
+        _lib.nwc_triples_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
+        _lib.nwc_triples_set_batch_bytes.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.nwc_triples_nccl_unique_id.argtypes = [C.c_char_p]
+        _lib.nwc_triples_nccl_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        _lib.nwc_triples_allreduce_energy.argtypes = [C.c_void_p, PD]
+        _lib.nwc_ccsd_t_gpu.argtypes = [C.POINTER(TceState), L, L, L, PD, PD]
+        _lib.nwc_ccsd_t_gpu_tuple.argtypes = [C.POINTER(TceState), PL, PD, PD, PD]
+    return _lib
+
+
+def _pl(a):
+    return a.ctypes.data_as(PL)
+
+
+def _pd(a):
+    return a.ctypes.data_as(PD)
+
+
+def make_state(st):
+    """BlockStores -> (nwc_tce_state, keepalive dict of the contiguous arrays it points into)."""
+    t = st.t
+    k = dict(spin=np.ascontiguousarray(t.spin, np.int64), sym=np.ascontiguousarray(t.sym, np.int64),
+             range=np.ascontiguousarray(t.range, np.int64), offset=np.ascontiguousarray(t.offset, np.int64),
+             alpha=np.ascontiguousarray(t.alpha, np.int64), evl=np.ascontiguousarray(t.evl_sorted, np.float64),
+             t1h=np.ascontiguousarray(st.t1_hash, np.int64), t1=np.ascontiguousarray(st.t1, np.float64),
+             t2h=np.ascontiguousarray(st.t2_hash, np.int64), t2=np.ascontiguousarray(st.t2, np.float64),
+             v2h=np.ascontiguousarray(st.v2_hash, np.int64), v2=np.ascontiguousarray(st.v2, np.float64))
+    s = TceState(t.noab, t.nvab, int(t.restricted), 0, 0, _pl(k["spin"]), _pl(k["sym"]), _pl(k["range"]),
+                 _pl(k["offset"]), _pl(k["alpha"]), _pd(k["evl"]), _pl(k["t1h"]), _pd(k["t1"]), _pl(k["t2h"]),
+                 _pd(k["t2"]), _pl(k["v2h"]), _pd(k["v2"]))
+    return s, k
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().nwc_triples_last_error().decode()}")
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier 1 through the host driver (mirrors ccsd_t_gpu.F)
+# ------------------------------------------------------------------------------------------------
+def ccsd_t_gpu(st, icuda=1, my_rank=0, nranks=1, ntasks=None):
+    """Whole (T) through the reference call surface (host block stores, per-call H2D copies).
+    Returns (E[T], E(T), per_task[ntasks,2])."""
+    s, keep = make_state(st)
+    e = np.zeros(2)
+    pt = np.zeros((max(ntasks or 0, 1), 2)) if ntasks else None
+    rc = lib().nwc_ccsd_t_gpu(C.byref(s), icuda, my_rank, nranks, _pd(e), _pd(pt) if pt is not None else None)
+    _check(rc, "nwc_ccsd_t_gpu")
+    return float(e[0]), float(e[1]), pt
+
+
+def ccsd_t_gpu_tuple(st, tup, dump=False):
+    """One tuple (p4b,p5b,p6b,h1b,h2b,h3b) through Tier 1; with dump=True also returns the singles and
+    doubles t3 tiles as arrays indexed [p4,p5,p6,h1,h2,h3]."""
+    s, keep = make_state(st)
+    tt = np.array(tup, np.int64)
+    e = np.zeros(2)
+    if dump:
+        dims = [st.t.r(int(b)) for b in tup]
+        d = np.zeros(int(np.prod(dims))); sg = np.zeros_like(d)
+        _check(lib().nwc_ccsd_t_gpu_tuple(C.byref(s), _pl(tt), _pd(e), _pd(d), _pd(sg)), "nwc_ccsd_t_gpu_tuple")
+        return float(e[0]), float(e[1]), sg.reshape(dims), d.reshape(dims)
+    _check(lib().nwc_ccsd_t_gpu_tuple(C.byref(s), _pl(tt), _pd(e), None, None), "nwc_ccsd_t_gpu_tuple")
+    return float(e[0]), float(e[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier 2
+# ------------------------------------------------------------------------------------------------
+class Triples:
+    """Native tier: block stores resident in HBM; static task partition; optional NCCL reduction."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().nwc_triples_create(C.byref(self._h), device), "nwc_triples_create")
+        self.t = None
+
+    def close(self):
+        if self._h:
+            lib().nwc_triples_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, st):
+        s, keep = make_state(st)
+        _check(lib().nwc_triples_set_state(self._h, C.byref(s)), "nwc_triples_set_state")
+        self.t = st.t
+
+    @property
+    def num_tasks(self) -> int:
+        return int(lib().nwc_triples_num_tasks(self._h))
+
+    def task_list(self):
+        n = self.num_tasks
+        kl = np.zeros((max(n, 1), 7), np.int64)
+        lib().nwc_triples_task_list(self._h, _pl(kl))
+        return kl[:n]
+
+    def run(self, first=0, stride=1, max_tasks=0, per_task=False):
+        e = np.zeros(2)
+        n = self.num_tasks
+        cnt = len(range(first, n, stride))
+        if max_tasks and max_tasks > 0:
+            cnt = min(cnt, max_tasks)
+        pt = np.zeros((max(cnt, 1), 2)) if per_task else None
+        _check(lib().nwc_triples_run(self._h, first, stride, max_tasks, _pd(e), _pd(pt) if per_task else None),
+               "nwc_triples_run")
+        return (float(e[0]), float(e[1]), pt[:cnt]) if per_task else (float(e[0]), float(e[1]))
+
+    def run_tuple(self, tup, dump=False):
+        tt = np.array(tup, np.int64)
+        e = np.zeros(2)
+        if dump:
+            dims = [self.t.r(int(b)) for b in tup]
+            d = np.zeros(int(np.prod(dims))); sg = np.zeros_like(d)
+            _check(lib().nwc_triples_run_tuple(self._h, _pl(tt), _pd(e), _pd(d), _pd(sg)), "nwc_triples_run_tuple")
+            return float(e[0]), float(e[1]), sg.reshape(dims), d.reshape(dims)
+        _check(lib().nwc_triples_run_tuple(self._h, _pl(tt), _pd(e), None, None), "nwc_triples_run_tuple")
+        return float(e[0]), float(e[1])
+
+    def set_timing(self, on=True):
+        lib().nwc_triples_set_timing(self._h, int(on))
+
+    def set_batch_bytes(self, n):
+        lib().nwc_triples_set_batch_bytes(self._h, int(n))
+
+    def stats(self, reset=False) -> dict:
+        s = Stats()
+        lib().nwc_triples_get_stats(self._h, C.byref(s), int(reset))
+        return s.asdict()
+
+    # multi-GPU (one process per GPU)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().nwc_triples_nccl_unique_id(buf), "nwc_triples_nccl_unique_id")
+        return buf.raw
+
+    def nccl_init(self, uid: bytes, rank: int, nranks: int):
+        _check(lib().nwc_triples_nccl_init(self._h, uid, rank, nranks), "nwc_triples_nccl_init")
+
+    def allreduce(self, e1, e2):
+        e = np.array([e1, e2], np.float64)
+        _check(lib().nwc_triples_allreduce_energy(self._h, _pd(e)), "nwc_triples_allreduce_energy")
+        return float(e[0]), float(e[1])
+
+
+# raw Tier-1 entry points for kernel-level tests (by-reference Fortran convention)
+def tier1_single_call(family, k, dims_task, dims_perm, kd, tsub, v2sub, eps, factor):
+    """Open a tuple with the TASK ranges dims_task=(h1d,h2d,h3d,p4d,p5d,p6d), issue ONE sd_t_{s1,d1,d2}_k_cuda_
+    call with the PERMUTED ranges dims_perm (same order), then nwc_compute_en_dump_.
+    Returns (e1, e2, singles_tile, doubles_tile) with tiles indexed [p4,p5,p6,h1,h2,h3]."""
+    l = lib()
+    ref = lambda v: C.byref(C.c_long(int(v)))
+    T = [C.c_long(int(x)) for x in dims_task]
+    P = [C.c_long(int(x)) for x in dims_perm]
+    K = C.c_long(int(kd))
+    l.initmemmodule_()
+    l.dev_mem_s_(*[C.byref(x) for x in T])
+    l.dev_mem_d_(*[C.byref(x) for x in T])
+    tsub = np.ascontiguousarray(tsub, np.float64); v2sub = np.ascontiguousarray(v2sub, np.float64)
+    name = {0: "s1", 1: "d1", 2: "d2"}[family]
+    fn = getattr(l, f"sd_t_{name}_{k}_cuda_")
+    h1, h2, h3, p4, p5, p6 = [C.byref(x) for x in P]
+    if family == 0:
+        fn(h1, h2, h3, p4, p5, p6, None, _pd(tsub), _pd(v2sub))
+    elif family == 1:
+        fn(h1, h2, h3, C.byref(K), p4, p5, p6, None, _pd(tsub), _pd(v2sub))
+    else:
+        fn(h1, h2, h3, p4, p5, p6, C.byref(K), None, _pd(tsub), _pd(v2sub))
+    e = np.zeros(2)
+    h1d, h2d, h3d, p4d, p5d, p6d = [int(x) for x in dims_task]
+    n = h1d * h2d * h3d * p4d * p5d * p6d
+    d = np.zeros(n); s = np.zeros(n)
+    ev = [np.ascontiguousarray(x, np.float64) for x in eps]  # h1,h2,h3,p4,p5,p6
+    f = C.c_double(factor)
+    l.nwc_compute_en_dump_(C.byref(f), _pd(e), *[_pd(x) for x in ev], *[C.byref(x) for x in T], _pd(d), _pd(s))
+    l.dev_release_()
+    l.finalizememmodule_()
+    shp = (p4d, p5d, p6d, h1d, h2d, h3d)
+    return float(e[0]), float(e[1]), s.reshape(shp), d.reshape(shp)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-only helpers (no device needed)
+# ------------------------------------------------------------------------------------------------
+def host_task_list(st):
+    s, keep = make_state(st)
+    l = lib()
+    l.nwc_host_task_list.restype = L
+    n = int(l.nwc_host_task_list(C.byref(s), None, L(0)))
+    kl = np.zeros((max(n, 1), 7), np.int64)
+    l.nwc_host_task_list(C.byref(s), _pl(kl), L(n))
+    return kl[:n]
+
+
+def host_count_tuple(st, tup, state=None):
+    s, keep = state if state is not None else make_state(st)
+    calls = np.zeros(3, np.int64); flops = np.zeros(3)
+    tt = np.array(tup, np.int64)
+    lib().nwc_host_count_tuple(C.byref(s), _pl(tt), _pl(calls), _pd(flops))
+    return calls, flops

@@ -1,0 +1,222 @@
+// Tier 1: the reference's Fortran-callable symbols (sd_t_total.cu, memory.cu, hybrid.c), re-implemented
+// with deferred execution on top of the fused kernel.  See include/nwc_triples.h.
+#include "engine.h"
+#include "../../include/nwc_triples.h"
+#include <cstring>
+
+using namespace nwc;
+
+extern "C" int util_my_smp_index() __attribute__((weak));  // src/util/util_getppn.c:132 when linked into NWChem
+
+namespace {
+Engine* g_eng = nullptr;
+long g_local_rank = -1;
+int g_R[6];          // task tuple ranges, physical order
+bool g_have_R = false;
+
+long local_rank() {
+  if (g_local_rank >= 0) return g_local_rank;
+  if (util_my_smp_index) return util_my_smp_index();
+  static const char* vars[] = {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID",
+                               "MPI_LOCALRANKID"};
+  for (const char* v : vars) {
+    const char* s = getenv(v);
+    if (s && *s) return atol(s);
+  }
+  return 0;
+}
+
+Engine& eng() {
+  if (!g_eng) {
+    int count = 0;
+    NWC_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0) { printf("nwc_triples: no CUDA device (there is no CPU fallback)\n"); exit(1); }
+    g_eng = new Engine((int)(local_rank() % count));
+  }
+  return *g_eng;
+}
+
+void open_tuple(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d) {
+  int R[6];
+  R[POS_H3] = (int)*h3d; R[POS_H2] = (int)*h2d; R[POS_H1] = (int)*h1d;
+  R[POS_P6] = (int)*p6d; R[POS_P5] = (int)*p5d; R[POS_P4] = (int)*p4d;
+  Engine& e = eng();
+  if (e.tuple_open()) {
+    if (memcmp(R, g_R, sizeof(R)) != 0) { printf("nwc_triples: dev_mem_s/dev_mem_d disagree on the tuple ranges\n"); exit(1); }
+    return;
+  }
+  memcpy(g_R, R, sizeof(R));
+  g_have_R = true;
+  e.begin_tuple(R);
+}
+
+const double* to_device(const double* host, size_t n) {
+  Engine& e = eng();
+  double* d = (double*)e.arena().alloc(n * sizeof(double));
+  // pageable source: returns once the source has been staged, so the caller may free it (MA_POP_STACK)
+  NWC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, e.stream()));
+  e.stats.h2d_bytes += n * sizeof(double);
+  return d;
+}
+
+// the permuted ranges passed by the caller must be the task ranges seen through kernel K's permutation
+void check_dims(int family, int k0, const Integer dims_by_name[6]) {
+  for (int q = 0; q < 6; q++)
+    if ((int)dims_by_name[DECL[family][k0][q]] != g_R[q]) {
+      printf("nwc_triples: sd_t_%s_%d_cuda: permuted ranges do not match the tuple opened by dev_mem_*\n",
+             family == 0 ? "s1" : family == 1 ? "d1" : "d2", k0 + 1);
+      exit(1);
+    }
+}
+
+void s1(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, double* t1sub,
+        double* v2sub) {
+  if (!eng().tuple_open()) { printf("nwc_triples: sd_t_s1 before dev_mem_s\n"); exit(1); }
+  Integer d[6]; d[N_H1] = *h1d; d[N_H2] = *h2d; d[N_H3] = *h3d; d[N_P4] = *p4d; d[N_P5] = *p5d; d[N_P6] = *p6d;
+  check_dims(0, k0, d);
+  OperandView t, v;
+  t.base = to_device(t1sub, (size_t)(d[N_P4] * d[N_H1]));                       // t1sub(p4,h1)
+  t.stride[N_P4] = 1; t.stride[N_H1] = d[N_P4];
+  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * d[N_P5]));   // v2sub(h3,h2,p6,p5)
+  v.stride[N_H3] = 1; v.stride[N_H2] = d[N_H3]; v.stride[N_P6] = d[N_H3] * d[N_H2];
+  v.stride[N_P5] = d[N_H3] * d[N_H2] * d[N_P6];
+  eng().add_singles(k0, t, v);
+}
+
+void d1(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* h7d, Integer* p4d, Integer* p5d, Integer* p6d,
+        double* t2sub, double* v2sub) {
+  if (!eng().tuple_open()) { printf("nwc_triples: sd_t_d1 before dev_mem_d\n"); exit(1); }
+  Integer d[6]; d[N_H1] = *h1d; d[N_H2] = *h2d; d[N_H3] = *h3d; d[N_P4] = *p4d; d[N_P5] = *p5d; d[N_P6] = *p6d;
+  const Integer K = *h7d;
+  check_dims(1, k0, d);
+  OperandView t, v;
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_P5] * d[N_H1]));         // t2sub(h7,p4,p5,h1)
+  t.kstride = 1; t.stride[N_P4] = K; t.stride[N_P5] = K * d[N_P4]; t.stride[N_H1] = K * d[N_P4] * d[N_P5];
+  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * K));         // v2sub(h3,h2,p6,h7)
+  v.stride[N_H3] = 1; v.stride[N_H2] = d[N_H3]; v.stride[N_P6] = d[N_H3] * d[N_H2];
+  v.kstride = d[N_H3] * d[N_H2] * d[N_P6];
+  eng().add_contraction(1, k0, (int)K, t, v);
+}
+
+void d2(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, Integer* p7d,
+        double* t2sub, double* v2sub) {
+  if (!eng().tuple_open()) { printf("nwc_triples: sd_t_d2 before dev_mem_d\n"); exit(1); }
+  Integer d[6]; d[N_H1] = *h1d; d[N_H2] = *h2d; d[N_H3] = *h3d; d[N_P4] = *p4d; d[N_P5] = *p5d; d[N_P6] = *p6d;
+  const Integer K = *p7d;
+  check_dims(2, k0, d);
+  OperandView t, v;
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_H1] * d[N_H2]));         // t2sub(p7,p4,h1,h2)
+  t.kstride = 1; t.stride[N_P4] = K; t.stride[N_H1] = K * d[N_P4]; t.stride[N_H2] = K * d[N_P4] * d[N_H1];
+  v.base = to_device(v2sub, (size_t)(K * d[N_H3] * d[N_P6] * d[N_P5]));         // v2sub(p7,h3,p6,p5)
+  v.kstride = 1; v.stride[N_H3] = K; v.stride[N_P6] = K * d[N_H3]; v.stride[N_P5] = K * d[N_H3] * d[N_P6];
+  eng().add_contraction(2, k0, (int)K, t, v);
+}
+
+void finish(double* factor, double* energy, double* eval_h1, double* eval_h2, double* eval_h3, double* eval_p4,
+            double* eval_p5, double* eval_p6, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d,
+            Integer* p6d, double* dump_d, double* dump_s) {
+  Engine& e = eng();
+  if (!e.tuple_open()) open_tuple(h1d, h2d, h3d, p4d, p5d, p6d);  // a tuple with no contributions at all
+  const double* hv[6] = {eval_h1, eval_h2, eval_h3, eval_p4, eval_p5, eval_p6};
+  const Integer n[6] = {*h1d, *h2d, *h3d, *p4d, *p5d, *p6d};
+  const int want[6] = {g_R[POS_H1], g_R[POS_H2], g_R[POS_H3], g_R[POS_P4], g_R[POS_P5], g_R[POS_P6]};
+  const double* dv[6];
+  for (int i = 0; i < 6; i++) {
+    if ((int)n[i] != want[i]) { printf("nwc_triples: compute_en: ranges differ from dev_mem_*\n"); exit(1); }
+    dv[i] = to_device(hv[i], (size_t)n[i]);
+  }
+  e.end_tuple(dv, *factor);
+  double out[2] = {0, 0};
+  double *dd = nullptr, *ds = nullptr;
+  size_t sz = 1;
+  if (dump_d) {
+    for (int q = 0; q < 6; q++) sz *= (size_t)g_R[q];
+    dd = (double*)e.arena().alloc(sz * sizeof(double));
+    ds = (double*)e.arena().alloc(sz * sizeof(double));
+    NWC_CUDA(cudaMemsetAsync(dd, 0, sz * sizeof(double), e.stream()));
+    NWC_CUDA(cudaMemsetAsync(ds, 0, sz * sizeof(double), e.stream()));
+  }
+  e.run(out, dd, ds);
+  if (dump_d) {
+    NWC_CUDA(cudaMemcpy(dump_d, dd, sz * sizeof(double), cudaMemcpyDeviceToHost));
+    NWC_CUDA(cudaMemcpy(dump_s, ds, sz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  energy[0] = out[0];
+  energy[1] = out[1];
+}
+}  // namespace
+
+namespace nwc {
+Engine& compat_engine() { return eng(); }
+}
+
+extern "C" {
+
+void nwc_triples_set_local_rank(Integer r) { g_local_rank = r; }
+
+int check_device_(Integer* icuda) { return local_rank() < *icuda ? 1 : 0; }  // hybrid.c:24-28
+
+int device_init_(Integer* icuda, Integer* cuda_device_number) {  // hybrid.c:31-58
+  int count = 0;
+  cudaGetDeviceCount(&count);
+  if (count < *icuda) {
+    printf("Warning: Please check whether you have %ld cuda devices per node\n", *icuda);
+    fflush(stdout);
+    *cuda_device_number = 30;
+  } else {
+    eng();
+  }
+  return 1;
+}
+
+void initmemmodule_(void) { eng(); }
+void finalizememmodule_(void) {
+  if (g_eng && g_eng->tuple_open()) { printf("nwc_triples: finalizememmodule with an open tuple\n"); exit(1); }
+}
+void dev_mem_s_(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d) {
+  open_tuple(h1d, h2d, h3d, p4d, p5d, p6d);
+}
+void dev_mem_d_(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d) {
+  open_tuple(h1d, h2d, h3d, p4d, p5d, p6d);
+}
+void dev_release_(void) {
+  if (g_eng) {
+    NWC_CUDA(cudaStreamSynchronize(g_eng->stream()));
+    g_eng->arena().reset();
+  }
+}
+
+#define DEF_S1(K)                                                                                            \
+  void sd_t_s1_##K##_cuda_(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, \
+                           double*, double* t1sub, double* v2sub) {                                          \
+    s1(K - 1, h1d, h2d, h3d, p4d, p5d, p6d, t1sub, v2sub);                                                   \
+  }
+#define DEF_D1(K)                                                                                            \
+  void sd_t_d1_##K##_cuda_(Integer* h1d, Integer* h2d, Integer* h3d, Integer* h7d, Integer* p4d, Integer* p5d, \
+                           Integer* p6d, double*, double* t2sub, double* v2sub) {                            \
+    d1(K - 1, h1d, h2d, h3d, h7d, p4d, p5d, p6d, t2sub, v2sub);                                              \
+  }
+#define DEF_D2(K)                                                                                            \
+  void sd_t_d2_##K##_cuda_(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, \
+                           Integer* p7d, double*, double* t2sub, double* v2sub) {                            \
+    d2(K - 1, h1d, h2d, h3d, p4d, p5d, p6d, p7d, t2sub, v2sub);                                              \
+  }
+DEF_S1(1) DEF_S1(2) DEF_S1(3) DEF_S1(4) DEF_S1(5) DEF_S1(6) DEF_S1(7) DEF_S1(8) DEF_S1(9)
+DEF_D1(1) DEF_D1(2) DEF_D1(3) DEF_D1(4) DEF_D1(5) DEF_D1(6) DEF_D1(7) DEF_D1(8) DEF_D1(9)
+DEF_D2(1) DEF_D2(2) DEF_D2(3) DEF_D2(4) DEF_D2(5) DEF_D2(6) DEF_D2(7) DEF_D2(8) DEF_D2(9)
+
+void compute_en_(double* factor, double* energy, double* eval_h1, double* eval_h2, double* eval_h3, double* eval_p4,
+                 double* eval_p5, double* eval_p6, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d,
+                 Integer* p5d, Integer* p6d, double*, double*) {
+  finish(factor, energy, eval_h1, eval_h2, eval_h3, eval_p4, eval_p5, eval_p6, h1d, h2d, h3d, p4d, p5d, p6d, nullptr,
+         nullptr);
+}
+
+void nwc_compute_en_dump_(double* factor, double* energy, double* eval_h1, double* eval_h2, double* eval_h3,
+                          double* eval_p4, double* eval_p5, double* eval_p6, Integer* h1d, Integer* h2d, Integer* h3d,
+                          Integer* p4d, Integer* p5d, Integer* p6d, double* host_doubles, double* host_singles) {
+  finish(factor, energy, eval_h1, eval_h2, eval_h3, eval_p4, eval_p5, eval_p6, h1d, h2d, h3d, p4d, p5d, p6d,
+         host_doubles, host_singles);
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Host driver above the kernel boundary: a C++ restatement of ccsd_t_gpu.F (task loop, :87-241),
+// ccsd_t_singles_gpu.F and ccsd_t_doubles_gpu.F that calls the Tier-1 symbols exactly as the Fortran does:
+// blocks are fetched from the (host) block stores, sorted on the host with TCE_SORT_2/4 semantics and passed
+// as host arrays.  It stands in for the Fortran in this image (no Fortran compiler); INTEGRATION.md shows
+// the ISO_C_BINDING module the real driver uses instead.
+#include "host_driver.h"
+#include "engine.h"
+#include <cstring>
+
+using namespace nwc;
+
+namespace {
+
+// sorted(i,j,k,l order, l fastest) = factor * unsorted(a,b,c,d order, d fastest): tce_sort_4 semantics
+void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integer d, int i, int j, int k, int l,
+           double factor) {
+  const Integer jd[4] = {a, b, c, d};
+  const int perm[4] = {i - 1, j - 1, k - 1, l - 1};
+  Integer ostride[4];  // stride in `out` of input index q
+  Integer s = 1;
+  for (int q = 3; q >= 0; q--) { ostride[perm[q]] = s; s *= jd[perm[q]]; }
+  Integer id[4];
+  for (id[0] = 0; id[0] < a; id[0]++)
+    for (id[1] = 0; id[1] < b; id[1]++)
+      for (id[2] = 0; id[2] < c; id[2]++) {
+        const double* src = in + d * (id[2] + c * (id[1] + b * id[0]));
+        double* dst = out + id[0] * ostride[0] + id[1] * ostride[1] + id[2] * ostride[2];
+        for (Integer x = 0; x < d; x++) dst[x * ostride[3]] = factor * src[x];
+      }
+}
+
+struct CompatSink {
+  const HostState& S;
+  const nwc_tce_state* st;
+  std::vector<double> a_sort, b_sort;
+
+  void singles(const Row& r, Integer p4b_1, Integer h1b_1, Integer p5b_2, Integer p6b_2, Integer h2b_2, Integer h3b_2,
+               const bool fire[9]) {
+    const Integer rp4 = S.rg(r.p4b), rh1 = S.rg(r.h1b);
+    const double* blk = st->t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
+    a_sort.resize((size_t)(rp4 * rh1));
+    for (Integer p = 0; p < rp4; p++)      // TCE_SORT_2(...,2,1): stored (p4,h1) h1 fastest -> t1sub(p4,h1)
+      for (Integer h = 0; h < rh1; h++) a_sort[p + rp4 * h] = blk[h + rh1 * p];
+    const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
+    Integer h1d = rh1, h2d = S.rg(r.h2b), h3d = S.rg(r.h3b), p4d = rp4, p5d = S.rg(r.p5b), p6d = S.rg(r.p6b);
+    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
+    static const fn F[9] = {sd_t_s1_1_cuda_, sd_t_s1_2_cuda_, sd_t_s1_3_cuda_, sd_t_s1_4_cuda_, sd_t_s1_5_cuda_,
+                            sd_t_s1_6_cuda_, sd_t_s1_7_cuda_, sd_t_s1_8_cuda_, sd_t_s1_9_cuda_};
+    for (int k = 0; k < 9; k++)
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, nullptr, a_sort.data(), const_cast<double*>(v));
+  }
+
+  void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
+    const Integer rp4 = S.rg(r.p4b), rp5 = S.rg(r.p5b), rh1 = S.rg(r.h1b), rh7 = S.rg(h7b);
+    a_sort.resize((size_t)(rp4 * rp5 * rh1 * rh7));
+    if (h7b < r.h1b) {  // ccsd_t_doubles_gpu.F:282-289
+      const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[3], am[2]), "t2");
+      sort4(blk, a_sort.data(), rp4, rp5, rh7, rh1, 4, 2, 1, 3, -1.0);
+    } else {            // :291-298
+      const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
+      sort4(blk, a_sort.data(), rp4, rp5, rh1, rh7, 3, 2, 1, 4, 1.0);
+    }
+    const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");  // :315-327
+    Integer h1d = rh1, h2d = S.rg(r.h2b), h3d = S.rg(r.h3b), h7d = rh7, p4d = rp4, p5d = rp5, p6d = S.rg(r.p6b);
+    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
+    static const fn F[9] = {sd_t_d1_1_cuda_, sd_t_d1_2_cuda_, sd_t_d1_3_cuda_, sd_t_d1_4_cuda_, sd_t_d1_5_cuda_,
+                            sd_t_d1_6_cuda_, sd_t_d1_7_cuda_, sd_t_d1_8_cuda_, sd_t_d1_9_cuda_};
+    for (int k = 0; k < 9; k++)
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &h7d, &p4d, &p5d, &p6d, nullptr, a_sort.data(), const_cast<double*>(v));
+  }
+
+  void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
+    const Integer rp4 = S.rg(r.p4b), rp7 = S.rg(p7b), rh1 = S.rg(r.h1b), rh2 = S.rg(r.h2b);
+    a_sort.resize((size_t)(rp4 * rp7 * rh1 * rh2));
+    if (p7b < r.p4b) {  // ccsd_t_doubles_gpu.F:942-949
+      const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[1], am[0], am[2], am[3]), "t2");
+      sort4(blk, a_sort.data(), rp7, rp4, rh1, rh2, 4, 3, 2, 1, -1.0);
+    } else {            // :950-957
+      const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
+      sort4(blk, a_sort.data(), rp4, rp7, rh1, rh2, 4, 3, 1, 2, 1.0);
+    }
+    const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");  // :964-976
+    Integer h1d = rh1, h2d = rh2, h3d = S.rg(r.h3b), p4d = rp4, p5d = S.rg(r.p5b), p6d = S.rg(r.p6b), p7d = rp7;
+    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
+    static const fn F[9] = {sd_t_d2_1_cuda_, sd_t_d2_2_cuda_, sd_t_d2_3_cuda_, sd_t_d2_4_cuda_, sd_t_d2_5_cuda_,
+                            sd_t_d2_6_cuda_, sd_t_d2_7_cuda_, sd_t_d2_8_cuda_, sd_t_d2_9_cuda_};
+    for (int k = 0; k < 9; k++)
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort.data(), const_cast<double*>(v));
+  }
+};
+
+// one task: ccsd_t_gpu.F:114-230
+void one_tuple(const HostState& S, const nwc_tce_state* st, const Integer t[6], double e[2], double* dump_d,
+               double* dump_s) {
+  Integer rp4 = S.rg(t[0]), rp5 = S.rg(t[1]), rp6 = S.rg(t[2]), rh1 = S.rg(t[3]), rh2 = S.rg(t[4]), rh3 = S.rg(t[5]);
+  initmemmodule_();                                   // :135
+  CompatSink sink{S, st, {}, {}};
+  dev_mem_s_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_singles_gpu.F:192-197
+  walk_singles(S, t, sink);                           // :139
+  dev_mem_d_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_doubles_gpu.F:227-232
+  walk_doubles(S, t, sink);                           // :144
+  double factor = tuple_factor(S, t);                 // :153-167
+  double* ev = const_cast<double*>(st->evl_sorted);
+  if (dump_d)
+    nwc_compute_en_dump_(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
+                         ev + S.offset[t[0] - 1], ev + S.offset[t[1] - 1], ev + S.offset[t[2] - 1], &rh1, &rh2, &rh3,
+                         &rp4, &rp5, &rp6, dump_d, dump_s);
+  else
+    compute_en_(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
+                ev + S.offset[t[0] - 1], ev + S.offset[t[1] - 1], ev + S.offset[t[2] - 1], &rh1, &rh2, &rh3, &rp4,
+                &rp5, &rp6, nullptr, nullptr);            // :205-215
+  dev_release_();                                     // :219
+  finalizememmodule_();                               // :220
+}
+
+}  // namespace
+
+extern "C" {
+
+int nwc_ccsd_t_gpu(const nwc_tce_state* st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
+                   double* per_task) {
+  HostState S;
+  S.load_tables(st);
+  Integer ic = icuda, devno = 0;
+  if (check_device_(&ic) != 1) { printf("nwc_ccsd_t_gpu: this rank owns no GPU and there is no CPU path\n"); return 2; }
+  device_init_(&ic, &devno);                          // ccsd_t_gpu.F:55-57
+  if (devno == 30) return 30;                         // :58-60
+  // same loop nest and filters as ccsd_t_gpu.F:87-112; the nxtask counter is replaced by a static deal
+  energy[0] = energy[1] = 0.0;
+  Integer count = 0;
+  const Integer n0 = S.noab, n1 = S.noab + S.nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              const Integer ps = S.sp(p4) + S.sp(p5) + S.sp(p6), hs = S.sp(h1) + S.sp(h2) + S.sp(h3);
+              if (ps != hs) continue;
+              if (S.restricted && ps + hs > 8) continue;
+              if ((S.sy(p4) ^ S.sy(p5) ^ S.sy(p6) ^ S.sy(h1) ^ S.sy(h2) ^ S.sy(h3)) != 0) continue;
+              if (count % nranks == my_rank) {
+                const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+                double e[2] = {0, 0};
+                one_tuple(S, st, t, e, nullptr, nullptr);
+                energy[0] += e[0];                    // :216-217
+                energy[1] += e[1];
+                if (per_task) { per_task[2 * count] = e[0]; per_task[2 * count + 1] = e[1]; }
+              }
+              count++;
+            }
+  return 0;
+}
+
+// ---- host-only helpers (no device needed): the task list and a dry run of the dispatch logic ----
+Integer nwc_host_task_list(const nwc_tce_state* st, Integer* klist7, Integer capacity_tasks) {
+  HostState S;
+  S.load_tables(st);
+  std::vector<Integer> kl;
+  build_task_list(S, kl);
+  const Integer n = (Integer)(kl.size() / 7);
+  if (klist7 && n <= capacity_tasks) memcpy(klist7, kl.data(), kl.size() * sizeof(Integer));
+  return n;
+}
+
+namespace {
+struct CountSink {
+  const HostState& S;
+  Integer calls[3] = {0, 0, 0};
+  double flops[3] = {0, 0, 0};
+  double prod(const Row& r) const {
+    return (double)S.rg(r.p4b) * S.rg(r.p5b) * S.rg(r.p6b) * S.rg(r.h1b) * S.rg(r.h2b) * S.rg(r.h3b);
+  }
+  void singles(const Row& r, Integer, Integer, Integer, Integer, Integer, Integer, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) { calls[0]++; flops[0] += 2.0 * prod(r); }
+  }
+  void d1_pair(const Row& r, Integer h7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) { calls[1]++; flops[1] += 2.0 * prod(r) * S.rg(h7b); }
+  }
+  void d2_pair(const Row& r, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) { calls[2]++; flops[2] += 2.0 * prod(r) * S.rg(p7b); }
+  }
+};
+}  // namespace
+
+// calls[3], flops[3] = fired sd_t_s1 / d1 / d2 kernels of one tuple and their algorithmic FLOPs
+int nwc_host_count_tuple(const nwc_tce_state* st, const Integer tuple[6], Integer calls[3], double flops[3]) {
+  HostState S;
+  S.load_tables(st);
+  CountSink sink{S};
+  walk_singles(S, tuple, sink);
+  walk_doubles(S, tuple, sink);
+  for (int i = 0; i < 3; i++) { calls[i] = sink.calls[i]; flops[i] = sink.flops[i]; }
+  return 0;
+}
+
+int nwc_ccsd_t_gpu_tuple(const nwc_tce_state* st, const Integer tuple[6], double energy[2], double* host_doubles,
+                         double* host_singles) {
+  HostState S;
+  S.load_tables(st);
+  one_tuple(S, st, tuple, energy, host_doubles, host_singles);
+  return 0;
+}
+
+}  // extern "C"

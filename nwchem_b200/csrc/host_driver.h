@@ -1,0 +1,235 @@
+// Host-side restatement of the per-tuple driver logic above the kernel boundary:
+//   ccsd_t_singles_gpu.F:36-574, ccsd_t_doubles_gpu.F:48-742 (_1, Sum h7) and :743-1345 (_2, Sum p7),
+//   tce_hashnsort.F, tce_restricted.F, tce_hash.F:271-322, ccsd_t_neword.F.
+// It walks the permutation table of one task tuple, applies the reference's filters and dispatch tests and
+// reports every (operand pair, fired kernels) event to a Sink.  Two sinks exist:
+//   * driver_replica.cu : fetch + TCE_SORT on the host, then call the Tier-1 symbols (as the Fortran does)
+//   * native_abi.cu     : emit device-side repack jobs / descriptors against the HBM-resident block stores
+#pragma once
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include "../../include/nwc_triples.h"
+
+namespace nwc {
+
+struct HostState {
+  Integer noab = 0, nvab = 0, restricted = 1, irrep_t = 0, irrep_v = 0;
+  std::vector<Integer> spin, sym, range, offset, alpha;
+  std::vector<double> evl;
+  std::vector<Integer> t1_hash, t2_hash, v2_hash;
+  void load_tables(const nwc_tce_state* s) {
+    noab = s->noab; nvab = s->nvab; restricted = s->restricted; irrep_t = s->irrep_t; irrep_v = s->irrep_v;
+    const Integer n = noab + nvab;
+    spin.assign(s->spin, s->spin + n); sym.assign(s->sym, s->sym + n); range.assign(s->range, s->range + n);
+    offset.assign(s->offset, s->offset + n); alpha.assign(s->alpha, s->alpha + n);
+    Integer ne = 0;
+    for (Integer i = 0; i < n; i++) ne = offset[i] + range[i] > ne ? offset[i] + range[i] : ne;
+    evl.assign(s->evl_sorted, s->evl_sorted + ne);
+    t1_hash.assign(s->t1_hash, s->t1_hash + 2 * s->t1_hash[0] + 1);
+    t2_hash.assign(s->t2_hash, s->t2_hash + 2 * s->t2_hash[0] + 1);
+    v2_hash.assign(s->v2_hash, s->v2_hash + 2 * s->v2_hash[0] + 1);
+  }
+  Integer sp(Integer b) const { return spin[b - 1]; }
+  Integer sy(Integer b) const { return sym[b - 1]; }
+  Integer rg(Integer b) const { return range[b - 1]; }
+  Integer N() const { return noab + nvab; }
+};
+
+// offset of block `key` in a TCE offset table (sorted keys): tce_hash.F:271-322.  -1 if absent.
+inline Integer hash_lookup(const Integer* hash, Integer key) {
+  Integer n = hash[0], lo = 1, hi = n;
+  while (lo <= hi) {
+    Integer mid = (lo + hi) >> 1;
+    if (hash[mid] == key) return hash[n + mid];
+    if (hash[mid] < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+inline Integer hash_lookup_or_die(const std::vector<Integer>& hash, Integer key, const char* what) {
+  Integer off = hash_lookup(hash.data(), key);
+  if (off < 0) { printf("nwc_triples: %s: block key %ld not found\n", what, key); fflush(stdout); exit(1); }
+  return off;
+}
+
+// block keys
+inline Integer t1_key(const HostState& S, Integer p, Integer h) { return h - 1 + S.noab * (p - S.noab - 1); }
+inline Integer t2_key(const HostState& S, Integer p1, Integer p2, Integer h3, Integer h4) {
+  return h4 - 1 + S.noab * (h3 - 1 + S.noab * (p2 - S.noab - 1 + S.nvab * (p1 - S.noab - 1)));
+}
+inline Integer v2_key(const HostState& S, Integer g3, Integer g4, Integer g1, Integer g2) {
+  const Integer N = S.N();
+  return g2 - 1 + N * (g1 - 1 + N * (g4 - 1 + N * (g3 - 1)));
+}
+
+// tce_restricted_2 / _4 (tce_restricted.F:1-71)
+inline void restricted_map(const HostState& S, int n, const Integer* in, Integer* out) {
+  Integer ssum = 0;
+  for (int i = 0; i < n; i++) ssum += S.sp(in[i]);
+  const bool map = S.restricted && ssum == 2 * n;
+  for (int i = 0; i < n; i++) out[i] = map ? S.alpha[in[i] - 1] : in[i];
+}
+
+struct Row { Integer p4b, p5b, p6b, h1b, h2b, h3b; };
+
+// the nine-row table: P/H choose which task tile plays which permuted role; duplicates are dropped
+inline int build_rows(const Integer t[6], const int P[3][3], const int H[3][3], Row rows[9]) {
+  int n = 0;
+  for (int ip = 0; ip < 3; ip++)
+    for (int ih = 0; ih < 3; ih++) {
+      Row r{t[P[ip][0]], t[P[ip][1]], t[P[ip][2]], t[3 + H[ih][0]], t[3 + H[ih][1]], t[3 + H[ih][2]]};
+      bool dup = false;
+      for (int j = 0; j < n; j++)
+        dup = dup || (rows[j].p4b == r.p4b && rows[j].p5b == r.p5b && rows[j].p6b == r.p6b && rows[j].h1b == r.h1b &&
+                      rows[j].h2b == r.h2b && rows[j].h3b == r.h3b);
+      if (!dup) rows[n++] = r;
+    }
+  return n;
+}
+
+inline bool row_ok(const HostState& S, const Row& r) {
+  const Integer ps = S.sp(r.p4b) + S.sp(r.p5b) + S.sp(r.p6b), hs = S.sp(r.h1b) + S.sp(r.h2b) + S.sp(r.h3b);
+  if (S.restricted && ps + hs == 12) return false;
+  if (ps != hs) return false;
+  return (S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.p6b) ^ S.sy(r.h1b) ^ S.sy(r.h2b) ^ S.sy(r.h3b)) == (S.irrep_v ^ S.irrep_t);
+}
+
+// which of the nine kernels fire for this row: kernel K=3*kp+kh fires iff the task tuple equals the row
+// permuted by TP[kp] (particles) and TH[kh] (holes)
+inline int fired(const Integer t[6], const Row& r, const int TP[3][3], const int TH[3][3], bool fire[9]) {
+  const Integer rp[3] = {r.p4b, r.p5b, r.p6b}, rh[3] = {r.h1b, r.h2b, r.h3b};
+  int n = 0;
+  for (int kp = 0; kp < 3; kp++)
+    for (int kh = 0; kh < 3; kh++) {
+      const bool f = t[0] == rp[TP[kp][0]] && t[1] == rp[TP[kp][1]] && t[2] == rp[TP[kp][2]] &&
+                     t[3] == rh[TH[kh][0]] && t[4] == rh[TH[kh][1]] && t[5] == rh[TH[kh][2]];
+      fire[3 * kp + kh] = f;
+      n += f;
+    }
+  return n;
+}
+
+// t = (t_p4b,t_p5b,t_p6b,t_h1b,t_h2b,t_h3b)
+template <class Sink>
+void walk_singles(const HostState& S, const Integer t[6], Sink& sink) {
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};   // ccsd_t_singles_gpu.F:101-162
+  static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+  static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}};  // tests :281,:370,:462
+  static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}};  // tests :281,:310,:340
+  Row rows[9];
+  const int n = build_rows(t, P, H, rows);
+  for (int i = 0; i < n; i++) {
+    const Row& r = rows[i];
+    if (!(r.p5b <= r.p6b && r.h2b <= r.h3b)) continue;                       // :200
+    if (!row_ok(S, r)) continue;                                             // :203-211
+    if (S.sp(r.p4b) != S.sp(r.h1b)) continue;                                // :218
+    if ((S.sy(r.p4b) ^ S.sy(r.h1b)) != S.irrep_t) continue;                  // :219
+    bool fire[9];
+    if (!fired(t, r, TP, TH, fire)) continue;
+    const Integer a[2] = {r.p4b, r.h1b}, b[4] = {r.p5b, r.p6b, r.h2b, r.h3b};
+    Integer am[2], bm[4];
+    restricted_map(S, 2, a, am);                                             // :221
+    restricted_map(S, 4, b, bm);                                             // :222
+    sink.singles(r, am[0], am[1], bm[0], bm[1], bm[2], bm[3], fire);
+  }
+}
+
+template <class Sink>
+void walk_doubles(const HostState& S, const Integer t[6], Sink& sink) {
+  {  // ---- Sum(h7): ccsd_t_doubles_gpu.F:120-742 ----
+    static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};
+    static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+    static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :357,:474,:597
+    static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}};  // tests :357,:394,:433
+    Row rows[9];
+    const int n = build_rows(t, P, H, rows);
+    for (int i = 0; i < n; i++) {
+      const Row& r = rows[i];
+      if (!(r.p4b <= r.p5b && r.h2b <= r.h3b)) continue;            // :236
+      if (!row_ok(S, r)) continue;                                  // :239-247
+      bool fire[9];
+      if (!fired(t, r, TP, TH, fire)) continue;
+      for (Integer h7b = 1; h7b <= S.noab; h7b++) {                 // :255
+        if (S.sp(r.p4b) + S.sp(r.p5b) != S.sp(r.h1b) + S.sp(h7b)) continue;
+        if ((S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.h1b) ^ S.sy(h7b)) != S.irrep_t) continue;
+        const Integer a[4] = {r.p4b, r.p5b, r.h1b, h7b}, b[4] = {r.p6b, h7b, r.h2b, r.h3b};
+        Integer am[4], bm[4];
+        restricted_map(S, 4, a, am);                                // :260
+        restricted_map(S, 4, b, bm);                                // :261
+        sink.d1_pair(r, h7b, am, bm, fire);
+      }
+    }
+  }
+  {  // ---- Sum(p7): ccsd_t_doubles_gpu.F:810-1345 ----
+    static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+    static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};
+    static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}};  // tests :998,:1106,:1214
+    static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :998,:1034,:1070
+    Row rows[9];
+    const int n = build_rows(t, P, H, rows);
+    for (int i = 0; i < n; i++) {
+      const Row& r = rows[i];
+      if (!(r.p5b <= r.p6b && r.h1b <= r.h2b)) continue;            // :909
+      if (!row_ok(S, r)) continue;
+      bool fire[9];
+      if (!fired(t, r, TP, TH, fire)) continue;
+      for (Integer p7b = S.noab + 1; p7b <= S.noab + S.nvab; p7b++) {  // :923
+        if (S.sp(r.p4b) + S.sp(p7b) != S.sp(r.h1b) + S.sp(r.h2b)) continue;
+        if ((S.sy(r.p4b) ^ S.sy(p7b) ^ S.sy(r.h1b) ^ S.sy(r.h2b)) != S.irrep_t) continue;
+        const Integer a[4] = {r.p4b, p7b, r.h1b, r.h2b}, b[4] = {r.p5b, r.p6b, r.h3b, p7b};
+        Integer am[4], bm[4];
+        restricted_map(S, 4, a, am);                                // :928
+        restricted_map(S, 4, b, bm);                                // :929
+        sink.d2_pair(r, p7b, am, bm, fire);
+      }
+    }
+  }
+}
+
+// ccsd_t_dot.F:52-66
+inline double tuple_factor(const HostState& S, const Integer t[6]) {
+  double f = S.restricted ? 2.0 : 1.0;
+  if (t[0] == t[1] && t[1] == t[2]) f /= 6.0; else if (t[0] == t[1] || t[1] == t[2]) f /= 2.0;
+  if (t[3] == t[4] && t[4] == t[5]) f /= 6.0; else if (t[3] == t[4] || t[4] == t[5]) f /= 2.0;
+  return f;
+}
+
+// task enumeration + heaviest-first banding: ccsd_t_neword.F:42-217.  Rows of 7: 6 tile ids + weight.
+inline void build_task_list(const HostState& S, std::vector<Integer>& klist) {
+  std::vector<Integer> aux;
+  const Integer n0 = S.noab, n1 = S.noab + S.nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              const Integer ps = S.sp(p4) + S.sp(p5) + S.sp(p6), hs = S.sp(h1) + S.sp(h2) + S.sp(h3);
+              if (ps != hs) continue;
+              if (S.restricted && ps + hs > 8) continue;
+              if ((S.sy(p4) ^ S.sy(p5) ^ S.sy(p6) ^ S.sy(h1) ^ S.sy(h2) ^ S.sy(h3)) != 0) continue;
+              const Integer w = S.rg(p4) * S.rg(p5) * S.rg(p6) * S.rg(h1) * S.rg(h2) * S.rg(h3);
+              const Integer row[7] = {p4, p5, p6, h1, h2, h3, w};
+              aux.insert(aux.end(), row, row + 7);
+            }
+  const size_t nt = aux.size() / 7;
+  klist.clear();
+  if (nt == 0) return;
+  Integer wmax = 0, wmin;
+  for (size_t i = 0; i < nt; i++) wmax = aux[7 * i + 6] > wmax ? aux[7 * i + 6] : wmax;
+  wmin = wmax;
+  for (size_t i = 0; i < nt; i++) wmin = aux[7 * i + 6] < wmin ? aux[7 * i + 6] : wmin;
+  if (((wmax - wmin) * 100.0) / wmax < 1.0) { klist = aux; return; }   // :136-143
+  klist.reserve(aux.size());
+  auto sweep = [&](Integer value) {
+    for (size_t i = 0; i < nt; i++)
+      if (aux[7 * i + 6] > value) {
+        klist.insert(klist.end(), aux.begin() + 7 * i, aux.begin() + 7 * i + 7);
+        aux[7 * i + 6] = -99;
+      }
+  };
+  for (Integer ii = 16; ii >= 1; ii--) sweep(wmin + ((wmax - wmin) * (ii - 1)) / 16);  // :168-173
+  sweep(0);                                                                              // :174
+}
+
+}  // namespace nwc

@@ -1,0 +1,73 @@
+// Device-side data structures and launchers of libnwc_triples (sm_100a).
+//
+// Operand "panel" format (both ABI tiers feed the fused kernel this format):
+//   a contraction operand  X(k ; x1,x2,x3)  -- k the contracted index, (x1,x2,x3) the three external
+//   indices in split order (G1: pa,h_lo,h_hi / G2: hb,p_hi,p_lo, see tables.h) -- is stored as
+//       P[kq][b3][b2][b1][i3][i2][i1][kk] ,  x_j = 4*b_j + i_j ,  k = 4*kq + kk ,
+//   zero padded to multiples of 4 in every index.  One (kq,b3,b2,b1) "base block" is 64 rows x 4 k
+//   = 256 doubles = 2 KiB contiguous: exactly the A (or B) operand of sixteen DMMA.8x8x4 row blocks,
+//   fetched with ONE cp.async.bulk (TMA) and read from shared memory conflict-free.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nwc {
+
+constexpr int SB = 4;              // base sub-tile edge (all six indices)
+constexpr int BLK_DOUBLES = 256;   // 64 rows x 4 k
+constexpr int SUBTILE = 4096;      // 4^6 t3 elements per work item
+
+struct ContrDesc {      // one fired sd_t_d1_K / sd_t_d2_K call
+  const double* g1;     // G1 panel
+  const double* g2;     // G2 panel
+  int nk4;              // number of k4 planes
+  int neg;              // 1: subtract the product
+};
+
+struct SinglesDesc {    // one fired sd_t_s1_K call:  S +-= t1[sum g*st1] * v2[sum g*sv2]
+  const double* t1;
+  const double* v2;
+  int st1[6];           // element strides per physical position (0 where the operand lacks the index)
+  int sv2[6];
+  int neg;
+  int pad;
+};
+
+struct TupleHdr {
+  int R[6];             // ranges by physical position (h3,h2,h1,p6,p5,p4)
+  int nb[6];            // ceil(R/4)
+  const double* eps[6]; // orbital energies of the six tiles (device)
+  double factor;        // ccsd_t_dot.F:52-66
+  int desc_begin[10];   // split s owns descs [desc_begin[s], desc_begin[s+1])
+  int sdesc_begin, sdesc_end;
+  long long item_begin; // first work item (sub-tile) of this tuple in the launch
+  int nitems;
+  int pad;
+};
+
+struct RepackJob {      // build one panel from a strided source
+  const double* src;
+  double* dst;
+  long long s1, s2, s3, sk;   // source strides (in doubles) of x1,x2,x3,k
+  int X1, X2, X3, K;
+  double scale;
+};
+
+inline long long panel_doubles(int X1, int X2, int X3, int K) {
+  auto c4 = [](int v) { return (long long)((v + 3) / 4); };
+  return c4(K) * c4(X1) * c4(X2) * c4(X3) * BLK_DOUBLES;
+}
+
+// launchers (kernels.cu).  All asynchronous on `stream`.
+void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
+void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
+                  double2* d_partials, long long total_items, cudaStream_t stream);
+void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_energies,
+                   cudaStream_t stream);
+// unfused debugging/validation path: materialise the two t3 tiles of ONE tuple in HBM
+void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
+                       double2* d_partials, long long total_items, double* d_doubles, double* d_singles,
+                       cudaStream_t stream);
+int fused_smem_bytes();
+
+}  // namespace nwc

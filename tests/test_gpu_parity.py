@@ -1,0 +1,250 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of
+libnwc_triples.so and is checked against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-element t3 values within 1e-11 relative (to the tile's
+largest element), |dE| <= 1e-9 Eh on energies.
+"""
+import os
+import numpy as np
+import pytest
+from nwchem_b200 import capi, synth, tiling as tl
+from nwchem_b200.kernel_tables import DECL, PHYS
+
+pytestmark = pytest.mark.gpu
+
+REL_T3 = 1e-11
+ABS_E = 1e-9
+FLOOR = 1e-8   # amplitudes/integrals of the synthetic inputs are O(1e-3..1e-1)
+
+
+def _relmax(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _eps(rng, dims_task):
+    h1d, h2d, h3d, p4d, p5d, p6d = dims_task
+    return [np.sort(rng.uniform(-2.0, -0.4, n)) for n in (h1d, h2d, h3d)] + \
+           [np.sort(rng.uniform(0.1, 3.0, n)) for n in (p4d, p5d, p6d)]
+
+
+def _oracle_energy(oracle, s, d, eps, factor, dims_task):
+    """ccsd_t_dot on [p4,p5,p6,h1,h2,h3] tiles."""
+    import ctypes as C
+    l = oracle.lib()
+    h1d, h2d, h3d, p4d, p5d, p6d = dims_task
+    e1 = C.c_double(0.0); e2 = C.c_double(0.0)
+    PD = C.POINTER(C.c_double); L = C.c_long
+    pd = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(PD)
+    s = np.ascontiguousarray(s); d = np.ascontiguousarray(d)
+    # restricted=0 and distinct tile ids -> factor 1; scale afterwards
+    l.ora_ccsd_t_dot(pd(s), pd(d), 0, L(1), L(2), L(3), L(4), L(5), L(6), pd(eps[0]), pd(eps[1]), pd(eps[2]),
+                     pd(eps[3]), pd(eps[4]), pd(eps[5]), L(h1d), L(h2d), L(h3d), L(p4d), L(p5d), L(p6d),
+                     C.byref(e1), C.byref(e2))
+    return factor * e1.value, factor * e2.value
+
+
+@pytest.mark.parametrize("family", [0, 1, 2])
+@pytest.mark.parametrize("k", range(1, 10))
+def test_each_entry_point_matches_oracle_kernel(oracle, family, k):
+    """One sd_t_{s1,d1,d2}_k_cuda_ call on ragged, mutually distinct ranges vs ccsd_t_kernels_omp.F restated."""
+    rng = np.random.default_rng(1000 * family + k)
+    R = dict(h3=5, h2=7, h1=3, p6=6, p5=9, p4=4)  # physical (task) ranges; none a multiple of 4 except p4
+    kd = 11
+    dims_task = (R["h1"], R["h2"], R["h3"], R["p4"], R["p5"], R["p6"])
+    decl = DECL[family][k - 1]
+    perm = {name: R[PHYS[pos]] for pos, name in enumerate(decl)}  # permuted name -> its range
+    dims_perm = (perm["h1"], perm["h2"], perm["h3"], perm["p4"], perm["p5"], perm["p6"])
+    if family == 0:
+        ts = rng.standard_normal(perm["p4"] * perm["h1"]); vs = rng.standard_normal(perm["h3"] * perm["h2"] * perm["p6"] * perm["p5"])
+    elif family == 1:
+        ts = rng.standard_normal(kd * perm["p4"] * perm["p5"] * perm["h1"]); vs = rng.standard_normal(perm["h3"] * perm["h2"] * perm["p6"] * kd)
+    else:
+        ts = rng.standard_normal(kd * perm["p4"] * perm["h1"] * perm["h2"]); vs = rng.standard_normal(kd * perm["h3"] * perm["p6"] * perm["p5"])
+    n = int(np.prod(dims_task))
+    t3 = np.zeros(n)
+    oracle.kernel(family, k, (perm["h3"], perm["h2"], perm["h1"], perm["p6"], perm["p5"], perm["p4"]), kd, t3, ts, vs)
+    shp = (R["p4"], R["p5"], R["p6"], R["h1"], R["h2"], R["h3"])
+    ref = t3.reshape(shp)
+    eps = _eps(rng, dims_task)
+    factor = 0.5
+    e1, e2, s_tile, d_tile = capi.tier1_single_call(family, k, dims_task, dims_perm, kd, ts, vs, eps, factor)
+    got = s_tile if family == 0 else d_tile
+    other = d_tile if family == 0 else s_tile
+    assert _relmax(got, ref) <= REL_T3
+    assert np.all(other == 0.0)
+    zero = np.zeros_like(ref)
+    oe1, oe2 = _oracle_energy(oracle, ref if family == 0 else zero, zero if family == 0 else ref, eps, factor, dims_task)
+    assert abs(e1 - oe1) <= 1e-11 * max(abs(oe1), 1.0)
+    assert abs(e2 - oe2) <= 1e-11 * max(abs(oe2), 1.0)
+
+
+def test_k_not_multiple_of_four_and_tiny_ranges(oracle):
+    """Ranges of 1 and contracted dims 1..9 (zero padding of the panels must be exact)."""
+    rng = np.random.default_rng(5)
+    for kd in (1, 2, 3, 5, 9):
+        R = dict(h3=1, h2=2, h1=1, p6=3, p5=1, p4=5)
+        dims_task = (R["h1"], R["h2"], R["h3"], R["p4"], R["p5"], R["p6"])
+        for family, k in ((2, 1), (2, 6), (1, 4), (1, 9)):
+            decl = DECL[family][k - 1]
+            perm = {name: R[PHYS[pos]] for pos, name in enumerate(decl)}
+            dims_perm = (perm["h1"], perm["h2"], perm["h3"], perm["p4"], perm["p5"], perm["p6"])
+            if family == 1:
+                ts = rng.standard_normal(kd * perm["p4"] * perm["p5"] * perm["h1"]); vs = rng.standard_normal(perm["h3"] * perm["h2"] * perm["p6"] * kd)
+            else:
+                ts = rng.standard_normal(kd * perm["p4"] * perm["h1"] * perm["h2"]); vs = rng.standard_normal(kd * perm["h3"] * perm["p6"] * perm["p5"])
+            t3 = np.zeros(int(np.prod(dims_task)))
+            oracle.kernel(family, k, (perm["h3"], perm["h2"], perm["h1"], perm["p6"], perm["p5"], perm["p4"]), kd, t3, ts, vs)
+            ref = t3.reshape(R["p4"], R["p5"], R["p6"], R["h1"], R["h2"], R["h3"])
+            _, _, _, d_tile = capi.tier1_single_call(family, k, dims_task, dims_perm, kd, ts, vs, _eps(rng, dims_task), 1.0)
+            assert _relmax(d_tile, ref) <= REL_T3, (kd, family, k)
+
+
+@pytest.fixture(scope="module")
+def h2o_c2v():
+    return synth.physical(synth.shape_tiling("h2o_ccpvdz_c2v"))
+
+
+def test_every_tuple_of_h2o_c2v_native_and_compat(oracle, h2o_c2v):
+    """All 230 tuples of the H2O/cc-pVDZ C2v tile table (irrep filter, ragged 1-8 tiles, k_alpha mapping):
+    t3 tiles and per-tuple energies of both ABI tiers vs the oracle."""
+    st = h2o_c2v
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    tasks = oracle.task_list(st.t)
+    assert np.array_equal(tr.task_list(), tasks)
+    worst = 0.0
+    for i, tup in enumerate(tasks):
+        s_ref, d_ref, e1, e2, _ = oracle.tuple_tiles(st, tup[:6])
+        g1, g2, s_n, d_n = tr.run_tuple(tup[:6], dump=True)
+        # relative to the tile's largest element, floored: tiles that vanish by symmetry hold only
+        # cancellation noise (~1e-20) in the oracle and exact zeros on the GPU
+        scale_d = max(np.max(np.abs(d_ref)), FLOOR); scale_s = max(np.max(np.abs(s_ref)), FLOOR)
+        assert np.max(np.abs(d_n - d_ref)) <= REL_T3 * scale_d, tup
+        assert np.max(np.abs(s_n - s_ref)) <= REL_T3 * scale_s, tup
+        assert abs(g1 - e1) <= ABS_E * 1e-3 and abs(g2 - e2) <= ABS_E * 1e-3, tup
+        if i % 7 == 0:  # Tier 1 (host fetch + sort + H2D per call) on a subset
+            c1, c2, s_c, d_c = capi.ccsd_t_gpu_tuple(st, tup[:6], dump=True)
+            assert np.max(np.abs(d_c - d_ref)) <= REL_T3 * scale_d, tup
+            assert np.max(np.abs(s_c - s_ref)) <= REL_T3 * scale_s, tup
+            assert abs(c1 - e1) <= ABS_E * 1e-3 and abs(c2 - e2) <= ABS_E * 1e-3, tup
+        worst = max(worst, np.max(np.abs(d_n - d_ref)) / scale_d)
+    tr.close()
+    assert worst <= REL_T3
+
+
+@pytest.mark.parametrize("shape,ts", [("h2o_ccpvdz_c2v", 20), ("h2o_ccpvdz_c2v", 5), ("h2o_ccpvdz_c1", 7), ("h2o_ccpvdz_c1", 20)])
+def test_total_energy_both_tiers(oracle, shape, ts):
+    st = synth.physical(synth.shape_tiling(shape, tilesize=ts))
+    ref = oracle.ccsd_t(st)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    e1, e2, pt = tr.run(per_task=True)
+    tr.close()
+    assert abs(e1 - ref["e1"]) <= ABS_E and abs(e2 - ref["e2"]) <= ABS_E
+    assert np.max(np.abs(pt - ref["per_task"])) <= ABS_E
+    assert abs(e1 - ref["e1"]) <= 1e-11 * abs(ref["e1"]) and abs(e2 - ref["e2"]) <= 1e-11 * abs(ref["e2"])
+    c1, c2, _ = capi.ccsd_t_gpu(st)
+    assert abs(c1 - ref["e1"]) <= ABS_E and abs(c2 - ref["e2"]) <= ABS_E
+
+
+def test_static_partition_sums_to_total(oracle, h2o_c2v):
+    """first/stride partition (replaces nxtask): rank partial sums add up to the single-rank result."""
+    tr = capi.Triples(0)
+    tr.set_state(h2o_c2v)
+    e1, e2 = tr.run()
+    parts = [tr.run(first=r, stride=4) for r in range(4)]
+    tr.close()
+    assert abs(sum(p[0] for p in parts) - e1) <= 1e-13 and abs(sum(p[1] for p in parts) - e2) <= 1e-13
+
+
+def test_tile_size_invariance_gpu_tile40_vs_oracle_tile10(oracle):
+    """Full-size tiles on the GPU (virtual tile 40, occupied tile 14) against the oracle at tilesize 10:
+    E[T]/E(T) are tile-size invariant for antisymmetric amplitudes, so this checks big ragged-free tiles
+    without a 40^6 CPU buffer."""
+    occ, virt = [14], [40]
+    st40 = synth.physical(tl.make_tiling(occ, virt, 40))
+    st10 = synth.physical(tl.make_tiling(occ, virt, 10))
+    ref = oracle.ccsd_t(st10)
+    tr = capi.Triples(0)
+    tr.set_state(st40)
+    e1, e2 = tr.run()
+    tr.close()
+    assert abs(e1 - ref["e1"]) <= ABS_E and abs(e2 - ref["e2"]) <= ABS_E
+    assert abs(e1 - ref["e1"]) <= 1e-11 * abs(ref["e1"])
+
+
+def test_microbench_t40_properties():
+    """BASELINE configs[1] at full size (o=v=40, tilesize 40, random tiles): determinism, and the quadratic /
+    bilinear scaling of E[T] and E(T)-E[T] under T2 -> a*T2, T1 -> b*T1."""
+    t = synth.shape_tiling("microbench_t40")
+    st = synth.random_blocks(t)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    e1, e2, pt = tr.run(per_task=True)
+    f1, f2, pt2 = tr.run(per_task=True)
+    assert (e1, e2) == (f1, f2) and np.array_equal(pt, pt2)   # bitwise reproducible
+    a, b = 0.5, 3.0
+    st2 = synth.BlockStores(t, st.t1_hash, st.t1 * b, st.t2_hash, st.t2 * a, st.v2_hash, st.v2)
+    tr.set_state(st2)
+    g1, g2 = tr.run()
+    st_ = tr.stats()
+    tr.close()
+    assert abs(g1 - a * a * e1) <= 1e-11 * abs(e1)
+    assert abs((g2 - g1) - a * b * (e2 - e1)) <= 1e-11 * abs(e2 - e1) + 1e-13 * abs(e1)
+    assert st_["flops"] > 0
+
+
+def test_reference_cuda_kernels_agree_with_oracle(oracle):
+    """Pins the oracle: the reference's own sd_t_total.cu + memory.cu (compiled unmodified into oracle/_ref)
+    run here and must reproduce the oracle's kernels and energy (tiles <= 32: its singles kernel overflows
+    shared memory above that, sd_t_total.cu:5406-5410)."""
+    import ctypes as C
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsd_t_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (reference sources not mounted at build time)")
+    ref = C.CDLL(path)
+    rng = np.random.default_rng(3)
+    R = dict(h3=5, h2=7, h1=3, p6=6, p5=9, p4=4)
+    kd = 11
+    dims_task = (R["h1"], R["h2"], R["h3"], R["p4"], R["p5"], R["p6"])
+    n = int(np.prod(dims_task))
+    PD = C.POINTER(C.c_double)
+    pd = lambda a: a.ctypes.data_as(PD)
+    T = [C.c_long(x) for x in dims_task]
+    eps = _eps(rng, dims_task)
+    s_acc = np.zeros(n); d_acc = np.zeros(n)
+    ref.initmemmodule_()
+    ref.dev_mem_s_(*[C.byref(x) for x in T])
+    ref.dev_mem_d_(*[C.byref(x) for x in T])
+    for family in (0, 1, 2):
+        for k in range(1, 10):
+            decl = DECL[family][k - 1]
+            perm = {name: R[PHYS[pos]] for pos, name in enumerate(decl)}
+            P = [C.c_long(perm[x]) for x in ("h1", "h2", "h3", "p4", "p5", "p6")]
+            K = C.c_long(kd)
+            if family == 0:
+                ts = rng.standard_normal(perm["p4"] * perm["h1"]); vs = rng.standard_normal(perm["h3"] * perm["h2"] * perm["p6"] * perm["p5"])
+            elif family == 1:
+                ts = rng.standard_normal(kd * perm["p4"] * perm["p5"] * perm["h1"]); vs = rng.standard_normal(perm["h3"] * perm["h2"] * perm["p6"] * kd)
+            else:
+                ts = rng.standard_normal(kd * perm["p4"] * perm["h1"] * perm["h2"]); vs = rng.standard_normal(kd * perm["h3"] * perm["p6"] * perm["p5"])
+            oracle.kernel(family, k, (perm["h3"], perm["h2"], perm["h1"], perm["p6"], perm["p5"], perm["p4"]), kd,
+                          s_acc if family == 0 else d_acc, ts, vs)
+            fn = getattr(ref, f"sd_t_{('s1', 'd1', 'd2')[family]}_{k}_cuda_")
+            h1, h2, h3, p4, p5, p6 = [C.byref(x) for x in P]
+            if family == 0:
+                fn(h1, h2, h3, p4, p5, p6, None, pd(ts), pd(vs))
+            elif family == 1:
+                fn(h1, h2, h3, C.byref(K), p4, p5, p6, None, pd(ts), pd(vs))
+            else:
+                fn(h1, h2, h3, p4, p5, p6, C.byref(K), None, pd(ts), pd(vs))
+    factor = C.c_double(0.25)
+    e = np.zeros(2); hd = np.zeros(n); hs = np.zeros(n)
+    ev = [np.ascontiguousarray(x) for x in eps]
+    ref.compute_en_(C.byref(factor), pd(e), *[pd(x) for x in ev], *[C.byref(x) for x in T], pd(hd), pd(hs), None, None)
+    ref.dev_release_()
+    ref.finalizememmodule_()
+    shp = (R["p4"], R["p5"], R["p6"], R["h1"], R["h2"], R["h3"])
+    oe1, oe2 = _oracle_energy(oracle, s_acc.reshape(shp), d_acc.reshape(shp), eps, 0.25, dims_task)
+    assert abs(e[0] - oe1) <= 1e-11 * abs(oe1)
+    assert abs(e[1] - oe2) <= 1e-11 * abs(oe2)

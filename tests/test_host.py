@@ -1,0 +1,78 @@
+"""CPU tests of the product's host side: the C-ABI library loads, exports every declared symbol, and its
+host-side driver logic (task list, dispatch walk) agrees with the oracle.  No compute calls (no GPU here)."""
+import os
+import re
+import numpy as np
+import pytest
+from nwchem_b200 import capi, synth, tiling as tl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nwc_triples.h")).read()
+    names = set(re.findall(r"\b(nwc_[a-z0-9_]+|check_device_|device_init_|initmemmodule_|finalizememmodule_|"
+                           r"dev_mem_s_|dev_mem_d_|dev_release_|compute_en_)\s*\(", src))
+    names -= {"nwc_tce_state", "nwc_triples_ctx", "nwc_triples_stats"}
+    for fam in ("s1", "d1", "d2"):
+        for k in range(1, 10):
+            names.add(f"sd_t_{fam}_{k}_cuda_")
+    return sorted(names)
+
+
+def test_library_loads_and_exports_all_declared_symbols():
+    l = capi.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 27 + 8 + 15
+    for s in syms:
+        assert hasattr(l, s), f"libnwc_triples.so does not export {s}"
+
+
+def test_kernel_tables_match_between_python_and_c_header():
+    from nwchem_b200.kernel_tables import DECL, SIGN
+    src = open(os.path.join(ROOT, "nwchem_b200", "csrc", "tables.h")).read()
+    rows = re.findall(r"\{(N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d)\}", src)
+    assert len(rows) == 27
+    flat = [tuple(x.strip()[2:].lower() for x in r.split(",")) for r in rows]
+    assert flat == [d for fam in DECL for d in fam]
+    signs = re.findall(r"\{([+-]1(?:, [+-]1){8})\}", src)
+    assert [tuple(int(x) for x in s.split(",")) for s in signs] == [tuple(s) for s in SIGN]
+
+
+@pytest.mark.parametrize("shape,ts", [("h2o_ccpvdz_c2v", 20), ("h2o_ccpvdz_c2v", 5), ("h2o_ccpvdz_c1", 7),
+                                      ("uracil_augccpvdz", 40)])
+def test_host_task_list_and_dispatch_match_oracle(oracle, shape, ts):
+    t = synth.shape_tiling(shape, tilesize=ts)
+
+    class D:
+        pass
+    d = D(); d.t = t
+    d.t1_hash = d.t2_hash = d.v2_hash = np.zeros(3, np.int64); d.t1 = d.t2 = d.v2 = np.zeros(1)
+    kl = capi.host_task_list(d)
+    ko = oracle.task_list(t)
+    assert np.array_equal(kl, ko)
+    c, keep = oracle.make_ctx(d)
+    state = capi.make_state(d)
+    for tup in kl[:: max(1, len(kl) // 60)]:
+        calls, flops = capi.host_count_tuple(d, tup[:6], state)
+        cnt = oracle.count_tuple(c, tup[:6], keep)
+        assert tuple(calls) == (cnt.calls_s1, cnt.calls_d1, cnt.calls_d2)
+        assert tuple(flops) == (cnt.flops_s1, cnt.flops_d1, cnt.flops_d2)
+
+
+def test_h2o10_flops_from_product_host_logic():
+    t = synth.shape_tiling("h2o10_augccpvtz")
+
+    class D:
+        pass
+    d = D(); d.t = t
+    d.t1_hash = d.t2_hash = d.v2_hash = np.zeros(3, np.int64); d.t1 = d.t2 = d.v2 = np.zeros(1)
+    kl = capi.host_task_list(d)
+    assert len(kl) == 7590
+    state = capi.make_state(d)
+    tot = np.zeros(3); calls = np.zeros(3, np.int64)
+    for tup in kl:
+        c, f = capi.host_count_tuple(d, tup[:6], state)
+        tot += f; calls += c
+    assert tuple(calls) == (46046, 62744, 1380368)
+    assert abs(tot.sum() - 4.52e17) / 4.52e17 < 5e-3
