@@ -136,6 +136,17 @@ int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3
                           double *host_doubles, double *host_singles);
 int nwc_triples_set_timing(nwc_triples_ctx *ctx, int on);
 int nwc_triples_get_stats(nwc_triples_ctx *ctx, nwc_triples_stats *out, int reset);
+/* device-side stopwatch: CUDA events recorded on the stream the kernels are launched on */
+int nwc_triples_timer_start(nwc_triples_ctx *ctx);
+int nwc_triples_timer_stop_ms(nwc_triples_ctx *ctx, double *ms);
+/* pin / unpin a host range (cudaHostRegister) so Tier-1 operand uploads are true async DMA */
+int nwc_host_register(void *ptr, size_t bytes);
+int nwc_host_unregister(void *ptr);
+/* counters of the Tier-1 engine (the one behind sd_t_*_cuda_ / compute_en_) */
+int nwc_compat_get_stats(nwc_triples_stats *out, int reset);
+int nwc_compat_set_timing(int on);
+int nwc_compat_timer_start(void);
+int nwc_compat_timer_stop_ms(double *ms);
 /* panel arena budget per batch in bytes (default 8 GiB) */
 int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
 

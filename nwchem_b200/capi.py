@@ -53,6 +53,10 @@ def lib() -> C.CDLL:
         _lib.nwc_triples_set_timing.argtypes = [C.c_void_p, C.c_int]
         _lib.nwc_triples_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
         _lib.nwc_triples_set_batch_bytes.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.nwc_triples_timer_start.argtypes = [C.c_void_p]
+        _lib.nwc_triples_timer_stop_ms.argtypes = [C.c_void_p, PD]
+        _lib.nwc_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.nwc_host_unregister.argtypes = [C.c_void_p]
         _lib.nwc_triples_nccl_unique_id.argtypes = [C.c_char_p]
         _lib.nwc_triples_nccl_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.nwc_triples_allreduce_energy.argtypes = [C.c_void_p, PD]
@@ -183,6 +187,14 @@ class Triples:
     def set_batch_bytes(self, n):
         lib().nwc_triples_set_batch_bytes(self._h, int(n))
 
+    def timer_start(self):
+        lib().nwc_triples_timer_start(self._h)
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_double(0.0)
+        lib().nwc_triples_timer_stop_ms(self._h, C.byref(ms))
+        return ms.value
+
     def stats(self, reset=False) -> dict:
         s = Stats()
         lib().nwc_triples_get_stats(self._h, C.byref(s), int(reset))
@@ -259,3 +271,31 @@ def host_count_tuple(st, tup, state=None):
     tt = np.array(tup, np.int64)
     lib().nwc_host_count_tuple(C.byref(s), _pl(tt), _pl(calls), _pd(flops))
     return calls, flops
+
+
+def compat_stats(reset=False) -> dict:
+    s = Stats()
+    lib().nwc_compat_get_stats(C.byref(s), int(reset))
+    return s.asdict()
+
+
+def compat_set_timing(on=True):
+    lib().nwc_compat_set_timing(int(on))
+
+
+def compat_timer_start():
+    lib().nwc_compat_timer_start()
+
+
+def compat_timer_stop_ms() -> float:
+    ms = C.c_double(0.0)
+    lib().nwc_compat_timer_stop_ms(C.byref(ms))
+    return ms.value
+
+
+def host_register(arr: np.ndarray):
+    _check(lib().nwc_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes), "nwc_host_register")
+
+
+def host_unregister(arr: np.ndarray):
+    lib().nwc_host_unregister(C.c_void_p(arr.ctypes.data))

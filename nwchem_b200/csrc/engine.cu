@@ -52,6 +52,16 @@ Engine::Engine(int device) : device_(device) {
   NWC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   NWC_CUDA(cudaEventCreate(&ev0_));
   NWC_CUDA(cudaEventCreate(&ev1_));
+  NWC_CUDA(cudaEventCreate(&evt0_));
+  NWC_CUDA(cudaEventCreate(&evt1_));
+}
+void Engine::timer_start() { NWC_CUDA(cudaEventRecord(evt0_, stream_)); }
+double Engine::timer_stop_ms() {
+  NWC_CUDA(cudaEventRecord(evt1_, stream_));
+  NWC_CUDA(cudaEventSynchronize(evt1_));
+  float ms = 0;
+  NWC_CUDA(cudaEventElapsedTime(&ms, evt0_, evt1_));
+  return ms;
 }
 Engine::~Engine() {
   cudaSetDevice(device_);
@@ -62,6 +72,8 @@ Engine::~Engine() {
   if (h_pin_) cudaFreeHost(h_pin_);
   cudaEventDestroy(ev0_);
   cudaEventDestroy(ev1_);
+  cudaEventDestroy(evt0_);
+  cudaEventDestroy(evt1_);
   cudaStreamDestroy(stream_);
 }
 

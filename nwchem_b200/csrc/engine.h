@@ -86,6 +86,8 @@ class Engine {
 
   EngineStats stats;
   bool timing = false;
+  void timer_start();
+  double timer_stop_ms();
 
  private:
   int device_;
@@ -100,7 +102,7 @@ class Engine {
   std::vector<RepackJob> jobs_;
   long long max_panel_ = 0;
   long long items_ = 0;
-  cudaEvent_t ev0_, ev1_;
+  cudaEvent_t ev0_, ev1_, evt0_, evt1_;
   // small reusable device buffers for descriptor uploads
   void* d_meta_ = nullptr; size_t d_meta_cap_ = 0;
   void* d_jobs_ = nullptr; size_t d_jobs_cap_ = 0;

@@ -97,27 +97,35 @@ void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubl
 // ------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int NTHREADS = 128;  // 4 warps, warp tile 32x32 of the 64x64 split GEMM
-constexpr int STAGES = 3;
-constexpr int KQ = 2;                                // k4 planes per stage
-constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block
-constexpr int STAGE_DOUBLES = KQ * PLANE_DOUBLES;    // 8 KiB
+constexpr int NCONSUMERS = 128; // 4 MMA warps, warp tile 32x32 of the 64x64 split GEMM
+constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
+constexpr int STAGES = 10;                           // ring depth; one k4 plane (4 KiB) per stage
+constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block = 4 KiB
+constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
 constexpr int MAX_SDESC = 16;
+constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
+constexpr int SD_PER_PASS = RING_DOUBLES / SD_TERM;                // 18 terms per pass (>= MAX_SDESC)
 
 struct SplitGeom {          // per (CTA, split): where this sub-tile's base blocks live inside a panel
   long long off1, ps1;      // G1: offset of (b_hhi,b_hlo,b_pa) block in plane 0; plane stride (doubles)
   long long off2, ps2;      // G2
 };
 
+struct SinglesTerm {        // per fired sd_t_s1_K term, derived once per CTA
+  short wt[6];              // multiplier of each physical position in the staged t1 block (0 if absent)
+  short wv[6];              // ... in the staged v2 block
+};
+
 struct __align__(16) FusedSmem {
   double canon[SUBTILE];                    // 32 KiB canonical t3 sub-tile (doubles part)
-  double stage[STAGES * STAGE_DOUBLES];     // 24 KiB operand ring
+  double ring[RING_DOUBLES];                // operand ring
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
+  uint64_t canon_bar;                       // split-phase barrier between the flushes of consecutive splits
   SplitGeom geom[9];
   double eps[6][4];
-  double red[2][NTHREADS / 32];
-  SinglesDesc sd[MAX_SDESC];
+  double red[2][NCONSUMERS / 32];
+  SinglesTerm st[MAX_SDESC];
   int desc_begin[10];
   int b[6];
   int R[6];
@@ -126,23 +134,52 @@ struct __align__(16) FusedSmem {
 
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
 
-// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; fold the two upper nibbles
-// into the bank-selecting nibble so that the nine fragment->canonical scatter patterns spread over banks
-__device__ __forceinline__ int canon_swz(int L) { return L ^ ((L >> 4) & 15) ^ ((L >> 8) & 15); }
+// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; fold the two upper nibbles into the
+// bank-selecting nibble so that the nine fragment->canonical scatter patterns spread over banks.
+// GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b), which lets thread part and unrolled constant part separate.
+__host__ __device__ constexpr int canon_swz(int L) { return L ^ ((L >> 4) & 15) ^ ((L >> 8) & 15); }
 
-struct Cursor {
-  int s, d, q;
+// split tables as compile-time constants
+template <int S> struct SplitC {
+  static constexpr int pa = 3 + S / 3, hb = S % 3;
+  static constexpr int hlo = (hb == 2) ? 1 : 2;                 // larger position of the remaining holes (lower name)
+  static constexpr int hhi = (hb == 0) ? 1 : 0;
+  static constexpr int phi = (pa == 3) ? 4 : 3;                 // smaller position of the remaining particles
+  static constexpr int plo = (pa == 5) ? 4 : 5;
 };
 
+// fold the fragment accumulators of split S into the canonical sub-tile and clear them
+template <int S>
+__device__ __forceinline__ void flush_split(double (&acc)[4][4][2], double* canon, int lane, int wm, int wn) {
+  using C = SplitC<S>;
+  constexpr int c_pa = 1 << (2 * C::pa), c_hlo = 1 << (2 * C::hlo), c_hhi = 1 << (2 * C::hhi);
+  constexpr int c_hb = 1 << (2 * C::hb), c_phi = 1 << (2 * C::phi), c_plo = 1 << (2 * C::plo);
+  // fragment element (warp wm,wn; block bi,bj; lane; j): row m = 32wm+8bi+lane/4 -> (i_pa,i_hlo,i_hhi) = (m&3,(m>>2)&3,m>>4)
+  //                                                      col n = 32wn+8bj+2(lane&3)+j -> (i_hb,i_phi,i_plo)
+  const int Lt = ((lane >> 2) & 3) * c_pa + ((lane >> 4) & 1) * c_hlo + (wm * 2) * c_hhi + ((lane & 1) * 2) * c_hb +
+                 ((lane >> 1) & 1) * c_phi + (wn * 2) * c_plo;
+  const int At = canon_swz(Lt);
+#pragma unroll
+  for (int bi = 0; bi < 4; bi++)
+#pragma unroll
+    for (int bj = 0; bj < 4; bj++) {
+      const int Lc = (bi & 1) * 2 * c_hlo + (bi >> 1) * c_hhi + (bj & 1) * 2 * c_phi + (bj >> 1) * c_plo;  // constant
+      canon[At ^ canon_swz(Lc)] += acc[bi][bj][0];
+      canon[At ^ canon_swz(Lc + c_hb)] += acc[bi][bj][1];
+      acc[bi][bj][0] = acc[bi][bj][1] = 0.0;
+    }
+}
+
 template <bool DUMP>
-__global__ void __launch_bounds__(NTHREADS, 4)
+__global__ void __launch_bounds__(NTHREADS, 3)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
                  double* __restrict__ dump_s) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;
+  const int wm = (warp >> 1) & 1, wn = warp & 1;
+  const bool is_producer = warp == NCONSUMERS / 32;
 
   // ---- locate the tuple of this work item (binary search over item_begin) ----
   const long long item = blockIdx.x;
@@ -164,14 +201,18 @@ __global__ void __launch_bounds__(NTHREADS, 4)
     }
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], NTHREADS / 32);
+      mbar_init(&sm.empty[s], NCONSUMERS / 32);
     }
+    mbar_init(&sm.canon_bar, NCONSUMERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
     sm.nsd = nsd < MAX_SDESC ? nsd : MAX_SDESC;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
-  for (int i = tid; i < SUBTILE; i += NTHREADS) sm.canon[i] = 0.0;
+  {
+    double2* c2 = reinterpret_cast<double2*>(sm.canon);
+    for (int i = tid; i < SUBTILE / 2; i += NTHREADS) c2[i] = make_double2(0.0, 0.0);
+  }
   __syncthreads();
   if (tid < 9) {
     const Split sp = make_split(tid);
@@ -188,160 +229,180 @@ __global__ void __launch_bounds__(NTHREADS, 4)
     if (g >= sm.R[q]) g = sm.R[q] - 1;
     sm.eps[q][i] = __ldg(T.eps[q] + g);
   }
-  for (int i = tid; i < sm.nsd; i += NTHREADS) sm.sd[i] = sdescs[T.sdesc_begin + i];
+  if (tid >= 64 && tid < 64 + sm.nsd) {  // staged-layout multipliers of each singles term
+    const SinglesDesc& sd = sdescs[T.sdesc_begin + (tid - 64)];
+    SinglesTerm st;
+    int mt = 1, mv = 1;
+    for (int q = 0; q < 6; q++) {
+      st.wt[q] = 0; st.wv[q] = 0;
+      if (sd.st1[q] != 0) { st.wt[q] = (short)mt; mt *= 4; }
+      else { st.wv[q] = (short)mv; mv *= 4; }
+    }
+    sm.st[tid - 64] = st;
+  }
   __syncthreads();
 
-  // ---- chunk sequence helpers: for s in splits, d in descs(s), q in 0,KQ,2KQ.. ----
-  auto first = [&](Cursor& c) {
-    c.s = 0; c.d = sm.desc_begin[0]; c.q = 0;
-    while (c.s < 9 && c.d == sm.desc_begin[c.s + 1]) c.s++;
-  };
-  auto advance = [&](Cursor& c, int nk4) {
-    c.q += KQ;
-    if (c.q >= nk4) {
-      c.q = 0; c.d++;
-      while (c.s < 9 && c.d == sm.desc_begin[c.s + 1]) c.s++;
-    }
-  };
-  auto issue = [&](const Cursor& c, int fill) {  // producer thread only
-    const ContrDesc dd = descs[c.d];
-    const int st = fill % STAGES;
-    if (fill >= STAGES) mbar_wait(&sm.empty[st], ((fill / STAGES) & 1) ^ 1);
-    const int np = (dd.nk4 - c.q) < KQ ? (dd.nk4 - c.q) : KQ;
-    mbar_arrive_expect_tx(&sm.full[st], (uint32_t)(np * PLANE_DOUBLES * 8));
-    const SplitGeom g = sm.geom[c.s];
-    double* dst = sm.stage + st * STAGE_DOUBLES;
-    for (int p = 0; p < np; p++) {
-      bulk_g2s(dst + p * PLANE_DOUBLES, dd.g1 + g.off1 + (long long)(c.q + p) * g.ps1, BLK_DOUBLES * 8, &sm.full[st]);
-      bulk_g2s(dst + p * PLANE_DOUBLES + BLK_DOUBLES, dd.g2 + g.off2 + (long long)(c.q + p) * g.ps2, BLK_DOUBLES * 8,
-               &sm.full[st]);
-    }
-    return dd.nk4;
-  };
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  // fold the fragment accumulators of split s into the canonical sub-tile, then clear them
-  auto flush = [&](int s) {
-    const Split sp = make_split(s);
-    const int c_pa = 1 << (2 * sp.pa), c_hlo = 1 << (2 * sp.hlo), c_hhi = 1 << (2 * sp.hhi);
-    const int c_hb = 1 << (2 * sp.hb), c_phi = 1 << (2 * sp.phi), c_plo = 1 << (2 * sp.plo);
-    const int Lbase = ((lane >> 2) & 3) * c_pa + ((lane >> 4) & 1) * c_hlo + (wm * 2) * c_hhi +
-                      ((lane & 1) * 2) * c_hb + ((lane >> 1) & 1) * c_phi + (wn * 2) * c_plo;
-#pragma unroll
-    for (int bi = 0; bi < 4; bi++)
-#pragma unroll
-      for (int bj = 0; bj < 4; bj++) {
-        const int L0 = Lbase + (bi & 1) * 2 * c_hlo + (bi >> 1) * c_hhi + (bj & 1) * 2 * c_phi + (bj >> 1) * c_plo;
-        sm.canon[canon_swz(L0)] += acc[bi][bj][0];
-        sm.canon[canon_swz(L0 + c_hb)] += acc[bi][bj][1];
-        acc[bi][bj][0] = acc[bi][bj][1] = 0.0;
-      }
-    __syncthreads();
-  };
-
-  // ---- main loop ----
-  Cursor cc, pc;
-  first(cc);
-  pc = cc;
-  int fills = 0;
-  if (tid == 0) {  // prologue: STAGES-1 chunks in flight
-    for (int i = 0; i < STAGES - 1 && pc.s < 9; i++) {
-      int nk4 = issue(pc, fills);
-      fills++;
-      advance(pc, nk4);
-    }
-  }
-  int it = 0;
-  int cur_s = cc.s;
-  while (cc.s < 9) {
-    if (cc.s != cur_s) {
-      flush(cur_s);
-      cur_s = cc.s;
-    }
-    if (tid == 0 && pc.s < 9) {  // keep the ring full: refill the stage consumed in the previous iteration
-      int nk4 = issue(pc, fills);
-      fills++;
-      advance(pc, nk4);
-    }
-    const ContrDesc dd = descs[cc.d];
-    const int st = it % STAGES;
-    const int np = (dd.nk4 - cc.q) < KQ ? (dd.nk4 - cc.q) : KQ;
-    const unsigned long long negmask = dd.neg ? 0x8000000000000000ull : 0ull;
-    mbar_wait(&sm.full[st], (it / STAGES) & 1);
-    const double* base = sm.stage + st * STAGE_DOUBLES;
-#pragma unroll
-    for (int p = 0; p < KQ; p++) {
-      if (p < np) {
-        const double* pa = base + p * PLANE_DOUBLES + (32 * wm) * 4 + lane;
-        const double* pb = base + p * PLANE_DOUBLES + BLK_DOUBLES + (32 * wn) * 4 + lane;
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          a[i] = __longlong_as_double(__double_as_longlong(pa[i * 32]) ^ negmask);
-          b[i] = pb[i * 32];
+  if (is_producer) {
+    // ===== TMA producer warp: one elected lane streams every plane of every fired contraction, split by split =====
+    if (lane == 0) {
+      int st = 0, ph = 1;   // parity to wait on for a free stage: first pass through the ring never blocks
+      for (int s = 0; s < 9; s++) {
+        const SplitGeom g = sm.geom[s];
+        for (int d = sm.desc_begin[s]; d < sm.desc_begin[s + 1]; d++) {
+          const ContrDesc dd = descs[d];
+          const double* g1 = dd.g1 + g.off1;
+          const double* g2 = dd.g2 + g.off2;
+          for (int q = 0; q < dd.nk4; q++) {
+            mbar_wait(&sm.empty[st], ph);
+            mbar_arrive_expect_tx(&sm.full[st], (uint32_t)(PLANE_DOUBLES * 8));
+            double* dst = sm.ring + st * PLANE_DOUBLES;
+            bulk_g2s(dst, g1, BLK_DOUBLES * 8, &sm.full[st]);
+            bulk_g2s(dst + BLK_DOUBLES, g2, BLK_DOUBLES * 8, &sm.full[st]);
+            g1 += g.ps1;
+            g2 += g.ps2;
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[st]);
-    it++;
-    advance(cc, dd.nk4);
+  } else {
+    // ===== MMA warps =====
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* fa = sm.ring + (32 * wm) * 4 + lane;
+    const double* fb = sm.ring + BLK_DOUBLES + (32 * wn) * 4 + lane;
+    int st = 0, ph = 0, nflush = 0;
+    for (int s = 0; s < 9; s++) {
+      const int d0 = sm.desc_begin[s], d1 = sm.desc_begin[s + 1];
+      if (d0 == d1) continue;
+      for (int d = d0; d < d1; d++) {
+        const int nk4 = __ldg(&descs[d].nk4);
+        const unsigned int neghi = __ldg(&descs[d].neg) ? 0x80000000u : 0u;
+        for (int q = 0; q < nk4; q++) {
+          mbar_wait(&sm.full[st], ph);
+          const double* pa = fa + st * PLANE_DOUBLES;
+          const double* pb = fb + st * PLANE_DOUBLES;
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const double v = pa[i * 32];
+            a[i] = __hiloint2double(__double2hiint(v) ^ neghi, __double2loint(v));   // contraction sign
+            b[i] = pb[i * 32];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.empty[st]);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+      // fold this split's fragments into the canonical sub-tile.  Split-phase ordering between the flushes of
+      // consecutive splits: wait until every warp finished the previous flush, flush, then arrive (no CTA-wide stall).
+      if (nflush > 0) mbar_wait(&sm.canon_bar, (nflush - 1) & 1);
+      switch (s) {
+        case 0: flush_split<0>(acc, sm.canon, lane, wm, wn); break;
+        case 1: flush_split<1>(acc, sm.canon, lane, wm, wn); break;
+        case 2: flush_split<2>(acc, sm.canon, lane, wm, wn); break;
+        case 3: flush_split<3>(acc, sm.canon, lane, wm, wn); break;
+        case 4: flush_split<4>(acc, sm.canon, lane, wm, wn); break;
+        case 5: flush_split<5>(acc, sm.canon, lane, wm, wn); break;
+        case 6: flush_split<6>(acc, sm.canon, lane, wm, wn); break;
+        case 7: flush_split<7>(acc, sm.canon, lane, wm, wn); break;
+        default: flush_split<8>(acc, sm.canon, lane, wm, wn); break;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.canon_bar);
+      nflush++;
+    }
   }
-  if (cur_s < 9) flush(cur_s);
+  __syncthreads();   // all flushes done, ring idle
+  if (is_producer) return;
 
-  // ---- epilogue: singles, denominators, energies ----
+  // ---- epilogue (MMA warps): singles, denominators, energies ----
+  // thread owns canonical elements L = tid + 128*jj : (h3,h2,h1, p6 bit0) fixed by tid, jj = p6hi + 2*p5 + 8*p4
+  const int nsd = sm.nsd;
+  const int i_h3 = tid & 3, i_h2 = (tid >> 2) & 3, i_h1 = (tid >> 4) & 3, i_p6lo = (tid >> 6) & 1;
+  double sing[32];
+#pragma unroll
+  for (int jj = 0; jj < 32; jj++) sing[jj] = 0.0;
+  if (nsd > 0) {
+    // stage t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges
+    for (int e = tid; e < nsd * SD_TERM; e += NCONSUMERS) {
+      const int t = e / SD_TERM, r = e - t * SD_TERM;
+      const SinglesDesc& sd = sdescs[T.sdesc_begin + t];
+      const SinglesTerm& stt = sm.st[t];
+      const bool is_t1 = r < SD_T1;
+      const int rr = is_t1 ? r : r - SD_T1;
+      long long off = 0;
+      bool valid = true;
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        const int w = is_t1 ? stt.wt[q] : stt.wv[q];
+        if (w != 0) {
+          const int g = 4 * sm.b[q] + ((rr / w) & 3);
+          valid = valid && (g < sm.R[q]);
+          off += (long long)g * (is_t1 ? sd.st1[q] : sd.sv2[q]);
+        }
+      }
+      double v = 0.0;
+      if (valid) v = is_t1 ? (sd.neg ? -__ldg(sd.t1 + off) : __ldg(sd.t1 + off)) : __ldg(sd.v2 + off);
+      sm.ring[e] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
+    for (int t = 0; t < nsd; t++) {
+      const SinglesTerm stt = sm.st[t];
+      const double* t1s = sm.ring + t * SD_TERM;
+      const double* v2s = t1s + SD_T1;
+      const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + i_p6lo * stt.wt[3];
+      const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + i_p6lo * stt.wv[3];
+      const int t6 = 2 * stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
+      const int v6 = 2 * stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            sing[c + 2 * b + 8 * a] += t1s[ft + c * t6 + b * t5 + a * t4] * v2s[fv + c * v6 + b * v5 + a * v4];
+    }
+  }
   const double factor = T.factor;
   double e1 = 0.0, e2 = 0.0;
-  const int nsd = sm.nsd;
-  long long tstride[6];
+  const double eh = sm.eps[POS_H1][i_h1] + sm.eps[POS_H2][i_h2] + sm.eps[POS_H3][i_h3];   // (h1+h2)+h3, ccsd_t_dot.F:114
+  const bool hvalid = (4 * sm.b[POS_H3] + i_h3 < sm.R[POS_H3]) && (4 * sm.b[POS_H2] + i_h2 < sm.R[POS_H2]) &&
+                      (4 * sm.b[POS_H1] + i_h1 < sm.R[POS_H1]);
+  const int At = canon_swz(tid);
+  long long tstride[6], obase = 0;
   if (DUMP) {
     long long s = 1;
     for (int q = 0; q < 6; q++) { tstride[q] = s; s *= sm.R[q]; }
+    obase = (4 * sm.b[POS_H3] + i_h3) * tstride[POS_H3] + (4 * sm.b[POS_H2] + i_h2) * tstride[POS_H2] +
+            (4 * sm.b[POS_H1] + i_h1) * tstride[POS_H1];
   }
-  for (int jj = 0; jj < SUBTILE / NTHREADS; jj++) {
-    const int L = tid + NTHREADS * jj;
-    int g[6];
-    bool valid = true;
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-      g[q] = 4 * sm.b[q] + ((L >> (2 * q)) & 3);
-      valid = valid && (g[q] < sm.R[q]);
-    }
-    if (!valid) continue;
-    const double doub = sm.canon[canon_swz(L)];
-    double sing = 0.0;
-    for (int t = 0; t < nsd; t++) {
-      const SinglesDesc& sd = sm.sd[t];
-      long long o1 = 0, o2 = 0;
-#pragma unroll
-      for (int q = 0; q < 6; q++) {
-        o1 += (long long)g[q] * sd.st1[q];
-        o2 += (long long)g[q] * sd.sv2[q];
+  for (int jj = 0; jj < 32; jj++) {
+    const int i_p6 = i_p6lo + 2 * (jj & 1), i_p5 = (jj >> 1) & 3, i_p4 = jj >> 3;
+    const bool valid = hvalid && (4 * sm.b[POS_P6] + i_p6 < sm.R[POS_P6]) && (4 * sm.b[POS_P5] + i_p5 < sm.R[POS_P5]) &&
+                       (4 * sm.b[POS_P4] + i_p4 < sm.R[POS_P4]);
+    if (valid) {
+      const double doub = sm.canon[At ^ canon_swz(128 * jj)];
+      // ccsd_t_dot.F:101-117
+      const double denom_0 = -(sm.eps[POS_P4][i_p4] + sm.eps[POS_P5][i_p5] + sm.eps[POS_P6][i_p6]);
+      const double delta = eh + denom_0;
+      const double denom = doub * factor / delta;
+      e1 += denom * doub;
+      e2 += denom * (doub + sing[jj]);
+      if (DUMP) {
+        const long long o = obase + (4 * sm.b[POS_P6] + i_p6) * tstride[POS_P6] + (4 * sm.b[POS_P5] + i_p5) * tstride[POS_P5] +
+                            (4 * sm.b[POS_P4] + i_p4) * tstride[POS_P4];
+        dump_d[o] = doub;
+        dump_s[o] = sing[jj];
       }
-      const double prod = __ldg(sd.t1 + o1) * __ldg(sd.v2 + o2);
-      sing += sd.neg ? -prod : prod;
-    }
-    // ccsd_t_dot.F:101-117
-    const double denom_0 = -(sm.eps[POS_P4][(L >> 10) & 3] + sm.eps[POS_P5][(L >> 8) & 3] + sm.eps[POS_P6][(L >> 6) & 3]);
-    const double delta = sm.eps[POS_H1][(L >> 4) & 3] + sm.eps[POS_H2][(L >> 2) & 3] + sm.eps[POS_H3][L & 3] + denom_0;
-    const double denom = doub * factor / delta;
-    e1 += denom * doub;
-    e2 += denom * (doub + sing);
-    if (DUMP) {
-      long long o = 0;
-#pragma unroll
-      for (int q = 0; q < 6; q++) o += g[q] * tstride[q];
-      dump_d[o] = doub;
-      dump_s[o] = sing;
     }
   }
 #pragma unroll
@@ -350,10 +411,10 @@ __global__ void __launch_bounds__(NTHREADS, 4)
     e2 += __shfl_xor_sync(0xffffffffu, e2, o);
   }
   if (lane == 0) { sm.red[0][warp] = e1; sm.red[1][warp] = e2; }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
   if (tid == 0) {
     double s1 = 0.0, s2 = 0.0;
-    for (int w = 0; w < NTHREADS / 32; w++) { s1 += sm.red[0][w]; s2 += sm.red[1][w]; }
+    for (int w = 0; w < NCONSUMERS / 32; w++) { s1 += sm.red[0][w]; s2 += sm.red[1][w]; }
     partials[item] = make_double2(s1, s2);
   }
 }
@@ -363,6 +424,8 @@ static void set_fused_attr() {
   if (!done) {
     cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
     cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done = true;
   }
 }

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 using namespace nwc;
+namespace nwc { Engine& compat_engine(); }  // compat_abi.cu
 
 static thread_local std::string g_err;
 #define NWC_TRY(x)                                                                           \
@@ -283,6 +284,27 @@ int nwc_triples_get_stats(nwc_triples_ctx* c, nwc_triples_stats* o, int reset) {
   if (reset) c->eng->stats = EngineStats();
   return 0;
 }
+
+static void fill_stats(const EngineStats& s, nwc_triples_stats* o, double resident) {
+  o->fused_ms = s.fused_ms; o->repack_ms = s.repack_ms;
+  o->fused_launches = s.fused_launches; o->repack_launches = s.repack_launches; o->reduce_launches = s.reduce_launches;
+  o->work_items = s.work_items; o->descs = s.descs; o->tuples = s.tuples; o->flops = s.flops;
+  o->h2d_bytes = (double)s.h2d_bytes; o->d2h_bytes = (double)s.d2h_bytes;
+  o->resident_bytes = resident;
+}
+int nwc_triples_timer_start(nwc_triples_ctx* c) { cudaSetDevice(c->eng->device()); c->eng->timer_start(); return 0; }
+int nwc_triples_timer_stop_ms(nwc_triples_ctx* c, double* ms) { cudaSetDevice(c->eng->device()); *ms = c->eng->timer_stop_ms(); return 0; }
+int nwc_host_register(void* ptr, size_t bytes) { NWC_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
+int nwc_host_unregister(void* ptr) { NWC_TRY(cudaHostUnregister(ptr)); return 0; }
+int nwc_compat_get_stats(nwc_triples_stats* o, int reset) {
+  Engine& e = nwc::compat_engine();
+  fill_stats(e.stats, o, 0.0);
+  if (reset) e.stats = EngineStats();
+  return 0;
+}
+int nwc_compat_set_timing(int on) { nwc::compat_engine().timing = on != 0; return 0; }
+int nwc_compat_timer_start(void) { nwc::compat_engine().timer_start(); return 0; }
+int nwc_compat_timer_stop_ms(double* ms) { *ms = nwc::compat_engine().timer_stop_ms(); return 0; }
 
 int nwc_triples_set_batch_bytes(nwc_triples_ctx* c, size_t bytes) { c->batch_bytes = bytes; return 0; }
 

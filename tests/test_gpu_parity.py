@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 REL_T3 = 1e-11
 ABS_E = 1e-9
-FLOOR = 1e-8   # amplitudes/integrals of the synthetic inputs are O(1e-3..1e-1)
+FLOOR = 1e-6   # nonzero t3 elements of the synthetic inputs are O(1e-5..1e-3); symmetry-zero tiles hold 1e-19 noise
 
 
 def _relmax(a, b):

@@ -6,7 +6,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "microbench_t40"
 t = synth.shape_tiling(name)
 t0 = time.time(); st = synth.random_blocks(t); print("gen", time.time() - t0, "s", flush=True)
 tr = capi.Triples(0); tr.set_state(st); tr.set_timing(True)
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", "3"))):
     tr.stats(reset=True)
     t0 = time.time(); e1, e2 = tr.run(); dt = time.time() - t0
     s = tr.stats()
