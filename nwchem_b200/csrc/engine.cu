@@ -106,9 +106,9 @@ void Engine::add_contraction(int family, int k0, int K7, const OperandView& tsub
   const Split sp = make_split(s);
   const OperandView& g1 = t_is_g1 ? tsub : v2sub;
   const OperandView& g2 = t_is_g1 ? v2sub : tsub;
-  const int n1[3] = {DECL[family][k0][sp.pa], DECL[family][k0][sp.hlo], DECL[family][k0][sp.hhi]};
-  const int n2[3] = {DECL[family][k0][sp.hb], DECL[family][k0][sp.phi], DECL[family][k0][sp.plo]};
-  const int p1[3] = {sp.pa, sp.hlo, sp.hhi}, p2[3] = {sp.hb, sp.phi, sp.plo};
+  const int n1[3] = {DECL[family][k0][sp.g1[0]], DECL[family][k0][sp.g1[1]], DECL[family][k0][sp.g1[2]]};
+  const int n2[3] = {DECL[family][k0][sp.g2[0]], DECL[family][k0][sp.g2[1]], DECL[family][k0][sp.g2[2]]};
+  const int p1[3] = {sp.g1[0], sp.g1[1], sp.g1[2]}, p2[3] = {sp.g2[0], sp.g2[1], sp.g2[2]};
   std::vector<PanelSlot>* c1 = t_is_g1 ? t_cache : v_cache;
   std::vector<PanelSlot>* c2 = t_is_g1 ? v_cache : t_cache;
   if (K7 <= 0) return;

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict
     const int b2 = (int)(blk % nb2); blk /= nb2;
     const int b3 = (int)(blk % nb3); blk /= nb3;
     const int kq = (int)blk;
-    const int x1 = 4 * b1 + (r & 3), x2 = 4 * b2 + ((r >> 2) & 3), x3 = 4 * b3 + (r >> 4), k = 4 * kq + kk;
+    // in-block row r = i1 | (i2&1)<<2 | (i3&1)<<3 | (i2>>1)<<4 | (i3>>1)<<5   (tables.h block_row)
+    const int i1 = r & 3, i2 = ((r >> 2) & 1) | (((r >> 4) & 1) << 1), i3 = ((r >> 3) & 1) | (((r >> 5) & 1) << 1);
+    const int x1 = 4 * b1 + i1, x2 = 4 * b2 + i2, x3 = 4 * b3 + i3, k = 4 * kq + kk;
     double v = 0.0;
     if (x1 < j.X1 && x2 < j.X2 && x3 < j.X3 && k < j.K)
       v = j.scale * __ldg(j.src + x1 * j.s1 + x2 * j.s2 + x3 * j.s3 + k * j.sk);
@@ -97,88 +99,188 @@ void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubl
 // ------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int NCONSUMERS = 128; // 4 MMA warps, warp tile 32x32 of the 64x64 split GEMM
+constexpr int NCONSUMERS = 128; // 4 MMA warps; each owns a fixed quarter of the sub-tile (see tables.h "owner indices")
 constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
 constexpr int STAGES = 10;                           // ring depth; one k4 plane (4 KiB) per stage
 constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block = 4 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
 constexpr int MAX_SDESC = 16;
 constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
-constexpr int SD_PER_PASS = RING_DOUBLES / SD_TERM;                // 18 terms per pass (>= MAX_SDESC)
+static_assert(MAX_SDESC * SD_TERM <= RING_DOUBLES, "singles staging must fit the ring");
 
 struct SplitGeom {          // per (CTA, split): where this sub-tile's base blocks live inside a panel
-  long long off1, ps1;      // G1: offset of (b_hhi,b_hlo,b_pa) block in plane 0; plane stride (doubles)
+  long long off1, ps1;      // G1: offset of the (b3,b2,b1) block in plane 0; plane stride (doubles)
   long long off2, ps2;      // G2
 };
 
 struct SinglesTerm {        // per fired sd_t_s1_K term, derived once per CTA
-  short wt[6];              // multiplier of each physical position in the staged t1 block (0 if absent)
-  short wv[6];              // ... in the staged v2 block
+  short wt[6];              // multiplier (1,4 / 1,4,16,64) of each physical position in the staged t1 / v2 block, 0 if absent
+  short wv[6];
+  signed char sh[6];        // log2 of whichever multiplier is non-zero
+  signed char in_t1[6];     // 1 if t1 carries the position
 };
 
 struct __align__(16) FusedSmem {
-  double canon[SUBTILE];                    // 32 KiB canonical t3 sub-tile (doubles part)
+  double canon[SUBTILE];                    // 32 KiB canonical t3 sub-tile (doubles part); quarter w is private to warp w
   double ring[RING_DOUBLES];                // operand ring
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
-  uint64_t canon_bar;                       // split-phase barrier between the flushes of consecutive splits
   SplitGeom geom[9];
   double eps[6][4];
+  double dp[NCONSUMERS / 32][32];           // -(eps_p4+eps_p5+eps_p6) of each warp's 32 particle triples
   double red[2][NCONSUMERS / 32];
   SinglesTerm st[MAX_SDESC];
   int desc_begin[10];
   int b[6];
   int R[6];
   int nsd;
+  int zero;                                 // run-time 0 (see mma_split)
 };
 
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
 
 // canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; fold the two upper nibbles into the
-// bank-selecting nibble so that the nine fragment->canonical scatter patterns spread over banks.
-// GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b), which lets thread part and unrolled constant part separate.
+// bank-selecting nibble so that the nine fragment<->canonical patterns spread over banks.  GF(2)-linear:
+// swz(a ^ b) == swz(a) ^ swz(b), so the thread part and the unrolled constant part separate into one XOR.
+// Bits 5 (h1 high) and 11 (p4 high) -- the owner bits -- are left in place: warp quarters stay disjoint.
 __host__ __device__ constexpr int canon_swz(int L) { return L ^ ((L >> 4) & 15) ^ ((L >> 8) & 15); }
 
-// split tables as compile-time constants
-template <int S> struct SplitC {
-  static constexpr int pa = 3 + S / 3, hb = S % 3;
-  static constexpr int hlo = (hb == 2) ? 1 : 2;                 // larger position of the remaining holes (lower name)
-  static constexpr int hhi = (hb == 0) ? 1 : 0;
-  static constexpr int phi = (pa == 3) ? 4 : 3;                 // smaller position of the remaining particles
-  static constexpr int plo = (pa == 5) ? 4 : 5;
-};
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
 
-// fold the fragment accumulators of split S into the canonical sub-tile and clear them
-template <int S>
-__device__ __forceinline__ void flush_split(double (&acc)[4][4][2], double* canon, int lane, int wm, int wn) {
-  using C = SplitC<S>;
-  constexpr int c_pa = 1 << (2 * C::pa), c_hlo = 1 << (2 * C::hlo), c_hhi = 1 << (2 * C::hhi);
-  constexpr int c_hb = 1 << (2 * C::hb), c_phi = 1 << (2 * C::phi), c_plo = 1 << (2 * C::plo);
-  // fragment element (warp wm,wn; block bi,bj; lane; j): row m = 32wm+8bi+lane/4 -> (i_pa,i_hlo,i_hhi) = (m&3,(m>>2)&3,m>>4)
-  //                                                      col n = 32wn+8bj+2(lane&3)+j -> (i_hb,i_phi,i_plo)
-  const int Lt = ((lane >> 2) & 3) * c_pa + ((lane >> 4) & 1) * c_hlo + (wm * 2) * c_hhi + ((lane & 1) * 2) * c_hb +
-                 ((lane >> 1) & 1) * c_phi + (wn * 2) * c_plo;
+// number of owner indices in G1 of split s (tables.h): G1 holds p4 iff pa==p4, holds h1 iff hb!=h1
+__device__ __forceinline__ int own1_of(int s) { return ((s >= 6) ? 1 : 0) + ((s % 3 != POS_H1) ? 1 : 0); }
+
+// Move the warp's 16 accumulator blocks between registers (fragment layout of split S) and its private quarter
+// of the canonical sub-tile.  LOAD at the start of a split (the DMMAs then accumulate on top of the running sum:
+// the nine permutations are fused without a single FP64 add), STORE at its end.
+template <int S, bool LOAD>
+__device__ __forceinline__ void xfer_split(double (&acc)[16][2], double* canon, int lane, int wo0, int wo1) {
+  constexpr Split sp = make_split(S);
+  constexpr int RB = 8 >> sp.own1, CB = 2 << sp.own1;
+  constexpr int own2 = 2 - sp.own1;
+  // first row / column block of this warp: the owner bits are the top bits of the block number
+  const int rb0 = (sp.own1 == 0) ? 0 : (sp.own1 == 2) ? (2 * wo0 + 4 * wo1) : (sp.g1[2] == POS_H1 ? 4 * wo0 : 4 * wo1);
+  const int cb0 = (own2 == 0) ? 0 : (own2 == 2) ? (2 * wo0 + 4 * wo1) : (sp.g2[2] == POS_H1 ? 4 * wo0 : 4 * wo1);
+  // fragment element (block rbi,cbi; lane; j): row m = 8(rb0+rbi) + lane/4 ; column n = 8(cb0+cbi) + 2(lane&3) + j
+  asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // keeps the address set-up here instead of hoisted (and spilled) for all 9 splits
+  const int Lt = canon_of_row(sp.g1, 8 * rb0 + (lane >> 2)) | canon_of_row(sp.g2, 8 * cb0 + 2 * (lane & 3));
   const int At = canon_swz(Lt);
 #pragma unroll
-  for (int bi = 0; bi < 4; bi++)
+  for (int rbi = 0; rbi < RB; rbi++)
 #pragma unroll
-    for (int bj = 0; bj < 4; bj++) {
-      const int Lc = (bi & 1) * 2 * c_hlo + (bi >> 1) * c_hhi + (bj & 1) * 2 * c_phi + (bj >> 1) * c_plo;  // constant
-      canon[At ^ canon_swz(Lc)] += acc[bi][bj][0];
-      canon[At ^ canon_swz(Lc + c_hb)] += acc[bi][bj][1];
-      acc[bi][bj][0] = acc[bi][bj][1] = 0.0;
+    for (int cbi = 0; cbi < CB; cbi++) {
+      const int Lc = canon_of_row(sp.g1, 8 * rbi) | canon_of_row(sp.g2, 8 * cbi);   // compile-time
+      const int L1 = canon_of_row(sp.g2, 1);
+      if (LOAD) {
+        acc[rbi * CB + cbi][0] = canon[At ^ canon_swz(Lc)];
+        acc[rbi * CB + cbi][1] = canon[At ^ canon_swz(Lc | L1)];
+      } else {
+        canon[At ^ canon_swz(Lc)] = acc[rbi * CB + cbi][0];
+        canon[At ^ canon_swz(Lc | L1)] = acc[rbi * CB + cbi][1];
+      }
     }
 }
 
-template <bool DUMP>
-__global__ void __launch_bounds__(NTHREADS, 3)
+template <bool LOAD>
+__device__ __forceinline__ void xfer_any(int s, double (&acc)[16][2], double* canon, int lane, int wo0, int wo1) {
+  switch (s) {
+    case 0: xfer_split<0, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 1: xfer_split<1, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 2: xfer_split<2, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 3: xfer_split<3, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 4: xfer_split<4, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 5: xfer_split<5, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 6: xfer_split<6, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 7: xfer_split<7, LOAD>(acc, canon, lane, wo0, wo1); break;
+    default: xfer_split<8, LOAD>(acc, canon, lane, wo0, wo1); break;
+  }
+}
+
+// All K loops of one split whose G1 holds OWN1 owner indices: the warp tile is (8>>OWN1) x (2<<OWN1) blocks of 8x8.
+// Descriptor headers (plane count, sign) are fetched one descriptor ahead; the plane loop itself is
+// wait -> LDS fragments -> sign -> release slot (once the loads have landed) -> 16 DMMA.
+template <int OWN1>
+__device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc* __restrict__ descs, int d0, int d1,
+                                          uint32_t a_base, uint32_t b_base, uint64_t* full, uint64_t* empty, int& st,
+                                          int& ph, int lane, unsigned int zero, unsigned long long& twait, bool timing) {
+  constexpr int RB = 8 >> OWN1, CB = 2 << OWN1;
+  // pin the two fragment base addresses in registers (otherwise they are re-derived from SR_TID every plane)
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_base));
+  asm volatile("mov.u32 %0, %0;" : "+r"(b_base));
+  int2 hdr_next = __ldg(reinterpret_cast<const int2*>(&descs[d0].nk4));
+  for (int d = d0; d < d1; d++) {
+    const int nk4 = hdr_next.x;
+    const unsigned int neghi = hdr_next.y ? 0x80000000u : 0u;
+    if (d + 1 < d1) hdr_next = __ldg(reinterpret_cast<const int2*>(&descs[d + 1].nk4));
+    for (int q = 0; q < nk4; q++) {
+      unsigned long long cw = 0;
+      if (timing) cw = clock64();
+      mbar_wait(&full[st], ph);
+      if (timing) twait += clock64() - cw;
+      const uint32_t off = (uint32_t)(st * PLANE_DOUBLES * 8);
+      double a[RB], b[CB];
+#pragma unroll
+      for (int i = 0; i < RB; i++) a[i] = lds64(a_base + off + i * 256);
+#pragma unroll
+      for (int j = 0; j < CB; j++) b[j] = lds64(b_base + off + j * 256);
+      // contraction sign: flip the sign bit of the smaller fragment set
+      if (RB <= CB) {
+#pragma unroll
+        for (int i = 0; i < RB; i++) a[i] = __hiloint2double(__double2hiint(a[i]) ^ neghi, __double2loint(a[i]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < CB; j++) b[j] = __hiloint2double(__double2hiint(b[j]) ^ neghi, __double2loint(b[j]));
+      }
+#pragma unroll
+      for (int i = 0; i < RB; i++)
+#pragma unroll
+        for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i], b[j]);
+      // Release the ring slot.  mbarrier.arrive may be scheduled right after the loads were *issued*, and the
+      // producer's TMA write can then overtake a still-queued LDS (a real WAR race: ~1e-9 energy noise in ~20 % of
+      // runs).  Making the barrier address depend on every fragment register forces the arrive behind the
+      // completion of all ten loads at the cost of a few LOP3s; `zero` is a run-time 0 the compiler cannot fold.
+      unsigned int dep = 0;
+#pragma unroll
+      for (int i = 0; i < RB; i++) dep ^= (unsigned int)__double2hiint(a[i]);
+#pragma unroll
+      for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j]);
+      dep &= zero;
+      if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[st]) + dep));
+      if (++st == STAGES) { st = 0; ph ^= 1; }
+    }
+  }
+}
+
+// reciprocal to ~1 ulp: MUFU seed (off the FP64 pipe) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
+// per-CTA phase clocks (debug builds of the kernel only): t0 start, t1 setup done, t2 first plane consumed,
+// t3 K loops done (before the CTA barrier), t4 after the barrier, t5 singles staged+accumulated, t6 end,
+// [7] = cycles spent moving accumulators to/from the canonical tile by warp 0
+__device__ unsigned long long* g_phase_buf = nullptr;
+__device__ unsigned int g_phase_cap = 0;
+
+template <bool DUMP, bool TIMING = false>
+__global__ void __launch_bounds__(NTHREADS, 3)   // 128 regs x 160 threads x 3 CTAs (144 would drop to 2 CTAs/SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
                  double* __restrict__ dump_s) {
+  unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (TIMING) tph[0] = clock64();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 1) & 1, wn = warp & 1;
+  const int wo0 = warp & 1, wo1 = (warp >> 1) & 1;   // owner bits: high bit of h1, high bit of p4
   const bool is_producer = warp == NCONSUMERS / 32;
 
   // ---- locate the tuple of this work item (binary search over item_begin) ----
@@ -203,10 +305,10 @@ __global__ void __launch_bounds__(NTHREADS, 3)
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], NCONSUMERS / 32);
     }
-    mbar_init(&sm.canon_bar, NCONSUMERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
     sm.nsd = nsd < MAX_SDESC ? nsd : MAX_SDESC;
+    sm.zero = 0;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
   {
@@ -217,10 +319,10 @@ __global__ void __launch_bounds__(NTHREADS, 3)
   if (tid < 9) {
     const Split sp = make_split(tid);
     SplitGeom g;
-    g.off1 = (((long long)sm.b[sp.hhi] * T.nb[sp.hlo] + sm.b[sp.hlo]) * T.nb[sp.pa] + sm.b[sp.pa]) * BLK_DOUBLES;
-    g.ps1 = (long long)T.nb[sp.pa] * T.nb[sp.hlo] * T.nb[sp.hhi] * BLK_DOUBLES;
-    g.off2 = (((long long)sm.b[sp.plo] * T.nb[sp.phi] + sm.b[sp.phi]) * T.nb[sp.hb] + sm.b[sp.hb]) * BLK_DOUBLES;
-    g.ps2 = (long long)T.nb[sp.hb] * T.nb[sp.phi] * T.nb[sp.plo] * BLK_DOUBLES;
+    g.off1 = (((long long)sm.b[sp.g1[2]] * T.nb[sp.g1[1]] + sm.b[sp.g1[1]]) * T.nb[sp.g1[0]] + sm.b[sp.g1[0]]) * BLK_DOUBLES;
+    g.ps1 = (long long)T.nb[sp.g1[0]] * T.nb[sp.g1[1]] * T.nb[sp.g1[2]] * BLK_DOUBLES;
+    g.off2 = (((long long)sm.b[sp.g2[2]] * T.nb[sp.g2[1]] + sm.b[sp.g2[1]]) * T.nb[sp.g2[0]] + sm.b[sp.g2[0]]) * BLK_DOUBLES;
+    g.ps2 = (long long)T.nb[sp.g2[0]] * T.nb[sp.g2[1]] * T.nb[sp.g2[2]] * BLK_DOUBLES;
     sm.geom[tid] = g;
   }
   if (tid >= 32 && tid < 32 + 24) {  // eps of the sub-tile, index clamped into range (padding never contributes)
@@ -232,15 +334,16 @@ __global__ void __launch_bounds__(NTHREADS, 3)
   if (tid >= 64 && tid < 64 + sm.nsd) {  // staged-layout multipliers of each singles term
     const SinglesDesc& sd = sdescs[T.sdesc_begin + (tid - 64)];
     SinglesTerm st;
-    int mt = 1, mv = 1;
+    int mt = 0, mv = 0;
     for (int q = 0; q < 6; q++) {
       st.wt[q] = 0; st.wv[q] = 0;
-      if (sd.st1[q] != 0) { st.wt[q] = (short)mt; mt *= 4; }
-      else { st.wv[q] = (short)mv; mv *= 4; }
+      if (sd.st1[q] != 0) { st.wt[q] = (short)(1 << mt); st.sh[q] = (signed char)mt; st.in_t1[q] = 1; mt += 2; }
+      else { st.wv[q] = (short)(1 << mv); st.sh[q] = (signed char)mv; st.in_t1[q] = 0; mv += 2; }
     }
     sm.st[tid - 64] = st;
   }
   __syncthreads();
+  if (TIMING) tph[1] = clock64();
 
   if (is_producer) {
     // ===== TMA producer warp: one elected lane streams every plane of every fired contraction, split by split =====
@@ -267,141 +370,152 @@ __global__ void __launch_bounds__(NTHREADS, 3)
     }
   } else {
     // ===== MMA warps =====
-    double acc[4][4][2];
+    // A warp's tile in split s is (8>>own1) x (2<<own1) blocks of 8x8; which blocks follows from the owner bits, so
+    // the warp accumulates the same physical t3 elements in every split and exchanges them with its private
+    // quarter of the canonical tile: LOAD the running sum into the accumulators, run the split's K loops on top,
+    // STORE back.  No FP64 adds, no cross-warp synchronisation.
+    double acc[16][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const double* fa = sm.ring + (32 * wm) * 4 + lane;
-    const double* fb = sm.ring + BLK_DOUBLES + (32 * wn) * 4 + lane;
-    int st = 0, ph = 0, nflush = 0;
+    for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
+    const uint32_t ring_u32 = smem_u32(sm.ring) + (uint32_t)(lane * 8);
+    int st = 0, ph = 0;
+    bool first_split = true;
+    const unsigned int zero_rt = (unsigned int)sm.zero;
     for (int s = 0; s < 9; s++) {
       const int d0 = sm.desc_begin[s], d1 = sm.desc_begin[s + 1];
       if (d0 == d1) continue;
-      for (int d = d0; d < d1; d++) {
-        const int nk4 = __ldg(&descs[d].nk4);
-        const unsigned int neghi = __ldg(&descs[d].neg) ? 0x80000000u : 0u;
-        for (int q = 0; q < nk4; q++) {
-          mbar_wait(&sm.full[st], ph);
-          const double* pa = fa + st * PLANE_DOUBLES;
-          const double* pb = fb + st * PLANE_DOUBLES;
-          double a[4], b[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const double v = pa[i * 32];
-            a[i] = __hiloint2double(__double2hiint(v) ^ neghi, __double2loint(v));   // contraction sign
-            b[i] = pb[i * 32];
-          }
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.empty[st]);
-          if (++st == STAGES) { st = 0; ph ^= 1; }
-        }
+      unsigned long long c0 = 0;
+      if (!first_split) {   // the first split starts from zero accumulators
+        if (TIMING) c0 = clock64();
+        xfer_any<true>(s, acc, sm.canon, lane, wo0, wo1);
+        if (TIMING) tph[7] += clock64() - c0;
       }
-      // fold this split's fragments into the canonical sub-tile.  Split-phase ordering between the flushes of
-      // consecutive splits: wait until every warp finished the previous flush, flush, then arrive (no CTA-wide stall).
-      if (nflush > 0) mbar_wait(&sm.canon_bar, (nflush - 1) & 1);
-      switch (s) {
-        case 0: flush_split<0>(acc, sm.canon, lane, wm, wn); break;
-        case 1: flush_split<1>(acc, sm.canon, lane, wm, wn); break;
-        case 2: flush_split<2>(acc, sm.canon, lane, wm, wn); break;
-        case 3: flush_split<3>(acc, sm.canon, lane, wm, wn); break;
-        case 4: flush_split<4>(acc, sm.canon, lane, wm, wn); break;
-        case 5: flush_split<5>(acc, sm.canon, lane, wm, wn); break;
-        case 6: flush_split<6>(acc, sm.canon, lane, wm, wn); break;
-        case 7: flush_split<7>(acc, sm.canon, lane, wm, wn); break;
-        default: flush_split<8>(acc, sm.canon, lane, wm, wn); break;
-      }
+      first_split = false;
+      // first row / column block of this warp in this split (same rule as xfer_split)
+      const int own1 = own1_of(s);
+      const int o_h1 = (s % 3 != POS_H1);          // h1 sits in G1 ?
+      int rb0, cb0;
+      if (own1 == 0) { rb0 = 0; cb0 = 2 * wo0 + 4 * wo1; }
+      else if (own1 == 2) { rb0 = 2 * wo0 + 4 * wo1; cb0 = 0; }
+      else { rb0 = 4 * (o_h1 ? wo0 : wo1); cb0 = 4 * (o_h1 ? wo1 : wo0); }
+      const uint32_t a_base = ring_u32 + (uint32_t)(rb0 * 256), b_base = ring_u32 + (uint32_t)(BLK_DOUBLES * 8 + cb0 * 256);
+      if (own1 == 1) mma_split<1>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
+      else if (own1 == 0) mma_split<0>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
+      else mma_split<2>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
+      if (TIMING) c0 = clock64();
+      xfer_any<false>(s, acc, sm.canon, lane, wo0, wo1);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.canon_bar);
-      nflush++;
+      if (TIMING) tph[7] += clock64() - c0;
     }
   }
-  __syncthreads();   // all flushes done, ring idle
+  if (TIMING) tph[3] = clock64();
+  __syncthreads();   // every plane consumed: the ring is idle and can stage the singles operands
+  if (TIMING) tph[4] = clock64();
   if (is_producer) return;
 
-  // ---- epilogue (MMA warps): singles, denominators, energies ----
-  // thread owns canonical elements L = tid + 128*jj : (h3,h2,h1, p6 bit0) fixed by tid, jj = p6hi + 2*p5 + 8*p4
+  // ---- epilogue (MMA warps): singles, denominators, energies.  Warp w works on its own quarter:
+  //      L = lane | wo0<<5 | jj<<6 | wo1<<11 ,  lane = (h3,h2,h1lo), jj = p6 + 4*p5 + 16*p4lo ----
   const int nsd = sm.nsd;
-  const int i_h3 = tid & 3, i_h2 = (tid >> 2) & 3, i_h1 = (tid >> 4) & 3, i_p6lo = (tid >> 6) & 1;
+  const int i_h3 = lane & 3, i_h2 = (lane >> 2) & 3, i_h1 = (lane >> 4) | (wo0 << 1);
   double sing[32];
 #pragma unroll
   for (int jj = 0; jj < 32; jj++) sing[jj] = 0.0;
   if (nsd > 0) {
-    // stage t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges
-    for (int e = tid; e < nsd * SD_TERM; e += NCONSUMERS) {
-      const int t = e / SD_TERM, r = e - t * SD_TERM;
-      const SinglesDesc& sd = sdescs[T.sdesc_begin + t];
-      const SinglesTerm& stt = sm.st[t];
-      const bool is_t1 = r < SD_T1;
-      const int rr = is_t1 ? r : r - SD_T1;
-      long long off = 0;
-      bool valid = true;
+    // stage the t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges;
+    // all loads of a batch of nine terms are issued before the first store (one exposed L2 latency per batch)
+    for (int t0 = 0; t0 < nsd; t0 += 9) {
+      double v0[9], v1[9], vt[9];
 #pragma unroll
-      for (int q = 0; q < 6; q++) {
-        const int w = is_t1 ? stt.wt[q] : stt.wv[q];
-        if (w != 0) {
-          const int g = 4 * sm.b[q] + ((rr / w) & 3);
-          valid = valid && (g < sm.R[q]);
-          off += (long long)g * (is_t1 ? sd.st1[q] : sd.sv2[q]);
+      for (int u = 0; u < 9; u++) {
+        v0[u] = v1[u] = vt[u] = 0.0;
+        if (t0 + u < nsd) {
+          const SinglesDesc& sd = sdescs[T.sdesc_begin + t0 + u];
+          const SinglesTerm stt = sm.st[t0 + u];
+          int offv0 = 0, offv1 = 0, offt = 0;
+          bool ok0 = true, ok1 = true, okt = true;
+#pragma unroll
+          for (int q = 0; q < 6; q++) {
+            const int base = 4 * sm.b[q], R = sm.R[q], sh = stt.sh[q];
+            if (stt.in_t1[q]) {
+              const int g = base + ((tid >> sh) & 3);
+              okt = okt && (g < R);
+              offt += g * sd.st1[q];
+            } else {
+              const int ga = base + ((tid >> sh) & 3), gb = base + (((tid + NCONSUMERS) >> sh) & 3);
+              ok0 = ok0 && (ga < R); ok1 = ok1 && (gb < R);
+              offv0 += ga * sd.sv2[q]; offv1 += gb * sd.sv2[q];
+            }
+          }
+          if (ok0) v0[u] = __ldg(sd.v2 + offv0);
+          if (ok1) v1[u] = __ldg(sd.v2 + offv1);
+          if (tid < SD_T1 && okt) { const double x = __ldg(sd.t1 + offt); vt[u] = sd.neg ? -x : x; }
         }
       }
-      double v = 0.0;
-      if (valid) v = is_t1 ? (sd.neg ? -__ldg(sd.t1 + off) : __ldg(sd.t1 + off)) : __ldg(sd.v2 + off);
-      sm.ring[e] = v;
+#pragma unroll
+      for (int u = 0; u < 9; u++)
+        if (t0 + u < nsd) {
+          double* dst = sm.ring + (t0 + u) * SD_TERM;
+          dst[SD_T1 + tid] = v0[u];
+          dst[SD_T1 + tid + NCONSUMERS] = v1[u];
+          if (tid < SD_T1) dst[tid] = vt[u];
+        }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
     for (int t = 0; t < nsd; t++) {
       const SinglesTerm stt = sm.st[t];
       const double* t1s = sm.ring + t * SD_TERM;
       const double* v2s = t1s + SD_T1;
-      const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + i_p6lo * stt.wt[3];
-      const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + i_p6lo * stt.wv[3];
-      const int t6 = 2 * stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
-      const int v6 = 2 * stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
+      const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + (2 * wo1) * stt.wt[5];
+      const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + (2 * wo1) * stt.wv[5];
+      const int t6 = stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
+      const int v6 = stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
-          for (int c = 0; c < 2; c++)
-            sing[c + 2 * b + 8 * a] += t1s[ft + c * t6 + b * t5 + a * t4] * v2s[fv + c * v6 + b * v5 + a * v4];
+          for (int c = 0; c < 4; c++)
+            sing[c + 4 * b + 16 * a] += t1s[ft + c * t6 + b * t5 + a * t4] * v2s[fv + c * v6 + b * v5 + a * v4];
     }
   }
-  const double factor = T.factor;
+  if (TIMING) tph[5] = clock64();
+  {   // particle part of the denominators of this warp: denom_0 = -(d_p4+d_p5+d_p6), ccsd_t_dot.F:105
+    const int p6 = lane & 3, p5 = (lane >> 2) & 3, p4 = (lane >> 4) | (wo1 << 1);
+    sm.dp[warp][lane] = -(sm.eps[POS_P4][p4] + sm.eps[POS_P5][p5] + sm.eps[POS_P6][p6]);
+  }
+  __syncwarp();
   double e1 = 0.0, e2 = 0.0;
   const double eh = sm.eps[POS_H1][i_h1] + sm.eps[POS_H2][i_h2] + sm.eps[POS_H3][i_h3];   // (h1+h2)+h3, ccsd_t_dot.F:114
-  const bool hvalid = (4 * sm.b[POS_H3] + i_h3 < sm.R[POS_H3]) && (4 * sm.b[POS_H2] + i_h2 < sm.R[POS_H2]) &&
-                      (4 * sm.b[POS_H1] + i_h1 < sm.R[POS_H1]);
-  const int At = canon_swz(tid);
-  long long tstride[6], obase = 0;
-  if (DUMP) {
-    long long s = 1;
-    for (int q = 0; q < 6; q++) { tstride[q] = s; s *= sm.R[q]; }
-    obase = (4 * sm.b[POS_H3] + i_h3) * tstride[POS_H3] + (4 * sm.b[POS_H2] + i_h2) * tstride[POS_H2] +
-            (4 * sm.b[POS_H1] + i_h1) * tstride[POS_H1];
-  }
+  const int At = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
+  // padded elements need no mask: their operands are exact zeros, so D = S = 0 and they add 0 to both sums
 #pragma unroll
   for (int jj = 0; jj < 32; jj++) {
-    const int i_p6 = i_p6lo + 2 * (jj & 1), i_p5 = (jj >> 1) & 3, i_p4 = jj >> 3;
-    const bool valid = hvalid && (4 * sm.b[POS_P6] + i_p6 < sm.R[POS_P6]) && (4 * sm.b[POS_P5] + i_p5 < sm.R[POS_P5]) &&
-                       (4 * sm.b[POS_P4] + i_p4 < sm.R[POS_P4]);
-    if (valid) {
-      const double doub = sm.canon[At ^ canon_swz(128 * jj)];
-      // ccsd_t_dot.F:101-117
-      const double denom_0 = -(sm.eps[POS_P4][i_p4] + sm.eps[POS_P5][i_p5] + sm.eps[POS_P6][i_p6]);
-      const double delta = eh + denom_0;
-      const double denom = doub * factor / delta;
-      e1 += denom * doub;
-      e2 += denom * (doub + sing[jj]);
-      if (DUMP) {
-        const long long o = obase + (4 * sm.b[POS_P6] + i_p6) * tstride[POS_P6] + (4 * sm.b[POS_P5] + i_p5) * tstride[POS_P5] +
-                            (4 * sm.b[POS_P4] + i_p4) * tstride[POS_P4];
-        dump_d[o] = doub;
-        dump_s[o] = sing[jj];
+    const double doub = sm.canon[At ^ canon_swz(jj << 6)];
+    const double delta = eh + sm.dp[warp][jj];
+    const double w = doub * fast_rcp(delta);      // D/Delta ; the tuple factor is applied once at the end
+    e1 = fma(w, doub, e1);                        // ccsd_t_dot.F:115
+    e2 = fma(w, doub + sing[jj], e2);             // ccsd_t_dot.F:116
+  }
+  e1 *= T.factor;
+  e2 *= T.factor;
+  if (DUMP) {
+    long long tstride[6], s = 1;
+    for (int q = 0; q < 6; q++) { tstride[q] = s; s *= sm.R[q]; }
+    for (int jj = 0; jj < 32; jj++) {
+      const int idx[6] = {i_h3, i_h2, i_h1, jj & 3, (jj >> 2) & 3, (jj >> 4) | (wo1 << 1)};
+      long long o = 0;
+      bool valid = true;
+      for (int q = 0; q < 6; q++) {
+        const int g = 4 * sm.b[q] + idx[q];
+        valid = valid && (g < sm.R[q]);
+        o += g * tstride[q];
+      }
+      if (valid) {
+        dump_d[o] = sm.canon[At ^ canon_swz(jj << 6)];
+        double sv = 0.0;
+#pragma unroll
+        for (int u = 0; u < 32; u++) if (u == jj) sv = sing[u];
+        dump_s[o] = sv;
       }
     }
   }
@@ -416,7 +530,18 @@ __global__ void __launch_bounds__(NTHREADS, 3)
     double s1 = 0.0, s2 = 0.0;
     for (int w = 0; w < NCONSUMERS / 32; w++) { s1 += sm.red[0][w]; s2 += sm.red[1][w]; }
     partials[item] = make_double2(s1, s2);
+    if (TIMING && g_phase_buf && item < g_phase_cap) {
+      tph[6] = clock64();
+      for (int i = 0; i < 8; i++) g_phase_buf[item * 8 + i] = tph[i];
+    }
   }
+}
+
+static bool g_phase_timing = false;
+void set_phase_timing(unsigned long long* d_buf, unsigned int cap_items) {
+  cudaMemcpyToSymbol(g_phase_buf, &d_buf, sizeof(d_buf));
+  cudaMemcpyToSymbol(g_phase_cap, &cap_items, sizeof(cap_items));
+  g_phase_timing = d_buf != nullptr;
 }
 
 static void set_fused_attr() {
@@ -426,6 +551,8 @@ static void set_fused_attr() {
     cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
     cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done = true;
   }
 }
@@ -434,6 +561,11 @@ void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_desc
                   double2* d_partials, long long total_items, cudaStream_t stream) {
   if (total_items <= 0) return;
   set_fused_attr();
+  if (g_phase_timing) {
+    fused_kernel<false, true><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs,
+                                                                                             d_sdescs, d_partials, nullptr, nullptr);
+    return;
+  }
   fused_kernel<false><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs, d_sdescs,
                                                                                      d_partials, nullptr, nullptr);
 }

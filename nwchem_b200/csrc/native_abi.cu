@@ -306,6 +306,26 @@ int nwc_compat_set_timing(int on) { nwc::compat_engine().timing = on != 0; retur
 int nwc_compat_timer_start(void) { nwc::compat_engine().timer_start(); return 0; }
 int nwc_compat_timer_stop_ms(double* ms) { *ms = nwc::compat_engine().timer_stop_ms(); return 0; }
 
+// debugging aid (not part of the public header): per-CTA phase clocks of the next launches; cap_items = 0 turns it off
+int nwc_debug_phase_timing(unsigned long long* host_out, unsigned int cap_items, int fetch) {
+  static unsigned long long* d_buf = nullptr;
+  static unsigned int cap = 0;
+  if (fetch) {
+    if (!d_buf) return 1;
+    NWC_TRY(cudaDeviceSynchronize());
+    NWC_TRY(cudaMemcpy(host_out, d_buf, (size_t)cap * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  if (d_buf) { cudaFree(d_buf); d_buf = nullptr; }
+  cap = cap_items;
+  if (cap_items) {
+    NWC_TRY(cudaMalloc((void**)&d_buf, (size_t)cap_items * 8 * sizeof(unsigned long long)));
+    NWC_TRY(cudaMemset(d_buf, 0, (size_t)cap_items * 8 * sizeof(unsigned long long)));
+  }
+  nwc::set_phase_timing(d_buf, cap_items);
+  return 0;
+}
+
 int nwc_triples_set_batch_bytes(nwc_triples_ctx* c, size_t bytes) { c->batch_bytes = bytes; return 0; }
 
 int nwc_triples_nccl_unique_id(char id128[128]) {

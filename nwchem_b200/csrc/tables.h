@@ -6,8 +6,8 @@
 // order therefore says which physical position each permuted name occupies.
 //
 // A "split" s = 3*(pa-3)+hb partitions the six indices into
-//     G1 = (pa ; h_lo, h_hi)   one particle + the two holes != hb   (rows    of the split GEMM)
-//     G2 = (hb ; p_hi, p_lo)   one hole + the two particles != pa   (columns of the split GEMM)
+//     G1 = {pa, the two holes != hb}       (rows    of the split GEMM)
+//     G2 = {hb, the two particles != pa}   (columns of the split GEMM)
 // sd_t_d2_K : t2sub is the G1 operand, v2sub the G2 operand (K = p7);
 // sd_t_d1_K : v2sub is the G1 operand, t2sub the G2 operand (K = h7).
 // Each of the nine d2 kernels and each of the nine d1 kernels lands in a different split.
@@ -52,22 +52,51 @@ inline int pos_of(int family, int k0, int name) {
   return -1;
 }
 
+// Owner indices: the HIGH bit of physical h1 (position 2) and of physical p4 (position 5) select the MMA warp,
+// so every warp owns the same 1024 t3 elements of the sub-tile in all nine splits (no cross-warp hazards on
+// the canonical tile).  Inside a 64-row base block the three indices (i1,i2,i3) of a group are ordered
+// non-owners first (ascending position), owners last (h1 before p4), and mapped to the row number
+//     m = i1 | (i2&1)<<2 | (i3&1)<<3 | (i2>>1)<<4 | (i3>>1)<<5
+// which puts the owner bits in m[5] (one owner) or m[5:4] (two owners): a warp's rows are contiguous.
 struct Split {
-  int pa, hlo, hhi;  // G1 = (pa; hlo, hhi)   physical positions
-  int hb, phi, plo;  // G2 = (hb; phi, plo)
+  int pa, hb;
+  int g1[3];   // G1 = one particle + two holes : physical positions in in-block order (i1,i2,i3)
+  int g2[3];   // G2 = one hole + two particles
+  int own1;    // number of owner indices in G1 (0,1,2); G2 holds 2-own1
 };
-// "lo/hi" follow the index NAME number: h1<h2<h3 (positions 2,1,0), p4<p5<p6 (positions 5,4,3)
-NWC_HD inline Split make_split(int s) {
-  Split sp;
+NWC_HD constexpr bool is_owner_pos(int q) { return q == POS_H1 || q == POS_P4; }
+NWC_HD constexpr Split make_split(int s) {
+  Split sp{};
   sp.pa = 3 + s / 3;
   sp.hb = s % 3;
-  int hs[2], ps[2], nh = 0, np = 0;
-  for (int q = 2; q >= 0; q--) if (q != sp.hb) hs[nh++] = q;   // descending position = ascending name
-  for (int q = 3; q <= 5; q++) if (q != sp.pa) ps[np++] = q;   // ascending position = descending name
-  sp.hlo = hs[0]; sp.hhi = hs[1];
-  sp.phi = ps[0]; sp.plo = ps[1];
+  int a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+  int na = 0, nb = 0;
+  a[na++] = sp.pa;
+  for (int q = 0; q < 3; q++) if (q != sp.hb) a[na++] = q;
+  b[nb++] = sp.hb;
+  for (int q = 3; q < 6; q++) if (q != sp.pa) b[nb++] = q;
+  // non-owners ascending, then h1, then p4
+  int n = 0;
+  for (int q = 0; q < 6; q++)
+    for (int i = 0; i < 3; i++) if (a[i] == q && !is_owner_pos(q)) sp.g1[n++] = q;
+  for (int i = 0; i < 3; i++) if (a[i] == POS_H1) sp.g1[n++] = POS_H1;
+  for (int i = 0; i < 3; i++) if (a[i] == POS_P4) sp.g1[n++] = POS_P4;
+  n = 0;
+  for (int q = 0; q < 6; q++)
+    for (int i = 0; i < 3; i++) if (b[i] == q && !is_owner_pos(q)) sp.g2[n++] = q;
+  for (int i = 0; i < 3; i++) if (b[i] == POS_H1) sp.g2[n++] = POS_H1;
+  for (int i = 0; i < 3; i++) if (b[i] == POS_P4) sp.g2[n++] = POS_P4;
+  sp.own1 = (sp.pa == POS_P4 ? 1 : 0) + (sp.hb != POS_H1 ? 1 : 0);
   return sp;
 }
-NWC_HD inline int split_id(int pa, int hb) { return 3 * (pa - 3) + hb; }
+NWC_HD constexpr int block_row(int i1, int i2, int i3) {
+  return i1 | ((i2 & 1) << 2) | ((i3 & 1) << 3) | ((i2 >> 1) << 4) | ((i3 >> 1) << 5);
+}
+// contribution of in-block row (or column) number m of group g[3] to the canonical linear index sum_q i_q * 4^q
+NWC_HD constexpr int canon_of_row(const int g[3], int m) {
+  const int i1 = m & 3, i2 = ((m >> 2) & 1) | (((m >> 4) & 1) << 1), i3 = ((m >> 3) & 1) | (((m >> 5) & 1) << 1);
+  return (i1 << (2 * g[0])) | (i2 << (2 * g[1])) | (i3 << (2 * g[2]));
+}
+NWC_HD constexpr int split_id(int pa, int hb) { return 3 * (pa - 3) + hb; }
 
 }  // namespace nwc
