@@ -101,12 +101,17 @@ void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubl
 // ------------------------------------------------------------------------------------------------
 constexpr int NCONSUMERS = 128; // 4 MMA warps; each owns a fixed quarter of the sub-tile (see tables.h "owner indices")
 constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
-constexpr int STAGES = 10;                           // ring depth; one k4 plane (4 KiB) per stage
+#ifndef NWC_CTAS_PER_SM
+#define NWC_CTAS_PER_SM 3
+#endif
+// 3 CTAs/SM: 128 registers, 10-stage ring (75 KiB smem);  4 CTAs/SM: 96 registers, 5-stage ring (55 KiB smem)
+constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 5 : 10;   // ring depth; one k4 plane (4 KiB) per stage
 constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block = 4 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
 constexpr int MAX_SDESC = 16;
 constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
-static_assert(MAX_SDESC * SD_TERM <= RING_DOUBLES, "singles staging must fit the ring");
+constexpr int SD_PER_PASS = (RING_DOUBLES / SD_TERM) < 9 ? (RING_DOUBLES / SD_TERM) : 9;   // terms staged per pass
+static_assert(SD_PER_PASS >= 1, "ring too small for the singles staging");
 
 struct SplitGeom {          // per (CTA, split): where this sub-tile's base blocks live inside a panel
   long long off1, ps1;      // G1: offset of the (b3,b2,b1) block in plane 0; plane stride (doubles)
@@ -271,7 +276,7 @@ __device__ unsigned long long* g_phase_buf = nullptr;
 __device__ unsigned int g_phase_cap = 0;
 
 template <bool DUMP, bool TIMING = false>
-__global__ void __launch_bounds__(NTHREADS, 3)   // 128 regs x 160 threads x 3 CTAs (144 would drop to 2 CTAs/SM)
+__global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
                  double* __restrict__ dump_s) {
@@ -423,12 +428,14 @@ __global__ void __launch_bounds__(NTHREADS, 3)   // 128 regs x 160 threads x 3 C
   if (nsd > 0) {
     // stage the t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges;
     // all loads of a batch of nine terms are issued before the first store (one exposed L2 latency per batch)
-    for (int t0 = 0; t0 < nsd; t0 += 9) {
-      double v0[9], v1[9], vt[9];
+    for (int t0 = 0; t0 < nsd; t0 += SD_PER_PASS) {
+      const int nt = (nsd - t0) < SD_PER_PASS ? (nsd - t0) : SD_PER_PASS;
+      if (t0 > 0) asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");   // previous pass fully consumed
+      double v0[SD_PER_PASS], v1[SD_PER_PASS], vt[SD_PER_PASS];
 #pragma unroll
-      for (int u = 0; u < 9; u++) {
+      for (int u = 0; u < SD_PER_PASS; u++) {
         v0[u] = v1[u] = vt[u] = 0.0;
-        if (t0 + u < nsd) {
+        if (u < nt) {
           const SinglesDesc& sd = sdescs[T.sdesc_begin + t0 + u];
           const SinglesTerm stt = sm.st[t0 + u];
           int offv0 = 0, offv1 = 0, offt = 0;
@@ -452,30 +459,49 @@ __global__ void __launch_bounds__(NTHREADS, 3)   // 128 regs x 160 threads x 3 C
         }
       }
 #pragma unroll
-      for (int u = 0; u < 9; u++)
-        if (t0 + u < nsd) {
-          double* dst = sm.ring + (t0 + u) * SD_TERM;
+      for (int u = 0; u < SD_PER_PASS; u++)
+        if (u < nt) {
+          double* dst = sm.ring + u * SD_TERM;
           dst[SD_T1 + tid] = v0[u];
           dst[SD_T1 + tid + NCONSUMERS] = v1[u];
           if (tid < SD_T1) dst[tid] = vt[u];
         }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
-    for (int t = 0; t < nsd; t++) {
-      const SinglesTerm stt = sm.st[t];
-      const double* t1s = sm.ring + t * SD_TERM;
-      const double* v2s = t1s + SD_T1;
-      const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + (2 * wo1) * stt.wt[5];
-      const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + (2 * wo1) * stt.wv[5];
-      const int t6 = stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
-      const int v6 = stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
+      asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
+      // FP64 ALU instructions share the pipe with the DMMAs of the other CTAs on this SM, and every isolated
+      // DFMA that lands between two DMMAs costs about one DMMA slot.  So: pull the operands of 16 elements into
+      // registers first, then issue the 16 DFMAs back to back.
+      for (int t = 0; t < nt; t++) {
+        const SinglesTerm stt = sm.st[t0 + t];
+        const double* t1s = sm.ring + t * SD_TERM;
+        const double* v2s = t1s + SD_T1;
+        const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + (2 * wo1) * stt.wt[5];
+        const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + (2 * wo1) * stt.wv[5];
+        const int t6 = stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
+        const int v6 = stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
+        // t1 carries exactly one particle index: over (p6,p5,p4lo) it takes at most four values tv[k]
+        const int tstep = t6 | t5 | t4;
+        double tv[4];
 #pragma unroll
-      for (int a = 0; a < 2; a++)
+        for (int k = 0; k < 4; k++) tv[k] = t1s[ft + k * tstep];
 #pragma unroll
-        for (int b = 0; b < 4; b++)
+        for (int a = 0; a < 2; a++) {
+          double vv[16];
 #pragma unroll
-          for (int c = 0; c < 4; c++)
-            sing[c + 4 * b + 16 * a] += t1s[ft + c * t6 + b * t5 + a * t4] * v2s[fv + c * v6 + b * v5 + a * v4];
+          for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) vv[c + 4 * b] = v2s[fv + c * v6 + b * v5 + a * v4];
+          if (t6) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[e & 3], vv[e], sing[e + 16 * a]);
+          } else if (t5) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[e >> 2], vv[e], sing[e + 16 * a]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[a], vv[e], sing[e + 16 * a]);
+          }
+        }
+      }
     }
   }
   if (TIMING) tph[5] = clock64();
@@ -487,15 +513,29 @@ __global__ void __launch_bounds__(NTHREADS, 3)   // 128 regs x 160 threads x 3 C
   double e1 = 0.0, e2 = 0.0;
   const double eh = sm.eps[POS_H1][i_h1] + sm.eps[POS_H2][i_h2] + sm.eps[POS_H3][i_h3];   // (h1+h2)+h3, ccsd_t_dot.F:114
   const int At = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
-  // padded elements need no mask: their operands are exact zeros, so D = S = 0 and they add 0 to both sums
+  // padded elements need no mask: their operands are exact zeros, so D = S = 0 and they add 0 to both sums.
+  // Batches of eight elements: loads first, then the FP64 work as dense groups of independent instructions.
+  double e2s = 0.0;   // sum w*S ; E(T) part = e1 + e2s
 #pragma unroll
-  for (int jj = 0; jj < 32; jj++) {
-    const double doub = sm.canon[At ^ canon_swz(jj << 6)];
-    const double delta = eh + sm.dp[warp][jj];
-    const double w = doub * fast_rcp(delta);      // D/Delta ; the tuple factor is applied once at the end
-    e1 = fma(w, doub, e1);                        // ccsd_t_dot.F:115
-    e2 = fma(w, doub + sing[jj], e2);             // ccsd_t_dot.F:116
+  for (int j0 = 0; j0 < 32; j0 += 8) {
+    double dd[8], rr[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      dd[u] = sm.canon[At ^ canon_swz((j0 + u) << 6)];
+      rr[u] = sm.dp[warp][j0 + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) rr[u] = eh + rr[u];                 // Delta, ccsd_t_dot.F:114
+#pragma unroll
+    for (int u = 0; u < 8; u++) rr[u] = fast_rcp(rr[u]);
+#pragma unroll
+    for (int u = 0; u < 8; u++) rr[u] = dd[u] * rr[u];              // w = D/Delta (tuple factor applied once at the end)
+#pragma unroll
+    for (int u = 0; u < 8; u++) e1 = fma(rr[u], dd[u], e1);         // ccsd_t_dot.F:115
+#pragma unroll
+    for (int u = 0; u < 8; u++) e2s = fma(rr[u], sing[j0 + u], e2s);   // ccsd_t_dot.F:116 minus :115
   }
+  e2 = e1 + e2s;
   e1 *= T.factor;
   e2 *= T.factor;
   if (DUMP) {

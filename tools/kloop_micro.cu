@@ -25,15 +25,40 @@ __device__ __forceinline__ double lds64(uint32_t a) { double v; asm volatile("ld
 constexpr int PLANE = 512;
 template <int STAGES, int PADKB> struct SmemT { double pad[PADKB * 128]; double ring[STAGES * PLANE]; uint64_t full[STAGES], empty[STAGES]; };
 
-template <int MODE, int STAGES, int PADKB, int MINB>
-__global__ void __launch_bounds__(160, MINB) kloop(const double* __restrict__ panel, long long panel_planes, int planes, double* out) {
+template <int MODE, int STAGES, int PADKB, int MINB, int EPI>
+__global__ void __launch_bounds__(192, MINB) kloop(const double* __restrict__ panel, long long panel_planes, int planes, double* out) {
   extern __shared__ __align__(128) unsigned char raw[];
   using Smem = SmemT<STAGES, PADKB>;
   Smem& sm = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  for (int i = tid; i < STAGES * PLANE; i += 160) sm.ring[i] = 1e-3 * (i % 7);
+  for (int i = tid; i < STAGES * PLANE; i += 192) sm.ring[i] = 1e-3 * (i % 7);
+  for (int i = tid; i < PADKB * 128; i += 192) sm.pad[i] = 1.0;
   __syncthreads();
+  if (warp == 5) {   // EPI: 0 idle, 1 isolated DFMAs (LDS -> DFMA -> LDS ...), 2 bursts of 16 DFMAs after 16 LDS, 3 pure DFMA chain
+    if (EPI == 0) return;
+    double accd[16]; for (int i = 0; i < 16; i++) accd[i] = i;
+    const uint32_t pbase = smem_u32(sm.pad) + lane * 8;
+    const int iters = planes * 2;   // ~ as long as the MMA warps run
+    for (int it = 0; it < iters; it++) {
+      if (EPI == 1) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) { double x = lds64(pbase + ((it * 16 + k) & 255) * 256); accd[0] = fma(accd[0], x, 1.0); }
+      } else if (EPI == 2) {
+        double x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = lds64(pbase + ((it * 16 + k) & 255) * 256);
+#pragma unroll
+        for (int k = 0; k < 16; k++) accd[k] = fma(accd[k], x[k], 1.0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) accd[k] = fma(accd[k], 1.0000001, 1.0);
+      }
+    }
+    double s = 0; for (int i = 0; i < 16; i++) s += accd[i];
+    if (s == 123.456) out[0] = s;
+    return;
+  }
   if (warp == 4) {
     if (MODE >= 2 && lane == 0) {
       int st = 0, ph = 1;
@@ -78,17 +103,17 @@ __global__ void __launch_bounds__(160, MINB) kloop(const double* __restrict__ pa
   if (s == 123.456) out[0] = s;
 }
 
-template <int MODE, int STAGES, int PADKB, int MINB> float run(const double* panel, long long pp, int planes, double* out, int ctas) {
+template <int MODE, int STAGES, int PADKB, int MINB, int EPI> float run(const double* panel, long long pp, int planes, double* out, int ctas) {
   using Smem = SmemT<STAGES, PADKB>;
-  auto kfn = kloop<MODE, STAGES, PADKB, MINB>;
+  auto kfn = kloop<MODE, STAGES, PADKB, MINB, EPI>;
   CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   CK(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 160, sizeof(Smem)));
+  int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 192, sizeof(Smem)));
   if (nb != MINB) printf(" [occupancy %d != %d] ", nb, MINB);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  kfn<<<ctas, 160, sizeof(Smem)>>>(panel, pp, planes, out); CK(cudaDeviceSynchronize());
+  kfn<<<ctas, 192, sizeof(Smem)>>>(panel, pp, planes, out); CK(cudaDeviceSynchronize());
   float best = 1e30f;
-  for (int r = 0; r < 3; r++) { CK(cudaEventRecord(e0)); kfn<<<ctas, 160, sizeof(Smem)>>>(panel, pp, planes, out); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = ms < best ? ms : best; }
+  for (int r = 0; r < 3; r++) { CK(cudaEventRecord(e0)); kfn<<<ctas, 192, sizeof(Smem)>>>(panel, pp, planes, out); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = ms < best ? ms : best; }
   CK(cudaGetLastError());
   return best;
 }
@@ -101,17 +126,10 @@ int main() {
   double* out; CK(cudaMalloc(&out, 64));
   auto fl = [&](int ctas) { return 2.0 * 64 * 64 * 4 * (double)planes * ctas; };
   printf("{");
-  printf("\"c3_s10_dmma\": %.2f", fl(sms*24) / run<0,10,32,3>(panel, pp, planes, out, sms*24) * 1e-9);
-  printf(", \"c3_s10_tma\": %.2f", fl(sms*24) / run<3,10,32,3>(panel, pp, planes, out, sms*24) * 1e-9);
-  printf(", \"c3_s5_tma\": %.2f", fl(sms*24) / run<3,5,52,3>(panel, pp, planes, out, sms*24) * 1e-9);
-  printf(", \"c2_s10_tma\": %.2f", fl(sms*16) / run<3,10,70,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c2_s8_tma\": %.2f", fl(sms*16) / run<3,8,78,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c2_s6_tma\": %.2f", fl(sms*16) / run<3,6,86,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c2_s16_tma\": %.2f", fl(sms*16) / run<3,16,46,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c2_s10_lds\": %.2f", fl(sms*16) / run<1,10,70,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c2_s10_mbar\": %.2f", fl(sms*16) / run<2,10,70,2>(panel, pp, planes, out, sms*16) * 1e-9);
-  printf(", \"c4_s5_tma\": %.2f", fl(sms*32) / run<3,5,32,4>(panel, pp, planes, out, sms*32) * 1e-9);
-  printf(", \"c1_s20_tma\": %.2f", fl(sms*8) / run<3,20,130,1>(panel, pp, planes, out, sms*8) * 1e-9);
+  printf("\"c3_noepi\": %.2f", fl(sms*24) / run<3,10,32,3,0>(panel, pp, planes, out, sms*24) * 1e-9);
+  printf(", \"c3_epi_isolated_dfma\": %.2f", fl(sms*24) / run<3,10,32,3,1>(panel, pp, planes, out, sms*24) * 1e-9);
+  printf(", \"c3_epi_burst16_dfma\": %.2f", fl(sms*24) / run<3,10,32,3,2>(panel, pp, planes, out, sms*24) * 1e-9);
+  printf(", \"c3_epi_pure_dfma\": %.2f", fl(sms*24) / run<3,10,32,3,3>(panel, pp, planes, out, sms*24) * 1e-9);
   printf("}\n");
   return 0;
 }
