@@ -70,13 +70,10 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_sample(steps=1):
-    """Bounded CPU sample of the same workload: tuple 1 of the microbench restricted to a p4 slab of 2
-    (all 9 sd_t_d2 + 9 sd_t_d1 + 9 sd_t_s1 kernels of ccsd_t_kernels_omp.F restated + ccsd_t_dot), all host threads."""
+def _cpu_slab(P4, steps):
     from oracle import oracle as ora
-    ora.lib()
     rng = np.random.default_rng(20240229)
-    T, P4 = 40, 2
+    T = 40
     dims = (T, T, T, T, T, P4)  # h3d,h2d,h1d,p6d,p5d,p4d
     n = T ** 5 * P4
     t3d = np.zeros(n); t3s = np.zeros(n)
@@ -93,10 +90,21 @@ def cpu_sample(steps=1):
             ora.kernel(2, kk, dims, T, t3d, t2a, v2a); flops += 2.0 * n * T
             ora.kernel(1, kk, dims, T, t3d, t2b, v2b); flops += 2.0 * n * T
             ora.kernel(0, kk, dims, 1, t3s, t1, v2s); flops += 2.0 * n
-    dt = time.perf_counter() - t0
-    return dict(seconds=dt, flops=flops, gflops=flops / dt * 1e-9, cores=ora.num_threads(),
-                sample=f"tuple 1 of {WORKLOAD} restricted to a p4 slab of {P4}/{T}: 9 sd_t_d2 + 9 sd_t_d1 + 9 sd_t_s1 "
-                       f"kernel calls at tilesize {T} ({flops:.3e} FLOP per step), OpenMP on all host threads")
+    return time.perf_counter() - t0, flops
+
+
+def cpu_sample(steps=1, target_s=15.0):
+    """Bounded CPU sample of the same workload: tuple 1 of the microbench restricted to a p4 slab
+    (all 9 sd_t_d2 + 9 sd_t_d1 + 9 sd_t_s1 kernels of ccsd_t_kernels_omp.F restated), all host threads.
+    The slab width is calibrated so that one step is about `target_s` seconds of CPU work."""
+    from oracle import oracle as ora
+    ora.lib()
+    dt, fl = _cpu_slab(1, 1)                      # calibration: slab of 1
+    P4 = int(max(1, min(12, round(target_s / max(dt, 1e-3)))))
+    dt, fl = _cpu_slab(P4, steps)
+    return dict(seconds=dt, flops=fl, gflops=fl / dt * 1e-9, cores=ora.num_threads(),
+                sample=f"tuple 1 of {WORKLOAD} restricted to a p4 slab of {P4}/40: 9 sd_t_d2 + 9 sd_t_d1 + 9 sd_t_s1 "
+                       f"kernel calls at tilesize 40 ({fl / steps:.3e} FLOP per step, {dt / steps:.1f} s), OpenMP on all host threads")
 
 
 def main():
@@ -119,11 +127,9 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        for _ in range(max(a.warmup, 0) and 1):
-            cpu_sample(1)
-        r = cpu_sample(max(1, a.steps))
+        r = cpu_sample(max(1, min(a.steps, 3)), target_s=12.0)
         line = {"impl": "reference", "metric": "(T) FP64 GFLOP/s", "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] / max(1, a.steps) * 1e3,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["seconds"] / max(1, min(a.steps, 3)) * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},

@@ -1,13 +1,13 @@
 // Hand-written sm_100a kernels of libnwc_triples.
 //
 //  repack_kernel : strided source block -> blocked K4 panel (the reference's TCE_SORT_4 + our layout, one pass)
-//  fused_kernel  : one CTA = one 4^6 sub-tile of the t3 tile of one (p4,p5,p6,h1,h2,h3) tile tuple.
-//                  For each of the nine index splits it runs the concatenated-K GEMM of every fired
-//                  sd_t_d2_K / sd_t_d1_K contraction of that split on FP64 tensor cores (DMMA.8x8x4),
-//                  operands staged by cp.async.bulk (TMA, SASS UBLKCP) through a 3-stage mbarrier ring,
-//                  folds the nine fragment layouts into one canonical sub-tile kept in shared memory,
-//                  adds the singles, applies factor/denominator and reduces E[T], E(T) with warp
-//                  shuffles.  The t3 tile never exists in HBM.
+//  fused_kernel  : one CTA (4 MMA warps + 1 TMA producer warp) = one 4^6 sub-tile of the t3 tile of one
+//                  (p4,p5,p6,h1,h2,h3) tile tuple.  For each of the nine index splits it runs the concatenated-K GEMM
+//                  of every fired sd_t_d2_K / sd_t_d1_K contraction of that split on FP64 tensor cores (DMMA.8x8x4),
+//                  operands staged by cp.async.bulk (TMA, SASS UBLKCP) through a 10-stage mbarrier ring; each warp
+//                  keeps the running sum of ITS quarter of the sub-tile in a canonical shared-memory copy and seeds
+//                  the accumulators of the next split from it (nine permutations fused with no FP64 add); then the
+//                  singles, factor/denominator and the E[T], E(T) reduction.  The t3 tile never exists in HBM.
 //  reduce_kernel : deterministic per-tuple sum of the per-sub-tile partial energies.
 //
 // Reference semantics: src/tce/ccsd_t/ccsd_t_kernels_omp.F (27 kernels), ccsd_t_dot.F:101-124 (energy).

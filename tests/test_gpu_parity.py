@@ -181,8 +181,9 @@ def test_microbench_t40_properties():
     tr = capi.Triples(0)
     tr.set_state(st)
     e1, e2, pt = tr.run(per_task=True)
-    f1, f2, pt2 = tr.run(per_task=True)
-    assert (e1, e2) == (f1, f2) and np.array_equal(pt, pt2)   # bitwise reproducible
+    for _ in range(12):   # bitwise reproducible run to run (this caught a ring WAR race that hit ~1 run in 6)
+        f1, f2, pt2 = tr.run(per_task=True)
+        assert (e1, e2) == (f1, f2) and np.array_equal(pt, pt2)
     a, b = 0.5, 3.0
     st2 = synth.BlockStores(t, st.t1_hash, st.t1 * b, st.t2_hash, st.t2 * a, st.v2_hash, st.v2)
     tr.set_state(st2)
