@@ -138,6 +138,8 @@ def main():
         print(json.dumps(line))
         return
 
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("NWC_BENCH_WATCHDOG_S", "900")), exit=True)   # never hang a GPU box
     import torch
     import torch.distributed as dist
     from nwchem_b200 import capi, synth
@@ -213,15 +215,16 @@ def main():
                 capi.host_register(arr); pinned.append(arr)
             except Exception:
                 pass
-        capi.lib().nwc_triples_set_local_rank(local)
+        import ctypes
+        capi.lib().nwc_triples_set_local_rank(ctypes.c_long(local))
         for _ in range(min(a.warmup, 1)):
-            capi.ccsd_t_gpu(st)
+            capi.ccsd_t_gpu(st, icuda=max(world, local + 1))
         capi.compat_stats(reset=True)
         barrier()
         t0 = time.perf_counter()
         nrep = max(1, min(a.steps, 3))
         for _ in range(nrep):
-            c1, c2, _ = capi.ccsd_t_gpu(st)
+            c1, c2, _ = capi.ccsd_t_gpu(st, icuda=max(world, local + 1))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         cs = capi.compat_stats()
