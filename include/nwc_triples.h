@@ -124,6 +124,17 @@ int nwc_triples_create(nwc_triples_ctx **out, int device);
 int nwc_triples_destroy(nwc_triples_ctx *ctx);
 /* copies the tiling tables and uploads the three block stores into HBM (replicated per GPU) */
 int nwc_triples_set_state(nwc_triples_ctx *ctx, const nwc_tce_state *st);
+/* Sharded V2 for shapes whose <pp||hp> class does not fit one HBM (replaces the ga_get of
+ * get_block.F:79-81 by NVLink peer reads): block i of the V2 offset table is owned by rank i % nranks and
+ * st->v2 holds THIS rank's blocks only (table order, compacted); T1/T2 stay replicated.  After set_state_sharded
+ * every rank publishes nwc_triples_v2_ipc_handle (64 bytes), the host all-gathers them and calls
+ * nwc_triples_v2_open_peers(handles[nranks*64]). */
+int nwc_triples_set_state_sharded(nwc_triples_ctx *ctx, const nwc_tce_state *st, int rank, int nranks);
+int nwc_triples_v2_ipc_handle(nwc_triples_ctx *ctx, char handle64[64]);
+int nwc_triples_v2_open_peers(nwc_triples_ctx *ctx, const char *handles);
+/* same-process alternative (several contexts in one process): exchange raw device pointers instead of IPC handles */
+void *nwc_triples_v2_shard_ptr(nwc_triples_ctx *ctx);
+int nwc_triples_v2_set_peer_ptr(nwc_triples_ctx *ctx, int rank, void *dev_ptr);
 /* task list of ccsd_t_neword.F (7 Integers per task: p4b,p5b,p6b,h1b,h2b,h3b,weight), heaviest first */
 Integer nwc_triples_num_tasks(nwc_triples_ctx *ctx);
 int nwc_triples_task_list(nwc_triples_ctx *ctx, Integer *klist7);

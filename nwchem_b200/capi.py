@@ -48,6 +48,9 @@ def lib() -> C.CDLL:
         _lib.nwc_triples_destroy.argtypes = [C.c_void_p]
         _lib.nwc_triples_set_state.argtypes = [C.c_void_p, C.POINTER(TceState)]
         _lib.nwc_triples_task_list.argtypes = [C.c_void_p, PL]
+        _lib.nwc_triples_set_state_sharded.argtypes = [C.c_void_p, C.POINTER(TceState), C.c_int, C.c_int]
+        _lib.nwc_triples_v2_ipc_handle.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.nwc_triples_v2_open_peers.argtypes = [C.c_void_p, C.c_char_p]
         _lib.nwc_triples_run.argtypes = [C.c_void_p, L, L, L, PD, PD]
         _lib.nwc_triples_run_tuple.argtypes = [C.c_void_p, PL, PD, PD, PD]
         _lib.nwc_triples_set_timing.argtypes = [C.c_void_p, C.c_int]
@@ -148,6 +151,29 @@ class Triples:
         s, keep = make_state(st)
         _check(lib().nwc_triples_set_state(self._h, C.byref(s)), "nwc_triples_set_state")
         self.t = st.t
+
+    def set_state_sharded(self, st_shard, rank: int, world: int):
+        """st_shard.v2 holds only this rank's V2 blocks (see synth.shard_v2); tables are the full ones."""
+        s, keep = make_state(st_shard)
+        _check(lib().nwc_triples_set_state_sharded(self._h, C.byref(s), rank, world), "nwc_triples_set_state_sharded")
+        self.t = st_shard.t
+
+    def v2_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().nwc_triples_v2_ipc_handle(self._h, buf), "nwc_triples_v2_ipc_handle")
+        return buf.raw
+
+    def v2_shard_ptr(self) -> int:
+        lib().nwc_triples_v2_shard_ptr.restype = C.c_void_p
+        lib().nwc_triples_v2_shard_ptr.argtypes = [C.c_void_p]
+        return int(lib().nwc_triples_v2_shard_ptr(self._h) or 0)
+
+    def v2_set_peer_ptr(self, rank: int, ptr: int):
+        lib().nwc_triples_v2_set_peer_ptr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _check(lib().nwc_triples_v2_set_peer_ptr(self._h, rank, C.c_void_p(ptr)), "nwc_triples_v2_set_peer_ptr")
+
+    def v2_open_peers(self, handles: bytes):
+        _check(lib().nwc_triples_v2_open_peers(self._h, handles), "nwc_triples_v2_open_peers")
 
     @property
     def num_tasks(self) -> int:

@@ -59,9 +59,37 @@ struct nwc_triples_ctx {
   size_t batch_bytes = (size_t)8 << 30;
   ncclComm_t comm = nullptr;
   int nranks = 1;
+  // sharded V2: block i of the V2 offset table lives on rank i % v2_nshards, compacted in table order;
+  // remote shards are mapped with CUDA IPC and read over NVLink by the repack kernel / singles staging.
+  int v2_nshards = 1, v2_rank = 0;
+  std::vector<Integer> v2_shard_off;        // per table index: offset inside its owner's shard
+  std::vector<double*> v2_peer;             // per rank: base of that rank's shard as seen from this process
+  std::vector<char> v2_peer_opened;
 };
 
 namespace {
+
+// position of `key` in a TCE offset table (1-based), -1 if absent
+Integer hash_index(const Integer* hash, Integer key) {
+  Integer n = hash[0], lo = 1, hi = n;
+  while (lo <= hi) {
+    Integer mid = (lo + hi) >> 1;
+    if (hash[mid] == key) return mid;
+    if (hash[mid] < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+const double* v2_block(const nwc_triples_ctx* c, Integer key, const char* what) {
+  const HostState& S = c->S;
+  if (c->v2_nshards <= 1) return c->d_v2 + hash_lookup_or_die(S.v2_hash, key, what);
+  const Integer idx = hash_index(S.v2_hash.data(), key);
+  if (idx < 0) { printf("nwc_triples: %s: block key %ld not found\n", what, key); fflush(stdout); exit(1); }
+  const int owner = (int)((idx - 1) % c->v2_nshards);
+  const double* base = c->v2_peer[owner];
+  if (!base) { printf("nwc_triples: V2 shard of rank %d is not mapped (nwc_triples_v2_open_peers)\n", owner); fflush(stdout); exit(1); }
+  return base + c->v2_shard_off[idx - 1];
+}
 
 struct NativeSink {
   nwc_triples_ctx* c;
@@ -75,7 +103,7 @@ struct NativeSink {
     t.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
     t.stride[N_H1] = 1; t.stride[N_P4] = S.rg(r.h1b);
     // V2 block <p5 p6||h2 h3> stored (p5,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,p5)
-    v.base = c->d_v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
+    v.base = v2_block(c, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.stride[N_P5] = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
     for (int k = 0; k < 9; k++)
@@ -96,7 +124,7 @@ struct NativeSink {
       sign = 1.0;
     }
     // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
-    v.base = c->d_v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");
+    v.base = v2_block(c, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.kstride = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
     std::vector<PanelSlot> tc, vc;
@@ -118,7 +146,7 @@ struct NativeSink {
       sign = 1.0;
     }
     // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161)
-    v.base = c->d_v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");
+    v.base = v2_block(c, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
     v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
     std::vector<PanelSlot> tc, vc;
@@ -190,6 +218,8 @@ int nwc_triples_destroy(nwc_triples_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->eng->device());
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (size_t r = 0; r < c->v2_peer.size(); r++)
+    if (c->v2_peer_opened[r] && c->v2_peer[r]) cudaIpcCloseMemHandle(c->v2_peer[r]);
   cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_evl); cudaFree(c->d_red);
   delete c->eng;
   delete c;
@@ -205,7 +235,72 @@ int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
   if (upload(&c->d_v2, &c->n_v2, st->v2, store_size(st->v2_hash, S, 3), c->eng)) return 1;
   size_t ne;
   if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
+  c->v2_nshards = 1; c->v2_rank = 0;
   build_task_list(S, c->klist);
+  return 0;
+}
+
+// Sharded variant: st->v2 points at THIS rank's shard only (its blocks, table order, compacted).
+int nwc_triples_set_state_sharded(nwc_triples_ctx* c, const nwc_tce_state* st, int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  c->S.load_tables(st);
+  const HostState& S = c->S;
+  if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
+  if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
+  // shard offsets of every block (all ranks compute the same table)
+  const Integer n = S.v2_hash[0];
+  const Integer total = (Integer)store_size(st->v2_hash, S, 3);
+  c->v2_shard_off.assign((size_t)n, 0);
+  std::vector<Integer> fill((size_t)nranks, 0);
+  for (Integer i = 0; i < n; i++) {
+    const Integer off = S.v2_hash[n + 1 + i], next = (i + 1 < n) ? S.v2_hash[n + 2 + i] : total;
+    const int owner = (int)(i % nranks);
+    c->v2_shard_off[(size_t)i] = fill[owner];
+    fill[owner] += next - off;
+  }
+  if (upload(&c->d_v2, &c->n_v2, st->v2, (size_t)fill[rank], c->eng)) return 1;
+  size_t ne;
+  if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
+  c->v2_nshards = nranks; c->v2_rank = rank;
+  c->v2_peer.assign((size_t)nranks, nullptr);
+  c->v2_peer_opened.assign((size_t)nranks, 0);
+  c->v2_peer[rank] = c->d_v2;
+  build_task_list(S, c->klist);
+  return 0;
+}
+
+// CUDA IPC handle (64 bytes) of this rank's V2 shard; the host all-gathers them (MPI/GA in NWChem)
+int nwc_triples_v2_ipc_handle(nwc_triples_ctx* c, char handle64[64]) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  cudaIpcMemHandle_t h;
+  NWC_TRY(cudaIpcGetMemHandle(&h, c->d_v2));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+// map every peer's shard (handles = nranks x 64 bytes, rank order); peer reads then go over NVLink
+int nwc_triples_v2_open_peers(nwc_triples_ctx* c, const char* handles) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  for (int r = 0; r < c->v2_nshards; r++) {
+    if (r == c->v2_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    NWC_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->v2_peer[(size_t)r] = (double*)p;
+    c->v2_peer_opened[(size_t)r] = 1;
+  }
+  return 0;
+}
+
+// same-process alternative to the IPC exchange (several contexts in one process, tests): device pointer of this
+// context's shard, and direct registration of a peer's shard pointer
+void* nwc_triples_v2_shard_ptr(nwc_triples_ctx* c) { return c->d_v2; }
+int nwc_triples_v2_set_peer_ptr(nwc_triples_ctx* c, int rank, void* dev_ptr) {
+  if (rank < 0 || rank >= c->v2_nshards) { g_err = "bad peer rank"; return 1; }
+  c->v2_peer[(size_t)rank] = (double*)dev_ptr;
   return 0;
 }
 

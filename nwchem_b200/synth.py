@@ -116,3 +116,14 @@ SHAPES = {
 def shape_tiling(name: str, tilesize: int | None = None, seed: int = 20240229) -> tl.Tiling:
     s = SHAPES[name]
     return tl.make_tiling(s["occ"], s["virt"], tilesize or s["tilesize"], True, seed)
+
+
+def shard_v2(st: BlockStores, rank: int, world: int) -> BlockStores:
+    """The V2 shard of `rank`: block i of the offset table belongs to rank i % world; the shard keeps its blocks in
+    table order, compacted.  Offset tables stay the full ones (every rank derives the same shard offsets)."""
+    h = st.v2_hash
+    n = int(h[0])
+    offs = [int(h[1 + n + i]) for i in range(n)] + [len(st.v2)]
+    parts = [st.v2[offs[i]:offs[i + 1]] for i in range(n) if i % world == rank]
+    v2 = np.concatenate(parts) if parts else np.zeros(0)
+    return BlockStores(st.t, st.t1_hash, st.t1, st.t2_hash, st.t2, st.v2_hash, np.ascontiguousarray(v2))

@@ -157,6 +157,26 @@ def test_static_partition_sums_to_total(oracle, h2o_c2v):
     assert abs(sum(p[0] for p in parts) - e1) <= 1e-13 and abs(sum(p[1] for p in parts) - e2) <= 1e-13
 
 
+def test_sharded_v2_two_contexts_one_gpu(oracle, h2o_c2v):
+    """Sharded V2 addressing (block i -> rank i % 2, compacted shards, peer pointers): two contexts on one GPU stand
+    in for two ranks; each runs its half of the task list reading the other's shard.  The IPC/NVLink flavour of the
+    same path is exercised by tools/nccl_smoke.py --sharded on a multi-GPU box."""
+    st = h2o_c2v
+    ref = oracle.ccsd_t(st)
+    ctx = []
+    for r in range(2):
+        tr = capi.Triples(0)
+        tr.set_state_sharded(synth.shard_v2(st, r, 2), r, 2)
+        ctx.append(tr)
+    ctx[0].v2_set_peer_ptr(1, ctx[1].v2_shard_ptr())
+    ctx[1].v2_set_peer_ptr(0, ctx[0].v2_shard_ptr())
+    parts = [ctx[r].run(first=r, stride=2) for r in range(2)]
+    for tr in ctx:
+        tr.close()
+    assert abs(parts[0][0] + parts[1][0] - ref["e1"]) <= 1e-12
+    assert abs(parts[0][1] + parts[1][1] - ref["e2"]) <= 1e-12
+
+
 def test_tile_size_invariance_gpu_tile40_vs_oracle_tile10(oracle):
     """Full-size tiles on the GPU (virtual tile 40, occupied tile 14) against the oracle at tilesize 10:
     E[T]/E(T) are tile-size invariant for antisymmetric amplitudes, so this checks big ragged-free tiles
