@@ -116,13 +116,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--strong", action="store_true", help="one task list dealt over the ranks (fixed total work) instead of one copy per rank")
+    ap.add_argument("--sharded", action="store_true", help="shard the V2 store over the ranks; remote blocks are read over NVLink (CUDA IPC)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     peak, peak_how = fp64_peak_tflops()
-    cfg = {"workload": f"{a.workload}: o=v=40 alpha orbitals, tilesize 40, random T1/T2/V2 tiles, RHF-restricted, 2 tile tuples",
-           "tilesize": 40, "tuples_per_step_per_gpu": 2,
-           "l2": "operand panels touched per step (1.4 GB) exceed the 126 MB L2; no explicit flush"}
+    if a.workload == WORKLOAD:
+        cfg = {"workload": f"{a.workload}: o=v=40 alpha orbitals, tilesize 40, random T1/T2/V2 tiles, RHF-restricted, 2 tile tuples",
+               "tilesize": 40, "tuples_per_step_per_gpu": 2,
+               "l2": "operand panels touched per step (1.4 GB) exceed the 126 MB L2; no explicit flush"}
+    else:
+        from nwchem_b200 import synth as _s
+        sh = _s.SHAPES[a.workload]
+        cfg = {"workload": f"{a.workload}: alpha occ/virt {sh['occ']}/{sh['virt']}, tilesize {sh['tilesize']}, random tiles, RHF-restricted",
+               "tilesize": sh["tilesize"], "v2": "sharded over ranks, NVLink peer reads" if a.sharded else "replicated",
+               "partition": "strong: heaviest-first task list dealt round-robin" if a.strong else "weak: one task list per rank",
+               "l2": "operand panels per tuple exceed the 126 MB L2; no explicit flush"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -154,9 +164,16 @@ def main():
         torch.cuda.synchronize()
 
     t = synth.shape_tiling(a.workload)
-    st = synth.random_blocks(t, seed=20240229 + rank)
+    st = synth.random_blocks(t, seed=20240229 + (0 if (a.strong or a.sharded) else rank))
     tr = capi.Triples(local)
-    tr.set_state(st)
+    if a.sharded and world > 1:
+        tr.set_state_sharded(synth.shard_v2(st, rank, world), rank, world)
+        mine = torch.tensor(list(tr.v2_ipc_handle()), dtype=torch.uint8, device="cuda")
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        tr.v2_open_peers(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    else:
+        tr.set_state(st)
     if world > 1:  # the library's own communicator: rank 0's id is broadcast with the torch plumbing
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -165,7 +182,7 @@ def main():
         tr.nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
     def step():
-        e1, e2 = tr.run()
+        e1, e2 = tr.run(first=rank, stride=world) if a.strong else tr.run()
         if world > 1:
             e1, e2 = tr.allreduce(e1, e2)   # replaces ga_dgop (ccsd_t.F:297)
         return e1, e2
@@ -206,7 +223,7 @@ def main():
 
     # ---- e2e through the reference-facing Tier-1 surface (host buffers), rank-local ----
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and a.workload == WORKLOAD and not a.strong:
         for arr in (st.t1, st.t2, st.v2):
             arr.setflags(write=True)
         pinned = []
@@ -246,7 +263,7 @@ def main():
                "seconds": r["seconds"]}
     if rank == 0:
         line = {"metric": "(T) FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong" if a.strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "wall_s_per_step": ms_max / a.steps * 1e-3, "flops_per_step": flops_all / a.steps,
                 "frac_of_fp64_peak": value * 1e-3 / (peak * world), "energy": list(e),
