@@ -67,6 +67,10 @@ void compute_en_(double *factor, double *energy, double *eval_h1, double *eval_h
 
 /* not in the reference: tell the library this process's rank on its node when util_my_smp_index() is not linked */
 void nwc_triples_set_local_rank(Integer local_rank);
+/* Upload policy of the sd_t_*_cuda_ calls.  Default 0: a call returns only when its host operands may be freed or
+ * overwritten (the reference's contract).  1: the caller promises that PINNED operands stay untouched until
+ * compute_en_ returns, so their copies run as asynchronous DMA overlapped with the caller's next sort. */
+void nwc_compat_set_async_uploads(int on);
 /* validation aid: like compute_en_, but also writes the two t3 tiles T3(h3,h2,h1,p6,p5,p4) to host arrays */
 void nwc_compute_en_dump_(double *factor, double *energy, double *eval_h1, double *eval_h2, double *eval_h3,
                           double *eval_p4, double *eval_p5, double *eval_p6, Integer *h1d, Integer *h2d, Integer *h3d,

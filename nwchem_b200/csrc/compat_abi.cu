@@ -14,6 +14,14 @@ long g_local_rank = -1;
 int g_R[6];          // task tuple ranges, physical order
 bool g_have_R = false;
 
+bool g_async_uploads = false;   // caller promises pinned sources stay untouched until compute_en_ returns
+
+// Under that promise an operand passed again (same host pointer and length) within the tuple is the same data:
+// the device copy and the repacked panels are reused.  The reference re-uploads the same sorted block for each
+// of the up to nine kernels one operand pair fires (ccsd_t_doubles_gpu.F:357-715).
+struct Uploaded { const double* host; size_t n; const double* dev; std::vector<PanelSlot> panels; };
+std::vector<Uploaded> g_uploaded;
+
 long local_rank() {
   if (g_local_rank >= 0) return g_local_rank;
   if (util_my_smp_index) return util_my_smp_index();
@@ -47,15 +55,37 @@ void open_tuple(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer*
   }
   memcpy(g_R, R, sizeof(R));
   g_have_R = true;
+  g_uploaded.clear();
   e.begin_tuple(R);
 }
 
-const double* to_device(const double* host, size_t n) {
+const double* to_device(const double* host, size_t n, std::vector<PanelSlot>** panels = nullptr) {
   Engine& e = eng();
+  if (panels) *panels = nullptr;
+  if (g_async_uploads) {
+    for (auto& u : g_uploaded)
+      if (u.host == host && u.n == n) { if (panels) *panels = &u.panels; return u.dev; }
+  }
   double* d = (double*)e.arena().alloc(n * sizeof(double));
-  // pageable source: returns once the source has been staged, so the caller may free it (MA_POP_STACK)
+  // Pageable source: cudaMemcpyAsync returns once the source has been staged, so the caller may free it right
+  // away (MA_POP_STACK, ccsd_t_doubles_gpu.F:723-726).  A pinned (cudaHostRegister'ed) source is read by DMA later:
+  // unless the caller opted into asynchronous uploads the copy is completed before returning.
   NWC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, e.stream()));
+  if (!g_async_uploads) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost)
+      NWC_CUDA(cudaStreamSynchronize(e.stream()));
+    else
+      cudaGetLastError();
+  }
   e.stats.h2d_bytes += n * sizeof(double);
+  if (g_async_uploads) {
+    if (g_uploaded.capacity() < 4096) g_uploaded.reserve(4096);   // panel-cache pointers must stay valid
+    if (g_uploaded.size() < 4096) {
+      g_uploaded.push_back(Uploaded{host, n, d, {}});
+      if (panels) *panels = &g_uploaded.back().panels;
+    }
+  }
   return d;
 }
 
@@ -90,12 +120,13 @@ void d1(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* h7d, Integer*
   const Integer K = *h7d;
   check_dims(1, k0, d);
   OperandView t, v;
-  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_P5] * d[N_H1]));         // t2sub(h7,p4,p5,h1)
+  std::vector<PanelSlot>*tc, *vc;
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_P5] * d[N_H1]), &tc);    // t2sub(h7,p4,p5,h1)
   t.kstride = 1; t.stride[N_P4] = K; t.stride[N_P5] = K * d[N_P4]; t.stride[N_H1] = K * d[N_P4] * d[N_P5];
-  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * K));         // v2sub(h3,h2,p6,h7)
+  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * K), &vc);    // v2sub(h3,h2,p6,h7)
   v.stride[N_H3] = 1; v.stride[N_H2] = d[N_H3]; v.stride[N_P6] = d[N_H3] * d[N_H2];
   v.kstride = d[N_H3] * d[N_H2] * d[N_P6];
-  eng().add_contraction(1, k0, (int)K, t, v);
+  eng().add_contraction(1, k0, (int)K, t, v, 1.0, tc, vc);
 }
 
 void d2(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, Integer* p7d,
@@ -105,11 +136,12 @@ void d2(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer*
   const Integer K = *p7d;
   check_dims(2, k0, d);
   OperandView t, v;
-  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_H1] * d[N_H2]));         // t2sub(p7,p4,h1,h2)
+  std::vector<PanelSlot>*tc, *vc;
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_H1] * d[N_H2]), &tc);    // t2sub(p7,p4,h1,h2)
   t.kstride = 1; t.stride[N_P4] = K; t.stride[N_H1] = K * d[N_P4]; t.stride[N_H2] = K * d[N_P4] * d[N_H1];
-  v.base = to_device(v2sub, (size_t)(K * d[N_H3] * d[N_P6] * d[N_P5]));         // v2sub(p7,h3,p6,p5)
+  v.base = to_device(v2sub, (size_t)(K * d[N_H3] * d[N_P6] * d[N_P5]), &vc);    // v2sub(p7,h3,p6,p5)
   v.kstride = 1; v.stride[N_H3] = K; v.stride[N_P6] = K * d[N_H3]; v.stride[N_P5] = K * d[N_H3] * d[N_P6];
-  eng().add_contraction(2, k0, (int)K, t, v);
+  eng().add_contraction(2, k0, (int)K, t, v, 1.0, tc, vc);
 }
 
 void finish(double* factor, double* energy, double* eval_h1, double* eval_h2, double* eval_h3, double* eval_p4,
@@ -143,16 +175,20 @@ void finish(double* factor, double* energy, double* eval_h1, double* eval_h2, do
   }
   energy[0] = out[0];
   energy[1] = out[1];
+  g_uploaded.clear();
 }
 }  // namespace
 
 namespace nwc {
 Engine& compat_engine() { return eng(); }
+void compat_set_async_uploads(bool on) { g_async_uploads = on; }
+void compat_forget_uploads() { g_uploaded.clear(); }   // host buffers are about to be reused with new contents
 }
 
 extern "C" {
 
 void nwc_triples_set_local_rank(Integer r) { g_local_rank = r; }
+void nwc_compat_set_async_uploads(int on) { g_async_uploads = on != 0; }
 
 int check_device_(Integer* icuda) { return local_rank() < *icuda ? 1 : 0; }  // hybrid.c:24-28
 

@@ -8,8 +8,39 @@
 #include <cstring>
 
 using namespace nwc;
+namespace nwc { Engine& compat_engine(); void compat_set_async_uploads(bool on); void compat_forget_uploads(); }
 
 namespace {
+
+// Pinned bump arena for the sorted T1/T2 operands of one tuple.  Every sorted block gets fresh pinned memory, so
+// (i) its upload is asynchronous DMA overlapping the host sort of the next block and (ii) the promise behind
+// nwc_compat_set_async_uploads(1) holds: an operand is never modified between the call that passes it and
+// compute_en_, which lets the library recognise the same block passed again for each fired kernel.  When the arena
+// wraps, in-flight copies are drained and the library is told to forget the host pointers it has seen.
+struct PinnedScratch {
+  double* base = nullptr;
+  size_t cap = 0, off = 0;
+  double* acquire(size_t n) {
+    n = (n + 31) & ~(size_t)31;
+    if (cap == 0) {
+      const char* e = getenv("NWC_PINNED_MB");
+      cap = (size_t)(e && *e ? atol(e) : 1024) * (1u << 20) / sizeof(double);
+    }
+    if (n > cap) { if (base) { NWC_CUDA(cudaStreamSynchronize(compat_engine().stream())); cudaFreeHost(base); base = nullptr; } cap = n; }
+    if (!base) { NWC_CUDA(cudaMallocHost((void**)&base, cap * sizeof(double))); off = 0; }
+    if (off + n > cap) {   // wrap: nothing may still be reading, and cached identities are void
+      NWC_CUDA(cudaStreamSynchronize(compat_engine().stream()));
+      compat_forget_uploads();
+      off = 0;
+    }
+    double* p = base + off;
+    off += n;
+    return p;
+  }
+  void submitted() {}
+  void tuple_done() { off = 0; }   // compute_en_ has synchronised the stream
+};
+PinnedScratch g_scratch;
 
 // sorted(i,j,k,l order, l fastest) = factor * unsorted(a,b,c,d order, d fastest): tce_sort_4 semantics
 void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integer d, int i, int j, int k, int l,
@@ -19,12 +50,12 @@ void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integ
   Integer ostride[4];  // stride in `out` of input index q
   Integer s = 1;
   for (int q = 3; q >= 0; q--) { ostride[perm[q]] = s; s *= jd[perm[q]]; }
-  Integer id[4];
-  for (id[0] = 0; id[0] < a; id[0]++)
-    for (id[1] = 0; id[1] < b; id[1]++)
-      for (id[2] = 0; id[2] < c; id[2]++) {
-        const double* src = in + d * (id[2] + c * (id[1] + b * id[0]));
-        double* dst = out + id[0] * ostride[0] + id[1] * ostride[1] + id[2] * ostride[2];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (Integer i0 = 0; i0 < a; i0++)
+    for (Integer i1 = 0; i1 < b; i1++)
+      for (Integer i2 = 0; i2 < c; i2++) {
+        const double* src = in + d * (i2 + c * (i1 + b * i0));
+        double* dst = out + i0 * ostride[0] + i1 * ostride[1] + i2 * ostride[2];
         for (Integer x = 0; x < d; x++) dst[x * ostride[3]] = factor * src[x];
       }
 }
@@ -32,13 +63,13 @@ void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integ
 struct CompatSink {
   const HostState& S;
   const nwc_tce_state* st;
-  std::vector<double> a_sort, b_sort;
+  double* a_sort = nullptr;
 
   void singles(const Row& r, Integer p4b_1, Integer h1b_1, Integer p5b_2, Integer p6b_2, Integer h2b_2, Integer h3b_2,
                const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rh1 = S.rg(r.h1b);
     const double* blk = st->t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
-    a_sort.resize((size_t)(rp4 * rh1));
+    a_sort = g_scratch.acquire((size_t)(rp4 * rh1));
     for (Integer p = 0; p < rp4; p++)      // TCE_SORT_2(...,2,1): stored (p4,h1) h1 fastest -> t1sub(p4,h1)
       for (Integer h = 0; h < rh1; h++) a_sort[p + rp4 * h] = blk[h + rh1 * p];
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
@@ -47,18 +78,19 @@ struct CompatSink {
     static const fn F[9] = {sd_t_s1_1_cuda_, sd_t_s1_2_cuda_, sd_t_s1_3_cuda_, sd_t_s1_4_cuda_, sd_t_s1_5_cuda_,
                             sd_t_s1_6_cuda_, sd_t_s1_7_cuda_, sd_t_s1_8_cuda_, sd_t_s1_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, nullptr, a_sort.data(), const_cast<double*>(v));
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
+    g_scratch.submitted();
   }
 
   void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rp5 = S.rg(r.p5b), rh1 = S.rg(r.h1b), rh7 = S.rg(h7b);
-    a_sort.resize((size_t)(rp4 * rp5 * rh1 * rh7));
+    a_sort = g_scratch.acquire((size_t)(rp4 * rp5 * rh1 * rh7));
     if (h7b < r.h1b) {  // ccsd_t_doubles_gpu.F:282-289
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[3], am[2]), "t2");
-      sort4(blk, a_sort.data(), rp4, rp5, rh7, rh1, 4, 2, 1, 3, -1.0);
+      sort4(blk, a_sort, rp4, rp5, rh7, rh1, 4, 2, 1, 3, -1.0);
     } else {            // :291-298
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
-      sort4(blk, a_sort.data(), rp4, rp5, rh1, rh7, 3, 2, 1, 4, 1.0);
+      sort4(blk, a_sort, rp4, rp5, rh1, rh7, 3, 2, 1, 4, 1.0);
     }
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");  // :315-327
     Integer h1d = rh1, h2d = S.rg(r.h2b), h3d = S.rg(r.h3b), h7d = rh7, p4d = rp4, p5d = rp5, p6d = S.rg(r.p6b);
@@ -66,18 +98,19 @@ struct CompatSink {
     static const fn F[9] = {sd_t_d1_1_cuda_, sd_t_d1_2_cuda_, sd_t_d1_3_cuda_, sd_t_d1_4_cuda_, sd_t_d1_5_cuda_,
                             sd_t_d1_6_cuda_, sd_t_d1_7_cuda_, sd_t_d1_8_cuda_, sd_t_d1_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &h7d, &p4d, &p5d, &p6d, nullptr, a_sort.data(), const_cast<double*>(v));
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &h7d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
+    g_scratch.submitted();
   }
 
   void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rp7 = S.rg(p7b), rh1 = S.rg(r.h1b), rh2 = S.rg(r.h2b);
-    a_sort.resize((size_t)(rp4 * rp7 * rh1 * rh2));
+    a_sort = g_scratch.acquire((size_t)(rp4 * rp7 * rh1 * rh2));
     if (p7b < r.p4b) {  // ccsd_t_doubles_gpu.F:942-949
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[1], am[0], am[2], am[3]), "t2");
-      sort4(blk, a_sort.data(), rp7, rp4, rh1, rh2, 4, 3, 2, 1, -1.0);
+      sort4(blk, a_sort, rp7, rp4, rh1, rh2, 4, 3, 2, 1, -1.0);
     } else {            // :950-957
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
-      sort4(blk, a_sort.data(), rp4, rp7, rh1, rh2, 4, 3, 1, 2, 1.0);
+      sort4(blk, a_sort, rp4, rp7, rh1, rh2, 4, 3, 1, 2, 1.0);
     }
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");  // :964-976
     Integer h1d = rh1, h2d = rh2, h3d = S.rg(r.h3b), p4d = rp4, p5d = S.rg(r.p5b), p6d = S.rg(r.p6b), p7d = rp7;
@@ -85,7 +118,8 @@ struct CompatSink {
     static const fn F[9] = {sd_t_d2_1_cuda_, sd_t_d2_2_cuda_, sd_t_d2_3_cuda_, sd_t_d2_4_cuda_, sd_t_d2_5_cuda_,
                             sd_t_d2_6_cuda_, sd_t_d2_7_cuda_, sd_t_d2_8_cuda_, sd_t_d2_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort.data(), const_cast<double*>(v));
+      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort, const_cast<double*>(v));
+    g_scratch.submitted();
   }
 };
 
@@ -94,7 +128,8 @@ void one_tuple(const HostState& S, const nwc_tce_state* st, const Integer t[6], 
                double* dump_s) {
   Integer rp4 = S.rg(t[0]), rp5 = S.rg(t[1]), rp6 = S.rg(t[2]), rh1 = S.rg(t[3]), rh2 = S.rg(t[4]), rh3 = S.rg(t[5]);
   initmemmodule_();                                   // :135
-  CompatSink sink{S, st, {}, {}};
+  CompatSink sink{S, st};
+  compat_set_async_uploads(true);   // this driver owns every pinned operand it passes and never touches one in flight
   dev_mem_s_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_singles_gpu.F:192-197
   walk_singles(S, t, sink);                           // :139
   dev_mem_d_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_doubles_gpu.F:227-232
@@ -109,6 +144,8 @@ void one_tuple(const HostState& S, const nwc_tce_state* st, const Integer t[6], 
     compute_en_(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
                 ev + S.offset[t[0] - 1], ev + S.offset[t[1] - 1], ev + S.offset[t[2] - 1], &rh1, &rh2, &rh3, &rp4,
                 &rp5, &rp6, nullptr, nullptr);            // :205-215
+  compat_set_async_uploads(false);
+  g_scratch.tuple_done();
   dev_release_();                                     // :219
   finalizememmodule_();                               // :220
 }

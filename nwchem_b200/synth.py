@@ -36,8 +36,10 @@ def random_blocks(t: tl.Tiling, seed: int = 20240229, scale=(0.05, 0.02, 0.1)) -
 
 
 def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12) -> BlockStores:
-    """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts."""
-    assert t.restricted
+    """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts.
+    With an unrestricted tiling (t.restricted False) the same closed-shell tensors are expanded into every spin
+    block (beta tiles are their own owners), so E[T]/E(T) must equal the restricted result: a check of the
+    `restricted` factor-2 / k_alpha logic (ccsd_t_dot.F:52-56, tce_restricted.F)."""
     no = int(sum(t.range[i] for i in range(t.noab) if t.spin[i] == 1))
     nv = int(sum(t.range[i] for i in range(t.noab, t.noab + t.nvab) if t.spin[i] == 1))
     n = no + nv
@@ -113,9 +115,9 @@ SHAPES = {
 }
 
 
-def shape_tiling(name: str, tilesize: int | None = None, seed: int = 20240229) -> tl.Tiling:
+def shape_tiling(name: str, tilesize: int | None = None, seed: int = 20240229, restricted: bool = True) -> tl.Tiling:
     s = SHAPES[name]
-    return tl.make_tiling(s["occ"], s["virt"], tilesize or s["tilesize"], True, seed)
+    return tl.make_tiling(s["occ"], s["virt"], tilesize or s["tilesize"], restricted, seed)
 
 
 def shard_v2(st: BlockStores, rank: int, world: int) -> BlockStores:

@@ -147,6 +147,20 @@ def test_total_energy_both_tiers(oracle, shape, ts):
     assert abs(c1 - ref["e1"]) <= ABS_E and abs(c2 - ref["e2"]) <= ABS_E
 
 
+def test_unrestricted_reference_state(oracle):
+    """restricted = .false. branch of every filter (no k_alpha mapping, all-beta blocks present, factor 1)."""
+    st = synth.physical(synth.shape_tiling("h2o_ccpvdz_c2v", restricted=False))
+    ref = oracle.ccsd_t(st)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    e1, e2, pt = tr.run(per_task=True)
+    tr.close()
+    assert abs(e1 - ref["e1"]) <= ABS_E and abs(e2 - ref["e2"]) <= ABS_E
+    assert np.max(np.abs(pt - ref["per_task"])) <= ABS_E * 1e-3
+    c1, c2, _ = capi.ccsd_t_gpu(st)
+    assert abs(c1 - ref["e1"]) <= ABS_E and abs(c2 - ref["e2"]) <= ABS_E
+
+
 def test_static_partition_sums_to_total(oracle, h2o_c2v):
     """first/stride partition (replaces nxtask): rank partial sums add up to the single-rank result."""
     tr = capi.Triples(0)
