@@ -40,7 +40,7 @@ def lib() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C nwchem_b200/csrc` "
                                "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("NWC_TRIPLES_LIB", LIB_PATH))   # override: experiments with alternative builds
         _lib.nwc_triples_last_error.restype = C.c_char_p
         _lib.nwc_triples_num_tasks.restype = L
         _lib.nwc_triples_num_tasks.argtypes = [C.c_void_p]

@@ -239,9 +239,13 @@ void Engine::run(double* energies_out, double* dump_doubles, double* dump_single
   if (dump_doubles)
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                       (double2*)(dm + o_p), items_, dump_doubles, dump_singles, stream_);
-  else
+  else {
+    bool ragged = false;
+    for (const TupleHdr& t : tuples_)
+      for (int q = 0; q < 6; q++) ragged = ragged || (t.R[q] % SB != 0);
     launch_fused((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
-                 (double2*)(dm + o_p), items_, stream_);
+                 (double2*)(dm + o_p), items_, ragged, stream_);
+  }
   NWC_CUDA(cudaGetLastError());
   if (timing) NWC_CUDA(cudaEventRecord(ev1_, stream_));
   launch_reduce((const TupleHdr*)(dm + o_t), nt, (const double2*)(dm + o_p), (double2*)(dm + o_e), stream_);

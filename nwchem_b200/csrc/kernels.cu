@@ -59,6 +59,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+// Four DMMAs executed `on` (0 or 1, warp-uniform) times.  Written as a do-while because ptxas turns a plain
+// branch around DMMAs into predication, and a predicated-off DMMA still occupies the pipe (tools/pred_dmma.cu).
+__device__ __forceinline__ void dmma884x4_if(double (&c0)[2], double (&c1)[2], double (&c2)[2], double (&c3)[2], double a0,
+                                             double b0, double a1, double b1, double a2, double b2, double a3, double b3,
+                                             unsigned int on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, %16;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE;\n\t"
+      "NWC_LOOP:\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%10}, {%11}, {%2,%3};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%12}, {%13}, {%4,%5};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%14}, {%15}, {%6,%7};\n\t"
+      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP;\n\t"
+      "NWC_DONE:\n\t}"
+      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1]), "+d"(c2[0]), "+d"(c2[1]), "+d"(c3[0]), "+d"(c3[1])
+      : "d"(a0), "d"(b0), "d"(a1), "d"(b1), "d"(a2), "d"(b2), "d"(a3), "d"(b3), "r"(on));
+}
 
 // ------------------------------------------------------------------------------------------------
 // repack: strided source -> blocked K4 panel (zero padded)
@@ -116,6 +134,7 @@ static_assert(SD_PER_PASS >= 1, "ring too small for the singles staging");
 struct SplitGeom {          // per (CTA, split): where this sub-tile's base blocks live inside a panel
   long long off1, ps1;      // G1: offset of the (b3,b2,b1) block in plane 0; plane stride (doubles)
   long long off2, ps2;      // G2
+  unsigned int amask, bmask; // bit r: 8-row block r of the G1 (G2) base block holds at least one in-range row
 };
 
 struct SinglesTerm {        // per fired sd_t_s1_K term, derived once per CTA
@@ -157,6 +176,9 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
 }
 
 // number of owner indices in G1 of split s (tables.h): G1 holds p4 iff pa==p4, holds h1 iff hb!=h1
+// the nine splits as a table (evaluating make_split at run time costs ~6 KB of code and local-memory traffic)
+__constant__ Split c_splits[9] = {make_split(0), make_split(1), make_split(2), make_split(3), make_split(4),
+                                  make_split(5), make_split(6), make_split(7), make_split(8)};
 __device__ __forceinline__ int own1_of(int s) { return ((s >= 6) ? 1 : 0) + ((s % 3 != POS_H1) ? 1 : 0); }
 
 // Move the warp's 16 accumulator blocks between registers (fragment layout of split S) and its private quarter
@@ -208,10 +230,10 @@ __device__ __forceinline__ void xfer_any(int s, double (&acc)[16][2], double* ca
 // All K loops of one split whose G1 holds OWN1 owner indices: the warp tile is (8>>OWN1) x (2<<OWN1) blocks of 8x8.
 // Descriptor headers (plane count, sign) are fetched one descriptor ahead; the plane loop itself is
 // wait -> LDS fragments -> sign -> release slot (once the loads have landed) -> 16 DMMA.
-template <int OWN1>
+template <int OWN1, bool MASKED>
 __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc* __restrict__ descs, int d0, int d1,
                                           uint32_t a_base, uint32_t b_base, uint64_t* full, uint64_t* empty, int& st,
-                                          int& ph, int lane, unsigned int zero, unsigned long long& twait, bool timing) {
+                                          int& ph, int lane, unsigned int zero, unsigned int live, unsigned long long& twait, bool timing) {
   constexpr int RB = 8 >> OWN1, CB = 2 << OWN1;
   // pin the two fragment base addresses in registers (otherwise they are re-derived from SR_TID every plane)
   asm volatile("mov.u32 %0, %0;" : "+r"(a_base));
@@ -240,21 +262,38 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
 #pragma unroll
         for (int j = 0; j < CB; j++) b[j] = __hiloint2double(__double2hiint(b[j]) ^ neghi, __double2loint(b[j]));
       }
-#pragma unroll
-      for (int i = 0; i < RB; i++)
-#pragma unroll
-        for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i], b[j]);
       // Release the ring slot.  mbarrier.arrive may be scheduled right after the loads were *issued*, and the
       // producer's TMA write can then overtake a still-queued LDS (a real WAR race: ~1e-9 energy noise in ~20 % of
       // runs).  Making the barrier address depend on every fragment register forces the arrive behind the
       // completion of all ten loads at the cost of a few LOP3s; `zero` is a run-time 0 the compiler cannot fold.
-      unsigned int dep = 0;
+      auto release = [&]() {
+        unsigned int dep = 0;
 #pragma unroll
-      for (int i = 0; i < RB; i++) dep ^= (unsigned int)__double2hiint(a[i]);
+        for (int i = 0; i < RB; i++) dep ^= (unsigned int)__double2hiint(a[i]);
 #pragma unroll
-      for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j]);
-      dep &= zero;
-      if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[st]) + dep));
+        for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j]);
+        dep &= zero;
+        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[st]) + dep));
+      };
+      if (MASKED) {
+        // Edge sub-tiles of ragged tiles: bit i*CB+j of `live` clear = block (i,j) lies in the zero padding.
+        // A predicated-off DMMA still holds the FP64 pipe for its full 16 cycles (tools/pred_dmma.cu) and ptxas
+        // if-converts plain branches around them, so blocks are skipped in groups of four by dmma884x4_if;
+        // the slot is released first (nothing is hoisted across those branches).
+        release();
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int u = 4 * g;
+          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB], b[u % CB], a[(u + 1) / CB], b[(u + 1) % CB],
+                       a[(u + 2) / CB], b[(u + 2) % CB], a[(u + 3) / CB], b[(u + 3) % CB], ((live >> u) & 15u) != 0u);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < RB; i++)
+#pragma unroll
+          for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i], b[j]);
+        release();
+      }
       if (++st == STAGES) { st = 0; ph ^= 1; }
     }
   }
@@ -275,7 +314,9 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ unsigned long long* g_phase_buf = nullptr;
 __device__ unsigned int g_phase_cap = 0;
 
-template <bool DUMP, bool TIMING = false>
+// RAGGED: the launch holds tuples whose tile ranges are not multiples of four; only that instantiation carries the
+// block-skipping K loops (their mere presence costs the aligned case ~3 %, so aligned launches use the plain kernel).
+template <bool DUMP, bool TIMING = false, bool RAGGED = true>
 __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
@@ -299,9 +340,9 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 
   // ---- per-CTA setup ----
   if (tid == 0) {
-    long long idx = item - T.item_begin;
+    unsigned int idx = (unsigned int)(item - T.item_begin);   // < nitems (an int)
     for (int q = 0; q < 6; q++) {
-      int nbq = T.nb[q];
+      const unsigned int nbq = (unsigned int)T.nb[q];
       sm.b[q] = (int)(idx % nbq);
       idx /= nbq;
       sm.R[q] = T.R[q];
@@ -322,12 +363,20 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   }
   __syncthreads();
   if (tid < 9) {
-    const Split sp = make_split(tid);
+    const Split& sp = c_splits[tid];
     SplitGeom g;
     g.off1 = (((long long)sm.b[sp.g1[2]] * T.nb[sp.g1[1]] + sm.b[sp.g1[1]]) * T.nb[sp.g1[0]] + sm.b[sp.g1[0]]) * BLK_DOUBLES;
     g.ps1 = (long long)T.nb[sp.g1[0]] * T.nb[sp.g1[1]] * T.nb[sp.g1[2]] * BLK_DOUBLES;
     g.off2 = (((long long)sm.b[sp.g2[2]] * T.nb[sp.g2[1]] + sm.b[sp.g2[1]]) * T.nb[sp.g2[0]] + sm.b[sp.g2[0]]) * BLK_DOUBLES;
     g.ps2 = (long long)T.nb[sp.g2[0]] * T.nb[sp.g2[1]] * T.nb[sp.g2[2]] * BLK_DOUBLES;
+    // ragged tiles: 8-row block r of a base block holds x3 = (r&1)|(r>>2)<<1 and x2 in {2*((r>>1)&1), +1}; blocks
+    // that lie entirely in the zero padding of an edge sub-tile are skipped by the MMA warps
+    g.amask = g.bmask = 0;
+    for (int r = 0; r < 8; r++) {
+      const int x3 = (r & 1) | ((r >> 2) << 1), x2 = 2 * ((r >> 1) & 1);
+      if (4 * sm.b[sp.g1[2]] + x3 < sm.R[sp.g1[2]] && 4 * sm.b[sp.g1[1]] + x2 < sm.R[sp.g1[1]]) g.amask |= 1u << r;
+      if (4 * sm.b[sp.g2[2]] + x3 < sm.R[sp.g2[2]] && 4 * sm.b[sp.g2[1]] + x2 < sm.R[sp.g2[1]]) g.bmask |= 1u << r;
+    }
     sm.geom[tid] = g;
   }
   if (tid >= 32 && tid < 32 + 24) {  // eps of the sub-tile, index clamped into range (padding never contributes)
@@ -404,9 +453,22 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       else if (own1 == 2) { rb0 = 2 * wo0 + 4 * wo1; cb0 = 0; }
       else { rb0 = 4 * (o_h1 ? wo0 : wo1); cb0 = 4 * (o_h1 ? wo1 : wo0); }
       const uint32_t a_base = ring_u32 + (uint32_t)(rb0 * 256), b_base = ring_u32 + (uint32_t)(BLK_DOUBLES * 8 + cb0 * 256);
-      if (own1 == 1) mma_split<1>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
-      else if (own1 == 0) mma_split<0>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
-      else mma_split<2>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, tph[2], TIMING);
+      // 8x8 blocks of this warp's tile that hold in-range rows and columns (all of them away from tile edges)
+      const unsigned int am = sm.geom[s].amask >> rb0, bm = sm.geom[s].bmask >> cb0;
+      const int lcb = own1 + 1;   // log2(column blocks)
+      unsigned int live = 0xFFFFu;
+      if (RAGGED) {
+        live = 0;
+        for (int i = 0; i < (8 >> own1); i++)
+          if ((am >> i) & 1u) live |= (bm & ((1u << (2 << own1)) - 1u)) << (i << lcb);
+      }
+#define NWC_MMA(O, M) mma_split<O, M>(acc, descs, d0, d1, a_base, b_base, sm.full, sm.empty, st, ph, lane, zero_rt, live, tph[2], TIMING)
+      if (!RAGGED || live == 0xFFFFu) {
+        if (own1 == 1) NWC_MMA(1, false); else if (own1 == 0) NWC_MMA(0, false); else NWC_MMA(2, false);
+      } else {
+        if (own1 == 1) NWC_MMA(1, true); else if (own1 == 0) NWC_MMA(0, true); else NWC_MMA(2, true);
+      }
+#undef NWC_MMA
       if (TIMING) c0 = clock64();
       xfer_any<false>(s, acc, sm.canon, lane, wo0, wo1);
       __syncwarp();
@@ -420,7 +482,11 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 
   // ---- epilogue (MMA warps): singles, denominators, energies.  Warp w works on its own quarter:
   //      L = lane | wo0<<5 | jj<<6 | wo1<<11 ,  lane = (h3,h2,h1lo), jj = p6 + 4*p5 + 16*p4lo ----
+#if defined(NWC_EXP) && (NWC_EXP & 1)
+  const int nsd = 0;            // timing experiment only: no singles
+#else
   const int nsd = sm.nsd;
+#endif
   const int i_h3 = lane & 3, i_h2 = (lane >> 2) & 3, i_h1 = (lane >> 4) | (wo0 << 1);
   double sing[32];
 #pragma unroll
@@ -516,6 +582,9 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   // padded elements need no mask: their operands are exact zeros, so D = S = 0 and they add 0 to both sums.
   // Batches of eight elements: loads first, then the FP64 work as dense groups of independent instructions.
   double e2s = 0.0;   // sum w*S ; E(T) part = e1 + e2s
+#if defined(NWC_EXP) && (NWC_EXP & 2)
+  e1 = sm.canon[At] + sing[0] + sing[31] + eh;   // timing experiment only: no energy arithmetic
+#else
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 8) {
     double dd[8], rr[8];
@@ -535,6 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 #pragma unroll
     for (int u = 0; u < 8; u++) e2s = fma(rr[u], sing[j0 + u], e2s);   // ccsd_t_dot.F:116 minus :115
   }
+#endif
   e2 = e1 + e2s;
   e1 *= T.factor;
   e2 *= T.factor;
@@ -593,14 +663,21 @@ static void set_fused_attr() {
     cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
     cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fused_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done = true;
   }
 }
 
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, cudaStream_t stream) {
+                  double2* d_partials, long long total_items, bool ragged, cudaStream_t stream) {
   if (total_items <= 0) return;
   set_fused_attr();
+  if (!ragged && !g_phase_timing) {
+    fused_kernel<false, false, false><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
+        d_tuples, ntuples, d_descs, d_sdescs, d_partials, nullptr, nullptr);
+    return;
+  }
   if (g_phase_timing) {
     fused_kernel<false, true><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs,
                                                                                              d_sdescs, d_partials, nullptr, nullptr);

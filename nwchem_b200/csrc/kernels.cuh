@@ -60,8 +60,9 @@ inline long long panel_doubles(int X1, int X2, int X3, int K) {
 
 // launchers (kernels.cu).  All asynchronous on `stream`.
 void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
+// ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, cudaStream_t stream);
+                  double2* d_partials, long long total_items, bool ragged, cudaStream_t stream);
 void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_energies,
                    cudaStream_t stream);
 // unfused debugging/validation path: materialise the two t3 tiles of ONE tuple in HBM

@@ -28,3 +28,16 @@ for i, n in enumerate(names):
     print(f"  {n:16s} {d[:, i].mean():9.0f} cyc  {d[:, i].mean() / tot.mean() * 100:5.1f}%   (p50 {np.median(d[:, i]):.0f})")
 print(f"  canon<->acc transfers (inside K loops) {b[:, 6].mean():9.0f} cyc  {b[:, 6].mean() / tot.mean() * 100:5.1f}%")
 print(f"  waiting for operands (inside K loops)  {waitc.mean():9.0f} cyc  {waitc.mean() / tot.mean() * 100:5.1f}%")
+if os.environ.get("NB"):   # NB=6,6,6,10,10,10 : blocks per index (h3,h2,h1,p6,p5,p4) of the first task -> group by edge count
+    nb = [int(x) for x in os.environ["NB"].split(",")]
+    idx = np.arange(cap)[2000:cap - 2000]
+    idx = idx[buf[2000:cap - 2000, 6] > 0]
+    nedge = np.zeros(len(idx), int)
+    r = idx.copy()
+    for q in range(6):
+        nedge += (r % nb[q] == nb[q] - 1)
+        r //= nb[q]
+    for e in range(7):
+        m = nedge == e
+        if m.any():
+            print(f"  sub-tiles with {e} edge indices: {m.sum():7d}   mean K-loop cycles {d[m, 1].mean():9.0f}   wait {waitc[m].mean():9.0f}")
