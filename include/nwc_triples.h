@@ -146,6 +146,17 @@ int nwc_triples_task_list(nwc_triples_ctx *ctx, Integer *klist7);
  * nothing across calls: it is set to this call's sums.  per_task: 2 doubles per task run, or NULL. */
 int nwc_triples_run(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
                     double *per_task);
+/* Restartable (T): replaces ccsd_t_restart.F:57-290.  *restart_begin and table[nvab] are the RTDB entries
+   'tce:ccsd_t_restart_begin' (1-based outer virtual tile index, :57-66) and 'tce:restart_triples_table' (:84-95).
+   For outer = *restart_begin .. nvab (at most max_outer of them when max_outer > 0) the CCSD(T) partial of every
+   tuple with t_p4b = noab+outer is computed -- this rank takes the tuples first, first+stride, ... of that outer
+   tile's loop order (:120-150), the static stand-in for the per-tile nxtask deal -- then, if a communicator was set up
+   with nwc_triples_nccl_init, summed over ranks (the ga_dgop at :255; collective: every rank must make the same
+   call), stored in table[outer-1] (:274) and *restart_begin advanced to outer+1 (:247).  The caller persists both
+   between calls (max_outer = 1 gives one checkpoint per outer tile like the reference).  table_bracket (optional,
+   nvab doubles) receives the CCSD[T] partials the same way.  *t_energy = sum(table) (:288-290). */
+int nwc_triples_run_restart(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer *restart_begin, double *table,
+                            double *table_bracket, Integer max_outer, double *t_energy);
 /* one tuple, optionally materialising the t3 tiles (validation only) */
 int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                           double *host_doubles, double *host_singles);

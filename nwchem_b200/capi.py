@@ -196,6 +196,21 @@ class Triples:
                "nwc_triples_run")
         return (float(e[0]), float(e[1]), pt[:cnt]) if per_task else (float(e[0]), float(e[1]))
 
+    def run_restart(self, begin=1, table=None, max_outer=0, first=0, stride=1):
+        """Restartable (T) (ccsd_t_restart.F): returns (new begin, table[nvab] of CCSD(T) partials per outer virtual
+        tile, table of CCSD[T] partials, t_energy).  Pass the returned begin/table back in to resume."""
+        nv = self.t.nvab
+        tab = np.zeros(nv) if table is None else np.ascontiguousarray(table, np.float64).copy()
+        tab1 = np.zeros(nv)
+        b = L(begin)
+        te = C.c_double(0.0)
+        l = lib()
+        l.nwc_triples_run_restart.argtypes = [C.c_void_p, L, L, C.POINTER(L), C.POINTER(C.c_double),
+                                              C.POINTER(C.c_double), L, C.POINTER(C.c_double)]
+        _check(l.nwc_triples_run_restart(self._h, first, stride, C.byref(b), _pd(tab), _pd(tab1), max_outer, C.byref(te)),
+               "nwc_triples_run_restart")
+        return int(b.value), tab, tab1, float(te.value)
+
     def run_tuple(self, tup, dump=False):
         tt = np.array(tup, np.int64)
         e = np.zeros(2)

@@ -175,7 +175,7 @@ void Engine::end_tuple(const double* const eps[6], double factor) {
   }
   cur_.desc_begin[9] = n;
   cur_.sdesc_end = (int)sdescs_.size();
-  if (cur_.sdesc_end - cur_.sdesc_begin > 16) { printf("nwc_triples: more than 16 singles terms in one tuple\n"); exit(1); }
+  if (cur_.sdesc_end - cur_.sdesc_begin > 12) { printf("nwc_triples: more than 12 singles terms in one tuple\n"); exit(1); }
   long long items = 1;
   for (int q = 0; q < 6; q++) items *= cur_.nb[q];
   cur_.item_begin = items_;

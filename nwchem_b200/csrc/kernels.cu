@@ -126,7 +126,7 @@ constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
 constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 5 : 10;   // ring depth; one k4 plane (4 KiB) per stage
 constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block = 4 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
-constexpr int MAX_SDESC = 16;
+constexpr int MAX_SDESC = 12;   // a tuple fires at most nine sd_t_s1_K kernels; the engine rejects more than 12
 constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
 constexpr int SD_PER_PASS = (RING_DOUBLES / SD_TERM) < 9 ? (RING_DOUBLES / SD_TERM) : 9;   // terms staged per pass
 static_assert(SD_PER_PASS >= 1, "ring too small for the singles staging");
@@ -137,12 +137,20 @@ struct SplitGeom {          // per (CTA, split): where this sub-tile's base bloc
   unsigned int amask, bmask; // bit r: 8-row block r of the G1 (G2) base block holds at least one in-range row
 };
 
-struct SinglesTerm {        // per fired sd_t_s1_K term, derived once per CTA
-  short wt[6];              // multiplier (1,4 / 1,4,16,64) of each physical position in the staged t1 / v2 block, 0 if absent
-  short wv[6];
-  signed char sh[6];        // log2 of whichever multiplier is non-zero
-  signed char in_t1[6];     // 1 if t1 carries the position
+struct __align__(8) SinglesTerm {   // per fired sd_t_s1_K term, derived once per CTA by one thread (72 bytes)
+  const double* t1;         // operand blocks (SinglesDesc)
+  const double* v2;
+  int vbase, tbase;         // element offset of this sub-tile's first element inside v2 / t1 (one tile: < 2^31)
+  int vs[4];                // source strides of the four v2 positions, in staged order (multipliers 1,4,16,64)
+  int ts[2];                // source strides of the two t1 positions (multipliers 1,4)
+  unsigned char vn[4];      // in-range count (1..4) of each v2 / t1 position
+  unsigned char tn[2];
+  unsigned char neg;
+  unsigned char edge;       // 1: some position of this sub-tile is cut by the tile edge (vn/tn < 4)
+  unsigned char wt[6];      // multiplier (1,4 / 1,4,16,64) of each physical position in the staged t1 / v2 block, 0 if absent
+  unsigned char wv[6];
 };
+static_assert(sizeof(SinglesTerm) == 72, "SinglesTerm layout");
 
 struct __align__(16) FusedSmem {
   double canon[SUBTILE];                    // 32 KiB canonical t3 sub-tile (doubles part); quarter w is private to warp w
@@ -299,18 +307,21 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
   }
 }
 
-// reciprocal to ~1 ulp: MUFU seed (off the FP64 pipe) + two Newton steps
+// reciprocal to < 1 ulp: MUFU seed r0 (off the FP64 pipe, relative error e ~ 2^-20), then one cubic step
+// r0*(1 + e + e^2), e = 1 - x*r0, leaves e^3 -- three FP64 instructions instead of the four of two Newton steps
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 }
 
 // per-CTA phase clocks (debug builds of the kernel only): t0 start, t1 setup done, t2 first plane consumed,
 // t3 K loops done (before the CTA barrier), t4 after the barrier, t5 singles staged+accumulated, t6 end,
 // [7] = cycles spent moving accumulators to/from the canonical tile by warp 0
+#ifdef NWC_EXP_ALIGN
+__device__ unsigned int g_align_cnt[1024];
+#endif
 __device__ unsigned long long* g_phase_buf = nullptr;
 __device__ unsigned int g_phase_cap = 0;
 
@@ -329,24 +340,39 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   const int wo0 = warp & 1, wo1 = (warp >> 1) & 1;   // owner bits: high bit of h1, high bit of p4
   const bool is_producer = warp == NCONSUMERS / 32;
 
-  // ---- locate the tuple of this work item (binary search over item_begin) ----
+  // ---- locate the tuple of this work item: 32-way search over item_begin (two dependent loads for <= 1024
+  //      tuples instead of log2(ntuples)) ----
   const long long item = blockIdx.x;
-  int lo = 0, hi = ntuples - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (tuples[mid].item_begin <= item) lo = mid; else hi = mid - 1;
+  int lo = 0;
+  for (int n = ntuples; n > 1;) {
+    const int step = (n + 31) >> 5, idx = lo + lane * step;
+    const bool le = idx < lo + n && tuples[idx].item_begin <= item;   // a prefix of the lanes; lane 0 always
+    const int k = 31 - __clz(__ballot_sync(0xffffffffu, le));
+    const int rem = n - k * step;
+    lo += k * step;
+    n = rem < step ? rem : step;
   }
   const TupleHdr& T = tuples[lo];
 
-  // ---- per-CTA setup ----
-  if (tid == 0) {
-    unsigned int idx = (unsigned int)(item - T.item_begin);   // < nitems (an int)
-    for (int q = 0; q < 6; q++) {
-      const unsigned int nbq = (unsigned int)T.nb[q];
-      sm.b[q] = (int)(idx % nbq);
-      idx /= nbq;
-      sm.R[q] = T.R[q];
+  // ---- per-CTA setup.  Lanes 0..5 of every warp hold block index / range / block count of position q = lane;
+  //      run-time indexed reads are shuffles, so nothing waits on another thread and one barrier suffices ----
+  const int q6 = lane < 6 ? lane : 0;
+  const int my_nb = T.nb[q6], my_R = T.R[q6];
+  int my_b;
+  {
+    unsigned int below = 1;   // product of the block counts of the faster positions
+#pragma unroll
+    for (int jq = 0; jq < 5; jq++) {
+      const unsigned int nbj = (unsigned int)__shfl_sync(0xffffffffu, my_nb, jq);
+      if (jq < q6) below *= nbj;
     }
+    my_b = (int)(((unsigned int)(item - T.item_begin) / below) % (unsigned int)my_nb);
+  }
+#define NWC_B(q) __shfl_sync(0xffffffffu, my_b, (q))
+#define NWC_NB(q) __shfl_sync(0xffffffffu, my_nb, (q))
+#define NWC_R(q) __shfl_sync(0xffffffffu, my_R, (q))
+  if (tid < 6) { sm.b[tid] = my_b; sm.R[tid] = my_R; }
+  if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], NCONSUMERS / 32);
@@ -357,45 +383,75 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     sm.zero = 0;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
-  {
-    double2* c2 = reinterpret_cast<double2*>(sm.canon);
+  if (T.desc_begin[9] == T.desc_begin[0]) {   // no contraction fires: the doubles tile is zero.  Otherwise the first
+    double2* c2 = reinterpret_cast<double2*>(sm.canon);   // split's STORE covers the whole canonical tile
     for (int i = tid; i < SUBTILE / 2; i += NTHREADS) c2[i] = make_double2(0.0, 0.0);
   }
-  __syncthreads();
-  if (tid < 9) {
-    const Split& sp = c_splits[tid];
-    SplitGeom g;
-    g.off1 = (((long long)sm.b[sp.g1[2]] * T.nb[sp.g1[1]] + sm.b[sp.g1[1]]) * T.nb[sp.g1[0]] + sm.b[sp.g1[0]]) * BLK_DOUBLES;
-    g.ps1 = (long long)T.nb[sp.g1[0]] * T.nb[sp.g1[1]] * T.nb[sp.g1[2]] * BLK_DOUBLES;
-    g.off2 = (((long long)sm.b[sp.g2[2]] * T.nb[sp.g2[1]] + sm.b[sp.g2[1]]) * T.nb[sp.g2[0]] + sm.b[sp.g2[0]]) * BLK_DOUBLES;
-    g.ps2 = (long long)T.nb[sp.g2[0]] * T.nb[sp.g2[1]] * T.nb[sp.g2[2]] * BLK_DOUBLES;
-    // ragged tiles: 8-row block r of a base block holds x3 = (r&1)|(r>>2)<<1 and x2 in {2*((r>>1)&1), +1}; blocks
-    // that lie entirely in the zero padding of an edge sub-tile are skipped by the MMA warps
-    g.amask = g.bmask = 0;
-    for (int r = 0; r < 8; r++) {
-      const int x3 = (r & 1) | ((r >> 2) << 1), x2 = 2 * ((r >> 1) & 1);
-      if (4 * sm.b[sp.g1[2]] + x3 < sm.R[sp.g1[2]] && 4 * sm.b[sp.g1[1]] + x2 < sm.R[sp.g1[1]]) g.amask |= 1u << r;
-      if (4 * sm.b[sp.g2[2]] + x3 < sm.R[sp.g2[2]] && 4 * sm.b[sp.g2[1]] + x2 < sm.R[sp.g2[1]]) g.bmask |= 1u << r;
+  if (warp == 0) {
+    const Split& sp = c_splits[lane < 9 ? lane : 0];
+    const int b10 = NWC_B(sp.g1[0]), b11 = NWC_B(sp.g1[1]), b12 = NWC_B(sp.g1[2]);
+    const int b20 = NWC_B(sp.g2[0]), b21 = NWC_B(sp.g2[1]), b22 = NWC_B(sp.g2[2]);
+    const int n10 = NWC_NB(sp.g1[0]), n11 = NWC_NB(sp.g1[1]), n12 = NWC_NB(sp.g1[2]);
+    const int n20 = NWC_NB(sp.g2[0]), n21 = NWC_NB(sp.g2[1]), n22 = NWC_NB(sp.g2[2]);
+    const int r11 = NWC_R(sp.g1[1]), r12 = NWC_R(sp.g1[2]), r21 = NWC_R(sp.g2[1]), r22 = NWC_R(sp.g2[2]);
+    if (lane < 9) {
+      SplitGeom g;
+      g.off1 = (((long long)b12 * n11 + b11) * n10 + b10) * BLK_DOUBLES;
+      g.ps1 = (long long)n10 * n11 * n12 * BLK_DOUBLES;
+      g.off2 = (((long long)b22 * n21 + b21) * n20 + b20) * BLK_DOUBLES;
+      g.ps2 = (long long)n20 * n21 * n22 * BLK_DOUBLES;
+      // ragged tiles: 8-row block r of a base block holds x3 = (r&1)|(r>>2)<<1 and x2 in {2*((r>>1)&1), +1};
+      // blocks that lie entirely in the zero padding of an edge sub-tile are skipped by the MMA warps
+      g.amask = g.bmask = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int x3 = (r & 1) | ((r >> 2) << 1), x2 = 2 * ((r >> 1) & 1);
+        if (4 * b12 + x3 < r12 && 4 * b11 + x2 < r11) g.amask |= 1u << r;
+        if (4 * b22 + x3 < r22 && 4 * b21 + x2 < r21) g.bmask |= 1u << r;
+      }
+      sm.geom[lane] = g;
     }
-    sm.geom[tid] = g;
   }
-  if (tid >= 32 && tid < 32 + 24) {  // eps of the sub-tile, index clamped into range (padding never contributes)
-    const int q = (tid - 32) >> 2, i = (tid - 32) & 3;
-    int g = 4 * sm.b[q] + i;
-    if (g >= sm.R[q]) g = sm.R[q] - 1;
-    sm.eps[q][i] = __ldg(T.eps[q] + g);
+  if (warp == 1) {  // eps of the sub-tile, index clamped into range (padding never contributes)
+    const int q = lane < 24 ? (lane >> 2) : 0, i = lane & 3;
+    const int bq = NWC_B(q), rq = NWC_R(q);
+    int g = 4 * bq + i;
+    if (g >= rq) g = rq - 1;
+    if (lane < 24) sm.eps[q][i] = __ldg(T.eps[q] + g);
   }
-  if (tid >= 64 && tid < 64 + sm.nsd) {  // staged-layout multipliers of each singles term
-    const SinglesDesc& sd = sdescs[T.sdesc_begin + (tid - 64)];
-    SinglesTerm st;
-    int mt = 0, mv = 0;
+  if (warp == 2) {  // one lane per singles term: staged-layout multipliers, source strides and sub-tile origin
+    const int nsd_l = min(T.sdesc_end - T.sdesc_begin, MAX_SDESC);
+    const bool act = lane < nsd_l;
+    const SinglesDesc* sd = act ? &sdescs[T.sdesc_begin + lane] : nullptr;
+    SinglesTerm& st = sm.st[lane < MAX_SDESC ? lane : 0];
+    int mt = 0, mv = 0, edge = 0;
+    int vbase = 0, tbase = 0;
+#pragma unroll
     for (int q = 0; q < 6; q++) {
-      st.wt[q] = 0; st.wv[q] = 0;
-      if (sd.st1[q] != 0) { st.wt[q] = (short)(1 << mt); st.sh[q] = (signed char)mt; st.in_t1[q] = 1; mt += 2; }
-      else { st.wv[q] = (short)(1 << mv); st.sh[q] = (signed char)mv; st.in_t1[q] = 0; mv += 2; }
+      const int bq = NWC_B(q), rq = NWC_R(q);
+      if (act) {
+        const int nin = (rq - 4 * bq) < 4 ? (rq - 4 * bq) : 4;
+        edge |= nin < 4;
+        const int s1 = sd->st1[q];
+        if (s1 != 0) {
+          st.wt[q] = (unsigned char)(1 << mt); st.wv[q] = 0;
+          st.ts[mt >> 1] = s1; st.tn[mt >> 1] = (unsigned char)nin;
+          tbase += 4 * bq * s1;
+          mt += 2;
+        } else {
+          const int s2 = sd->sv2[q];
+          st.wv[q] = (unsigned char)(1 << mv); st.wt[q] = 0;
+          st.vs[mv >> 1] = s2; st.vn[mv >> 1] = (unsigned char)nin;
+          vbase += 4 * bq * s2;
+          mv += 2;
+        }
+      }
     }
-    sm.st[tid - 64] = st;
+    if (act) { st.t1 = sd->t1; st.v2 = sd->v2; st.vbase = vbase; st.tbase = tbase; st.neg = (unsigned char)(sd->neg != 0); st.edge = (unsigned char)edge; }
   }
+#undef NWC_B
+#undef NWC_NB
+#undef NWC_R
   __syncthreads();
   if (TIMING) tph[1] = clock64();
 
@@ -476,6 +532,17 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     }
   }
   if (TIMING) tph[3] = clock64();
+#ifdef NWC_EXP_ALIGN
+  // experiment: phase-align the CTAs that share an SM (bounded spin on a per-SM arrival counter)
+  if (tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int mine = atomicAdd(&g_align_cnt[smid], 1u) + 1u;
+    const unsigned int target = (mine + NWC_EXP_ALIGN - 1) / NWC_EXP_ALIGN * NWC_EXP_ALIGN;
+    const long long t0 = clock64();
+    while ((int)(*((volatile unsigned int*)&g_align_cnt[smid]) - target) < 0 && clock64() - t0 < 60000) __nanosleep(100);
+  }
+#endif
   __syncthreads();   // every plane consumed: the ring is idle and can stage the singles operands
   if (TIMING) tph[4] = clock64();
   if (is_producer) return;
@@ -498,30 +565,24 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       const int nt = (nsd - t0) < SD_PER_PASS ? (nsd - t0) : SD_PER_PASS;
       if (t0 > 0) asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");   // previous pass fully consumed
       double v0[SD_PER_PASS], v1[SD_PER_PASS], vt[SD_PER_PASS];
+      const int d0 = tid & 3, d1 = (tid >> 2) & 3, d2 = (tid >> 4) & 3, d3 = (tid >> 6) & 3;   // staged v2 digits
 #pragma unroll
       for (int u = 0; u < SD_PER_PASS; u++) {
         v0[u] = v1[u] = vt[u] = 0.0;
         if (u < nt) {
-          const SinglesDesc& sd = sdescs[T.sdesc_begin + t0 + u];
-          const SinglesTerm stt = sm.st[t0 + u];
-          int offv0 = 0, offv1 = 0, offt = 0;
+          const SinglesTerm& stt = sm.st[t0 + u];
+          const int offv = stt.vbase + d0 * stt.vs[0] + d1 * stt.vs[1] + d2 * stt.vs[2] + d3 * stt.vs[3];
+          const int offt = stt.tbase + d0 * stt.ts[0] + d1 * stt.ts[1];
           bool ok0 = true, ok1 = true, okt = true;
-#pragma unroll
-          for (int q = 0; q < 6; q++) {
-            const int base = 4 * sm.b[q], R = sm.R[q], sh = stt.sh[q];
-            if (stt.in_t1[q]) {
-              const int g = base + ((tid >> sh) & 3);
-              okt = okt && (g < R);
-              offt += g * sd.st1[q];
-            } else {
-              const int ga = base + ((tid >> sh) & 3), gb = base + (((tid + NCONSUMERS) >> sh) & 3);
-              ok0 = ok0 && (ga < R); ok1 = ok1 && (gb < R);
-              offv0 += ga * sd.sv2[q]; offv1 += gb * sd.sv2[q];
-            }
+          if (stt.edge) {
+            const bool lowok = d0 < stt.vn[0] && d1 < stt.vn[1] && d2 < stt.vn[2];
+            ok0 = lowok && d3 < stt.vn[3];
+            ok1 = lowok && d3 + 2 < stt.vn[3];
+            okt = d0 < stt.tn[0] && d1 < stt.tn[1];
           }
-          if (ok0) v0[u] = __ldg(sd.v2 + offv0);
-          if (ok1) v1[u] = __ldg(sd.v2 + offv1);
-          if (tid < SD_T1 && okt) { const double x = __ldg(sd.t1 + offt); vt[u] = sd.neg ? -x : x; }
+          if (ok0) v0[u] = __ldg(stt.v2 + offv);
+          if (ok1) v1[u] = __ldg(stt.v2 + offv + 2 * stt.vs[3]);   // element tid+128: fourth digit + 2
+          if (tid < SD_T1 && okt) { const double x = __ldg(stt.t1 + offt); vt[u] = stt.neg ? -x : x; }
         }
       }
 #pragma unroll
@@ -669,6 +730,7 @@ static void set_fused_attr() {
   }
 }
 
+static_assert(NWC_CTAS_PER_SM * (sizeof(FusedSmem) + 1024) <= 228 * 1024, "FusedSmem too large for the intended CTAs/SM");
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                   double2* d_partials, long long total_items, bool ragged, cudaStream_t stream) {
   if (total_items <= 0) return;

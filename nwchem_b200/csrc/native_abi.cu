@@ -341,6 +341,59 @@ int nwc_triples_run(nwc_triples_ctx* c, Integer first, Integer stride, Integer m
   return 0;
 }
 
+int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, Integer* restart_begin, double* table,
+                            double* table_bracket, Integer max_outer, double* t_energy) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (stride <= 0) stride = 1;
+  if (*restart_begin < 1) *restart_begin = 1;
+  const HostState& S = c->S;
+  Engine& e = *c->eng;
+  const Integer n0 = S.noab, n1 = S.noab + S.nvab;
+  std::vector<double> eb;
+  Integer done = 0;
+  for (Integer p4 = n0 + *restart_begin; p4 <= n1; p4++) {
+    if (max_outer > 0 && done >= max_outer) break;
+    double en[2] = {0.0, 0.0};
+    auto flush = [&]() {
+      const int n = e.pending_tuples();
+      if (n == 0) return;
+      eb.assign(2 * (size_t)n, 0.0);
+      e.run(eb.data());
+      for (int i = 0; i < n; i++) { en[0] += eb[2 * i]; en[1] += eb[2 * i + 1]; }
+      e.arena().reset();
+    };
+    Integer count = 0;   // position in this outer tile's loop order (ccsd_t_restart.F:120-150)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              const Integer ps = S.sp(p4) + S.sp(p5) + S.sp(p6), hs = S.sp(h1) + S.sp(h2) + S.sp(h3);
+              if (ps != hs) continue;
+              if (S.restricted && ps + hs > 8) continue;
+              if ((S.sy(p4) ^ S.sy(p5) ^ S.sy(p6) ^ S.sy(h1) ^ S.sy(h2) ^ S.sy(h3)) != 0) continue;
+              const Integer k = count++;
+              if (k < first || (k - first) % stride != 0) continue;
+              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+              emit_tuple(c, t);
+              if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)1500000000 || e.pending_tuples() >= 4096)
+                flush();
+            }
+    flush();
+    if (c->comm) {
+      if (nwc_triples_allreduce_energy(c, en) != 0) return 1;
+    }
+    const Integer outer = p4 - n0;
+    table[outer - 1] = en[1];
+    if (table_bracket) table_bracket[outer - 1] = en[0];
+    *restart_begin = outer + 1;
+    done++;
+  }
+  *t_energy = 0.0;
+  for (Integer i = 0; i < S.nvab; i++) *t_energy += table[i];
+  return 0;
+}
+
 int nwc_triples_run_tuple(nwc_triples_ctx* c, const Integer t[6], double energy[2], double* host_doubles,
                           double* host_singles) {
   NWC_TRY(cudaSetDevice(c->eng->device()));

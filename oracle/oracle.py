@@ -99,6 +99,20 @@ def ccsd_t(st, per_task=False, count=False):
     return dict(e1=float(e[0]), e2=float(e[1]), tasks=kl[:n], per_task=pt[:n], counts=cnt)
 
 
+def ccsd_t_restart(st, begin=1, table=None, max_outer=0):
+    """Restartable (T), ccsd_t_restart.F: returns (new begin, table[nvab], t_energy, outer tiles done)."""
+    l = lib()
+    c, keep = make_ctx(st)
+    tab = np.zeros(st.t.nvab) if table is None else np.ascontiguousarray(table, np.float64).copy()
+    b = L(begin)
+    te = C.c_double(0.0)
+    l.ora_ccsd_t_restart.restype = L
+    done = l.ora_ccsd_t_restart(C.byref(c), C.byref(b), _pd(tab), L(max_outer), C.byref(te))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return int(b.value), tab, float(te.value), int(done)
+
+
 def tuple_tiles(st, tup):
     """One tuple (p4b,p5b,p6b,h1b,h2b,h3b): returns (singles, doubles, e1, e2) with the t3 tiles as
     arrays indexed [p4,p5,p6,h1,h2,h3] (C order == Fortran T3(h3,h2,h1,p6,p5,p4))."""

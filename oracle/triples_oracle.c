@@ -682,6 +682,52 @@ Integer ora_ccsd_t(const ora_ctx *c, double *energy /*[2]*/, Integer *klist_out 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Restartable (T): ccsd_t_restart.F:57-290 on one rank.  The RTDB entries become arguments: */
+/*   *restart_begin = 'tce:ccsd_t_restart_begin' (1-based outer virtual tile, :57-66),       */
+/*   table[nvab]    = 'tce:restart_triples_table' (:84-95), one CCSD(T) partial per t_p4b.   */
+/* Outer loop over t_p4b (:120), inner loops and filters :129-150, energy accumulation       */
+/* E += f*D*(S+D)/Delta (:188-206), table update :274, begin update :247, final sum :288.    */
+/* max_outer > 0 stops after that many outer tiles (an interrupted run); the tile bodies use */
+/* the same singles/doubles restatement as ora_ccsd_t_loop (ccsd_t_restart.F calls the       */
+/* non-offload ccsd_t_singles/ccsd_t_doubles, which build the same two tiles).               */
+/* ------------------------------------------------------------------------------------ */
+Integer ora_ccsd_t_restart(const ora_ctx *c, Integer *restart_begin, double *table, Integer max_outer,
+                           double *t_energy) {
+  Integer range_p4 = 0, range_h1 = 0;
+  for (Integer b = c->noab + 1; b <= c->noab + c->nvab; b++) if (RANGE(b) > range_p4) range_p4 = RANGE(b);
+  for (Integer b = 1; b <= c->noab; b++) if (RANGE(b) > range_h1) range_h1 = RANGE(b);
+  const size_t size = (size_t)range_p4 * range_p4 * range_p4 * range_h1 * range_h1 * range_h1;
+  double *a_singles = (double *)malloc(sizeof(double) * (size + 8));
+  double *a_doubles = (double *)malloc(sizeof(double) * (size + 8));
+  Integer done = 0;
+  if (*restart_begin < 1) *restart_begin = 1;
+  for (Integer t_p4b = c->noab + *restart_begin; t_p4b <= c->noab + c->nvab; t_p4b++) {
+    if (max_outer > 0 && done >= max_outer) break;
+    double energy = 0.0;
+    const Integer outer_virtual_index = t_p4b - c->noab;
+    for (Integer t_p5b = t_p4b; t_p5b <= c->noab + c->nvab; t_p5b++)
+      for (Integer t_p6b = t_p5b; t_p6b <= c->noab + c->nvab; t_p6b++)
+        for (Integer t_h1b = 1; t_h1b <= c->noab; t_h1b++)
+          for (Integer t_h2b = t_h1b; t_h2b <= c->noab; t_h2b++)
+            for (Integer t_h3b = t_h2b; t_h3b <= c->noab; t_h3b++) {
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b))
+                continue;
+              const Integer tuple[6] = {t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b};
+              double e[2] = {0.0, 0.0};
+              ora_ccsd_t_loop(c, tuple, a_singles, a_doubles, e, NULL);
+              energy += e[1];
+            }
+    *restart_begin = outer_virtual_index + 1;   /* :247 */
+    table[outer_virtual_index - 1] = energy;    /* :274 */
+    done++;
+  }
+  *t_energy = 0.0;
+  for (Integer i = 0; i < c->nvab; i++) *t_energy += table[i]; /* :288-290 */
+  free(a_singles); free(a_doubles);
+  return done;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Tiling: tce_tile.F:330-357 (one spin/irrep orbital group of n orbitals -> tile sizes) */
 /* returns the number of tiles, writes ranges[]                                          */
 /* ------------------------------------------------------------------------------------ */

@@ -171,6 +171,27 @@ def test_static_partition_sums_to_total(oracle, h2o_c2v):
     assert abs(sum(p[0] for p in parts) - e1) <= 1e-13 and abs(sum(p[1] for p in parts) - e2) <= 1e-13
 
 
+def test_restartable_t_matches_oracle_and_resumes(oracle, h2o_c2v):
+    """nwc_triples_run_restart (ccsd_t_restart.F): per-outer-virtual-tile table against the oracle's, interrupted +
+    resumed == uninterrupted (bitwise), and two ranks' tables (first/stride deal inside each outer tile) add up."""
+    st = h2o_c2v
+    _, otab, ote, _ = oracle.ccsd_t_restart(st)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    e1, e2 = tr.run()
+    begin, tab, tab1, te = tr.run_restart()
+    assert begin == st.t.nvab + 1
+    assert np.max(np.abs(tab - otab)) <= ABS_E and abs(te - ote) <= ABS_E
+    assert abs(te - e2) <= 1e-13 and abs(tab1.sum() - e1) <= 1e-13
+    b1, t1, _, _ = tr.run_restart(max_outer=3)
+    assert b1 == 4 and np.all(t1[3:] == 0.0)
+    b2, t2, _, te2 = tr.run_restart(begin=b1, table=t1)
+    assert b2 == st.t.nvab + 1 and np.array_equal(t2, tab) and te2 == te
+    parts = [tr.run_restart(first=r, stride=2)[1] for r in range(2)]
+    tr.close()
+    assert np.max(np.abs(parts[0] + parts[1] - tab)) <= 1e-13
+
+
 def test_sharded_v2_two_contexts_one_gpu(oracle, h2o_c2v):
     """Sharded V2 addressing (block i -> rank i % 2, compacted shards, peer pointers): two contexts on one GPU stand
     in for two ranks; each runs its half of the task list reading the other's shard.  The IPC/NVLink flavour of the

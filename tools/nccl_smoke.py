@@ -35,6 +35,10 @@ e1, e2 = tr.run(first=rank, stride=world)
 log("partial", e1, e2)
 t1, t2 = tr.allreduce(e1, e2)
 log("allreduced", t1, t2)
+# restartable (T): every rank gets the rank-summed table (one allreduce per outer virtual tile, ccsd_t_restart.F:255)
+rb, rtab, _, rte = tr.run_restart(first=rank, stride=world)
+log("restart table sum", rte)
+assert abs(rte - t2) < 1e-12 and rb == st.t.nvab + 1, (rte, t2, rb)
 if rank == 0:
     from oracle import oracle as ora
     ref = ora.ccsd_t(st)
