@@ -319,9 +319,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // per-CTA phase clocks (debug builds of the kernel only): t0 start, t1 setup done, t2 first plane consumed,
 // t3 K loops done (before the CTA barrier), t4 after the barrier, t5 singles staged+accumulated, t6 end,
 // [7] = cycles spent moving accumulators to/from the canonical tile by warp 0
-#ifdef NWC_EXP_ALIGN
-__device__ unsigned int g_align_cnt[1024];
-#endif
 __device__ unsigned long long* g_phase_buf = nullptr;
 __device__ unsigned int g_phase_cap = 0;
 
@@ -532,17 +529,6 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     }
   }
   if (TIMING) tph[3] = clock64();
-#ifdef NWC_EXP_ALIGN
-  // experiment: phase-align the CTAs that share an SM (bounded spin on a per-SM arrival counter)
-  if (tid == 0) {
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const unsigned int mine = atomicAdd(&g_align_cnt[smid], 1u) + 1u;
-    const unsigned int target = (mine + NWC_EXP_ALIGN - 1) / NWC_EXP_ALIGN * NWC_EXP_ALIGN;
-    const long long t0 = clock64();
-    while ((int)(*((volatile unsigned int*)&g_align_cnt[smid]) - target) < 0 && clock64() - t0 < 60000) __nanosleep(100);
-  }
-#endif
   __syncthreads();   // every plane consumed: the ring is idle and can stage the singles operands
   if (TIMING) tph[4] = clock64();
   if (is_producer) return;
