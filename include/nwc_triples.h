@@ -146,6 +146,26 @@ int nwc_triples_task_list(nwc_triples_ctx *ctx, Integer *klist7);
  * nothing across calls: it is set to this call's sums.  per_task: 2 doubles per task run, or NULL. */
 int nwc_triples_run(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
                     double *per_task);
+/* `2eorb` V2 storage (tce.fh `intorb`): the two-electron integrals are kept spin-free over the ALPHA
+   tiles and every spin-orbital block <g3 g4||g1 g2> = (g3 g1|g4 g2) - (g3 g2|g4 g1) is antisymmetrised on the
+   device when a tuple needs it -- replaces get_hash_block_i (get_hash_block.F:47-118) -> get_block_ind_i
+   (get_block_ind.F:818-1538) -> tce_hash_v2 (tce_hash.F:1-135).  The arrays are the reference's own:
+   b2am = int_mb(k_b2am) (tce_tile.F:1156-1212), spin/sym/range_alpha = k_spin_alpha.. (tce_tile.F:1376-1383),
+   v2orb_hash = int_mb(k_v2_alpha_offset), the checkpointed table of tce_mo2e_offset_intorb.F:52-150
+   ([length1 | keys | offsets | g3b | g4b | g1b | g2b], 6*(length1+1)+1 integers), v2orb = the d_v2orb file,
+   block (g3b<=g4b | g1b<=g2b) holding (k l|i j), k in g4b fastest, l in g3b, i in g2b, j in g1b
+   (tce_mo2e_trans.F:707-723). */
+typedef struct {
+  Integer noa, nva;
+  const Integer *b2am;          /* [noab+nvab] */
+  const Integer *spin_alpha;    /* [noa+nva] */
+  const Integer *sym_alpha;
+  const Integer *range_alpha;
+  const Integer *v2orb_hash;
+  const double *v2orb;
+} nwc_tce_orb_state;
+/* like nwc_triples_set_state, but V2 comes from `orb`; st->v2_hash / st->v2 are not read (may be NULL) */
+int nwc_triples_set_state_2eorb(nwc_triples_ctx *ctx, const nwc_tce_state *st, const nwc_tce_orb_state *orb);
 /* Restartable (T): replaces ccsd_t_restart.F:57-290.  *restart_begin and table[nvab] are the RTDB entries
    'tce:ccsd_t_restart_begin' (1-based outer virtual tile index, :57-66) and 'tce:restart_triples_table' (:84-95).
    For outer = *restart_begin .. nvab (at most max_outer of them when max_outer > 0) the CCSD(T) partial of every

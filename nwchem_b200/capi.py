@@ -21,6 +21,11 @@ class TceState(C.Structure):  # nwc_tce_state
                 ("t1_hash", PL), ("t1", PD), ("t2_hash", PL), ("t2", PD), ("v2_hash", PL), ("v2", PD)]
 
 
+class OrbState(C.Structure):  # nwc_tce_orb_state
+    _fields_ = [("noa", L), ("nva", L), ("b2am", PL), ("spin_alpha", PL), ("sym_alpha", PL), ("range_alpha", PL),
+                ("v2orb_hash", PL), ("v2orb", PD)]
+
+
 class Stats(C.Structure):  # nwc_triples_stats
     _fields_ = [("fused_ms", C.c_double), ("repack_ms", C.c_double), ("fused_launches", C.c_longlong),
                 ("repack_launches", C.c_longlong), ("reduce_launches", C.c_longlong), ("work_items", C.c_longlong),
@@ -150,6 +155,20 @@ class Triples:
     def set_state(self, st):
         s, keep = make_state(st)
         _check(lib().nwc_triples_set_state(self._h, C.byref(s)), "nwc_triples_set_state")
+        self.t = st.t
+
+    def set_state_2eorb(self, st):
+        """`2eorb` storage: V2 is read from st.orb (synth.OrbitalV2), never from st.v2."""
+        s, keep = make_state(st)
+        a = st.orb.a
+        k = dict(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
+                 sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
+                 voh=np.ascontiguousarray(st.orb.v2orb_hash, np.int64), vo=np.ascontiguousarray(st.orb.v2orb, np.float64))
+        o = OrbState(a.noa, a.nva, _pl(k["b2am"]), _pl(k["spa"]), _pl(k["sya"]), _pl(k["rga"]), _pl(k["voh"]), _pd(k["vo"]))
+        s.v2_hash = None; s.v2 = None
+        l = lib()
+        l.nwc_triples_set_state_2eorb.argtypes = [C.c_void_p, C.POINTER(TceState), C.POINTER(OrbState)]
+        _check(l.nwc_triples_set_state_2eorb(self._h, C.byref(s), C.byref(o)), "nwc_triples_set_state_2eorb")
         self.t = st.t
 
     def set_state_sharded(self, st_shard, rank: int, world: int):

@@ -69,6 +69,7 @@ Engine::~Engine() {
   arena_.release();
   if (d_meta_) cudaFree(d_meta_);
   if (d_jobs_) cudaFree(d_jobs_);
+  if (d_ajobs_) cudaFree(d_ajobs_);
   if (h_pin_) cudaFreeHost(h_pin_);
   cudaEventDestroy(ev0_);
   cudaEventDestroy(ev1_);
@@ -185,7 +186,30 @@ void Engine::end_tuple(const double* const eps[6], double factor) {
   open_ = false;
 }
 
+void Engine::add_antisym(const AntisymJob& job) {
+  ajobs_.push_back(job);
+  const long long n = (long long)job.n[0] * job.n[1] * job.n[2] * job.n[3];
+  if (n > max_ablock_) max_ablock_ = n;
+}
+
 void Engine::flush_repack() {
+  if (!ajobs_.empty()) {   // the spin-orbital blocks first: the repack jobs below read them (same stream)
+    const size_t bytes = ajobs_.size() * sizeof(AntisymJob);
+    if (bytes > d_ajobs_cap_) {
+      if (d_ajobs_) { NWC_CUDA(cudaStreamSynchronize(stream_)); NWC_CUDA(cudaFree(d_ajobs_)); }
+      d_ajobs_cap_ = std::max(bytes * 2, (size_t)1 << 16);
+      NWC_CUDA(cudaMalloc(&d_ajobs_, d_ajobs_cap_));
+    } else {
+      NWC_CUDA(cudaStreamSynchronize(stream_));
+    }
+    NWC_CUDA(cudaMemcpyAsync(d_ajobs_, ajobs_.data(), bytes, cudaMemcpyHostToDevice, stream_));
+    launch_antisym((const AntisymJob*)d_ajobs_, (int)ajobs_.size(), max_ablock_, stream_);
+    NWC_CUDA(cudaGetLastError());
+    stats.antisym_launches += (long long)((ajobs_.size() + 32767) / 32768);
+    stats.h2d_bytes += bytes;
+    ajobs_.clear();
+    max_ablock_ = 0;
+  }
   if (jobs_.empty()) return;
   const size_t bytes = jobs_.size() * sizeof(RepackJob);
   if (bytes > d_jobs_cap_) {

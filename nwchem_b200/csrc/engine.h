@@ -52,7 +52,7 @@ struct PanelSlot {
 
 struct EngineStats {
   double fused_ms = 0, repack_ms = 0;   // CUDA-event time of the kernels (when timing enabled)
-  long long fused_launches = 0, repack_launches = 0, reduce_launches = 0;
+  long long fused_launches = 0, repack_launches = 0, reduce_launches = 0, antisym_launches = 0;
   long long work_items = 0, descs = 0, tuples = 0;
   double flops = 0;                     // algorithmic FLOPs: 2*prod(R)*K per fired contraction, 2*prod(R) per singles
   size_t h2d_bytes = 0, d2h_bytes = 0;
@@ -82,7 +82,9 @@ class Engine {
 
   // ---- execution: runs every pending tuple in one batch; energies[2*i..] = (E1,E2) of tuple i ----
   void run(double* energies_out, double* dump_doubles = nullptr, double* dump_singles = nullptr);
-  void flush_repack();      // launch pending repack jobs now (asynchronous)
+  void flush_repack();      // launch pending antisym + repack jobs now (asynchronous)
+  // `2eorb`: queue the construction of one dense spin-orbital V2 block (job.dst must come from arena())
+  void add_antisym(const AntisymJob& job);
 
   EngineStats stats;
   bool timing = false;
@@ -100,6 +102,9 @@ class Engine {
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;
   std::vector<RepackJob> jobs_;
+  std::vector<AntisymJob> ajobs_;
+  long long max_ablock_ = 0;
+  void* d_ajobs_ = nullptr; size_t d_ajobs_cap_ = 0;
   long long max_panel_ = 0;
   long long items_ = 0;
   cudaEvent_t ev0_, ev1_, evt0_, evt1_;

@@ -7,6 +7,8 @@
 //   * native_abi.cu     : emit device-side repack jobs / descriptors against the HBM-resident block stores
 #pragma once
 #include <vector>
+#include <unordered_map>
+#include <string>
 #include <cstdio>
 #include <cstdlib>
 #include "../../include/nwc_triples.h"
@@ -28,7 +30,46 @@ struct HostState {
     evl.assign(s->evl_sorted, s->evl_sorted + ne);
     t1_hash.assign(s->t1_hash, s->t1_hash + 2 * s->t1_hash[0] + 1);
     t2_hash.assign(s->t2_hash, s->t2_hash + 2 * s->t2_hash[0] + 1);
-    v2_hash.assign(s->v2_hash, s->v2_hash + 2 * s->v2_hash[0] + 1);
+    if (s->v2_hash) v2_hash.assign(s->v2_hash, s->v2_hash + 2 * s->v2_hash[0] + 1); else v2_hash.assign(1, 0);
+    intorb = false;
+  }
+  // ---- `2eorb` storage (tce.fh intorb): V2 spin-free over the alpha tiles -------------------------------------
+  bool intorb = false;
+  Integer noa = 0, nva = 0;
+  std::vector<Integer> b2am, spin_alpha, sym_alpha, range_alpha;
+  std::unordered_map<Integer, Integer> orb_off;   // orbital block key -> offset in d_v2orb (every stored block)
+  Integer orb_size = 0;                           // doubles in d_v2orb
+  static Integer index_pair(Integer i, Integer j) { return (i * (i - 1)) / 2 + j; }   // tce_mo2e_offset_intorb.F:615
+  // Expands the checkpointed table k_v2_alpha_offset into a full key -> offset map by running the block loops of
+  // tce_mo2e_offset_intorb.F:32-50 once (tce_hash_v2 re-walks them from a checkpoint at every lookup) and checks
+  // every checkpoint of the caller's table against it.  Returns "" or an error text.
+  std::string load_orbital(Integer noa_, Integer nva_, const Integer* b2am_, const Integer* spin_a, const Integer* sym_a,
+                           const Integer* range_a, const Integer* table) {
+    noa = noa_; nva = nva_;
+    const Integer n = noa + nva;
+    b2am.assign(b2am_, b2am_ + noab + nvab);
+    spin_alpha.assign(spin_a, spin_a + n); sym_alpha.assign(sym_a, sym_a + n); range_alpha.assign(range_a, range_a + n);
+    orb_off.clear();
+    Integer size = 0;
+    for (Integer g3b = 1; g3b <= n; g3b++)
+      for (Integer g4b = g3b; g4b <= n; g4b++)
+        for (Integer g1b = 1; g1b <= n; g1b++)
+          for (Integer g2b = g1b; g2b <= n; g2b++) {
+            if (spin_alpha[g3b - 1] + spin_alpha[g4b - 1] != spin_alpha[g1b - 1] + spin_alpha[g2b - 1]) continue;
+            if ((sym_alpha[g3b - 1] ^ sym_alpha[g4b - 1] ^ sym_alpha[g1b - 1] ^ sym_alpha[g2b - 1]) != irrep_v) continue;
+            if (index_pair(g4b, g3b) < index_pair(g2b, g1b)) continue;
+            orb_off[g2b - 1 + n * (g1b - 1 + n * (g4b - 1 + n * (g3b - 1)))] = size;
+            size += range_alpha[g3b - 1] * range_alpha[g4b - 1] * range_alpha[g1b - 1] * range_alpha[g2b - 1];
+          }
+    orb_size = size;
+    const Integer length1 = table[0];
+    for (Integer pos = 1; pos <= length1 + 1; pos++) {
+      const Integer key = table[pos], off = table[(length1 + 1) + pos];
+      auto it = orb_off.find(key);
+      if (it == orb_off.end() || it->second != off) return "k_v2_alpha_offset does not match the alpha tiling (checkpoint " + std::to_string(pos) + ")";
+    }
+    intorb = true;
+    return "";
   }
   Integer sp(Integer b) const { return spin[b - 1]; }
   Integer sy(Integer b) const { return sym[b - 1]; }

@@ -79,6 +79,38 @@ __device__ __forceinline__ void dmma884x4_if(double (&c0)[2], double (&c1)[2], d
 }
 
 // ------------------------------------------------------------------------------------------------
+// `2eorb` V2: spin-orbital block from (up to) two orbital-form blocks -- the device form of the two
+// tce_sortacc_4 calls of get_block_ind_i (get_block_ind.F:1054-1244 direct, :1333-1523 exchange)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) antisym_kernel(const AntisymJob* __restrict__ jobs) {
+  const AntisymJob j = jobs[blockIdx.y];
+  const long long total = (long long)j.n[0] * j.n[1] * j.n[2] * j.n[3];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int x3 = (int)(r % j.n[3]); r /= j.n[3];
+    const int x2 = (int)(r % j.n[2]); r /= j.n[2];
+    const int x1 = (int)(r % j.n[1]); r /= j.n[1];
+    const int x0 = (int)r;
+    double v = 0.0;
+    if (j.a) v = j.ca * __ldg(j.a + x0 * j.sa[0] + x1 * j.sa[1] + x2 * j.sa[2] + x3 * j.sa[3]);
+    if (j.b) v = fma(j.cb, __ldg(j.b + x0 * j.sb[0] + x1 * j.sb[1] + x2 * j.sb[2] + x3 * j.sb[3]), v);
+    j.dst[e] = v;
+  }
+}
+
+void launch_antisym(const AntisymJob* d_jobs, int njobs, long long max_block_doubles, cudaStream_t stream) {
+  if (njobs <= 0) return;
+  long long bx = (max_block_doubles + 256 * 8 - 1) / (256 * 8);
+  if (bx < 1) bx = 1;
+  if (bx > 2048) bx = 2048;
+  for (int j0 = 0; j0 < njobs; j0 += 32768) {
+    int n = njobs - j0 < 32768 ? njobs - j0 : 32768;
+    antisym_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, stream>>>(d_jobs + j0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // repack: strided source -> blocked K4 panel (zero padded)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict__ jobs) {

@@ -53,12 +53,22 @@ struct RepackJob {      // build one panel from a strided source
   double scale;
 };
 
+struct AntisymJob {     // dense block dst[x0][x1][x2][x3] (x3 fastest) = ca*a[sum x_i*sa_i] + cb*b[sum x_i*sb_i]
+  double* dst;
+  const double* a;      // may be null (term absent)
+  const double* b;
+  long long sa[4], sb[4];
+  int n[4];
+  double ca, cb;
+};
+
 inline long long panel_doubles(int X1, int X2, int X3, int K) {
   auto c4 = [](int v) { return (long long)((v + 3) / 4); };
   return c4(K) * c4(X1) * c4(X2) * c4(X3) * BLK_DOUBLES;
 }
 
 // launchers (kernels.cu).  All asynchronous on `stream`.
+void launch_antisym(const AntisymJob* d_jobs, int njobs, long long max_block_doubles, cudaStream_t stream);
 void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
 // ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,

@@ -6,6 +6,8 @@
 #include "engine.h"
 #include "host_driver.h"
 #include <cstring>
+#include <algorithm>
+#include <unordered_map>
 #include <string>
 #include <dlfcn.h>
 
@@ -65,6 +67,10 @@ struct nwc_triples_ctx {
   std::vector<Integer> v2_shard_off;        // per table index: offset inside its owner's shard
   std::vector<double*> v2_peer;             // per rank: base of that rank's shard as seen from this process
   std::vector<char> v2_peer_opened;
+  // `2eorb` storage: orbital-form integrals resident, spin-orbital blocks built per batch in the arena
+  double* d_v2orb = nullptr;
+  size_t n_v2orb = 0;
+  std::unordered_map<Integer, const double*> v2_built;   // spin-orbital key -> block built since the last arena reset
 };
 
 namespace {
@@ -91,6 +97,70 @@ const double* v2_block(const nwc_triples_ctx* c, Integer key, const char* what) 
   return base + c->v2_shard_off[idx - 1];
 }
 
+// `2eorb`: <g3 g4||g1 g2> = (g3 g1|g4 g2) - (g3 g2|g4 g1) as one antisym job (get_block_ind.F:818-1538).
+// A Mulliken integral (ab|cd) with a in tile A, ... is read from the stored block whose row pair is the larger of
+// {A,B},{C,D} (index_pair order, larger tile first inside a pair); inside a block the element order is
+// (k l|i j): k (larger row tile) fastest, then l, then i (larger column tile), then j (tce_mo2e_trans.F:707-723).
+struct MullikenSrc { const double* base; long long stride[4]; };   // strides of the four arguments a,b,c,d
+
+MullikenSrc mulliken_source(const nwc_triples_ctx* c, const Integer tile[4]) {
+  const HostState& S = c->S;
+  const Integer n = S.noa + S.nva;
+  int ia = 0, ib = 1, ic = 2, id = 3;                       // argument slots: (a b | c d)
+  if (tile[ia] < tile[ib]) std::swap(ia, ib);               // larger tile first inside each pair
+  if (tile[ic] < tile[id]) std::swap(ic, id);
+  if (HostState::index_pair(tile[ia], tile[ib]) < HostState::index_pair(tile[ic], tile[id])) { std::swap(ia, ic); std::swap(ib, id); }
+  // now row pair = (ia, ib) -> (k, l), column pair = (ic, id) -> (i, j)
+  const Integer key = tile[ic] - 1 + n * (tile[id] - 1 + n * (tile[ia] - 1 + n * (tile[ib] - 1)));
+  auto it = S.orb_off.find(key);
+  if (it == S.orb_off.end()) { printf("nwc_triples: orbital V2 block key %ld not found\n", key); fflush(stdout); exit(1); }
+  MullikenSrc m;
+  m.base = c->d_v2orb + it->second;
+  const long long rk = S.range_alpha[tile[ia] - 1], rl = S.range_alpha[tile[ib] - 1], ri = S.range_alpha[tile[ic] - 1];
+  m.stride[ia] = 1; m.stride[ib] = rk; m.stride[ic] = rk * rl; m.stride[id] = rk * rl * ri;
+  return m;
+}
+
+const double* v2_block_2eorb(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g1b, Integer g2b) {
+  const HostState& S = c->S;
+  const Integer skey = v2_key(S, g3b, g4b, g1b, g2b);
+  auto hit = c->v2_built.find(skey);
+  if (hit != c->v2_built.end()) return hit->second;
+  AntisymJob j{};
+  j.n[0] = (int)S.rg(g3b); j.n[1] = (int)S.rg(g4b); j.n[2] = (int)S.rg(g1b); j.n[3] = (int)S.rg(g2b);
+  const size_t bytes = sizeof(double) * (size_t)j.n[0] * j.n[1] * j.n[2] * j.n[3];
+  j.dst = (double*)c->eng->arena().alloc(bytes);
+  const Integer s3 = S.sp(g3b), s4 = S.sp(g4b), s1 = S.sp(g1b), s2 = S.sp(g2b);
+  const Integer a3 = S.b2am[g3b - 1], a4 = S.b2am[g4b - 1], a1 = S.b2am[g1b - 1], a2 = S.b2am[g2b - 1];
+  if (s3 == s1 && s4 == s2) {   // direct (g3 g1|g4 g2): uaadaa, ubbdbb, uabdab, ubadba (get_block_ind.F:983)
+    const Integer tile[4] = {a3, a1, a4, a2};
+    const MullikenSrc m = mulliken_source(c, tile);
+    j.a = m.base; j.ca = 1.0;
+    j.sa[0] = m.stride[0]; j.sa[2] = m.stride[1]; j.sa[1] = m.stride[2]; j.sa[3] = m.stride[3];   // x0=g3,x1=g4,x2=g1,x3=g2
+  }
+  if (s3 == s2 && s4 == s1) {   // exchange (g3 g2|g4 g1): uaadaa, ubbdbb, uabdba, ubadab (:1264)
+    const Integer tile[4] = {a3, a2, a4, a1};
+    const MullikenSrc m = mulliken_source(c, tile);
+    j.b = m.base; j.cb = -1.0;
+    j.sb[0] = m.stride[0]; j.sb[3] = m.stride[1]; j.sb[1] = m.stride[2]; j.sb[2] = m.stride[3];
+  }
+  c->eng->add_antisym(j);
+  c->v2_built[skey] = j.dst;
+  return j.dst;
+}
+
+// V2 block <g3 g4||g1 g2> (tile ids after tce_restricted_4), from whichever storage the context holds
+const double* v2_operand(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g1b, Integer g2b, const char* what) {
+  if (c->S.intorb) return v2_block_2eorb(c, g3b, g4b, g1b, g2b);
+  return v2_block(c, v2_key(c->S, g3b, g4b, g1b, g2b), what);
+}
+
+// the arena is about to be rewound: blocks built in it are gone
+void reset_arena(nwc_triples_ctx* c) {
+  c->eng->arena().reset();
+  c->v2_built.clear();
+}
+
 struct NativeSink {
   nwc_triples_ctx* c;
   Engine& e;
@@ -103,7 +173,7 @@ struct NativeSink {
     t.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
     t.stride[N_H1] = 1; t.stride[N_P4] = S.rg(r.h1b);
     // V2 block <p5 p6||h2 h3> stored (p5,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,p5)
-    v.base = v2_block(c, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
+    v.base = v2_operand(c, p5b_2, p6b_2, h2b_2, h3b_2, "v2(pphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.stride[N_P5] = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
     for (int k = 0; k < 9; k++)
@@ -124,7 +194,7 @@ struct NativeSink {
       sign = 1.0;
     }
     // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
-    v.base = v2_block(c, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");
+    v.base = v2_operand(c, bm[1], bm[0], bm[2], bm[3], "v2(hphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.kstride = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
     std::vector<PanelSlot> tc, vc;
@@ -146,7 +216,7 @@ struct NativeSink {
       sign = 1.0;
     }
     // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161)
-    v.base = v2_block(c, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");
+    v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
     v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
     std::vector<PanelSlot> tc, vc;
@@ -220,7 +290,7 @@ int nwc_triples_destroy(nwc_triples_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (size_t r = 0; r < c->v2_peer.size(); r++)
     if (c->v2_peer_opened[r] && c->v2_peer[r]) cudaIpcCloseMemHandle(c->v2_peer[r]);
-  cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_evl); cudaFree(c->d_red);
+  cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl); cudaFree(c->d_red);
   delete c->eng;
   delete c;
   return 0;
@@ -236,6 +306,28 @@ int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
   size_t ne;
   if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
   c->v2_nshards = 1; c->v2_rank = 0;
+  build_task_list(S, c->klist);
+  return 0;
+}
+
+int nwc_triples_set_state_2eorb(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  nwc_tce_state s2 = *st;
+  s2.v2_hash = nullptr;   // not read in this mode
+  c->S.load_tables(&s2);
+  HostState& S = c->S;
+  const std::string err = S.load_orbital(orb->noa, orb->nva, orb->b2am, orb->spin_alpha, orb->sym_alpha,
+                                         orb->range_alpha, orb->v2orb_hash);
+  if (!err.empty()) { g_err = err; return 1; }
+  if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
+  if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
+  if (upload(&c->d_v2orb, &c->n_v2orb, orb->v2orb, (size_t)S.orb_size, c->eng)) return 1;
+  if (c->d_v2) { cudaFree(c->d_v2); c->d_v2 = nullptr; }
+  c->n_v2 = 0;
+  size_t ne;
+  if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
+  c->v2_nshards = 1; c->v2_rank = 0;
+  c->v2_built.clear();
   build_task_list(S, c->klist);
   return 0;
 }
@@ -331,7 +423,7 @@ int nwc_triples_run(nwc_triples_ctx* c, Integer first, Integer stride, Integer m
       if (per_task) { per_task[2 * (out_pos + i)] = eb[2 * i]; per_task[2 * (out_pos + i) + 1] = eb[2 * i + 1]; }
     }
     out_pos += n;
-    e.arena().reset();
+    reset_arena(c);
   };
   for (Integer k = first; k < nt && (max_tasks <= 0 || done < max_tasks); k += stride, done++) {
     emit_tuple(c, &c->klist[7 * k]);
@@ -360,7 +452,7 @@ int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, I
       eb.assign(2 * (size_t)n, 0.0);
       e.run(eb.data());
       for (int i = 0; i < n; i++) { en[0] += eb[2 * i]; en[1] += eb[2 * i + 1]; }
-      e.arena().reset();
+      reset_arena(c);
     };
     Integer count = 0;   // position in this outer tile's loop order (ccsd_t_restart.F:120-150)
     for (Integer p5 = p4; p5 <= n1; p5++)
@@ -414,7 +506,7 @@ int nwc_triples_run_tuple(nwc_triples_ctx* c, const Integer t[6], double energy[
     NWC_TRY(cudaMemcpy(host_doubles, dd, sz * sizeof(double), cudaMemcpyDeviceToHost));
     NWC_TRY(cudaMemcpy(host_singles, ds, sz * sizeof(double), cudaMemcpyDeviceToHost));
   }
-  e.arena().reset();
+  reset_arena(c);
   energy[0] = out[0];
   energy[1] = out[1];
   return 0;
@@ -428,7 +520,7 @@ int nwc_triples_get_stats(nwc_triples_ctx* c, nwc_triples_stats* o, int reset) {
   o->fused_launches = s.fused_launches; o->repack_launches = s.repack_launches; o->reduce_launches = s.reduce_launches;
   o->work_items = s.work_items; o->descs = s.descs; o->tuples = s.tuples; o->flops = s.flops;
   o->h2d_bytes = (double)s.h2d_bytes; o->d2h_bytes = (double)s.d2h_bytes;
-  o->resident_bytes = 8.0 * (double)(c->n_t1 + c->n_t2 + c->n_v2);
+  o->resident_bytes = 8.0 * (double)(c->n_t1 + c->n_t2 + c->n_v2 + c->n_v2orb);
   if (reset) c->eng->stats = EngineStats();
   return 0;
 }

@@ -13,11 +13,20 @@ from . import tiling as tl
 
 
 @dataclasses.dataclass
+class OrbitalV2:
+    """`2eorb` storage of the two-electron integrals (tce intorb): spin-free blocks over the alpha tiles."""
+    a: tl.AlphaTiling
+    v2orb_hash: np.ndarray    # k_v2_alpha_offset (checkpointed table, tce_mo2e_offset_intorb.F)
+    v2orb: np.ndarray         # d_v2orb
+
+
+@dataclasses.dataclass
 class BlockStores:
     t: tl.Tiling
     t1_hash: np.ndarray; t1: np.ndarray
     t2_hash: np.ndarray; t2: np.ndarray
     v2_hash: np.ndarray; v2: np.ndarray
+    orb: OrbitalV2 | None = None   # when set, V2 is read from the orbital-form store instead of v2_hash/v2
 
 
 def _iter_hash(h):
@@ -35,7 +44,15 @@ def random_blocks(t: tl.Tiling, seed: int = 20240229, scale=(0.05, 0.02, 0.1)) -
     return BlockStores(t, t1h, t1, t2h, t2, v2h, v2)
 
 
-def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12) -> BlockStores:
+def random_orbital(t: tl.Tiling, seed: int = 20240229, scale: float = 0.1) -> OrbitalV2:
+    """iid orbital-form V2 store for large shapes (timing, oracle-vs-GPU parity); not tied to a spin-orbital store."""
+    a = tl.alpha_tiling(t)
+    tab, size = tl.v2orb_offset(a)
+    rng = np.random.default_rng(seed + 1)
+    return OrbitalV2(a, tab, rng.uniform(-1, 1, size) * scale)
+
+
+def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = False) -> BlockStores:
     """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts.
     With an unrestricted tiling (t.restricted False) the same closed-shell tensors are expanded into every spin
     block (beta tiles are their own owners), so E[T]/E(T) must equal the restricted result: a check of the
@@ -100,7 +117,20 @@ def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12) -> BlockStores:
     for key, off in _iter_hash(v2h):
         blk = v_block(*tl.decode_v2_key(t, key))
         v2[off:off + blk.size] = blk.ravel()
-    return BlockStores(t, t1h, t1, t2h, t2, v2h, v2)
+    orb = None
+    if intorb:
+        # the same integrals in `2eorb` form: block (g3b<=g4b | g1b<=g2b) over alpha tiles holds (k l|i j) with
+        # k in g4b fastest, then l in g3b, i in g2b, j in g1b (tce_mo2e_trans.F:707-723)
+        a = tl.alpha_tiling(t)
+        tab, size = tl.v2orb_offset(a)
+        blocks, _ = tl.v2orb_blocks(a)
+        vo = np.zeros(size)
+        for g3b, g4b, g1b, g2b, key, off, n in blocks:
+            mk, ml, mi, mj = a.members[g4b - 1], a.members[g3b - 1], a.members[g2b - 1], a.members[g1b - 1]
+            blk = eri[np.ix_(mk, ml, mi, mj)].transpose(3, 2, 1, 0)   # [j][i][l][k], k fastest
+            vo[off:off + n] = blk.ravel()
+        orb = OrbitalV2(a, tab, vo)
+    return BlockStores(t, t1h, t1, t2h, t2, v2h, v2, orb)
 
 
 # ---- named shapes of BASELINE.json's configs (alpha occ / alpha virt, C1 unless stated) ----

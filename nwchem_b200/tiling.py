@@ -189,3 +189,101 @@ def decode_v2_key(t: Tiling, key: int):
     g1b = key % N + 1; key //= N
     g4b = key % N + 1; key //= N
     return key + 1, g4b, g1b, g2b  # (g3b,g4b,g1b,g2b)
+
+
+# ------------------------------------------------------------------------------------------------
+# `2eorb` storage (intorb): V2 kept spin-free over the alpha tiles, SURVEY 8f-2
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class AlphaTiling:
+    """The alpha-space arrays tce_tile.F builds when intorb is set (tce_tile.F:1156-1212, :1376-1383):
+    noa hole + nva particle tiles; b2am maps every spin-orbital tile (1-based) to its alpha-space tile."""
+    noa: int
+    nva: int
+    b2am: np.ndarray          # [noab+nvab]
+    spin_alpha: np.ndarray    # [noa+nva] (all 1 for a closed-shell reference)
+    sym_alpha: np.ndarray
+    range_alpha: np.ndarray
+    members: list             # spatial orbital ids of each alpha tile
+
+
+def alpha_tiling(t: Tiling) -> AlphaTiling:
+    """No active tiles (activecalc off): hole beta j -> hole alpha j, particle beta j -> particle alpha j."""
+    noa = int(np.sum(t.spin[:t.noab] == 1)); nob = t.noab - noa
+    nva = int(np.sum(t.spin[t.noab:] == 1)); nvb = t.nvab - nva
+    if (nob, nvb) != (noa, nva):
+        raise ValueError("2eorb needs a closed-shell tiling (same alpha and beta tiles)")
+    b2am = np.zeros(t.noab + t.nvab, dtype=I64)
+    b2am[:noa] = np.arange(1, noa + 1)                         # hole alpha          (tce_tile.F:1162-1164)
+    b2am[noa:t.noab] = np.arange(1, noa + 1)                   # hole beta           (:1166-1172)
+    b2am[t.noab:t.noab + nva] = noa + np.arange(1, nva + 1)    # particle alpha      (:1174-1176)
+    b2am[t.noab + nva:] = noa + np.arange(1, nva + 1)          # particle beta       (:1192-1207)
+    idx = list(range(noa)) + list(range(t.noab, t.noab + nva))
+    return AlphaTiling(noa, nva, b2am, np.ones(noa + nva, dtype=I64), t.sym[idx].copy(), t.range[idx].copy(),
+                       [t.members[i] for i in idx])
+
+
+def index_pair(i: int, j: int) -> int:   # tce_mo2e_offset_intorb.F:615
+    return (i * (i - 1)) // 2 + j
+
+
+def v2orb_blocks(a: AlphaTiling, irrep_v: int = 0):
+    """Stored orbital blocks in storage order: (g3b, g4b, g1b, g2b, key, offset, size), tce_mo2e_offset_intorb.F:32-50."""
+    N = a.noa + a.nva
+    out, size = [], 0
+    for g3b in range(1, N + 1):
+        for g4b in range(g3b, N + 1):
+            for g1b in range(1, N + 1):
+                for g2b in range(g1b, N + 1):
+                    if a.spin_alpha[g3b - 1] + a.spin_alpha[g4b - 1] != a.spin_alpha[g1b - 1] + a.spin_alpha[g2b - 1]:
+                        continue
+                    if (a.sym_alpha[g3b - 1] ^ a.sym_alpha[g4b - 1] ^ a.sym_alpha[g1b - 1] ^ a.sym_alpha[g2b - 1]) != irrep_v:
+                        continue
+                    if index_pair(g4b, g3b) < index_pair(g2b, g1b):
+                        continue
+                    n = int(a.range_alpha[g3b - 1] * a.range_alpha[g4b - 1] * a.range_alpha[g1b - 1] * a.range_alpha[g2b - 1])
+                    key = g2b - 1 + N * (g1b - 1 + N * (g4b - 1 + N * (g3b - 1)))
+                    out.append((g3b, g4b, g1b, g2b, key, size, n))
+                    size += n
+    return out, size
+
+
+def v2orb_offset(a: AlphaTiling, irrep_v: int = 0, idiv2e: int = 2):
+    """The checkpointed offset table `k_v2_alpha_offset` exactly as tce_mo2e_offset_intorb.F:52-150 lays it out:
+    [length1 | keys(length1+1) | offsets | g3b | g4b | g1b | g2b], one entry per `ipiece_l` stored blocks
+    (idiv2e = 2 in tce_energy.F:673); tce_hash_v2 walks the block loops from the nearest checkpoint."""
+    blocks, size = v2orb_blocks(a, irrep_v)
+    length = len(blocks)
+    ipiece_l = length // idiv2e
+    if ipiece_l * idiv2e == length:
+        length1 = idiv2e
+    else:
+        length1 = idiv2e + 1
+    if length == 0 or ipiece_l == 0:
+        raise ValueError("too few orbital blocks for idiv2e checkpoints")
+    tab = np.zeros(6 * (length1 + 1) + 1, dtype=I64)
+    tab[0] = length1
+    ipos, i_counter, addr = 1, 0, 0
+
+    def put(pos, blk):
+        g3b, g4b, g1b, g2b, key, off, _ = blk
+        tab[pos] = key
+        tab[(length1 + 1) + pos] = off
+        tab[2 * (length1 + 1) + pos] = g3b
+        tab[3 * (length1 + 1) + pos] = g4b
+        tab[4 * (length1 + 1) + pos] = g1b
+        tab[5 * (length1 + 1) + pos] = g2b
+
+    last = None
+    for blk in blocks:
+        i_counter += 1
+        if addr == 0:
+            put(ipos, blk); ipos += 1
+        if i_counter == ipiece_l:
+            put(ipos, blk); ipos += 1
+            i_counter = 0
+        addr += 1
+        last = blk
+    if i_counter != 0:
+        put(ipos, last)
+    return tab, size

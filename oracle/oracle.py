@@ -22,7 +22,9 @@ def build(quiet=True):
 class Ctx(C.Structure):
     _fields_ = [("noab", L), ("nvab", L), ("restricted", L), ("irrep_t", L), ("irrep_v", L),
                 ("spin", PL), ("sym", PL), ("range", PL), ("offset", PL), ("alpha", PL), ("evl_sorted", PD),
-                ("t1_hash", PL), ("t1", PD), ("t2_hash", PL), ("t2", PD), ("v2_hash", PL), ("v2", PD)]
+                ("t1_hash", PL), ("t1", PD), ("t2_hash", PL), ("t2", PD), ("v2_hash", PL), ("v2", PD),
+                ("intorb", L), ("noa", L), ("nva", L), ("b2am", PL), ("spin_alpha", PL), ("sym_alpha", PL),
+                ("range_alpha", PL), ("v2orb_hash", PL), ("v2orb", PD)]
 
 
 class Counts(C.Structure):
@@ -71,6 +73,15 @@ def make_ctx(st):
     c = Ctx(t.noab, t.nvab, int(t.restricted), 0, 0, _pl(arrs["spin"]), _pl(arrs["sym"]), _pl(arrs["range"]),
             _pl(arrs["offset"]), _pl(arrs["alpha"]), _pd(arrs["evl"]), _pl(arrs["t1h"]), _pd(arrs["t1"]),
             _pl(arrs["t2h"]), _pd(arrs["t2"]), _pl(arrs["v2h"]), _pd(arrs["v2"]))
+    orb = getattr(st, "orb", None)
+    if orb is not None:   # `2eorb` storage: V2 comes from the orbital-form store (synth.OrbitalV2)
+        a = orb.a
+        arrs.update(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
+                    sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
+                    voh=np.ascontiguousarray(orb.v2orb_hash, np.int64), vo=np.ascontiguousarray(orb.v2orb, np.float64))
+        c.intorb = 1; c.noa = a.noa; c.nva = a.nva
+        c.b2am = _pl(arrs["b2am"]); c.spin_alpha = _pl(arrs["spa"]); c.sym_alpha = _pl(arrs["sya"])
+        c.range_alpha = _pl(arrs["rga"]); c.v2orb_hash = _pl(arrs["voh"]); c.v2orb = _pd(arrs["vo"])
     return c, arrs
 
 
@@ -111,6 +122,29 @@ def ccsd_t_restart(st, begin=1, table=None, max_outer=0):
     if l.ora_error():
         raise RuntimeError("oracle: block key not found")
     return int(b.value), tab, float(te.value), int(done)
+
+
+def hash_v2(orb, key, irrep_v=0):
+    """tce_hash_v2 on an orbital-form store (synth.OrbitalV2): offset of block `key` or -1."""
+    l = lib()
+    a = orb.a
+    l.ora_tce_hash_v2.restype = L
+    h = np.ascontiguousarray(orb.v2orb_hash, np.int64)
+    sp = np.ascontiguousarray(a.spin_alpha, np.int64); sy = np.ascontiguousarray(a.sym_alpha, np.int64)
+    rg = np.ascontiguousarray(a.range_alpha, np.int64)
+    return int(l.ora_tce_hash_v2(_pl(h), L(key), L(a.noa), L(a.nva), _pl(sp), _pl(sy), _pl(rg), L(irrep_v)))
+
+
+def v2_block_intorb(st, g3b, g4b, g1b, g2b):
+    """get_block_ind_i: the antisymmetrised spin-orbital block <g3b g4b||g1b g2b> built from the orbital store."""
+    l = lib()
+    c, keep = make_ctx(st)
+    n = st.t.r(g3b) * st.t.r(g4b) * st.t.r(g1b) * st.t.r(g2b)
+    out = np.zeros(n)
+    l.ora_get_block_ind_i(C.byref(c), _pd(out), L(n), L(g2b), L(g1b), L(g4b), L(g3b))
+    if l.ora_error():
+        raise RuntimeError("oracle: orbital block not found")
+    return out
 
 
 def tuple_tiles(st, tup):

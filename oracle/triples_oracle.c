@@ -280,6 +280,15 @@ typedef struct {
   const Integer *t1_hash; const double *t1; /* tce_t1_offset_new.F */
   const Integer *t2_hash; const double *t2; /* tce_t2_offset_new.F */
   const Integer *v2_hash; const double *v2; /* tce_mo2e_offset.F   */
+  /* `2eorb` storage (tce.fh: intorb): V2 spin-free over the alpha tiles, antisymmetrised block by block */
+  Integer intorb;                /* 0: v2_hash/v2 above; 1: the fields below replace them */
+  Integer noa, nva;              /* alpha hole / particle tiles */
+  const Integer *b2am;           /* k_b2am       [noab+nvab] spin-orbital tile -> alpha-space tile (tce_tile.F:1156-1212) */
+  const Integer *spin_alpha;     /* k_spin_alpha [noa+nva] */
+  const Integer *sym_alpha;      /* k_sym_alpha  */
+  const Integer *range_alpha;    /* k_range_alpha */
+  const Integer *v2orb_hash;     /* k_v2_alpha_offset: checkpointed table of tce_mo2e_offset_intorb.F */
+  const double *v2orb;           /* d_v2orb */
 } ora_ctx;
 
 #define SPIN(b) (c->spin[(b) - 1])
@@ -296,6 +305,147 @@ static void restricted_4(const ora_ctx *c, Integer a1, Integer a2, Integer a3, I
   if (c->restricted && SPIN(a1) + SPIN(a2) + SPIN(a3) + SPIN(a4) == 8) {
     *b1 = c->alpha[a1 - 1]; *b2 = c->alpha[a2 - 1]; *b3 = c->alpha[a3 - 1]; *b4 = c->alpha[a4 - 1];
   } else { *b1 = a1; *b2 = a2; *b3 = a3; *b4 = a4; }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* `2eorb` V2: get_hash_block_i (get_hash_block.F:47-118) -> get_block_ind_i */
+/* (get_block_ind.F:818-1538), offsets by tce_hash_v2 (tce_hash.F:1-135)                    */
+/* ------------------------------------------------------------------------------------ */
+static Integer index_pair(Integer i, Integer j) { return (i * (i - 1)) / 2 + j; } /* tce_mo2e_offset_intorb.F:615 */
+static Integer indx_point(Integer i, Integer j, Integer n) { return (i * (2 * n + 1 - i)) / 2 - n + j; } /* tce_hash.F:27 */
+
+/* tce_sortacc_4: src/tce/sort/tce_sortacc4.F (sorted += factor * permuted unsorted) */
+void ora_tce_sortacc_4(const double *unsorted, double *sorted, Integer a, Integer b, Integer c, Integer d,
+                       Integer i, Integer j, Integer k, Integer l, double factor) {
+  Integer jd[4] = {a, b, c, d};
+  Integer id[4];
+  for (id[0] = 0; id[0] < a; id[0]++)
+    for (id[1] = 0; id[1] < b; id[1]++)
+      for (id[2] = 0; id[2] < c; id[2]++)
+        for (id[3] = 0; id[3] < d; id[3]++) {
+          Integer ia = id[3] + d * (id[2] + c * (id[1] + b * id[0]));
+          Integer ib = id[l - 1] + jd[l - 1] * (id[k - 1] + jd[k - 1] * (id[j - 1] + jd[j - 1] * id[i - 1]));
+          sorted[ib] += unsorted[ia] * factor;
+        }
+}
+
+/* tce_hash_v2 (tce_hash.F:1-135): offset of the orbital block `key`, found by walking the block loops of
+ * tce_mo2e_offset_intorb.F from the checkpoint below it.  Returns -1 if the key is not stored. */
+Integer ora_tce_hash_v2(const Integer *hash, Integer key, Integer noa, Integer nva, const Integer *spin_alpha,
+                        const Integer *sym_alpha, const Integer *range_alpha, Integer irrep_v) {
+  const Integer length = hash[0], n = noa + nva;
+  Integer middle = -1;
+  for (Integer i = 1; i <= length; i++)
+    if (hash[i] <= key && key <= hash[i + 1]) { middle = i; break; } /* :33-38 */
+  if (middle < 0) return -1;
+#define H(blockno, pos) hash[(blockno) * (length + 1) + (pos)]
+  Integer i = H(2, middle), j = H(3, middle), k = H(4, middle), l = H(5, middle);           /* :44-47 */
+  const Integer i_stop = H(2, middle + 1), j_stop = H(3, middle + 1), k_stop = H(4, middle + 1),
+                l_stop = H(5, middle + 1);                                                   /* :49-52 */
+  Integer offset = H(1, middle);                                                             /* :54 */
+#undef H
+  const Integer pos1_l = indx_point(i, j, n), pos1_u = indx_point(i_stop, j_stop, n);
+  for (Integer pos1 = pos1_l; pos1 <= pos1_u; pos1++) { /* :66 */
+    const Integer sa_ij = spin_alpha[i - 1] + spin_alpha[j - 1];
+    for (;;) { /* label 100 */
+      const Integer sa_kl = spin_alpha[k - 1] + spin_alpha[l - 1];
+      const Integer ieo_kl = sym_alpha[k - 1] ^ sym_alpha[l - 1];
+      if (sa_ij == sa_kl && (sym_alpha[i - 1] ^ sym_alpha[j - 1] ^ ieo_kl) == irrep_v &&
+          index_pair(j, i) >= index_pair(l, k)) { /* :82-89 */
+        const Integer key_loop = l - 1 + n * (k - 1 + n * (j - 1 + n * (i - 1)));
+        if (key_loop == key) return offset; /* :92 */
+        offset += range_alpha[i - 1] * range_alpha[j - 1] * range_alpha[k - 1] * range_alpha[l - 1];
+      }
+      if (i == i_stop && j == j_stop && k == k_stop && l == l_stop) return -1; /* :99-100 -> errquit */
+      if (k == n && l == n) break;                                             /* :101 -> 200 */
+      if (l == n) { k = k + 1; l = k; } else l = l + 1;                        /* :102-107 */
+    }
+    k = 1; l = 1; /* :113-114 */
+    if (pos1 + 1 == indx_point(i + 1, i + 1, n)) { i = i + 1; j = i; } else j = j + 1; /* :117-122 */
+  }
+  return -1;
+}
+
+/* the 8 + 8 tce_sortacc_4 calls of get_block_ind_i: operand sizes (as indices into size1..size4) and the
+ * permutation, indexed by (pair order swapped, first index pair swapped, second index pair swapped) */
+typedef struct { int dims[4]; int perm[4]; } sortcase;
+static const sortcase DIRECT_CASES[2][2][2] = { /* [lp31p42][l31s][l42s], get_block_ind.F:1054-1244 */
+    {{{{2, 1, 4, 3}, {4, 2, 3, 1}}, {{4, 2, 1, 3}, {4, 1, 3, 2}}},
+     {{{2, 4, 3, 1}, {3, 2, 4, 1}}, {{4, 2, 3, 1}, {3, 1, 4, 2}}}},
+    {{{{1, 3, 2, 4}, {2, 4, 1, 3}}, {{1, 3, 4, 2}, {2, 3, 1, 4}}},
+     {{{3, 1, 2, 4}, {1, 4, 2, 3}}, {{3, 1, 4, 2}, {1, 3, 2, 4}}}}};
+static const sortcase EXCHANGE_CASES[2][2][2] = { /* [lp32p41][l32s][l41s], get_block_ind.F:1333-1523 */
+    {{{{1, 4, 2, 3}, {4, 2, 1, 3}}, {{2, 1, 4, 3}, {4, 1, 2, 3}}},
+     {{{1, 4, 3, 2}, {3, 2, 1, 4}}, {{1, 4, 3, 2}, {3, 1, 2, 4}}}},
+    {{{{2, 3, 1, 4}, {2, 4, 3, 1}}, {{2, 1, 4, 3}, {2, 3, 4, 1}}},
+     {{{3, 2, 1, 4}, {1, 4, 3, 2}}, {{3, 2, 1, 4}, {1, 3, 4, 2}}}}};
+
+static Integer orb_key(Integer n, Integer a1, Integer b1, Integer a2, Integer b2) {
+  /* get_block_ind.F:884-918: the pairs (a1,b1) and (a2,b2), each ordered larger first, the larger pair first */
+  Integer i = a1 >= b1 ? a1 : b1, j = a1 >= b1 ? b1 : a1;
+  Integer k = a2 >= b2 ? a2 : b2, l = a2 >= b2 ? b2 : a2;
+  if (index_pair(i, j) >= index_pair(k, l)) return k - 1 + n * (l - 1 + n * (i - 1 + n * (j - 1)));
+  return i - 1 + n * (j - 1 + n * (k - 1 + n * (l - 1)));
+}
+
+/* get_block_ind_i (ioalg = 2): array(size) := v^{g3b g4b}_{g1b g2b} = (g3 g1|g4 g2) - (g3 g2|g4 g1) */
+void ora_get_block_ind_i(const ora_ctx *c, double *array, Integer size, Integer w2b, Integer w1b, Integer w4b,
+                         Integer w3b) {
+  const Integer n = c->noa + c->nva;
+  const Integer g3b = w3b, g4b = w4b, g1b = w1b, g2b = w2b;
+  const Integer ig1b = c->b2am[g1b - 1], ig2b = c->b2am[g2b - 1], ig3b = c->b2am[g3b - 1], ig4b = c->b2am[g4b - 1];
+  const Integer first_h = orb_key(n, ig1b, ig3b, ig2b, ig4b);  /* :884-918 */
+  const Integer second_h = orb_key(n, ig2b, ig3b, ig1b, ig4b); /* :919-947 */
+  const Integer s3 = SPIN(g3b), s4 = SPIN(g4b), s1 = SPIN(g1b), s2 = SPIN(g2b);
+  const Integer ispin = s3 + s4 + s1 + s2;
+  const int uaadaa = ispin == 4, ubbdbb = ispin == 8;
+  const int uabdab = s3 == 1 && s4 == 2 && s1 == 1 && s2 == 2, ubadba = s3 == 2 && s4 == 1 && s1 == 2 && s2 == 1;
+  const int ubadab = s3 == 2 && s4 == 1 && s1 == 1 && s2 == 2, uabdba = s3 == 1 && s4 == 2 && s1 == 2 && s2 == 1;
+  const Integer sz[5] = {0, RANGE(g1b), RANGE(g2b), RANGE(g3b), RANGE(g4b)};
+  double *f_a = (double *)malloc(sizeof(double) * (size_t)size);
+  for (int half = 0; half < 2; half++) {
+    int fire, sw_a, sw_b, lp;
+    Integer key_alpha;
+    if (half == 0) { /* ( g3 g1 | g4 g2 ), :990-1260 */
+      fire = uaadaa || ubbdbb || uabdab || ubadba;
+      key_alpha = first_h;
+      sw_a = !(ig3b >= ig1b); /* l31s */
+      sw_b = !(ig4b >= ig2b); /* l42s */
+      Integer irow = sw_a ? index_pair(ig1b, ig3b) : index_pair(ig3b, ig1b);
+      Integer icol = sw_b ? index_pair(ig2b, ig4b) : index_pair(ig4b, ig2b);
+      lp = !(irow >= icol); /* lp31p42 */
+      if (fire) memset(array, 0, sizeof(double) * (size_t)size); /* :1041-1046 */
+    } else { /* ( g3 g2 | g4 g1 ), :1264-1538 */
+      fire = uaadaa || ubbdbb || uabdba || ubadab;
+      key_alpha = second_h;
+      sw_a = !(ig3b >= ig2b); /* l32s */
+      sw_b = !(ig4b >= ig1b); /* l41s */
+      Integer irow = sw_a ? index_pair(ig2b, ig3b) : index_pair(ig3b, ig2b);
+      Integer icol = sw_b ? index_pair(ig1b, ig4b) : index_pair(ig4b, ig1b);
+      lp = !(irow >= icol); /* lp32p41 */
+      if (fire && (uabdba || ubadab)) memset(array, 0, sizeof(double) * (size_t)size); /* :1295-1301 */
+    }
+    if (!fire) continue;
+    const Integer off_a = ora_tce_hash_v2(c->v2orb_hash, key_alpha, c->noa, c->nva, c->spin_alpha, c->sym_alpha,
+                                          c->range_alpha, c->irrep_v);
+    if (off_a < 0) {
+      fprintf(stderr, "oracle: tce_hash_v2: key not found %ld\n", key_alpha);
+      g_error = 1;
+      continue;
+    }
+    memcpy(f_a, c->v2orb + off_a, sizeof(double) * (size_t)size); /* ga_get(d_v2orb, off_a+1, off_a+size) */
+    const sortcase *sc = half == 0 ? &DIRECT_CASES[lp][sw_a][sw_b] : &EXCHANGE_CASES[lp][sw_a][sw_b];
+    ora_tce_sortacc_4(f_a, array, sz[sc->dims[0]], sz[sc->dims[1]], sz[sc->dims[2]], sz[sc->dims[3]], sc->perm[0],
+                      sc->perm[1], sc->perm[2], sc->perm[3], half == 0 ? 1.0 : -1.0);
+  }
+  free(f_a);
+}
+
+/* get_hash_block_i (get_hash_block.F:47-118): V2 block by key, from whichever storage the run uses */
+static void get_v2_block(const ora_ctx *c, double *array, Integer size, Integer key, Integer g2b, Integer g1b,
+                         Integer g4b, Integer g3b) {
+  if (!c->intorb) get_hash_block(c->v2, array, size, c->v2_hash, key);
+  else ora_get_block_ind_i(c, array, size, g2b, g1b, g4b, g3b);
 }
 
 /* de-duplication of the 9-row permutation table (ccsd_t_singles_l.F / ccsd_t_singles_gpu.F:166-182) */
@@ -365,8 +515,8 @@ void ora_ccsd_t_singles_l(const ora_ctx *c, double *a_c, Integer t_h1b, Integer 
       k_b_sort = (double *)malloc(sizeof(double) * dimb);
       get_hash_block(c->t1, k_a, dima, c->t1_hash, h1b_1 - 1 + c->noab * (p4b_1 - c->noab - 1)); /* :234 */
       ora_tce_sort_2(k_a, k_a_sort, RANGE(p4b), RANGE(h1b), 2, 1, 1.0); /* :237 */
-      get_hash_block(c->v2, k_b_sort, dimb, c->v2_hash,
-                     h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1)))); /* :246 */
+      get_v2_block(c, k_b_sort, dimb, h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1))), h3b_2, h2b_2,
+                   p6b_2, p5b_2); /* :246 / :253-263 */
     }
     /* nine dispatch tests (ccsd_t_singles_gpu.F:281,310,340,370,401,431,462,493,524):
      * test K holds when (t_p4b,t_p5b,t_p6b) == row permuted by TP[K] and (t_h..) by TH[K] */
@@ -418,8 +568,8 @@ static int hashnsort(const ora_ctx *c, int dryrun, Integer p4b, Integer p5b, Int
     }
     free(k_a);
     if (h7b <= p6b) /* :66-80 (always true: occupied tiles precede virtual tiles) */
-      get_hash_block(c->v2, v2sub, dimb, c->v2_hash,
-                     h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (h7b_2 - 1))));
+      get_v2_block(c, v2sub, dimb, h3b_2 - 1 + N * (h2b_2 - 1 + N * (p6b_2 - 1 + N * (h7b_2 - 1))), h3b_2, h2b_2,
+                   p6b_2, h7b_2); /* tce_hashnsort.F:68-79 */
   }
   return 1;
 }
@@ -449,8 +599,8 @@ static int hashnsort_2(const ora_ctx *c, int dryrun, Integer p4b, Integer p7b, I
     }
     free(k_a);
     if (h3b <= p7b) /* :149-161 (always true) */
-      get_hash_block(c->v2, v2sub, dimb, c->v2_hash,
-                     p7b_2 - 1 + N * (h3b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1))));
+      get_v2_block(c, v2sub, dimb, p7b_2 - 1 + N * (h3b_2 - 1 + N * (p6b_2 - 1 + N * (p5b_2 - 1))), p7b_2, h3b_2,
+                   p6b_2, p5b_2); /* tce_hashnsort.F:150-161 */
   }
   return 1;
 }

@@ -5,7 +5,13 @@ from nwchem_b200 import capi, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "microbench_t40"
 t = synth.shape_tiling(name)
 t0 = time.time(); st = synth.random_blocks(t); print("gen", time.time() - t0, "s", flush=True)
-tr = capi.Triples(0); tr.set_state(st); tr.set_timing(True)
+tr = capi.Triples(0)
+if os.environ.get("INTORB"):   # `2eorb` storage: V2 antisymmetrised on the device from an orbital-form store
+    t0 = time.time(); st.orb = synth.random_orbital(t); print("orbital store", len(st.orb.v2orb) * 8e-9, "GB", time.time() - t0, "s", flush=True)
+    tr.set_state_2eorb(st)
+else:
+    tr.set_state(st)
+tr.set_timing(True)
 for it in range(int(os.environ.get("ITERS", "3"))):
     tr.stats(reset=True)
     t0 = time.time(); e1, e2 = tr.run(); dt = time.time() - t0
