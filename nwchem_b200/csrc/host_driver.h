@@ -37,8 +37,12 @@ struct HostState {
   bool intorb = false;
   Integer noa = 0, nva = 0;
   std::vector<Integer> b2am, spin_alpha, sym_alpha, range_alpha;
-  std::unordered_map<Integer, Integer> orb_off;   // orbital block key -> offset in d_v2orb (every stored block)
-  Integer orb_size = 0;                           // doubles in d_v2orb
+  std::unordered_map<Integer, Integer> orb_off;   // orbital block key -> offset in the RESIDENT (compacted) store
+  std::unordered_map<Integer, Integer> host_off;  // scratch: key -> offset in the caller's full store
+  struct OrbRun { Integer src, dst, n; };         // contiguous run of needed blocks: host offset -> resident offset
+  std::vector<OrbRun> orb_runs;
+  Integer orb_size = 0;                           // doubles resident on the device
+  Integer orb_host_size = 0;                      // doubles in the caller's d_v2orb
   static Integer index_pair(Integer i, Integer j) { return (i * (i - 1)) / 2 + j; }   // tce_mo2e_offset_intorb.F:615
   // Expands the checkpointed table k_v2_alpha_offset into a full key -> offset map by running the block loops of
   // tce_mo2e_offset_intorb.F:32-50 once (tce_hash_v2 re-walks them from a checkpoint at every lookup) and checks
@@ -50,7 +54,12 @@ struct HostState {
     b2am.assign(b2am_, b2am_ + noab + nvab);
     spin_alpha.assign(spin_a, spin_a + n); sym_alpha.assign(sym_a, sym_a + n); range_alpha.assign(range_a, range_a + n);
     orb_off.clear();
-    Integer size = 0;
+    orb_runs.clear();
+    // (T) reads <pp||hh>, <hp||hh> and <pp||hp> only, i.e. the Mulliken blocks (vo|vo), (oo|vo) and (vo|vv): a stored
+    // block can be touched iff at least one of its two tile pairs is mixed (one hole tile, one particle tile).
+    // Everything else -- (oo|oo), (oo|vv), (vv|vv), the bulk of the store -- stays on the host.
+    auto is_p = [&](Integer a) { return a > noa; };
+    Integer size = 0, resident = 0;
     for (Integer g3b = 1; g3b <= n; g3b++)
       for (Integer g4b = g3b; g4b <= n; g4b++)
         for (Integer g1b = 1; g1b <= n; g1b++)
@@ -58,16 +67,28 @@ struct HostState {
             if (spin_alpha[g3b - 1] + spin_alpha[g4b - 1] != spin_alpha[g1b - 1] + spin_alpha[g2b - 1]) continue;
             if ((sym_alpha[g3b - 1] ^ sym_alpha[g4b - 1] ^ sym_alpha[g1b - 1] ^ sym_alpha[g2b - 1]) != irrep_v) continue;
             if (index_pair(g4b, g3b) < index_pair(g2b, g1b)) continue;
-            orb_off[g2b - 1 + n * (g1b - 1 + n * (g4b - 1 + n * (g3b - 1)))] = size;
-            size += range_alpha[g3b - 1] * range_alpha[g4b - 1] * range_alpha[g1b - 1] * range_alpha[g2b - 1];
+            const Integer key = g2b - 1 + n * (g1b - 1 + n * (g4b - 1 + n * (g3b - 1)));
+            const Integer bs = range_alpha[g3b - 1] * range_alpha[g4b - 1] * range_alpha[g1b - 1] * range_alpha[g2b - 1];
+            const int pr = (int)is_p(g3b) + (int)is_p(g4b), pc = (int)is_p(g1b) + (int)is_p(g2b);
+            const bool needed = pr == 1 || pc == 1;
+            host_off[key] = size;
+            if (needed) {
+              orb_off[key] = resident;
+              if (!orb_runs.empty() && orb_runs.back().src + orb_runs.back().n == size) orb_runs.back().n += bs;
+              else orb_runs.push_back({size, resident, bs});
+              resident += bs;
+            }
+            size += bs;
           }
-    orb_size = size;
+    orb_size = resident;
+    orb_host_size = size;
     const Integer length1 = table[0];
     for (Integer pos = 1; pos <= length1 + 1; pos++) {
       const Integer key = table[pos], off = table[(length1 + 1) + pos];
-      auto it = orb_off.find(key);
-      if (it == orb_off.end() || it->second != off) return "k_v2_alpha_offset does not match the alpha tiling (checkpoint " + std::to_string(pos) + ")";
+      auto it = host_off.find(key);
+      if (it == host_off.end() || it->second != off) return "k_v2_alpha_offset does not match the alpha tiling (checkpoint " + std::to_string(pos) + ")";
     }
+    host_off.clear();
     intorb = true;
     return "";
   }

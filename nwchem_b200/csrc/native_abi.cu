@@ -321,7 +321,13 @@ int nwc_triples_set_state_2eorb(nwc_triples_ctx* c, const nwc_tce_state* st, con
   if (!err.empty()) { g_err = err; return 1; }
   if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
   if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
-  if (upload(&c->d_v2orb, &c->n_v2orb, orb->v2orb, (size_t)S.orb_size, c->eng)) return 1;
+  // only the blocks (T) can touch become resident, compacted run by run (the rest of d_v2orb stays on the host)
+  if (c->d_v2orb) { cudaFree(c->d_v2orb); c->d_v2orb = nullptr; }
+  NWC_TRY(cudaMalloc((void**)&c->d_v2orb, (size_t)(S.orb_size ? S.orb_size : 1) * sizeof(double)));
+  for (const HostState::OrbRun& r : S.orb_runs)
+    NWC_TRY(cudaMemcpy(c->d_v2orb + r.dst, orb->v2orb + r.src, (size_t)r.n * sizeof(double), cudaMemcpyHostToDevice));
+  c->n_v2orb = (size_t)S.orb_size;
+  c->eng->stats.h2d_bytes += (size_t)S.orb_size * sizeof(double);
   if (c->d_v2) { cudaFree(c->d_v2); c->d_v2 = nullptr; }
   c->n_v2 = 0;
   size_t ne;

@@ -213,6 +213,15 @@ def test_2eorb_storage_native(oracle, shape, ts, restricted):
         os_, od = oracle.tuple_tiles(st, tup)[:2]
         assert np.max(np.abs(gd - od)) <= REL_T3 * max(np.max(np.abs(od)), FLOOR)
         assert np.max(np.abs(gs - os_)) <= REL_T3 * max(np.max(np.abs(os_)), FLOOR)
+    # only the orbital blocks (T) can touch are resident: (vo|vo), (oo|vo), (vo|vv)
+    resident = tr.stats()["resident_bytes"] - 8.0 * (len(st.t1) + len(st.t2))
+    assert 0 < resident < 8.0 * len(st.orb.v2orb)
+    tr.close()
+    bad = dataclasses.replace(st, orb=dataclasses.replace(st.orb, v2orb_hash=st.orb.v2orb_hash.copy()))
+    bad.orb.v2orb_hash[int(bad.orb.v2orb_hash[0]) + 3] += 1      # second checkpoint's offset
+    tr = capi.Triples(0)
+    with pytest.raises(RuntimeError, match="k_v2_alpha_offset"):
+        tr.set_state_2eorb(bad)
     tr.close()
     tr = capi.Triples(0)
     tr.set_state(dataclasses.replace(st, orb=None))   # same integrals, spin-orbital store
