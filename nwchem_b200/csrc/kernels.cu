@@ -203,11 +203,15 @@ struct __align__(16) FusedSmem {
 
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
 
-// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; fold the two upper nibbles into the
-// bank-selecting nibble so that the nine fragment<->canonical patterns spread over banks.  GF(2)-linear:
-// swz(a ^ b) == swz(a) ^ swz(b), so the thread part and the unrolled constant part separate into one XOR.
+// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; a GF(2)-linear function of the two upper
+// nibbles is folded into the bank-selecting nibble.  Linear: swz(a ^ b) == swz(a) ^ swz(b), so the thread part and
+// the unrolled constant part separate into one XOR.  f(x) = x ^ rot2(x) is the choice for which, in ALL nine
+// fragment<->canonical patterns, the four lane bits of a half-warp (bits 2*g2[0]+1, 2*g2[1], 2*g1[0], 2*g1[0]+1 of L)
+// land on linearly independent bank bits, i.e. every LDS.64/STS.64 of the transfers is conflict-free (the plain fold
+// x -> x was conflict-free for three splits, 2-way for five, 4-way for one: ncu showed 1.97 wavefronts per ideal one).
 // Bits 5 (h1 high) and 11 (p4 high) -- the owner bits -- are left in place: warp quarters stay disjoint.
-__host__ __device__ constexpr int canon_swz(int L) { return L ^ ((L >> 4) & 15) ^ ((L >> 8) & 15); }
+__host__ __device__ constexpr int canon_fold(int x) { return (x ^ ((x << 2) | (x >> 2))) & 15; }
+__host__ __device__ constexpr int canon_swz(int L) { return L ^ canon_fold((L >> 4) & 15) ^ canon_fold((L >> 8) & 15); }
 
 __device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
