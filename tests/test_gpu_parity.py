@@ -288,6 +288,19 @@ def test_microbench_t40_properties():
     assert st_["flops"] > 0
 
 
+def test_ragged_full_size_tuples_bitwise_reproducible():
+    """Uracil-shaped tiling (occupied tile 21, virtual tiles 38/39): the heaviest tuples run through the block-skipping
+    K loops of the edge sub-tiles; three repeats must agree bit for bit (a ring WAR race shows up as energy noise)."""
+    st = synth.random_blocks(synth.shape_tiling("uracil_augccpvdz"))
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    runs = [tr.run(per_task=True, max_tasks=3) for _ in range(3)]
+    tr.close()
+    for r in runs[1:]:
+        assert r[0] == runs[0][0] and r[1] == runs[0][1] and np.array_equal(r[2], runs[0][2])
+    assert np.all(runs[0][2][:, 0] != 0.0)
+
+
 def test_reference_cuda_kernels_agree_with_oracle(oracle):
     """Pins the oracle: the reference's own sd_t_total.cu + memory.cu (compiled unmodified into oracle/_ref)
     run here and must reproduce the oracle's kernels and energy (tiles <= 32: its singles kernel overflows
