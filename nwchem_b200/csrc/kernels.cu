@@ -617,8 +617,8 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
         }
       asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
       // FP64 ALU instructions share the pipe with the DMMAs of the other CTAs on this SM, and every isolated
-      // DFMA that lands between two DMMAs costs about one DMMA slot.  So: pull the operands of 16 elements into
-      // registers first, then issue the 16 DFMAs back to back.
+      // DFMA that lands between two DMMAs costs about one DMMA slot.  So: pull the operands of a term into registers
+      // first, then issue its 32 DFMAs back to back.
       for (int t = 0; t < nt; t++) {
         const SinglesTerm stt = sm.st[t0 + t];
         const double* t1s = sm.ring + t * SD_TERM;
@@ -632,23 +632,32 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
         double tv[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) tv[k] = t1s[ft + k * tstep];
+        // v2 lacks the particle index t1 carries, so a thread needs only 8 (or 16) distinct v2 values per term;
+        // all loads first, then the 32 DFMAs of the term as one burst
+        if (t6) {          // t1(p6,.): v2 over (p5, p4lo)
+          double v8[8];
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) v8[b + 4 * a] = v2s[fv + b * v5 + a * v4];
+#pragma unroll
+          for (int e = 0; e < 32; e++) sing[e] = fma(tv[e & 3], v8[((e >> 2) & 3) + 4 * (e >> 4)], sing[e]);
+        } else if (t5) {   // t1(p5,.): v2 over (p6, p4lo)
+          double v8[8];
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) v8[c + 4 * a] = v2s[fv + c * v6 + a * v4];
+#pragma unroll
+          for (int e = 0; e < 32; e++) sing[e] = fma(tv[(e >> 2) & 3], v8[(e & 3) + 4 * (e >> 4)], sing[e]);
+        } else {           // t1(p4,.): v2 over (p6, p5)
           double vv[16];
 #pragma unroll
           for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) vv[c + 4 * b] = v2s[fv + c * v6 + b * v5 + a * v4];
-          if (t6) {
+            for (int c = 0; c < 4; c++) vv[c + 4 * b] = v2s[fv + c * v6 + b * v5];
 #pragma unroll
-            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[e & 3], vv[e], sing[e + 16 * a]);
-          } else if (t5) {
-#pragma unroll
-            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[e >> 2], vv[e], sing[e + 16 * a]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; e++) sing[e + 16 * a] = fma(tv[a], vv[e], sing[e + 16 * a]);
-          }
+          for (int e = 0; e < 32; e++) sing[e] = fma(tv[e >> 4], vv[e & 15], sing[e]);
         }
       }
     }
