@@ -246,7 +246,7 @@ void Engine::run(double* energies_out, double* dump_doubles, double* dump_single
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_t = 0, o_d = al(o_t + nt * sizeof(TupleHdr)), o_s = al(o_d + descs_.size() * sizeof(ContrDesc)),
                o_e = al(o_s + sdescs_.size() * sizeof(SinglesDesc)), o_p = al(o_e + nt * sizeof(double2)),
-               total = al(o_p + (size_t)items_ * sizeof(double2));
+               total = al(o_p + (size_t)items_ * partials_per_item() * sizeof(double2));
   if (total > d_meta_cap_) {
     if (d_meta_) NWC_CUDA(cudaFree(d_meta_));
     d_meta_cap_ = total + total / 4;

@@ -192,7 +192,6 @@ struct __align__(16) FusedSmem {
   SplitGeom geom[9];
   double eps[6][4];
   double dp[NCONSUMERS / 32][32];           // -(eps_p4+eps_p5+eps_p6) of each warp's 32 particle triples
-  double red[2][NCONSUMERS / 32];
   SinglesTerm st[MAX_SDESC];
   int desc_begin[10];
   int b[6];
@@ -202,6 +201,7 @@ struct __align__(16) FusedSmem {
 };
 
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
+int partials_per_item() { return NCONSUMERS / 32; }
 
 // canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; a GF(2)-linear function of the two upper
 // nibbles is folded into the bank-selecting nibble.  Linear: swz(a ^ b) == swz(a) ^ swz(b), so the thread part and
@@ -726,16 +726,12 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     e1 += __shfl_xor_sync(0xffffffffu, e1, o);
     e2 += __shfl_xor_sync(0xffffffffu, e2, o);
   }
-  if (lane == 0) { sm.red[0][warp] = e1; sm.red[1][warp] = e2; }
-  asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
-  if (tid == 0) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int w = 0; w < NCONSUMERS / 32; w++) { s1 += sm.red[0][w]; s2 += sm.red[1][w]; }
-    partials[item] = make_double2(s1, s2);
-    if (TIMING && g_phase_buf && item < g_phase_cap) {
-      tph[6] = clock64();
-      for (int i = 0; i < 8; i++) g_phase_buf[item * 8 + i] = tph[i];
-    }
+  // one partial per warp: no CTA-wide rendezvous at the end, every warp leaves as soon as it is done
+  // (reduce_kernel adds the four in a fixed order)
+  if (lane == 0) partials[item * (NCONSUMERS / 32) + warp] = make_double2(e1, e2);
+  if (TIMING && tid == 0 && g_phase_buf && item < g_phase_cap) {
+    tph[6] = clock64();
+    for (int i = 0; i < 8; i++) g_phase_buf[item * 8 + i] = tph[i];
   }
 }
 
@@ -798,8 +794,9 @@ __global__ void __launch_bounds__(256) reduce_kernel(const TupleHdr* __restrict_
   __shared__ double s1[256], s2[256];
   const TupleHdr& T = tuples[blockIdx.x];
   double a = 0.0, b = 0.0;
-  for (long long i = threadIdx.x; i < T.nitems; i += 256) {
-    const double2 v = partials[T.item_begin + i];
+  const long long n = (long long)T.nitems * (NCONSUMERS / 32), base = T.item_begin * (NCONSUMERS / 32);
+  for (long long i = threadIdx.x; i < n; i += 256) {   // four per-warp partials per sub-tile, fixed order
+    const double2 v = partials[base + i];
     a += v.x; b += v.y;
   }
   s1[threadIdx.x] = a; s2[threadIdx.x] = b;

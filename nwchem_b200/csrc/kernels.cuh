@@ -80,6 +80,7 @@ void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d
                        double2* d_partials, long long total_items, double* d_doubles, double* d_singles,
                        cudaStream_t stream);
 int fused_smem_bytes();
+int partials_per_item();   // double2 partials the fused kernel writes per work item (one per MMA warp)
 // debugging aid: per-CTA phase clocks (8 x u64 per work item < cap_items) from a timing build of the kernel
 void set_phase_timing(unsigned long long* d_buf, unsigned int cap_items);
 
