@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--strong", action="store_true", help="one task list dealt over the ranks (fixed total work) instead of one copy per rank")
     ap.add_argument("--sharded", action="store_true", help="shard the V2 store over the ranks; remote blocks are read over NVLink (CUDA IPC)")
+    ap.add_argument("--intorb", action="store_true", help="V2 in the reference's spin-free `2eorb` form, antisymmetrised on the device")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -133,6 +134,8 @@ def main():
                "tilesize": sh["tilesize"], "v2": "sharded over ranks, NVLink peer reads" if a.sharded else "replicated",
                "partition": "strong: heaviest-first task list dealt round-robin" if a.strong else "weak: one task list per rank",
                "l2": "operand panels per tuple exceed the 126 MB L2; no explicit flush"}
+    if a.intorb:
+        cfg["v2"] = "2eorb: spin-free orbital-form store resident, blocks antisymmetrised on the device per batch"
 
     if a.impl == "reference":
         if rank != 0:
@@ -172,6 +175,9 @@ def main():
         allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
         dist.all_gather(allh, mine)
         tr.v2_open_peers(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    elif a.intorb:
+        st.orb = synth.random_orbital(t, seed=20240229 + (0 if a.strong else rank))
+        tr.set_state_2eorb(st)
     else:
         tr.set_state(st)
     if world > 1:  # the library's own communicator: rank 0's id is broadcast with the torch plumbing
