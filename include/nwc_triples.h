@@ -164,6 +164,11 @@ typedef struct {
   const Integer *v2orb_hash;
   const double *v2orb;
 } nwc_tce_orb_state;
+/* host-only view of the device-side antisymmetrisation plan (tests): where the direct / exchange halves of
+   <g3 g4||g1 g2> sit in the caller's d_v2orb (element offset, -1 = half absent for these spins) and the element
+   strides of (g3,g4,g1,g2) in each */
+int nwc_host_2eorb_plan(const nwc_tce_state *st, const nwc_tce_orb_state *orb, const Integer g3g4g1g2[4],
+                        Integer off_host[2], Integer strides[8]);
 /* like nwc_triples_set_state, but V2 comes from `orb`; st->v2_hash / st->v2 are not read (may be NULL) */
 int nwc_triples_set_state_2eorb(nwc_triples_ctx *ctx, const nwc_tce_state *st, const nwc_tce_orb_state *orb);
 /* Restartable (T): replaces ccsd_t_restart.F:57-290.  *restart_begin and table[nvab] are the RTDB entries

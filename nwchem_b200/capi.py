@@ -315,6 +315,24 @@ def tier1_single_call(family, k, dims_task, dims_perm, kd, tsub, v2sub, eps, fac
 # ------------------------------------------------------------------------------------------------
 # host-only helpers (no device needed)
 # ------------------------------------------------------------------------------------------------
+def host_2eorb_plan(st, g3b, g4b, g1b, g2b):
+    """Product host logic of the `2eorb` path (no device): (off_direct, off_exchange, strides[2][4]) into st.orb.v2orb."""
+    s, keep = make_state(st)
+    a = st.orb.a
+    k = dict(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
+             sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
+             voh=np.ascontiguousarray(st.orb.v2orb_hash, np.int64), vo=np.ascontiguousarray(st.orb.v2orb, np.float64))
+    o = OrbState(a.noa, a.nva, _pl(k["b2am"]), _pl(k["spa"]), _pl(k["sya"]), _pl(k["rga"]), _pl(k["voh"]), _pd(k["vo"]))
+    g = np.array([g3b, g4b, g1b, g2b], np.int64)
+    off = np.zeros(2, np.int64); strides = np.zeros(8, np.int64)
+    l = lib()
+    l.nwc_host_2eorb_plan.argtypes = [C.POINTER(TceState), C.POINTER(OrbState), PL, PL, PL]
+    rc = l.nwc_host_2eorb_plan(C.byref(s), C.byref(o), _pl(g), _pl(off), _pl(strides))
+    if rc != 0:
+        raise RuntimeError("nwc_host_2eorb_plan: offset table does not match the tiling")
+    return int(off[0]), int(off[1]), strides.reshape(2, 4)
+
+
 def host_task_list(st):
     s, keep = make_state(st)
     l = lib()

@@ -231,6 +231,24 @@ int nwc_host_count_tuple(const nwc_tce_state* st, const Integer tuple[6], Intege
   return 0;
 }
 
+// `2eorb`: where the two Mulliken halves of <g3 g4||g1 g2> sit in the caller's d_v2orb (host-only; no device needed).
+// off_host[2] = element offsets of the direct / exchange source blocks (-1: that half does not fire), strides[8] =
+// element strides of (g3,g4,g1,g2) in the two sources.  Returns non-zero if the table does not match the tiling.
+int nwc_host_2eorb_plan(const nwc_tce_state* st, const nwc_tce_orb_state* orb, const Integer g3g4g1g2[4],
+                        Integer off_host[2], Integer strides[8]) {
+  HostState S;
+  nwc_tce_state s2 = *st;
+  s2.v2_hash = nullptr;
+  S.load_tables(&s2);
+  if (!S.load_orbital(orb->noa, orb->nva, orb->b2am, orb->spin_alpha, orb->sym_alpha, orb->range_alpha, orb->v2orb_hash).empty())
+    return 1;
+  const HostState::OrbPlan p = S.block_plan(g3g4g1g2[0], g3g4g1g2[1], g3g4g1g2[2], g3g4g1g2[3]);
+  off_host[0] = p.key_a >= 0 ? S.host_off.at(p.key_a) : -1;
+  off_host[1] = p.key_b >= 0 ? S.host_off.at(p.key_b) : -1;
+  for (int q = 0; q < 4; q++) { strides[q] = p.sa[q]; strides[4 + q] = p.sb[q]; }
+  return 0;
+}
+
 int nwc_ccsd_t_gpu_tuple(const nwc_tce_state* st, const Integer tuple[6], double energy[2], double* host_doubles,
                          double* host_singles) {
   HostState S;

@@ -88,9 +88,46 @@ struct HostState {
       auto it = host_off.find(key);
       if (it == host_off.end() || it->second != off) return "k_v2_alpha_offset does not match the alpha tiling (checkpoint " + std::to_string(pos) + ")";
     }
-    host_off.clear();
     intorb = true;
     return "";
+  }
+  // One Mulliken integral class (a b|c d), a in alpha tile tile[0], ...: which stored block holds it and with which
+  // element strides (get_block_ind.F:884-1016 pair ordering; tce_mo2e_trans.F:707-723 element order (k l|i j), k fastest).
+  struct OrbSource { Integer key; long long stride[4]; };
+  OrbSource mulliken_source(const Integer tile[4]) const {
+    const Integer n = noa + nva;
+    int ia = 0, ib = 1, ic = 2, id = 3;                       // argument slots: (a b | c d)
+    if (tile[ia] < tile[ib]) { int t = ia; ia = ib; ib = t; } // larger tile first inside each pair
+    if (tile[ic] < tile[id]) { int t = ic; ic = id; id = t; }
+    if (index_pair(tile[ia], tile[ib]) < index_pair(tile[ic], tile[id])) { int t = ia; ia = ic; ic = t; t = ib; ib = id; id = t; }
+    // now row pair = (ia, ib) -> (k, l), column pair = (ic, id) -> (i, j)
+    OrbSource m;
+    m.key = tile[ic] - 1 + n * (tile[id] - 1 + n * (tile[ia] - 1 + n * (tile[ib] - 1)));
+    const long long rk = range_alpha[tile[ia] - 1], rl = range_alpha[tile[ib] - 1], ri = range_alpha[tile[ic] - 1];
+    m.stride[ia] = 1; m.stride[ib] = rk; m.stride[ic] = rk * rl; m.stride[id] = rk * rl * ri;
+    return m;
+  }
+  // <g3 g4||g1 g2> = (g3 g1|g4 g2) - (g3 g2|g4 g1) (get_block_ind.F:818-1538): the (up to) two sources with the
+  // strides of the target indices x0=g3, x1=g4, x2=g1, x3=g2; key < 0 = that half does not fire for these spins
+  struct OrbPlan { Integer key_a, key_b; long long sa[4], sb[4]; };
+  OrbPlan block_plan(Integer g3b, Integer g4b, Integer g1b, Integer g2b) const {
+    OrbPlan p{};
+    p.key_a = p.key_b = -1;
+    const Integer s3 = sp(g3b), s4 = sp(g4b), s1 = sp(g1b), s2 = sp(g2b);
+    const Integer a3 = b2am[g3b - 1], a4 = b2am[g4b - 1], a1 = b2am[g1b - 1], a2 = b2am[g2b - 1];
+    if (s3 == s1 && s4 == s2) {   // direct: uaadaa, ubbdbb, uabdab, ubadba (get_block_ind.F:983)
+      const Integer tile[4] = {a3, a1, a4, a2};
+      const OrbSource m = mulliken_source(tile);
+      p.key_a = m.key;
+      p.sa[0] = m.stride[0]; p.sa[2] = m.stride[1]; p.sa[1] = m.stride[2]; p.sa[3] = m.stride[3];
+    }
+    if (s3 == s2 && s4 == s1) {   // exchange: uaadaa, ubbdbb, uabdba, ubadab (:1264)
+      const Integer tile[4] = {a3, a2, a4, a1};
+      const OrbSource m = mulliken_source(tile);
+      p.key_b = m.key;
+      p.sb[0] = m.stride[0]; p.sb[3] = m.stride[1]; p.sb[1] = m.stride[2]; p.sb[2] = m.stride[3];
+    }
+    return p;
   }
   Integer sp(Integer b) const { return spin[b - 1]; }
   Integer sy(Integer b) const { return sym[b - 1]; }

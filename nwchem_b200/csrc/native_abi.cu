@@ -97,28 +97,11 @@ const double* v2_block(const nwc_triples_ctx* c, Integer key, const char* what) 
   return base + c->v2_shard_off[idx - 1];
 }
 
-// `2eorb`: <g3 g4||g1 g2> = (g3 g1|g4 g2) - (g3 g2|g4 g1) as one antisym job (get_block_ind.F:818-1538).
-// A Mulliken integral (ab|cd) with a in tile A, ... is read from the stored block whose row pair is the larger of
-// {A,B},{C,D} (index_pair order, larger tile first inside a pair); inside a block the element order is
-// (k l|i j): k (larger row tile) fastest, then l, then i (larger column tile), then j (tce_mo2e_trans.F:707-723).
-struct MullikenSrc { const double* base; long long stride[4]; };   // strides of the four arguments a,b,c,d
-
-MullikenSrc mulliken_source(const nwc_triples_ctx* c, const Integer tile[4]) {
-  const HostState& S = c->S;
-  const Integer n = S.noa + S.nva;
-  int ia = 0, ib = 1, ic = 2, id = 3;                       // argument slots: (a b | c d)
-  if (tile[ia] < tile[ib]) std::swap(ia, ib);               // larger tile first inside each pair
-  if (tile[ic] < tile[id]) std::swap(ic, id);
-  if (HostState::index_pair(tile[ia], tile[ib]) < HostState::index_pair(tile[ic], tile[id])) { std::swap(ia, ic); std::swap(ib, id); }
-  // now row pair = (ia, ib) -> (k, l), column pair = (ic, id) -> (i, j)
-  const Integer key = tile[ic] - 1 + n * (tile[id] - 1 + n * (tile[ia] - 1 + n * (tile[ib] - 1)));
-  auto it = S.orb_off.find(key);
-  if (it == S.orb_off.end()) { printf("nwc_triples: orbital V2 block key %ld not found\n", key); fflush(stdout); exit(1); }
-  MullikenSrc m;
-  m.base = c->d_v2orb + it->second;
-  const long long rk = S.range_alpha[tile[ia] - 1], rl = S.range_alpha[tile[ib] - 1], ri = S.range_alpha[tile[ic] - 1];
-  m.stride[ia] = 1; m.stride[ib] = rk; m.stride[ic] = rk * rl; m.stride[id] = rk * rl * ri;
-  return m;
+// `2eorb`: <g3 g4||g1 g2> as one antisym job built from HostState::block_plan (get_block_ind.F:818-1538)
+const double* orb_block_ptr(const nwc_triples_ctx* c, Integer key) {
+  auto it = c->S.orb_off.find(key);
+  if (it == c->S.orb_off.end()) { printf("nwc_triples: orbital V2 block key %ld is not resident\n", key); fflush(stdout); exit(1); }
+  return c->d_v2orb + it->second;
 }
 
 const double* v2_block_2eorb(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g1b, Integer g2b) {
@@ -130,20 +113,9 @@ const double* v2_block_2eorb(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integ
   j.n[0] = (int)S.rg(g3b); j.n[1] = (int)S.rg(g4b); j.n[2] = (int)S.rg(g1b); j.n[3] = (int)S.rg(g2b);
   const size_t bytes = sizeof(double) * (size_t)j.n[0] * j.n[1] * j.n[2] * j.n[3];
   j.dst = (double*)c->eng->arena().alloc(bytes);
-  const Integer s3 = S.sp(g3b), s4 = S.sp(g4b), s1 = S.sp(g1b), s2 = S.sp(g2b);
-  const Integer a3 = S.b2am[g3b - 1], a4 = S.b2am[g4b - 1], a1 = S.b2am[g1b - 1], a2 = S.b2am[g2b - 1];
-  if (s3 == s1 && s4 == s2) {   // direct (g3 g1|g4 g2): uaadaa, ubbdbb, uabdab, ubadba (get_block_ind.F:983)
-    const Integer tile[4] = {a3, a1, a4, a2};
-    const MullikenSrc m = mulliken_source(c, tile);
-    j.a = m.base; j.ca = 1.0;
-    j.sa[0] = m.stride[0]; j.sa[2] = m.stride[1]; j.sa[1] = m.stride[2]; j.sa[3] = m.stride[3];   // x0=g3,x1=g4,x2=g1,x3=g2
-  }
-  if (s3 == s2 && s4 == s1) {   // exchange (g3 g2|g4 g1): uaadaa, ubbdbb, uabdba, ubadab (:1264)
-    const Integer tile[4] = {a3, a2, a4, a1};
-    const MullikenSrc m = mulliken_source(c, tile);
-    j.b = m.base; j.cb = -1.0;
-    j.sb[0] = m.stride[0]; j.sb[3] = m.stride[1]; j.sb[1] = m.stride[2]; j.sb[2] = m.stride[3];
-  }
+  const HostState::OrbPlan p = S.block_plan(g3b, g4b, g1b, g2b);
+  if (p.key_a >= 0) { j.a = orb_block_ptr(c, p.key_a); j.ca = 1.0; for (int q = 0; q < 4; q++) j.sa[q] = p.sa[q]; }
+  if (p.key_b >= 0) { j.b = orb_block_ptr(c, p.key_b); j.cb = -1.0; for (int q = 0; q < 4; q++) j.sb[q] = p.sb[q]; }
   c->eng->add_antisym(j);
   c->v2_built[skey] = j.dst;
   return j.dst;

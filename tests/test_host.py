@@ -2,6 +2,7 @@
 host-side driver logic (task list, dispatch walk) agrees with the oracle.  No compute calls (no GPU here)."""
 import os
 import re
+import dataclasses
 import numpy as np
 import pytest
 from nwchem_b200 import capi, synth, tiling as tl
@@ -76,3 +77,34 @@ def test_h2o10_flops_from_product_host_logic():
         tot += f; calls += c
     assert tuple(calls) == (46046, 62744, 1380368)
     assert abs(tot.sum() - 4.52e17) / 4.52e17 < 5e-3
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_2eorb_host_plan_reproduces_spin_orbital_blocks(restricted):
+    """The library's host logic for `2eorb` storage (which stored orbital block, which strides, which sign -- the
+    device kernel only executes this plan): applied with numpy to the orbital-form store it must rebuild every
+    spin-orbital V2 block the (T) path reads, bit for bit (get_block_ind.F:818-1538 collapsed into strides)."""
+    t = synth.shape_tiling("h2o_ccpvdz_c2v", restricted=restricted)
+    st = synth.physical(t, intorb=True)
+    vo = st.orb.v2orb
+    halves = set()
+    for key, off in synth._iter_hash(st.v2_hash):
+        g3b, g4b, g1b, g2b = tl.decode_v2_key(t, key)
+        dims = [t.r(g3b), t.r(g4b), t.r(g1b), t.r(g2b)]
+        oa, ob, strides = capi.host_2eorb_plan(st, g3b, g4b, g1b, g2b)
+        idx = np.indices(dims).reshape(4, -1)
+        blk = np.zeros(idx.shape[1])
+        if oa >= 0:
+            blk += vo[oa + (idx * strides[0][:, None]).sum(0)]
+        if ob >= 0:
+            blk -= vo[ob + (idx * strides[1][:, None]).sum(0)]
+        halves.add((oa >= 0, ob >= 0))
+        n = int(np.prod(dims))
+        assert np.array_equal(blk, st.v2[off:off + n]), (g3b, g4b, g1b, g2b)
+    assert (True, True) in halves and (True, False) in halves
+    if not restricted:
+        assert (False, True) in halves
+    bad = dataclasses.replace(st, orb=dataclasses.replace(st.orb, v2orb_hash=st.orb.v2orb_hash.copy()))
+    bad.orb.v2orb_hash[1] += 1
+    with pytest.raises(RuntimeError):
+        capi.host_2eorb_plan(bad, 4, 4, 1, 1)
