@@ -147,6 +147,34 @@ def v2_block_intorb(st, g3b, g4b, g1b, g2b):
     return out
 
 
+def singles_tce(st, tup):
+    """Singles tile of one tuple through the original TCE formulation (ccsd_t_singles.F: sort, outer product,
+    nine TCE_SORTACC_6), indexed [p4,p5,p6,h1,h2,h3]."""
+    l = lib()
+    c, keep = make_ctx(st)
+    dims = [st.t.r(b) for b in tup]
+    s = np.zeros(int(np.prod(dims)))
+    p4, p5, p6, h1, h2, h3 = [L(int(x)) for x in tup]
+    l.ora_ccsd_t_singles_tce(C.byref(c), _pd(s), h1, h2, h3, p4, p5, p6)
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return s.reshape(dims)
+
+
+def doubles_tce(st, tup):
+    """Doubles tile of one tuple through the original TCE formulation (ccsd_t_doubles.F: sorts, DGEMM, eighteen
+    TCE_SORTACC_6), indexed [p4,p5,p6,h1,h2,h3]."""
+    l = lib()
+    c, keep = make_ctx(st)
+    dims = [st.t.r(b) for b in tup]
+    d = np.zeros(int(np.prod(dims)))
+    p4, p5, p6, h1, h2, h3 = [L(int(x)) for x in tup]
+    l.ora_ccsd_t_doubles_tce(C.byref(c), _pd(d), h1, h2, h3, p4, p5, p6)
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return d.reshape(dims)
+
+
 def tuple_tiles(st, tup):
     """One tuple (p4b,p5b,p6b,h1b,h2b,h3b): returns (singles, doubles, e1, e2) with the t3 tiles as
     arrays indexed [p4,p5,p6,h1,h2,h3] (C order == Fortran T3(h3,h2,h1,p6,p5,p4))."""

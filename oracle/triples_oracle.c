@@ -13,10 +13,13 @@
  * oracle is pinned by (i) the H2O/cc-pVDZ tile table of QA/tests/tce_ccsd_t_h2o
  * (tce_ccsd_t_h2o.out:644-659), (ii) agreement of the 27 kernels + energy kernel with the
  * reference's own CUDA implementation (sd_t_total.cu + memory.cu compiled unmodified into
- * oracle/_ref, run on the GPU box), (iii) an independent second formulation
- * (sort -> GEMM -> sortacc_6, ccsd_t_doubles.F:195-267) and (iv) tile-size invariance of
- * E[T]/E(T) on antisymmetric synthetic amplitudes.  End-to-end energies of the QA outputs
- * need converged CCSD amplitudes that nothing in scope can produce: that part is unpinned.
+ * oracle/_ref, run on the GPU box), (iii) the reference's independent second formulation of
+ * the same tiles (sort -> DGEMM -> TCE_SORTACC_6 with the 27 permutation/sign pairs of
+ * ccsd_t_singles.F / ccsd_t_doubles.F) on every tuple of the H2O table, (iv) tile-size
+ * invariance of E[T]/E(T) on antisymmetric synthetic amplitudes, (v) for the `2eorb` path,
+ * bit-exact reconstruction of every spin-orbital V2 block from an orbital-form store of the
+ * same integrals.  End-to-end energies of the QA outputs need converged CCSD amplitudes
+ * that nothing in scope can produce: that part is unpinned.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -476,11 +479,30 @@ typedef struct {
   Integer calls_s1, calls_d1, calls_d2;
 } ora_counts;
 
+void ora_tce_sortacc_6(const double *unsorted, double *sorted, Integer a, Integer b, Integer c, Integer d,
+                       Integer e, Integer f, Integer i, Integer j, Integer k, Integer l, Integer m, Integer n,
+                       double factor);
+
 /* ------------------------------------------------------------------------------------ */
 /* Singles: ccsd_t_singles_l.F:30-463 == ccsd_t_singles_gpu.F:36-574                     */
+/* tce_form != 0: the original TCE-generated formulation instead of the nine loop kernels  */
+/* (ccsd_t_singles.F:140-246): b sorted (4,3,2,1), c_sort = a_sort x b_sort (the DGEMM with */
+/* dim_common = 1), then one TCE_SORTACC_6 per dispatch test with the permutation and sign  */
+/* written there -- an independent derivation of the nine layouts/signs (tests only).       */
 /* ------------------------------------------------------------------------------------ */
+void ora_dgemm_tn(Integer m, Integer n, Integer k, const double *a, const double *b, double *cmat);
+static void singles_body(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                         Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt, int tce_form);
 void ora_ccsd_t_singles_l(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t_h2b, Integer t_h3b,
                           Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt) {
+  singles_body(c, a_c, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, dryrun, cnt, 0);
+}
+void ora_ccsd_t_singles_tce(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                            Integer t_p4b, Integer t_p5b, Integer t_p6b) {
+  singles_body(c, a_c, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL, 1);
+}
+static void singles_body(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                         Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt, int tce_form) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   /* P rows (p4|p5 p6): (p4,p5,p6),(p5,p4,p6),(p6,p4,p5); H rows: (h1,h2,h3),(h2,h1,h3),(h3,h1,h2)
    * ccsd_t_singles_gpu.F:101-162 */
@@ -533,8 +555,23 @@ void ora_ccsd_t_singles_l(const ora_ctx *c, double *a_c, Integer t_h1b, Integer 
           cnt->calls_s1++;
           cnt->flops_s1 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) * RANGE(h3b);
         }
-        if (!dryrun)
+        if (!dryrun && !tce_form)
           S1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort);
+        if (!dryrun && tce_form) {
+          /* ccsd_t_singles.F:185-240: permutation of (h3b,h2b,p6b,p5b,h1b,p4b) and sign of test K+1 */
+          static const int PERM[9][6] = {{6, 4, 3, 5, 2, 1}, {6, 4, 3, 2, 5, 1}, {6, 4, 3, 2, 1, 5},
+                                         {4, 6, 3, 5, 2, 1}, {4, 6, 3, 2, 5, 1}, {4, 6, 3, 2, 1, 5},
+                                         {4, 3, 6, 5, 2, 1}, {4, 3, 6, 2, 5, 1}, {4, 3, 6, 2, 1, 5}};
+          static const double SGN[9] = {1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0};
+          double *b4 = (double *)malloc(sizeof(double) * dimb);
+          double *c_sort = (double *)malloc(sizeof(double) * dima * dimb);
+          ora_tce_sort_4(k_b_sort, b4, RANGE(p5b), RANGE(p6b), RANGE(h2b), RANGE(h3b), 4, 3, 2, 1, 1.0); /* :167-169 */
+          for (Integer ib = 0; ib < dimb; ib++) /* DGEMM('T','N',dima_sort,dimb_sort,1,...), :172-174 */
+            for (Integer ia = 0; ia < dima; ia++) c_sort[ia + dima * ib] = k_a_sort[ia] * b4[ib];
+          ora_tce_sortacc_6(c_sort, a_c, RANGE(h3b), RANGE(h2b), RANGE(p6b), RANGE(p5b), RANGE(h1b), RANGE(p4b),
+                            PERM[K][0], PERM[K][1], PERM[K][2], PERM[K][3], PERM[K][4], PERM[K][5], SGN[K]);
+          free(b4); free(c_sort);
+        }
       }
     free(k_a); free(k_a_sort); free(k_b_sort);
   }
@@ -609,8 +646,33 @@ static int hashnsort_2(const ora_ctx *c, int dryrun, Integer p4b, Integer p7b, I
 /* Doubles: offl_ccsd_t_doubles_l.F:72-1041 (ccsd_t_doubles_l_12)                        */
 /*          == ccsd_t_doubles_gpu.F:48-742 (_1) and :743-1345 (_2)                       */
 /* ------------------------------------------------------------------------------------ */
+/* tce_form != 0 (tests only): the original TCE-generated formulation (ccsd_t_doubles.F:120-270, :370-520): the V2
+ * operand sorted so that the contracted index is fastest, DGEMM('T','N'), then one TCE_SORTACC_6 per dispatch test
+ * with the permutation and sign written there, instead of the loop kernels sd_t_d1_K / sd_t_d2_K. */
+static void doubles_body(const ora_ctx *c, double *triplesx, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                         Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt, int tce_form);
 void ora_ccsd_t_doubles_l(const ora_ctx *c, double *triplesx, Integer t_h1b, Integer t_h2b, Integer t_h3b,
                           Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt) {
+  doubles_body(c, triplesx, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, dryrun, cnt, 0);
+}
+void ora_ccsd_t_doubles_tce(const ora_ctx *c, double *triplesx, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                            Integer t_p4b, Integer t_p5b, Integer t_p6b) {
+  doubles_body(c, triplesx, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL, 1);
+}
+/* c_sort = a_sort^T b_sort of one (row, contracted tile) pair, then TCE_SORTACC_6 into the tile */
+static void tce_pair(double *triplesx, const double *a_sort, const double *b_raw, Integer ka, Integer kb, Integer kc,
+                     Integer kd, const int bperm[4], Integer m, Integer n, Integer k, const Integer dims[6],
+                     const int perm[6], double sign) {
+  double *b_sort = (double *)malloc(sizeof(double) * (size_t)(n * k));
+  double *c_sort = (double *)calloc((size_t)(m * n), sizeof(double));
+  ora_tce_sort_4(b_raw, b_sort, ka, kb, kc, kd, bperm[0], bperm[1], bperm[2], bperm[3], 1.0);
+  ora_dgemm_tn(m, n, k, a_sort, b_sort, c_sort);
+  ora_tce_sortacc_6(c_sort, triplesx, dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], perm[0], perm[1], perm[2],
+                    perm[3], perm[4], perm[5], sign);
+  free(b_sort); free(c_sort);
+}
+static void doubles_body(const ora_ctx *c, double *triplesx, Integer t_h1b, Integer t_h2b, Integer t_h3b,
+                         Integer t_p4b, Integer t_p5b, Integer t_p6b, int dryrun, ora_counts *cnt, int tce_form) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   const Integer noab = c->noab, nvab = c->nvab;
   /* scratch sized as ccsd_t_v2t2lgth (ccsd_t_doubles_l.F:118-141): max tile^4 */
@@ -655,9 +717,20 @@ void ora_ccsd_t_doubles_l(const ora_ctx *c, double *triplesx, Integer t_h1b, Int
               cnt->flops_d1 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) *
                                RANGE(h3b) * RANGE(h7b);
             }
-            if (!dryrun)
+            if (!dryrun && !tce_form)
               D1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b),
                     triplesx, t2sub, v2sub);
+            if (!dryrun && tce_form) { /* ccsd_t_doubles.F:189-191 (b sort), :195, :206-267 (perm, sign of test K+1) */
+              static const int PERM[9][6] = {{6, 5, 3, 4, 2, 1}, {6, 5, 3, 2, 4, 1}, {6, 5, 3, 2, 1, 4},
+                                             {3, 6, 5, 4, 2, 1}, {3, 6, 5, 2, 4, 1}, {3, 6, 5, 2, 1, 4},
+                                             {6, 3, 5, 4, 2, 1}, {6, 3, 5, 2, 4, 1}, {6, 3, 5, 2, 1, 4}};
+              static const double SGN[9] = {-1.0, 1.0, -1.0, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0};
+              static const int BPERM[4] = {4, 3, 2, 1};
+              const Integer dims[6] = {RANGE(h3b), RANGE(h2b), RANGE(p6b), RANGE(h1b), RANGE(p5b), RANGE(p4b)};
+              tce_pair(triplesx, t2sub, v2sub, RANGE(h7b), RANGE(p6b), RANGE(h2b), RANGE(h3b), BPERM,
+                       RANGE(p4b) * RANGE(p5b) * RANGE(h1b), RANGE(p6b) * RANGE(h2b) * RANGE(h3b), RANGE(h7b), dims,
+                       PERM[K], SGN[K]);
+            }
           }
       }
     }
@@ -695,9 +768,20 @@ void ora_ccsd_t_doubles_l(const ora_ctx *c, double *triplesx, Integer t_h1b, Int
               cnt->flops_d2 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) *
                                RANGE(h3b) * RANGE(p7b);
             }
-            if (!dryrun)
+            if (!dryrun && !tce_form)
               D2[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b),
                     triplesx, t2sub, v2sub);
+            if (!dryrun && tce_form) { /* ccsd_t_doubles.F:440-442 (b sort), :446, :457-520 */
+              static const int PERM[9][6] = {{6, 3, 2, 5, 4, 1}, {6, 3, 2, 1, 5, 4}, {6, 3, 2, 5, 1, 4},
+                                             {3, 6, 2, 5, 4, 1}, {3, 6, 2, 1, 5, 4}, {3, 6, 2, 5, 1, 4},
+                                             {3, 2, 6, 5, 4, 1}, {3, 2, 6, 1, 5, 4}, {3, 2, 6, 5, 1, 4}};
+              static const double SGN[9] = {-1.0, -1.0, 1.0, 1.0, 1.0, -1.0, -1.0, -1.0, 1.0};
+              static const int BPERM[4] = {3, 2, 1, 4};
+              const Integer dims[6] = {RANGE(h3b), RANGE(p6b), RANGE(p5b), RANGE(h2b), RANGE(h1b), RANGE(p4b)};
+              tce_pair(triplesx, t2sub, v2sub, RANGE(p5b), RANGE(p6b), RANGE(h3b), RANGE(p7b), BPERM,
+                       RANGE(p4b) * RANGE(h1b) * RANGE(h2b), RANGE(p5b) * RANGE(p6b) * RANGE(h3b), RANGE(p7b), dims,
+                       PERM[K], SGN[K]);
+            }
           }
       }
     }

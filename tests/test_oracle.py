@@ -183,6 +183,42 @@ def test_second_formulation_doubles(oracle):
     assert np.allclose(t3.reshape(p4d, p5d, p6d, h1d, h2d, h3d), ref, rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("restricted", [True, False])
+def test_second_formulation_singles_every_tuple(oracle, restricted):
+    """The singles tile of EVERY tuple of the H2O C2v table through the original TCE-generated form
+    (ccsd_t_singles.F:140-246: TCE_SORT_4(4,3,2,1), outer product, one TCE_SORTACC_6 per dispatch test with the
+    permutation and sign written there) equals the nine loop kernels sd_t_s1_1..9 -- the layouts and signs of the
+    kernels derived a second, independent way, including diagonal tuples where several tests fire on one row."""
+    st = synth.physical(synth.shape_tiling("h2o_ccpvdz_c2v", restricted=restricted))
+    tasks = oracle.task_list(st.t)
+    fired = 0
+    for row in tasks:
+        tup = [int(x) for x in row[:6]]
+        a = oracle.tuple_tiles(st, tup)[0]
+        b = oracle.singles_tce(st, tup)
+        assert np.allclose(a, b, rtol=0, atol=1e-16), tup
+        fired += int(np.any(a != 0.0))
+    assert fired > len(tasks) // 4
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_second_formulation_doubles_every_tuple(oracle, restricted):
+    """The doubles tile of EVERY tuple of the H2O C2v table through ccsd_t_doubles.F's own formulation -- V2 sorted
+    with the contracted index fastest (TCE_SORT_4 4,3,2,1 / 3,2,1,4), DGEMM('T','N'), and the eighteen TCE_SORTACC_6
+    permutations and signs written in ccsd_t_doubles.F:206-267 and :457-520 -- equals the eighteen loop kernels
+    sd_t_d1_1..9 / sd_t_d2_1..9 driven by offl_ccsd_t_doubles_l.F."""
+    st = synth.physical(synth.shape_tiling("h2o_ccpvdz_c2v", restricted=restricted))
+    tasks = oracle.task_list(st.t)
+    scale = 0.0
+    for row in tasks:
+        tup = [int(x) for x in row[:6]]
+        a = oracle.tuple_tiles(st, tup)[1]
+        b = oracle.doubles_tce(st, tup)
+        assert np.allclose(a, b, rtol=0, atol=1e-15 * max(1.0, float(np.abs(a).max()))), tup
+        scale = max(scale, float(np.abs(a).max()))
+    assert scale > 0.0
+
+
 def test_all_27_kernels_against_numpy(oracle):
     """Each kernel == its declaration: triplesx(<declared order>) +-= tsub * v2sub (ccsd_t_kernels_omp.F)."""
     from nwchem_b200.kernel_tables import DECL, SIGN  # the product's own table, checked here against the oracle
