@@ -921,9 +921,8 @@ Integer ora_ccsd_t(const ora_ctx *c, double *energy /*[2]*/, Integer *klist_out 
 /*   table[nvab]    = 'tce:restart_triples_table' (:84-95), one CCSD(T) partial per t_p4b.   */
 /* Outer loop over t_p4b (:120), inner loops and filters :129-150, energy accumulation       */
 /* E += f*D*(S+D)/Delta (:188-206), table update :274, begin update :247, final sum :288.    */
-/* max_outer > 0 stops after that many outer tiles (an interrupted run); the tile bodies use */
-/* the same singles/doubles restatement as ora_ccsd_t_loop (ccsd_t_restart.F calls the       */
-/* non-offload ccsd_t_singles/ccsd_t_doubles, which build the same two tiles).               */
+/* max_outer > 0 stops after that many outer tiles (an interrupted run); the tile bodies are   */
+/* ccsd_t_singles / ccsd_t_doubles in their TCE-generated form, as in ccsd_t_restart.F:157-160 */
 /* ------------------------------------------------------------------------------------ */
 Integer ora_ccsd_t_restart(const ora_ctx *c, Integer *restart_begin, double *table, Integer max_outer,
                            double *t_energy) {
@@ -948,7 +947,18 @@ Integer ora_ccsd_t_restart(const ora_ctx *c, Integer *restart_begin, double *tab
                 continue;
               const Integer tuple[6] = {t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b};
               double e[2] = {0.0, 0.0};
-              ora_ccsd_t_loop(c, tuple, a_singles, a_doubles, e, NULL);
+              const Integer sz = RANGE(t_p4b) * RANGE(t_p5b) * RANGE(t_p6b) * RANGE(t_h1b) * RANGE(t_h2b) * RANGE(t_h3b);
+              memset(a_singles, 0, sizeof(double) * (size_t)sz); /* :153-156 */
+              memset(a_doubles, 0, sizeof(double) * (size_t)sz);
+              ora_ccsd_t_singles_tce(c, a_singles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* ccsd_t_singles, :157 */
+              ora_ccsd_t_doubles_tce(c, a_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* ccsd_t_doubles, :159 */
+              ora_ccsd_t_dot(a_singles, a_doubles, (int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b,
+                             c->evl_sorted + c->offset[t_h1b - 1], c->evl_sorted + c->offset[t_h2b - 1],
+                             c->evl_sorted + c->offset[t_h3b - 1], c->evl_sorted + c->offset[t_p4b - 1],
+                             c->evl_sorted + c->offset[t_p5b - 1], c->evl_sorted + c->offset[t_p6b - 1], RANGE(t_h1b),
+                             RANGE(t_h2b), RANGE(t_h3b), RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), &e[0],
+                             &e[1]); /* factor and the energy loop, :161-206 */
+              (void)tuple;
               energy += e[1];
             }
     *restart_begin = outer_virtual_index + 1;   /* :247 */
