@@ -115,19 +115,19 @@ void launch_antisym(const AntisymJob* d_jobs, int njobs, long long max_block_dou
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict__ jobs) {
   const RepackJob j = jobs[blockIdx.y];
-  const int nb1 = (j.X1 + 3) >> 2, nb2 = (j.X2 + 3) >> 2, nb3 = (j.X3 + 3) >> 2, nk4 = (j.K + 3) >> 2;
-  const long long total = (long long)nk4 * nb1 * nb2 * nb3 * BLK_DOUBLES;
+  const int nb1 = (j.X1 + 3) >> 2, nb2 = (j.X2 + 3) >> 2, nb3 = (j.X3 + 3) >> 2, nkq = (j.K + 4 * KPL - 1) / (4 * KPL);
+  const long long total = (long long)nkq * nb1 * nb2 * nb3 * BLK_DOUBLES;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const int kk = (int)(e & 3), r = (int)((e >> 2) & 63);
-    long long blk = e >> 8;
+    const int pl = (int)(e & (KPL - 1)), kk = (int)((e >> 1) & 3), r = (int)((e >> 3) & 63);
+    long long blk = e >> 9;
     const int b1 = (int)(blk % nb1); blk /= nb1;
     const int b2 = (int)(blk % nb2); blk /= nb2;
     const int b3 = (int)(blk % nb3); blk /= nb3;
     const int kq = (int)blk;
     // in-block row r = i1 | (i2&1)<<2 | (i3&1)<<3 | (i2>>1)<<4 | (i3>>1)<<5   (tables.h block_row)
     const int i1 = r & 3, i2 = ((r >> 2) & 1) | (((r >> 4) & 1) << 1), i3 = ((r >> 3) & 1) | (((r >> 5) & 1) << 1);
-    const int x1 = 4 * b1 + i1, x2 = 4 * b2 + i2, x3 = 4 * b3 + i3, k = 4 * kq + kk;
+    const int x1 = 4 * b1 + i1, x2 = 4 * b2 + i2, x3 = 4 * b3 + i3, k = 4 * KPL * kq + 4 * pl + kk;
     double v = 0.0;
     if (x1 < j.X1 && x2 < j.X2 && x3 < j.X3 && k < j.K)
       v = j.scale * __ldg(j.src + x1 * j.s1 + x2 * j.s2 + x3 * j.s3 + k * j.sk);
@@ -155,13 +155,14 @@ constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
 #define NWC_CTAS_PER_SM 3
 #endif
 // 3 CTAs/SM: 128 registers, 10-stage ring (75 KiB smem);  4 CTAs/SM: 96 registers, 5-stage ring (55 KiB smem)
-constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 5 : 10;   // ring depth; one k4 plane (4 KiB) per stage
-constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // G1 block + G2 block = 4 KiB
+constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 2 : 5;   // ring depth; KPL k4 planes (8 KiB: G1 block + G2 block) per stage
+constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // one stage: G1 block + G2 block = 8 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
 constexpr int MAX_SDESC = 12;   // a tuple fires at most nine sd_t_s1_K kernels; the engine rejects more than 12
 constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
 constexpr int SD_PER_PASS = (RING_DOUBLES / SD_TERM) < 9 ? (RING_DOUBLES / SD_TERM) : 9;   // terms staged per pass
 static_assert(SD_PER_PASS >= 1, "ring too small for the singles staging");
+static_assert(KPL == 2 && BLK_DOUBLES == 512, "repack_kernel and the LDS.128 fragment loads assume two planes per block");
 
 struct SplitGeom {          // per (CTA, split): where this sub-tile's base blocks live inside a panel
   long long off1, ps1;      // G1: offset of the (b3,b2,b1) block in plane 0; plane stride (doubles)
@@ -213,6 +214,11 @@ int partials_per_item() { return NCONSUMERS / 32; }
 __host__ __device__ constexpr int canon_fold(int x) { return (x ^ ((x << 2) | (x >> 2))) & 15; }
 __host__ __device__ constexpr int canon_swz(int L) { return L ^ canon_fold((L >> 4) & 15) ^ canon_fold((L >> 8) & 15); }
 
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -287,38 +293,48 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
     const int nk4 = hdr_next.x;
     const unsigned int neghi = hdr_next.y ? 0x80000000u : 0u;
     if (d + 1 < d1) hdr_next = __ldg(reinterpret_cast<const int2*>(&descs[d + 1].nk4));
-    for (int q = 0; q < nk4; q++) {
+    const int nst = (nk4 + KPL - 1) / KPL;   // ring stages of this contraction: two k4 planes each
+    for (int q = 0; q < nst; q++) {
       unsigned long long cw = 0;
       if (timing) cw = clock64();
       mbar_wait(&full[st], ph);
       if (timing) twait += clock64() - cw;
       const uint32_t off = (uint32_t)(st * PLANE_DOUBLES * 8);
-      double a[RB], b[CB];
+      // .x = plane 0, .y = plane 1 of the stage: one LDS.128 per 8-row block serves both k4 steps
+      double2 a[RB], b[CB];
 #pragma unroll
-      for (int i = 0; i < RB; i++) a[i] = lds64(a_base + off + i * 256);
+      for (int i = 0; i < RB; i++) a[i] = lds128(a_base + off + i * 512);
 #pragma unroll
-      for (int j = 0; j < CB; j++) b[j] = lds64(b_base + off + j * 256);
+      for (int j = 0; j < CB; j++) b[j] = lds128(b_base + off + j * 512);
       // contraction sign: flip the sign bit of the smaller fragment set
       if (RB <= CB) {
 #pragma unroll
-        for (int i = 0; i < RB; i++) a[i] = __hiloint2double(__double2hiint(a[i]) ^ neghi, __double2loint(a[i]));
+        for (int i = 0; i < RB; i++) {
+          a[i].x = __hiloint2double(__double2hiint(a[i].x) ^ neghi, __double2loint(a[i].x));
+          a[i].y = __hiloint2double(__double2hiint(a[i].y) ^ neghi, __double2loint(a[i].y));
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < CB; j++) b[j] = __hiloint2double(__double2hiint(b[j]) ^ neghi, __double2loint(b[j]));
+        for (int j = 0; j < CB; j++) {
+          b[j].x = __hiloint2double(__double2hiint(b[j].x) ^ neghi, __double2loint(b[j].x));
+          b[j].y = __hiloint2double(__double2hiint(b[j].y) ^ neghi, __double2loint(b[j].y));
+        }
       }
       // Release the ring slot.  mbarrier.arrive may be scheduled right after the loads were *issued*, and the
       // producer's TMA write can then overtake a still-queued LDS (a real WAR race: ~1e-9 energy noise in ~20 % of
       // runs).  Making the barrier address depend on every fragment register forces the arrive behind the
-      // completion of all ten loads at the cost of a few LOP3s; `zero` is a run-time 0 the compiler cannot fold.
+      // completion of all the loads at the cost of a few LOP3s; `zero` is a run-time 0 the compiler cannot fold.
       auto release = [&]() {
         unsigned int dep = 0;
 #pragma unroll
-        for (int i = 0; i < RB; i++) dep ^= (unsigned int)__double2hiint(a[i]);
+        for (int i = 0; i < RB; i++) dep ^= (unsigned int)__double2hiint(a[i].x) ^ (unsigned int)__double2hiint(a[i].y);
 #pragma unroll
-        for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j]);
+        for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j].x) ^ (unsigned int)__double2hiint(b[j].y);
         dep &= zero;
         if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[st]) + dep));
       };
+      // an odd plane count leaves the second plane of the last stage all zero (k padding): its DMMAs are skipped
+      const bool two = (KPL * q + 1) < nk4;
       if (MASKED) {
         // Edge sub-tiles of ragged tiles: bit i*CB+j of `live` clear = block (i,j) lies in the zero padding.
         // A predicated-off DMMA still holds the FP64 pipe for its full 16 cycles (tools/pred_dmma.cu) and ptxas
@@ -328,15 +344,29 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
 #pragma unroll
         for (int g = 0; g < 4; g++) {
           const int u = 4 * g;
-          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB], b[u % CB], a[(u + 1) / CB], b[(u + 1) % CB],
-                       a[(u + 2) / CB], b[(u + 2) % CB], a[(u + 3) / CB], b[(u + 3) % CB], ((live >> u) & 15u) != 0u);
+          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].x, b[u % CB].x, a[(u + 1) / CB].x,
+                       b[(u + 1) % CB].x, a[(u + 2) / CB].x, b[(u + 2) % CB].x, a[(u + 3) / CB].x, b[(u + 3) % CB].x,
+                       ((live >> u) & 15u) != 0u);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int u = 4 * g;
+          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].y, b[u % CB].y, a[(u + 1) / CB].y,
+                       b[(u + 1) % CB].y, a[(u + 2) / CB].y, b[(u + 2) % CB].y, a[(u + 3) / CB].y, b[(u + 3) % CB].y,
+                       two && ((live >> u) & 15u) != 0u);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < RB; i++)
 #pragma unroll
-          for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i], b[j]);
+          for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i].x, b[j].x);
         release();
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < RB; i++)
+#pragma unroll
+            for (int j = 0; j < CB; j++) dmma884(acc[i * CB + j][0], acc[i * CB + j][1], a[i].y, b[j].y);
+        }
       }
       if (++st == STAGES) { st = 0; ph ^= 1; }
     }
@@ -498,7 +528,8 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
           const ContrDesc dd = descs[d];
           const double* g1 = dd.g1 + g.off1;
           const double* g2 = dd.g2 + g.off2;
-          for (int q = 0; q < dd.nk4; q++) {
+          const int nst = (dd.nk4 + KPL - 1) / KPL;
+          for (int q = 0; q < nst; q++) {
             mbar_wait(&sm.empty[st], ph);
             mbar_arrive_expect_tx(&sm.full[st], (uint32_t)(PLANE_DOUBLES * 8));
             double* dst = sm.ring + st * PLANE_DOUBLES;
@@ -520,7 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     double acc[16][2];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
-    const uint32_t ring_u32 = smem_u32(sm.ring) + (uint32_t)(lane * 8);
+    const uint32_t ring_u32 = smem_u32(sm.ring) + (uint32_t)(lane * 16);   // a lane's two planes are adjacent: LDS.128
     int st = 0, ph = 0;
     bool first_split = true;
     const unsigned int zero_rt = (unsigned int)sm.zero;
@@ -541,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       if (own1 == 0) { rb0 = 0; cb0 = 2 * wo0 + 4 * wo1; }
       else if (own1 == 2) { rb0 = 2 * wo0 + 4 * wo1; cb0 = 0; }
       else { rb0 = 4 * (o_h1 ? wo0 : wo1); cb0 = 4 * (o_h1 ? wo1 : wo0); }
-      const uint32_t a_base = ring_u32 + (uint32_t)(rb0 * 256), b_base = ring_u32 + (uint32_t)(BLK_DOUBLES * 8 + cb0 * 256);
+      const uint32_t a_base = ring_u32 + (uint32_t)(rb0 * 512), b_base = ring_u32 + (uint32_t)(BLK_DOUBLES * 8 + cb0 * 512);
       // 8x8 blocks of this warp's tile that hold in-range rows and columns (all of them away from tile edges)
       const unsigned int am = sm.geom[s].amask >> rb0, bm = sm.geom[s].bmask >> cb0;
       const int lcb = own1 + 1;   // log2(column blocks)

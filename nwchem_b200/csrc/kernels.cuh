@@ -3,10 +3,11 @@
 // Operand "panel" format (both ABI tiers feed the fused kernel this format):
 //   a contraction operand  X(k ; x1,x2,x3)  -- k the contracted index, (x1,x2,x3) the three external
 //   indices in split order (G1: pa,h_lo,h_hi / G2: hb,p_hi,p_lo, see tables.h) -- is stored as
-//       P[kq][b3][b2][b1][i3][i2][i1][kk] ,  x_j = 4*b_j + i_j ,  k = 4*kq + kk ,
-//   zero padded to multiples of 4 in every index.  One (kq,b3,b2,b1) "base block" is 64 rows x 4 k
-//   = 256 doubles = 2 KiB contiguous: exactly the A (or B) operand of sixteen DMMA.8x8x4 row blocks,
-//   fetched with ONE cp.async.bulk (TMA) and read from shared memory conflict-free.
+//       P[kq][b3][b2][b1][i3][i2][i1][kk][pl] ,  x_j = 4*b_j + i_j ,  k = 8*kq + 4*pl + kk ,
+//   zero padded to multiples of 4 in the external indices and of 8 in k.  One (kq,b3,b2,b1) "base block" is
+//   64 rows x 4 kk x 2 planes = 512 doubles = 4 KiB contiguous: the A (or B) operand of TWO k4 steps of sixteen
+//   DMMA.8x8x4 row blocks each, fetched with ONE cp.async.bulk (TMA); a lane's fragment elements of the two planes
+//   are adjacent, so one conflict-free LDS.128 per 8-row block serves both steps.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -14,7 +15,8 @@
 namespace nwc {
 
 constexpr int SB = 4;              // base sub-tile edge (all six indices)
-constexpr int BLK_DOUBLES = 256;   // 64 rows x 4 k
+constexpr int KPL = 2;             // k4 planes per base block / ring stage
+constexpr int BLK_DOUBLES = 256 * KPL;   // 64 rows x 4 kk x KPL planes
 constexpr int SUBTILE = 4096;      // 4^6 t3 elements per work item
 
 struct ContrDesc {      // one fired sd_t_d1_K / sd_t_d2_K call
@@ -64,7 +66,7 @@ struct AntisymJob {     // dense block dst[x0][x1][x2][x3] (x3 fastest) = ca*a[s
 
 inline long long panel_doubles(int X1, int X2, int X3, int K) {
   auto c4 = [](int v) { return (long long)((v + 3) / 4); };
-  return c4(K) * c4(X1) * c4(X2) * c4(X3) * BLK_DOUBLES;
+  return (long long)((K + 4 * KPL - 1) / (4 * KPL)) * c4(X1) * c4(X2) * c4(X3) * BLK_DOUBLES;
 }
 
 // launchers (kernels.cu).  All asynchronous on `stream`.
