@@ -4,7 +4,7 @@
 //  fused_kernel  : one CTA (4 MMA warps + 1 TMA producer warp) = one 4^6 sub-tile of the t3 tile of one
 //                  (p4,p5,p6,h1,h2,h3) tile tuple.  For each of the nine index splits it runs the concatenated-K GEMM
 //                  of every fired sd_t_d2_K / sd_t_d1_K contraction of that split on FP64 tensor cores (DMMA.8x8x4),
-//                  operands staged by cp.async.bulk (TMA, SASS UBLKCP) through a 10-stage mbarrier ring; each warp
+//                  operands staged by cp.async.bulk (TMA, SASS UBLKCP) through a 5-stage mbarrier ring of 8 KiB stages (two k4 planes each); each warp
 //                  keeps the running sum of ITS quarter of the sub-tile in a canonical shared-memory copy and seeds
 //                  the accumulators of the next split from it (nine permutations fused with no FP64 add); then the
 //                  singles, factor/denominator and the E[T], E(T) reduction.  The t3 tile never exists in HBM.
@@ -154,7 +154,7 @@ constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
 #ifndef NWC_CTAS_PER_SM
 #define NWC_CTAS_PER_SM 3
 #endif
-// 3 CTAs/SM: 128 registers, 10-stage ring (75 KiB smem);  4 CTAs/SM: 96 registers, 5-stage ring (55 KiB smem)
+// 3 CTAs/SM: 128 registers, 5-stage ring of 8 KiB stages (75 KiB smem);  4 CTAs/SM: 96 registers, 2 stages (measured slower)
 constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 2 : 5;   // ring depth; KPL k4 planes (8 KiB: G1 block + G2 block) per stage
 constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // one stage: G1 block + G2 block = 8 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
@@ -278,8 +278,8 @@ __device__ __forceinline__ void xfer_any(int s, double (&acc)[16][2], double* ca
 }
 
 // All K loops of one split whose G1 holds OWN1 owner indices: the warp tile is (8>>OWN1) x (2<<OWN1) blocks of 8x8.
-// Descriptor headers (plane count, sign) are fetched one descriptor ahead; the plane loop itself is
-// wait -> LDS fragments -> sign -> release slot (once the loads have landed) -> 16 DMMA.
+// Descriptor headers (plane count, sign) are fetched one descriptor ahead; the stage loop itself is
+// wait -> LDS.128 fragments of two k4 planes -> sign -> release slot (once the loads have landed) -> 2 x 16 DMMA.
 template <int OWN1, bool MASKED>
 __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc* __restrict__ descs, int d0, int d1,
                                           uint32_t a_base, uint32_t b_base, uint64_t* full, uint64_t* empty, int& st,
