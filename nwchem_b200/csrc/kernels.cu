@@ -77,6 +77,28 @@ __device__ __forceinline__ void dmma884x4_if(double (&c0)[2], double (&c1)[2], d
       : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1]), "+d"(c2[0]), "+d"(c2[1]), "+d"(c3[0]), "+d"(c3[1])
       : "d"(a0), "d"(b0), "d"(a1), "d"(b1), "d"(a2), "d"(b2), "d"(a3), "d"(b3), "r"(on));
 }
+// the same for both k4 planes of a stage: eight DMMAs (plane 0 then plane 1 of four blocks) behind one guard
+__device__ __forceinline__ void dmma884x8_if(double (&c0)[2], double (&c1)[2], double (&c2)[2], double (&c3)[2], double2 a0,
+                                             double2 b0, double2 a1, double2 b1, double2 a2, double2 b2, double2 a3,
+                                             double2 b3, unsigned int on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, %24;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE8;\n\t"
+      "NWC_LOOP8:\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%10}, {%11}, {%2,%3};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%12}, {%13}, {%4,%5};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%14}, {%15}, {%6,%7};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%16}, {%17}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%18}, {%19}, {%2,%3};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%20}, {%21}, {%4,%5};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%22}, {%23}, {%6,%7};\n\t"
+      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP8;\n\t"
+      "NWC_DONE8:\n\t}"
+      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1]), "+d"(c2[0]), "+d"(c2[1]), "+d"(c3[0]), "+d"(c3[1])
+      : "d"(a0.x), "d"(b0.x), "d"(a1.x), "d"(b1.x), "d"(a2.x), "d"(b2.x), "d"(a3.x), "d"(b3.x), "d"(a0.y), "d"(b0.y),
+        "d"(a1.y), "d"(b1.y), "d"(a2.y), "d"(b2.y), "d"(a3.y), "d"(b3.y), "r"(on));
+}
 
 // ------------------------------------------------------------------------------------------------
 // `2eorb` V2: spin-orbital block from (up to) two orbital-form blocks -- the device form of the two
@@ -341,19 +363,21 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
         // if-converts plain branches around them, so blocks are skipped in groups of four by dmma884x4_if;
         // the slot is released first (nothing is hoisted across those branches).
         release();
+        if (two) {
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int u = 4 * g;
-          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].x, b[u % CB].x, a[(u + 1) / CB].x,
-                       b[(u + 1) % CB].x, a[(u + 2) / CB].x, b[(u + 2) % CB].x, a[(u + 3) / CB].x, b[(u + 3) % CB].x,
-                       ((live >> u) & 15u) != 0u);
-        }
+          for (int g = 0; g < 4; g++) {
+            const int u = 4 * g;
+            dmma884x8_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB], b[u % CB], a[(u + 1) / CB], b[(u + 1) % CB],
+                         a[(u + 2) / CB], b[(u + 2) % CB], a[(u + 3) / CB], b[(u + 3) % CB], ((live >> u) & 15u) != 0u);
+          }
+        } else {
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int u = 4 * g;
-          dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].y, b[u % CB].y, a[(u + 1) / CB].y,
-                       b[(u + 1) % CB].y, a[(u + 2) / CB].y, b[(u + 2) % CB].y, a[(u + 3) / CB].y, b[(u + 3) % CB].y,
-                       two && ((live >> u) & 15u) != 0u);
+          for (int g = 0; g < 4; g++) {
+            const int u = 4 * g;
+            dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].x, b[u % CB].x, a[(u + 1) / CB].x,
+                         b[(u + 1) % CB].x, a[(u + 2) / CB].x, b[(u + 2) % CB].x, a[(u + 3) / CB].x, b[(u + 3) % CB].x,
+                         ((live >> u) & 15u) != 0u);
+          }
         }
       } else {
 #pragma unroll
