@@ -27,4 +27,15 @@ for shape, ts in (("h2o_ccpvdz_c2v", 20), ("h2o_ccpvdz_c2v", 5), ("h2o_ccpvdz_c1
     cases.append(dict(shape=shape, tilesize=ts, tasks=len(r["tasks"]), e1=r["e1"], e2=r["e2"], flops=r["counts"].flops))
 json.dump(dict(generator="tests/golden/make_golden.py", seed=20240229, cases=cases),
           open(os.path.join(HERE, "oracle_energies.json"), "w"), indent=1)
+# regression pins of the widened rows: the restart table and the `2eorb` offset table of the H2O C2v tiling
+from nwchem_b200 import tiling as tl
+st = synth.physical(synth.shape_tiling("h2o_ccpvdz_c2v"), intorb=True)
+begin, table, t_energy, done = ora.ccsd_t_restart(st)
+tab, size = tl.v2orb_offset(st.orb.a)
+json.dump(dict(generator="tests/golden/make_golden.py", shape="h2o_ccpvdz_c2v", tilesize=20,
+               restart_table=[float(x) for x in table], restart_t_energy=t_energy,
+               b2am=[int(x) for x in st.orb.a.b2am], range_alpha=[int(x) for x in st.orb.a.range_alpha],
+               sym_alpha=[int(x) for x in st.orb.a.sym_alpha], v2orb_hash=[int(x) for x in tab], v2orb_size=int(size),
+               v2orb_blocks=len(tl.v2orb_blocks(st.orb.a)[0])),
+          open(os.path.join(HERE, "h2o_restart_2eorb.json"), "w"), indent=1)
 print("ok")

@@ -118,6 +118,20 @@ def test_golden_energies(oracle):
         assert r["counts"].flops == case["flops"]
 
 
+def test_golden_restart_table_and_2eorb_offsets(oracle):
+    # regression pins generated by tests/golden/make_golden.py (restart table: ccsd_t_restart.F; k_b2am and the
+    # checkpointed k_v2_alpha_offset table: tce_tile.F:1156-1212, tce_mo2e_offset_intorb.F)
+    g = json.load(open(os.path.join(GOLD, "h2o_restart_2eorb.json")))
+    st = synth.physical(synth.shape_tiling(g["shape"], tilesize=g["tilesize"]), intorb=True)
+    _, table, t_energy, _ = oracle.ccsd_t_restart(st)
+    assert np.allclose(table, g["restart_table"], rtol=1e-12, atol=1e-16)
+    assert abs(t_energy - g["restart_t_energy"]) <= 1e-12 * abs(t_energy)
+    a = st.orb.a
+    assert [int(x) for x in a.b2am] == g["b2am"] and [int(x) for x in a.range_alpha] == g["range_alpha"]
+    assert [int(x) for x in a.sym_alpha] == g["sym_alpha"]
+    assert [int(x) for x in st.orb.v2orb_hash] == g["v2orb_hash"] and len(st.orb.v2orb) == g["v2orb_size"]
+
+
 def test_survey_flop_and_call_counts(oracle):
     # dry run of the dispatch logic, no arithmetic
     class D:
