@@ -108,3 +108,34 @@ def test_2eorb_host_plan_reproduces_spin_orbital_blocks(restricted):
     bad.orb.v2orb_hash[1] += 1
     with pytest.raises(RuntimeError):
         capi.host_2eorb_plan(bad, 4, 4, 1, 1)
+
+
+def test_public_struct_layouts_match_the_ctypes_mirror(tmp_path):
+    """include/nwc_triples.h compiled as plain C (it is the C ABI a Fortran/C caller sees): the sizes and field offsets
+    of the public structs must be what nwchem_b200/capi.py mirrors with ctypes."""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = {"nwc_tce_state": [f for f, _ in capi.TceState._fields_],
+              "nwc_triples_stats": [f for f, _ in capi.Stats._fields_],
+              "nwc_tce_orb_state": [f for f, _ in capi.OrbState._fields_]}
+    body = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "nwc_triples.h")}"',
+            'int main(void) {']
+    for st_, fl in fields.items():
+        body.append(f'  printf("{st_} %zu", sizeof({st_}));')
+        for f in fl:
+            body.append(f'  printf(" %zu", offsetof({st_}, {f}));')
+        body.append('  printf("\\n");')
+    body += ['  return 0;', '}']
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    mirror = {"nwc_tce_state": capi.TceState, "nwc_triples_stats": capi.Stats, "nwc_tce_orb_state": capi.OrbState}
+    for line in out:
+        if not line.strip():
+            continue
+        name, size, *offs = line.split()
+        cls = mirror[name]
+        assert int(size) == C.sizeof(cls), name
+        assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
