@@ -405,7 +405,7 @@ int nwc_triples_run(nwc_triples_ctx* c, Integer first, Integer stride, Integer m
   };
   for (Integer k = first; k < nt && (max_tasks <= 0 || done < max_tasks); k += stride, done++) {
     emit_tuple(c, &c->klist[7 * k]);
-    if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)1500000000 || e.pending_tuples() >= 4096) flush();
+    if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)32000000 || e.pending_tuples() >= 4096) flush();
   }
   flush();
   return 0;
@@ -446,7 +446,7 @@ int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, I
               if (k < first || (k - first) % stride != 0) continue;
               const Integer t[6] = {p4, p5, p6, h1, h2, h3};
               emit_tuple(c, t);
-              if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)1500000000 || e.pending_tuples() >= 4096)
+              if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)32000000 || e.pending_tuples() >= 4096)
                 flush();
             }
     flush();
