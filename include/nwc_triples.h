@@ -16,7 +16,9 @@
  * Tier 2 ("native"): resident block stores, task partitioning and multi-GPU reduction, for hosts
  *   that keep T1/T2/V2 in HBM (replaces the Global Arrays gets of get_block.F:79-81, the nxtask
  *   counter of util_gnxtval.c:31 and the ga_dgop of ccsd_t.F:297).  Functions return 0 on success,
- *   nonzero on error with a message available from nwc_triples_last_error().
+ *   nonzero on error with a message available from nwc_triples_last_error(); after an error the context has
+ *   dropped whatever batch it was building and can be used again (CUDA errors, a missing block key, an arena
+ *   over its cap never terminate the process in this tier).
  */
 #ifndef NWC_TRIPLES_H
 #define NWC_TRIPLES_H
@@ -100,6 +102,19 @@ typedef struct {
  * as `my_rank`-th of `nranks` (nranks=1: all).  energy[0]=E[T], energy[1]=E(T), unreduced. */
 int nwc_ccsd_t_gpu(const nwc_tce_state *st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
                    double *per_task /* 2*ntasks or NULL */);
+/* the same for a given list of tasks (ntasks x 6 tile ids), e.g. a prefix of the heaviest-first list */
+int nwc_ccsd_t_gpu_tasks(const nwc_tce_state *st, Integer icuda, const Integer *tasks6, Integer ntasks, double energy[2],
+                         double *per_task /* 2*ntasks or NULL */);
+/* 1: the host driver above behaves exactly like the unmodified Fortran call sites (one pageable scratch buffer refilled
+ * per operand pair, nothing pinned, no promise to the library); 0 (default): pinned scratch + nwc_compat_set_async_uploads */
+void nwc_driver_set_reference_contract(int on);
+/* Route the host driver's Tier-1 calls (the 27 kernels, dev_mem_*, compute_en_, dev_release_, init/finalizememmodule_)
+ * into another shared library that exports the reference's symbols -- e.g. the reference's own sd_t_total.cu + memory.cu
+ * compiled unmodified -- instead of this library's.  NULL or "": back to this library.  0 on success. */
+int nwc_driver_bind_backend(const char *so_path);
+/* threads of the library's host-side loops (TCE_SORT_4 of the host driver, staging copies); <= 0: leave unchanged.
+ * torch.distributed.run exports OMP_NUM_THREADS=1, so a launcher should pass cores / ranks-per-node here. */
+void nwc_triples_set_host_threads(int n);
 /* one tuple through the Tier-1 surface; optional t3 tiles out (host, T3(h3,h2,h1,p6,p5,p4)) */
 int nwc_ccsd_t_gpu_tuple(const nwc_tce_state *st, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                          double *host_doubles, double *host_singles);
@@ -120,13 +135,19 @@ typedef struct {
   long long work_items, descs, tuples;
   double flops;                        /* algorithmic FLOPs of the tuples run */
   double h2d_bytes, d2h_bytes;
-  double resident_bytes;               /* T1+T2+V2 in HBM */
+  double resident_bytes;               /* T1+T2+V2 in HBM (this rank's shard when V2 is sharded) */
+  double pull_ms;                      /* CUDA-event time of the peer-block pulls (NVLink) while timing is on */
+  double peer_bytes;                   /* bytes pulled from other GPUs' V2 shards */
+  long long pull_launches, antisym_launches;
 } nwc_triples_stats;
 
 const char *nwc_triples_last_error(void);
 int nwc_triples_create(nwc_triples_ctx **out, int device);
 int nwc_triples_destroy(nwc_triples_ctx *ctx);
-/* copies the tiling tables and uploads the three block stores into HBM (replicated per GPU) */
+/* copies the tiling tables and uploads the three block stores into HBM (replicated per GPU).  In every set_state*
+ * variant a NULL data pointer (st->t1, st->t2, st->v2, orb->v2orb) means "allocate the store, do not upload": the
+ * caller fills it on the device (nwc_triples_synth_fill).  A new set_state* call releases whatever the previous one
+ * held (other storage modes' buffers, peer mappings). */
 int nwc_triples_set_state(nwc_triples_ctx *ctx, const nwc_tce_state *st);
 /* Sharded V2 for shapes whose <pp||hp> class does not fit one HBM (replaces the ga_get of
  * get_block.F:79-81 by NVLink peer reads): block i of the V2 offset table is owned by rank i % nranks and
@@ -146,6 +167,31 @@ int nwc_triples_task_list(nwc_triples_ctx *ctx, Integer *klist7);
  * nothing across calls: it is set to this call's sums.  per_task: 2 doubles per task run, or NULL. */
 int nwc_triples_run(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
                     double *per_task);
+/* Static block partition of the task space over `nranks` GPUs, the stand-in for nxtask's dynamic counter
+ * (ccsd_t.F:174-255, util_gnxtval.c:31-36): tasks [first_task, first_task+ntasks) of the heaviest-first list (ntasks <= 0:
+ * to the end) are laid end to end, each 4^6 sub-tile weighted by the k4 steps its tuple contracts, and rank r runs the
+ * r-th equal-cost contiguous piece; a tuple on a boundary is shared between two ranks at sub-tile granularity (the
+ * energies are additive), so the balance does not depend on the number of tuples.  energy[2] = this rank's sums
+ * (combine with nwc_triples_allreduce_energy); per_task (optional, 2*ntasks doubles indexed by task - first_task) = this
+ * rank's possibly partial per-task energies. */
+int nwc_triples_run_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                              double energy[2], double *per_task);
+/* one tuple restricted to sub-tiles [item_lo, item_hi) of its linear sub-tile order (4-wide blocks, h3 block fastest,
+ * p4 block slowest; nwc_triples_tuple_items = their number): e.g. the p4 slab [4a,4b) of the t3 tile is
+ * [a*m, b*m), m = items / ceil(range(p4)/4).  Energies of disjoint ranges add up to the tuple's. */
+int nwc_triples_run_items(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], long long item_lo, long long item_hi,
+                          double energy[2]);
+long long nwc_triples_tuple_items(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6]);
+/* Synthetic stores generated on the device (benchmarks, tests): fills T1, T2 and the V2 store the context holds (whole,
+ * or this rank's shard) with scale * U(-1,1) values that are a pure function of (seed, store, block key, element index)
+ * -- no rank ever holds a store on the host and every rank count sees the same tensors.  nwchem_b200/synth.py restates
+ * the generator in numpy for the oracle. */
+int nwc_triples_synth_fill(nwc_triples_ctx *ctx, unsigned long long seed, double scale_t1, double scale_t2,
+                           double scale_v2);
+/* validation aids: read back part of a resident store (which: 1 T1, 2 T2, 3 V2 shard, 4 orbital-form V2 shard), and
+ * the spin-orbital block <g3 g4||g1 g2> as the (T) path sees it (from whichever storage the context holds) */
+int nwc_triples_debug_read(nwc_triples_ctx *ctx, int which, size_t offset, size_t n, double *host_out);
+int nwc_triples_export_v2_block(nwc_triples_ctx *ctx, const Integer g3g4g1g2[4], double *host_out);
 /* `2eorb` V2 storage (tce.fh `intorb`): the two-electron integrals are kept spin-free over the ALPHA
    tiles and every spin-orbital block <g3 g4||g1 g2> = (g3 g1|g4 g2) - (g3 g2|g4 g1) is antisymmetrised on the
    device when a tuple needs it -- replaces get_hash_block_i (get_hash_block.F:47-118) -> get_block_ind_i
@@ -171,6 +217,14 @@ int nwc_host_2eorb_plan(const nwc_tce_state *st, const nwc_tce_orb_state *orb, c
                         Integer off_host[2], Integer strides[8]);
 /* like nwc_triples_set_state, but V2 comes from `orb`; st->v2_hash / st->v2 are not read (may be NULL) */
 int nwc_triples_set_state_2eorb(nwc_triples_ctx *ctx, const nwc_tce_state *st, const nwc_tce_orb_state *orb);
+/* `2eorb` AND sharded (the only form in which (H2O)10/aug-cc-pVTZ fits: 105 GB orbital-form vs 527 GB spin-orbital,
+ * get_hash_block.F:47-118, get_block_ind.F:818-1538): the i-th orbital block (T) can touch, in storage order, is owned
+ * by rank i % nranks.  orb->v2orb, if not NULL, is the caller's full d_v2orb file (only this rank's blocks are read).
+ * Peers are mapped with the same nwc_triples_v2_ipc_handle / nwc_triples_v2_open_peers exchange as above.  The remote
+ * orbital blocks a batch of tuples needs are pulled whole over NVLink into the batch arena (contiguous 16-byte loads)
+ * and antisymmetrised locally. */
+int nwc_triples_set_state_2eorb_sharded(nwc_triples_ctx *ctx, const nwc_tce_state *st, const nwc_tce_orb_state *orb,
+                                        int rank, int nranks);
 /* Restartable (T): replaces ccsd_t_restart.F:57-290.  *restart_begin and table[nvab] are the RTDB entries
    'tce:ccsd_t_restart_begin' (1-based outer virtual tile index, :57-66) and 'tce:restart_triples_table' (:84-95).
    For outer = *restart_begin .. nvab (at most max_outer of them when max_outer > 0) the CCSD(T) partial of every
@@ -198,14 +252,18 @@ int nwc_compat_get_stats(nwc_triples_stats *out, int reset);
 int nwc_compat_set_timing(int on);
 int nwc_compat_timer_start(void);
 int nwc_compat_timer_stop_ms(double *ms);
-/* panel arena budget per batch in bytes (default 8 GiB) */
+/* panel arena budget per batch in bytes (default 8 GiB; two batches are in flight) and the hard cap of one batch
+ * arena (default 150 GiB): beyond it a call fails with an error instead of exhausting the device */
 int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
+int nwc_triples_set_arena_cap(nwc_triples_ctx *ctx, size_t bytes);
 
 /* multi-GPU: one process per GPU.  The host distributes the 128-byte id (MPI/GA broadcast in NWChem,
  * torch.distributed in bench.py), then every rank calls init; allreduce replaces ga_dgop (ccsd_t.F:297). */
 int nwc_triples_nccl_unique_id(char id128[128]);
 int nwc_triples_nccl_init(nwc_triples_ctx *ctx, const char id128[128], int rank, int nranks);
 int nwc_triples_allreduce_energy(nwc_triples_ctx *ctx, double energy[2]);
+/* the same collective on n doubles (per-task energies of a partitioned run) */
+int nwc_triples_allreduce_sum(nwc_triples_ctx *ctx, double *buf, size_t n);
 
 #ifdef __cplusplus
 }

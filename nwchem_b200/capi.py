@@ -30,7 +30,8 @@ class Stats(C.Structure):  # nwc_triples_stats
     _fields_ = [("fused_ms", C.c_double), ("repack_ms", C.c_double), ("fused_launches", C.c_longlong),
                 ("repack_launches", C.c_longlong), ("reduce_launches", C.c_longlong), ("work_items", C.c_longlong),
                 ("descs", C.c_longlong), ("tuples", C.c_longlong), ("flops", C.c_double), ("h2d_bytes", C.c_double),
-                ("d2h_bytes", C.c_double), ("resident_bytes", C.c_double)]
+                ("d2h_bytes", C.c_double), ("resident_bytes", C.c_double), ("pull_ms", C.c_double),
+                ("peer_bytes", C.c_double), ("pull_launches", C.c_longlong), ("antisym_launches", C.c_longlong)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,6 +70,20 @@ def lib() -> C.CDLL:
         _lib.nwc_triples_nccl_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.nwc_triples_allreduce_energy.argtypes = [C.c_void_p, PD]
         _lib.nwc_ccsd_t_gpu.argtypes = [C.POINTER(TceState), L, L, L, PD, PD]
+        _lib.nwc_ccsd_t_gpu_tasks.argtypes = [C.POINTER(TceState), L, PL, L, PD, PD]
+        _lib.nwc_triples_set_state_2eorb.argtypes = [C.c_void_p, C.POINTER(TceState), C.POINTER(OrbState)]
+        _lib.nwc_triples_set_state_2eorb_sharded.argtypes = [C.c_void_p, C.POINTER(TceState), C.POINTER(OrbState), C.c_int, C.c_int]
+        _lib.nwc_triples_run_partition.argtypes = [C.c_void_p, L, L, L, L, PD, PD]
+        _lib.nwc_triples_run_items.argtypes = [C.c_void_p, PL, C.c_longlong, C.c_longlong, PD]
+        _lib.nwc_triples_tuple_items.argtypes = [C.c_void_p, PL]
+        _lib.nwc_triples_tuple_items.restype = C.c_longlong
+        _lib.nwc_triples_synth_fill.argtypes = [C.c_void_p, C.c_ulonglong, C.c_double, C.c_double, C.c_double]
+        _lib.nwc_triples_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, PD]
+        _lib.nwc_triples_export_v2_block.argtypes = [C.c_void_p, PL, PD]
+        _lib.nwc_triples_allreduce_sum.argtypes = [C.c_void_p, PD, C.c_size_t]
+        _lib.nwc_triples_set_arena_cap.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.nwc_triples_set_host_threads.argtypes = [C.c_int]
+        _lib.nwc_driver_set_reference_contract.argtypes = [C.c_int]
         _lib.nwc_ccsd_t_gpu_tuple.argtypes = [C.POINTER(TceState), PL, PD, PD, PD]
     return _lib
 
@@ -82,18 +97,31 @@ def _pd(a):
 
 
 def make_state(st):
-    """BlockStores -> (nwc_tce_state, keepalive dict of the contiguous arrays it points into)."""
+    """BlockStores -> (nwc_tce_state, keepalive dict of the contiguous arrays it points into).
+    A data array that is None becomes a NULL pointer: the library allocates that store without uploading."""
     t = st.t
-    k = dict(spin=np.ascontiguousarray(t.spin, np.int64), sym=np.ascontiguousarray(t.sym, np.int64),
-             range=np.ascontiguousarray(t.range, np.int64), offset=np.ascontiguousarray(t.offset, np.int64),
-             alpha=np.ascontiguousarray(t.alpha, np.int64), evl=np.ascontiguousarray(t.evl_sorted, np.float64),
-             t1h=np.ascontiguousarray(st.t1_hash, np.int64), t1=np.ascontiguousarray(st.t1, np.float64),
-             t2h=np.ascontiguousarray(st.t2_hash, np.int64), t2=np.ascontiguousarray(st.t2, np.float64),
-             v2h=np.ascontiguousarray(st.v2_hash, np.int64), v2=np.ascontiguousarray(st.v2, np.float64))
+    f64 = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+    i64 = lambda a: None if a is None else np.ascontiguousarray(a, np.int64)
+    k = dict(spin=i64(t.spin), sym=i64(t.sym), range=i64(t.range), offset=i64(t.offset), alpha=i64(t.alpha),
+             evl=f64(t.evl_sorted), t1h=i64(st.t1_hash), t1=f64(st.t1), t2h=i64(st.t2_hash), t2=f64(st.t2),
+             v2h=i64(st.v2_hash), v2=f64(st.v2))
+    pl = lambda a: None if a is None else _pl(a)
+    pd = lambda a: None if a is None else _pd(a)
     s = TceState(t.noab, t.nvab, int(t.restricted), 0, 0, _pl(k["spin"]), _pl(k["sym"]), _pl(k["range"]),
-                 _pl(k["offset"]), _pl(k["alpha"]), _pd(k["evl"]), _pl(k["t1h"]), _pd(k["t1"]), _pl(k["t2h"]),
-                 _pd(k["t2"]), _pl(k["v2h"]), _pd(k["v2"]))
+                 _pl(k["offset"]), _pl(k["alpha"]), _pd(k["evl"]), pl(k["t1h"]), pd(k["t1"]), pl(k["t2h"]),
+                 pd(k["t2"]), pl(k["v2h"]), pd(k["v2"]))
     return s, k
+
+
+def make_orb_state(orb):
+    a = orb.a
+    k = dict(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
+             sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
+             voh=np.ascontiguousarray(orb.v2orb_hash, np.int64),
+             vo=None if orb.v2orb is None else np.ascontiguousarray(orb.v2orb, np.float64))
+    o = OrbState(a.noa, a.nva, _pl(k["b2am"]), _pl(k["spa"]), _pl(k["sya"]), _pl(k["rga"]), _pl(k["voh"]),
+                 None if k["vo"] is None else _pd(k["vo"]))
+    return o, k
 
 
 def _check(rc, what):
@@ -113,6 +141,33 @@ def ccsd_t_gpu(st, icuda=1, my_rank=0, nranks=1, ntasks=None):
     rc = lib().nwc_ccsd_t_gpu(C.byref(s), icuda, my_rank, nranks, _pd(e), _pd(pt) if pt is not None else None)
     _check(rc, "nwc_ccsd_t_gpu")
     return float(e[0]), float(e[1]), pt
+
+
+def ccsd_t_gpu_tasks(st, tasks, icuda=1):
+    """A given list of tasks (rows of >= 6 tile ids) through Tier 1.  Returns (E[T], E(T), per_task[n,2])."""
+    s, keep = make_state(st)
+    tt = np.ascontiguousarray(np.asarray(tasks, np.int64)[:, :6])
+    e = np.zeros(2)
+    pt = np.zeros((max(len(tt), 1), 2))
+    _check(lib().nwc_ccsd_t_gpu_tasks(C.byref(s), icuda, _pl(tt), len(tt), _pd(e), _pd(pt)), "nwc_ccsd_t_gpu_tasks")
+    return float(e[0]), float(e[1]), pt[:len(tt)]
+
+
+def bind_backend(so_path):
+    """Route the host driver's Tier-1 calls into another library exporting the reference's symbols (None: back)."""
+    l = lib()
+    l.nwc_driver_bind_backend.argtypes = [C.c_char_p]
+    rc = l.nwc_driver_bind_backend(so_path.encode() if so_path else None)
+    if rc != 0:
+        raise RuntimeError(f"nwc_driver_bind_backend({so_path}) failed")
+
+
+def set_reference_contract(on=True):
+    lib().nwc_driver_set_reference_contract(int(on))
+
+
+def set_host_threads(n):
+    lib().nwc_triples_set_host_threads(int(n))
 
 
 def ccsd_t_gpu_tuple(st, tup, dump=False):
@@ -157,19 +212,64 @@ class Triples:
         _check(lib().nwc_triples_set_state(self._h, C.byref(s)), "nwc_triples_set_state")
         self.t = st.t
 
-    def set_state_2eorb(self, st):
-        """`2eorb` storage: V2 is read from st.orb (synth.OrbitalV2), never from st.v2."""
+    def set_state_2eorb(self, st, rank: int = 0, world: int = 1):
+        """`2eorb` storage: V2 is read from st.orb (synth.OrbitalV2), never from st.v2.  world > 1: the orbital
+        blocks are sharded over the ranks (block i of the needed ones -> rank i % world); st.orb.v2orb is the full
+        store (or None: allocate only, fill with synth_fill)."""
         s, keep = make_state(st)
-        a = st.orb.a
-        k = dict(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
-                 sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
-                 voh=np.ascontiguousarray(st.orb.v2orb_hash, np.int64), vo=np.ascontiguousarray(st.orb.v2orb, np.float64))
-        o = OrbState(a.noa, a.nva, _pl(k["b2am"]), _pl(k["spa"]), _pl(k["sya"]), _pl(k["rga"]), _pl(k["voh"]), _pd(k["vo"]))
+        o, keep2 = make_orb_state(st.orb)
         s.v2_hash = None; s.v2 = None
-        l = lib()
-        l.nwc_triples_set_state_2eorb.argtypes = [C.c_void_p, C.POINTER(TceState), C.POINTER(OrbState)]
-        _check(l.nwc_triples_set_state_2eorb(self._h, C.byref(s), C.byref(o)), "nwc_triples_set_state_2eorb")
+        if world > 1:
+            _check(lib().nwc_triples_set_state_2eorb_sharded(self._h, C.byref(s), C.byref(o), rank, world),
+                   "nwc_triples_set_state_2eorb_sharded")
+        else:
+            _check(lib().nwc_triples_set_state_2eorb(self._h, C.byref(s), C.byref(o)), "nwc_triples_set_state_2eorb")
         self.t = st.t
+
+    def synth_fill(self, seed: int, scale=(0.05, 0.02, 0.1)):
+        """Fill the resident stores on the device with the keyed generator (synth.keyed_* restates it in numpy)."""
+        _check(lib().nwc_triples_synth_fill(self._h, seed, float(scale[0]), float(scale[1]), float(scale[2])),
+               "nwc_triples_synth_fill")
+
+    def debug_read(self, which: int, offset: int, n: int) -> np.ndarray:
+        out = np.zeros(n)
+        _check(lib().nwc_triples_debug_read(self._h, which, offset, n, _pd(out)), "nwc_triples_debug_read")
+        return out
+
+    def export_v2_block(self, g3b, g4b, g1b, g2b) -> np.ndarray:
+        g = np.array([g3b, g4b, g1b, g2b], np.int64)
+        out = np.zeros(int(np.prod([self.t.r(int(b)) for b in g])))
+        _check(lib().nwc_triples_export_v2_block(self._h, _pl(g), _pd(out)), "nwc_triples_export_v2_block")
+        return out
+
+    def run_partition(self, rank: int, world: int, first_task: int = 0, ntasks: int = 0, per_task=False):
+        """Static equal-cost block partition of tasks [first_task, first_task+ntasks) over `world` ranks, tuples on a
+        boundary shared at sub-tile granularity.  Returns this rank's (E[T], E(T)[, per_task partials])."""
+        e = np.zeros(2)
+        n = self.num_tasks - first_task if ntasks <= 0 else min(ntasks, self.num_tasks - first_task)
+        pt = np.zeros((max(n, 1), 2)) if per_task else None
+        _check(lib().nwc_triples_run_partition(self._h, rank, world, first_task, ntasks, _pd(e), _pd(pt) if per_task else None),
+               "nwc_triples_run_partition")
+        return (float(e[0]), float(e[1]), pt[:n]) if per_task else (float(e[0]), float(e[1]))
+
+    def tuple_items(self, tup) -> int:
+        tt = np.array(tup, np.int64)
+        return int(lib().nwc_triples_tuple_items(self._h, _pl(tt)))
+
+    def run_items(self, tup, item_lo: int, item_hi: int):
+        """One tuple restricted to sub-tiles [item_lo, item_hi) (linear 4-wide-block order, p4 block slowest)."""
+        tt = np.array(tup, np.int64)
+        e = np.zeros(2)
+        _check(lib().nwc_triples_run_items(self._h, _pl(tt), item_lo, item_hi, _pd(e)), "nwc_triples_run_items")
+        return float(e[0]), float(e[1])
+
+    def set_arena_cap(self, n):
+        lib().nwc_triples_set_arena_cap(self._h, int(n))
+
+    def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(arr, np.float64).copy()
+        _check(lib().nwc_triples_allreduce_sum(self._h, _pd(a), a.size), "nwc_triples_allreduce_sum")
+        return a
 
     def set_state_sharded(self, st_shard, rank: int, world: int):
         """st_shard.v2 holds only this rank's V2 blocks (see synth.shard_v2); tables are the full ones."""
@@ -318,11 +418,7 @@ def tier1_single_call(family, k, dims_task, dims_perm, kd, tsub, v2sub, eps, fac
 def host_2eorb_plan(st, g3b, g4b, g1b, g2b):
     """Product host logic of the `2eorb` path (no device): (off_direct, off_exchange, strides[2][4]) into st.orb.v2orb."""
     s, keep = make_state(st)
-    a = st.orb.a
-    k = dict(b2am=np.ascontiguousarray(a.b2am, np.int64), spa=np.ascontiguousarray(a.spin_alpha, np.int64),
-             sya=np.ascontiguousarray(a.sym_alpha, np.int64), rga=np.ascontiguousarray(a.range_alpha, np.int64),
-             voh=np.ascontiguousarray(st.orb.v2orb_hash, np.int64), vo=np.ascontiguousarray(st.orb.v2orb, np.float64))
-    o = OrbState(a.noa, a.nva, _pl(k["b2am"]), _pl(k["spa"]), _pl(k["sya"]), _pl(k["rga"]), _pl(k["voh"]), _pd(k["vo"]))
+    o, keep2 = make_orb_state(st.orb)
     g = np.array([g3b, g4b, g1b, g2b], np.int64)
     off = np.zeros(2, np.int64); strides = np.zeros(8, np.int64)
     l = lib()

@@ -6,6 +6,7 @@
 #include "host_driver.h"
 #include "engine.h"
 #include <cstring>
+#include <dlfcn.h>
 
 using namespace nwc;
 namespace nwc { Engine& compat_engine(); void compat_set_async_uploads(bool on); void compat_forget_uploads(); }
@@ -37,10 +38,24 @@ struct PinnedScratch {
     off += n;
     return p;
   }
-  void submitted() {}
   void tuple_done() { off = 0; }   // compute_en_ has synchronised the stream
 };
 PinnedScratch g_scratch;
+
+// Reference contract (nwc_driver_set_reference_contract(1)): behave exactly like the unmodified Fortran call sites --
+// the sorted operand lives in ONE pageable scratch buffer that is refilled for every (row, h7b/p7b) pair (the MA
+// push/pop of k_a_sort, ccsd_t_doubles_gpu.F:262-304,723-726), nothing is pinned, and the library is given no promise.
+bool g_reference_contract = false;
+struct PageableScratch {
+  double* base = nullptr;
+  size_t cap = 0;
+  double* acquire(size_t n) {
+    if (n > cap) { free(base); base = (double*)malloc(n * sizeof(double)); cap = n; }
+    return base;
+  }
+};
+PageableScratch g_ma_scratch;
+double* scratch(size_t n) { return g_reference_contract ? g_ma_scratch.acquire(n) : g_scratch.acquire(n); }
 
 // sorted(i,j,k,l order, l fastest) = factor * unsorted(a,b,c,d order, d fastest): tce_sort_4 semantics
 void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integer d, int i, int j, int k, int l,
@@ -60,6 +75,32 @@ void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integ
       }
 }
 
+// The Tier-1 call surface as a table.  By default it is this library's own symbols; nwc_driver_bind_backend() points it
+// at any other shared library that exports the reference's names -- e.g. the reference's own sd_t_total.cu + memory.cu
+// compiled unmodified (oracle/_ref) -- so the same host driver can be run against the reference kernels (a test of
+// the driver's calling sequence against reference code).
+typedef void (*s1_fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
+typedef void (*dx_fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
+typedef void (*mem_fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*);
+typedef void (*en_fn)(double*, double*, double*, double*, double*, double*, double*, double*, Integer*, Integer*, Integer*,
+                      Integer*, Integer*, Integer*, double*, double*);
+struct Tier1Api {
+  s1_fn s1[9] = {sd_t_s1_1_cuda_, sd_t_s1_2_cuda_, sd_t_s1_3_cuda_, sd_t_s1_4_cuda_, sd_t_s1_5_cuda_,
+                 sd_t_s1_6_cuda_, sd_t_s1_7_cuda_, sd_t_s1_8_cuda_, sd_t_s1_9_cuda_};
+  dx_fn d1[9] = {sd_t_d1_1_cuda_, sd_t_d1_2_cuda_, sd_t_d1_3_cuda_, sd_t_d1_4_cuda_, sd_t_d1_5_cuda_,
+                 sd_t_d1_6_cuda_, sd_t_d1_7_cuda_, sd_t_d1_8_cuda_, sd_t_d1_9_cuda_};
+  dx_fn d2[9] = {sd_t_d2_1_cuda_, sd_t_d2_2_cuda_, sd_t_d2_3_cuda_, sd_t_d2_4_cuda_, sd_t_d2_5_cuda_,
+                 sd_t_d2_6_cuda_, sd_t_d2_7_cuda_, sd_t_d2_8_cuda_, sd_t_d2_9_cuda_};
+  mem_fn mem_s = dev_mem_s_, mem_d = dev_mem_d_;
+  en_fn compute_en = compute_en_;
+  void (*init)(void) = initmemmodule_;
+  void (*fini)(void) = finalizememmodule_;
+  void (*release)(void) = dev_release_;
+  bool foreign = false;
+  void* handle = nullptr;
+};
+Tier1Api g_api;
+
 struct CompatSink {
   const HostState& S;
   const nwc_tce_state* st;
@@ -69,22 +110,18 @@ struct CompatSink {
                const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rh1 = S.rg(r.h1b);
     const double* blk = st->t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
-    a_sort = g_scratch.acquire((size_t)(rp4 * rh1));
+    a_sort = scratch((size_t)(rp4 * rh1));
     for (Integer p = 0; p < rp4; p++)      // TCE_SORT_2(...,2,1): stored (p4,h1) h1 fastest -> t1sub(p4,h1)
       for (Integer h = 0; h < rh1; h++) a_sort[p + rp4 * h] = blk[h + rh1 * p];
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "v2(pphh)");
     Integer h1d = rh1, h2d = S.rg(r.h2b), h3d = S.rg(r.h3b), p4d = rp4, p5d = S.rg(r.p5b), p6d = S.rg(r.p6b);
-    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
-    static const fn F[9] = {sd_t_s1_1_cuda_, sd_t_s1_2_cuda_, sd_t_s1_3_cuda_, sd_t_s1_4_cuda_, sd_t_s1_5_cuda_,
-                            sd_t_s1_6_cuda_, sd_t_s1_7_cuda_, sd_t_s1_8_cuda_, sd_t_s1_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
-    g_scratch.submitted();
+      if (fire[k]) g_api.s1[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
   }
 
   void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rp5 = S.rg(r.p5b), rh1 = S.rg(r.h1b), rh7 = S.rg(h7b);
-    a_sort = g_scratch.acquire((size_t)(rp4 * rp5 * rh1 * rh7));
+    a_sort = scratch((size_t)(rp4 * rp5 * rh1 * rh7));
     if (h7b < r.h1b) {  // ccsd_t_doubles_gpu.F:282-289
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[3], am[2]), "t2");
       sort4(blk, a_sort, rp4, rp5, rh7, rh1, 4, 2, 1, 3, -1.0);
@@ -94,17 +131,13 @@ struct CompatSink {
     }
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[1], bm[0], bm[2], bm[3]), "v2(hphh)");  // :315-327
     Integer h1d = rh1, h2d = S.rg(r.h2b), h3d = S.rg(r.h3b), h7d = rh7, p4d = rp4, p5d = rp5, p6d = S.rg(r.p6b);
-    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
-    static const fn F[9] = {sd_t_d1_1_cuda_, sd_t_d1_2_cuda_, sd_t_d1_3_cuda_, sd_t_d1_4_cuda_, sd_t_d1_5_cuda_,
-                            sd_t_d1_6_cuda_, sd_t_d1_7_cuda_, sd_t_d1_8_cuda_, sd_t_d1_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &h7d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
-    g_scratch.submitted();
+      if (fire[k]) g_api.d1[k](&h1d, &h2d, &h3d, &h7d, &p4d, &p5d, &p6d, nullptr, a_sort, const_cast<double*>(v));
   }
 
   void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
     const Integer rp4 = S.rg(r.p4b), rp7 = S.rg(p7b), rh1 = S.rg(r.h1b), rh2 = S.rg(r.h2b);
-    a_sort = g_scratch.acquire((size_t)(rp4 * rp7 * rh1 * rh2));
+    a_sort = scratch((size_t)(rp4 * rp7 * rh1 * rh2));
     if (p7b < r.p4b) {  // ccsd_t_doubles_gpu.F:942-949
       const double* blk = st->t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[1], am[0], am[2], am[3]), "t2");
       sort4(blk, a_sort, rp7, rp4, rh1, rh2, 4, 3, 2, 1, -1.0);
@@ -114,12 +147,8 @@ struct CompatSink {
     }
     const double* v = st->v2 + hash_lookup_or_die(S.v2_hash, v2_key(S, bm[0], bm[1], bm[2], bm[3]), "v2(pphp)");  // :964-976
     Integer h1d = rh1, h2d = rh2, h3d = S.rg(r.h3b), p4d = rp4, p5d = S.rg(r.p5b), p6d = S.rg(r.p6b), p7d = rp7;
-    typedef void (*fn)(Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, Integer*, double*, double*, double*);
-    static const fn F[9] = {sd_t_d2_1_cuda_, sd_t_d2_2_cuda_, sd_t_d2_3_cuda_, sd_t_d2_4_cuda_, sd_t_d2_5_cuda_,
-                            sd_t_d2_6_cuda_, sd_t_d2_7_cuda_, sd_t_d2_8_cuda_, sd_t_d2_9_cuda_};
     for (int k = 0; k < 9; k++)
-      if (fire[k]) F[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort, const_cast<double*>(v));
-    g_scratch.submitted();
+      if (fire[k]) g_api.d2[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort, const_cast<double*>(v));
   }
 };
 
@@ -127,35 +156,104 @@ struct CompatSink {
 void one_tuple(const HostState& S, const nwc_tce_state* st, const Integer t[6], double e[2], double* dump_d,
                double* dump_s) {
   Integer rp4 = S.rg(t[0]), rp5 = S.rg(t[1]), rp6 = S.rg(t[2]), rh1 = S.rg(t[3]), rh2 = S.rg(t[4]), rh3 = S.rg(t[5]);
-  initmemmodule_();                                   // :135
+  g_api.init();                                       // :135
   CompatSink sink{S, st};
-  compat_set_async_uploads(true);   // this driver owns every pinned operand it passes and never touches one in flight
-  dev_mem_s_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_singles_gpu.F:192-197
+  // opt-in fast path: this driver owns every pinned operand it passes and never touches one in flight
+  compat_set_async_uploads(!g_reference_contract && !g_api.foreign);
+  g_api.mem_s(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);    // ccsd_t_singles_gpu.F:192-197
   walk_singles(S, t, sink);                           // :139
-  dev_mem_d_(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);     // ccsd_t_doubles_gpu.F:227-232
+  g_api.mem_d(&rh1, &rh2, &rh3, &rp4, &rp5, &rp6);    // ccsd_t_doubles_gpu.F:227-232
   walk_doubles(S, t, sink);                           // :144
   double factor = tuple_factor(S, t);                 // :153-167
   double* ev = const_cast<double*>(st->evl_sorted);
-  if (dump_d)
+  if (dump_d && !g_api.foreign)
     nwc_compute_en_dump_(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
                          ev + S.offset[t[0] - 1], ev + S.offset[t[1] - 1], ev + S.offset[t[2] - 1], &rh1, &rh2, &rh3,
                          &rp4, &rp5, &rp6, dump_d, dump_s);
   else
-    compute_en_(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
+    g_api.compute_en(&factor, e, ev + S.offset[t[3] - 1], ev + S.offset[t[4] - 1], ev + S.offset[t[5] - 1],
                 ev + S.offset[t[0] - 1], ev + S.offset[t[1] - 1], ev + S.offset[t[2] - 1], &rh1, &rh2, &rh3, &rp4,
                 &rp5, &rp6, nullptr, nullptr);            // :205-215
   compat_set_async_uploads(false);
   g_scratch.tuple_done();
-  dev_release_();                                     // :219
-  finalizememmodule_();                               // :220
+  g_api.release();                                    // :219
+  g_api.fini();                                       // :220
 }
 
 }  // namespace
 
 extern "C" {
 
+void nwc_driver_set_reference_contract(int on) { g_reference_contract = on != 0; }
+
+// Route the host driver's Tier-1 calls into another shared library exporting the reference's symbols (NULL or "" =
+// back to this library).  Returns 0, or 1 if the library or one of its 33 symbols is missing.
+int nwc_driver_bind_backend(const char* so_path) {
+  if (g_api.handle) { dlclose(g_api.handle); }
+  g_api = Tier1Api();
+  if (!so_path || !*so_path) return 0;
+  void* h = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { printf("nwc_driver_bind_backend: %s\n", dlerror()); return 1; }
+  Tier1Api a;
+  bool ok = true;
+  auto sym = [&](const std::string& n) { void* p = dlsym(h, n.c_str()); ok = ok && p != nullptr; return p; };
+  for (int k = 0; k < 9; k++) {
+    a.s1[k] = (s1_fn)sym("sd_t_s1_" + std::to_string(k + 1) + "_cuda_");
+    a.d1[k] = (dx_fn)sym("sd_t_d1_" + std::to_string(k + 1) + "_cuda_");
+    a.d2[k] = (dx_fn)sym("sd_t_d2_" + std::to_string(k + 1) + "_cuda_");
+  }
+  a.mem_s = (mem_fn)sym("dev_mem_s_"); a.mem_d = (mem_fn)sym("dev_mem_d_");
+  a.compute_en = (en_fn)sym("compute_en_");
+  a.init = (void (*)(void))sym("initmemmodule_"); a.fini = (void (*)(void))sym("finalizememmodule_");
+  a.release = (void (*)(void))sym("dev_release_");
+  if (!ok) { dlclose(h); printf("nwc_driver_bind_backend: %s lacks part of the call surface\n", so_path); return 1; }
+  a.foreign = true; a.handle = h;
+  g_api = a;
+  return 0;
+}
+
+static int ccsd_t_gpu_impl(const nwc_tce_state* st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
+                           double* per_task);
 int nwc_ccsd_t_gpu(const nwc_tce_state* st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
                    double* per_task) {
+  try {
+    return ccsd_t_gpu_impl(st, icuda, my_rank, nranks, energy, per_task);
+  } catch (const std::exception& ex) {   // reference behaviour above the kernel boundary: errquit
+    printf("%s\n", ex.what());
+    fflush(stdout);
+    exit(1);
+  }
+}
+
+// a given list of tasks (ntasks x 6 tile ids: p4b,p5b,p6b,h1b,h2b,h3b) through the Tier-1 surface, e.g. a prefix of
+// the heaviest-first list; energy[2] = their sums
+int nwc_ccsd_t_gpu_tasks(const nwc_tce_state* st, Integer icuda, const Integer* tasks6, Integer ntasks, double energy[2],
+                         double* per_task) {
+  try {
+    HostState S;
+    S.load_tables(st);
+    Integer ic = icuda, devno = 0;
+    if (check_device_(&ic) != 1) { printf("nwc_ccsd_t_gpu: this rank owns no GPU and there is no CPU path\n"); return 2; }
+    device_init_(&ic, &devno);
+    if (devno == 30) return 30;
+    energy[0] = energy[1] = 0.0;
+    for (Integer k = 0; k < ntasks; k++) {
+      double e[2] = {0, 0};
+      one_tuple(S, st, tasks6 + 6 * k, e, nullptr, nullptr);
+      energy[0] += e[0];
+      energy[1] += e[1];
+      if (per_task) { per_task[2 * k] = e[0]; per_task[2 * k + 1] = e[1]; }
+    }
+    return 0;
+  } catch (const std::exception& ex) {
+    printf("%s\n", ex.what());
+    fflush(stdout);
+    exit(1);
+  }
+}
+
+static int ccsd_t_gpu_impl(const nwc_tce_state* st, Integer icuda, Integer my_rank, Integer nranks, double energy[2],
+                           double* per_task) {
   HostState S;
   S.load_tables(st);
   Integer ic = icuda, devno = 0;
@@ -251,10 +349,16 @@ int nwc_host_2eorb_plan(const nwc_tce_state* st, const nwc_tce_orb_state* orb, c
 
 int nwc_ccsd_t_gpu_tuple(const nwc_tce_state* st, const Integer tuple[6], double energy[2], double* host_doubles,
                          double* host_singles) {
-  HostState S;
-  S.load_tables(st);
-  one_tuple(S, st, tuple, energy, host_doubles, host_singles);
-  return 0;
+  try {
+    HostState S;
+    S.load_tables(st);
+    one_tuple(S, st, tuple, energy, host_doubles, host_singles);
+    return 0;
+  } catch (const std::exception& ex) {
+    printf("%s\n", ex.what());
+    fflush(stdout);
+    exit(1);
+  }
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// Host-side engine: arena, descriptor building for one or many tile tuples, batch launch.
+// Host-side engine: arenas, descriptor building for one or many tile tuples, asynchronous batch launch.
 #include "engine.h"
 #include <cstring>
 #include <algorithm>
@@ -22,6 +22,9 @@ void* Arena::alloc(size_t bytes) {
   Chunk c;
   c.size = std::max(bytes, min_chunk);
   c.off = 0;
+  if (capacity() + c.size > max_bytes)
+    throw Error("nwc_triples: batch arena would exceed its cap (" + std::to_string(max_bytes >> 20) +
+                " MiB); lower the batch budget (nwc_triples_set_batch_bytes)");
   NWC_CUDA(cudaMalloc((void**)&c.base, c.size));
   chunks_.push_back(c);
   cur_ = chunks_.size() - 1;
@@ -50,10 +53,12 @@ size_t Arena::capacity() const {
 Engine::Engine(int device) : device_(device) {
   NWC_CUDA(cudaSetDevice(device_));
   NWC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  NWC_CUDA(cudaEventCreate(&ev0_));
-  NWC_CUDA(cudaEventCreate(&ev1_));
   NWC_CUDA(cudaEventCreate(&evt0_));
   NWC_CUDA(cudaEventCreate(&evt1_));
+  for (Slot& s : slots_) {
+    NWC_CUDA(cudaEventCreate(&s.done));
+    for (cudaEvent_t& e : s.ev) NWC_CUDA(cudaEventCreate(&e));
+  }
 }
 void Engine::timer_start() { NWC_CUDA(cudaEventRecord(evt0_, stream_)); }
 double Engine::timer_stop_ms() {
@@ -66,27 +71,39 @@ double Engine::timer_stop_ms() {
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
-  arena_.release();
-  if (d_meta_) cudaFree(d_meta_);
-  if (d_jobs_) cudaFree(d_jobs_);
-  if (d_ajobs_) cudaFree(d_ajobs_);
-  if (h_pin_) cudaFreeHost(h_pin_);
-  cudaEventDestroy(ev0_);
-  cudaEventDestroy(ev1_);
+  for (Slot& s : slots_) {
+    s.arena.release();
+    if (s.d_meta) cudaFree(s.d_meta);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.h_stage) cudaFreeHost(s.h_stage);
+    cudaEventDestroy(s.done);
+    for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+  }
   cudaEventDestroy(evt0_);
   cudaEventDestroy(evt1_);
   cudaStreamDestroy(stream_);
 }
 
+void Engine::abort() {
+  cudaStreamSynchronize(stream_);
+  cudaGetLastError();
+  open_ = false;
+  tuples_.clear(); descs_.clear(); sdescs_.clear(); jobs_.clear(); ajobs_.clear(); cjobs_.clear();
+  items_ = 0; max_chunks_ = 1; max_ablock_ = max_panel_ = max_copy_ = 0;
+  for (Slot& s : slots_) { s.arena.reset(); s.busy = false; s.ntuples = 0; s.h_stage_off = 0; s.timed[0] = s.timed[1] = s.timed[2] = false; }
+}
+
 void Engine::begin_tuple(const int R_phys[6]) {
-  if (open_) { printf("nwc_triples: begin_tuple while a tuple is open\n"); exit(1); }
-  memset(&cur_, 0, sizeof(cur_));
+  if (open_) throw Error("nwc_triples: begin_tuple while a tuple is open");
+  if (slots_[cur_].busy) throw Error("nwc_triples: the batch slot being built is still in flight (collect it first)");
+  memset(&cur_hdr_, 0, sizeof(cur_hdr_));
   for (int q = 0; q < 6; q++) {
-    cur_.R[q] = R_phys[q];
-    cur_.nb[q] = (R_phys[q] + SB - 1) / SB;
+    if (R_phys[q] <= 0) throw Error("nwc_triples: tuple with an empty tile range");
+    cur_hdr_.R[q] = R_phys[q];
+    cur_hdr_.nb[q] = (R_phys[q] + SB - 1) / SB;
   }
   for (int s = 0; s < 9; s++) cur_descs_[s].clear();
-  cur_.sdesc_begin = (int)sdescs_.size();
+  cur_hdr_.sdesc_begin = (int)sdescs_.size();
   open_ = true;
 }
 
@@ -96,9 +113,15 @@ static inline double prodR(const int R[6]) {
   return p;
 }
 
+long long Engine::tuple_items(const int R_phys[6]) {
+  long long items = 1;
+  for (int q = 0; q < 6; q++) items *= (R_phys[q] + SB - 1) / SB;
+  return items;
+}
+
 void Engine::add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale,
                              std::vector<PanelSlot>* t_cache, std::vector<PanelSlot>* v_cache) {
-  if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8) { printf("nwc_triples: bad add_contraction\n"); exit(1); }
+  if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8) throw Error("nwc_triples: bad add_contraction");
   // which operand is the G1 (one particle + two holes) one, and the singleton names
   const bool t_is_g1 = (family == 2);
   const int pa = pos_of(family, k0, family == 2 ? N_P4 : N_P6);
@@ -117,10 +140,10 @@ void Engine::add_contraction(int family, int k0, int K7, const OperandView& tsub
     RepackJob j;
     j.src = op.base;
     j.s1 = op.stride[nm[0]]; j.s2 = op.stride[nm[1]]; j.s3 = op.stride[nm[2]]; j.sk = op.kstride;
-    j.X1 = cur_.R[ps[0]]; j.X2 = cur_.R[ps[1]]; j.X3 = cur_.R[ps[2]]; j.K = K7;
+    j.X1 = cur_hdr_.R[ps[0]]; j.X2 = cur_hdr_.R[ps[1]]; j.X3 = cur_hdr_.R[ps[2]]; j.K = K7;
     j.scale = scale;
     const long long n = panel_doubles(j.X1, j.X2, j.X3, j.K);
-    j.dst = (double*)arena_.alloc((size_t)n * sizeof(double));
+    j.dst = (double*)arena().alloc((size_t)n * sizeof(double));
     max_panel_ = std::max(max_panel_, n);
     jobs_.push_back(j);
     return j.dst;
@@ -143,11 +166,11 @@ void Engine::add_contraction(int family, int k0, int K7, const OperandView& tsub
   d.nk4 = (K7 + 3) / 4;
   d.neg = SIGN[family][k0] < 0 ? 1 : 0;
   cur_descs_[s].push_back(d);
-  stats.flops += 2.0 * prodR(cur_.R) * K7;
+  cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R) * K7;   // FLOPs of the whole tuple, parked here until end_tuple
 }
 
 void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub) {
-  if (!open_ || k0 < 0 || k0 > 8) { printf("nwc_triples: bad add_singles\n"); exit(1); }
+  if (!open_ || k0 < 0 || k0 > 8) throw Error("nwc_triples: bad add_singles");
   SinglesDesc d;
   memset(&d, 0, sizeof(d));
   d.t1 = t1sub.base;
@@ -159,31 +182,37 @@ void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2
   }
   d.neg = SIGN[0][k0] < 0 ? 1 : 0;
   sdescs_.push_back(d);
-  stats.flops += 2.0 * prodR(cur_.R);
+  cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R);
 }
 
-void Engine::end_tuple(const double* const eps[6], double factor) {
-  if (!open_) { printf("nwc_triples: end_tuple without begin_tuple\n"); exit(1); }
+void Engine::end_tuple(const double* const eps[6], double factor, long long item_lo, long long item_hi) {
+  if (!open_) throw Error("nwc_triples: end_tuple without begin_tuple");
   // reference argument order (h1,h2,h3,p4,p5,p6) -> physical positions
-  cur_.eps[POS_H1] = eps[0]; cur_.eps[POS_H2] = eps[1]; cur_.eps[POS_H3] = eps[2];
-  cur_.eps[POS_P4] = eps[3]; cur_.eps[POS_P5] = eps[4]; cur_.eps[POS_P6] = eps[5];
-  cur_.factor = factor;
+  cur_hdr_.eps[POS_H1] = eps[0]; cur_hdr_.eps[POS_H2] = eps[1]; cur_hdr_.eps[POS_H3] = eps[2];
+  cur_hdr_.eps[POS_P4] = eps[3]; cur_hdr_.eps[POS_P5] = eps[4]; cur_hdr_.eps[POS_P6] = eps[5];
+  const double tuple_flops = cur_hdr_.factor;
+  cur_hdr_.factor = factor;
   int n = (int)descs_.size();
   for (int s = 0; s < 9; s++) {
-    cur_.desc_begin[s] = n;
+    cur_hdr_.desc_begin[s] = n;
     descs_.insert(descs_.end(), cur_descs_[s].begin(), cur_descs_[s].end());
     n += (int)cur_descs_[s].size();
   }
-  cur_.desc_begin[9] = n;
-  cur_.sdesc_end = (int)sdescs_.size();
-  if (cur_.sdesc_end - cur_.sdesc_begin > 12) { printf("nwc_triples: more than 12 singles terms in one tuple\n"); exit(1); }
-  long long items = 1;
-  for (int q = 0; q < 6; q++) items *= cur_.nb[q];
-  cur_.item_begin = items_;
-  cur_.nitems = (int)items;
-  items_ += items;
-  tuples_.push_back(cur_);
+  cur_hdr_.desc_begin[9] = n;
+  cur_hdr_.sdesc_end = (int)sdescs_.size();
   open_ = false;
+  if (cur_hdr_.sdesc_end - cur_hdr_.sdesc_begin > 12) throw Error("nwc_triples: more than 12 singles terms in one tuple");
+  const long long all = tuple_items(cur_hdr_.R);
+  if (item_hi < 0 || item_hi > all) item_hi = all;
+  if (item_lo < 0) item_lo = 0;
+  if (item_lo > item_hi) item_lo = item_hi;
+  cur_hdr_.item_begin = items_;
+  cur_hdr_.nitems = (int)(item_hi - item_lo);
+  cur_hdr_.item_first = (int)item_lo;
+  items_ += cur_hdr_.nitems;
+  max_chunks_ = std::max(max_chunks_, reduce_chunks(cur_hdr_.nitems));
+  stats.flops += tuple_flops * ((double)cur_hdr_.nitems / (double)all);
+  tuples_.push_back(cur_hdr_);
 }
 
 void Engine::add_antisym(const AntisymJob& job) {
@@ -192,74 +221,106 @@ void Engine::add_antisym(const AntisymJob& job) {
   if (n > max_ablock_) max_ablock_ = n;
 }
 
-void Engine::flush_repack() {
-  if (!ajobs_.empty()) {   // the spin-orbital blocks first: the repack jobs below read them (same stream)
-    const size_t bytes = ajobs_.size() * sizeof(AntisymJob);
-    if (bytes > d_ajobs_cap_) {
-      if (d_ajobs_) { NWC_CUDA(cudaStreamSynchronize(stream_)); NWC_CUDA(cudaFree(d_ajobs_)); }
-      d_ajobs_cap_ = std::max(bytes * 2, (size_t)1 << 16);
-      NWC_CUDA(cudaMalloc(&d_ajobs_, d_ajobs_cap_));
-    } else {
-      NWC_CUDA(cudaStreamSynchronize(stream_));
-    }
-    NWC_CUDA(cudaMemcpyAsync(d_ajobs_, ajobs_.data(), bytes, cudaMemcpyHostToDevice, stream_));
-    launch_antisym((const AntisymJob*)d_ajobs_, (int)ajobs_.size(), max_ablock_, stream_);
+void Engine::add_copy(const CopyJob& job) {
+  cjobs_.push_back(job);
+  if (job.n > max_copy_) max_copy_ = job.n;
+  stats.peer_bytes += (size_t)job.n * sizeof(double);
+}
+
+// Host bytes -> device through the slot's pinned staging buffer: a copy from pageable memory may make the driver wait
+// for the stream (CUDA API synchronisation rules), which would serialise the host walk of the next batch behind the
+// running one.  The staging buffer is reused only after the slot has been collected.
+void Engine::upload(void* dst, const void* host, size_t bytes) {
+  if (bytes == 0) return;
+  Slot& S = slots_[cur_];
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (S.h_stage_off + need > S.h_stage_cap) {
+    // grow: copies queued from the old buffer must have been read first
+    NWC_CUDA(cudaStreamSynchronize(stream_));
+    if (S.h_stage) NWC_CUDA(cudaFreeHost(S.h_stage));
+    S.h_stage = nullptr;
+    const size_t cap = std::max((S.h_stage_off + need) * 2, (size_t)4 << 20);
+    NWC_CUDA(cudaMallocHost((void**)&S.h_stage, cap));
+    S.h_stage_cap = cap;
+    S.h_stage_off = 0;
+  }
+  char* p = S.h_stage + S.h_stage_off;
+  S.h_stage_off += need;
+  memcpy(p, host, bytes);
+  NWC_CUDA(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, stream_));
+  stats.h2d_bytes += bytes;
+}
+
+// job lists live in the slot's arena: it is private to the batch, so nothing in flight can still read it
+void* Engine::upload_jobs(const void* host, size_t bytes) {
+  void* d = arena().alloc(bytes);
+  upload(d, host, bytes);
+  return d;
+}
+
+void Engine::flush_prep() {
+  Slot& S = slots_[cur_];
+  if (!cjobs_.empty()) {   // remote blocks first: antisym / repack read the local copies (same stream)
+    const CopyJob* d = (const CopyJob*)upload_jobs(cjobs_.data(), cjobs_.size() * sizeof(CopyJob));
+    if (timing) NWC_CUDA(cudaEventRecord(S.ev[0], stream_));
+    launch_pull(d, (int)cjobs_.size(), max_copy_, stream_);
+    NWC_CUDA(cudaGetLastError());
+    if (timing) { NWC_CUDA(cudaEventRecord(S.ev[1], stream_)); S.timed[0] = true; }
+    stats.pull_launches += (long long)((cjobs_.size() + 32767) / 32768);
+    cjobs_.clear();
+    max_copy_ = 0;
+  }
+  if (!ajobs_.empty()) {   // then the spin-orbital blocks: the repack jobs below read them
+    const AntisymJob* d = (const AntisymJob*)upload_jobs(ajobs_.data(), ajobs_.size() * sizeof(AntisymJob));
+    launch_antisym(d, (int)ajobs_.size(), max_ablock_, stream_);
     NWC_CUDA(cudaGetLastError());
     stats.antisym_launches += (long long)((ajobs_.size() + 32767) / 32768);
-    stats.h2d_bytes += bytes;
     ajobs_.clear();
     max_ablock_ = 0;
   }
   if (jobs_.empty()) return;
-  const size_t bytes = jobs_.size() * sizeof(RepackJob);
-  if (bytes > d_jobs_cap_) {
-    if (d_jobs_) { NWC_CUDA(cudaStreamSynchronize(stream_)); NWC_CUDA(cudaFree(d_jobs_)); }
-    d_jobs_cap_ = std::max(bytes * 2, (size_t)1 << 16);
-    NWC_CUDA(cudaMalloc(&d_jobs_, d_jobs_cap_));
-  } else {
-    // the previous job list may still be in use by an in-flight repack launch
-    NWC_CUDA(cudaStreamSynchronize(stream_));
-  }
-  NWC_CUDA(cudaMemcpyAsync(d_jobs_, jobs_.data(), bytes, cudaMemcpyHostToDevice, stream_));
-  if (timing) NWC_CUDA(cudaEventRecord(ev0_, stream_));
-  launch_repack((const RepackJob*)d_jobs_, (int)jobs_.size(), max_panel_, stream_);
+  const RepackJob* d = (const RepackJob*)upload_jobs(jobs_.data(), jobs_.size() * sizeof(RepackJob));
+  if (timing) NWC_CUDA(cudaEventRecord(S.ev[2], stream_));
+  launch_repack(d, (int)jobs_.size(), max_panel_, stream_);
   NWC_CUDA(cudaGetLastError());
-  if (timing) {
-    NWC_CUDA(cudaEventRecord(ev1_, stream_));
-    NWC_CUDA(cudaEventSynchronize(ev1_));
-    float ms = 0;
-    NWC_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
-    stats.repack_ms += ms;
-  }
+  if (timing) { NWC_CUDA(cudaEventRecord(S.ev[3], stream_)); S.timed[1] = true; }
   stats.repack_launches += (long long)((jobs_.size() + 32767) / 32768);
-  stats.h2d_bytes += bytes;
   jobs_.clear();
   max_panel_ = 0;
 }
 
-void Engine::run(double* energies_out, double* dump_doubles, double* dump_singles) {
-  if (open_) { printf("nwc_triples: run with an open tuple\n"); exit(1); }
+int Engine::submit(double* dump_doubles, double* dump_singles) {
+  if (open_) throw Error("nwc_triples: submit with an open tuple");
   const int nt = (int)tuples_.size();
-  if (nt == 0) return;
-  flush_repack();
-  // one metadata buffer: tuples | descs | sdescs | energies | partials
+  if (nt == 0) return -1;
+  Slot& S = slots_[cur_];
+  if (S.busy) throw Error("nwc_triples: batch slot still in flight");
+  flush_prep();
+  // one metadata buffer per slot: tuples | descs | sdescs | energies | chunk sums | partials
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_t = 0, o_d = al(o_t + nt * sizeof(TupleHdr)), o_s = al(o_d + descs_.size() * sizeof(ContrDesc)),
-               o_e = al(o_s + sdescs_.size() * sizeof(SinglesDesc)), o_p = al(o_e + nt * sizeof(double2)),
+               o_e = al(o_s + sdescs_.size() * sizeof(SinglesDesc)), o_c = al(o_e + nt * sizeof(double2)),
+               o_p = al(o_c + (size_t)nt * max_chunks_ * sizeof(double2)),
                total = al(o_p + (size_t)items_ * partials_per_item() * sizeof(double2));
-  if (total > d_meta_cap_) {
-    if (d_meta_) NWC_CUDA(cudaFree(d_meta_));
-    d_meta_cap_ = total + total / 4;
-    NWC_CUDA(cudaMalloc(&d_meta_, d_meta_cap_));
+  if (total > S.d_meta_cap) {
+    if (S.d_meta) NWC_CUDA(cudaFree(S.d_meta));
+    S.d_meta = nullptr; S.d_meta_cap = 0;
+    NWC_CUDA(cudaMalloc(&S.d_meta, total + total / 4));
+    S.d_meta_cap = total + total / 4;
   }
-  char* dm = (char*)d_meta_;
-  NWC_CUDA(cudaMemcpyAsync(dm + o_t, tuples_.data(), nt * sizeof(TupleHdr), cudaMemcpyHostToDevice, stream_));
-  if (!descs_.empty())
-    NWC_CUDA(cudaMemcpyAsync(dm + o_d, descs_.data(), descs_.size() * sizeof(ContrDesc), cudaMemcpyHostToDevice, stream_));
-  if (!sdescs_.empty())
-    NWC_CUDA(cudaMemcpyAsync(dm + o_s, sdescs_.data(), sdescs_.size() * sizeof(SinglesDesc), cudaMemcpyHostToDevice, stream_));
-  stats.h2d_bytes += nt * sizeof(TupleHdr) + descs_.size() * sizeof(ContrDesc) + sdescs_.size() * sizeof(SinglesDesc);
-  if (timing) NWC_CUDA(cudaEventRecord(ev0_, stream_));
+  if ((size_t)nt > S.h_out_cap) {
+    if (S.h_out) NWC_CUDA(cudaFreeHost(S.h_out));
+    S.h_out = nullptr; S.h_out_cap = 0;
+    const size_t cap = std::max((size_t)nt * 2, (size_t)256);
+    NWC_CUDA(cudaMallocHost((void**)&S.h_out, cap * sizeof(double2)));
+    S.h_out_cap = cap;
+  }
+  char* dm = (char*)S.d_meta;
+  upload(dm + o_t, tuples_.data(), nt * sizeof(TupleHdr));
+  upload(dm + o_d, descs_.data(), descs_.size() * sizeof(ContrDesc));
+  upload(dm + o_s, sdescs_.data(), sdescs_.size() * sizeof(SinglesDesc));
+  S.timed[2] = timing;
+  if (timing) NWC_CUDA(cudaEventRecord(S.ev[4], stream_));
   if (dump_doubles)
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                       (double2*)(dm + o_p), items_, dump_doubles, dump_singles, stream_);
@@ -271,19 +332,17 @@ void Engine::run(double* energies_out, double* dump_doubles, double* dump_single
                  (double2*)(dm + o_p), items_, ragged, stream_);
   }
   NWC_CUDA(cudaGetLastError());
-  if (timing) NWC_CUDA(cudaEventRecord(ev1_, stream_));
-  launch_reduce((const TupleHdr*)(dm + o_t), nt, (const double2*)(dm + o_p), (double2*)(dm + o_e), stream_);
+  if (timing) NWC_CUDA(cudaEventRecord(S.ev[5], stream_));
+  launch_reduce((const TupleHdr*)(dm + o_t), nt, (const double2*)(dm + o_p), (double2*)(dm + o_c), max_chunks_,
+                (double2*)(dm + o_e), stream_);
   NWC_CUDA(cudaGetLastError());
-  NWC_CUDA(cudaMemcpyAsync(energies_out, dm + o_e, nt * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
-  NWC_CUDA(cudaStreamSynchronize(stream_));
-  if (timing) {
-    float ms = 0;
-    NWC_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
-    stats.fused_ms += ms;
-  }
+  NWC_CUDA(cudaMemcpyAsync(S.h_out, dm + o_e, nt * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+  NWC_CUDA(cudaEventRecord(S.done, stream_));
+  S.ntuples = nt;
+  S.busy = true;
   stats.d2h_bytes += nt * sizeof(double2);
   stats.fused_launches += 1;
-  stats.reduce_launches += 1;
+  stats.reduce_launches += 2;
   stats.work_items += items_;
   stats.descs += (long long)descs_.size();
   stats.tuples += nt;
@@ -291,6 +350,35 @@ void Engine::run(double* energies_out, double* dump_doubles, double* dump_single
   descs_.clear();
   sdescs_.clear();
   items_ = 0;
+  max_chunks_ = 1;
+  const int submitted = cur_;
+  cur_ ^= 1;
+  return submitted;
+}
+
+void Engine::collect(int slot, double* energies_out) {
+  if (slot < 0) return;
+  Slot& S = slots_[slot];
+  if (!S.busy) return;
+  NWC_CUDA(cudaEventSynchronize(S.done));
+  double* acc[3] = {&stats.pull_ms, &stats.repack_ms, &stats.fused_ms};
+  for (int k = 0; k < 3; k++)
+    if (S.timed[k]) {
+      float ms = 0;
+      NWC_CUDA(cudaEventElapsedTime(&ms, S.ev[2 * k], S.ev[2 * k + 1]));
+      *acc[k] += ms;
+      S.timed[k] = false;
+    }
+  S.h_stage_off = 0;
+  if (energies_out) memcpy(energies_out, S.h_out, (size_t)S.ntuples * sizeof(double2));
+  S.busy = false;
+  S.arena.reset();
+}
+
+void Engine::run(double* energies_out, double* dump_doubles, double* dump_singles) {
+  const int s = submit(dump_doubles, dump_singles);
+  collect(s, energies_out);
+  if (s >= 0 && !slots_[cur_].busy) cur_ = s;   // synchronous callers keep building in the same slot (one warm arena)
 }
 
 }  // namespace nwc

@@ -1,24 +1,33 @@
-// Host-side engine shared by the two ABI tiers: device arena, per-tuple descriptor building, batch launch.
+// Host-side engine shared by the two ABI tiers: device arenas, per-tuple descriptor building, batch launch.
+//
+// Two batch slots (arena + metadata buffer + pinned result buffer + events each): submit() queues everything a batch
+// needs on the stream and returns at once, so the host walks the driver logic of the NEXT batch (host_driver.h) while the
+// GPU runs the current one; collect() waits for a slot and hands out its per-tuple energies.  run() = submit + collect.
+//
+// Errors are C++ exceptions (nwc::Error).  The Tier-2 entry points turn them into a status + nwc_triples_last_error();
+// the Tier-1 compat layer prints and exits like the reference does (src/tce/ccsd_t/header.h:27-37).
 #pragma once
 #include <cstdio>
 #include <cstdlib>
-#include <vector>
+#include <stdexcept>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "kernels.cuh"
 #include "tables.h"
 
 namespace nwc {
 
-// reference error behaviour: print and exit(1) (src/tce/ccsd_t/header.h:27-37)
-#define NWC_CUDA(x)                                                                                       \
-  do {                                                                                                    \
-    cudaError_t _e = (x);                                                                                 \
-    if (_e != cudaSuccess) {                                                                              \
-      printf("CUDA CALL FAILED AT LINE %d OF FILE %s error %s\n", __LINE__, __FILE__, cudaGetErrorString(_e)); \
-      fflush(stdout);                                                                                     \
-      exit(1);                                                                                            \
-    }                                                                                                     \
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define NWC_CUDA(x)                                                                                        \
+  do {                                                                                                     \
+    cudaError_t _e = (x);                                                                                  \
+    if (_e != cudaSuccess)                                                                                 \
+      throw ::nwc::Error(std::string("CUDA CALL FAILED AT LINE ") + std::to_string(__LINE__) + " OF FILE " + \
+                         __FILE__ + " error " + cudaGetErrorString(_e) + " (" #x ")");                      \
   } while (0)
 
 // bump allocator over a few large cudaMalloc chunks (replaces the size-keyed free lists of memory.cu:74-163)
@@ -30,6 +39,7 @@ class Arena {
   size_t used() const { return used_; }
   size_t capacity() const;
   size_t min_chunk = (size_t)256 << 20;
+  size_t max_bytes = (size_t)150 << 30;   // growth cap: beyond it alloc() throws instead of driving the GPU out of memory
  private:
   struct Chunk { char* base; size_t size; size_t off; };
   std::vector<Chunk> chunks_;
@@ -51,11 +61,12 @@ struct PanelSlot {
 };
 
 struct EngineStats {
-  double fused_ms = 0, repack_ms = 0;   // CUDA-event time of the kernels (when timing enabled)
-  long long fused_launches = 0, repack_launches = 0, reduce_launches = 0, antisym_launches = 0;
+  double fused_ms = 0, repack_ms = 0, pull_ms = 0;   // CUDA-event time of the kernels (when timing enabled)
+  long long fused_launches = 0, repack_launches = 0, reduce_launches = 0, antisym_launches = 0, pull_launches = 0;
   long long work_items = 0, descs = 0, tuples = 0;
   double flops = 0;                     // algorithmic FLOPs: 2*prod(R)*K per fired contraction, 2*prod(R) per singles
   size_t h2d_bytes = 0, d2h_bytes = 0;
+  size_t peer_bytes = 0;                // bytes pulled from other GPUs' shards over NVLink
 };
 
 class Engine {
@@ -64,7 +75,9 @@ class Engine {
   ~Engine();
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
-  Arena& arena() { return arena_; }
+  Arena& arena() { return slots_[cur_].arena; }   // arena of the batch being built
+  int current_slot() const { return cur_; }
+  void set_arena_cap(size_t bytes) { for (auto& s : slots_) s.arena.max_bytes = bytes; }
 
   // ---- tuple building (all pointers are device pointers) ----
   void begin_tuple(const int R_phys[6]);
@@ -75,16 +88,31 @@ class Engine {
                        double tscale = 1.0, std::vector<PanelSlot>* t_cache = nullptr,
                        std::vector<PanelSlot>* v_cache = nullptr);
   void add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub);
-  // eps: six DEVICE vectors in reference argument order (h1,h2,h3,p4,p5,p6)
-  void end_tuple(const double* const d_eps_h1h2h3p4p5p6[6], double factor);
+  // eps: six DEVICE vectors in reference argument order (h1,h2,h3,p4,p5,p6).  [item_lo, item_hi) restricts the launch
+  // to a sub-range of the tuple's 4^6 sub-tiles (linear index, h3 block fastest, p4 block slowest; item_hi < 0 = all):
+  // energies are additive over sub-tiles, so a tuple can be shared between GPUs or evaluated slab by slab.
+  void end_tuple(const double* const d_eps_h1h2h3p4p5p6[6], double factor, long long item_lo = 0, long long item_hi = -1);
+  static long long tuple_items(const int R_phys[6]);
   int pending_tuples() const { return (int)tuples_.size(); }
   size_t pending_items() const { return (size_t)items_; }
 
-  // ---- execution: runs every pending tuple in one batch; energies[2*i..] = (E1,E2) of tuple i ----
+  // ---- execution ----
+  // queue every pending tuple of the current slot (pull -> antisym -> repack -> fused -> reduce -> D2H) and switch to
+  // the other slot, which must have been collected.  Returns the slot to collect, or -1 if nothing was pending.
+  int submit(double* dump_doubles = nullptr, double* dump_singles = nullptr);
+  // wait for a submitted slot; energies_out[2*i..] = (E1,E2) of its tuple i.  Rewinds the slot's arena.
+  void collect(int slot, double* energies_out);
+  int slot_tuples(int slot) const { return slots_[slot].ntuples; }
+  bool slot_busy(int slot) const { return slots_[slot].busy; }
+  // synchronous convenience: submit + collect
   void run(double* energies_out, double* dump_doubles = nullptr, double* dump_singles = nullptr);
-  void flush_repack();      // launch pending antisym + repack jobs now (asynchronous)
+  // error recovery: drop everything pending / in flight and rewind both arenas
+  void abort();
+  void flush_prep();      // launch pending pull + antisym + repack jobs now (asynchronous)
   // `2eorb`: queue the construction of one dense spin-orbital V2 block (job.dst must come from arena())
   void add_antisym(const AntisymJob& job);
+  // sharded stores: queue the pull of one remote block into the arena
+  void add_copy(const CopyJob& job);
 
   EngineStats stats;
   bool timing = false;
@@ -92,26 +120,37 @@ class Engine {
   double timer_stop_ms();
 
  private:
+  struct Slot {
+    Arena arena;
+    void* d_meta = nullptr; size_t d_meta_cap = 0;
+    double2* h_out = nullptr; size_t h_out_cap = 0;   // pinned
+    char* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging of job lists + metadata
+    cudaEvent_t done = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pull, repack, fused: begin/end
+    bool timed[3] = {false, false, false};
+    int ntuples = 0;
+    bool busy = false;
+  };
   int device_;
   cudaStream_t stream_;
-  Arena arena_;
+  Slot slots_[2];
+  int cur_ = 0;
   bool open_ = false;
-  TupleHdr cur_{};
+  TupleHdr cur_hdr_{};
   std::vector<ContrDesc> cur_descs_[9];
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;
   std::vector<RepackJob> jobs_;
   std::vector<AntisymJob> ajobs_;
-  long long max_ablock_ = 0;
-  void* d_ajobs_ = nullptr; size_t d_ajobs_cap_ = 0;
-  long long max_panel_ = 0;
+  std::vector<CopyJob> cjobs_;
+  long long max_ablock_ = 0, max_panel_ = 0, max_copy_ = 0;
   long long items_ = 0;
-  cudaEvent_t ev0_, ev1_, evt0_, evt1_;
-  // small reusable device buffers for descriptor uploads
-  void* d_meta_ = nullptr; size_t d_meta_cap_ = 0;
-  void* d_jobs_ = nullptr; size_t d_jobs_cap_ = 0;
-  void* h_pin_ = nullptr; size_t h_pin_cap_ = 0;
+  int max_chunks_ = 1;
+  cudaEvent_t evt0_, evt1_;
+  // host bytes -> pinned staging of the current slot -> `dst` (device), truly asynchronous
+  void upload(void* dst, const void* host, size_t bytes);
+  void* upload_jobs(const void* host, size_t bytes);
 };
 
 }  // namespace nwc

@@ -11,6 +11,7 @@
 #include <string>
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include "../../include/nwc_triples.h"
 
 namespace nwc {
@@ -41,6 +42,9 @@ struct HostState {
   std::unordered_map<Integer, Integer> host_off;  // scratch: key -> offset in the caller's full store
   struct OrbRun { Integer src, dst, n; };         // contiguous run of needed blocks: host offset -> resident offset
   std::vector<OrbRun> orb_runs;
+  struct OrbBlock { Integer key, host_off, size; };   // the needed blocks in storage order (the unit of sharding)
+  std::vector<OrbBlock> orb_blocks;
+  std::unordered_map<Integer, Integer> orb_index; // orbital block key -> index into orb_blocks
   Integer orb_size = 0;                           // doubles resident on the device
   Integer orb_host_size = 0;                      // doubles in the caller's d_v2orb
   static Integer index_pair(Integer i, Integer j) { return (i * (i - 1)) / 2 + j; }   // tce_mo2e_offset_intorb.F:615
@@ -54,7 +58,10 @@ struct HostState {
     b2am.assign(b2am_, b2am_ + noab + nvab);
     spin_alpha.assign(spin_a, spin_a + n); sym_alpha.assign(sym_a, sym_a + n); range_alpha.assign(range_a, range_a + n);
     orb_off.clear();
+    host_off.clear();
     orb_runs.clear();
+    orb_blocks.clear();
+    orb_index.clear();
     // (T) reads <pp||hh>, <hp||hh> and <pp||hp> only, i.e. the Mulliken blocks (vo|vo), (oo|vo) and (vo|vv): a stored
     // block can be touched iff at least one of its two tile pairs is mixed (one hole tile, one particle tile).
     // Everything else -- (oo|oo), (oo|vv), (vv|vv), the bulk of the store -- stays on the host.
@@ -74,6 +81,8 @@ struct HostState {
             host_off[key] = size;
             if (needed) {
               orb_off[key] = resident;
+              orb_index[key] = (Integer)orb_blocks.size();
+              orb_blocks.push_back({key, size, bs});
               if (!orb_runs.empty() && orb_runs.back().src + orb_runs.back().n == size) orb_runs.back().n += bs;
               else orb_runs.push_back({size, resident, bs});
               resident += bs;
@@ -147,7 +156,7 @@ inline Integer hash_lookup(const Integer* hash, Integer key) {
 }
 inline Integer hash_lookup_or_die(const std::vector<Integer>& hash, Integer key, const char* what) {
   Integer off = hash_lookup(hash.data(), key);
-  if (off < 0) { printf("nwc_triples: %s: block key %ld not found\n", what, key); fflush(stdout); exit(1); }
+  if (off < 0) throw std::runtime_error(std::string("nwc_triples: ") + what + ": block key " + std::to_string(key) + " not found");
   return off;
 }
 

@@ -133,6 +133,76 @@ void launch_antisym(const AntisymJob* d_jobs, int njobs, long long max_block_dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// pull: whole stored blocks of a peer GPU's shard -> local arena, contiguous 16-byte loads over NVLink (the coalesced
+// form of the reference's ga_get per tile, get_block.F:79-81); repack / antisym then read the local copy
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pull_kernel(const CopyJob* __restrict__ jobs) {
+  const CopyJob j = jobs[blockIdx.y];
+  const long long n2 = j.n >> 1;   // blocks are 256-byte aligned on both sides (arena / compacted shards of whole blocks)
+  const double2* __restrict__ s2 = reinterpret_cast<const double2*>(j.src);
+  double2* __restrict__ d2 = reinterpret_cast<double2*>(j.dst);
+  const bool vec = ((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.dst)) & 15) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent 16-byte loads in flight per thread: NVLink latency is ~2x local HBM latency
+    for (; e + 3 * stride < n2; e += 4 * stride) {
+      const double2 a = __ldg(s2 + e), b = __ldg(s2 + e + stride), c = __ldg(s2 + e + 2 * stride), d = __ldg(s2 + e + 3 * stride);
+      d2[e] = a; d2[e + stride] = b; d2[e + 2 * stride] = c; d2[e + 3 * stride] = d;
+    }
+    for (; e < n2; e += stride) d2[e] = __ldg(s2 + e);
+    if ((j.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) j.dst[j.n - 1] = __ldg(j.src + j.n - 1);
+  } else {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < j.n; e += stride) j.dst[e] = __ldg(j.src + e);
+  }
+}
+
+void launch_pull(const CopyJob* d_jobs, int njobs, long long max_doubles, cudaStream_t stream) {
+  if (njobs <= 0) return;
+  long long bx = (max_doubles / 2 + 256 * 4 - 1) / (256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 1024) bx = 1024;
+  for (int j0 = 0; j0 < njobs; j0 += 32768) {
+    int n = njobs - j0 < 32768 ? njobs - j0 : 32768;
+    pull_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, stream>>>(d_jobs + j0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic stores generated in place (bench / tests): element e of the block with key `key` of store `store` is
+// scale * (2u - 1), u = the top 53 bits of a splitmix64-style hash of (seed, store, key, e) -- a pure function of
+// the block key, so every rank of a sharded run fills its own blocks and all rank counts see the same tensors.
+// nwchem_b200/synth.py restates the same function in numpy for the oracle.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long synth_mix(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) synth_fill_kernel(const FillJob* __restrict__ jobs, unsigned long long seed,
+                                                        unsigned long long store, double scale) {
+  const FillJob j = jobs[blockIdx.y];
+  const unsigned long long hk = synth_mix((seed * 0x9E3779B97F4A7C15ULL + store * 0xD1B54A32D192ED03ULL) ^ (unsigned long long)j.key);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < j.n; e += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long h = synth_mix(hk + (unsigned long long)e * 0x9E3779B97F4A7C15ULL);
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+    j.dst[e] = scale * (2.0 * u - 1.0);
+  }
+}
+
+void launch_synth_fill(const FillJob* d_jobs, int njobs, long long max_doubles, unsigned long long seed,
+                       unsigned long long store, double scale, cudaStream_t stream) {
+  if (njobs <= 0) return;
+  long long bx = (max_doubles + 256 * 8 - 1) / (256 * 8);
+  if (bx < 1) bx = 1;
+  if (bx > 1024) bx = 1024;
+  for (int j0 = 0; j0 < njobs; j0 += 32768) {
+    int n = njobs - j0 < 32768 ? njobs - j0 : 32768;
+    synth_fill_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, stream>>>(d_jobs + j0, seed, store, scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // repack: strided source -> blocked K4 panel (zero padded)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict__ jobs) {
@@ -353,6 +423,7 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
 #pragma unroll
         for (int j = 0; j < CB; j++) dep ^= (unsigned int)__double2hiint(b[j].x) ^ (unsigned int)__double2hiint(b[j].y);
         dep &= zero;
+        __syncwarp();   // every lane's fragment loads are ordered before lane 0's arrive (not only lane 0's own)
         if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(&empty[st]) + dep));
       };
       // an odd plane count leaves the second plane of the last stage all zero (k padding): its DMMAs are skipped
@@ -453,7 +524,8 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       const unsigned int nbj = (unsigned int)__shfl_sync(0xffffffffu, my_nb, jq);
       if (jq < q6) below *= nbj;
     }
-    my_b = (int)(((unsigned int)(item - T.item_begin) / below) % (unsigned int)my_nb);
+    // item_first: this launch may own only a sub-range of the tuple's sub-tiles (multi-GPU split inside a tuple)
+    my_b = (int)(((unsigned int)(item - T.item_begin + T.item_first) / below) % (unsigned int)my_nb);
   }
 #define NWC_B(q) __shfl_sync(0xffffffffu, my_b, (q))
 #define NWC_NB(q) __shfl_sync(0xffffffffu, my_nb, (q))
@@ -841,32 +913,71 @@ void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d
 }
 
 // ------------------------------------------------------------------------------------------------
-// deterministic per-tuple reduction of the per-sub-tile partials
+// deterministic per-tuple reduction of the per-sub-tile partials, two levels: CTA (c, t) sums the fixed chunk
+// [c*REDUCE_CHUNK, (c+1)*REDUCE_CHUNK) of tuple t's partials in a fixed order, then one CTA per tuple sums the chunk
+// sums in a fixed order.  The chunking depends only on the tuple, never on the grid, so results are bitwise
+// reproducible; a 40^6 tuple (4.2e6 partials) is summed by ~1000 CTAs instead of one.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_kernel(const TupleHdr* __restrict__ tuples,
-                                                    const double2* __restrict__ partials,
-                                                    double2* __restrict__ energies) {
-  __shared__ double s1[256], s2[256];
-  const TupleHdr& T = tuples[blockIdx.x];
-  double a = 0.0, b = 0.0;
-  const long long n = (long long)T.nitems * (NCONSUMERS / 32), base = T.item_begin * (NCONSUMERS / 32);
-  for (long long i = threadIdx.x; i < n; i += 256) {   // four per-warp partials per sub-tile, fixed order
-    const double2 v = partials[base + i];
-    a += v.x; b += v.y;
-  }
+constexpr int REDUCE_CHUNK = 4096;
+int reduce_chunks(long long nitems) {
+  const long long n = nitems * (NCONSUMERS / 32);
+  return (int)((n + REDUCE_CHUNK - 1) / REDUCE_CHUNK);
+}
+
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* s1, double* s2) {
   s1[threadIdx.x] = a; s2[threadIdx.x] = b;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) energies[blockIdx.x] = make_double2(s1[0], s2[0]);
+  a = s1[0]; b = s2[0];
 }
 
-void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_energies,
-                   cudaStream_t stream) {
+__global__ void __launch_bounds__(256) reduce_chunk_kernel(const TupleHdr* __restrict__ tuples,
+                                                          const double2* __restrict__ partials,
+                                                          double2* __restrict__ chunk_sums, int max_chunks) {
+  __shared__ double s1[256], s2[256];
+  const TupleHdr& T = tuples[blockIdx.y];
+  const long long n = (long long)T.nitems * (NCONSUMERS / 32), base = T.item_begin * (NCONSUMERS / 32);
+  const long long lo = (long long)blockIdx.x * REDUCE_CHUNK;
+  if (lo >= n) return;
+  const long long hi = (lo + REDUCE_CHUNK < n) ? lo + REDUCE_CHUNK : n;
+  double a = 0.0, b = 0.0;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+    const double2 v = partials[base + i];
+    a += v.x; b += v.y;
+  }
+  block_sum2(a, b, s1, s2);
+  if (threadIdx.x == 0) chunk_sums[(long long)blockIdx.y * max_chunks + blockIdx.x] = make_double2(a, b);
+}
+
+__global__ void __launch_bounds__(256) reduce_final_kernel(const TupleHdr* __restrict__ tuples,
+                                                          const double2* __restrict__ chunk_sums,
+                                                          double2* __restrict__ energies, int max_chunks) {
+  __shared__ double s1[256], s2[256];
+  const TupleHdr& T = tuples[blockIdx.x];
+  const long long n = (long long)T.nitems * (NCONSUMERS / 32);
+  const int nch = (int)((n + REDUCE_CHUNK - 1) / REDUCE_CHUNK);
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nch; i += 256) {
+    const double2 v = chunk_sums[(long long)blockIdx.x * max_chunks + i];
+    a += v.x; b += v.y;
+  }
+  block_sum2(a, b, s1, s2);
+  if (threadIdx.x == 0) energies[blockIdx.x] = make_double2(a, b);
+}
+
+void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_chunk_sums,
+                   int max_chunks, double2* d_energies, cudaStream_t stream) {
   if (ntuples <= 0) return;
-  reduce_kernel<<<ntuples, 256, 0, stream>>>(d_tuples, d_partials, d_energies);
+  if (max_chunks < 1) max_chunks = 1;
+  for (int t0 = 0; t0 < ntuples; t0 += 32768) {   // gridDim.y limit
+    const int n = ntuples - t0 < 32768 ? ntuples - t0 : 32768;
+    reduce_chunk_kernel<<<dim3((unsigned)max_chunks, (unsigned)n), 256, 0, stream>>>(
+        d_tuples + t0, d_partials, d_chunk_sums + (long long)t0 * max_chunks, max_chunks);
+  }
+  reduce_final_kernel<<<ntuples, 256, 0, stream>>>(d_tuples, d_chunk_sums, d_energies, max_chunks);
 }
 
 }  // namespace nwc

@@ -43,8 +43,8 @@ struct TupleHdr {
   int desc_begin[10];   // split s owns descs [desc_begin[s], desc_begin[s+1])
   int sdesc_begin, sdesc_end;
   long long item_begin; // first work item (sub-tile) of this tuple in the launch
-  int nitems;
-  int pad;
+  int nitems;            // work items of this launch (a sub-range when the tuple is split across GPUs)
+  int item_first;        // index of the first of them inside the tuple's full sub-tile space
 };
 
 struct RepackJob {      // build one panel from a strided source
@@ -64,6 +64,18 @@ struct AntisymJob {     // dense block dst[x0][x1][x2][x3] (x3 fastest) = ca*a[s
   double ca, cb;
 };
 
+struct CopyJob {        // contiguous block copy (peer shard -> local arena)
+  const double* src;
+  double* dst;
+  long long n;
+};
+
+struct FillJob {        // synthetic generator: one stored block
+  double* dst;
+  long long key;        // TCE block key
+  long long n;
+};
+
 inline long long panel_doubles(int X1, int X2, int X3, int K) {
   auto c4 = [](int v) { return (long long)((v + 3) / 4); };
   return (long long)((K + 4 * KPL - 1) / (4 * KPL)) * c4(X1) * c4(X2) * c4(X3) * BLK_DOUBLES;
@@ -71,12 +83,18 @@ inline long long panel_doubles(int X1, int X2, int X3, int K) {
 
 // launchers (kernels.cu).  All asynchronous on `stream`.
 void launch_antisym(const AntisymJob* d_jobs, int njobs, long long max_block_doubles, cudaStream_t stream);
+void launch_pull(const CopyJob* d_jobs, int njobs, long long max_doubles, cudaStream_t stream);
+void launch_synth_fill(const FillJob* d_jobs, int njobs, long long max_doubles, unsigned long long seed,
+                       unsigned long long store, double scale, cudaStream_t stream);
 void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
 // ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                   double2* d_partials, long long total_items, bool ragged, cudaStream_t stream);
-void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_energies,
-                   cudaStream_t stream);
+// two-level deterministic reduction; d_chunk_sums holds ntuples * max_chunks double2 (max_chunks >= the largest
+// reduce_chunks(nitems) of the launch)
+int reduce_chunks(long long nitems);
+void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_partials, double2* d_chunk_sums,
+                   int max_chunks, double2* d_energies, cudaStream_t stream);
 // unfused debugging/validation path: materialise the two t3 tiles of ONE tuple in HBM
 void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                        double2* d_partials, long long total_items, double* d_doubles, double* d_singles,

@@ -56,24 +56,65 @@ struct nwc_triples_ctx {
   Engine* eng = nullptr;
   HostState S;
   double *d_t1 = nullptr, *d_t2 = nullptr, *d_v2 = nullptr, *d_evl = nullptr, *d_red = nullptr;
-  size_t n_t1 = 0, n_t2 = 0, n_v2 = 0;
+  size_t n_t1 = 0, n_t2 = 0, n_v2 = 0, n_red = 0;
   std::vector<Integer> klist;
   size_t batch_bytes = (size_t)8 << 30;
   ncclComm_t comm = nullptr;
   int nranks = 1;
-  // sharded V2: block i of the V2 offset table lives on rank i % v2_nshards, compacted in table order;
-  // remote shards are mapped with CUDA IPC and read over NVLink by the repack kernel / singles staging.
+  // Sharded V2: block i of the store -- entry i of the spin-orbital offset table, or the i-th orbital block
+  // (T) can touch in `2eorb` form -- lives on rank i % v2_nshards, compacted in that order.  Remote shards are mapped
+  // with CUDA IPC; the blocks a batch needs are pulled whole over NVLink into its arena (pull_kernel), which replaces
+  // the ga_get per tile of get_block.F:79-81.
   int v2_nshards = 1, v2_rank = 0;
-  std::vector<Integer> v2_shard_off;        // per table index: offset inside its owner's shard
+  std::vector<Integer> v2_shard_off;        // per block index: offset inside its owner's shard
+  std::vector<Integer> v2_block_n;          // per block index: doubles
   std::vector<double*> v2_peer;             // per rank: base of that rank's shard as seen from this process
   std::vector<char> v2_peer_opened;
+  bool peer_direct = false;                 // NWC_PEER_DIRECT=1: read remote blocks in place (strided 8-byte loads), for A/B runs
   // `2eorb` storage: orbital-form integrals resident, spin-orbital blocks built per batch in the arena
   double* d_v2orb = nullptr;
   size_t n_v2orb = 0;
-  std::unordered_map<Integer, const double*> v2_built;   // spin-orbital key -> block built since the last arena reset
+  // per batch slot (engine.h): blocks that live in that slot's arena
+  std::unordered_map<Integer, const double*> v2_built[2];   // spin-orbital key -> antisymmetrised block
+  std::unordered_map<Integer, const double*> pulled[2];     // block index -> local copy of a remote block
 };
 
 namespace {
+
+void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_state* variant
+  cudaSetDevice(c->eng->device());
+  c->eng->abort();
+  for (size_t r = 0; r < c->v2_peer.size(); r++)
+    if (c->v2_peer_opened[r] && c->v2_peer[r]) cudaIpcCloseMemHandle(c->v2_peer[r]);
+  c->v2_peer.clear(); c->v2_peer_opened.clear(); c->v2_shard_off.clear(); c->v2_block_n.clear();
+  c->v2_nshards = 1; c->v2_rank = 0;
+  cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl);
+  c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = nullptr;
+  c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = 0;
+  for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
+  c->S.intorb = false; c->S.orb_off.clear(); c->S.host_off.clear(); c->S.orb_runs.clear(); c->S.orb_blocks.clear();
+  c->S.orb_index.clear(); c->S.orb_size = c->S.orb_host_size = 0;
+  c->klist.clear();
+  const char* pd = getenv("NWC_PEER_DIRECT");
+  c->peer_direct = pd && *pd == '1';
+}
+
+void recover(nwc_triples_ctx* c) {
+  if (!c || !c->eng) return;
+  c->eng->abort();
+  for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
+}
+
+template <class F>
+int guarded(nwc_triples_ctx* c, F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    recover(c);
+    return 1;
+  }
+}
 
 // position of `key` in a TCE offset table (1-based), -1 if absent
 Integer hash_index(const Integer* hash, Integer key) {
@@ -86,38 +127,59 @@ Integer hash_index(const Integer* hash, Integer key) {
   return -1;
 }
 
-const double* v2_block(const nwc_triples_ctx* c, Integer key, const char* what) {
+// block `idx` of the sharded store: local pointer if this rank owns it, else its pulled copy in the current batch arena
+const double* sharded_block(nwc_triples_ctx* c, Integer idx, double* local_base) {
+  const int owner = (int)(idx % c->v2_nshards);
+  const Integer off = c->v2_shard_off[(size_t)idx];
+  if (owner == c->v2_rank) return local_base + off;
+  const double* base = c->v2_peer[(size_t)owner];
+  if (!base) throw Error("nwc_triples: V2 shard of rank " + std::to_string(owner) + " is not mapped (nwc_triples_v2_open_peers)");
+  if (c->peer_direct) return base + off;
+  auto& cache = c->pulled[c->eng->current_slot()];
+  auto hit = cache.find(idx);
+  if (hit != cache.end()) return hit->second;
+  const Integer n = c->v2_block_n[(size_t)idx];
+  double* dst = (double*)c->eng->arena().alloc((size_t)n * sizeof(double));
+  c->eng->add_copy(CopyJob{base + off, dst, (long long)n});
+  cache[idx] = dst;
+  return dst;
+}
+
+const double* v2_block(nwc_triples_ctx* c, Integer key, const char* what) {
   const HostState& S = c->S;
   if (c->v2_nshards <= 1) return c->d_v2 + hash_lookup_or_die(S.v2_hash, key, what);
   const Integer idx = hash_index(S.v2_hash.data(), key);
-  if (idx < 0) { printf("nwc_triples: %s: block key %ld not found\n", what, key); fflush(stdout); exit(1); }
-  const int owner = (int)((idx - 1) % c->v2_nshards);
-  const double* base = c->v2_peer[owner];
-  if (!base) { printf("nwc_triples: V2 shard of rank %d is not mapped (nwc_triples_v2_open_peers)\n", owner); fflush(stdout); exit(1); }
-  return base + c->v2_shard_off[idx - 1];
+  if (idx < 0) throw Error(std::string("nwc_triples: ") + what + ": block key " + std::to_string(key) + " not found");
+  return sharded_block(c, idx - 1, c->d_v2);
 }
 
 // `2eorb`: <g3 g4||g1 g2> as one antisym job built from HostState::block_plan (get_block_ind.F:818-1538)
-const double* orb_block_ptr(const nwc_triples_ctx* c, Integer key) {
-  auto it = c->S.orb_off.find(key);
-  if (it == c->S.orb_off.end()) { printf("nwc_triples: orbital V2 block key %ld is not resident\n", key); fflush(stdout); exit(1); }
-  return c->d_v2orb + it->second;
+const double* orb_block_ptr(nwc_triples_ctx* c, Integer key) {
+  if (c->v2_nshards <= 1) {
+    auto it = c->S.orb_off.find(key);
+    if (it == c->S.orb_off.end()) throw Error("nwc_triples: orbital V2 block key " + std::to_string(key) + " is not resident");
+    return c->d_v2orb + it->second;
+  }
+  auto it = c->S.orb_index.find(key);
+  if (it == c->S.orb_index.end()) throw Error("nwc_triples: orbital V2 block key " + std::to_string(key) + " is not resident");
+  return sharded_block(c, it->second, c->d_v2orb);
 }
 
 const double* v2_block_2eorb(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g1b, Integer g2b) {
   const HostState& S = c->S;
   const Integer skey = v2_key(S, g3b, g4b, g1b, g2b);
-  auto hit = c->v2_built.find(skey);
-  if (hit != c->v2_built.end()) return hit->second;
+  auto& built = c->v2_built[c->eng->current_slot()];
+  auto hit = built.find(skey);
+  if (hit != built.end()) return hit->second;
   AntisymJob j{};
   j.n[0] = (int)S.rg(g3b); j.n[1] = (int)S.rg(g4b); j.n[2] = (int)S.rg(g1b); j.n[3] = (int)S.rg(g2b);
   const size_t bytes = sizeof(double) * (size_t)j.n[0] * j.n[1] * j.n[2] * j.n[3];
-  j.dst = (double*)c->eng->arena().alloc(bytes);
   const HostState::OrbPlan p = S.block_plan(g3b, g4b, g1b, g2b);
   if (p.key_a >= 0) { j.a = orb_block_ptr(c, p.key_a); j.ca = 1.0; for (int q = 0; q < 4; q++) j.sa[q] = p.sa[q]; }
   if (p.key_b >= 0) { j.b = orb_block_ptr(c, p.key_b); j.cb = -1.0; for (int q = 0; q < 4; q++) j.sb[q] = p.sb[q]; }
+  j.dst = (double*)c->eng->arena().alloc(bytes);
   c->eng->add_antisym(j);
-  c->v2_built[skey] = j.dst;
+  built[skey] = j.dst;
   return j.dst;
 }
 
@@ -127,10 +189,11 @@ const double* v2_operand(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g
   return v2_block(c, v2_key(c->S, g3b, g4b, g1b, g2b), what);
 }
 
-// the arena is about to be rewound: blocks built in it are gone
-void reset_arena(nwc_triples_ctx* c) {
-  c->eng->arena().reset();
-  c->v2_built.clear();
+// a batch slot has been collected: blocks built / pulled in its arena are gone
+void slot_done(nwc_triples_ctx* c, int slot) {
+  if (slot < 0) return;
+  c->v2_built[slot].clear();
+  c->pulled[slot].clear();
 }
 
 struct NativeSink {
@@ -197,26 +260,88 @@ struct NativeSink {
   }
 };
 
-void emit_tuple(nwc_triples_ctx* c, const Integer t[6]) {
-  const HostState& S = c->S;
-  int R[6];
+void tuple_ranges(const HostState& S, const Integer t[6], int R[6]) {
   R[POS_P4] = (int)S.rg(t[0]); R[POS_P5] = (int)S.rg(t[1]); R[POS_P6] = (int)S.rg(t[2]);
   R[POS_H1] = (int)S.rg(t[3]); R[POS_H2] = (int)S.rg(t[4]); R[POS_H3] = (int)S.rg(t[5]);
+}
+
+// [item_lo, item_hi): sub-range of the tuple's sub-tiles this launch evaluates (item_hi < 0: all)
+void emit_tuple(nwc_triples_ctx* c, const Integer t[6], long long item_lo = 0, long long item_hi = -1) {
+  const HostState& S = c->S;
+  int R[6];
+  tuple_ranges(S, t, R);
   c->eng->begin_tuple(R);
   NativeSink sink{c, *c->eng, S};
   walk_singles(S, t, sink);
   walk_doubles(S, t, sink);
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
-  c->eng->end_tuple(eps, tuple_factor(S, t));
+  c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
 }
+
+// Double-buffered batch loop: while the GPU runs batch k the host walks the driver logic of batch k+1 into the other
+// slot.  Energies are accumulated in task order (deterministic).  slot_of[i] (optional) = where result i goes in per_task.
+struct Pipeline {
+  nwc_triples_ctx* c;
+  Engine& e;
+  double* energy;
+  double* per_task;
+  std::vector<Integer> cur_pos, prev_pos;   // per_task row of each tuple of the batch being built / in flight
+  int prev = -1;
+  std::vector<double> eb;
+  Pipeline(nwc_triples_ctx* c_, double* en, double* pt) : c(c_), e(*c_->eng), energy(en), per_task(pt) {}
+  void emitted(Integer row) {
+    cur_pos.push_back(row);
+    if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)32000000 || e.pending_tuples() >= 4096) flush();
+  }
+  void wait_prev() {
+    if (prev < 0) return;
+    eb.assign(2 * prev_pos.size() + 2, 0.0);
+    e.collect(prev, eb.data());
+    for (size_t i = 0; i < prev_pos.size(); i++) {
+      energy[0] += eb[2 * i];
+      energy[1] += eb[2 * i + 1];
+      if (per_task && prev_pos[i] >= 0) { per_task[2 * prev_pos[i]] += eb[2 * i]; per_task[2 * prev_pos[i] + 1] += eb[2 * i + 1]; }
+    }
+    slot_done(c, prev);
+    prev = -1;
+  }
+  void flush() {
+    const int s = e.submit();
+    if (s < 0) return;
+    wait_prev();          // frees the slot the engine has just switched to; the GPU already has batch s queued
+    prev = s;
+    prev_pos.swap(cur_pos);
+    cur_pos.clear();
+  }
+  void finish() { flush(); wait_prev(); }
+};
+
+// dry walk: planes (k4 steps) of all fired contractions of one tuple -- the cost model of the static partition
+struct CostSink {
+  const HostState& S;
+  long long planes = 0;
+  void singles(const Row&, Integer, Integer, Integer, Integer, Integer, Integer, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += 1;
+  }
+  void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(h7b) + 3) / 4;
+  }
+  void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(p7b) + 3) / 4;
+  }
+};
 
 int upload(double** dst, size_t* n_out, const double* src, size_t n, Engine* e) {
   if (*dst) { cudaFree(*dst); *dst = nullptr; }
   NWC_TRY(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(double)));
-  if (n) NWC_TRY(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+  if (n && src) {
+    NWC_TRY(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+    e->stats.h2d_bytes += n * sizeof(double);
+  } else if (n) {   // no host data: the store is allocated only (filled on the device, nwc_triples_synth_fill)
+    NWC_TRY(cudaMemset(*dst, 0, n * sizeof(double)));
+  }
   *n_out = n;
-  e->stats.h2d_bytes += n * sizeof(double);
   return 0;
 }
 
@@ -226,6 +351,8 @@ size_t store_size(const Integer* hash, const HostState& S, int which) {
   if (n == 0) return 0;
   Integer key = hash[n], off = hash[2 * n];
   Integer sz = 0;
+  const Integer top = which == 1 ? S.noab * S.nvab : which == 2 ? S.noab * S.noab * S.nvab * S.nvab : S.N() * S.N() * S.N() * S.N();
+  if (key < 0 || key >= top || off < 0) throw Error("nwc_triples: offset table does not belong to this tiling (last key out of range)");
   if (which == 1) { Integer h = key % S.noab + 1, p = key / S.noab + S.noab + 1; sz = S.rg(h) * S.rg(p); }
   else if (which == 2) {
     Integer h4 = key % S.noab + 1; key /= S.noab; Integer h3 = key % S.noab + 1; key /= S.noab;
@@ -250,40 +377,70 @@ int nwc_triples_create(nwc_triples_ctx** out, int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { g_err = "no CUDA device (there is no CPU fallback)"; return 1; }
   if (device < 0 || device >= count) { g_err = "device index out of range"; return 1; }
-  nwc_triples_ctx* c = new nwc_triples_ctx();
-  c->eng = new Engine(device);
-  *out = c;
-  return 0;
+  return guarded(nullptr, [&]() {
+    nwc_triples_ctx* c = new nwc_triples_ctx();
+    c->eng = new Engine(device);
+    *out = c;
+    return 0;
+  });
 }
 
 int nwc_triples_destroy(nwc_triples_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->eng->device());
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (size_t r = 0; r < c->v2_peer.size(); r++)
-    if (c->v2_peer_opened[r] && c->v2_peer[r]) cudaIpcCloseMemHandle(c->v2_peer[r]);
-  cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl); cudaFree(c->d_red);
+  free_stores(c);
+  cudaFree(c->d_red);
   delete c->eng;
   delete c;
   return 0;
 }
 
-int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
-  NWC_TRY(cudaSetDevice(c->eng->device()));
-  c->S.load_tables(st);
-  const HostState& S = c->S;
-  if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
-  if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
-  if (upload(&c->d_v2, &c->n_v2, st->v2, store_size(st->v2_hash, S, 3), c->eng)) return 1;
+static int finish_state(nwc_triples_ctx* c) {
   size_t ne;
-  if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
-  c->v2_nshards = 1; c->v2_rank = 0;
-  build_task_list(S, c->klist);
+  if (upload(&c->d_evl, &ne, c->S.evl.data(), c->S.evl.size(), c->eng)) return 1;
+  build_task_list(c->S, c->klist);
   return 0;
 }
 
-int nwc_triples_set_state_2eorb(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb) {
+}  // extern "C"
+// shard layout of `n` blocks of sizes size(i): block i -> rank i % nranks, compacted in index order
+template <class SizeOf>
+static void build_shards(nwc_triples_ctx* c, Integer n, int rank, int nranks, SizeOf size_of, Integer* my_doubles) {
+  c->v2_shard_off.assign((size_t)n, 0);
+  c->v2_block_n.assign((size_t)n, 0);
+  std::vector<Integer> fill((size_t)nranks, 0);
+  for (Integer i = 0; i < n; i++) {
+    const int owner = (int)(i % nranks);
+    const Integer sz = size_of(i);
+    c->v2_shard_off[(size_t)i] = fill[owner];
+    c->v2_block_n[(size_t)i] = sz;
+    fill[owner] += sz;
+  }
+  *my_doubles = fill[rank];
+  c->v2_nshards = nranks; c->v2_rank = rank;
+  c->v2_peer.assign((size_t)nranks, nullptr);
+  c->v2_peer_opened.assign((size_t)nranks, 0);
+}
+
+extern "C" {
+int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    free_stores(c);
+    c->S.load_tables(st);
+    const HostState& S = c->S;
+    if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
+    if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
+    if (upload(&c->d_v2, &c->n_v2, st->v2, store_size(st->v2_hash, S, 3), c->eng)) return 1;
+    return finish_state(c);
+  });
+}
+
+static int set_state_orbital(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb, int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
   NWC_TRY(cudaSetDevice(c->eng->device()));
+  free_stores(c);
   nwc_tce_state s2 = *st;
   s2.v2_hash = nullptr;   // not read in this mode
   c->S.load_tables(&s2);
@@ -293,58 +450,73 @@ int nwc_triples_set_state_2eorb(nwc_triples_ctx* c, const nwc_tce_state* st, con
   if (!err.empty()) { g_err = err; return 1; }
   if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
   if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
-  // only the blocks (T) can touch become resident, compacted run by run (the rest of d_v2orb stays on the host)
-  if (c->d_v2orb) { cudaFree(c->d_v2orb); c->d_v2orb = nullptr; }
-  NWC_TRY(cudaMalloc((void**)&c->d_v2orb, (size_t)(S.orb_size ? S.orb_size : 1) * sizeof(double)));
-  for (const HostState::OrbRun& r : S.orb_runs)
-    NWC_TRY(cudaMemcpy(c->d_v2orb + r.dst, orb->v2orb + r.src, (size_t)r.n * sizeof(double), cudaMemcpyHostToDevice));
-  c->n_v2orb = (size_t)S.orb_size;
-  c->eng->stats.h2d_bytes += (size_t)S.orb_size * sizeof(double);
-  if (c->d_v2) { cudaFree(c->d_v2); c->d_v2 = nullptr; }
-  c->n_v2 = 0;
-  size_t ne;
-  if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
-  c->v2_nshards = 1; c->v2_rank = 0;
-  c->v2_built.clear();
-  build_task_list(S, c->klist);
-  return 0;
+  // only the blocks (T) can touch become resident (the rest of d_v2orb stays on the host)
+  if (nranks == 1) {
+    NWC_TRY(cudaMalloc((void**)&c->d_v2orb, (size_t)(S.orb_size ? S.orb_size : 1) * sizeof(double)));
+    if (orb->v2orb) {
+      for (const HostState::OrbRun& r : S.orb_runs)   // compacted run by run
+        NWC_TRY(cudaMemcpy(c->d_v2orb + r.dst, orb->v2orb + r.src, (size_t)r.n * sizeof(double), cudaMemcpyHostToDevice));
+      c->eng->stats.h2d_bytes += (size_t)S.orb_size * sizeof(double);
+    }
+    c->n_v2orb = (size_t)S.orb_size;
+  } else {
+    // sharded: needed block i -> rank i % nranks; orb->v2orb (if given) is the caller's FULL d_v2orb file, of which
+    // only this rank's blocks are read
+    Integer mine = 0;
+    build_shards(c, (Integer)S.orb_blocks.size(), rank, nranks, [&](Integer i) { return S.orb_blocks[(size_t)i].size; }, &mine);
+    NWC_TRY(cudaMalloc((void**)&c->d_v2orb, (size_t)(mine ? mine : 1) * sizeof(double)));
+    if (orb->v2orb) {
+      for (size_t i = (size_t)rank; i < S.orb_blocks.size(); i += (size_t)nranks)
+        NWC_TRY(cudaMemcpy(c->d_v2orb + c->v2_shard_off[i], orb->v2orb + S.orb_blocks[i].host_off,
+                           (size_t)S.orb_blocks[i].size * sizeof(double), cudaMemcpyHostToDevice));
+      c->eng->stats.h2d_bytes += (size_t)mine * sizeof(double);
+    }
+    c->n_v2orb = (size_t)mine;
+    c->v2_peer[(size_t)rank] = c->d_v2orb;
+  }
+  return finish_state(c);
 }
 
-// Sharded variant: st->v2 points at THIS rank's shard only (its blocks, table order, compacted).
+int nwc_triples_set_state_2eorb(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb) {
+  return guarded(c, [&]() { return set_state_orbital(c, st, orb, 0, 1); });
+}
+
+int nwc_triples_set_state_2eorb_sharded(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb, int rank,
+                                        int nranks) {
+  return guarded(c, [&]() { return set_state_orbital(c, st, orb, rank, nranks); });
+}
+
+// Sharded variant: st->v2 points at THIS rank's shard only (its blocks, table order, compacted), or is NULL.
 int nwc_triples_set_state_sharded(nwc_triples_ctx* c, const nwc_tce_state* st, int rank, int nranks) {
   if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
-  NWC_TRY(cudaSetDevice(c->eng->device()));
-  c->S.load_tables(st);
-  const HostState& S = c->S;
-  if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
-  if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
-  // shard offsets of every block (all ranks compute the same table)
-  const Integer n = S.v2_hash[0];
-  const Integer total = (Integer)store_size(st->v2_hash, S, 3);
-  c->v2_shard_off.assign((size_t)n, 0);
-  std::vector<Integer> fill((size_t)nranks, 0);
-  for (Integer i = 0; i < n; i++) {
-    const Integer off = S.v2_hash[n + 1 + i], next = (i + 1 < n) ? S.v2_hash[n + 2 + i] : total;
-    const int owner = (int)(i % nranks);
-    c->v2_shard_off[(size_t)i] = fill[owner];
-    fill[owner] += next - off;
-  }
-  if (upload(&c->d_v2, &c->n_v2, st->v2, (size_t)fill[rank], c->eng)) return 1;
-  size_t ne;
-  if (upload(&c->d_evl, &ne, S.evl.data(), S.evl.size(), c->eng)) return 1;
-  c->v2_nshards = nranks; c->v2_rank = rank;
-  c->v2_peer.assign((size_t)nranks, nullptr);
-  c->v2_peer_opened.assign((size_t)nranks, 0);
-  c->v2_peer[rank] = c->d_v2;
-  build_task_list(S, c->klist);
-  return 0;
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    free_stores(c);
+    c->S.load_tables(st);
+    const HostState& S = c->S;
+    if (upload(&c->d_t1, &c->n_t1, st->t1, store_size(st->t1_hash, S, 1), c->eng)) return 1;
+    if (upload(&c->d_t2, &c->n_t2, st->t2, store_size(st->t2_hash, S, 2), c->eng)) return 1;
+    // shard offsets of every block (all ranks compute the same table)
+    const Integer n = S.v2_hash[0];
+    const Integer total = (Integer)store_size(st->v2_hash, S, 3);
+    Integer mine = 0;
+    build_shards(c, n, rank, nranks, [&](Integer i) {
+      const Integer off = S.v2_hash[(size_t)(n + 1 + i)], next = (i + 1 < n) ? S.v2_hash[(size_t)(n + 2 + i)] : total;
+      return next - off;
+    }, &mine);
+    if (upload(&c->d_v2, &c->n_v2, st->v2, (size_t)mine, c->eng)) return 1;
+    c->v2_peer[(size_t)rank] = c->d_v2;
+    return finish_state(c);
+  });
 }
+
+static double* shard_base(nwc_triples_ctx* c) { return c->S.intorb ? c->d_v2orb : c->d_v2; }
 
 // CUDA IPC handle (64 bytes) of this rank's V2 shard; the host all-gathers them (MPI/GA in NWChem)
 int nwc_triples_v2_ipc_handle(nwc_triples_ctx* c, char handle64[64]) {
   NWC_TRY(cudaSetDevice(c->eng->device()));
   cudaIpcMemHandle_t h;
-  NWC_TRY(cudaIpcGetMemHandle(&h, c->d_v2));
+  NWC_TRY(cudaIpcGetMemHandle(&h, shard_base(c)));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
   memcpy(handle64, &h, 64);
   return 0;
@@ -367,11 +539,96 @@ int nwc_triples_v2_open_peers(nwc_triples_ctx* c, const char* handles) {
 
 // same-process alternative to the IPC exchange (several contexts in one process, tests): device pointer of this
 // context's shard, and direct registration of a peer's shard pointer
-void* nwc_triples_v2_shard_ptr(nwc_triples_ctx* c) { return c->d_v2; }
+void* nwc_triples_v2_shard_ptr(nwc_triples_ctx* c) { return shard_base(c); }
 int nwc_triples_v2_set_peer_ptr(nwc_triples_ctx* c, int rank, void* dev_ptr) {
   if (rank < 0 || rank >= c->v2_nshards) { g_err = "bad peer rank"; return 1; }
   c->v2_peer[(size_t)rank] = (double*)dev_ptr;
   return 0;
+}
+
+// ---- synthetic stores generated on the device (bench / tests) ----
+// Fills T1, T2 and the V2 store this context holds (whole, or this rank's shard) with scale * U(-1,1) values that are a
+// pure function of (seed, store, block key, element): no rank ever needs the store on the host, and every rank count sees
+// the same tensors.  store ids: 1 = T1, 2 = T2, 3 = spin-orbital V2, 4 = orbital-form V2.
+int nwc_triples_synth_fill(nwc_triples_ctx* c, unsigned long long seed, double scale_t1, double scale_t2, double scale_v2) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    cudaStream_t st = c->eng->stream();
+    auto run = [&](std::vector<FillJob>& jobs, unsigned long long store, double scale) -> int {
+      if (jobs.empty()) return 0;
+      long long mx = 0;
+      for (const FillJob& j : jobs) mx = std::max(mx, j.n);
+      FillJob* d = nullptr;
+      NWC_TRY(cudaMalloc((void**)&d, jobs.size() * sizeof(FillJob)));
+      NWC_TRY(cudaMemcpyAsync(d, jobs.data(), jobs.size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
+      launch_synth_fill(d, (int)jobs.size(), mx, seed, store, scale, st);
+      NWC_TRY(cudaGetLastError());
+      NWC_TRY(cudaStreamSynchronize(st));
+      NWC_TRY(cudaFree(d));
+      return 0;
+    };
+    auto table_jobs = [&](const std::vector<Integer>& hash, double* base, size_t total, std::vector<FillJob>& jobs) {
+      const Integer n = hash[0];
+      for (Integer i = 0; i < n; i++) {
+        const Integer off = hash[(size_t)(n + 1 + i)], next = (i + 1 < n) ? hash[(size_t)(n + 2 + i)] : (Integer)total;
+        jobs.push_back(FillJob{base + off, (long long)hash[(size_t)(1 + i)], (long long)(next - off)});
+      }
+    };
+    std::vector<FillJob> jobs;
+    table_jobs(S.t1_hash, c->d_t1, c->n_t1, jobs);
+    if (run(jobs, 1, scale_t1)) return 1;
+    jobs.clear();
+    table_jobs(S.t2_hash, c->d_t2, c->n_t2, jobs);
+    if (run(jobs, 2, scale_t2)) return 1;
+    jobs.clear();
+    if (S.intorb) {
+      for (size_t i = 0; i < S.orb_blocks.size(); i++) {
+        const HostState::OrbBlock& b = S.orb_blocks[i];
+        if (c->v2_nshards <= 1) jobs.push_back(FillJob{c->d_v2orb + S.orb_off.at(b.key), (long long)b.key, (long long)b.size});
+        else if ((int)(i % (size_t)c->v2_nshards) == c->v2_rank)
+          jobs.push_back(FillJob{c->d_v2orb + c->v2_shard_off[i], (long long)b.key, (long long)b.size});
+      }
+      if (run(jobs, 4, scale_v2)) return 1;
+    } else if (c->v2_nshards <= 1) {
+      table_jobs(S.v2_hash, c->d_v2, c->n_v2, jobs);
+      if (run(jobs, 3, scale_v2)) return 1;
+    } else {
+      const Integer n = S.v2_hash[0];
+      for (Integer i = c->v2_rank; i < n; i += c->v2_nshards)
+        jobs.push_back(FillJob{c->d_v2 + c->v2_shard_off[(size_t)i], (long long)S.v2_hash[(size_t)(1 + i)], (long long)c->v2_block_n[(size_t)i]});
+      if (run(jobs, 3, scale_v2)) return 1;
+    }
+    return 0;
+  });
+}
+
+// validation aid: read back part of a resident store.  which: 1 = T1, 2 = T2, 3 = V2 (this rank's shard), 4 = orbital V2
+int nwc_triples_debug_read(nwc_triples_ctx* c, int which, size_t offset, size_t n, double* host_out) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  const double* base = which == 1 ? c->d_t1 : which == 2 ? c->d_t2 : which == 3 ? c->d_v2 : c->d_v2orb;
+  const size_t cap = which == 1 ? c->n_t1 : which == 2 ? c->n_t2 : which == 3 ? c->n_v2 : c->n_v2orb;
+  if (!base || offset + n > cap) { g_err = "nwc_triples_debug_read: out of range"; return 1; }
+  NWC_TRY(cudaMemcpy(host_out, base + offset, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// The spin-orbital block <g3 g4||g1 g2> (tile ids as stored, i.e. after tce_restricted_4) as the (T) path sees it,
+// copied to the host: the device form of get_hash_block / get_hash_block_i for one block.
+int nwc_triples_export_v2_block(nwc_triples_ctx* c, const Integer g3g4g1g2[4], double* host_out) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    const Integer g3 = g3g4g1g2[0], g4 = g3g4g1g2[1], g1 = g3g4g1g2[2], g2 = g3g4g1g2[3];
+    const double* p = v2_operand(c, g3, g4, g1, g2, "v2(export)");
+    c->eng->flush_prep();
+    const size_t n = (size_t)(S.rg(g3) * S.rg(g4) * S.rg(g1) * S.rg(g2));
+    NWC_TRY(cudaMemcpyAsync(host_out, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->eng->stream()));
+    NWC_TRY(cudaStreamSynchronize(c->eng->stream()));
+    c->eng->arena().reset();
+    slot_done(c, c->eng->current_slot());
+    return 0;
+  });
 }
 
 Integer nwc_triples_num_tasks(nwc_triples_ctx* c) { return (Integer)(c->klist.size() / 7); }
@@ -383,125 +640,173 @@ int nwc_triples_task_list(nwc_triples_ctx* c, Integer* klist7) {
 
 int nwc_triples_run(nwc_triples_ctx* c, Integer first, Integer stride, Integer max_tasks, double energy[2],
                     double* per_task) {
-  NWC_TRY(cudaSetDevice(c->eng->device()));
-  if (stride <= 0) stride = 1;
-  const Integer nt = (Integer)(c->klist.size() / 7);
-  Engine& e = *c->eng;
-  energy[0] = energy[1] = 0.0;
-  std::vector<double> eb;
-  Integer done = 0, out_pos = 0;
-  auto flush = [&]() {
-    const int n = e.pending_tuples();
-    if (n == 0) return;
-    eb.assign(2 * (size_t)n, 0.0);
-    e.run(eb.data());
-    for (int i = 0; i < n; i++) {
-      energy[0] += eb[2 * i];
-      energy[1] += eb[2 * i + 1];
-      if (per_task) { per_task[2 * (out_pos + i)] = eb[2 * i]; per_task[2 * (out_pos + i) + 1] = eb[2 * i + 1]; }
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    if (stride <= 0) stride = 1;
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    energy[0] = energy[1] = 0.0;
+    Integer done = 0;
+    for (Integer k = first; per_task && k < nt && (max_tasks <= 0 || done < max_tasks); k += stride, done++)
+      per_task[2 * done] = per_task[2 * done + 1] = 0.0;
+    Pipeline pipe(c, energy, per_task);
+    done = 0;
+    for (Integer k = first; k < nt && (max_tasks <= 0 || done < max_tasks); k += stride, done++) {
+      emit_tuple(c, &c->klist[7 * k]);
+      pipe.emitted(done);
     }
-    out_pos += n;
-    reset_arena(c);
-  };
-  for (Integer k = first; k < nt && (max_tasks <= 0 || done < max_tasks); k += stride, done++) {
-    emit_tuple(c, &c->klist[7 * k]);
-    if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)32000000 || e.pending_tuples() >= 4096) flush();
-  }
-  flush();
-  return 0;
+    pipe.finish();
+    return 0;
+  });
+}
+
+// Static block partition of the task space (north star: "the tile-tuple task space is block-partitioned across the
+// GPUs"), the stand-in for the nxtask counter (ccsd_t.F:174-255).  Tasks [first_task, first_task + ntasks) of the
+// heaviest-first list are laid end to end, every 4^6 sub-tile weighted by the k4 planes its tuple contracts (+ a constant
+// for the per-sub-tile epilogue); rank r takes the r-th of nranks equal-cost contiguous pieces.  A tuple that straddles a
+// boundary is shared between two ranks at sub-tile granularity (energies are additive over sub-tiles), so the balance
+// does not depend on how many tuples there are.  per_task (optional, 2*ntasks, indexed by task - first_task) receives
+// this rank's (partial) energies; summed over ranks it holds the per-task energies.
+int nwc_triples_run_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                              double energy[2], double* per_task) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+    if (first_task < 0) first_task = 0;
+    if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
+    energy[0] = energy[1] = 0.0;
+    if (per_task) for (Integer i = 0; i < 2 * ntasks; i++) per_task[i] = 0.0;
+    if (ntasks <= 0) return 0;
+    const long long EPILOGUE_PLANES = 24;   // per-sub-tile fixed work (transfers, singles, energy) in units of one k4 plane
+    std::vector<long long> items((size_t)ntasks), w((size_t)ntasks);
+    std::vector<__int128> cum((size_t)ntasks + 1, 0);
+    for (Integer i = 0; i < ntasks; i++) {
+      const Integer* t = &c->klist[7 * (first_task + i)];
+      int R[6];
+      tuple_ranges(S, t, R);
+      CostSink cs{S};
+      walk_singles(S, t, cs);
+      walk_doubles(S, t, cs);
+      items[(size_t)i] = Engine::tuple_items(R);
+      w[(size_t)i] = cs.planes + EPILOGUE_PLANES;
+      cum[(size_t)i + 1] = cum[(size_t)i] + (__int128)items[(size_t)i] * w[(size_t)i];
+    }
+    const __int128 total = cum[(size_t)ntasks];
+    const __int128 lo = total * rank / nranks, hi = total * (rank + 1) / nranks;
+    auto cut = [&](__int128 bound, Integer i) -> long long {   // first sub-tile of task i at or beyond `bound`
+      const __int128 rel = bound - cum[(size_t)i];
+      if (rel <= 0) return 0;
+      const __int128 q = (rel + w[(size_t)i] - 1) / w[(size_t)i];
+      return q > items[(size_t)i] ? items[(size_t)i] : (long long)q;
+    };
+    Pipeline pipe(c, energy, per_task);
+    for (Integer i = 0; i < ntasks; i++) {
+      const long long a = cut(lo, i), b = cut(hi, i);
+      if (b <= a) continue;
+      emit_tuple(c, &c->klist[7 * (first_task + i)], a, b);
+      pipe.emitted(i);
+    }
+    pipe.finish();
+    return 0;
+  });
+}
+
+// one tuple restricted to the sub-tiles [item_lo, item_hi) of its linear sub-tile order (h3 block fastest, p4 block
+// slowest): e.g. a p4 slab [4a, 4b) of the t3 tile is the range [a*m, b*m), m = sub-tiles per p4 block
+int nwc_triples_run_items(nwc_triples_ctx* c, const Integer t[6], long long item_lo, long long item_hi, double energy[2]) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    emit_tuple(c, t, item_lo, item_hi);
+    double out[2] = {0, 0};
+    c->eng->run(out);
+    slot_done(c, c->eng->current_slot());
+    energy[0] = out[0];
+    energy[1] = out[1];
+    return 0;
+  });
+}
+
+long long nwc_triples_tuple_items(nwc_triples_ctx* c, const Integer t[6]) {
+  int R[6];
+  tuple_ranges(c->S, t, R);
+  return Engine::tuple_items(R);
 }
 
 int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, Integer* restart_begin, double* table,
                             double* table_bracket, Integer max_outer, double* t_energy) {
-  NWC_TRY(cudaSetDevice(c->eng->device()));
-  if (stride <= 0) stride = 1;
-  if (*restart_begin < 1) *restart_begin = 1;
-  const HostState& S = c->S;
-  Engine& e = *c->eng;
-  const Integer n0 = S.noab, n1 = S.noab + S.nvab;
-  std::vector<double> eb;
-  Integer done = 0;
-  for (Integer p4 = n0 + *restart_begin; p4 <= n1; p4++) {
-    if (max_outer > 0 && done >= max_outer) break;
-    double en[2] = {0.0, 0.0};
-    auto flush = [&]() {
-      const int n = e.pending_tuples();
-      if (n == 0) return;
-      eb.assign(2 * (size_t)n, 0.0);
-      e.run(eb.data());
-      for (int i = 0; i < n; i++) { en[0] += eb[2 * i]; en[1] += eb[2 * i + 1]; }
-      reset_arena(c);
-    };
-    Integer count = 0;   // position in this outer tile's loop order (ccsd_t_restart.F:120-150)
-    for (Integer p5 = p4; p5 <= n1; p5++)
-      for (Integer p6 = p5; p6 <= n1; p6++)
-        for (Integer h1 = 1; h1 <= n0; h1++)
-          for (Integer h2 = h1; h2 <= n0; h2++)
-            for (Integer h3 = h2; h3 <= n0; h3++) {
-              const Integer ps = S.sp(p4) + S.sp(p5) + S.sp(p6), hs = S.sp(h1) + S.sp(h2) + S.sp(h3);
-              if (ps != hs) continue;
-              if (S.restricted && ps + hs > 8) continue;
-              if ((S.sy(p4) ^ S.sy(p5) ^ S.sy(p6) ^ S.sy(h1) ^ S.sy(h2) ^ S.sy(h3)) != 0) continue;
-              const Integer k = count++;
-              if (k < first || (k - first) % stride != 0) continue;
-              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
-              emit_tuple(c, t);
-              if (e.arena().used() >= c->batch_bytes || e.pending_items() > (size_t)32000000 || e.pending_tuples() >= 4096)
-                flush();
-            }
-    flush();
-    if (c->comm) {
-      if (nwc_triples_allreduce_energy(c, en) != 0) return 1;
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    if (stride <= 0) stride = 1;
+    if (*restart_begin < 1) *restart_begin = 1;
+    const HostState& S = c->S;
+    const Integer n0 = S.noab, n1 = S.noab + S.nvab;
+    Integer done = 0;
+    for (Integer p4 = n0 + *restart_begin; p4 <= n1; p4++) {
+      if (max_outer > 0 && done >= max_outer) break;
+      double en[2] = {0.0, 0.0};
+      Pipeline pipe(c, en, nullptr);
+      Integer count = 0;   // position in this outer tile's loop order (ccsd_t_restart.F:120-150)
+      for (Integer p5 = p4; p5 <= n1; p5++)
+        for (Integer p6 = p5; p6 <= n1; p6++)
+          for (Integer h1 = 1; h1 <= n0; h1++)
+            for (Integer h2 = h1; h2 <= n0; h2++)
+              for (Integer h3 = h2; h3 <= n0; h3++) {
+                const Integer ps = S.sp(p4) + S.sp(p5) + S.sp(p6), hs = S.sp(h1) + S.sp(h2) + S.sp(h3);
+                if (ps != hs) continue;
+                if (S.restricted && ps + hs > 8) continue;
+                if ((S.sy(p4) ^ S.sy(p5) ^ S.sy(p6) ^ S.sy(h1) ^ S.sy(h2) ^ S.sy(h3)) != 0) continue;
+                const Integer k = count++;
+                if (k < first || (k - first) % stride != 0) continue;
+                const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+                emit_tuple(c, t);
+                pipe.emitted(-1);
+              }
+      pipe.finish();
+      if (c->comm) {
+        if (nwc_triples_allreduce_energy(c, en) != 0) return 1;
+      }
+      const Integer outer = p4 - n0;
+      table[outer - 1] = en[1];
+      if (table_bracket) table_bracket[outer - 1] = en[0];
+      *restart_begin = outer + 1;
+      done++;
     }
-    const Integer outer = p4 - n0;
-    table[outer - 1] = en[1];
-    if (table_bracket) table_bracket[outer - 1] = en[0];
-    *restart_begin = outer + 1;
-    done++;
-  }
-  *t_energy = 0.0;
-  for (Integer i = 0; i < S.nvab; i++) *t_energy += table[i];
-  return 0;
+    *t_energy = 0.0;
+    for (Integer i = 0; i < S.nvab; i++) *t_energy += table[i];
+    return 0;
+  });
 }
 
 int nwc_triples_run_tuple(nwc_triples_ctx* c, const Integer t[6], double energy[2], double* host_doubles,
                           double* host_singles) {
-  NWC_TRY(cudaSetDevice(c->eng->device()));
-  Engine& e = *c->eng;
-  emit_tuple(c, t);
-  double *dd = nullptr, *ds = nullptr;
-  size_t sz = 1;
-  if (host_doubles) {
-    for (int q = 0; q < 6; q++) sz *= (size_t)c->S.rg(t[q]);
-    dd = (double*)e.arena().alloc(sz * sizeof(double));
-    ds = (double*)e.arena().alloc(sz * sizeof(double));
-    NWC_TRY(cudaMemsetAsync(dd, 0, sz * sizeof(double), e.stream()));
-    NWC_TRY(cudaMemsetAsync(ds, 0, sz * sizeof(double), e.stream()));
-  }
-  double out[2] = {0, 0};
-  e.run(out, dd, ds);
-  if (host_doubles) {
-    NWC_TRY(cudaMemcpy(host_doubles, dd, sz * sizeof(double), cudaMemcpyDeviceToHost));
-    NWC_TRY(cudaMemcpy(host_singles, ds, sz * sizeof(double), cudaMemcpyDeviceToHost));
-  }
-  reset_arena(c);
-  energy[0] = out[0];
-  energy[1] = out[1];
-  return 0;
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    Engine& e = *c->eng;
+    emit_tuple(c, t);
+    double *dd = nullptr, *ds = nullptr;
+    size_t sz = 1;
+    if (host_doubles) {
+      for (int q = 0; q < 6; q++) sz *= (size_t)c->S.rg(t[q]);
+      dd = (double*)e.arena().alloc(sz * sizeof(double));
+      ds = (double*)e.arena().alloc(sz * sizeof(double));
+      NWC_TRY(cudaMemsetAsync(dd, 0, sz * sizeof(double), e.stream()));
+      NWC_TRY(cudaMemsetAsync(ds, 0, sz * sizeof(double), e.stream()));
+    }
+    double out[2] = {0, 0};
+    e.run(out, dd, ds);
+    slot_done(c, e.current_slot());
+    if (host_doubles) {   // the arena has been rewound but not released: the tiles are still there
+      NWC_TRY(cudaMemcpy(host_doubles, dd, sz * sizeof(double), cudaMemcpyDeviceToHost));
+      NWC_TRY(cudaMemcpy(host_singles, ds, sz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    energy[0] = out[0];
+    energy[1] = out[1];
+    return 0;
+  });
 }
 
 int nwc_triples_set_timing(nwc_triples_ctx* c, int on) { c->eng->timing = on != 0; return 0; }
-
-int nwc_triples_get_stats(nwc_triples_ctx* c, nwc_triples_stats* o, int reset) {
-  const EngineStats& s = c->eng->stats;
-  o->fused_ms = s.fused_ms; o->repack_ms = s.repack_ms;
-  o->fused_launches = s.fused_launches; o->repack_launches = s.repack_launches; o->reduce_launches = s.reduce_launches;
-  o->work_items = s.work_items; o->descs = s.descs; o->tuples = s.tuples; o->flops = s.flops;
-  o->h2d_bytes = (double)s.h2d_bytes; o->d2h_bytes = (double)s.d2h_bytes;
-  o->resident_bytes = 8.0 * (double)(c->n_t1 + c->n_t2 + c->n_v2 + c->n_v2orb);
-  if (reset) c->eng->stats = EngineStats();
-  return 0;
-}
 
 static void fill_stats(const EngineStats& s, nwc_triples_stats* o, double resident) {
   o->fused_ms = s.fused_ms; o->repack_ms = s.repack_ms;
@@ -509,20 +814,33 @@ static void fill_stats(const EngineStats& s, nwc_triples_stats* o, double reside
   o->work_items = s.work_items; o->descs = s.descs; o->tuples = s.tuples; o->flops = s.flops;
   o->h2d_bytes = (double)s.h2d_bytes; o->d2h_bytes = (double)s.d2h_bytes;
   o->resident_bytes = resident;
+  o->pull_ms = s.pull_ms; o->peer_bytes = (double)s.peer_bytes;
+  o->pull_launches = s.pull_launches; o->antisym_launches = s.antisym_launches;
 }
-int nwc_triples_timer_start(nwc_triples_ctx* c) { cudaSetDevice(c->eng->device()); c->eng->timer_start(); return 0; }
-int nwc_triples_timer_stop_ms(nwc_triples_ctx* c, double* ms) { cudaSetDevice(c->eng->device()); *ms = c->eng->timer_stop_ms(); return 0; }
+int nwc_triples_get_stats(nwc_triples_ctx* c, nwc_triples_stats* o, int reset) {
+  fill_stats(c->eng->stats, o, 8.0 * (double)(c->n_t1 + c->n_t2 + c->n_v2 + c->n_v2orb));
+  if (reset) c->eng->stats = EngineStats();
+  return 0;
+}
+int nwc_triples_timer_start(nwc_triples_ctx* c) {
+  return guarded(c, [&]() { cudaSetDevice(c->eng->device()); c->eng->timer_start(); return 0; });
+}
+int nwc_triples_timer_stop_ms(nwc_triples_ctx* c, double* ms) {
+  return guarded(c, [&]() { cudaSetDevice(c->eng->device()); *ms = c->eng->timer_stop_ms(); return 0; });
+}
 int nwc_host_register(void* ptr, size_t bytes) { NWC_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
 int nwc_host_unregister(void* ptr) { NWC_TRY(cudaHostUnregister(ptr)); return 0; }
 int nwc_compat_get_stats(nwc_triples_stats* o, int reset) {
-  Engine& e = nwc::compat_engine();
-  fill_stats(e.stats, o, 0.0);
-  if (reset) e.stats = EngineStats();
-  return 0;
+  return guarded(nullptr, [&]() {
+    Engine& e = nwc::compat_engine();
+    fill_stats(e.stats, o, 0.0);
+    if (reset) e.stats = EngineStats();
+    return 0;
+  });
 }
-int nwc_compat_set_timing(int on) { nwc::compat_engine().timing = on != 0; return 0; }
-int nwc_compat_timer_start(void) { nwc::compat_engine().timer_start(); return 0; }
-int nwc_compat_timer_stop_ms(double* ms) { *ms = nwc::compat_engine().timer_stop_ms(); return 0; }
+int nwc_compat_set_timing(int on) { return guarded(nullptr, [&]() { nwc::compat_engine().timing = on != 0; return 0; }); }
+int nwc_compat_timer_start(void) { return guarded(nullptr, [&]() { nwc::compat_engine().timer_start(); return 0; }); }
+int nwc_compat_timer_stop_ms(double* ms) { return guarded(nullptr, [&]() { *ms = nwc::compat_engine().timer_stop_ms(); return 0; }); }
 
 // debugging aid (not part of the public header): per-CTA phase clocks of the next launches; cap_items = 0 turns it off
 int nwc_debug_phase_timing(unsigned long long* host_out, unsigned int cap_items, int fetch) {
@@ -545,6 +863,7 @@ int nwc_debug_phase_timing(unsigned long long* host_out, unsigned int cap_items,
 }
 
 int nwc_triples_set_batch_bytes(nwc_triples_ctx* c, size_t bytes) { c->batch_bytes = bytes; return 0; }
+int nwc_triples_set_arena_cap(nwc_triples_ctx* c, size_t bytes) { c->eng->set_arena_cap(bytes); return 0; }
 
 int nwc_triples_nccl_unique_id(char id128[128]) {
   if (!g_nccl.load()) return 1;
@@ -563,20 +882,28 @@ int nwc_triples_nccl_init(nwc_triples_ctx* c, const char id128[128], int rank, i
   int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
   if (r != 0) { g_err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return 1; }
   c->nranks = nranks;
-  if (!c->d_red) NWC_TRY(cudaMalloc((void**)&c->d_red, 2 * sizeof(double)));
   return 0;
 }
 
-int nwc_triples_allreduce_energy(nwc_triples_ctx* c, double energy[2]) {
+// sum over ranks of n doubles, in place (host buffer): one ncclAllReduce on the library's stream
+int nwc_triples_allreduce_sum(nwc_triples_ctx* c, double* buf, size_t n) {
   if (!c->comm) { if (c->nranks == 1) return 0; g_err = "nccl not initialised"; return 1; }
   NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (n > c->n_red) {
+    if (c->d_red) cudaFree(c->d_red);
+    c->d_red = nullptr; c->n_red = 0;
+    NWC_TRY(cudaMalloc((void**)&c->d_red, n * sizeof(double)));
+    c->n_red = n;
+  }
   cudaStream_t s = c->eng->stream();
-  NWC_TRY(cudaMemcpyAsync(c->d_red, energy, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
-  int r = g_nccl.AllReduce(c->d_red, c->d_red, 2, NCCL_DOUBLE, NCCL_SUM, c->comm, s);  // replaces ga_dgop (ccsd_t.F:297)
+  NWC_TRY(cudaMemcpyAsync(c->d_red, buf, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  int r = g_nccl.AllReduce(c->d_red, c->d_red, n, NCCL_DOUBLE, NCCL_SUM, c->comm, s);  // replaces ga_dgop (ccsd_t.F:297)
   if (r != 0) { g_err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return 1; }
-  NWC_TRY(cudaMemcpyAsync(energy, c->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  NWC_TRY(cudaMemcpyAsync(buf, c->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   NWC_TRY(cudaStreamSynchronize(s));
   return 0;
 }
+
+int nwc_triples_allreduce_energy(nwc_triples_ctx* c, double energy[2]) { return nwc_triples_allreduce_sum(c, energy, 2); }
 
 }  // extern "C"

@@ -44,6 +44,68 @@ def random_blocks(t: tl.Tiling, seed: int = 20240229, scale=(0.05, 0.02, 0.1)) -
     return BlockStores(t, t1h, t1, t2h, t2, v2h, v2)
 
 
+# ---- the keyed generator of nwc_triples_synth_fill (csrc/kernels.cu synth_fill_kernel), restated in numpy ----
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_C1, _C2, _C3 = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xD1B54A32D192ED03), np.uint64(0xBF58476D1CE4E5B9)
+_C4 = np.uint64(0x94D049BB133111EB)
+
+
+def _mix(z):
+    z = (z ^ (z >> np.uint64(30))) * _C3
+    z = (z ^ (z >> np.uint64(27))) * _C4
+    return z ^ (z >> np.uint64(31))
+
+
+def keyed_values(seed: int, store: int, key: int, n: int, scale: float) -> np.ndarray:
+    """Element e of block `key` of store `store` (1 T1, 2 T2, 3 spin-orbital V2, 4 orbital V2): scale*(2u-1),
+    u = top 53 bits of a splitmix64-style hash of (seed, store, key, e).  Bit-identical to the device generator."""
+    with np.errstate(over="ignore"):
+        hk = _mix(np.array([(np.uint64(seed) * _C1 + np.uint64(store) * _C2) ^ np.uint64(key)], np.uint64))
+        h = _mix(hk + np.arange(n, dtype=np.uint64) * _C1)
+    u = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return scale * (2.0 * u - 1.0)
+
+
+def _fill_table(h, total, seed, store, scale):
+    out = np.zeros(total)
+    n = int(h[0])
+    offs = [int(h[1 + n + i]) for i in range(n)] + [total]
+    for i in range(n):
+        out[offs[i]:offs[i + 1]] = keyed_values(seed, store, int(h[1 + i]), offs[i + 1] - offs[i], scale)
+    return out
+
+
+def keyed_blocks(t: tl.Tiling, seed: int = 20240229, scale=(0.05, 0.02, 0.1), intorb: bool = False) -> BlockStores:
+    """Host copy of what Triples.synth_fill(seed, scale) puts on the device (small shapes: oracle parity)."""
+    t1h, n1 = tl.t1_offset(t); t2h, n2 = tl.t2_offset(t); v2h, nv = tl.v2_offset(t)
+    st = BlockStores(t, t1h, _fill_table(t1h, n1, seed, 1, scale[0]), t2h, _fill_table(t2h, n2, seed, 2, scale[1]),
+                     v2h, None if intorb else _fill_table(v2h, nv, seed, 3, scale[2]))
+    if intorb:
+        a = tl.alpha_tiling(t)
+        tab, size = tl.v2orb_offset(a)
+        blocks, _ = tl.v2orb_blocks(a)
+        vo = np.zeros(size)
+        is_p = lambda b: b > a.noa
+        for g3b, g4b, g1b, g2b, key, off, n in blocks:
+            # the device holds (and fills) only the blocks (T) can touch: one mixed hole/particle tile pair at least
+            if int(is_p(g3b)) + int(is_p(g4b)) == 1 or int(is_p(g1b)) + int(is_p(g2b)) == 1:
+                vo[off:off + n] = keyed_values(seed, 4, key, n, scale[2])
+        st.orb = OrbitalV2(a, tab, vo)
+        st.v2 = np.zeros(0)
+    return st
+
+
+def empty_stores(t: tl.Tiling, intorb: bool = False) -> BlockStores:
+    """Tables only, no data: the library allocates the stores and Triples.synth_fill generates them on the device."""
+    t1h, _ = tl.t1_offset(t); t2h, _ = tl.t2_offset(t)
+    if intorb:
+        a = tl.alpha_tiling(t)
+        tab, _ = tl.v2orb_offset(a)
+        return BlockStores(t, t1h, None, t2h, None, np.zeros(1, np.int64), None, OrbitalV2(a, tab, None))
+    v2h, _ = tl.v2_offset(t)
+    return BlockStores(t, t1h, None, t2h, None, v2h, None)
+
+
 def random_orbital(t: tl.Tiling, seed: int = 20240229, scale: float = 0.1) -> OrbitalV2:
     """iid orbital-form V2 store for large shapes (timing, oracle-vs-GPU parity); not tied to a spin-orbital store."""
     a = tl.alpha_tiling(t)

@@ -192,6 +192,34 @@ def tuple_tiles(st, tup):
     return s.reshape(dims), d.reshape(dims), float(e[0]), float(e[1]), cnt
 
 
+def tuple_slab(st, tup, lo, hi, tiles=False):
+    """One tuple restricted to the p4 slab [lo,hi) of its t3 tile (the slicing of ccsd_t_6dts.F restated on the 27
+    kernels): returns (e1, e2) of the slab [, singles, doubles indexed [p4-lo,p5,p6,h1,h2,h3]].  Slabs add up to the tuple."""
+    l = lib()
+    c, keep = make_ctx(st)
+    t = st.t
+    hi = min(hi, t.r(int(tup[0])))
+    dims = [hi - lo] + [t.r(int(b)) for b in tup[1:6]]
+    size = int(np.prod(dims))
+    s = np.zeros(size); d = np.zeros(size); e = np.zeros(2)
+    tt = np.array(tup[:6], np.int64)
+    l.ora_ccsd_t_loop_slab(C.byref(c), _pl(tt), L(lo), L(hi), _pd(s), _pd(d), _pd(e))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    if tiles:
+        return float(e[0]), float(e[1]), s.reshape(dims), d.reshape(dims)
+    return float(e[0]), float(e[1])
+
+
+def tuple_sliced(st, tup, width=4):
+    """Whole tuple, p4-sliced `width` at a time (never holds more than width/range(p4) of the tile)."""
+    e1 = e2 = 0.0
+    for lo in range(0, st.t.r(int(tup[0])), width):
+        a, b = tuple_slab(st, tup, lo, lo + width)
+        e1 += a; e2 += b
+    return e1, e2
+
+
 def count_tuple(st_or_ctx, tup, keep=None):
     l = lib()
     c, keep = make_ctx(st_or_ctx) if keep is None else (st_or_ctx, keep)

@@ -149,6 +149,36 @@ static const d_fn D1[9] = {ora_sd_t_d1_1, ora_sd_t_d1_2, ora_sd_t_d1_3, ora_sd_t
 static const d_fn D2[9] = {ora_sd_t_d2_1, ora_sd_t_d2_2, ora_sd_t_d2_3, ora_sd_t_d2_4, ora_sd_t_d2_5,
                            ora_sd_t_d2_6, ora_sd_t_d2_7, ora_sd_t_d2_8, ora_sd_t_d2_9};
 
+/* ------------------------------------------------------------------------------------ */
+/* p4 slab (the slicing of ccsd_t_6dts.F:136-141 restated generically): when a slab is   */
+/* set, the per-tuple drivers below form only T3(h3,h2,h1,p6,p5,p4 in [lo,hi)) of the    */
+/* TASK tuple.  Each of the 27 kernels is declared with some permuted particle name at    */
+/* the slowest physical position (the table below, read off the DEF_* lists above); that  */
+/* name's range is cut to the slab and the operand that carries it is sliced accordingly. */
+/* A 40^6 tile (30 GiB) is then evaluated 4 p4 values at a time.                          */
+/* ------------------------------------------------------------------------------------ */
+static Integer g_slab_lo = 0, g_slab_hi = -1; /* hi < 0: no slab */
+void ora_set_p4_slab(Integer lo, Integer hi) { g_slab_lo = lo; g_slab_hi = hi; }
+enum { SL_P4 = 4, SL_P5 = 5, SL_P6 = 6 };
+static const int SLOWEST[3][9] = {{SL_P4, SL_P4, SL_P4, SL_P5, SL_P5, SL_P5, SL_P5, SL_P5, SL_P5},   /* s1 */
+                                  {SL_P4, SL_P4, SL_P4, SL_P6, SL_P6, SL_P6, SL_P4, SL_P4, SL_P4},   /* d1 */
+                                  {SL_P4, SL_P4, SL_P4, SL_P5, SL_P5, SL_P5, SL_P5, SL_P5, SL_P5}};  /* d2 */
+/* copy of a(d0,d1,d2,d3) (first index fastest) with index `dim` restricted to [lo, lo+w) */
+static double *slice4(const double *a, Integer d0, Integer d1, Integer d2, Integer d3, int dim, Integer lo, Integer w) {
+  Integer d[4] = {d0, d1, d2, d3}, n[4] = {d0, d1, d2, d3};
+  n[dim] = w;
+  double *out = (double *)malloc(sizeof(double) * (size_t)(n[0] * n[1] * n[2] * n[3] + 1));
+  for (Integer i3 = 0; i3 < n[3]; i3++)
+    for (Integer i2 = 0; i2 < n[2]; i2++)
+      for (Integer i1 = 0; i1 < n[1]; i1++)
+        for (Integer i0 = 0; i0 < n[0]; i0++) {
+          Integer s[4] = {i0, i1, i2, i3};
+          s[dim] += lo;
+          out[i0 + n[0] * (i1 + n[1] * (i2 + n[2] * i3))] = a[s[0] + d[0] * (s[1] + d[1] * (s[2] + d[2] * s[3]))];
+        }
+  return out;
+}
+
 /* generic entry points by (family, k): family 0 = s1, 1 = d1, 2 = d2; kd ignored for s1 */
 void ora_sd_t_kernel(Integer family, Integer k, Integer h3d, Integer h2d, Integer h1d, Integer p6d,
                      Integer p5d, Integer p4d, Integer kd, double *triplesx, const double *tsub,
@@ -156,6 +186,31 @@ void ora_sd_t_kernel(Integer family, Integer k, Integer h3d, Integer h2d, Intege
   if (family == 0) S1[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, triplesx, tsub, v2sub);
   else if (family == 1) D1[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
   else D2[k - 1](h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
+}
+
+/* kernel (family, K0) as the per-tuple drivers call it, honouring the p4 slab */
+static void call_kernel(int family, int K0, Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,
+                        Integer p4d, Integer kd, double *triplesx, const double *tsub, const double *v2sub) {
+  if (g_slab_hi < 0) {
+    ora_sd_t_kernel(family, K0 + 1, h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
+    return;
+  }
+  const Integer lo = g_slab_lo, w = g_slab_hi - g_slab_lo;
+  const int name = SLOWEST[family][K0];
+  double *ts = NULL, *vs = NULL;
+  const double *t = tsub, *v = v2sub;
+  if (family == 0) {        /* t1sub(p4,h1), v2sub(h3,h2,p6,p5) */
+    if (name == SL_P4) { ts = slice4(tsub, p4d, h1d, 1, 1, 0, lo, w); t = ts; p4d = w; }
+    else { v = v2sub + h3d * h2d * p6d * lo; p5d = w; }
+  } else if (family == 1) { /* t2sub(h7,p4,p5,h1), v2sub(h3,h2,p6,h7) */
+    if (name == SL_P4) { ts = slice4(tsub, kd, p4d, p5d, h1d, 1, lo, w); t = ts; p4d = w; }
+    else { vs = slice4(v2sub, h3d, h2d, p6d, kd, 2, lo, w); v = vs; p6d = w; }
+  } else {                  /* t2sub(p7,p4,h1,h2), v2sub(p7,h3,p6,p5) */
+    if (name == SL_P4) { ts = slice4(tsub, kd, p4d, h1d, h2d, 1, lo, w); t = ts; p4d = w; }
+    else { v = v2sub + kd * h3d * p6d * lo; p5d = w; }
+  }
+  ora_sd_t_kernel(family, K0 + 1, h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, t, v);
+  free(ts); free(vs);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -556,7 +611,7 @@ static void singles_body(const ora_ctx *c, double *a_c, Integer t_h1b, Integer t
           cnt->flops_s1 += 2.0 * (double)RANGE(p4b) * RANGE(p5b) * RANGE(p6b) * RANGE(h1b) * RANGE(h2b) * RANGE(h3b);
         }
         if (!dryrun && !tce_form)
-          S1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort);
+          call_kernel(0, K, RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), 1, a_c, k_a_sort, k_b_sort);
         if (!dryrun && tce_form) {
           /* ccsd_t_singles.F:185-240: permutation of (h3b,h2b,p6b,p5b,h1b,p4b) and sign of test K+1 */
           static const int PERM[9][6] = {{6, 4, 3, 5, 2, 1}, {6, 4, 3, 2, 5, 1}, {6, 4, 3, 2, 1, 5},
@@ -718,8 +773,8 @@ static void doubles_body(const ora_ctx *c, double *triplesx, Integer t_h1b, Inte
                                RANGE(h3b) * RANGE(h7b);
             }
             if (!dryrun && !tce_form)
-              D1[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b),
-                    triplesx, t2sub, v2sub);
+              call_kernel(1, K, RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b),
+                          triplesx, t2sub, v2sub);
             if (!dryrun && tce_form) { /* ccsd_t_doubles.F:189-191 (b sort), :195, :206-267 (perm, sign of test K+1) */
               static const int PERM[9][6] = {{6, 5, 3, 4, 2, 1}, {6, 5, 3, 2, 4, 1}, {6, 5, 3, 2, 1, 4},
                                              {3, 6, 5, 4, 2, 1}, {3, 6, 5, 2, 4, 1}, {3, 6, 5, 2, 1, 4},
@@ -769,8 +824,8 @@ static void doubles_body(const ora_ctx *c, double *triplesx, Integer t_h1b, Inte
                                RANGE(h3b) * RANGE(p7b);
             }
             if (!dryrun && !tce_form)
-              D2[K](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b),
-                    triplesx, t2sub, v2sub);
+              call_kernel(2, K, RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b),
+                          triplesx, t2sub, v2sub);
             if (!dryrun && tce_form) { /* ccsd_t_doubles.F:440-442 (b sort), :446, :457-520 */
               static const int PERM[9][6] = {{6, 3, 2, 5, 4, 1}, {6, 3, 2, 1, 5, 4}, {6, 3, 2, 5, 1, 4},
                                              {3, 6, 2, 5, 4, 1}, {3, 6, 2, 1, 5, 4}, {3, 6, 2, 5, 1, 4},
@@ -807,6 +862,29 @@ void ora_ccsd_t_loop(const ora_ctx *c, const Integer *tuple /* p4b,p5b,p6b,h1b,h
                  c->evl_sorted + c->offset[t_p5b - 1], c->evl_sorted + c->offset[t_p6b - 1], RANGE(t_h1b),
                  RANGE(t_h2b), RANGE(t_h3b), RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), &energy[0],
                  &energy[1]); /* :447 */
+}
+
+/* One tuple, p4 slab [lo,hi) of its t3 tile only: a_singles/a_doubles hold (hi-lo)*prod(other five ranges)
+ * doubles; the energies are the slab's share of the tuple's (the whole tuple = sum over disjoint slabs). */
+void ora_ccsd_t_loop_slab(const ora_ctx *c, const Integer *tuple, Integer lo, Integer hi, double *a_singles,
+                          double *a_doubles, double *energy /*[2], accumulated*/) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2];
+  const Integer t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  if (hi > RANGE(t_p4b)) hi = RANGE(t_p4b);
+  if (lo < 0) lo = 0;
+  if (hi <= lo) return;
+  const Integer size = (hi - lo) * RANGE(t_p5b) * RANGE(t_p6b) * RANGE(t_h1b) * RANGE(t_h2b) * RANGE(t_h3b);
+  memset(a_singles, 0, sizeof(double) * (size_t)size);
+  memset(a_doubles, 0, sizeof(double) * (size_t)size);
+  ora_set_p4_slab(lo, hi);
+  ora_ccsd_t_singles_l(c, a_singles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL);
+  ora_ccsd_t_doubles_l(c, a_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL);
+  ora_set_p4_slab(0, -1);
+  ora_ccsd_t_dot(a_singles, a_doubles, (int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b,
+                 c->evl_sorted + c->offset[t_h1b - 1], c->evl_sorted + c->offset[t_h2b - 1],
+                 c->evl_sorted + c->offset[t_h3b - 1], c->evl_sorted + c->offset[t_p4b - 1] + lo,
+                 c->evl_sorted + c->offset[t_p5b - 1], c->evl_sorted + c->offset[t_p6b - 1], RANGE(t_h1b),
+                 RANGE(t_h2b), RANGE(t_h3b), hi - lo, RANGE(t_p5b), RANGE(t_p6b), &energy[0], &energy[1]);
 }
 
 /* dry run of one tuple: call and flop counts only (SURVEY 8d "algorithmic FLOPs") */
