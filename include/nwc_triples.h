@@ -121,6 +121,14 @@ int nwc_ccsd_t_gpu_tuple(const nwc_tce_state *st, const Integer tuple_p4p5p6h1h2
 
 /* host-only helpers (no device): task list of ccsd_t_neword.F and a dry run of one tuple's dispatch */
 Integer nwc_host_task_list(const nwc_tce_state *st, Integer *klist7, Integer capacity_tasks);
+/* sorted unique block keys of store `which` (1 T1, 2 T2, 3 spin-orbital V2) read by the given tasks (ntasks x 6 tile
+ * ids): a caller can stage only those blocks on the host.  Returns their number (keys_out filled if cap suffices). */
+Integer nwc_host_collect_blocks(const nwc_tce_state *st, const Integer *tasks6, Integer ntasks, int which,
+                                Integer *keys_out, Integer cap);
+/* host-only view of nwc_triples_run_partition (below): ranges[2*i], ranges[2*i+1] = the sub-tile range of task
+ * first_task+i that `rank` of `nranks` runs (ntasks <= 0: to the end of the list; ranges holds 2*ntasks entries) */
+int nwc_host_block_partition(const nwc_tce_state *st, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                             long long *ranges);
 int nwc_host_count_tuple(const nwc_tce_state *st, const Integer tuple_p4p5p6h1h2h3[6], Integer calls_s1_d1_d2[3],
                          double flops_s1_d1_d2[3]);
 
@@ -256,6 +264,10 @@ int nwc_compat_timer_stop_ms(double *ms);
  * arena (default 150 GiB): beyond it a call fails with an error instead of exhausting the device */
 int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
 int nwc_triples_set_arena_cap(nwc_triples_ctx *ctx, size_t bytes);
+
+/* roofline denominator measured in-process: rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop on `device`
+ * (the FP64 tensor instruction of the K loop; MEASURED_PEAKS.json has no FP64 figure).  ~0.1 s. */
+int nwc_fp64_peak_probe(int device, double *dmma_tflops);
 
 /* multi-GPU: one process per GPU.  The host distributes the 128-byte id (MPI/GA broadcast in NWChem,
  * torch.distributed in bench.py), then every rank calls init; allreduce replaces ga_dgop (ccsd_t.F:297). */

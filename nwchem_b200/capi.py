@@ -439,6 +439,30 @@ def host_task_list(st):
     return kl[:n]
 
 
+def host_collect_blocks(st, tasks, which):
+    """Sorted unique block keys of store `which` (1 T1, 2 T2, 3 spin-orbital V2) the given tasks read (host only)."""
+    s, keep = make_state(st)
+    tt = np.ascontiguousarray(np.asarray(tasks, np.int64)[:, :6])
+    l = lib()
+    l.nwc_host_collect_blocks.restype = L
+    l.nwc_host_collect_blocks.argtypes = [C.POINTER(TceState), PL, L, C.c_int, PL, L]
+    n = int(l.nwc_host_collect_blocks(C.byref(s), _pl(tt), len(tt), which, None, 0))
+    if n < 0:
+        raise RuntimeError("nwc_host_collect_blocks failed")
+    out = np.zeros(max(n, 1), np.int64)
+    l.nwc_host_collect_blocks(C.byref(s), _pl(tt), len(tt), which, _pl(out), n)
+    return out[:n]
+
+
+def fp64_peak_probe(device=0) -> float:
+    v = C.c_double(0.0)
+    l = lib()
+    l.nwc_fp64_peak_probe.argtypes = [C.c_int, PD]
+    if l.nwc_fp64_peak_probe(device, C.byref(v)) != 0:
+        raise RuntimeError("nwc_fp64_peak_probe failed")
+    return float(v.value)
+
+
 def host_count_tuple(st, tup, state=None):
     s, keep = state if state is not None else make_state(st)
     calls = np.zeros(3, np.int64); flops = np.zeros(3)

@@ -7,6 +7,7 @@
 #include "engine.h"
 #include <cstring>
 #include <dlfcn.h>
+#include <algorithm>
 
 using namespace nwc;
 namespace nwc { Engine& compat_engine(); void compat_set_async_uploads(bool on); void compat_forget_uploads(); }
@@ -317,6 +318,73 @@ struct CountSink {
   }
 };
 }  // namespace
+
+namespace {
+struct CollectSink {   // block keys one tuple touches, per store
+  const HostState& S;
+  std::vector<Integer>* keys[3];   // T1, T2, V2
+  void singles(const Row&, Integer p4b_1, Integer h1b_1, Integer p5b_2, Integer p6b_2, Integer h2b_2, Integer h3b_2,
+               const bool[9]) {
+    keys[0]->push_back(t1_key(S, p4b_1, h1b_1));
+    keys[2]->push_back(v2_key(S, p5b_2, p6b_2, h2b_2, h3b_2));
+  }
+  void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool[9]) {
+    keys[1]->push_back(h7b < r.h1b ? t2_key(S, am[0], am[1], am[3], am[2]) : t2_key(S, am[0], am[1], am[2], am[3]));
+    keys[2]->push_back(v2_key(S, bm[1], bm[0], bm[2], bm[3]));
+  }
+  void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool[9]) {
+    keys[1]->push_back(p7b < r.p4b ? t2_key(S, am[1], am[0], am[2], am[3]) : t2_key(S, am[0], am[1], am[2], am[3]));
+    keys[2]->push_back(v2_key(S, bm[0], bm[1], bm[2], bm[3]));
+  }
+};
+}  // namespace
+
+// Sorted unique block keys of store `which` (1 T1, 2 T2, 3 spin-orbital V2) that the given tasks read: lets a caller
+// stage only those blocks on the host (st needs the tiling tables and the T1/T2 offset tables; no data, no device).
+// Returns the number of keys; keys_out (capacity `cap`) is filled when it is large enough.
+Integer nwc_host_collect_blocks(const nwc_tce_state* st, const Integer* tasks6, Integer ntasks, int which,
+                                Integer* keys_out, Integer cap) {
+  try {
+    HostState S;
+    S.load_tables(st);
+    std::vector<Integer> k[3];
+    CollectSink sink{S, {&k[0], &k[1], &k[2]}};
+    for (Integer i = 0; i < ntasks; i++) {
+      walk_singles(S, tasks6 + 6 * i, sink);
+      walk_doubles(S, tasks6 + 6 * i, sink);
+    }
+    if (which < 1 || which > 3) return -1;
+    std::vector<Integer>& v = k[which - 1];
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    if (keys_out && (Integer)v.size() <= cap) memcpy(keys_out, v.data(), v.size() * sizeof(Integer));
+    return (Integer)v.size();
+  } catch (const std::exception& ex) {
+    printf("%s\n", ex.what());
+    return -1;
+  }
+}
+
+// host-only view of nwc_triples_run_partition: ranges[2*i..] = sub-tile range of task first_task+i that `rank` runs
+int nwc_host_block_partition(const nwc_tce_state* st, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                             long long* ranges) {
+  try {
+    HostState S;
+    S.load_tables(st);
+    std::vector<Integer> kl;
+    build_task_list(S, kl);
+    const Integer nt = (Integer)(kl.size() / 7);
+    if (nranks < 1 || rank < 0 || rank >= nranks || first_task < 0 || first_task > nt) return 1;
+    if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
+    std::vector<long long> r;
+    block_partition(S, kl, rank, nranks, first_task, ntasks, r);
+    memcpy(ranges, r.data(), r.size() * sizeof(long long));
+    return 0;
+  } catch (const std::exception& ex) {
+    printf("%s\n", ex.what());
+    return 1;
+  }
+}
 
 // calls[3], flops[3] = fired sd_t_s1 / d1 / d2 kernels of one tuple and their algorithmic FLOPs
 int nwc_host_count_tuple(const nwc_tce_state* st, const Integer tuple[6], Integer calls[3], double flops[3]) {

@@ -302,6 +302,61 @@ inline double tuple_factor(const HostState& S, const Integer t[6]) {
   return f;
 }
 
+// dry walk: k4 planes of all fired contractions of one tuple -- the cost model of the static block partition
+struct CostSink {
+  const HostState& S;
+  long long planes = 0;
+  void singles(const Row&, Integer, Integer, Integer, Integer, Integer, Integer, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += 1;
+  }
+  void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(h7b) + 3) / 4;
+  }
+  void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(p7b) + 3) / 4;
+  }
+};
+
+inline long long tuple_sub_tiles(const HostState& S, const Integer t[6]) {
+  long long n = 1;
+  for (int q = 0; q < 6; q++) n *= (S.rg(t[q]) + 3) / 4;
+  return n;
+}
+
+// Static block partition of tasks [first, first+ntasks) of `klist` (rows of 7) over nranks: the tasks are laid end to
+// end, every 4^6 sub-tile weighted by the k4 planes its tuple contracts plus a constant for the per-sub-tile epilogue,
+// and rank r takes the r-th equal-cost contiguous piece.  ranges[2*i], ranges[2*i+1] = the sub-tile range
+// [item_lo, item_hi) of task first+i that `rank` runs (empty when lo == hi).  Pure integer arithmetic: every rank
+// derives the same cuts.
+inline void block_partition(const HostState& S, const std::vector<Integer>& klist, Integer rank, Integer nranks,
+                            Integer first, Integer ntasks, std::vector<long long>& ranges) {
+  const long long EPILOGUE_PLANES = 24;   // transfers, singles, energy of one sub-tile in units of one k4 plane
+  std::vector<long long> items((size_t)ntasks), w((size_t)ntasks);
+  std::vector<__int128> cum((size_t)ntasks + 1, 0);
+  for (Integer i = 0; i < ntasks; i++) {
+    const Integer* t = &klist[7 * (size_t)(first + i)];
+    CostSink cs{S};
+    walk_singles(S, t, cs);
+    walk_doubles(S, t, cs);
+    items[(size_t)i] = tuple_sub_tiles(S, t);
+    w[(size_t)i] = cs.planes + EPILOGUE_PLANES;
+    cum[(size_t)i + 1] = cum[(size_t)i] + (__int128)items[(size_t)i] * w[(size_t)i];
+  }
+  const __int128 total = cum[(size_t)ntasks];
+  const __int128 lo = total * rank / nranks, hi = total * (rank + 1) / nranks;
+  auto cut = [&](__int128 bound, Integer i) -> long long {   // first sub-tile of task i at or beyond `bound`
+    const __int128 rel = bound - cum[(size_t)i];
+    if (rel <= 0) return 0;
+    const __int128 q = (rel + w[(size_t)i] - 1) / w[(size_t)i];
+    return q > items[(size_t)i] ? items[(size_t)i] : (long long)q;
+  };
+  ranges.assign(2 * (size_t)ntasks, 0);
+  for (Integer i = 0; i < ntasks; i++) {
+    ranges[2 * (size_t)i] = cut(lo, i);
+    ranges[2 * (size_t)i + 1] = cut(hi, i);
+  }
+}
+
 // task enumeration + heaviest-first banding: ccsd_t_neword.F:42-217.  Rows of 7: 6 tile ids + weight.
 inline void build_task_list(const HostState& S, std::vector<Integer>& klist) {
   std::vector<Integer> aux;

@@ -317,21 +317,6 @@ struct Pipeline {
   void finish() { flush(); wait_prev(); }
 };
 
-// dry walk: planes (k4 steps) of all fired contractions of one tuple -- the cost model of the static partition
-struct CostSink {
-  const HostState& S;
-  long long planes = 0;
-  void singles(const Row&, Integer, Integer, Integer, Integer, Integer, Integer, const bool fire[9]) {
-    for (int k = 0; k < 9; k++) if (fire[k]) planes += 1;
-  }
-  void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) {
-    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(h7b) + 3) / 4;
-  }
-  void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
-    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(p7b) + 3) / 4;
-  }
-};
-
 int upload(double** dst, size_t* n_out, const double* src, size_t n, Engine* e) {
   if (*dst) { cudaFree(*dst); *dst = nullptr; }
   NWC_TRY(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(double)));
@@ -678,31 +663,11 @@ int nwc_triples_run_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, 
     energy[0] = energy[1] = 0.0;
     if (per_task) for (Integer i = 0; i < 2 * ntasks; i++) per_task[i] = 0.0;
     if (ntasks <= 0) return 0;
-    const long long EPILOGUE_PLANES = 24;   // per-sub-tile fixed work (transfers, singles, energy) in units of one k4 plane
-    std::vector<long long> items((size_t)ntasks), w((size_t)ntasks);
-    std::vector<__int128> cum((size_t)ntasks + 1, 0);
-    for (Integer i = 0; i < ntasks; i++) {
-      const Integer* t = &c->klist[7 * (first_task + i)];
-      int R[6];
-      tuple_ranges(S, t, R);
-      CostSink cs{S};
-      walk_singles(S, t, cs);
-      walk_doubles(S, t, cs);
-      items[(size_t)i] = Engine::tuple_items(R);
-      w[(size_t)i] = cs.planes + EPILOGUE_PLANES;
-      cum[(size_t)i + 1] = cum[(size_t)i] + (__int128)items[(size_t)i] * w[(size_t)i];
-    }
-    const __int128 total = cum[(size_t)ntasks];
-    const __int128 lo = total * rank / nranks, hi = total * (rank + 1) / nranks;
-    auto cut = [&](__int128 bound, Integer i) -> long long {   // first sub-tile of task i at or beyond `bound`
-      const __int128 rel = bound - cum[(size_t)i];
-      if (rel <= 0) return 0;
-      const __int128 q = (rel + w[(size_t)i] - 1) / w[(size_t)i];
-      return q > items[(size_t)i] ? items[(size_t)i] : (long long)q;
-    };
+    std::vector<long long> ranges;
+    block_partition(S, c->klist, rank, nranks, first_task, ntasks, ranges);
     Pipeline pipe(c, energy, per_task);
     for (Integer i = 0; i < ntasks; i++) {
-      const long long a = cut(lo, i), b = cut(hi, i);
+      const long long a = ranges[2 * (size_t)i], b = ranges[2 * (size_t)i + 1];
       if (b <= a) continue;
       emit_tuple(c, &c->klist[7 * (first_task + i)], a, b);
       pipe.emitted(i);

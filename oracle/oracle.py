@@ -237,6 +237,18 @@ def kernel(family, k, dims_perm, kd, triplesx, tsub, v2sub):
                       _pd(triplesx), _pd(tsub), _pd(v2sub))
 
 
+def kernel_slab(family, k, dims_perm, kd, lo, hi, triplesx, tsub, v2sub):
+    """One of the 27 CPU kernels restricted to the p4 slab [lo,hi) of the TASK tuple's tile; triplesx holds the slab."""
+    l = lib()
+    h3d, h2d, h1d, p6d, p5d, p4d = [int(x) for x in dims_perm]
+    l.ora_sd_t_kernel_slab(L(family), L(k), L(h3d), L(h2d), L(h1d), L(p6d), L(p5d), L(p4d), L(int(kd)), L(lo), L(hi),
+                           _pd(triplesx), _pd(tsub), _pd(v2sub))
+
+
+def set_num_threads(n):
+    lib().ora_set_num_threads(int(n))
+
+
 def tile_group(n, isize):
     l = lib()
     out = np.zeros(max(n, 1), np.int64)

@@ -1099,6 +1099,24 @@ void ora_dgemm_tn(Integer m, Integer n, Integer k, const double *a /*k x m*/, co
     }
 }
 
+/* thread count of the OpenMP loops (bench.py: torch.distributed.run exports OMP_NUM_THREADS=1) */
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* one kernel on the p4 slab [lo,hi) of the task tuple's tile (timing samples of bench.py) */
+void ora_sd_t_kernel_slab(Integer family, Integer k, Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,
+                          Integer p4d, Integer kd, Integer lo, Integer hi, double *triplesx, const double *tsub,
+                          const double *v2sub) {
+  ora_set_p4_slab(lo, hi);
+  call_kernel((int)family, (int)k - 1, h3d, h2d, h1d, p6d, p5d, p4d, kd, triplesx, tsub, v2sub);
+  ora_set_p4_slab(0, -1);
+}
+
 int ora_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
