@@ -5,9 +5,10 @@ Default workload (config.workload) = BASELINE.json's target shape, (H2O)10/aug-c
 virtual alpha orbitals, tilesize 40, 7 590 tile tuples, 4.5e17 FLOP): the block stores are generated ON THE DEVICE
 (keyed hash, no store ever on the host), V2 in the reference's spin-free `2eorb` form (105 GB; the spin-orbital form
 would be 527 GB), resident whole on one GPU and sharded over the N GPUs otherwise, remote blocks pulled over NVLink.
-A step = one pass of the hot path over the SAME fixed prefix of the heaviest-first task list at every N (--tasks, the
-whole list does not fit the per-N time limit: 4.5e17 FLOP ~ 4 h on one GPU), partitioned over the ranks in equal-cost
-contiguous blocks (strong scaling), one ncclAllReduce of the two energies per step (ga_dgop, ccsd_t.F:297).
+A step = one pass of the hot path over the SAME fixed sample of the heaviest-first task list at every N (--tasks M:
+tasks floor(i*7590/M), i < M -- diagonal, off-diagonal, 40- and 39-wide tiles in the list's proportions; the whole list
+does not fit the per-N time limit: 4.5e17 FLOP ~ 3.7 h on one GPU), partitioned over the ranks in equal-cost contiguous
+blocks (strong scaling), one ncclAllReduce of the two energies per step (ga_dgop, ccsd_t.F:297).
 
   value : whole-job GFLOP/s (algorithmic FLOPs of SURVEY 8d / device time, CUDA events on the library's stream, max
           over ranks), stores resident in HBM (Tier 2 / native API)
@@ -39,7 +40,7 @@ SEED = 20240229
 GOLDEN = os.path.join(ROOT, "tests", "golden", "bench_energies.json")
 # per workload: storage, default task prefix (0 = whole list), generator scales (t1, t2, v2) chosen so |E| = O(1) Eh
 WORKLOADS = {
-    "h2o10_augccpvtz": dict(intorb=True, tasks=6, scale=(1e-3, 5e-5, 5e-3), device_gen=True,
+    "h2o10_augccpvtz": dict(intorb=True, tasks=8, scale=(1e-3, 5e-5, 5e-3), device_gen=True,
                             what="(H2O)10/aug-cc-pVTZ-shaped: alpha occ/virt 40/870, tilesize 40 (2+44 tiles, 7590 tuples)"),
     "benzene_dimer_augccpvtz": dict(intorb=True, tasks=12, scale=(1e-3, 5e-5, 5e-3), device_gen=True,
                                     what="benzene-dimer/aug-cc-pVTZ-shaped: alpha occ/virt 30/786, tilesize 40 (2+40 tiles, 5740 tuples)"),
@@ -145,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="h2o10_augccpvtz", choices=sorted(WORKLOADS))
-    ap.add_argument("--tasks", type=int, default=-1, help="prefix of the heaviest-first task list run per step (0 = whole list)")
+    ap.add_argument("--tasks", type=int, default=-1, help="size M of the strided sample of the heaviest-first task list run per step (0 = whole list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicated", action="store_true", help="N > 1: keep the whole V2 store on every GPU instead of sharding it")
@@ -240,15 +241,16 @@ def main():
     tr.set_batch_bytes(6 << 30)
     ntot = tr.num_tasks
     ntasks = ntot if ntasks_req <= 0 else min(ntasks_req, ntot)
-    tasks = tr.task_list()[:ntasks]
+    ids = np.array([(i * ntot) // ntasks for i in range(ntasks)], np.int64)   # strided sample, the same at every N
+    tasks = tr.task_list()[ids]
     setup_s = time.perf_counter() - t_setup
     resident_gb = tr.stats()["resident_bytes"] * 1e-9
 
     def step():
         if a.weak or world == 1:
-            e1, e2 = tr.run_partition(0, 1, 0, ntasks)
+            e1, e2 = tr.run_partition_list(0, 1, ids)
         else:
-            e1, e2 = tr.run_partition(rank, world, 0, ntasks)
+            e1, e2 = tr.run_partition_list(rank, world, ids)
         if world > 1 and not a.weak:
             e1, e2 = tr.allreduce(e1, e2)   # replaces ga_dgop (ccsd_t.F:297)
         return e1, e2
@@ -293,7 +295,7 @@ def main():
                   "pull_ms_per_step_max_rank": pm / a.steps}
 
     # ---- energies: reproducible step to step, and equal to the N=1 energies of the same prefix ----
-    key = f"{a.workload}:tasks={ntasks}:seed={SEED}"
+    key = f"{a.workload}:sample={ntasks}of{ntot}:seed={SEED}"
     golden = {}
     try:
         golden = json.load(open(GOLDEN))
@@ -336,7 +338,7 @@ def main():
     if not a.no_e2e:
         import ctypes
         capi.lib().nwc_triples_set_local_rank(ctypes.c_long(local))
-        nrep = max(1, min(a.steps, 2))
+        nrep = 1 if len(my_tasks) >= 6 else max(1, min(a.steps, 2))
 
         def tier1(reference_contract):
             capi.set_reference_contract(reference_contract)
@@ -401,12 +403,12 @@ def main():
 
     if rank == 0:
         cfg = {"workload": f"{a.workload}: {W['what']}; " +
-                           (f"first {ntasks} of {ntot} tuples of the heaviest-first list per step" if ntasks < ntot else f"all {ntot} tuples per step"),
+                           (f"strided sample of {ntasks} of the {ntot} tuples of the heaviest-first list per step (tasks floor(i*{ntot}/{ntasks}))" if ntasks < ntot else f"all {ntot} tuples per step"),
                "tilesize": 40, "tasks_per_step": int(ntasks),
                "v2": ("2eorb (spin-free orbital form, antisymmetrised on the device per batch)" if W["intorb"] else "spin-orbital blocks") +
                      (f", sharded over {world} GPUs, remote blocks pulled over NVLink" if sharded else ", whole store resident on every GPU"),
                "stores": "generated on the device (keyed hash)" if W["device_gen"] else "host random blocks uploaded once",
-               "resident_GB_per_gpu": resident_gb, "setup_s": setup_s,
+               "resident_GB_per_gpu": resident_gb, "setup_s": setup_s, "panel_index_order": tr.order,
                "partition": "weak: replicas" if a.weak else "strong: equal-cost contiguous blocks of the task prefix, boundary tuples split at sub-tile granularity",
                "l2": "operand panels per tuple (>= 1.4 GB) exceed the 126 MB L2; no explicit flush"}
         line = {"metric": "(T) FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps,
@@ -414,6 +416,7 @@ def main():
                 "scaling": "weak" if a.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "wall_s_per_step": ms_max / a.steps * 1e-3, "flops_per_step": flops_all / a.steps,
                 "frac_of_fp64_peak": value * 1e-3 / (peak * world), "energy": list(e), "energy_check": energy_check,
+                "full_list_extrapolated_s": (4.5208e17 / (value * 1e9)) if a.workload == "h2o10_augccpvtz" else None,
                 "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))

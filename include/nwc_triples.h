@@ -184,6 +184,10 @@ int nwc_triples_run(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer
  * rank's possibly partial per-task energies. */
 int nwc_triples_run_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
                               double energy[2], double *per_task);
+/* the same for an explicit list of n task indices (e.g. a strided sample of the list), partitioned in the order given;
+ * per_task is indexed by position in the list */
+int nwc_triples_run_partition_list(nwc_triples_ctx *ctx, Integer rank, Integer nranks, const Integer *task_ids, Integer n,
+                                   double energy[2], double *per_task);
 /* one tuple restricted to sub-tiles [item_lo, item_hi) of its linear sub-tile order (4-wide blocks, h3 block fastest,
  * p4 block slowest; nwc_triples_tuple_items = their number): e.g. the p4 slab [4a,4b) of the t3 tile is
  * [a*m, b*m), m = items / ceil(range(p4)/4).  Energies of disjoint ranges add up to the tuple's. */
@@ -264,6 +268,9 @@ int nwc_compat_timer_stop_ms(double *ms);
  * arena (default 150 GiB): beyond it a call fails with an error instead of exhausting the device */
 int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
 int nwc_triples_set_arena_cap(nwc_triples_ctx *ctx, size_t bytes);
+/* index order inside the operand panels chosen for this tiling: 0 holes first, 1 particles first (the less ragged tile
+ * type goes first so that more padding rows can be skipped; env NWC_ORDER overrides) */
+int nwc_triples_get_order(nwc_triples_ctx *ctx);
 
 /* roofline denominator measured in-process: rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop on `device`
  * (the FP64 tensor instruction of the K loop; MEASURED_PEAKS.json has no FP64 figure).  ~0.1 s. */

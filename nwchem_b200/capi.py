@@ -252,6 +252,17 @@ class Triples:
                "nwc_triples_run_partition")
         return (float(e[0]), float(e[1]), pt[:n]) if per_task else (float(e[0]), float(e[1]))
 
+    def run_partition_list(self, rank: int, world: int, task_ids, per_task=False):
+        """Like run_partition for an explicit list of task indices (partitioned in the order given)."""
+        ids = np.ascontiguousarray(task_ids, np.int64)
+        e = np.zeros(2)
+        pt = np.zeros((max(len(ids), 1), 2)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_partition_list.argtypes = [C.c_void_p, L, L, PL, L, PD, PD]
+        _check(l.nwc_triples_run_partition_list(self._h, rank, world, _pl(ids), len(ids), _pd(e), _pd(pt) if per_task else None),
+               "nwc_triples_run_partition_list")
+        return (float(e[0]), float(e[1]), pt[:len(ids)]) if per_task else (float(e[0]), float(e[1]))
+
     def tuple_items(self, tup) -> int:
         tt = np.array(tup, np.int64)
         return int(lib().nwc_triples_tuple_items(self._h, _pl(tt)))
@@ -262,6 +273,11 @@ class Triples:
         e = np.zeros(2)
         _check(lib().nwc_triples_run_items(self._h, _pl(tt), item_lo, item_hi, _pd(e)), "nwc_triples_run_items")
         return float(e[0]), float(e[1])
+
+    @property
+    def order(self) -> int:
+        lib().nwc_triples_get_order.argtypes = [C.c_void_p]
+        return int(lib().nwc_triples_get_order(self._h))
 
     def set_arena_cap(self, n):
         lib().nwc_triples_set_arena_cap(self._h, int(n))

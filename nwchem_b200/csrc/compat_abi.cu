@@ -20,8 +20,12 @@ bool g_async_uploads = false;   // caller promises pinned sources stay untouched
 // Under that promise an operand passed again (same host pointer and length) within the tuple is the same data:
 // the device copy and the repacked panels are reused.  The reference re-uploads the same sorted block for each
 // of the up to nine kernels one operand pair fires (ccsd_t_doubles_gpu.F:357-715).
-struct Uploaded { const double* host; size_t n; const double* dev; std::vector<PanelSlot> panels; };
+struct Uploaded { const double* host; size_t n; const double* dev; };
 std::vector<Uploaded> g_uploaded;
+// Within a tuple every call of one kernel sd_t_d1_K / sd_t_d2_K belongs to the same row of the permutation table (same
+// external ranges, one call per h7b / p7b tile), so the calls are collected per (family, K) and become ONE contraction
+// group at compute_en_: their K ranges are concatenated and padded once (engine.h Segment).
+std::vector<Segment> g_groups[2][9];
 
 // reference error behaviour: print and exit(1) (src/tce/ccsd_t/header.h:27-37)
 [[noreturn]] void die(const char* msg) {
@@ -128,12 +132,18 @@ void open_tuple(Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer*
   memcpy(g_R, R, sizeof(R));
   g_have_R = true;
   g_uploaded.clear();
+  for (auto& fam : g_groups) for (auto& g : fam) g.clear();
+  {   // panel index order that wastes the fewest DMMAs on this tuple's padding (engine.h set_order)
+    const char* env = getenv("NWC_ORDER");
+    int order = (env && (*env == '0' || *env == '1')) ? *env - '0'
+                                                      : (Engine::padding_cost(R, 1) < 0.995 * Engine::padding_cost(R, 0) ? 1 : 0);
+    e.set_order(order);
+  }
   e.begin_tuple(R);
 }
 
-const double* to_device(const double* host, size_t n, std::vector<PanelSlot>** panels = nullptr) {
+const double* to_device(const double* host, size_t n) {
   Engine& e = eng();
-  if (panels) *panels = nullptr;
   // The opt-in promise (nwc_compat_set_async_uploads) covers PINNED operands only: such an operand stays untouched until
   // compute_en_ returns, so (i) it is read by DMA in place and (ii) the same (pointer, length) passed again within the
   // tuple is the same data and its device copy and panels are reused.  A pageable buffer -- e.g. the reference's MA
@@ -141,16 +151,12 @@ const double* to_device(const double* host, size_t n, std::vector<PanelSlot>** p
   const bool promised = g_async_uploads && is_pinned(host);
   if (promised) {
     for (auto& u : g_uploaded)
-      if (u.host == host && u.n == n) { if (panels) *panels = &u.panels; return u.dev; }
+      if (u.host == host && u.n == n) return u.dev;
   }
   double* d = (double*)e.arena().alloc(n * sizeof(double));
   if (promised) {
     NWC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, e.stream()));
-    if (g_uploaded.capacity() < 4096) g_uploaded.reserve(4096);   // panel-cache pointers must stay valid
-    if (g_uploaded.size() < 4096) {
-      g_uploaded.push_back(Uploaded{host, n, d, {}});
-      if (panels) *panels = &g_uploaded.back().panels;
-    }
+    if (g_uploaded.size() < 65536) g_uploaded.push_back(Uploaded{host, n, d});
   } else {
     // reference contract: the caller may reuse `host` as soon as we return
     char* stage = g_stage.acquire(n * sizeof(double), e.stream());
@@ -190,13 +196,14 @@ void d1(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* h7d, Integer*
   const Integer K = *h7d;
   check_dims(1, k0, d);
   OperandView t, v;
-  std::vector<PanelSlot>*tc, *vc;
-  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_P5] * d[N_H1]), &tc);    // t2sub(h7,p4,p5,h1)
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_P5] * d[N_H1]));         // t2sub(h7,p4,p5,h1)
   t.kstride = 1; t.stride[N_P4] = K; t.stride[N_P5] = K * d[N_P4]; t.stride[N_H1] = K * d[N_P4] * d[N_P5];
-  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * K), &vc);    // v2sub(h3,h2,p6,h7)
+  v.base = to_device(v2sub, (size_t)(d[N_H3] * d[N_H2] * d[N_P6] * K));         // v2sub(h3,h2,p6,h7)
   v.stride[N_H3] = 1; v.stride[N_H2] = d[N_H3]; v.stride[N_P6] = d[N_H3] * d[N_H2];
   v.kstride = d[N_H3] * d[N_H2] * d[N_P6];
-  eng().add_contraction(1, k0, (int)K, t, v, 1.0, tc, vc);
+  Segment sg;
+  sg.K = (int)K; sg.t = t; sg.v = v;
+  g_groups[0][k0].push_back(sg);
 }
 
 void d2(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer* p5d, Integer* p6d, Integer* p7d,
@@ -206,12 +213,13 @@ void d2(int k0, Integer* h1d, Integer* h2d, Integer* h3d, Integer* p4d, Integer*
   const Integer K = *p7d;
   check_dims(2, k0, d);
   OperandView t, v;
-  std::vector<PanelSlot>*tc, *vc;
-  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_H1] * d[N_H2]), &tc);    // t2sub(p7,p4,h1,h2)
+  t.base = to_device(t2sub, (size_t)(K * d[N_P4] * d[N_H1] * d[N_H2]));         // t2sub(p7,p4,h1,h2)
   t.kstride = 1; t.stride[N_P4] = K; t.stride[N_H1] = K * d[N_P4]; t.stride[N_H2] = K * d[N_P4] * d[N_H1];
-  v.base = to_device(v2sub, (size_t)(K * d[N_H3] * d[N_P6] * d[N_P5]), &vc);    // v2sub(p7,h3,p6,p5)
+  v.base = to_device(v2sub, (size_t)(K * d[N_H3] * d[N_P6] * d[N_P5]));         // v2sub(p7,h3,p6,p5)
   v.kstride = 1; v.stride[N_H3] = K; v.stride[N_P6] = K * d[N_H3]; v.stride[N_P5] = K * d[N_H3] * d[N_P6];
-  eng().add_contraction(2, k0, (int)K, t, v, 1.0, tc, vc);
+  Segment sg;
+  sg.K = (int)K; sg.t = t; sg.v = v;
+  g_groups[1][k0].push_back(sg);
 }
 
 void finish(double* factor, double* energy, double* eval_h1, double* eval_h2, double* eval_h3, double* eval_p4,
@@ -226,6 +234,14 @@ void finish(double* factor, double* energy, double* eval_h1, double* eval_h2, do
   for (int i = 0; i < 6; i++) {
     if ((int)n[i] != want[i]) die("nwc_triples: compute_en: ranges differ from dev_mem_*");
     dv[i] = to_device(hv[i], (size_t)n[i]);
+  }
+  {   // the collected calls become contraction groups; kernels fed the same device blocks share panels
+    std::vector<GroupPanel> tc, vc;
+    for (int f = 0; f < 2; f++)
+      for (int k = 0; k < 9; k++) {
+        if (!g_groups[f][k].empty()) e.add_contraction_group(f + 1, k, g_groups[f][k].data(), (int)g_groups[f][k].size(), &tc, &vc);
+        g_groups[f][k].clear();
+      }
   }
   e.end_tuple(dv, *factor);
   double out[2] = {0, 0};

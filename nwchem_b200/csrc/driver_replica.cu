@@ -151,6 +151,7 @@ struct CompatSink {
     for (int k = 0; k < 9; k++)
       if (fire[k]) g_api.d2[k](&h1d, &h2d, &h3d, &p4d, &p5d, &p6d, &p7d, nullptr, a_sort, const_cast<double*>(v));
   }
+  void row_end(int) {}   // the Fortran calls the kernels tile by tile; the library concatenates them itself
 };
 
 // one task: ccsd_t_gpu.F:114-230
@@ -316,6 +317,7 @@ struct CountSink {
   void d2_pair(const Row& r, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
     for (int k = 0; k < 9; k++) if (fire[k]) { calls[2]++; flops[2] += 2.0 * prod(r) * S.rg(p7b); }
   }
+  void row_end(int) {}
 };
 }  // namespace
 
@@ -336,6 +338,7 @@ struct CollectSink {   // block keys one tuple touches, per store
     keys[1]->push_back(p7b < r.p4b ? t2_key(S, am[1], am[0], am[2], am[3]) : t2_key(S, am[0], am[1], am[2], am[3]));
     keys[2]->push_back(v2_key(S, bm[0], bm[1], bm[2], bm[3]));
   }
+  void row_end(int) {}
 };
 }  // namespace
 
@@ -377,7 +380,9 @@ int nwc_host_block_partition(const nwc_tce_state* st, Integer rank, Integer nran
     if (nranks < 1 || rank < 0 || rank >= nranks || first_task < 0 || first_task > nt) return 1;
     if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
     std::vector<long long> r;
-    block_partition(S, kl, rank, nranks, first_task, ntasks, r);
+    std::vector<Integer> ids;
+    for (Integer i = 0; i < ntasks; i++) ids.push_back(first_task + i);
+    block_partition(S, kl, rank, nranks, ids, r);
     memcpy(ranges, r.data(), r.size() * sizeof(long long));
     return 0;
   } catch (const std::exception& ex) {

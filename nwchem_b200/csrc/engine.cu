@@ -93,6 +93,37 @@ void Engine::abort() {
   for (Slot& s : slots_) { s.arena.reset(); s.busy = false; s.ntuples = 0; s.h_stage_off = 0; s.timed[0] = s.timed[1] = s.timed[2] = false; }
 }
 
+void Engine::set_order(int order) {
+  order = order ? 1 : 0;
+  if (order == order_) return;
+  if (open_ || !tuples_.empty() || !jobs_.empty()) throw Error("nwc_triples: the panel index order cannot change inside a batch");
+  order_ = order;
+}
+
+// Fraction of the padded 8x8 blocks the K loops execute: an index with n in-range values in a 4-wide block keeps
+// 1 (first in its group), ceil(n/2)/2 (second) or n/4 (third) of the rows; summed over the blocks of each range and
+// multiplied over the six indices of each split.  Divided by the same with every n/4 it is the executed / useful ratio.
+double Engine::padding_cost(const int R[6], int order) {
+  auto S = [](int range, int role) {
+    const int nb = (range + 3) / 4;
+    double tot = 0;
+    for (int b = 0; b < nb; b++) {
+      const int n = range - 4 * b < 4 ? range - 4 * b : 4;
+      tot += role == 0 ? 1.0 : role == 1 ? ((n + 1) / 2) / 2.0 : n / 4.0;
+    }
+    return tot / nb;
+  };
+  double ex = 0, ideal = 1;
+  for (int q = 0; q < 6; q++) ideal *= S(R[q], 2);
+  for (int s = 0; s < 9; s++) {
+    const Split sp = make_split(s, order);
+    double e = 1;
+    for (int r = 0; r < 3; r++) e *= S(R[sp.g1[r]], r) * S(R[sp.g2[r]], r);
+    ex += e;
+  }
+  return ex / (9.0 * ideal);
+}
+
 void Engine::begin_tuple(const int R_phys[6]) {
   if (open_) throw Error("nwc_triples: begin_tuple while a tuple is open");
   if (slots_[cur_].busy) throw Error("nwc_triples: the batch slot being built is still in flight (collect it first)");
@@ -119,54 +150,68 @@ long long Engine::tuple_items(const int R_phys[6]) {
   return items;
 }
 
-void Engine::add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale,
-                             std::vector<PanelSlot>* t_cache, std::vector<PanelSlot>* v_cache) {
+void Engine::add_contraction_group(int family, int k0, const Segment* segs, int nseg, std::vector<GroupPanel>* t_cache,
+                                   std::vector<GroupPanel>* v_cache) {
   if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8) throw Error("nwc_triples: bad add_contraction");
   // which operand is the G1 (one particle + two holes) one, and the singleton names
   const bool t_is_g1 = (family == 2);
   const int pa = pos_of(family, k0, family == 2 ? N_P4 : N_P6);
   const int hb = pos_of(family, k0, family == 2 ? N_H3 : N_H1);
   const int s = split_id(pa, hb);
-  const Split sp = make_split(s);
-  const OperandView& g1 = t_is_g1 ? tsub : v2sub;
-  const OperandView& g2 = t_is_g1 ? v2sub : tsub;
+  const Split sp = make_split(s, order_);
   const int n1[3] = {DECL[family][k0][sp.g1[0]], DECL[family][k0][sp.g1[1]], DECL[family][k0][sp.g1[2]]};
   const int n2[3] = {DECL[family][k0][sp.g2[0]], DECL[family][k0][sp.g2[1]], DECL[family][k0][sp.g2[2]]};
   const int p1[3] = {sp.g1[0], sp.g1[1], sp.g1[2]}, p2[3] = {sp.g2[0], sp.g2[1], sp.g2[2]};
-  std::vector<PanelSlot>* c1 = t_is_g1 ? t_cache : v_cache;
-  std::vector<PanelSlot>* c2 = t_is_g1 ? v_cache : t_cache;
-  if (K7 <= 0) return;
-  auto make_job = [&](const OperandView& op, const int nm[3], const int ps[3], double scale) -> const double* {
-    RepackJob j;
-    j.src = op.base;
-    j.s1 = op.stride[nm[0]]; j.s2 = op.stride[nm[1]]; j.s3 = op.stride[nm[2]]; j.sk = op.kstride;
-    j.X1 = cur_hdr_.R[ps[0]]; j.X2 = cur_hdr_.R[ps[1]]; j.X3 = cur_hdr_.R[ps[2]]; j.K = K7;
-    j.scale = scale;
-    const long long n = panel_doubles(j.X1, j.X2, j.X3, j.K);
-    j.dst = (double*)arena().alloc((size_t)n * sizeof(double));
-    max_panel_ = std::max(max_panel_, n);
-    jobs_.push_back(j);
-    return j.dst;
-  };
-  auto get_panel = [&](std::vector<PanelSlot>* cache, const OperandView& op, const int nm[3], const int ps[3],
-                       double scale) -> const double* {
+  std::vector<GroupPanel>* c1 = t_is_g1 ? t_cache : v_cache;
+  std::vector<GroupPanel>* c2 = t_is_g1 ? v_cache : t_cache;
+  long long Ktot = 0;
+  for (int i = 0; i < nseg; i++) Ktot += segs[i].K > 0 ? segs[i].K : 0;
+  if (Ktot <= 0) return;
+  if (Ktot > 2000000) throw Error("nwc_triples: contracted range too long");
+  // one panel per operand for the whole group, one repack job per segment
+  auto build = [&](bool is_g1, const int nm[3], const int ps[3], std::vector<GroupPanel>* cache) -> const double* {
+    const bool is_t = (is_g1 == t_is_g1);
     if (cache)
-      for (const PanelSlot& sl : *cache)
-        if (sl.names[0] == nm[0] && sl.names[1] == nm[1] && sl.names[2] == nm[2]) return sl.p;
-    PanelSlot sl;
-    sl.p = make_job(op, nm, ps, scale);
-    sl.names[0] = nm[0]; sl.names[1] = nm[1]; sl.names[2] = nm[2];
-    if (cache) cache->push_back(sl);
-    return sl.p;
+      for (const GroupPanel& gp : *cache) {
+        if (gp.names[0] != nm[0] || gp.names[1] != nm[1] || gp.names[2] != nm[2] || (int)gp.bases.size() != nseg) continue;
+        bool same = true;
+        for (int i = 0; i < nseg && same; i++)
+          same = gp.bases[(size_t)i] == (is_t ? segs[i].t.base : segs[i].v.base) && gp.scales[(size_t)i] == (is_t ? segs[i].tscale : 1.0);
+        if (same) return gp.p;
+      }
+    const int X1 = cur_hdr_.R[ps[0]], X2 = cur_hdr_.R[ps[1]], X3 = cur_hdr_.R[ps[2]];
+    const long long n = panel_doubles(X1, X2, X3, (int)Ktot);
+    double* dst = (double*)arena().alloc((size_t)n * sizeof(double));
+    GroupPanel gp;
+    gp.p = dst; gp.names[0] = nm[0]; gp.names[1] = nm[1]; gp.names[2] = nm[2];
+    int k_off = 0, last = -1;
+    for (int i = 0; i < nseg; i++) if (segs[i].K > 0) last = i;
+    for (int i = 0; i < nseg; i++) {
+      const OperandView& op = is_t ? segs[i].t : segs[i].v;
+      gp.bases.push_back(op.base);
+      gp.scales.push_back(is_t ? segs[i].tscale : 1.0);
+      if (segs[i].K <= 0) continue;
+      RepackJob j;
+      j.src = op.base; j.dst = dst;
+      j.s1 = op.stride[nm[0]]; j.s2 = op.stride[nm[1]]; j.s3 = op.stride[nm[2]]; j.sk = op.kstride;
+      j.X1 = X1; j.X2 = X2; j.X3 = X3; j.K = segs[i].K;
+      j.k_off = k_off;
+      j.k_end = (i == last) ? (int)((Ktot + 4 * KPL - 1) / (4 * KPL)) * 4 * KPL : k_off + segs[i].K;
+      j.scale = is_t ? segs[i].tscale : 1.0;
+      max_panel_ = std::max(max_panel_, panel_doubles(X1, X2, X3, j.k_end - (j.k_off / (4 * KPL)) * 4 * KPL));
+      jobs_.push_back(j);
+      k_off += segs[i].K;
+    }
+    if (cache) cache->push_back(gp);
+    return dst;
   };
-  const double* g1p = get_panel(c1, g1, n1, p1, t_is_g1 ? tscale : 1.0);
-  const double* g2p = get_panel(c2, g2, n2, p2, t_is_g1 ? 1.0 : tscale);
   ContrDesc d;
-  d.g1 = g1p; d.g2 = g2p;
-  d.nk4 = (K7 + 3) / 4;
+  d.g1 = build(true, n1, p1, c1);
+  d.g2 = build(false, n2, p2, c2);
+  d.nk4 = (int)((Ktot + 3) / 4);
   d.neg = SIGN[family][k0] < 0 ? 1 : 0;
   cur_descs_[s].push_back(d);
-  cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R) * K7;   // FLOPs of the whole tuple, parked here until end_tuple
+  cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R) * (double)Ktot;   // FLOPs of the whole tuple, parked here until end_tuple
 }
 
 void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub) {
@@ -323,13 +368,13 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[4], stream_));
   if (dump_doubles)
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
-                      (double2*)(dm + o_p), items_, dump_doubles, dump_singles, stream_);
+                      (double2*)(dm + o_p), items_, dump_doubles, dump_singles, order_, stream_);
   else {
     bool ragged = false;
     for (const TupleHdr& t : tuples_)
       for (int q = 0; q < 6; q++) ragged = ragged || (t.R[q] % SB != 0);
     launch_fused((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
-                 (double2*)(dm + o_p), items_, ragged, stream_);
+                 (double2*)(dm + o_p), items_, ragged, order_, stream_);
   }
   NWC_CUDA(cudaGetLastError());
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[5], stream_));

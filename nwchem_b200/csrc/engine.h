@@ -38,7 +38,7 @@ class Arena {
   void release();          // cudaFree everything
   size_t used() const { return used_; }
   size_t capacity() const;
-  size_t min_chunk = (size_t)256 << 20;
+  size_t min_chunk = (size_t)1 << 30;   // few, large chunks: cudaMalloc synchronises the device, so growth must stop early
   size_t max_bytes = (size_t)150 << 30;   // growth cap: beyond it alloc() throws instead of driving the GPU out of memory
  private:
   struct Chunk { char* base; size_t size; size_t off; };
@@ -53,11 +53,22 @@ struct OperandView {
   long long kstride = 0;
 };
 
-// a built panel and the permuted-name order of its (x1,x2,x3); lets the native tier share one panel
-// between the several kernels one operand pair fires on diagonal tuples
-struct PanelSlot {
+// One contracted tile of a contraction group: sd_t_d1_K / sd_t_d2_K called for one h7b / p7b tile.  All calls of one
+// kernel K within a tuple hit the same split with the same external ranges, so their K ranges are concatenated into
+// ONE panel pair and one descriptor: K is padded to a multiple of 8 once per group instead of once per tile
+// (uracil: 5 x 38/39 -> 192 instead of 200 k values).
+struct Segment {
+  int K = 0;
+  OperandView t, v;
+  double tscale = 1.0;
+};
+// a built group panel: permuted-name order of its (x1,x2,x3) and the source block of every segment; lets the kernels
+// one operand list fires on diagonal tuples share a panel
+struct GroupPanel {
   const double* p = nullptr;
   int names[3] = {-1, -1, -1};
+  std::vector<const double*> bases;
+  std::vector<double> scales;
 };
 
 struct EngineStats {
@@ -78,15 +89,28 @@ class Engine {
   Arena& arena() { return slots_[cur_].arena; }   // arena of the batch being built
   int current_slot() const { return cur_; }
   void set_arena_cap(size_t bytes) { for (auto& s : slots_) s.arena.max_bytes = bytes; }
+  // Index order inside the operand panels' 64-row blocks (tables.h make_split): 0 = holes first, 1 = particles first.
+  // Padding rows of ragged tiles are skipped at a granularity of 4 / 2 / 1 values for the first / second / third
+  // index of a group, so the less ragged index type goes first.  Fixed for all tuples of a batch.
+  void set_order(int order);
+  int order() const { return order_; }
+  // executed / useful 8x8 DMMA blocks for a tuple of these ranges (physical order h3,h2,h1,p6,p5,p4) under `order`
+  static double padding_cost(const int R_phys[6], int order);
 
   // ---- tuple building (all pointers are device pointers) ----
   void begin_tuple(const int R_phys[6]);
   bool tuple_open() const { return open_; }
-  // family 1 (sd_t_d1_K) or 2 (sd_t_d2_K); k0 = K-1; K7 = range of the contracted tile.
-  // t_cache / v_cache (optional): panels already built from the same operand; reused when the index order matches.
-  void add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub,
-                       double tscale = 1.0, std::vector<PanelSlot>* t_cache = nullptr,
-                       std::vector<PanelSlot>* v_cache = nullptr);
+  // family 1 (sd_t_d1_K) or 2 (sd_t_d2_K); k0 = K-1; segs = the contracted tiles (h7b / p7b) of this kernel in this
+  // tuple, concatenated along K.  t_cache / v_cache (optional): group panels already built; reused when the index
+  // order and the segments' source blocks match.
+  void add_contraction_group(int family, int k0, const Segment* segs, int nseg, std::vector<GroupPanel>* t_cache = nullptr,
+                             std::vector<GroupPanel>* v_cache = nullptr);
+  // one contracted tile on its own (K7 = its range)
+  void add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale = 1.0) {
+    Segment sg;
+    sg.K = K7; sg.t = tsub; sg.v = v2sub; sg.tscale = tscale;
+    add_contraction_group(family, k0, &sg, 1);
+  }
   void add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub);
   // eps: six DEVICE vectors in reference argument order (h1,h2,h3,p4,p5,p6).  [item_lo, item_hi) restricts the launch
   // to a sub-range of the tuple's 4^6 sub-tiles (linear index, h3 block fastest, p4 block slowest; item_hi < 0 = all):
@@ -147,6 +171,7 @@ class Engine {
   long long max_ablock_ = 0, max_panel_ = 0, max_copy_ = 0;
   long long items_ = 0;
   int max_chunks_ = 1;
+  int order_ = 0;
   cudaEvent_t evt0_, evt1_;
   // host bytes -> pinned staging of the current slot -> `dst` (device), truly asynchronous
   void upload(void* dst, const void* host, size_t bytes);

@@ -266,6 +266,7 @@ void walk_doubles(const HostState& S, const Integer t[6], Sink& sink) {
         restricted_map(S, 4, b, bm);                                // :261
         sink.d1_pair(r, h7b, am, bm, fire);
       }
+      sink.row_end(1);   // all h7 tiles of this row have been reported
     }
   }
   {  // ---- Sum(p7): ccsd_t_doubles_gpu.F:810-1345 ----
@@ -290,6 +291,7 @@ void walk_doubles(const HostState& S, const Integer t[6], Sink& sink) {
         restricted_map(S, 4, b, bm);                                // :929
         sink.d2_pair(r, p7b, am, bm, fire);
       }
+      sink.row_end(2);   // all p7 tiles of this row have been reported
     }
   }
 }
@@ -306,15 +308,18 @@ inline double tuple_factor(const HostState& S, const Integer t[6]) {
 struct CostSink {
   const HostState& S;
   long long planes = 0;
+  long long rowK = 0; int rowfired = 0;   // the contracted tiles of one row are concatenated along K (engine.h Segment)
   void singles(const Row&, Integer, Integer, Integer, Integer, Integer, Integer, const bool fire[9]) {
     for (int k = 0; k < 9; k++) if (fire[k]) planes += 1;
   }
-  void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) {
-    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(h7b) + 3) / 4;
+  void pair(Integer K, const bool fire[9]) {
+    rowK += K;
+    rowfired = 0;
+    for (int k = 0; k < 9; k++) rowfired += fire[k] ? 1 : 0;
   }
-  void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) {
-    for (int k = 0; k < 9; k++) if (fire[k]) planes += (S.rg(p7b) + 3) / 4;
-  }
+  void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) { pair(S.rg(h7b), fire); }
+  void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) { pair(S.rg(p7b), fire); }
+  void row_end(int) { planes += rowfired * ((rowK + 3) / 4); rowK = 0; rowfired = 0; }
 };
 
 inline long long tuple_sub_tiles(const HostState& S, const Integer t[6]) {
@@ -323,18 +328,19 @@ inline long long tuple_sub_tiles(const HostState& S, const Integer t[6]) {
   return n;
 }
 
-// Static block partition of tasks [first, first+ntasks) of `klist` (rows of 7) over nranks: the tasks are laid end to
-// end, every 4^6 sub-tile weighted by the k4 planes its tuple contracts plus a constant for the per-sub-tile epilogue,
+// Static block partition of the tasks `ids` (indices into `klist`, rows of 7) over nranks: the tasks are laid end to
+// end in the order given, every 4^6 sub-tile weighted by the k4 planes its tuple contracts plus a constant for the per-sub-tile epilogue,
 // and rank r takes the r-th equal-cost contiguous piece.  ranges[2*i], ranges[2*i+1] = the sub-tile range
-// [item_lo, item_hi) of task first+i that `rank` runs (empty when lo == hi).  Pure integer arithmetic: every rank
+// [item_lo, item_hi) of task ids[i] that `rank` runs (empty when lo == hi).  Pure integer arithmetic: every rank
 // derives the same cuts.
 inline void block_partition(const HostState& S, const std::vector<Integer>& klist, Integer rank, Integer nranks,
-                            Integer first, Integer ntasks, std::vector<long long>& ranges) {
+                            const std::vector<Integer>& ids, std::vector<long long>& ranges) {
+  const Integer ntasks = (Integer)ids.size();
   const long long EPILOGUE_PLANES = 24;   // transfers, singles, energy of one sub-tile in units of one k4 plane
   std::vector<long long> items((size_t)ntasks), w((size_t)ntasks);
   std::vector<__int128> cum((size_t)ntasks + 1, 0);
   for (Integer i = 0; i < ntasks; i++) {
-    const Integer* t = &klist[7 * (size_t)(first + i)];
+    const Integer* t = &klist[7 * (size_t)ids[(size_t)i]];
     CostSink cs{S};
     walk_singles(S, t, cs);
     walk_doubles(S, t, cs);

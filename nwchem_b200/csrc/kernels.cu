@@ -59,45 +59,39 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-// Four DMMAs executed `on` (0 or 1, warp-uniform) times.  Written as a do-while because ptxas turns a plain
-// branch around DMMAs into predication, and a predicated-off DMMA still occupies the pipe (tools/pred_dmma.cu).
-__device__ __forceinline__ void dmma884x4_if(double (&c0)[2], double (&c1)[2], double (&c2)[2], double (&c3)[2], double a0,
-                                             double b0, double a1, double b1, double a2, double b2, double a3, double b3,
-                                             unsigned int on) {
+// Written as a do-while because ptxas turns a plain branch around DMMAs into predication, and a predicated-off DMMA
+// still occupies the pipe (tools/pred_dmma.cu).
+// Two adjacent 8x8 blocks, both k4 planes of a stage (or one plane), executed `on` (0 or 1, warp-uniform) times.
+// Per-block guards skip ~3 % more padding but were measured slower (two dependent DMMAs behind every branch pair:
+// uracil 10.4 s vs 9.85 s with the groups of four of round 1); two blocks x two planes keeps four DMMAs in flight
+// behind each guard and, with the particle-first panel order, executes 9 % fewer DMMAs than the groups of four.
+__device__ __forceinline__ void dmma884x2x2_if(double (&c0)[2], double (&c1)[2], double2 a0, double2 b0, double2 a1, double2 b1,
+                                               unsigned int on) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
-      "mov.u32 n, %16;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE;\n\t"
-      "NWC_LOOP:\n\t"
+      "mov.u32 n, %12;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE22;\n\t"
+      "NWC_LOOP22:\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%6}, {%7}, {%2,%3};\n\t"
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%10}, {%11}, {%2,%3};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%12}, {%13}, {%4,%5};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%14}, {%15}, {%6,%7};\n\t"
-      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP;\n\t"
-      "NWC_DONE:\n\t}"
-      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1]), "+d"(c2[0]), "+d"(c2[1]), "+d"(c3[0]), "+d"(c3[1])
-      : "d"(a0), "d"(b0), "d"(a1), "d"(b1), "d"(a2), "d"(b2), "d"(a3), "d"(b3), "r"(on));
+      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP22;\n\t"
+      "NWC_DONE22:\n\t}"
+      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1])
+      : "d"(a0.x), "d"(b0.x), "d"(a1.x), "d"(b1.x), "d"(a0.y), "d"(b0.y), "d"(a1.y), "d"(b1.y), "r"(on));
 }
-// the same for both k4 planes of a stage: eight DMMAs (plane 0 then plane 1 of four blocks) behind one guard
-__device__ __forceinline__ void dmma884x8_if(double (&c0)[2], double (&c1)[2], double (&c2)[2], double (&c3)[2], double2 a0,
-                                             double2 b0, double2 a1, double2 b1, double2 a2, double2 b2, double2 a3,
-                                             double2 b3, unsigned int on) {
+__device__ __forceinline__ void dmma884x2x1_if(double (&c0)[2], double (&c1)[2], double a0, double b0, double a1, double b1,
+                                               unsigned int on) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
-      "mov.u32 n, %24;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE8;\n\t"
-      "NWC_LOOP8:\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%10}, {%11}, {%2,%3};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%12}, {%13}, {%4,%5};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%14}, {%15}, {%6,%7};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%16}, {%17}, {%0,%1};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%18}, {%19}, {%2,%3};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%20}, {%21}, {%4,%5};\n\t"
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%22}, {%23}, {%6,%7};\n\t"
-      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP8;\n\t"
-      "NWC_DONE8:\n\t}"
-      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1]), "+d"(c2[0]), "+d"(c2[1]), "+d"(c3[0]), "+d"(c3[1])
-      : "d"(a0.x), "d"(b0.x), "d"(a1.x), "d"(b1.x), "d"(a2.x), "d"(b2.x), "d"(a3.x), "d"(b3.x), "d"(a0.y), "d"(b0.y),
-        "d"(a1.y), "d"(b1.y), "d"(a2.y), "d"(b2.y), "d"(a3.y), "d"(b3.y), "r"(on));
+      "mov.u32 n, %8;\n\tsetp.eq.u32 p, n, 0;\n\t@p bra.uni NWC_DONE21;\n\t"
+      "NWC_LOOP21:\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%6}, {%7}, {%2,%3};\n\t"
+      "sub.u32 n, n, 1;\n\tsetp.ne.u32 p, n, 0;\n\t@p bra.uni NWC_LOOP21;\n\t"
+      "NWC_DONE21:\n\t}"
+      : "+d"(c0[0]), "+d"(c0[1]), "+d"(c1[0]), "+d"(c1[1])
+      : "d"(a0), "d"(b0), "d"(a1), "d"(b1), "r"(on));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,8 +201,11 @@ void launch_synth_fill(const FillJob* d_jobs, int njobs, long long max_doubles, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict__ jobs) {
   const RepackJob j = jobs[blockIdx.y];
-  const int nb1 = (j.X1 + 3) >> 2, nb2 = (j.X2 + 3) >> 2, nb3 = (j.X3 + 3) >> 2, nkq = (j.K + 4 * KPL - 1) / (4 * KPL);
-  const long long total = (long long)nkq * nb1 * nb2 * nb3 * BLK_DOUBLES;
+  const int nb1 = (j.X1 + 3) >> 2, nb2 = (j.X2 + 3) >> 2, nb3 = (j.X3 + 3) >> 2;
+  const int kq_lo = j.k_off / (4 * KPL), kq_hi = (j.k_end + 4 * KPL - 1) / (4 * KPL);
+  const long long per_kq = (long long)nb1 * nb2 * nb3 * BLK_DOUBLES;
+  const long long total = (long long)(kq_hi - kq_lo) * per_kq;
+  double* __restrict__ dst = j.dst + (long long)kq_lo * per_kq;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int pl = (int)(e & (KPL - 1)), kk = (int)((e >> 1) & 3), r = (int)((e >> 3) & 63);
@@ -216,14 +213,16 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackJob* __restrict
     const int b1 = (int)(blk % nb1); blk /= nb1;
     const int b2 = (int)(blk % nb2); blk /= nb2;
     const int b3 = (int)(blk % nb3); blk /= nb3;
-    const int kq = (int)blk;
+    const int kq = kq_lo + (int)blk;
     // in-block row r = i1 | (i2&1)<<2 | (i3&1)<<3 | (i2>>1)<<4 | (i3>>1)<<5   (tables.h block_row)
     const int i1 = r & 3, i2 = ((r >> 2) & 1) | (((r >> 4) & 1) << 1), i3 = ((r >> 3) & 1) | (((r >> 5) & 1) << 1);
     const int x1 = 4 * b1 + i1, x2 = 4 * b2 + i2, x3 = 4 * b3 + i3, k = 4 * KPL * kq + 4 * pl + kk;
+    if (k < j.k_off || k >= j.k_end) continue;   // another job's part of a shared base block
+    const int ks = k - j.k_off;
     double v = 0.0;
-    if (x1 < j.X1 && x2 < j.X2 && x3 < j.X3 && k < j.K)
-      v = j.scale * __ldg(j.src + x1 * j.s1 + x2 * j.s2 + x3 * j.s3 + k * j.sk);
-    j.dst[e] = v;
+    if (x1 < j.X1 && x2 < j.X2 && x3 < j.X3 && ks < j.K)
+      v = j.scale * __ldg(j.src + x1 * j.s1 + x2 * j.s2 + x3 * j.s3 + ks * j.sk);
+    dst[e] = v;
   }
 }
 
@@ -296,15 +295,21 @@ struct __align__(16) FusedSmem {
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
 int partials_per_item() { return NCONSUMERS / 32; }
 
-// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; a GF(2)-linear function of the two upper
-// nibbles is folded into the bank-selecting nibble.  Linear: swz(a ^ b) == swz(a) ^ swz(b), so the thread part and
-// the unrolled constant part separate into one XOR.  f(x) = x ^ rot2(x) is the choice for which, in ALL nine
-// fragment<->canonical patterns, the four lane bits of a half-warp (bits 2*g2[0]+1, 2*g2[1], 2*g1[0], 2*g1[0]+1 of L)
+// canonical sub-tile address swizzle: linear L = sum_pos i_pos * 4^pos; a GF(2)-linear function of bits 4..11 is folded
+// into the bank-selecting nibble (bits 0..3).  Linear: swz(a ^ b) == swz(a) ^ swz(b), so the thread part and the
+// unrolled constant part separate into one XOR.  The eight images SWZ_V[i] of bits 4..11 were found by search
+// (gpurun_out/swz.py, tools/swizzle_search.py) such that in ALL nine fragment<->canonical patterns of BOTH split orders
+// (tables.h make_split order 0 / 1) the four lane bits of a half-warp (bits 2*g2[0]+1, 2*g2[1], 2*g1[0], 2*g1[0]+1 of L)
 // land on linearly independent bank bits, i.e. every LDS.64/STS.64 of the transfers is conflict-free (the plain fold
 // x -> x was conflict-free for three splits, 2-way for five, 4-way for one: ncu showed 1.97 wavefronts per ideal one).
-// Bits 5 (h1 high) and 11 (p4 high) -- the owner bits -- are left in place: warp quarters stay disjoint.
-__host__ __device__ constexpr int canon_fold(int x) { return (x ^ ((x << 2) | (x >> 2))) & 15; }
-__host__ __device__ constexpr int canon_swz(int L) { return L ^ canon_fold((L >> 4) & 15) ^ canon_fold((L >> 8) & 15); }
+// Only the low nibble changes: bits 5 (h1 high) and 11 (p4 high) -- the owner bits -- stay in place, warp quarters stay
+// disjoint, and the epilogue's lane-linear reads (bits 0..4 from the lane id) are conflict-free for any choice.
+__host__ __device__ constexpr int canon_swz(int L) {
+  constexpr int SWZ_V[8] = {14, 9, 15, 10, 15, 8, 10, 9};
+  int f = 0;
+  for (int i = 0; i < 8; i++) f ^= ((L >> (4 + i)) & 1) ? SWZ_V[i] : 0;
+  return L ^ f;
+}
 
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
@@ -319,16 +324,19 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
 
 // number of owner indices in G1 of split s (tables.h): G1 holds p4 iff pa==p4, holds h1 iff hb!=h1
 // the nine splits as a table (evaluating make_split at run time costs ~6 KB of code and local-memory traffic)
-__constant__ Split c_splits[9] = {make_split(0), make_split(1), make_split(2), make_split(3), make_split(4),
-                                  make_split(5), make_split(6), make_split(7), make_split(8)};
+__constant__ Split c_splits[2][9] = {
+    {make_split(0, 0), make_split(1, 0), make_split(2, 0), make_split(3, 0), make_split(4, 0), make_split(5, 0),
+     make_split(6, 0), make_split(7, 0), make_split(8, 0)},
+    {make_split(0, 1), make_split(1, 1), make_split(2, 1), make_split(3, 1), make_split(4, 1), make_split(5, 1),
+     make_split(6, 1), make_split(7, 1), make_split(8, 1)}};
 __device__ __forceinline__ int own1_of(int s) { return ((s >= 6) ? 1 : 0) + ((s % 3 != POS_H1) ? 1 : 0); }
 
 // Move the warp's 16 accumulator blocks between registers (fragment layout of split S) and its private quarter
 // of the canonical sub-tile.  LOAD at the start of a split (the DMMAs then accumulate on top of the running sum:
 // the nine permutations are fused without a single FP64 add), STORE at its end.
-template <int S, bool LOAD>
+template <int S, bool LOAD, int ORDER>
 __device__ __forceinline__ void xfer_split(double (&acc)[16][2], double* canon, int lane, int wo0, int wo1) {
-  constexpr Split sp = make_split(S);
+  constexpr Split sp = make_split(S, ORDER);
   constexpr int RB = 8 >> sp.own1, CB = 2 << sp.own1;
   constexpr int own2 = 2 - sp.own1;
   // first row / column block of this warp: the owner bits are the top bits of the block number
@@ -354,18 +362,18 @@ __device__ __forceinline__ void xfer_split(double (&acc)[16][2], double* canon, 
     }
 }
 
-template <bool LOAD>
+template <bool LOAD, int ORDER>
 __device__ __forceinline__ void xfer_any(int s, double (&acc)[16][2], double* canon, int lane, int wo0, int wo1) {
   switch (s) {
-    case 0: xfer_split<0, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 1: xfer_split<1, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 2: xfer_split<2, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 3: xfer_split<3, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 4: xfer_split<4, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 5: xfer_split<5, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 6: xfer_split<6, LOAD>(acc, canon, lane, wo0, wo1); break;
-    case 7: xfer_split<7, LOAD>(acc, canon, lane, wo0, wo1); break;
-    default: xfer_split<8, LOAD>(acc, canon, lane, wo0, wo1); break;
+    case 0: xfer_split<0, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 1: xfer_split<1, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 2: xfer_split<2, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 3: xfer_split<3, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 4: xfer_split<4, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 5: xfer_split<5, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 6: xfer_split<6, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    case 7: xfer_split<7, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
+    default: xfer_split<8, LOAD, ORDER>(acc, canon, lane, wo0, wo1); break;
   }
 }
 
@@ -431,24 +439,18 @@ __device__ __forceinline__ void mma_split(double (&acc)[16][2], const ContrDesc*
       if (MASKED) {
         // Edge sub-tiles of ragged tiles: bit i*CB+j of `live` clear = block (i,j) lies in the zero padding.
         // A predicated-off DMMA still holds the FP64 pipe for its full 16 cycles (tools/pred_dmma.cu) and ptxas
-        // if-converts plain branches around them, so blocks are skipped in groups of four by dmma884x4_if;
-        // the slot is released first (nothing is hoisted across those branches).
+        // if-converts plain branches around them, so the DMMAs of every pair of adjacent blocks (both planes) sit behind
+        // a real branch (dmma884x2x2_if); the slot is released first (nothing is hoisted across those branches).
         release();
         if (two) {
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const int u = 4 * g;
-            dmma884x8_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB], b[u % CB], a[(u + 1) / CB], b[(u + 1) % CB],
-                         a[(u + 2) / CB], b[(u + 2) % CB], a[(u + 3) / CB], b[(u + 3) % CB], ((live >> u) & 15u) != 0u);
-          }
+          for (int u = 0; u < 16; u += 2)
+            dmma884x2x2_if(acc[u], acc[u + 1], a[u / CB], b[u % CB], a[(u + 1) / CB], b[(u + 1) % CB], ((live >> u) & 3u) != 0u);
         } else {
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const int u = 4 * g;
-            dmma884x4_if(acc[u], acc[u + 1], acc[u + 2], acc[u + 3], a[u / CB].x, b[u % CB].x, a[(u + 1) / CB].x,
-                         b[(u + 1) % CB].x, a[(u + 2) / CB].x, b[(u + 2) % CB].x, a[(u + 3) / CB].x, b[(u + 3) % CB].x,
-                         ((live >> u) & 15u) != 0u);
-          }
+          for (int u = 0; u < 16; u += 2)
+            dmma884x2x1_if(acc[u], acc[u + 1], a[u / CB].x, b[u % CB].x, a[(u + 1) / CB].x, b[(u + 1) % CB].x,
+                           ((live >> u) & 3u) != 0u);
         }
       } else {
 #pragma unroll
@@ -485,7 +487,7 @@ __device__ unsigned int g_phase_cap = 0;
 
 // RAGGED: the launch holds tuples whose tile ranges are not multiples of four; only that instantiation carries the
 // block-skipping K loops (their mere presence costs the aligned case ~3 %, so aligned launches use the plain kernel).
-template <bool DUMP, bool TIMING = false, bool RAGGED = true>
+template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0>
 __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
@@ -495,7 +497,6 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wo0 = warp & 1, wo1 = (warp >> 1) & 1;   // owner bits: high bit of h1, high bit of p4
   const bool is_producer = warp == NCONSUMERS / 32;
 
   // ---- locate the tuple of this work item: 32-way search over item_begin (two dependent loads for <= 1024
@@ -530,11 +531,36 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 #define NWC_B(q) __shfl_sync(0xffffffffu, my_b, (q))
 #define NWC_NB(q) __shfl_sync(0xffffffffu, my_nb, (q))
 #define NWC_R(q) __shfl_sync(0xffffffffu, my_R, (q))
+  // Owner bits of this warp: which quarter (high bit of h1, high bit of p4) of the sub-tile it accumulates.  The
+  // quarter rotates with the tuple-local sub-tile number: on ragged tiles whole quarters are padding (their warps have
+  // nothing to contract), and a fixed warp -> quarter map would starve the same two SM sub-partitions in every edge
+  // sub-tile.  (Tuple-local, so a tuple split across GPUs sums in the same order.)
+  // Only tuples with a ragged range rotate, so a 4-aligned tuple sums in the same order in either instantiation.
+  int wq = warp & 3;
+  if (RAGGED) {
+    const bool ragged_tuple = __ballot_sync(0xffffffffu, lane < 6 && (my_R & 3) != 0) != 0u;
+    if (ragged_tuple) wq = (warp + (int)(unsigned int)(item - T.item_begin + T.item_first)) & 3;
+  }
+  const int wo0 = wq & 1, wo1 = (wq >> 1) & 1;
+  // ragged tiles: a quarter whose h1 or p4 values all lie beyond the tile range holds only padding.  Such warps skip
+  // the K loops altogether, and the ring's `empty` barriers count only the live warps.
+  int nlive_warps = NCONSUMERS / 32;
+  bool dead_quarter = false;
+  if (RAGGED) {
+    const int h1lo = 4 * NWC_B(POS_H1), rh1 = NWC_R(POS_H1), p4lo = 4 * NWC_B(POS_P4), rp4 = NWC_R(POS_P4);
+    nlive_warps = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const bool dq = (h1lo + 2 * (q & 1) >= rh1) || (p4lo + 2 * (q >> 1) >= rp4);
+      nlive_warps += dq ? 0 : 1;
+      if (q == wq) dead_quarter = dq && !is_producer;
+    }
+  }
   if (tid < 6) { sm.b[tid] = my_b; sm.R[tid] = my_R; }
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], NCONSUMERS / 32);
+      mbar_init(&sm.empty[s], nlive_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
@@ -547,7 +573,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     for (int i = tid; i < SUBTILE / 2; i += NTHREADS) c2[i] = make_double2(0.0, 0.0);
   }
   if (warp == 0) {
-    const Split& sp = c_splits[lane < 9 ? lane : 0];
+    const Split& sp = c_splits[ORDER][lane < 9 ? lane : 0];
     const int b10 = NWC_B(sp.g1[0]), b11 = NWC_B(sp.g1[1]), b12 = NWC_B(sp.g1[2]);
     const int b20 = NWC_B(sp.g2[0]), b21 = NWC_B(sp.g2[1]), b22 = NWC_B(sp.g2[2]);
     const int n10 = NWC_NB(sp.g1[0]), n11 = NWC_NB(sp.g1[1]), n12 = NWC_NB(sp.g1[2]);
@@ -638,6 +664,11 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
         }
       }
     }
+  } else if (RAGGED && dead_quarter) {
+    // ===== MMA warp whose quarter is all padding: its part of the doubles tile is zero =====
+    const int Az = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) sm.canon[Az ^ canon_swz(jj << 6)] = 0.0;
   } else {
     // ===== MMA warps =====
     // A warp's tile in split s is (8>>own1) x (2<<own1) blocks of 8x8; which blocks follows from the owner bits, so
@@ -657,7 +688,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       unsigned long long c0 = 0;
       if (!first_split) {   // the first split starts from zero accumulators
         if (TIMING) c0 = clock64();
-        xfer_any<true>(s, acc, sm.canon, lane, wo0, wo1);
+        xfer_any<true, ORDER>(s, acc, sm.canon, lane, wo0, wo1);
         if (TIMING) tph[7] += clock64() - c0;
       }
       first_split = false;
@@ -686,7 +717,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
       }
 #undef NWC_MMA
       if (TIMING) c0 = clock64();
-      xfer_any<false>(s, acc, sm.canon, lane, wo0, wo1);
+      xfer_any<false, ORDER>(s, acc, sm.canon, lane, wo0, wo1);
       __syncwarp();
       if (TIMING) tph[7] += clock64() - c0;
     }
@@ -869,47 +900,37 @@ void set_phase_timing(unsigned long long* d_buf, unsigned int cap_items) {
   g_phase_timing = d_buf != nullptr;
 }
 
-static void set_fused_attr() {
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaFuncSetAttribute(fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(fused_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaFuncSetAttribute(fused_kernel<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    done = true;
+template <bool DUMP, bool TIMING, bool RAGGED, int ORDER>
+static void launch_one(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
+                       double2* d_partials, long long total_items, double* dd, double* ds, cudaStream_t stream) {
+  static bool attr_done = false;   // one flag per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr_done = true;
   }
+  fused_kernel<DUMP, TIMING, RAGGED, ORDER><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
+      d_tuples, ntuples, d_descs, d_sdescs, d_partials, dd, ds);
 }
 
 static_assert(NWC_CTAS_PER_SM * (sizeof(FusedSmem) + 1024) <= 228 * 1024, "FusedSmem too large for the intended CTAs/SM");
+// order: index order inside the panel blocks (tables.h make_split), the one the panels of this launch were built with
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, cudaStream_t stream) {
+                  double2* d_partials, long long total_items, bool ragged, int order, cudaStream_t stream) {
   if (total_items <= 0) return;
-  set_fused_attr();
-  if (!ragged && !g_phase_timing) {
-    fused_kernel<false, false, false><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
-        d_tuples, ntuples, d_descs, d_sdescs, d_partials, nullptr, nullptr);
-    return;
-  }
-  if (g_phase_timing) {
-    fused_kernel<false, true><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs,
-                                                                                             d_sdescs, d_partials, nullptr, nullptr);
-    return;
-  }
-  fused_kernel<false><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs, d_sdescs,
-                                                                                     d_partials, nullptr, nullptr);
+#define NWC_L(D, T, R, O) launch_one<D, T, R, O>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream)
+  if (g_phase_timing) { if (order) NWC_L(false, true, true, 1); else NWC_L(false, true, true, 0); return; }
+  if (!ragged) { if (order) NWC_L(false, false, false, 1); else NWC_L(false, false, false, 0); return; }
+  if (order) NWC_L(false, false, true, 1); else NWC_L(false, false, true, 0);
+#undef NWC_L
 }
 
 void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                       double2* d_partials, long long total_items, double* d_doubles, double* d_singles,
+                       double2* d_partials, long long total_items, double* d_doubles, double* d_singles, int order,
                        cudaStream_t stream) {
   if (total_items <= 0) return;
-  set_fused_attr();
-  fused_kernel<true><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(d_tuples, ntuples, d_descs, d_sdescs,
-                                                                                    d_partials, d_doubles, d_singles);
+  if (order) launch_one<true, false, true, 1>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, d_doubles, d_singles, stream);
+  else launch_one<true, false, true, 0>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, d_doubles, d_singles, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

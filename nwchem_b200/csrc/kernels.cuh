@@ -47,11 +47,12 @@ struct TupleHdr {
   int item_first;        // index of the first of them inside the tuple's full sub-tile space
 };
 
-struct RepackJob {      // build one panel from a strided source
+struct RepackJob {      // build the k range [k_off, k_end) of one panel from a strided source
   const double* src;
-  double* dst;
+  double* dst;          // the whole panel (k = 0)
   long long s1, s2, s3, sk;   // source strides (in doubles) of x1,x2,x3,k
-  int X1, X2, X3, K;
+  int X1, X2, X3, K;    // K source values land at panel k = k_off .. k_off+K-1; [k_off+K, k_end) is zero filled
+  int k_off, k_end;     // several jobs (one per contracted tile) fill one panel: K is padded once, at the very end
   double scale;
 };
 
@@ -88,8 +89,9 @@ void launch_synth_fill(const FillJob* d_jobs, int njobs, long long max_doubles, 
                        unsigned long long store, double scale, cudaStream_t stream);
 void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
 // ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
+// order: index order inside the panel blocks (tables.h make_split) the launch's panels were built with
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, cudaStream_t stream);
+                  double2* d_partials, long long total_items, bool ragged, int order, cudaStream_t stream);
 // two-level deterministic reduction; d_chunk_sums holds ntuples * max_chunks double2 (max_chunks >= the largest
 // reduce_chunks(nitems) of the launch)
 int reduce_chunks(long long nitems);
@@ -97,7 +99,7 @@ void launch_reduce(const TupleHdr* d_tuples, int ntuples, const double2* d_parti
                    int max_chunks, double2* d_energies, cudaStream_t stream);
 // unfused debugging/validation path: materialise the two t3 tiles of ONE tuple in HBM
 void launch_fused_dump(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                       double2* d_partials, long long total_items, double* d_doubles, double* d_singles,
+                       double2* d_partials, long long total_items, double* d_doubles, double* d_singles, int order,
                        cudaStream_t stream);
 int fused_smem_bytes();
 int partials_per_item();   // double2 partials the fused kernel writes per work item (one per MMA warp)

@@ -200,6 +200,23 @@ struct NativeSink {
   nwc_triples_ctx* c;
   Engine& e;
   const HostState& S;
+  // contracted tiles of the current row, concatenated along K when the row ends (engine.h Segment)
+  std::vector<Segment> segs;
+  bool row_fire[9] = {false, false, false, false, false, false, false, false, false};
+  void push(const OperandView& t, const OperandView& v, double sign, Integer K, const bool fire[9]) {
+    Segment sg;
+    sg.K = (int)K; sg.t = t; sg.v = v; sg.tscale = sign;
+    segs.push_back(sg);
+    for (int k = 0; k < 9; k++) row_fire[k] = fire[k];
+  }
+  void row_end(int family) {
+    if (!segs.empty()) {
+      std::vector<GroupPanel> tc, vc;   // kernels fired by the same operand list (diagonal tuples) share panels
+      for (int k = 0; k < 9; k++)
+        if (row_fire[k]) e.add_contraction_group(family, k, segs.data(), (int)segs.size(), &tc, &vc);
+    }
+    segs.clear();
+  }
 
   void singles(const Row& r, Integer p4b_1, Integer h1b_1, Integer p5b_2, Integer p6b_2, Integer h2b_2, Integer h3b_2,
                const bool fire[9]) {
@@ -232,9 +249,7 @@ struct NativeSink {
     v.base = v2_operand(c, bm[1], bm[0], bm[2], bm[3], "v2(hphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.kstride = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
-    std::vector<PanelSlot> tc, vc;
-    for (int k = 0; k < 9; k++)
-      if (fire[k]) e.add_contraction(1, k, (int)rh7, t, v, sign, &tc, &vc);
+    push(t, v, sign, rh7, fire);
   }
 
   void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
@@ -254,9 +269,7 @@ struct NativeSink {
     v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
     v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
-    std::vector<PanelSlot> tc, vc;
-    for (int k = 0; k < 9; k++)
-      if (fire[k]) e.add_contraction(2, k, (int)rp7, t, v, sign, &tc, &vc);
+    push(t, v, sign, rp7, fire);
   }
 };
 
@@ -381,10 +394,29 @@ int nwc_triples_destroy(nwc_triples_ctx* c) {
   return 0;
 }
 
+// Panel index order for this tiling (engine.h set_order): the padding model evaluated on a tuple made of the average
+// hole tile and the average particle tile decides whether holes or particles go first inside the 64-row blocks.
+static int choose_order(const HostState& S) {
+  const char* e = getenv("NWC_ORDER");
+  if (e && (*e == '0' || *e == '1')) return *e - '0';
+  double cost[2] = {0, 0};
+  long long n = 0;
+  for (Integer h = 1; h <= S.noab; h++)
+    for (Integer p = S.noab + 1; p <= S.noab + S.nvab; p++) {
+      const int R[6] = {(int)S.rg(h), (int)S.rg(h), (int)S.rg(h), (int)S.rg(p), (int)S.rg(p), (int)S.rg(p)};
+      const double w = (double)S.rg(h) * S.rg(p);
+      cost[0] += w * Engine::padding_cost(R, 0);
+      cost[1] += w * Engine::padding_cost(R, 1);
+      n++;
+    }
+  return cost[1] < cost[0] * 0.995 ? 1 : 0;
+}
+
 static int finish_state(nwc_triples_ctx* c) {
   size_t ne;
   if (upload(&c->d_evl, &ne, c->S.evl.data(), c->S.evl.size(), c->eng)) return 1;
   build_task_list(c->S, c->klist);
+  c->eng->set_order(choose_order(c->S));
   return 0;
 }
 
@@ -651,29 +683,48 @@ int nwc_triples_run(nwc_triples_ctx* c, Integer first, Integer stride, Integer m
 // boundary is shared between two ranks at sub-tile granularity (energies are additive over sub-tiles), so the balance
 // does not depend on how many tuples there are.  per_task (optional, 2*ntasks, indexed by task - first_task) receives
 // this rank's (partial) energies; summed over ranks it holds the per-task energies.
+static int run_partition_ids(nwc_triples_ctx* c, Integer rank, Integer nranks, const std::vector<Integer>& ids,
+                             double energy[2], double* per_task) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  const HostState& S = c->S;
+  const Integer nt = (Integer)(c->klist.size() / 7);
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+  for (Integer id : ids)
+    if (id < 0 || id >= nt) { g_err = "task index out of range"; return 1; }
+  energy[0] = energy[1] = 0.0;
+  if (per_task) for (size_t i = 0; i < 2 * ids.size(); i++) per_task[i] = 0.0;
+  if (ids.empty()) return 0;
+  std::vector<long long> ranges;
+  block_partition(S, c->klist, rank, nranks, ids, ranges);
+  Pipeline pipe(c, energy, per_task);
+  for (size_t i = 0; i < ids.size(); i++) {
+    const long long a = ranges[2 * i], b = ranges[2 * i + 1];
+    if (b <= a) continue;
+    emit_tuple(c, &c->klist[7 * (size_t)ids[i]], a, b);
+    pipe.emitted((Integer)i);
+  }
+  pipe.finish();
+  return 0;
+}
+
 int nwc_triples_run_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
                               double energy[2], double* per_task) {
   return guarded(c, [&]() {
-    NWC_TRY(cudaSetDevice(c->eng->device()));
-    const HostState& S = c->S;
     const Integer nt = (Integer)(c->klist.size() / 7);
-    if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
     if (first_task < 0) first_task = 0;
     if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
-    energy[0] = energy[1] = 0.0;
-    if (per_task) for (Integer i = 0; i < 2 * ntasks; i++) per_task[i] = 0.0;
-    if (ntasks <= 0) return 0;
-    std::vector<long long> ranges;
-    block_partition(S, c->klist, rank, nranks, first_task, ntasks, ranges);
-    Pipeline pipe(c, energy, per_task);
-    for (Integer i = 0; i < ntasks; i++) {
-      const long long a = ranges[2 * (size_t)i], b = ranges[2 * (size_t)i + 1];
-      if (b <= a) continue;
-      emit_tuple(c, &c->klist[7 * (first_task + i)], a, b);
-      pipe.emitted(i);
-    }
-    pipe.finish();
-    return 0;
+    std::vector<Integer> ids;
+    for (Integer i = 0; i < ntasks; i++) ids.push_back(first_task + i);
+    return run_partition_ids(c, rank, nranks, ids, energy, per_task);
+  });
+}
+
+// the same for an explicit list of task indices (e.g. a strided sample of the list), partitioned in the order given
+int nwc_triples_run_partition_list(nwc_triples_ctx* c, Integer rank, Integer nranks, const Integer* task_ids, Integer n,
+                                   double energy[2], double* per_task) {
+  return guarded(c, [&]() {
+    std::vector<Integer> ids(task_ids, task_ids + (n > 0 ? n : 0));
+    return run_partition_ids(c, rank, nranks, ids, energy, per_task);
   });
 }
 
@@ -828,6 +879,7 @@ int nwc_debug_phase_timing(unsigned long long* host_out, unsigned int cap_items,
 }
 
 int nwc_triples_set_batch_bytes(nwc_triples_ctx* c, size_t bytes) { c->batch_bytes = bytes; return 0; }
+int nwc_triples_get_order(nwc_triples_ctx* c) { return c->eng->order(); }
 int nwc_triples_set_arena_cap(nwc_triples_ctx* c, size_t bytes) { c->eng->set_arena_cap(bytes); return 0; }
 
 int nwc_triples_nccl_unique_id(char id128[128]) {

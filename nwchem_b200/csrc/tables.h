@@ -65,7 +65,25 @@ struct Split {
   int own1;    // number of owner indices in G1 (0,1,2); G2 holds 2-own1
 };
 NWC_HD constexpr bool is_owner_pos(int q) { return q == POS_H1 || q == POS_P4; }
-NWC_HD constexpr Split make_split(int s) {
+// order 0: non-owner indices in ascending position (holes before particles); order 1: particles before holes.
+// Padding of ragged tiles can be skipped at a granularity of 4 values for i1, 2 for i2 and 1 for i3, so the LESS
+// ragged index type should sit first; the engine picks the order per tiling (Engine::set_order).
+NWC_HD constexpr bool split_before(int a, int b, int order) {
+  return order == 0 ? a < b : ((a >= 3) != (b >= 3) ? a >= 3 : a < b);
+}
+NWC_HD constexpr void split_order3(int (&out)[3], const int (&in)[3], int order) {
+  int non[3] = {0, 0, 0};
+  int nn = 0;
+  for (int i = 0; i < 3; i++) if (!is_owner_pos(in[i])) non[nn++] = in[i];
+  for (int i = 0; i < nn; i++)           // insertion sort of at most three entries
+    for (int j = i + 1; j < nn; j++)
+      if (split_before(non[j], non[i], order)) { int t = non[i]; non[i] = non[j]; non[j] = t; }
+  int n = 0;
+  for (int i = 0; i < nn; i++) out[n++] = non[i];
+  for (int i = 0; i < 3; i++) if (in[i] == POS_H1) out[n++] = POS_H1;
+  for (int i = 0; i < 3; i++) if (in[i] == POS_P4) out[n++] = POS_P4;
+}
+NWC_HD constexpr Split make_split(int s, int order = 0) {
   Split sp{};
   sp.pa = 3 + s / 3;
   sp.hb = s % 3;
@@ -75,17 +93,9 @@ NWC_HD constexpr Split make_split(int s) {
   for (int q = 0; q < 3; q++) if (q != sp.hb) a[na++] = q;
   b[nb++] = sp.hb;
   for (int q = 3; q < 6; q++) if (q != sp.pa) b[nb++] = q;
-  // non-owners ascending, then h1, then p4
-  int n = 0;
-  for (int q = 0; q < 6; q++)
-    for (int i = 0; i < 3; i++) if (a[i] == q && !is_owner_pos(q)) sp.g1[n++] = q;
-  for (int i = 0; i < 3; i++) if (a[i] == POS_H1) sp.g1[n++] = POS_H1;
-  for (int i = 0; i < 3; i++) if (a[i] == POS_P4) sp.g1[n++] = POS_P4;
-  n = 0;
-  for (int q = 0; q < 6; q++)
-    for (int i = 0; i < 3; i++) if (b[i] == q && !is_owner_pos(q)) sp.g2[n++] = q;
-  for (int i = 0; i < 3; i++) if (b[i] == POS_H1) sp.g2[n++] = POS_H1;
-  for (int i = 0; i < 3; i++) if (b[i] == POS_P4) sp.g2[n++] = POS_P4;
+  // non-owners in the chosen order, then h1, then p4
+  split_order3(sp.g1, a, order);
+  split_order3(sp.g2, b, order);
   sp.own1 = (sp.pa == POS_P4 ? 1 : 0) + (sp.hb != POS_H1 ? 1 : 0);
   return sp;
 }

@@ -410,6 +410,9 @@ def test_block_partition_sums_to_total(oracle, h2o_c2v, world):
     assert 0 <= shared <= world - 1          # at most one shared tuple per boundary
     pre = [tr.run_partition(r, world, first_task=0, ntasks=5, per_task=True) for r in range(world)]
     assert np.max(np.abs(sum(p[2] for p in pre) - pt[:5])) <= 1e-14
+    ids = [(i * len(pt)) // 7 for i in range(7)]          # a strided sample of the list, as bench.py runs it
+    smp = [tr.run_partition_list(r, world, ids, per_task=True) for r in range(world)]
+    assert np.max(np.abs(sum(p[2] for p in smp) - pt[ids])) <= 1e-14
     tr.close()
 
 
