@@ -204,6 +204,9 @@ SHAPES = {
     "uracil_augccpvdz": dict(occ=[21], virt=[191], tilesize=40),
     "benzene_dimer_augccpvtz": dict(occ=[30], virt=[786], tilesize=40),
     "h2o10_augccpvtz": dict(occ=[40], virt=[870], tilesize=40),
+    # profiling stand-in for the (H2O)10 shape: same 40-wide tiles, 4 instead of 22 virtual tiles per spin, so the
+    # resident store is < 1 GB (ncu's kernel replay saves and restores device memory around every pass)
+    "h2o10_slice_v160": dict(occ=[40], virt=[160], tilesize=40),
 }
 
 

@@ -139,3 +139,24 @@ def test_public_struct_layouts_match_the_ctypes_mirror(tmp_path):
         cls = mirror[name]
         assert int(size) == C.sizeof(cls), name
         assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
+
+
+def test_fortran_binding_names_every_symbol_the_library_exports():
+    """integration/nwc_triples_mod.F90 (the ISO_C_BINDING module a maintainer adds) cannot be compiled here (no Fortran
+    compiler), but every bind(C, name=...) in it must be a symbol libnwc_triples.so exports, with all 27 kernel entry
+    points present; and every function the public header declares must be exported too."""
+    import re
+    import subprocess
+    mod = open(os.path.join(ROOT, "integration", "nwc_triples_mod.F90")).read()
+    names = set(re.findall(r"bind\(C,\s*name='([A-Za-z0-9_]+)'\)", mod))
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert names <= exported, sorted(names - exported)
+    for fam in ("s1", "d1", "d2"):
+        for k in range(1, 10):
+            assert f"sd_t_{fam}_{k}_cuda_" in names
+    hdr = open(os.path.join(ROOT, "include", "nwc_triples.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nwc_[a-z0-9_]+|check_device_|device_init_|initmemmodule_|finalizememmodule_|dev_mem_s_|dev_mem_d_|dev_release_|compute_en_)\s*\(", hdr))
+    declared -= {"nwc_tce_state", "nwc_tce_orb_state", "nwc_triples_stats", "nwc_triples_ctx"}
+    assert declared <= exported, sorted(declared - exported)
