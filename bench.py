@@ -273,6 +273,13 @@ def main():
     tr.set_timing(False)
     s = tr.stats()
     ms_max, flops_all = allmax(ms), allsum(s["flops"])
+    # per-rank device time of the fused kernel and of the whole timed region (load balance of the static partition)
+    per_rank = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
+    per_rank[2 * rank] = s["fused_ms"] / a.steps
+    per_rank[2 * rank + 1] = ms / a.steps
+    if world > 1:
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    per_rank = [round(float(x), 2) for x in per_rank.tolist()]
     value = flops_all / (ms_max * 1e-3) * 1e-9
     launches = int(s["fused_launches"] + s["repack_launches"] + s["reduce_launches"] + s["pull_launches"] + s["antisym_launches"])
     fused_avg_ms = s["fused_ms"] / max(1, s["fused_launches"])
@@ -417,6 +424,7 @@ def main():
                 "wall_s_per_step": ms_max / a.steps * 1e-3, "flops_per_step": flops_all / a.steps,
                 "frac_of_fp64_peak": value * 1e-3 / (peak * world), "energy": list(e), "energy_check": energy_check,
                 "full_list_extrapolated_s": (4.5208e17 / (value * 1e9)) if a.workload == "h2o10_augccpvtz" else None,
+                "rank_fused_ms_per_step": per_rank[0::2], "rank_ms_per_step": per_rank[1::2],
                 "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))

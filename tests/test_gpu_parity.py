@@ -656,3 +656,30 @@ def test_uracil_three_tuples_vs_oracle(oracle):
         assert abs(g1 - a) <= ABS_E and abs(g2 - b) <= ABS_E, (tup, g1, a, g2, b)
         assert abs(g1 - a) <= 1e-11 * abs(a) and abs(g2 - b) <= 1e-11 * abs(b), (tup, g1, a, g2, b)
     tr.close()
+
+
+def test_bench_tile_sizes_39_40_slabs_vs_oracle(oracle):
+    """The tile sizes of the (H2O)10 bench sample (occupied 40, virtual 39 and 40 mixed): p4 slabs of three tuples --
+    all-40 (aligned kernel), one 39-wide tile, and 39-wide outer tile (the slab itself ragged) -- against the oracle's
+    slab energies, <= 1e-11 relative; stores from the device generator on the GPU and its numpy twin on the host."""
+    if _host_gb() < 8:
+        pytest.skip("needs ~4 GB of host memory")
+    t = tl.make_tiling([40], [79], 40)          # virtual alpha tiles of 39 and 40
+    host = synth.keyed_blocks(t, seed=9, scale=(1e-3, 5e-5, 5e-3))
+    tr = capi.Triples(0)
+    tr.set_state(synth.empty_stores(t))
+    tr.synth_fill(9, (1e-3, 5e-5, 5e-3))
+    tasks = [[int(x) for x in r[:6]] for r in tr.task_list()]
+    rng = lambda tup: [t.r(b) for b in tup]
+    picks = [next(x for x in tasks if rng(x) == [40] * 6),
+             next(x for x in tasks if sorted(rng(x)[:3]) == [39, 40, 40] and rng(x)[0] == 40),
+             next(x for x in tasks if rng(x)[0] == 39)]
+    for tup in picks:
+        items = tr.tuple_items(tup)
+        nb4 = (t.r(tup[0]) + 3) // 4
+        per = items // nb4
+        for blk in (0, nb4 - 1):                 # first slab and the last one (3 valid p4 values when the tile is 39 wide)
+            g1, g2 = tr.run_items(tup, blk * per, (blk + 1) * per)
+            o1, o2 = oracle.tuple_slab(host, tup, 4 * blk, 4 * blk + 4)
+            assert abs(g1 - o1) <= 1e-11 * abs(o1) and abs(g2 - o2) <= 1e-11 * abs(o2), (tup, blk, g1, o1, g2, o2)
+    tr.close()
