@@ -125,6 +125,10 @@ Integer nwc_host_task_list(const nwc_tce_state *st, Integer *klist7, Integer cap
  * ids): a caller can stage only those blocks on the host.  Returns their number (keys_out filled if cap suffices). */
 Integer nwc_host_collect_blocks(const nwc_tce_state *st, const Integer *tasks6, Integer ntasks, int which,
                                 Integer *keys_out, Integer cap);
+/* host-only: the host driver's TCE_SORT_4 -- sorted(i,j,k,l order) = factor * unsorted(a,b,c,d order), last index
+ * fastest (src/tce/sort/new_sort4.F semantics), cache-blocked and threaded */
+void nwc_host_sort4(const double *unsorted, double *sorted, Integer a, Integer b, Integer c, Integer d, int i, int j,
+                    int k, int l, double factor);
 /* host-only view of nwc_triples_run_partition (below): ranges[2*i], ranges[2*i+1] = the sub-tile range of task
  * first_task+i that `rank` of `nranks` runs (ntasks <= 0: to the end of the list; ranges holds 2*ntasks entries) */
 int nwc_host_block_partition(const nwc_tce_state *st, Integer rank, Integer nranks, Integer first_task, Integer ntasks,

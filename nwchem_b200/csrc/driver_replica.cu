@@ -59,20 +59,48 @@ PageableScratch g_ma_scratch;
 double* scratch(size_t n) { return g_reference_contract ? g_ma_scratch.acquire(n) : g_scratch.acquire(n); }
 
 // sorted(i,j,k,l order, l fastest) = factor * unsorted(a,b,c,d order, d fastest): tce_sort_4 semantics
+// (src/tce/sort/new_sort4.F).  Cache-blocked: the input's fastest index (d) and the output's fastest index are moved in
+// 16 x 16 tiles, so both the reads and the writes touch whole cache lines; the naive loop writes one double per cache
+// line (a 40^4 block: 2.56e6 strided stores) and was the largest host cost of the Tier-1 path.
 void sort4(const double* in, double* out, Integer a, Integer b, Integer c, Integer d, int i, int j, int k, int l,
            double factor) {
   const Integer jd[4] = {a, b, c, d};
   const int perm[4] = {i - 1, j - 1, k - 1, l - 1};
-  Integer ostride[4];  // stride in `out` of input index q
+  Integer ostride[4], istride[4];  // strides in `out` / `in` of input index q
   Integer s = 1;
   for (int q = 3; q >= 0; q--) { ostride[perm[q]] = s; s *= jd[perm[q]]; }
-#pragma omp parallel for collapse(2) schedule(static)
-  for (Integer i0 = 0; i0 < a; i0++)
-    for (Integer i1 = 0; i1 < b; i1++)
-      for (Integer i2 = 0; i2 < c; i2++) {
-        const double* src = in + d * (i2 + c * (i1 + b * i0));
-        double* dst = out + i0 * ostride[0] + i1 * ostride[1] + i2 * ostride[2];
-        for (Integer x = 0; x < d; x++) dst[x * ostride[3]] = factor * src[x];
+  istride[3] = 1; istride[2] = d; istride[1] = c * d; istride[0] = b * c * d;
+  const int f = perm[3];            // input index that is fastest in the output
+  if (f == 3) {                     // same fastest index: contiguous runs of length d
+#pragma omp parallel for collapse(3) schedule(static)
+    for (Integer i0 = 0; i0 < a; i0++)
+      for (Integer i1 = 0; i1 < b; i1++)
+        for (Integer i2 = 0; i2 < c; i2++) {
+          const double* src = in + i0 * istride[0] + i1 * istride[1] + i2 * istride[2];
+          double* dst = out + i0 * ostride[0] + i1 * ostride[1] + i2 * ostride[2];
+          for (Integer x = 0; x < d; x++) dst[x] = factor * src[x];
+        }
+    return;
+  }
+  int r[2], nr = 0;                 // the two indices that are fastest in neither array
+  for (int q = 0; q < 3; q++) if (q != f) r[nr++] = q;
+  const Integer T = 16, nx = (d + T - 1) / T, ny = (jd[f] + T - 1) / T;
+  const Integer os3 = ostride[3], isf = istride[f];
+#pragma omp parallel for collapse(3) schedule(static)
+  for (Integer u0 = 0; u0 < jd[r[0]]; u0++)
+    for (Integer u1 = 0; u1 < jd[r[1]]; u1++)
+      for (Integer ty = 0; ty < ny; ty++) {
+        const double* src0 = in + u0 * istride[r[0]] + u1 * istride[r[1]];
+        double* dst0 = out + u0 * ostride[r[0]] + u1 * ostride[r[1]];
+        const Integer y0 = ty * T, y1 = y0 + T < jd[f] ? y0 + T : jd[f];
+        for (Integer tx = 0; tx < nx; tx++) {
+          const Integer x0 = tx * T, x1 = x0 + T < d ? x0 + T : d;
+          for (Integer x = x0; x < x1; x++) {
+            const double* src = src0 + x;
+            double* dst = dst0 + x * os3;
+            for (Integer y = y0; y < y1; y++) dst[y] = factor * src[y * isf];
+          }
+        }
       }
 }
 
@@ -389,6 +417,12 @@ int nwc_host_block_partition(const nwc_tce_state* st, Integer rank, Integer nran
     printf("%s\n", ex.what());
     return 1;
   }
+}
+
+// host-only: the driver's TCE_SORT_4 (tests compare it with the oracle's restatement for all 24 permutations)
+void nwc_host_sort4(const double* unsorted, double* sorted, Integer a, Integer b, Integer c, Integer d, int i, int j, int k,
+                    int l, double factor) {
+  sort4(unsorted, sorted, a, b, c, d, i, j, k, l, factor);
 }
 
 // calls[3], flops[3] = fired sd_t_s1 / d1 / d2 kernels of one tuple and their algorithmic FLOPs

@@ -160,3 +160,23 @@ def test_fortran_binding_names_every_symbol_the_library_exports():
     declared = set(re.findall(r"\b(nwc_[a-z0-9_]+|check_device_|device_init_|initmemmodule_|finalizememmodule_|dev_mem_s_|dev_mem_d_|dev_release_|compute_en_)\s*\(", hdr))
     declared -= {"nwc_tce_state", "nwc_tce_orb_state", "nwc_triples_stats", "nwc_triples_ctx"}
     assert declared <= exported, sorted(declared - exported)
+
+
+def test_host_sort4_matches_oracle_for_all_permutations(oracle):
+    """The host driver's cache-blocked TCE_SORT_4 against the oracle's plain restatement: all 24 permutations, ragged
+    dims that are not multiples of the 16-wide tile."""
+    import ctypes as C
+    import itertools
+    l = capi.lib()
+    PD = C.POINTER(C.c_double)
+    l.nwc_host_sort4.argtypes = [PD, PD, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+    ol = oracle.lib()
+    ol.ora_tce_sort_4.argtypes = [PD, PD, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_double]
+    rng = np.random.default_rng(4)
+    for dims in ((5, 17, 3, 21), (40, 39, 2, 18), (1, 1, 33, 1)):
+        x = rng.standard_normal(int(np.prod(dims)))
+        for perm in itertools.permutations((1, 2, 3, 4)):
+            a = np.zeros_like(x); b = np.zeros_like(x)
+            l.nwc_host_sort4(x.ctypes.data_as(PD), a.ctypes.data_as(PD), *dims, *perm, -0.5)
+            ol.ora_tce_sort_4(x.ctypes.data_as(PD), b.ctypes.data_as(PD), *dims, *perm, -0.5)
+            assert np.array_equal(a, b), (dims, perm)
