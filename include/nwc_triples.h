@@ -252,6 +252,17 @@ int nwc_triples_set_state_2eorb_sharded(nwc_triples_ctx *ctx, const nwc_tce_stat
    nvab doubles) receives the CCSD[T] partials the same way.  *t_energy = sum(table) (:288-290). */
 int nwc_triples_run_restart(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer *restart_begin, double *table,
                             double *table_bracket, Integer max_outer, double *t_energy);
+/* Lambda-CCSD(T) (src/tce/ccsd_t/lambda_ccsd_t.F, tce_energy.F:3404-3437): the sibling correction that shares the 27
+ * contractions.  set_lambda uploads lambda_1 (h,p), lambda_2 (hh,pp) and the (h,p) Fock blocks in the reference's block
+ * layout with their offset tables (keys: lambda_ccsd_t_left.F:154-155, :378-380, :390-391); run_lambda returns
+ * energy[0] = sum f Td Yd/Delta (Lambda-CCSD[T]) and energy[1] = sum f Td (Ys+Yd)/Delta (Lambda-CCSD(T)) over tasks
+ * first, first+stride, ... of the heaviest-first list, per_task (optional) 2 doubles per task run.  The left-hand tiles
+ * are paired with the right-hand tile in T3 index order, i.e. with the L3->T3 sort lambda_ccsd_t.F:35-36 announces (the
+ * file as written multiplies them with one running index; both readings coincide at tilesize 1 -- see DESIGN.md 8). */
+int nwc_triples_set_lambda(nwc_triples_ctx *ctx, const Integer *y1_hash, const double *y1, const Integer *y2_hash,
+                           const double *y2, const Integer *f1_hash, const double *f1);
+int nwc_triples_run_lambda(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
+                           double *per_task);
 /* one tuple, optionally materialising the t3 tiles (validation only) */
 int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                           double *host_doubles, double *host_singles);

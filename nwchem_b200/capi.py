@@ -263,6 +263,28 @@ class Triples:
                "nwc_triples_run_partition_list")
         return (float(e[0]), float(e[1]), pt[:len(ids)]) if per_task else (float(e[0]), float(e[1]))
 
+    def set_lambda(self, lam):
+        """lam: synth.LambdaStores (lambda_1, lambda_2, Fock (h,p) blocks + offset tables)."""
+        k = [np.ascontiguousarray(a, np.int64 if i % 2 == 0 else np.float64)
+             for i, a in enumerate((lam.y1_hash, lam.y1, lam.y2_hash, lam.y2, lam.f1_hash, lam.f1))]
+        l = lib()
+        l.nwc_triples_set_lambda.argtypes = [C.c_void_p, PL, PD, PL, PD, PL, PD]
+        _check(l.nwc_triples_set_lambda(self._h, _pl(k[0]), _pd(k[1]), _pl(k[2]), _pd(k[3]), _pl(k[4]), _pd(k[5])),
+               "nwc_triples_set_lambda")
+
+    def run_lambda(self, first=0, stride=1, max_tasks=0, per_task=False):
+        """Lambda-CCSD[T] / Lambda-CCSD(T) correction energies (lambda_ccsd_t.F), tasks first, first+stride, ..."""
+        e = np.zeros(2)
+        cnt = len(range(first, self.num_tasks, stride))
+        if max_tasks and max_tasks > 0:
+            cnt = min(cnt, max_tasks)
+        pt = np.zeros((max(cnt, 1), 2)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_lambda.argtypes = [C.c_void_p, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_lambda(self._h, first, stride, max_tasks, _pd(e), _pd(pt) if per_task else None),
+               "nwc_triples_run_lambda")
+        return (float(e[0]), float(e[1]), pt[:cnt]) if per_task else (float(e[0]), float(e[1]))
+
     def tuple_items(self, tup) -> int:
         tt = np.array(tup, np.int64)
         return int(lib().nwc_triples_tuple_items(self._h, _pl(tt)))

@@ -134,7 +134,8 @@ void Engine::begin_tuple(const int R_phys[6]) {
     cur_hdr_.nb[q] = (R_phys[q] + SB - 1) / SB;
   }
   for (int s = 0; s < 9; s++) cur_descs_[s].clear();
-  cur_hdr_.sdesc_begin = (int)sdescs_.size();
+  cur_sd_singles_.clear();
+  cur_sd_doubles_.clear();
   open_ = true;
 }
 
@@ -226,7 +227,27 @@ void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2
     d.sv2[q] = (int)v2sub.stride[name];
   }
   d.neg = SIGN[0][k0] < 0 ? 1 : 0;
-  sdescs_.push_back(d);
+  cur_sd_singles_.push_back(d);
+  cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R);
+}
+
+void Engine::add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, bool to_doubles) {
+  if (!open_) throw Error("nwc_triples: add_outer_product outside a tuple");
+  SinglesDesc d;
+  memset(&d, 0, sizeof(d));
+  d.t1 = a;
+  d.v2 = b;
+  int na = 0, nb = 0;
+  for (int q = 0; q < 6; q++) {
+    d.st1[q] = sa[q];
+    d.sv2[q] = sb[q];
+    na += sa[q] != 0; nb += sb[q] != 0;
+    if (sa[q] != 0 && sb[q] != 0) throw Error("nwc_triples: outer product operands share an index");
+  }
+  // (a stride may legitimately be 0 only for an index the operand lacks; ranges of 1 still carry stride >= 1)
+  if (na != 2 || nb != 4) throw Error("nwc_triples: outer product needs a 2-index and a 4-index operand");
+  d.neg = negative ? 1 : 0;
+  (to_doubles ? cur_sd_doubles_ : cur_sd_singles_).push_back(d);
   cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R);
 }
 
@@ -244,9 +265,14 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
     n += (int)cur_descs_[s].size();
   }
   cur_hdr_.desc_begin[9] = n;
+  cur_hdr_.sdesc_begin = (int)sdescs_.size();
+  sdescs_.insert(sdescs_.end(), cur_sd_doubles_.begin(), cur_sd_doubles_.end());
+  cur_hdr_.sdesc_mid = (int)sdescs_.size();
+  sdescs_.insert(sdescs_.end(), cur_sd_singles_.begin(), cur_sd_singles_.end());
   cur_hdr_.sdesc_end = (int)sdescs_.size();
   open_ = false;
-  if (cur_hdr_.sdesc_end - cur_hdr_.sdesc_begin > 12) throw Error("nwc_triples: more than 12 singles terms in one tuple");
+  if (cur_hdr_.sdesc_end - cur_hdr_.sdesc_begin > MAX_SINGLES_TERMS)
+    throw Error("nwc_triples: more than " + std::to_string(MAX_SINGLES_TERMS) + " outer-product terms in one tuple");
   const long long all = tuple_items(cur_hdr_.R);
   if (item_hi < 0 || item_hi > all) item_hi = all;
   if (item_lo < 0) item_lo = 0;
@@ -366,15 +392,19 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   upload(dm + o_s, sdescs_.data(), sdescs_.size() * sizeof(SinglesDesc));
   S.timed[2] = timing;
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[4], stream_));
-  if (dump_doubles)
+  if (dump_doubles) {
+    for (const TupleHdr& t : tuples_)
+      if (t.sdesc_mid > t.sdesc_begin) throw Error("nwc_triples: the validation dump does not support doubles-bound outer products");
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                       (double2*)(dm + o_p), items_, dump_doubles, dump_singles, order_, stream_);
-  else {
-    bool ragged = false;
-    for (const TupleHdr& t : tuples_)
+  } else {
+    bool ragged = false, lambda = false;
+    for (const TupleHdr& t : tuples_) {
       for (int q = 0; q < 6; q++) ragged = ragged || (t.R[q] % SB != 0);
+      lambda = lambda || (t.sdesc_mid > t.sdesc_begin);
+    }
     launch_fused((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
-                 (double2*)(dm + o_p), items_, ragged, order_, stream_);
+                 (double2*)(dm + o_p), items_, ragged, order_, lambda, stream_);
   }
   NWC_CUDA(cudaGetLastError());
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[5], stream_));

@@ -112,6 +112,10 @@ class Engine {
     add_contraction_group(family, k0, &sg, 1);
   }
   void add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub);
+  // generic outer-product term  +-a[sum g*sa] * b[sum g*sb]  (element strides per PHYSICAL position h3,h2,h1,p6,p5,p4;
+  // `a` carries one hole and one particle index, `b` the other four).  to_doubles: the term belongs to the doubles
+  // tile (added before the energy pass) instead of the singles tile.
+  void add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, bool to_doubles);
   // eps: six DEVICE vectors in reference argument order (h1,h2,h3,p4,p5,p6).  [item_lo, item_hi) restricts the launch
   // to a sub-range of the tuple's 4^6 sub-tiles (linear index, h3 block fastest, p4 block slowest; item_hi < 0 = all):
   // energies are additive over sub-tiles, so a tuple can be shared between GPUs or evaluated slab by slab.
@@ -165,6 +169,7 @@ class Engine {
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;
+  std::vector<SinglesDesc> cur_sd_singles_, cur_sd_doubles_;   // of the tuple being built
   std::vector<RepackJob> jobs_;
   std::vector<AntisymJob> ajobs_;
   std::vector<CopyJob> cjobs_;

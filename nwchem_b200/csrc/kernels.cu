@@ -249,7 +249,7 @@ constexpr int NTHREADS = 160;   // + 1 producer warp (TMA issue only)
 constexpr int STAGES = (NWC_CTAS_PER_SM >= 4) ? 2 : 5;   // ring depth; KPL k4 planes (8 KiB: G1 block + G2 block) per stage
 constexpr int PLANE_DOUBLES = 2 * BLK_DOUBLES;       // one stage: G1 block + G2 block = 8 KiB
 constexpr int RING_DOUBLES = STAGES * PLANE_DOUBLES; // 40 KiB; reused by the epilogue for the singles operands
-constexpr int MAX_SDESC = 12;   // a tuple fires at most nine sd_t_s1_K kernels; the engine rejects more than 12
+constexpr int MAX_SDESC = MAX_SINGLES_TERMS;   // nine sd_t_s1_K terms + nine doubles-bound outer products; the engine rejects more
 constexpr int SD_T1 = 16, SD_V2 = 256, SD_TERM = SD_T1 + SD_V2;   // staged singles operands per term
 constexpr int SD_PER_PASS = (RING_DOUBLES / SD_TERM) < 9 ? (RING_DOUBLES / SD_TERM) : 9;   // terms staged per pass
 static_assert(SD_PER_PASS >= 1, "ring too small for the singles staging");
@@ -289,6 +289,7 @@ struct __align__(16) FusedSmem {
   int b[6];
   int R[6];
   int nsd;
+  int nsd_mid;                              // terms [0, nsd_mid) are added to the doubles tile, [nsd_mid, nsd) are the singles
   int zero;                                 // run-time 0 (see mma_split)
 };
 
@@ -487,7 +488,9 @@ __device__ unsigned int g_phase_cap = 0;
 
 // RAGGED: the launch holds tuples whose tile ranges are not multiples of four; only that instantiation carries the
 // block-skipping K loops (their mere presence costs the aligned case ~3 %, so aligned launches use the plain kernel).
-template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0>
+// LAMBDA: the launch holds tuples with doubles-bound outer-product terms (Lambda-CCSD(T)); the plain (T) instantiations
+// do not carry that code (it costs registers in the epilogue).
+template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0, bool LAMBDA = false>
 __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
@@ -565,6 +568,8 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
     sm.nsd = nsd < MAX_SDESC ? nsd : MAX_SDESC;
+    const int nmid = T.sdesc_mid - T.sdesc_begin;
+    sm.nsd_mid = nmid < 0 ? 0 : (nmid < sm.nsd ? nmid : sm.nsd);
     sm.zero = 0;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
@@ -738,12 +743,20 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   double sing[32];
 #pragma unroll
   for (int jj = 0; jj < 32; jj++) sing[jj] = 0.0;
-  if (nsd > 0) {
+  // Two groups of outer-product terms: [0, nsd_mid) belong to the DOUBLES tile (Lambda-CCSD(T): y2 * f, lambda_ccsd_t_left_2)
+  // and are added into the canonical tile before the energy pass; [nsd_mid, nsd) are the singles (sd_t_s1_K).  Plain
+  // (T) has nsd_mid = 0.
+  bool staged_before = false;
+#pragma unroll 1
+  for (int grp = LAMBDA ? 0 : 1; grp < 2; grp++) {
+    const int glo = (!LAMBDA || grp == 0) ? 0 : sm.nsd_mid, ghi = (LAMBDA && grp == 0) ? sm.nsd_mid : nsd;
+    if (ghi <= glo) continue;
     // stage the t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges;
     // all loads of a batch of nine terms are issued before the first store (one exposed L2 latency per batch)
-    for (int t0 = 0; t0 < nsd; t0 += SD_PER_PASS) {
-      const int nt = (nsd - t0) < SD_PER_PASS ? (nsd - t0) : SD_PER_PASS;
-      if (t0 > 0) asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");   // previous pass fully consumed
+    for (int t0 = glo; t0 < ghi; t0 += SD_PER_PASS) {
+      const int nt = (ghi - t0) < SD_PER_PASS ? (ghi - t0) : SD_PER_PASS;
+      if (staged_before) asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");   // previous pass fully consumed
+      staged_before = true;
       double v0[SD_PER_PASS], v1[SD_PER_PASS], vt[SD_PER_PASS];
       const int d0 = tid & 3, d1 = (tid >> 2) & 3, d2 = (tid >> 4) & 3, d3 = (tid >> 6) & 3;   // staged v2 digits
 #pragma unroll
@@ -817,6 +830,14 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 #pragma unroll
           for (int e = 0; e < 32; e++) sing[e] = fma(tv[e >> 4], vv[e & 15], sing[e]);
         }
+      }
+    }
+    if (LAMBDA && grp == 0) {   // doubles-bound terms: fold them into this warp's quarter of the canonical tile, start the singles from 0
+      const int Ad = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        sm.canon[Ad ^ canon_swz(jj << 6)] += sing[jj];
+        sing[jj] = 0.0;
       }
     }
   }
@@ -900,24 +921,29 @@ void set_phase_timing(unsigned long long* d_buf, unsigned int cap_items) {
   g_phase_timing = d_buf != nullptr;
 }
 
-template <bool DUMP, bool TIMING, bool RAGGED, int ORDER>
+template <bool DUMP, bool TIMING, bool RAGGED, int ORDER, bool LAMBDA = false>
 static void launch_one(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                        double2* d_partials, long long total_items, double* dd, double* ds, cudaStream_t stream) {
   static bool attr_done = false;   // one flag per instantiation
   if (!attr_done) {
-    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_done = true;
   }
-  fused_kernel<DUMP, TIMING, RAGGED, ORDER><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
+  fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
       d_tuples, ntuples, d_descs, d_sdescs, d_partials, dd, ds);
 }
 
 static_assert(NWC_CTAS_PER_SM * (sizeof(FusedSmem) + 1024) <= 228 * 1024, "FusedSmem too large for the intended CTAs/SM");
 // order: index order inside the panel blocks (tables.h make_split), the one the panels of this launch were built with
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, int order, cudaStream_t stream) {
+                  double2* d_partials, long long total_items, bool ragged, int order, bool lambda, cudaStream_t stream) {
   if (total_items <= 0) return;
+  if (lambda) {   // the general (ragged-capable) kernel with the doubles-bound outer-product group
+    if (order) launch_one<false, false, true, 1, true>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream);
+    else launch_one<false, false, true, 0, true>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream);
+    return;
+  }
 #define NWC_L(D, T, R, O) launch_one<D, T, R, O>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream)
   if (g_phase_timing) { if (order) NWC_L(false, true, true, 1); else NWC_L(false, true, true, 0); return; }
   if (!ragged) { if (order) NWC_L(false, false, false, 1); else NWC_L(false, false, false, 0); return; }

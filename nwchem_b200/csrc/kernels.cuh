@@ -34,6 +34,7 @@ struct SinglesDesc {    // one fired sd_t_s1_K call:  S +-= t1[sum g*st1] * v2[s
   int neg;
   int pad;
 };
+constexpr int MAX_SINGLES_TERMS = 18;   // per tuple: nine sd_t_s1_K terms + nine doubles-bound outer products (Lambda-CCSD(T))
 
 struct TupleHdr {
   int R[6];             // ranges by physical position (h3,h2,h1,p6,p5,p4)
@@ -42,6 +43,8 @@ struct TupleHdr {
   double factor;        // ccsd_t_dot.F:52-66
   int desc_begin[10];   // split s owns descs [desc_begin[s], desc_begin[s+1])
   int sdesc_begin, sdesc_end;
+  int sdesc_mid;        // outer-product terms [sdesc_begin, sdesc_mid) are added to the DOUBLES tile, the rest are the singles
+  int pad2;
   long long item_begin; // first work item (sub-tile) of this tuple in the launch
   int nitems;            // work items of this launch (a sub-range when the tuple is split across GPUs)
   int item_first;        // index of the first of them inside the tuple's full sub-tile space
@@ -91,7 +94,7 @@ void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubl
 // ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
 // order: index order inside the panel blocks (tables.h make_split) the launch's panels were built with
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, int order, cudaStream_t stream);
+                  double2* d_partials, long long total_items, bool ragged, int order, bool lambda, cudaStream_t stream);
 // two-level deterministic reduction; d_chunk_sums holds ntuples * max_chunks double2 (max_chunks >= the largest
 // reduce_chunks(nitems) of the launch)
 int reduce_chunks(long long nitems);

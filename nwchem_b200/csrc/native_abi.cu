@@ -74,6 +74,10 @@ struct nwc_triples_ctx {
   // `2eorb` storage: orbital-form integrals resident, spin-orbital blocks built per batch in the arena
   double* d_v2orb = nullptr;
   size_t n_v2orb = 0;
+  // Lambda-CCSD(T) inputs (nwc_triples_set_lambda): lambda_1 (h,p), lambda_2 (hh,pp), Fock (h,p) blocks, replicated
+  double *d_y1 = nullptr, *d_y2 = nullptr, *d_f1 = nullptr;
+  size_t n_y1 = 0, n_y2 = 0, n_f1 = 0;
+  std::vector<Integer> y1_hash, y2_hash, f1_hash;
   // per batch slot (engine.h): blocks that live in that slot's arena
   std::unordered_map<Integer, const double*> v2_built[2];   // spin-orbital key -> antisymmetrised block
   std::unordered_map<Integer, const double*> pulled[2];     // block index -> local copy of a remote block
@@ -89,8 +93,10 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
   c->v2_peer.clear(); c->v2_peer_opened.clear(); c->v2_shard_off.clear(); c->v2_block_n.clear();
   c->v2_nshards = 1; c->v2_rank = 0;
   cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl);
-  c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = nullptr;
-  c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = 0;
+  cudaFree(c->d_y1); cudaFree(c->d_y2); cudaFree(c->d_f1);
+  c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = c->d_y1 = c->d_y2 = c->d_f1 = nullptr;
+  c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = c->n_y1 = c->n_y2 = c->n_f1 = 0;
+  c->y1_hash.clear(); c->y2_hash.clear(); c->f1_hash.clear();
   for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
   c->S.intorb = false; c->S.orb_off.clear(); c->S.host_off.clear(); c->S.orb_runs.clear(); c->S.orb_blocks.clear();
   c->S.orb_index.clear(); c->S.orb_size = c->S.orb_host_size = 0;
@@ -196,16 +202,31 @@ void slot_done(nwc_triples_ctx* c, int slot) {
   c->pulled[slot].clear();
 }
 
+// lambda_2 block key (h4b<=h5b, p1b<=p2b): lambda_ccsd_t_left.F:378-380
+inline Integer y2_key(const HostState& S, Integer h4, Integer h5, Integer p1, Integer p2) {
+  return p2 - S.noab - 1 + S.nvab * (p1 - S.noab - 1 + S.nvab * (h5 - 1 + S.noab * (h4 - 1)));
+}
+
+// The walkers of host_driver.h report the operand pairs of the (T) right-hand side.  With `lam` set the same walk
+// produces the Lambda-CCSD(T) LEFT-hand tiles: term by term, lambda_ccsd_t_left_1/_3/_4 are ccsd_t_singles /
+// ccsd_t_doubles with t1(p,h) -> lambda_1(h,p), t2(pp,hh) -> lambda_2(hh,pp) and every V2 block replaced by its
+// bra<->ket transpose, which for real orbitals is the same block the (T) path already holds (same index permutations,
+// same signs: compare lambda_ccsd_t_left.F:6-9 with ccsd_t_doubles.F / ccsd_t_singles.F).  So only the amplitude views
+// change: where they come from (Y stores), their block keys and their element strides (transposed layout).
 struct NativeSink {
   nwc_triples_ctx* c;
   Engine& e;
   const HostState& S;
+  bool lam = false;          // amplitudes from the lambda stores (left-hand side)
+  double yscale = 1.0;       // sign of the left-hand contractions in this run (+1 / -1: polarisation, see run_lambda)
+  bool want_singles = true;  // (T) right-hand side of Lambda-CCSD(T) uses the doubles only (lambda_ccsd_t.F:109-111)
+  bool want_doubles = true;
   // contracted tiles of the current row, concatenated along K when the row ends (engine.h Segment)
   std::vector<Segment> segs;
   bool row_fire[9] = {false, false, false, false, false, false, false, false, false};
   void push(const OperandView& t, const OperandView& v, double sign, Integer K, const bool fire[9]) {
     Segment sg;
-    sg.K = (int)K; sg.t = t; sg.v = v; sg.tscale = sign;
+    sg.K = (int)K; sg.t = t; sg.v = v; sg.tscale = sign * (lam ? yscale : 1.0);
     segs.push_back(sg);
     for (int k = 0; k < 9; k++) row_fire[k] = fire[k];
   }
@@ -217,13 +238,32 @@ struct NativeSink {
     }
     segs.clear();
   }
+  // two-particle amplitude block over the tiles (pA<=pB | hC<=hD) (ids after tce_restricted_4; ranges rA..rD):
+  // base pointer and the element strides of pA, pB, hC, hD
+  const double* amp2(Integer pA, Integer pB, Integer hC, Integer hD, Integer rA, Integer rB, Integer rC, Integer rD,
+                     long long st[4]) const {
+    if (!lam) {   // T2 block [pA][pB][hC][hD], hD fastest (tce_t2_offset_new.F)
+      st[3] = 1; st[2] = rD; st[1] = rC * rD; st[0] = rB * rC * rD;
+      return c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, pA, pB, hC, hD), "t2");
+    }
+    // lambda_2 block [hC][hD][pA][pB], pB fastest
+    st[1] = 1; st[0] = rB; st[3] = rA * rB; st[2] = rD * rA * rB;
+    return c->d_y2 + hash_lookup_or_die(c->y2_hash, y2_key(S, hC, hD, pA, pB), "lambda2");
+  }
 
   void singles(const Row& r, Integer p4b_1, Integer h1b_1, Integer p5b_2, Integer p6b_2, Integer h2b_2, Integer h3b_2,
                const bool fire[9]) {
+    if (!want_singles) return;
     OperandView t, v;
-    // T1 block stored (p4,h1) with h1 fastest; the reference's TCE_SORT_2(2,1) becomes a stride swap
-    t.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
-    t.stride[N_H1] = 1; t.stride[N_P4] = S.rg(r.h1b);
+    if (!lam) {
+      // T1 block stored (p4,h1) with h1 fastest; the reference's TCE_SORT_2(2,1) becomes a stride swap
+      t.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, p4b_1, h1b_1), "t1");
+      t.stride[N_H1] = 1; t.stride[N_P4] = S.rg(r.h1b);
+    } else {
+      // lambda_1 block stored (h4,p1), p1 fastest; key p1b-noab-1 + nvab*(h4b-1) (lambda_ccsd_t_left.F:154-155)
+      t.base = c->d_y1 + hash_lookup_or_die(c->y1_hash, p4b_1 - S.noab - 1 + S.nvab * (h1b_1 - 1), "lambda1");
+      t.stride[N_P4] = 1; t.stride[N_H1] = S.rg(r.p4b);
+    }
     // V2 block <p5 p6||h2 h3> stored (p5,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,p5)
     v.base = v2_operand(c, p5b_2, p6b_2, h2b_2, h3b_2, "v2(pphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
@@ -233,16 +273,18 @@ struct NativeSink {
   }
 
   void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
-    const Integer rp5 = S.rg(r.p5b), rh1 = S.rg(r.h1b), rh7 = S.rg(h7b);
+    if (!want_doubles) return;
+    const Integer rp4 = S.rg(r.p4b), rp5 = S.rg(r.p5b), rh1 = S.rg(r.h1b), rh7 = S.rg(h7b);
     OperandView t, v;
     double sign;
-    if (h7b < r.h1b) {  // block <p4 p5||h7 h1>, h1 fastest; TCE_SORT_4(4,2,1,3), factor -1 (tce_hashnsort.F:47-53)
-      t.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[3], am[2]), "t2");
-      t.stride[N_H1] = 1; t.kstride = rh1; t.stride[N_P5] = rh7 * rh1; t.stride[N_P4] = rp5 * rh7 * rh1;
+    long long st[4];
+    if (h7b < r.h1b) {  // block <p4 p5||h7 h1>; TCE_SORT_4(4,2,1,3), factor -1 (tce_hashnsort.F:47-53; left_3 :614-621)
+      t.base = amp2(am[0], am[1], am[3], am[2], rp4, rp5, rh7, rh1, st);
+      t.stride[N_P4] = st[0]; t.stride[N_P5] = st[1]; t.kstride = st[2]; t.stride[N_H1] = st[3];
       sign = -1.0;
-    } else {            // block <p4 p5||h1 h7>, h7 fastest; TCE_SORT_4(3,2,1,4), factor +1 (:55-62)
-      t.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
-      t.kstride = 1; t.stride[N_H1] = rh7; t.stride[N_P5] = rh1 * rh7; t.stride[N_P4] = rp5 * rh1 * rh7;
+    } else {            // block <p4 p5||h1 h7>; TCE_SORT_4(3,2,1,4), factor +1 (:55-62; left_3 :622-629)
+      t.base = amp2(am[0], am[1], am[2], am[3], rp4, rp5, rh1, rh7, st);
+      t.stride[N_P4] = st[0]; t.stride[N_P5] = st[1]; t.stride[N_H1] = st[2]; t.kstride = st[3];
       sign = 1.0;
     }
     // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
@@ -253,16 +295,18 @@ struct NativeSink {
   }
 
   void d2_pair(const Row& r, Integer p7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
+    if (!want_doubles) return;
     const Integer rp4 = S.rg(r.p4b), rp7 = S.rg(p7b), rh1 = S.rg(r.h1b), rh2 = S.rg(r.h2b);
     OperandView t, v;
     double sign;
-    if (p7b < r.p4b) {  // block <p7 p4||h1 h2>; TCE_SORT_4(4,3,2,1), factor -1 (tce_hashnsort.F:129-135)
-      t.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[1], am[0], am[2], am[3]), "t2");
-      t.stride[N_H2] = 1; t.stride[N_H1] = rh2; t.stride[N_P4] = rh1 * rh2; t.kstride = rp4 * rh1 * rh2;
+    long long st[4];
+    if (p7b < r.p4b) {  // block <p7 p4||h1 h2>; TCE_SORT_4(4,3,2,1), factor -1 (tce_hashnsort.F:129-135; left_4 :856-863)
+      t.base = amp2(am[1], am[0], am[2], am[3], rp7, rp4, rh1, rh2, st);
+      t.kstride = st[0]; t.stride[N_P4] = st[1]; t.stride[N_H1] = st[2]; t.stride[N_H2] = st[3];
       sign = -1.0;
-    } else {            // block <p4 p7||h1 h2>; TCE_SORT_4(4,3,1,2), factor +1 (:137-144)
-      t.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
-      t.stride[N_H2] = 1; t.stride[N_H1] = rh2; t.kstride = rh1 * rh2; t.stride[N_P4] = rp7 * rh1 * rh2;
+    } else {            // block <p4 p7||h1 h2>; TCE_SORT_4(4,3,1,2), factor +1 (:137-144; left_4 :864-871)
+      t.base = amp2(am[0], am[1], am[2], am[3], rp4, rp7, rh1, rh2, st);
+      t.stride[N_P4] = st[0]; t.kstride = st[1]; t.stride[N_H1] = st[2]; t.stride[N_H2] = st[3];
       sign = 1.0;
     }
     // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161)
@@ -290,6 +334,58 @@ void emit_tuple(nwc_triples_ctx* c, const Integer t[6], long long item_lo = 0, l
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
   c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
+}
+
+// Lambda-CCSD(T), one of the two polarisation runs of a tuple (yscale = +1 / -1):
+//   doubles tile D = Td + yscale * Yd,  singles tile S = Ys,
+// Td = ccsd_t_doubles(T2,V2) (lambda_ccsd_t.F:109-111), Ys = y1*v (lambda_ccsd_t_left_1), Yd = y2*f (left_2, the
+// doubles-bound outer products) - sum_h7 y2*v (left_3) - sum_p7 y2*v (left_4).
+void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale) {
+  const HostState& S = c->S;
+  int R[6];
+  tuple_ranges(S, t, R);
+  c->eng->begin_tuple(R);
+  {   // right-hand doubles
+    NativeSink rhs{c, *c->eng, S};
+    rhs.want_singles = false;
+    walk_doubles(S, t, rhs);
+  }
+  {   // left-hand contractions (into the same doubles tile, signed) and left-hand singles
+    NativeSink lhs{c, *c->eng, S};
+    lhs.lam = true;
+    lhs.yscale = yscale;
+    walk_singles(S, t, lhs);
+    walk_doubles(S, t, lhs);
+  }
+  // lambda_ccsd_t_left_2: i0(h4 h5 h6 p1 p2 p3) += P(9) y(h4 h5 p1 p2) f(h6 p3).  Written from the algebra: one particle
+  // P_a and one hole H_b of the tuple go to f, the other two of each kind (ascending, hence canonical blocks) to y2;
+  // P(h4 h5 / h6) = 1 - (h6<->h4) - (h6<->h5) gives the sign -1 exactly when the MIDDLE hole (particle) is the special
+  // one (cf. the nine TCE_SORTACC_6 factors at lambda_ccsd_t_left.F:416-472).  Equal tiles need no special casing: the
+  // nine terms are distinct index assignments of the same t3 element.
+  const int ppos[3] = {POS_P4, POS_P5, POS_P6}, hpos[3] = {POS_H1, POS_H2, POS_H3};
+  const Integer N = S.N();
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2, x = b == 0 ? 1 : 0, y = b == 2 ? 1 : 2;
+      const Integer Pa = t[a], Pu = t[u], Pv = t[v], Hb = t[3 + b], Hx = t[3 + x], Hy = t[3 + y];
+      if (S.sp(Hb) != S.sp(Pa) || (S.sy(Hb) ^ S.sy(Pa)) != 0) continue;                                     // :366-367
+      if (S.sp(Hx) + S.sp(Hy) != S.sp(Pu) + S.sp(Pv) || (S.sy(Hx) ^ S.sy(Hy) ^ S.sy(Pu) ^ S.sy(Pv)) != 0) continue;
+      const Integer four[4] = {Hx, Hy, Pu, Pv}, two[2] = {Hb, Pa};
+      Integer m4[4], m2[2];
+      restricted_map(S, 4, four, m4);                                                                       // :368
+      restricted_map(S, 2, two, m2);                                                                        // :369
+      const double* fblk = c->d_f1 + hash_lookup_or_die(c->f1_hash, m2[1] - 1 + N * (m2[0] - 1), "f1(hp)");  // :390-391
+      const double* yblk = c->d_y2 + hash_lookup_or_die(c->y2_hash, y2_key(S, m4[0], m4[1], m4[2], m4[3]), "lambda2");
+      int sa[6] = {0, 0, 0, 0, 0, 0}, sb[6] = {0, 0, 0, 0, 0, 0};
+      sa[ppos[a]] = 1; sa[hpos[b]] = (int)S.rg(Pa);                       // f block (h6,p3), p3 fastest
+      sb[ppos[v]] = 1; sb[ppos[u]] = (int)S.rg(Pv);                       // y2 block (h4,h5,p1,p2), p2 fastest
+      sb[hpos[y]] = (int)(S.rg(Pu) * S.rg(Pv)); sb[hpos[x]] = (int)(S.rg(Hy) * S.rg(Pu) * S.rg(Pv));
+      const bool neg = ((a == 1) != (b == 1)) != (yscale < 0);
+      c->eng->add_outer_product(fblk, sa, yblk, sb, neg, /*to_doubles=*/true);
+    }
+  const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
+                          c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
+  c->eng->end_tuple(eps, tuple_factor(S, t));
 }
 
 // Double-buffered batch loop: while the GPU runs batch k the host walks the driver logic of batch k+1 into the other
@@ -790,6 +886,86 @@ int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, I
     }
     *t_energy = 0.0;
     for (Integer i = 0; i < S.nvab; i++) *t_energy += table[i];
+    return 0;
+  });
+}
+
+// ---- Lambda-CCSD(T) (src/tce/ccsd_t/lambda_ccsd_t.F) ----
+// lambda_1 / lambda_2 / Fock(h,p) block stores with their offset tables ([n, keys.., offsets..]; keys as in
+// lambda_ccsd_t_left.F:154-155, :378-380, :390-391), replicated in HBM.  Call after a set_state* variant.
+int nwc_triples_set_lambda(nwc_triples_ctx* c, const Integer* y1_hash, const double* y1, const Integer* y2_hash,
+                           const double* y2, const Integer* f1_hash, const double* f1) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    auto load = [&](const Integer* h, const double* data, std::vector<Integer>& tab, double** d, size_t* n, int kind) -> int {
+      const Integer nb = h[0];
+      tab.assign(h, h + 2 * nb + 1);
+      size_t total = 0;
+      if (nb > 0) {   // size of the last block from its key
+        Integer key = h[nb], sz = 0;
+        if (kind == 2) {
+          const Integer p2 = key % S.nvab + S.noab + 1; key /= S.nvab;
+          const Integer p1 = key % S.nvab + S.noab + 1; key /= S.nvab;
+          const Integer h5 = key % S.noab + 1; key /= S.noab;
+          if (key < 0 || key >= S.noab) throw Error("nwc_triples: lambda_2 offset table does not belong to this tiling");
+          sz = S.rg(key + 1) * S.rg(h5) * S.rg(p1) * S.rg(p2);
+        } else if (kind == 1) {
+          const Integer p1 = key % S.nvab + S.noab + 1, h4 = key / S.nvab + 1;
+          if (h4 < 1 || h4 > S.noab) throw Error("nwc_triples: lambda_1 offset table does not belong to this tiling");
+          sz = S.rg(h4) * S.rg(p1);
+        } else {
+          const Integer g2 = key % S.N() + 1, g1 = key / S.N() + 1;
+          if (g1 < 1 || g1 > S.N()) throw Error("nwc_triples: f1 offset table does not belong to this tiling");
+          sz = S.rg(g1) * S.rg(g2);
+        }
+        total = (size_t)(h[2 * nb] + sz);
+      }
+      return upload(d, n, data, total, c->eng);
+    };
+    if (load(y1_hash, y1, c->y1_hash, &c->d_y1, &c->n_y1, 1)) return 1;
+    if (load(y2_hash, y2, c->y2_hash, &c->d_y2, &c->n_y2, 2)) return 1;
+    if (load(f1_hash, f1, c->f1_hash, &c->d_f1, &c->n_f1, 3)) return 1;
+    return 0;
+  });
+}
+
+// Lambda-CCSD[T] / Lambda-CCSD(T) correction energies of tasks first, first+stride, ... (lambda_ccsd_t.F:59-190):
+//   energy[0] = sum f Td Yd / Delta ,  energy[1] = sum f Td (Ys + Yd) / Delta ,
+// the left-hand tiles taken in T3 order (the sort lambda_ccsd_t.F:35-36 announces; see oracle/triples_oracle.c for the
+// literal reading of the file).  The t3-sized tiles never exist in HBM here either: every tuple goes through the
+// UNMODIFIED fused kernel twice, with doubles tile D+ = Td + Yd and D- = Td - Yd and singles tile Ys, and
+//   sum Td Yd / Delta = ( E[D+] - E[D-] ) / 4 ,   sum Td Ys / Delta = ( ES[D+] + ES[D-] ) / 2
+// (polarisation identity; E = the kernel's sum f D^2/Delta, ES = its sum f D S/Delta).  Costs twice the minimal
+// FLOPs of this sibling, in exchange for no second kernel.
+int nwc_triples_run_lambda(nwc_triples_ctx* c, Integer first, Integer stride, Integer max_tasks, double energy[2],
+                           double* per_task) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_run_lambda: call nwc_triples_set_lambda first"; return 1; }
+    if (stride <= 0) stride = 1;
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    Integer cnt = 0;
+    for (Integer k = first; k < nt && (max_tasks <= 0 || cnt < max_tasks); k += stride) cnt++;
+    std::vector<double> raw(4 * (size_t)cnt + 4, 0.0);   // per task: (E, E+ES) of the + run, then of the - run
+    double dummy[2] = {0.0, 0.0};
+    Pipeline pipe(c, dummy, raw.data());
+    Integer done = 0;
+    for (Integer k = first; k < nt && done < cnt; k += stride, done++) {
+      emit_tuple_lambda(c, &c->klist[7 * k], +1.0);
+      pipe.emitted(2 * done);
+      emit_tuple_lambda(c, &c->klist[7 * k], -1.0);
+      pipe.emitted(2 * done + 1);
+    }
+    pipe.finish();
+    energy[0] = energy[1] = 0.0;
+    for (Integer i = 0; i < cnt; i++) {
+      const double ep = raw[4 * i], sp_ = raw[4 * i + 1] - raw[4 * i], em = raw[4 * i + 2], sm_ = raw[4 * i + 3] - raw[4 * i + 2];
+      const double e1 = 0.25 * (ep - em), e2 = e1 + 0.5 * (sp_ + sm_);
+      energy[0] += e1;
+      energy[1] += e2;
+      if (per_task) { per_task[2 * i] = e1; per_task[2 * i + 1] = e2; }
+    }
     return 0;
   });
 }

@@ -195,6 +195,67 @@ def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = 
     return BlockStores(t, t1h, t1, t2h, t2, v2h, v2, orb)
 
 
+@dataclasses.dataclass
+class LambdaStores:
+    """Inputs of the Lambda-CCSD(T) left-hand side: lambda_1 (h,p), lambda_2 (hh,pp), Fock (h,p) blocks."""
+    y1_hash: np.ndarray; y1: np.ndarray
+    y2_hash: np.ndarray; y2: np.ndarray
+    f1_hash: np.ndarray; f1: np.ndarray
+
+
+def physical_lambda(t: tl.Tiling, seed: int = 777) -> LambdaStores:
+    """Closed-shell spatial lambda_1[i,a], lambda_2[i,j,a,b] (= lambda_2[j,i,b,a]) and f[i,a], spin-integrated into TCE
+    blocks exactly like `physical` does for t1/t2 (tiling-independent draws, so tile-size invariance can be tested)."""
+    no = int(sum(t.range[i] for i in range(t.noab) if t.spin[i] == 1))
+    nv = int(sum(t.range[i] for i in range(t.noab, t.noab + t.nvab) if t.spin[i] == 1))
+    irr = np.zeros(no + nv, dtype=np.int64)
+    for b in range(t.noab + t.nvab):
+        if t.spin[b] == 1:
+            irr[t.members[b]] = t.sym[b]
+    rng = np.random.default_rng(seed)
+    y1s = rng.uniform(-1, 1, (no, nv)) * 0.05
+    y2s = rng.uniform(-1, 1, (no, no, nv, nv)) * 0.02
+    y2s = 0.5 * (y2s + y2s.transpose(1, 0, 3, 2))
+    fs = rng.uniform(-1, 1, (no, nv)) * 0.01
+    io, iv = irr[:no], irr[no:]
+    y1s[(io[:, None] ^ iv[None, :]) != 0] = 0.0
+    fs[(io[:, None] ^ iv[None, :]) != 0] = 0.0
+    m = io[:, None, None, None] ^ io[None, :, None, None] ^ iv[None, None, :, None] ^ iv[None, None, None, :]
+    y2s[m != 0] = 0.0
+
+    def so(b):
+        return t.members[b - 1], int(t.spin[b - 1])
+
+    y1h, n1 = tl.y1_offset(t); y2h, n2 = tl.y2_offset(t); f1h, nf = tl.f1_hp_offset(t)
+    y1 = np.zeros(n1); y2 = np.zeros(n2); f1 = np.zeros(nf)
+    N = t.noab + t.nvab
+    for key, off in _iter_hash(y1h):
+        h4b, p1b = key // t.nvab + 1, key % t.nvab + t.noab + 1
+        (i, _), (a, _) = so(h4b), so(p1b)
+        blk = y1s[np.ix_(i, a - no)]
+        y1[off:off + blk.size] = blk.ravel()
+    for key, off in _iter_hash(f1h):
+        h6b, p3b = key // N + 1, key % N + 1
+        (i, _), (a, _) = so(h6b), so(p3b)
+        blk = fs[np.ix_(i, a - no)]
+        f1[off:off + blk.size] = blk.ravel()
+    for key, off in _iter_hash(y2h):
+        k = key
+        p2b = k % t.nvab + t.noab + 1; k //= t.nvab
+        p1b = k % t.nvab + t.noab + 1; k //= t.nvab
+        h5b = k % t.noab + 1; k //= t.noab
+        h4b = k + 1
+        (i, si), (j, sj), (a, sa), (b, sb) = so(h4b), so(h5b), so(p1b), so(p2b)
+        a, b = a - no, b - no
+        blk = np.zeros((len(i), len(j), len(a), len(b)))
+        if si == sa and sj == sb:
+            blk += y2s[np.ix_(i, j, a, b)]
+        if si == sb and sj == sa:
+            blk -= y2s[np.ix_(i, j, b, a)].transpose(0, 1, 3, 2)
+        y2[off:off + blk.size] = blk.ravel()
+    return LambdaStores(y1h, y1, y2h, y2, f1h, f1)
+
+
 # ---- named shapes of BASELINE.json's configs (alpha occ / alpha virt, C1 unless stated) ----
 SHAPES = {
     # H2O cc-pVDZ on the exact QA tile table (tce_ccsd_t_h2o.out:644-659): irreps a1,a2,b1,b2 = 0,1,2,3

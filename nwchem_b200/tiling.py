@@ -172,6 +172,57 @@ def v2_offset(t: Tiling, irrep_v: int = 0, triples_only: bool = True):
     return _hash(keys, sizes)
 
 
+# ---- Lambda-CCSD(T) inputs (src/tce/ccsd_t/lambda_ccsd_t_left.F): lambda_1, lambda_2 and the (h,p) Fock blocks ----
+def y1_offset(t: Tiling, irrep: int = 0):
+    """lambda_1 blocks (h4b, p1b), key p1b-noab-1 + nvab*(h4b-1) (lambda_ccsd_t_left.F:154-155)."""
+    keys, sizes = [], []
+    for h4b in range(1, t.noab + 1):
+        for p1b in range(t.noab + 1, t.noab + t.nvab + 1):
+            if t.spin[h4b - 1] != t.spin[p1b - 1] or (t.sym[h4b - 1] ^ t.sym[p1b - 1]) != irrep:
+                continue
+            if t.restricted and t.spin[h4b - 1] + t.spin[p1b - 1] == 4:
+                continue
+            keys.append(p1b - t.noab - 1 + t.nvab * (h4b - 1))
+            sizes.append(t.r(h4b) * t.r(p1b))
+    return _hash(keys, sizes)
+
+
+def y2_offset(t: Tiling, irrep: int = 0):
+    """lambda_2 blocks (h4b<=h5b, p1b<=p2b), key p2b-noab-1 + nvab*(p1b-noab-1 + nvab*(h5b-1 + noab*(h4b-1)))
+    (lambda_ccsd_t_left.F:378-380)."""
+    keys, sizes = [], []
+    sp, sy = t.spin, t.sym
+    for h4b in range(1, t.noab + 1):
+        for h5b in range(h4b, t.noab + 1):
+            for p1b in range(t.noab + 1, t.noab + t.nvab + 1):
+                for p2b in range(p1b, t.noab + t.nvab + 1):
+                    if sp[h4b - 1] + sp[h5b - 1] != sp[p1b - 1] + sp[p2b - 1]:
+                        continue
+                    if (sy[h4b - 1] ^ sy[h5b - 1] ^ sy[p1b - 1] ^ sy[p2b - 1]) != irrep:
+                        continue
+                    if t.restricted and sp[h4b - 1] + sp[h5b - 1] + sp[p1b - 1] + sp[p2b - 1] == 8:
+                        continue
+                    keys.append(p2b - t.noab - 1 + t.nvab * (p1b - t.noab - 1 + t.nvab * (h5b - 1 + t.noab * (h4b - 1))))
+                    sizes.append(t.r(h4b) * t.r(h5b) * t.r(p1b) * t.r(p2b))
+    return _hash(keys, sizes)
+
+
+def f1_hp_offset(t: Tiling, irrep: int = 0):
+    """The (hole, particle) blocks of the Fock file, key p3b-1 + (noab+nvab)*(h6b-1) (lambda_ccsd_t_left.F:390-391);
+    the other classes of f1 are not read by the (T)-type corrections and are left out of the table."""
+    keys, sizes = [], []
+    N = t.noab + t.nvab
+    for h6b in range(1, t.noab + 1):
+        for p3b in range(t.noab + 1, N + 1):
+            if t.spin[h6b - 1] != t.spin[p3b - 1] or (t.sym[h6b - 1] ^ t.sym[p3b - 1]) != irrep:
+                continue
+            if t.restricted and t.spin[h6b - 1] + t.spin[p3b - 1] == 4:
+                continue
+            keys.append(p3b - 1 + N * (h6b - 1))
+            sizes.append(t.r(h6b) * t.r(p3b))
+    return _hash(keys, sizes)
+
+
 def decode_t1_key(t: Tiling, key: int):
     return key // t.noab + t.noab + 1, key % t.noab + 1  # (p5b, h6b)
 

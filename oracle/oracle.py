@@ -220,6 +220,51 @@ def tuple_sliced(st, tup, width=4):
     return e1, e2
 
 
+class Lambda(C.Structure):   # ora_lambda
+    _fields_ = [("y1_hash", PL), ("y1", PD), ("y2_hash", PL), ("y2", PD), ("f1_hash", PL), ("f1", PD),
+                ("irrep_y", L), ("irrep_f", L)]
+
+
+def make_lambda(lam):
+    k = dict(y1h=np.ascontiguousarray(lam.y1_hash, np.int64), y1=np.ascontiguousarray(lam.y1, np.float64),
+             y2h=np.ascontiguousarray(lam.y2_hash, np.int64), y2=np.ascontiguousarray(lam.y2, np.float64),
+             f1h=np.ascontiguousarray(lam.f1_hash, np.int64), f1=np.ascontiguousarray(lam.f1, np.float64))
+    return Lambda(_pl(k["y1h"]), _pd(k["y1"]), _pl(k["y2h"]), _pd(k["y2"]), _pl(k["f1h"]), _pd(k["f1"]), 0, 0), k
+
+
+def lambda_ccsd_t(st, lam, sorted=True):
+    """Lambda-CCSD(T) on the CPU (lambda_ccsd_t.F + lambda_ccsd_t_left.F restated).  sorted=False reproduces the file
+    literally (L3-ordered left tiles multiplied element-wise with the T3-ordered right tile); sorted=True applies the
+    sort its declarations announce.  Returns dict(e1, e2, per_task) in the loop order of lambda_ccsd_t.F:59-64."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_lambda(lam)
+    n = len(task_list(st.t))
+    e = np.zeros(2); pt = np.zeros((max(n, 1), 2))
+    l.ora_lambda_ccsd_t.restype = L
+    cnt = l.ora_lambda_ccsd_t(C.byref(c), C.byref(y), int(bool(sorted)), _pd(e), _pd(pt))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return dict(e1=float(e[0]), e2=float(e[1]), per_task=pt[:cnt])
+
+
+def lambda_tuple(st, lam, tup, sorted=True):
+    """One tuple (p4b..h3b): (e1, e2, tdoubles [p4,p5,p6,h1,h2,h3], ysingles, ydoubles [h1,h2,h3,p4,p5,p6])."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_lambda(lam)
+    t = st.t
+    dims = [t.r(int(b)) for b in tup[:6]]
+    n = int(np.prod(dims))
+    td = np.zeros(n); ys = np.zeros(n); yd = np.zeros(n); e = np.zeros(2)
+    tt = np.array(tup[:6], np.int64)
+    l.ora_lambda_ccsd_t_tuple(C.byref(c), C.byref(y), _pl(tt), int(bool(sorted)), _pd(e), _pd(td), _pd(ys), _pd(yd))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    ld = dims[3:] + dims[:3]
+    return float(e[0]), float(e[1]), td.reshape(dims), ys.reshape(ld), yd.reshape(ld)
+
+
 def count_tuple(st_or_ctx, tup, keep=None):
     l = lib()
     c, keep = make_ctx(st_or_ctx) if keep is None else (st_or_ctx, keep)

@@ -1124,3 +1124,245 @@ int ora_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Lambda-CCSD(T): src/tce/ccsd_t/lambda_ccsd_t.F + lambda_ccsd_t_left.F                  */
+/*                                                                                        */
+/* E1 = sum f * Td * Yd / Delta, E2 = sum f * Td * (Ys + Yd) / Delta (lambda_ccsd_t.F     */
+/* :137-176) with Td = ccsd_t_doubles (the TCE form restated above, :109-111), Ys =        */
+/* lambda_ccsd_t_left toggle 1 (:121-124), Yd = toggle 2 (:131-134).  The left-hand side   */
+/* is TCE-generated like ccsd_t_singles.F / ccsd_t_doubles.F: a six-deep tile loop, nine   */
+/* dispatch tests, operands sorted, DGEMM('T','N'), one TCE_SORTACC_6 per test.  The loop  */
+/* bounds, tests, c_sort dimension order and the 36 permutation/sign pairs are in          */
+/* lambda_tables.h, extracted mechanically from lambda_ccsd_t_left.F by                    */
+/* oracle/gen_lambda_tables.py; the operand fetches below are restated by hand with their  */
+/* line numbers.                                                                           */
+/*                                                                                        */
+/* NOTE on layouts.  The nine TCE_SORTACC_6 calls of every left routine deliver            */
+/* a_i0(h4,h5,h6,p1,p2,p3), p3 fastest ("L3 form"), whereas ccsd_t_doubles delivers        */
+/* (p4,p5,p6,h1,h2,h3), h3 fastest ("T3 form"), and lambda_ccsd_t.F:147-176 multiplies the */
+/* two arrays element by element with ONE running index.  Its declarations (:35-36) name   */
+/* a sort from L3 to T3 form that the file does not contain.  `sorted` = 0 reproduces the  */
+/* file literally, `sorted` = 1 applies the announced sort first.  The two coincide when   */
+/* every tile has range 1 (tilesize 1); only the sorted form is tile-size invariant        */
+/* (tests/test_lambda.py).                                                                 */
+/* ------------------------------------------------------------------------------------ */
+#include "lambda_tables.h"
+
+typedef struct {
+  const Integer *y1_hash; const double *y1; /* lambda_1 (h4,p1) blocks, key p1b-noab-1 + nvab*(h4b-1)            */
+  const Integer *y2_hash; const double *y2; /* lambda_2 (h4<=h5,p1<=p2) blocks                                   */
+  const Integer *f1_hash; const double *f1; /* Fock blocks, key g2b-1 + (noab+nvab)*(g1b-1); only (h,p) are read */
+  Integer irrep_y, irrep_f;
+} ora_lambda;
+
+/* c_sort of routine r for the tiles v[] = (h4b,h5b,h6b,p1b,p2b,p3b); returns 0 if the tile filters reject them */
+static int lambda_left_csort(const ora_ctx *c, const ora_lambda *y, int r, const Integer v[6], double *c_sort) {
+  const Integer h4b = v[0], h5b = v[1], h6b = v[2], p1b = v[3], p2b = v[4], p3b = v[5];
+  const Integer noab = c->noab, nvab = c->nvab, N = noab + nvab;
+  const Integer ssum = SPIN(h4b) + SPIN(h5b) + SPIN(h6b) + SPIN(p1b) + SPIN(p2b) + SPIN(p3b);
+  if (c->restricted && ssum == 12) return 0;                                            /* e.g. :120-122 */
+  if (SPIN(h4b) + SPIN(h5b) + SPIN(h6b) != SPIN(p1b) + SPIN(p2b) + SPIN(p3b)) return 0; /* :123-125 */
+  const Integer irr = (r == 1) ? (y->irrep_y ^ y->irrep_f) : (y->irrep_y ^ c->irrep_v);  /* :126-128 / :350-352 */
+  if ((SYM(h4b) ^ SYM(h5b) ^ SYM(h6b) ^ SYM(p1b) ^ SYM(p2b) ^ SYM(p3b)) != irr) return 0;
+  const Integer dimc = RANGE(h4b) * RANGE(h5b) * RANGE(h6b) * RANGE(p1b) * RANGE(p2b) * RANGE(p3b);
+  memset(c_sort, 0, sizeof(double) * (size_t)dimc);
+  if (r == 0) { /* lambda_ccsd_t_left_1: y(h4 p1) * v(h5 h6 p2 p3), :134-176 */
+    if (SPIN(h4b) != SPIN(p1b) || (SYM(h4b) ^ SYM(p1b)) != y->irrep_y) return 1;
+    Integer h4b_1, p1b_1, h5b_2, h6b_2, p2b_2, p3b_2;
+    restricted_2(c, h4b, p1b, &h4b_1, &p1b_1);
+    restricted_4(c, h5b, h6b, p2b, p3b, &h5b_2, &h6b_2, &p2b_2, &p3b_2);
+    const Integer dima = RANGE(h4b) * RANGE(p1b), dimb = RANGE(h5b) * RANGE(h6b) * RANGE(p2b) * RANGE(p3b);
+    double *k_a = (double *)malloc(sizeof(double) * dima), *a_sort = (double *)malloc(sizeof(double) * dima);
+    double *k_b = (double *)malloc(sizeof(double) * dimb), *b_sort = (double *)malloc(sizeof(double) * dimb);
+    get_hash_block(y->y1, k_a, dima, y->y1_hash, p1b_1 - noab - 1 + nvab * (h4b_1 - 1));               /* :154-155 */
+    ora_tce_sort_2(k_a, a_sort, RANGE(h4b), RANGE(p1b), 2, 1, 1.0);                                    /* :156-157 */
+    get_v2_block(c, k_b, dimb, p3b_2 - 1 + N * (p2b_2 - 1 + N * (h6b_2 - 1 + N * (h5b_2 - 1))), p3b_2, p2b_2, h6b_2,
+                 h5b_2);                                                                               /* :164-166 */
+    ora_tce_sort_4(k_b, b_sort, RANGE(h5b), RANGE(h6b), RANGE(p2b), RANGE(p3b), 4, 3, 2, 1, 1.0);      /* :167-169 */
+    for (Integer ib = 0; ib < dimb; ib++) /* DGEMM('T','N',dima_sort,dimb_sort,1,...), :172-174 */
+      for (Integer ia = 0; ia < dima; ia++) c_sort[ia + dima * ib] += a_sort[ia] * b_sort[ib];
+    free(k_a); free(a_sort); free(k_b); free(b_sort);
+  } else if (r == 1) { /* _2: y(h4 h5 p1 p2) * f(h6 p3), :358-400 */
+    if (SPIN(h4b) + SPIN(h5b) != SPIN(p1b) + SPIN(p2b) || (SYM(h4b) ^ SYM(h5b) ^ SYM(p1b) ^ SYM(p2b)) != y->irrep_y) return 1;
+    Integer h4b_1, h5b_1, p1b_1, p2b_1, h6b_2, p3b_2;
+    restricted_4(c, h4b, h5b, p1b, p2b, &h4b_1, &h5b_1, &p1b_1, &p2b_1);
+    restricted_2(c, h6b, p3b, &h6b_2, &p3b_2);
+    const Integer dima = RANGE(h4b) * RANGE(h5b) * RANGE(p1b) * RANGE(p2b), dimb = RANGE(h6b) * RANGE(p3b);
+    double *k_a = (double *)malloc(sizeof(double) * dima), *a_sort = (double *)malloc(sizeof(double) * dima);
+    double *k_b = (double *)malloc(sizeof(double) * dimb), *b_sort = (double *)malloc(sizeof(double) * dimb);
+    get_hash_block(y->y2, k_a, dima, y->y2_hash,
+                   p2b_1 - noab - 1 + nvab * (p1b_1 - noab - 1 + nvab * (h5b_1 - 1 + noab * (h4b_1 - 1))));   /* :378-380 */
+    ora_tce_sort_4(k_a, a_sort, RANGE(h4b), RANGE(h5b), RANGE(p1b), RANGE(p2b), 4, 3, 2, 1, 1.0);             /* :381-383 */
+    get_hash_block(y->f1, k_b, dimb, y->f1_hash, p3b_2 - 1 + N * (h6b_2 - 1));                                /* :390-391 */
+    ora_tce_sort_2(k_b, b_sort, RANGE(h6b), RANGE(p3b), 2, 1, 1.0);                                           /* :392-393 */
+    for (Integer ib = 0; ib < dimb; ib++)
+      for (Integer ia = 0; ia < dima; ia++) c_sort[ia + dima * ib] += a_sort[ia] * b_sort[ib];
+    free(k_a); free(a_sort); free(k_b); free(b_sort);
+  } else if (r == 2) { /* _3: - sum_h7 y(h4 h7 p1 p2) * v(h5 h6 h7 p3), :595-650 */
+    for (Integer h7b = 1; h7b <= noab; h7b++) {
+      if (SPIN(h4b) + SPIN(h7b) != SPIN(p1b) + SPIN(p2b) || (SYM(h4b) ^ SYM(h7b) ^ SYM(p1b) ^ SYM(p2b)) != y->irrep_y) continue;
+      Integer h4b_1, h7b_1, p1b_1, p2b_1, h5b_2, h6b_2, p3b_2, h7b_2;
+      restricted_4(c, h4b, h7b, p1b, p2b, &h4b_1, &h7b_1, &p1b_1, &p2b_1);
+      restricted_4(c, h5b, h6b, p3b, h7b, &h5b_2, &h6b_2, &p3b_2, &h7b_2);
+      const Integer K = RANGE(h7b), ma = RANGE(h4b) * RANGE(p1b) * RANGE(p2b), mb = RANGE(h5b) * RANGE(h6b) * RANGE(p3b);
+      if (K * ma <= 0 || K * mb <= 0) continue;
+      double *k_a = (double *)malloc(sizeof(double) * K * ma), *a_sort = (double *)malloc(sizeof(double) * K * ma);
+      double *k_b = (double *)malloc(sizeof(double) * K * mb), *b_sort = (double *)calloc((size_t)(K * mb), sizeof(double));
+      if (h7b < h4b) { /* :614-621 */
+        get_hash_block(y->y2, k_a, K * ma, y->y2_hash,
+                       p2b_1 - noab - 1 + nvab * (p1b_1 - noab - 1 + nvab * (h4b_1 - 1 + noab * (h7b_1 - 1))));
+        ora_tce_sort_4(k_a, a_sort, RANGE(h7b), RANGE(h4b), RANGE(p1b), RANGE(p2b), 4, 3, 2, 1, -1.0);
+      }
+      if (h4b <= h7b) { /* :622-629 */
+        get_hash_block(y->y2, k_a, K * ma, y->y2_hash,
+                       p2b_1 - noab - 1 + nvab * (p1b_1 - noab - 1 + nvab * (h7b_1 - 1 + noab * (h4b_1 - 1))));
+        ora_tce_sort_4(k_a, a_sort, RANGE(h4b), RANGE(h7b), RANGE(p1b), RANGE(p2b), 4, 3, 1, 2, 1.0);
+      }
+      if (h7b <= p3b) { /* :636-643 (always true) */
+        get_v2_block(c, k_b, K * mb, p3b_2 - 1 + N * (h7b_2 - 1 + N * (h6b_2 - 1 + N * (h5b_2 - 1))), p3b_2, h7b_2, h6b_2,
+                     h5b_2);
+        ora_tce_sort_4(k_b, b_sort, RANGE(h5b), RANGE(h6b), RANGE(h7b), RANGE(p3b), 4, 2, 1, 3, 1.0);
+      }
+      ora_dgemm_tn(ma, mb, K, a_sort, b_sort, c_sort); /* :646-648 */
+      free(k_a); free(a_sort); free(k_b); free(b_sort);
+    }
+  } else { /* _4: - sum_p7 y(h4 h5 p1 p7) * v(h6 p7 p2 p3), :837-892 */
+    for (Integer p7b = noab + 1; p7b <= noab + nvab; p7b++) {
+      if (SPIN(h4b) + SPIN(h5b) != SPIN(p1b) + SPIN(p7b) || (SYM(h4b) ^ SYM(h5b) ^ SYM(p1b) ^ SYM(p7b)) != y->irrep_y) continue;
+      Integer h4b_1, h5b_1, p1b_1, p7b_1, h6b_2, p7b_2, p2b_2, p3b_2;
+      restricted_4(c, h4b, h5b, p1b, p7b, &h4b_1, &h5b_1, &p1b_1, &p7b_1);
+      restricted_4(c, h6b, p7b, p2b, p3b, &h6b_2, &p7b_2, &p2b_2, &p3b_2);
+      const Integer K = RANGE(p7b), ma = RANGE(h4b) * RANGE(h5b) * RANGE(p1b), mb = RANGE(h6b) * RANGE(p2b) * RANGE(p3b);
+      if (K * ma <= 0 || K * mb <= 0) continue;
+      double *k_a = (double *)malloc(sizeof(double) * K * ma), *a_sort = (double *)malloc(sizeof(double) * K * ma);
+      double *k_b = (double *)malloc(sizeof(double) * K * mb), *b_sort = (double *)calloc((size_t)(K * mb), sizeof(double));
+      if (p7b < p1b) { /* :856-863 */
+        get_hash_block(y->y2, k_a, K * ma, y->y2_hash,
+                       p1b_1 - noab - 1 + nvab * (p7b_1 - noab - 1 + nvab * (h5b_1 - 1 + noab * (h4b_1 - 1))));
+        ora_tce_sort_4(k_a, a_sort, RANGE(h4b), RANGE(h5b), RANGE(p7b), RANGE(p1b), 4, 2, 1, 3, -1.0);
+      }
+      if (p1b <= p7b) { /* :864-871 */
+        get_hash_block(y->y2, k_a, K * ma, y->y2_hash,
+                       p7b_1 - noab - 1 + nvab * (p1b_1 - noab - 1 + nvab * (h5b_1 - 1 + noab * (h4b_1 - 1))));
+        ora_tce_sort_4(k_a, a_sort, RANGE(h4b), RANGE(h5b), RANGE(p1b), RANGE(p7b), 3, 2, 1, 4, 1.0);
+      }
+      if (h6b <= p7b) { /* :874-881 (always true) */
+        get_v2_block(c, k_b, K * mb, p3b_2 - 1 + N * (p2b_2 - 1 + N * (p7b_2 - 1 + N * (h6b_2 - 1))), p3b_2, p2b_2, p7b_2,
+                     h6b_2);
+        ora_tce_sort_4(k_b, b_sort, RANGE(h6b), RANGE(p7b), RANGE(p2b), RANGE(p3b), 4, 3, 1, 2, 1.0);
+      }
+      ora_dgemm_tn(ma, mb, K, a_sort, b_sort, c_sort); /* :884-886 */
+      free(k_a); free(a_sort); free(k_b); free(b_sort);
+    }
+  }
+  return 1;
+}
+
+/* lambda_ccsd_t_left_{r+1}: a_c(h4,h5,h6,p1,p2,p3) += ... for the tuple t = (t_h4b,t_h5b,t_h6b,t_p1b,t_p2b,t_p3b).
+ * The reference loops over ALL tiles and skips unless one of the nine tests holds (:98-118 ...); here the candidate
+ * tiles are generated from the tests themselves -- the same set, each visited once. */
+static void lambda_left_r(const ora_ctx *c, const ora_lambda *y, int r, double *a_c, const Integer t[6]) {
+  Integer seen[9][6];
+  int nseen = 0;
+  double *c_sort = NULL;
+  for (int k = 0; k < 9; k++) {
+    Integer v[6] = {0, 0, 0, 0, 0, 0};
+    int ok = 1;
+    for (int i = 0; i < 6; i++) { /* t_(i) == v[TEST[k][i]] */
+      const int q = LAM_TEST[r][k][i];
+      if (v[q] != 0 && v[q] != t[i]) ok = 0;
+      v[q] = t[i];
+    }
+    for (int i = 0; i < 6 && ok; i++) { /* loop bounds, e.g. DO h6b = h5b,noab */
+      const int lo = LAM_LOOP_LO[r][i];
+      if (lo >= 0 && v[i] < v[lo]) ok = 0;
+    }
+    if (!ok) continue;
+    int dup = 0;
+    for (int s = 0; s < nseen; s++) { int same = 1; for (int i = 0; i < 6; i++) same &= (seen[s][i] == v[i]); dup |= same; }
+    if (dup) continue;
+    memcpy(seen[nseen++], v, sizeof(v));
+    const Integer dimc = RANGE(v[0]) * RANGE(v[1]) * RANGE(v[2]) * RANGE(v[3]) * RANGE(v[4]) * RANGE(v[5]);
+    c_sort = (double *)realloc(c_sort, sizeof(double) * (size_t)(dimc + 1));
+    if (!lambda_left_csort(c, y, r, v, c_sort)) continue;
+    for (int k2 = 0; k2 < 9; k2++) { /* every test this tile sextuple satisfies gets its TCE_SORTACC_6 */
+      int hit = 1;
+      for (int i = 0; i < 6; i++) hit &= (t[i] == v[LAM_TEST[r][k2][i]]);
+      if (!hit) continue;
+      const int *d = LAM_DIMS[r], *p = LAM_PERM[r][k2];
+      ora_tce_sortacc_6(c_sort, a_c, RANGE(v[d[0]]), RANGE(v[d[1]]), RANGE(v[d[2]]), RANGE(v[d[3]]), RANGE(v[d[4]]),
+                        RANGE(v[d[5]]), p[0], p[1], p[2], p[3], p[4], p[5], LAM_SIGN[r][k2]);
+    }
+  }
+  free(c_sort);
+}
+
+/* lambda_ccsd_t_left(a_i0, ..., toggle): toggle 1 -> _1 ; toggle 2 -> _2, _3, _4 (lambda_ccsd_t_left.F:31-38) */
+void ora_lambda_ccsd_t_left(const ora_ctx *c, const ora_lambda *y, double *a_i0, const Integer t_h4h5h6p1p2p3[6], int toggle) {
+  if (toggle == 1) lambda_left_r(c, y, 0, a_i0, t_h4h5h6p1p2p3);
+  if (toggle == 2) { lambda_left_r(c, y, 1, a_i0, t_h4h5h6p1p2p3); lambda_left_r(c, y, 2, a_i0, t_h4h5h6p1p2p3); lambda_left_r(c, y, 3, a_i0, t_h4h5h6p1p2p3); }
+}
+
+/* One tuple of lambda_ccsd_t.F:59-190.  tuple = (p4b,p5b,p6b,h1b,h2b,h3b).  sorted = 0: the element-by-element product
+ * of the file as written; sorted = 1: the left-hand tiles brought from L3 to T3 form first (:35-36).  Optional outputs:
+ * tdoubles (T3 form), ysingles / ydoubles (L3 form as delivered), each prod(ranges) doubles. */
+void ora_lambda_ccsd_t_tuple(const ora_ctx *c, const ora_lambda *y, const Integer *tuple, int sorted, double *energy,
+                             double *tdoubles_out, double *ysingles_out, double *ydoubles_out) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2], t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  double *td = (double *)calloc(size + 1, sizeof(double)), *ys = (double *)calloc(size + 1, sizeof(double));
+  double *yd = (double *)calloc(size + 1, sizeof(double));
+  ora_ccsd_t_doubles_tce(c, td, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b);            /* :109-111 */
+  const Integer tl[6] = {t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b};
+  ora_lambda_ccsd_t_left(c, y, ys, tl, 1);                                            /* :121-124 */
+  ora_lambda_ccsd_t_left(c, y, yd, tl, 2);                                            /* :131-134 */
+  const double factor = ora_ccsd_t_factor((int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* :136-147 */
+  const double *e4 = c->evl_sorted + c->offset[t_p4b - 1], *e5 = c->evl_sorted + c->offset[t_p5b - 1];
+  const double *e6 = c->evl_sorted + c->offset[t_p6b - 1], *e1 = c->evl_sorted + c->offset[t_h1b - 1];
+  const double *e2 = c->evl_sorted + c->offset[t_h2b - 1], *e3 = c->evl_sorted + c->offset[t_h3b - 1];
+  double en1 = 0.0, en2 = 0.0;
+  size_t i = 0;
+  for (Integer p4 = 0; p4 < R[0]; p4++)
+    for (Integer p5 = 0; p5 < R[1]; p5++)
+      for (Integer p6 = 0; p6 < R[2]; p6++)
+        for (Integer h1 = 0; h1 < R[3]; h1++)
+          for (Integer h2 = 0; h2 < R[4]; h2++)
+            for (Integer h3 = 0; h3 < R[5]; h3++, i++) {
+              /* L3 index of the same orbitals: (h1,h2,h3,p4,p5,p6), p6 fastest */
+              const size_t il = sorted ? (size_t)(((((h1 * R[4] + h2) * R[5] + h3) * R[0] + p4) * R[1] + p5) * R[2] + p6) : i;
+              const double den = -e4[p4] - e5[p5] - e6[p6] + e1[h1] + e2[h2] + e3[h3];
+              en1 += factor * td[i] * yd[il] / den;               /* :162-169 */
+              en2 += factor * td[i] * (ys[il] + yd[il]) / den;    /* :170-177 */
+            }
+  energy[0] += en1;
+  energy[1] += en2;
+  if (tdoubles_out) memcpy(tdoubles_out, td, sizeof(double) * size);
+  if (ysingles_out) memcpy(ysingles_out, ys, sizeof(double) * size);
+  if (ydoubles_out) memcpy(ydoubles_out, yd, sizeof(double) * size);
+  free(td); free(ys); free(yd);
+}
+
+/* lambda_ccsd_t: all tuples (the loop order of lambda_ccsd_t.F:59-64); per_task (optional) 2 doubles per tuple in that order */
+Integer ora_lambda_ccsd_t(const ora_ctx *c, const ora_lambda *y, int sorted, double *energy, double *per_task) {
+  Integer count = 0;
+  energy[0] = energy[1] = 0.0;
+  const Integer n0 = c->noab, n1 = c->noab + c->nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue; /* :65-85 */
+              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+              double e[2] = {0.0, 0.0};
+              ora_lambda_ccsd_t_tuple(c, y, t, sorted, e, NULL, NULL, NULL);
+              if (per_task) { per_task[2 * count] = e[0]; per_task[2 * count + 1] = e[1]; }
+              energy[0] += e[0];
+              energy[1] += e[1];
+              count++;
+            }
+  return count;
+}
