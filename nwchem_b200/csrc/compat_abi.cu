@@ -307,7 +307,7 @@ void dev_release_(void) {
   guard([&]() {
     if (g_eng) {
       NWC_CUDA(cudaStreamSynchronize(g_eng->stream()));
-      g_eng->arena().reset();
+      g_eng->arena().reset(/*compact=*/true);
       g_stage.drained();
     }
   });

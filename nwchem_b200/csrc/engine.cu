@@ -32,7 +32,21 @@ void* Arena::alloc(size_t bytes) {
   used_ += bytes;
   return chunks_[cur_].base;
 }
-void Arena::reset() {
+void Arena::reset(bool compact) {
+  // (compact) A batch that needed several chunks leaves a fragmented arena, and the next batch (other sizes, other order) may
+  // not fit it the same way: it would grow again, and every cudaMalloc synchronises the device under the running
+  // batch.  Coalesce once into one chunk with head-room; later batches of similar size then never allocate.
+  if (compact && chunks_.size() > 1) {
+    size_t total = capacity();
+    total += total / 4;
+    if (total > max_bytes) total = max_bytes;
+    for (auto& c : chunks_) cudaFree(c.base);
+    chunks_.clear();
+    Chunk c;
+    c.size = total; c.off = 0; c.base = nullptr;
+    if (cudaMalloc((void**)&c.base, c.size) == cudaSuccess) chunks_.push_back(c);
+    else cudaGetLastError();   // fall back to growing on demand
+  }
   for (auto& c : chunks_) c.off = 0;
   cur_ = 0;
   used_ = 0;
@@ -431,7 +445,7 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   return submitted;
 }
 
-void Engine::collect(int slot, double* energies_out) {
+void Engine::collect(int slot, double* energies_out, bool compact) {
   if (slot < 0) return;
   Slot& S = slots_[slot];
   if (!S.busy) return;
@@ -447,7 +461,7 @@ void Engine::collect(int slot, double* energies_out) {
   S.h_stage_off = 0;
   if (energies_out) memcpy(energies_out, S.h_out, (size_t)S.ntuples * sizeof(double2));
   S.busy = false;
-  S.arena.reset();
+  S.arena.reset(compact);
 }
 
 void Engine::run(double* energies_out, double* dump_doubles, double* dump_singles) {

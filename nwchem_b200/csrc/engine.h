@@ -34,7 +34,7 @@ struct Error : std::runtime_error {
 class Arena {
  public:
   void* alloc(size_t bytes);
-  void reset();            // keep chunks, rewind
+  void reset(bool compact = false);   // rewind; compact: merge several chunks into one (frees memory: nothing may still point into it)
   void release();          // cudaFree everything
   size_t used() const { return used_; }
   size_t capacity() const;
@@ -129,7 +129,8 @@ class Engine {
   // the other slot, which must have been collected.  Returns the slot to collect, or -1 if nothing was pending.
   int submit(double* dump_doubles = nullptr, double* dump_singles = nullptr);
   // wait for a submitted slot; energies_out[2*i..] = (E1,E2) of its tuple i.  Rewinds the slot's arena.
-  void collect(int slot, double* energies_out);
+  // compact: also merge a fragmented arena into one chunk (only when nothing allocated from it is read afterwards)
+  void collect(int slot, double* energies_out, bool compact = false);
   int slot_tuples(int slot) const { return slots_[slot].ntuples; }
   bool slot_busy(int slot) const { return slots_[slot].busy; }
   // synchronous convenience: submit + collect

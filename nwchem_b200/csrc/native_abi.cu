@@ -406,7 +406,7 @@ struct Pipeline {
   void wait_prev() {
     if (prev < 0) return;
     eb.assign(2 * prev_pos.size() + 2, 0.0);
-    e.collect(prev, eb.data());
+    e.collect(prev, eb.data(), /*compact=*/true);
     for (size_t i = 0; i < prev_pos.size(); i++) {
       energy[0] += eb[2 * i];
       energy[1] += eb[2 * i + 1];
