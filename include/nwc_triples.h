@@ -263,6 +263,9 @@ int nwc_triples_set_lambda(nwc_triples_ctx *ctx, const Integer *y1_hash, const d
                            const double *y2, const Integer *f1_hash, const double *f1);
 int nwc_triples_run_lambda(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double energy[2],
                            double *per_task);
+/* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_energy) */
+int nwc_triples_run_lambda_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task,
+                                     Integer ntasks, double energy[2], double *per_task);
 /* one tuple, optionally materialising the t3 tiles (validation only) */
 int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                           double *host_doubles, double *host_singles);

@@ -302,6 +302,23 @@ module nwc_triples_mod
       type(c_ptr), value :: table_bracket                ! c_null_ptr or nvab doubles ([T] partials)
       real(c_double), intent(out) :: t_energy
     end function
+    ! Lambda-CCSD(T) (lambda_ccsd_t.F): lambda_1 / lambda_2 / Fock(h,p) block stores with their offset tables
+    ! (int_mb(k_y1_offset), int_mb(k_y2_offset), int_mb(k_f1_offset) restricted to the (h,p) blocks)
+    integer(c_int) function nwc_triples_set_lambda(ctx, y1_hash, y1, y2_hash, y2, f1_hash, f1) &
+        bind(C, name='nwc_triples_set_lambda')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), intent(in) :: y1_hash(*), y2_hash(*), f1_hash(*)
+      real(c_double), intent(in) :: y1(*), y2(*), f1(*)
+    end function
+    integer(c_int) function nwc_triples_run_lambda_partition(ctx, rank, nranks, first_task, ntasks, energy, per_task) &
+        bind(C, name='nwc_triples_run_lambda_partition')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), value :: rank, nranks, first_task, ntasks
+      real(c_double), intent(out) :: energy(2)       ! Lambda-CCSD[T], Lambda-CCSD(T) corrections of this rank
+      type(c_ptr), value :: per_task
+    end function
     integer(c_int) function nwc_triples_nccl_unique_id(id) bind(C, name='nwc_triples_nccl_unique_id')
       import :: c_int, c_char
       character(kind=c_char) :: id(128)

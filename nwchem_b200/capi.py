@@ -285,6 +285,16 @@ class Triples:
                "nwc_triples_run_lambda")
         return (float(e[0]), float(e[1]), pt[:cnt]) if per_task else (float(e[0]), float(e[1]))
 
+    def run_lambda_partition(self, rank: int, world: int, first_task: int = 0, ntasks: int = 0, per_task=False):
+        e = np.zeros(2)
+        n = self.num_tasks - first_task if ntasks <= 0 else min(ntasks, self.num_tasks - first_task)
+        pt = np.zeros((max(n, 1), 2)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_lambda_partition.argtypes = [C.c_void_p, L, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_lambda_partition(self._h, rank, world, first_task, ntasks, _pd(e), _pd(pt) if per_task else None),
+               "nwc_triples_run_lambda_partition")
+        return (float(e[0]), float(e[1]), pt[:n]) if per_task else (float(e[0]), float(e[1]))
+
     def tuple_items(self, tup) -> int:
         tt = np.array(tup, np.int64)
         return int(lib().nwc_triples_tuple_items(self._h, _pl(tt)))

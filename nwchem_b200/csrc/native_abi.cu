@@ -340,7 +340,7 @@ void emit_tuple(nwc_triples_ctx* c, const Integer t[6], long long item_lo = 0, l
 //   doubles tile D = Td + yscale * Yd,  singles tile S = Ys,
 // Td = ccsd_t_doubles(T2,V2) (lambda_ccsd_t.F:109-111), Ys = y1*v (lambda_ccsd_t_left_1), Yd = y2*f (left_2, the
 // doubles-bound outer products) - sum_h7 y2*v (left_3) - sum_p7 y2*v (left_4).
-void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale) {
+void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale, long long item_lo = 0, long long item_hi = -1) {
   const HostState& S = c->S;
   int R[6];
   tuple_ranges(S, t, R);
@@ -385,7 +385,7 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale) {
     }
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
-  c->eng->end_tuple(eps, tuple_factor(S, t));
+  c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
 }
 
 // Double-buffered batch loop: while the GPU runs batch k the host walks the driver logic of batch k+1 into the other
@@ -938,35 +938,59 @@ int nwc_triples_set_lambda(nwc_triples_ctx* c, const Integer* y1_hash, const dou
 //   sum Td Yd / Delta = ( E[D+] - E[D-] ) / 4 ,   sum Td Ys / Delta = ( ES[D+] + ES[D-] ) / 2
 // (polarisation identity; E = the kernel's sum f D^2/Delta, ES = its sum f D S/Delta).  Costs twice the minimal
 // FLOPs of this sibling, in exchange for no second kernel.
+static int run_lambda_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const std::vector<long long>* ranges,
+                          double energy[2], double* per_task) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_run_lambda: call nwc_triples_set_lambda first"; return 1; }
+  const size_t cnt = ids.size();
+  std::vector<double> raw(4 * cnt + 4, 0.0);   // per task: (E, E+ES) of the + run, then of the - run
+  double dummy[2] = {0.0, 0.0};
+  Pipeline pipe(c, dummy, raw.data());
+  for (size_t i = 0; i < cnt; i++) {
+    const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
+    if (ranges && b <= a) continue;
+    emit_tuple_lambda(c, &c->klist[7 * (size_t)ids[i]], +1.0, a, b);
+    pipe.emitted((Integer)(2 * i));
+    emit_tuple_lambda(c, &c->klist[7 * (size_t)ids[i]], -1.0, a, b);
+    pipe.emitted((Integer)(2 * i + 1));
+  }
+  pipe.finish();
+  energy[0] = energy[1] = 0.0;
+  for (size_t i = 0; i < cnt; i++) {
+    const double ep = raw[4 * i], sp_ = raw[4 * i + 1] - raw[4 * i], em = raw[4 * i + 2], sm_ = raw[4 * i + 3] - raw[4 * i + 2];
+    const double e1 = 0.25 * (ep - em), e2 = e1 + 0.5 * (sp_ + sm_);
+    energy[0] += e1;
+    energy[1] += e2;
+    if (per_task) { per_task[2 * i] = e1; per_task[2 * i + 1] = e2; }
+  }
+  return 0;
+}
+
 int nwc_triples_run_lambda(nwc_triples_ctx* c, Integer first, Integer stride, Integer max_tasks, double energy[2],
                            double* per_task) {
   return guarded(c, [&]() {
-    NWC_TRY(cudaSetDevice(c->eng->device()));
-    if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_run_lambda: call nwc_triples_set_lambda first"; return 1; }
     if (stride <= 0) stride = 1;
     const Integer nt = (Integer)(c->klist.size() / 7);
-    Integer cnt = 0;
-    for (Integer k = first; k < nt && (max_tasks <= 0 || cnt < max_tasks); k += stride) cnt++;
-    std::vector<double> raw(4 * (size_t)cnt + 4, 0.0);   // per task: (E, E+ES) of the + run, then of the - run
-    double dummy[2] = {0.0, 0.0};
-    Pipeline pipe(c, dummy, raw.data());
-    Integer done = 0;
-    for (Integer k = first; k < nt && done < cnt; k += stride, done++) {
-      emit_tuple_lambda(c, &c->klist[7 * k], +1.0);
-      pipe.emitted(2 * done);
-      emit_tuple_lambda(c, &c->klist[7 * k], -1.0);
-      pipe.emitted(2 * done + 1);
-    }
-    pipe.finish();
-    energy[0] = energy[1] = 0.0;
-    for (Integer i = 0; i < cnt; i++) {
-      const double ep = raw[4 * i], sp_ = raw[4 * i + 1] - raw[4 * i], em = raw[4 * i + 2], sm_ = raw[4 * i + 3] - raw[4 * i + 2];
-      const double e1 = 0.25 * (ep - em), e2 = e1 + 0.5 * (sp_ + sm_);
-      energy[0] += e1;
-      energy[1] += e2;
-      if (per_task) { per_task[2 * i] = e1; per_task[2 * i + 1] = e2; }
-    }
-    return 0;
+    std::vector<Integer> ids;
+    for (Integer k = first; k < nt && (max_tasks <= 0 || (Integer)ids.size() < max_tasks); k += stride) ids.push_back(k);
+    return run_lambda_ids(c, ids, nullptr, energy, per_task);
+  });
+}
+
+// Lambda-CCSD(T) over the static block partition of nwc_triples_run_partition (both polarisation runs of a tuple take
+// the same sub-tile range; the kernel's sums are additive over sub-tiles, so the rank sums add up exactly as for (T)).
+int nwc_triples_run_lambda_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                                     double energy[2], double* per_task) {
+  return guarded(c, [&]() {
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+    if (first_task < 0) first_task = 0;
+    if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
+    std::vector<Integer> ids;
+    for (Integer i = 0; i < ntasks; i++) ids.push_back(first_task + i);
+    std::vector<long long> ranges;
+    if (!ids.empty()) block_partition(c->S, c->klist, rank, nranks, ids, ranges);
+    return run_lambda_ids(c, ids, &ranges, energy, per_task);
   });
 }
 

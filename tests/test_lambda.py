@@ -109,3 +109,24 @@ def test_lambda_ccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, intorb)
     assert abs(e1 - ref["e1"]) <= 1e-12 and abs(e2 - ref["e2"]) <= 1e-12, (e1, ref["e1"], e2, ref["e2"])
     assert np.max(np.abs(got - ref["per_task"])) <= 1e-13
     assert abs(e1 - ref["e1"]) <= 1e-10 * abs(ref["e1"])
+
+
+@pytest.mark.gpu
+def test_lambda_block_partition_sums_to_total(oracle):
+    """nwc_triples_run_lambda_partition: the polarisation sums are additive over sub-tiles, so rank pieces (tuples on a
+    boundary shared at sub-tile granularity) add up to the single-rank energies, and those match the oracle."""
+    from nwchem_b200 import capi
+    import dataclasses
+    t = synth.shape_tiling("h2o_ccpvdz_c2v")
+    st = synth.physical(t, intorb=True)
+    lam = synth.physical_lambda(t)
+    ref = oracle.lambda_ccsd_t(st, lam, sorted=True)
+    tr = capi.Triples(0)
+    tr.set_state(dataclasses.replace(st, orb=None))
+    tr.set_lambda(lam)
+    e1, e2, pt = tr.run_lambda(per_task=True)
+    parts = [tr.run_lambda_partition(r, 3, per_task=True) for r in range(3)]
+    tr.close()
+    assert abs(e1 - ref["e1"]) <= 1e-12 and abs(e2 - ref["e2"]) <= 1e-12
+    assert abs(sum(p[0] for p in parts) - e1) <= 1e-14 and abs(sum(p[1] for p in parts) - e2) <= 1e-14
+    assert np.max(np.abs(sum(p[2] for p in parts) - pt)) <= 1e-15
