@@ -271,6 +271,7 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     tr.set_timing(False)
+    mem_free = {"after_timed_loop_GB": torch.cuda.mem_get_info()[0] * 1e-9}
     s = tr.stats()
     ms_max, flops_all = allmax(ms), allsum(s["flops"])
     # per-rank device time of the fused kernel and of the whole timed region (load balance of the static partition)
@@ -334,6 +335,15 @@ def main():
     # ---- host copy of exactly the blocks this rank's Tier-1 tasks read (exported from the device) ----
     need_host = (not a.no_e2e) or (rank == 0 and world == 1 and not a.no_cpu_baseline)
     my_tasks = tasks[rank::world] if world > 1 else tasks
+    tr.trim()   # Tier 1 has its own engine: give Tier 2's batch arenas back first (130 GB of stores are resident)
+    if need_host and W["device_gen"]:   # bound the host copy by the memory the box has (~8 GB per (H2O)10 tuple)
+        try:
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        except Exception:
+            avail = 64 << 30
+        fit = max(1, int(0.5 * avail / max(1, world) / 9e9))
+        if fit < len(my_tasks):
+            my_tasks = my_tasks[:fit]
     host = None
     if need_host and len(my_tasks) and W["device_gen"]:
         host = sparse_host_store(tr, t, st, my_tasks, capi, synth, tl)
@@ -381,11 +391,16 @@ def main():
         e2e["api"] = ("nwc_ccsd_t_gpu_tasks -> sd_t_*_cuda_/compute_en_ (Tier 1), host block stores, host TCE_SORT_4 included; "
                       "reference contract: pageable operands, refilled right after each call (ccsd_t_doubles_gpu.F:282-327,723-726); "
                       "tasks dealt whole to ranks (the reference's granularity)")
+        n_e2e = int(allsum(len(my_tasks)))
+        e2e["tasks"] = n_e2e
         e2e["energy_matches_native"] = bool(abs(d["energy"][0] - e[0]) <= 1e-9 * max(1.0, abs(e[0])) and
-                                            abs(d["energy"][1] - e[1]) <= 1e-9 * max(1.0, abs(e[1]))) if not a.weak else None
+                                            abs(d["energy"][1] - e[1]) <= 1e-9 * max(1.0, abs(e[1]))) if (not a.weak and n_e2e == ntasks) else None
         e2e["optin"] = {k: o[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step")}
         e2e["optin"]["contract"] = "nwc_compat_set_async_uploads(1) + pinned host stores (operands untouched until compute_en_)"
 
+    if not a.no_e2e:
+        mem_free["after_e2e_GB"] = torch.cuda.mem_get_info()[0] * 1e-9
+        capi.compat_trim()
     # ---- CPU baseline + GPU-vs-oracle parity on a p4 slab of task 0 (N = 1 only) ----
     cpu = None; parity = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and host is not None:
@@ -426,7 +441,7 @@ def main():
                 "full_list_extrapolated_s": (4.5208e17 / (value * 1e9)) if a.workload == "h2o10_augccpvtz" else None,
                 "rank_fused_ms_per_step": per_rank[0::2], "rank_ms_per_step": per_rank[1::2],
                 "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clocks}
+                "gpu_launches": launches, "gpu_mem_free": mem_free, "clocks": clocks}
         print(json.dumps(line))
     tr.close()
     if world > 1:

@@ -286,6 +286,10 @@ int nwc_compat_timer_stop_ms(double *ms);
  * arena (default 150 GiB): beyond it a call fails with an error instead of exhausting the device */
 int nwc_triples_set_batch_bytes(nwc_triples_ctx *ctx, size_t bytes);
 int nwc_triples_set_arena_cap(nwc_triples_ctx *ctx, size_t bytes);
+/* give the batch arenas back to the device (tens of GB after large tuples; re-allocated on demand).  The resident
+ * stores stay.  nwc_compat_trim does the same for the Tier-1 engine. */
+int nwc_triples_trim(nwc_triples_ctx *ctx);
+int nwc_compat_trim(void);
 /* index order inside the operand panels chosen for this tiling: 0 holes first, 1 particles first (the less ragged tile
  * type goes first so that more padding rows can be skipped; env NWC_ORDER overrides) */
 int nwc_triples_get_order(nwc_triples_ctx *ctx);

@@ -311,6 +311,11 @@ class Triples:
         lib().nwc_triples_get_order.argtypes = [C.c_void_p]
         return int(lib().nwc_triples_get_order(self._h))
 
+    def trim(self):
+        """Release the batch arenas (the resident stores stay)."""
+        lib().nwc_triples_trim.argtypes = [C.c_void_p]
+        _check(lib().nwc_triples_trim(self._h), "nwc_triples_trim")
+
     def set_arena_cap(self, n):
         lib().nwc_triples_set_arena_cap(self._h, int(n))
 
@@ -523,6 +528,10 @@ def compat_stats(reset=False) -> dict:
     s = Stats()
     lib().nwc_compat_get_stats(C.byref(s), int(reset))
     return s.asdict()
+
+
+def compat_trim():
+    lib().nwc_compat_trim()
 
 
 def compat_set_timing(on=True):

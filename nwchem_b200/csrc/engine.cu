@@ -38,7 +38,7 @@ void Arena::reset(bool compact) {
   // batch.  Coalesce once into one chunk with head-room; later batches of similar size then never allocate.
   if (compact && chunks_.size() > 1) {
     size_t total = capacity();
-    total += total / 4;
+    total += total / 16;   // little head-room: the resident stores may leave few GB (130 GB of 180 for (H2O)10 on one GPU)
     if (total > max_bytes) total = max_bytes;
     for (auto& c : chunks_) cudaFree(c.base);
     chunks_.clear();
@@ -96,6 +96,14 @@ Engine::~Engine() {
   cudaEventDestroy(evt0_);
   cudaEventDestroy(evt1_);
   cudaStreamDestroy(stream_);
+}
+
+void Engine::trim() {
+  abort();
+  for (Slot& s : slots_) {
+    s.arena.release();
+    if (s.d_meta) { cudaFree(s.d_meta); s.d_meta = nullptr; s.d_meta_cap = 0; }
+  }
 }
 
 void Engine::abort() {

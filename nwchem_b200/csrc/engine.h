@@ -137,6 +137,8 @@ class Engine {
   void run(double* energies_out, double* dump_doubles = nullptr, double* dump_singles = nullptr);
   // error recovery: drop everything pending / in flight and rewind both arenas
   void abort();
+  // give the batch arenas and metadata buffers back to the device (they are re-allocated on demand)
+  void trim();
   void flush_prep();      // launch pending pull + antisym + repack jobs now (asynchronous)
   // `2eorb`: queue the construction of one dense spin-orbital V2 block (job.dst must come from arena())
   void add_antisym(const AntisymJob& job);

@@ -1079,6 +1079,16 @@ int nwc_debug_phase_timing(unsigned long long* host_out, unsigned int cap_items,
 }
 
 int nwc_triples_set_batch_bytes(nwc_triples_ctx* c, size_t bytes) { c->batch_bytes = bytes; return 0; }
+// release the batch arenas (tens of GB after large tuples); the resident stores stay, the next run re-allocates
+int nwc_triples_trim(nwc_triples_ctx* c) {
+  return guarded(c, [&]() {
+    NWC_TRY(cudaSetDevice(c->eng->device()));
+    c->eng->trim();
+    for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
+    return 0;
+  });
+}
+int nwc_compat_trim(void) { return guarded(nullptr, [&]() { nwc::compat_engine().trim(); return 0; }); }
 int nwc_triples_get_order(nwc_triples_ctx* c) { return c->eng->order(); }
 int nwc_triples_set_arena_cap(nwc_triples_ctx* c, size_t bytes) { c->eng->set_arena_cap(bytes); return 0; }
 
