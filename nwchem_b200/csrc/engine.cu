@@ -155,7 +155,9 @@ void Engine::begin_tuple(const int R_phys[6]) {
     cur_hdr_.R[q] = R_phys[q];
     cur_hdr_.nb[q] = (R_phys[q] + SB - 1) / SB;
   }
-  for (int s = 0; s < 9; s++) cur_descs_[s].clear();
+  for (int side = 0; side < 2; side++)
+    for (int s = 0; s < 9; s++) cur_descs_[side][s].clear();
+  two_sided_ = false;
   cur_sd_singles_.clear();
   cur_sd_doubles_.clear();
   open_ = true;
@@ -174,8 +176,9 @@ long long Engine::tuple_items(const int R_phys[6]) {
 }
 
 void Engine::add_contraction_group(int family, int k0, const Segment* segs, int nseg, std::vector<GroupPanel>* t_cache,
-                                   std::vector<GroupPanel>* v_cache) {
-  if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8) throw Error("nwc_triples: bad add_contraction");
+                                   std::vector<GroupPanel>* v_cache, int side) {
+  if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8 || side < 0 || side > 1) throw Error("nwc_triples: bad add_contraction");
+  if (side == 1) two_sided_ = true;
   // which operand is the G1 (one particle + two holes) one, and the singleton names
   const bool t_is_g1 = (family == 2);
   const int pa = pos_of(family, k0, family == 2 ? N_P4 : N_P6);
@@ -233,7 +236,7 @@ void Engine::add_contraction_group(int family, int k0, const Segment* segs, int 
   d.g2 = build(false, n2, p2, c2);
   d.nk4 = (int)((Ktot + 3) / 4);
   d.neg = SIGN[family][k0] < 0 ? 1 : 0;
-  cur_descs_[s].push_back(d);
+  cur_descs_[side][s].push_back(d);
   cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R) * (double)Ktot;   // FLOPs of the whole tuple, parked here until end_tuple
 }
 
@@ -283,10 +286,17 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
   int n = (int)descs_.size();
   for (int s = 0; s < 9; s++) {
     cur_hdr_.desc_begin[s] = n;
-    descs_.insert(descs_.end(), cur_descs_[s].begin(), cur_descs_[s].end());
-    n += (int)cur_descs_[s].size();
+    descs_.insert(descs_.end(), cur_descs_[0][s].begin(), cur_descs_[0][s].end());
+    n += (int)cur_descs_[0][s].size();
   }
   cur_hdr_.desc_begin[9] = n;
+  for (int s = 0; s < 9; s++) {
+    cur_hdr_.desc2_begin[s] = n;
+    descs_.insert(descs_.end(), cur_descs_[1][s].begin(), cur_descs_[1][s].end());
+    n += (int)cur_descs_[1][s].size();
+  }
+  cur_hdr_.desc2_begin[9] = n;
+  cur_hdr_.two_sided = two_sided_ ? 1 : 0;
   cur_hdr_.sdesc_begin = (int)sdescs_.size();
   sdescs_.insert(sdescs_.end(), cur_sd_doubles_.begin(), cur_sd_doubles_.end());
   cur_hdr_.sdesc_mid = (int)sdescs_.size();
@@ -416,15 +426,19 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[4], stream_));
   if (dump_doubles) {
     for (const TupleHdr& t : tuples_)
-      if (t.sdesc_mid > t.sdesc_begin) throw Error("nwc_triples: the validation dump does not support doubles-bound outer products");
+      if (t.two_sided) throw Error("nwc_triples: the validation dump does not support two-sided (Lambda) tuples");
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                       (double2*)(dm + o_p), items_, dump_doubles, dump_singles, order_, stream_);
   } else {
-    bool ragged = false, lambda = false;
+    bool ragged = false, lambda = false, plain = false;
     for (const TupleHdr& t : tuples_) {
       for (int q = 0; q < 6; q++) ragged = ragged || (t.R[q] % SB != 0);
-      lambda = lambda || (t.sdesc_mid > t.sdesc_begin);
+      const bool l = t.two_sided != 0;
+      if (!l && t.sdesc_mid > t.sdesc_begin) throw Error("nwc_triples: doubles-bound outer products need a two-sided tuple");
+      lambda = lambda || l;
+      plain = plain || !l;
     }
+    if (lambda && plain) throw Error("nwc_triples: a batch cannot mix (T) tuples and two-sided (Lambda) tuples");
     launch_fused((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                  (double2*)(dm + o_p), items_, ragged, order_, lambda, stream_);
   }

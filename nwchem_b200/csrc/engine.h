@@ -103,8 +103,11 @@ class Engine {
   // family 1 (sd_t_d1_K) or 2 (sd_t_d2_K); k0 = K-1; segs = the contracted tiles (h7b / p7b) of this kernel in this
   // tuple, concatenated along K.  t_cache / v_cache (optional): group panels already built; reused when the index
   // order and the segments' source blocks match.
+  // side 0: the tuple's doubles tile; side 1 (Lambda-CCSD(T)): the LEFT-hand doubles tile, accumulated separately and
+  // paired with the side-0 tile in the energy pass (a tuple with side-1 contractions is "two-sided")
   void add_contraction_group(int family, int k0, const Segment* segs, int nseg, std::vector<GroupPanel>* t_cache = nullptr,
-                             std::vector<GroupPanel>* v_cache = nullptr);
+                             std::vector<GroupPanel>* v_cache = nullptr, int side = 0);
+  void set_two_sided() { two_sided_ = true; }   // even if no left-hand contraction fires (its tile is then the outer products)
   // one contracted tile on its own (K7 = its range)
   void add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale = 1.0) {
     Segment sg;
@@ -168,7 +171,8 @@ class Engine {
   int cur_ = 0;
   bool open_ = false;
   TupleHdr cur_hdr_{};
-  std::vector<ContrDesc> cur_descs_[9];
+  std::vector<ContrDesc> cur_descs_[2][9];
+  bool two_sided_ = false;
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;

@@ -8,7 +8,9 @@
 //                  keeps the running sum of ITS quarter of the sub-tile in a canonical shared-memory copy and seeds
 //                  the accumulators of the next split from it (nine permutations fused with no FP64 add); then the
 //                  singles, factor/denominator and the E[T], E(T) reduction.  The t3 tile never exists in HBM.
-//  reduce_kernel : deterministic per-tuple sum of the per-sub-tile partial energies.
+//  reduce_chunk_kernel / reduce_final_kernel : two-level deterministic per-tuple sum of the per-sub-tile partial energies.
+//  pull_kernel   : whole blocks of a peer GPU's V2 shard -> local batch arena (coalesced NVLink reads)
+//  antisym_kernel: `2eorb` spin-orbital block from the orbital-form store;  synth_fill_kernel: keyed synthetic stores
 //
 // Reference semantics: src/tce/ccsd_t/ccsd_t_kernels_omp.F (27 kernels), ccsd_t_dot.F:101-124 (energy).
 #include "kernels.cuh"
@@ -293,6 +295,14 @@ struct __align__(16) FusedSmem {
   int zero;                                 // run-time 0 (see mma_split)
 };
 
+// Lambda-CCSD(T) launches append a second canonical tile: the right-hand doubles Td are parked there while the
+// left-hand tile Yd is accumulated in `canon` (2 CTAs/SM instead of 3)
+struct __align__(16) LambdaSmem {
+  double canon2[SUBTILE];
+  int desc2_begin[10];
+  int pad[2];
+};
+
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
 int partials_per_item() { return NCONSUMERS / 32; }
 
@@ -491,7 +501,7 @@ __device__ unsigned int g_phase_cap = 0;
 // LAMBDA: the launch holds tuples with doubles-bound outer-product terms (Lambda-CCSD(T)); the plain (T) instantiations
 // do not carry that code (it costs registers in the epilogue).
 template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0, bool LAMBDA = false>
-__global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
+__global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
                  double* __restrict__ dump_s) {
@@ -499,6 +509,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
   if (TIMING) tph[0] = clock64();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+  LambdaSmem& lm = *reinterpret_cast<LambdaSmem*>(smem_raw + ((sizeof(FusedSmem) + 127) & ~(size_t)127));   // LAMBDA launches only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == NCONSUMERS / 32;
 
@@ -573,6 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     sm.zero = 0;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
+  if (LAMBDA && tid >= 32 && tid < 42) lm.desc2_begin[tid - 32] = T.desc2_begin[tid - 32];
   if (T.desc_begin[9] == T.desc_begin[0]) {   // no contraction fires: the doubles tile is zero.  Otherwise the first
     double2* c2 = reinterpret_cast<double2*>(sm.canon);   // split's STORE covers the whole canonical tile
     for (int i = tid; i < SUBTILE / 2; i += NTHREADS) c2[i] = make_double2(0.0, 0.0);
@@ -649,9 +661,11 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     // ===== TMA producer warp: one elected lane streams every plane of every fired contraction, split by split =====
     if (lane == 0) {
       int st = 0, ph = 1;   // parity to wait on for a free stage: first pass through the ring never blocks
-      for (int s = 0; s < 9; s++) {
+      for (int ss = 0; ss < (LAMBDA ? 18 : 9); ss++) {   // LAMBDA: the right-hand side's nine splits, then the left-hand side's
+        const int s = ss < 9 ? ss : ss - 9;
+        const int* dbeg = (LAMBDA && ss >= 9) ? lm.desc2_begin : sm.desc_begin;
         const SplitGeom g = sm.geom[s];
-        for (int d = sm.desc_begin[s]; d < sm.desc_begin[s + 1]; d++) {
+        for (int d = dbeg[s]; d < dbeg[s + 1]; d++) {
           const ContrDesc dd = descs[d];
           const double* g1 = dd.g1 + g.off1;
           const double* g2 = dd.g2 + g.off2;
@@ -673,7 +687,10 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     // ===== MMA warp whose quarter is all padding: its part of the doubles tile is zero =====
     const int Az = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
 #pragma unroll
-    for (int jj = 0; jj < 32; jj++) sm.canon[Az ^ canon_swz(jj << 6)] = 0.0;
+    for (int jj = 0; jj < 32; jj++) {
+      sm.canon[Az ^ canon_swz(jj << 6)] = 0.0;
+      if (LAMBDA) lm.canon2[Az ^ canon_swz(jj << 6)] = 0.0;
+    }
   } else {
     // ===== MMA warps =====
     // A warp's tile in split s is (8>>own1) x (2<<own1) blocks of 8x8; which blocks follows from the owner bits, so
@@ -687,8 +704,27 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     int st = 0, ph = 0;
     bool first_split = true;
     const unsigned int zero_rt = (unsigned int)sm.zero;
-    for (int s = 0; s < 9; s++) {
-      const int d0 = sm.desc_begin[s], d1 = sm.desc_begin[s + 1];
+    for (int ss = 0; ss < (LAMBDA ? 18 : 9); ss++) {
+      const int s = ss < 9 ? ss : ss - 9;
+      if (LAMBDA && ss == 9) {
+        // the right-hand doubles Td are complete in this warp's quarter of `canon`: park them in canon2 and start
+        // the left-hand tile from zero (if the right-hand side fired nothing, canon was zero-filled at set-up)
+        __syncwarp();
+        const int Ac = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
+        const bool left_empty = lm.desc2_begin[9] == lm.desc2_begin[0];
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) {
+          const int a = Ac ^ canon_swz(jj << 6);
+          lm.canon2[a] = sm.canon[a];
+          if (left_empty) sm.canon[a] = 0.0;   // no left-hand contraction will overwrite it
+        }
+        __syncwarp();
+        first_split = true;
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
+      }
+      const int* dbeg = (LAMBDA && ss >= 9) ? lm.desc2_begin : sm.desc_begin;
+      const int d0 = dbeg[s], d1 = dbeg[s + 1];
       if (d0 == d1) continue;
       unsigned long long c0 = 0;
       if (!first_split) {   // the first split starts from zero accumulators
@@ -858,10 +894,11 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 #else
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 8) {
-    double dd[8], rr[8];
+    double dd[8], rr[8], td[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       dd[u] = sm.canon[At ^ canon_swz((j0 + u) << 6)];
+      td[u] = LAMBDA ? lm.canon2[At ^ canon_swz((j0 + u) << 6)] : dd[u];   // Lambda-CCSD(T): w = f*Td/Delta, E1 += w*Yd
       rr[u] = sm.dp[warp][j0 + u];
     }
 #pragma unroll
@@ -869,7 +906,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
 #pragma unroll
     for (int u = 0; u < 8; u++) rr[u] = fast_rcp(rr[u]);
 #pragma unroll
-    for (int u = 0; u < 8; u++) rr[u] = dd[u] * rr[u];              // w = D/Delta (tuple factor applied once at the end)
+    for (int u = 0; u < 8; u++) rr[u] = td[u] * rr[u];              // w = D/Delta (tuple factor applied once at the end)
 #pragma unroll
     for (int u = 0; u < 8; u++) e1 = fma(rr[u], dd[u], e1);         // ccsd_t_dot.F:115
 #pragma unroll
@@ -906,7 +943,7 @@ __global__ void __launch_bounds__(NTHREADS, NWC_CTAS_PER_SM)
     e2 += __shfl_xor_sync(0xffffffffu, e2, o);
   }
   // one partial per warp: no CTA-wide rendezvous at the end, every warp leaves as soon as it is done
-  // (reduce_kernel adds the four in a fixed order)
+  // (reduce_chunk_kernel adds the four in a fixed order)
   if (lane == 0) partials[item * (NCONSUMERS / 32) + warp] = make_double2(e1, e2);
   if (TIMING && tid == 0 && g_phase_buf && item < g_phase_cap) {
     tph[6] = clock64();
@@ -925,12 +962,13 @@ template <bool DUMP, bool TIMING, bool RAGGED, int ORDER, bool LAMBDA = false>
 static void launch_one(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                        double2* d_partials, long long total_items, double* dd, double* ds, cudaStream_t stream) {
   static bool attr_done = false;   // one flag per instantiation
+  const size_t smem_bytes = LAMBDA ? ((sizeof(FusedSmem) + 127) & ~(size_t)127) + sizeof(LambdaSmem) : sizeof(FusedSmem);
   if (!attr_done) {
-    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     cudaFuncSetAttribute(fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_done = true;
   }
-  fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA><<<(unsigned)total_items, NTHREADS, sizeof(FusedSmem), stream>>>(
+  fused_kernel<DUMP, TIMING, RAGGED, ORDER, LAMBDA><<<(unsigned)total_items, NTHREADS, smem_bytes, stream>>>(
       d_tuples, ntuples, d_descs, d_sdescs, d_partials, dd, ds);
 }
 

@@ -44,7 +44,8 @@ struct TupleHdr {
   int desc_begin[10];   // split s owns descs [desc_begin[s], desc_begin[s+1])
   int sdesc_begin, sdesc_end;
   int sdesc_mid;        // outer-product terms [sdesc_begin, sdesc_mid) are added to the DOUBLES tile, the rest are the singles
-  int pad2;
+  int two_sided;        // Lambda-CCSD(T): desc2_begin lists the LEFT-hand contractions, the energy pairs the two tiles
+  int desc2_begin[10];  // split s of the left-hand side owns descs [desc2_begin[s], desc2_begin[s+1])
   long long item_begin; // first work item (sub-tile) of this tuple in the launch
   int nitems;            // work items of this launch (a sub-range when the tuple is split across GPUs)
   int item_first;        // index of the first of them inside the tuple's full sub-tile space

@@ -218,7 +218,7 @@ struct NativeSink {
   Engine& e;
   const HostState& S;
   bool lam = false;          // amplitudes from the lambda stores (left-hand side)
-  double yscale = 1.0;       // sign of the left-hand contractions in this run (+1 / -1: polarisation, see run_lambda)
+  int side = 0;              // 0: the tuple's doubles tile; 1: the left-hand doubles tile of a two-sided (Lambda) tuple
   bool want_singles = true;  // (T) right-hand side of Lambda-CCSD(T) uses the doubles only (lambda_ccsd_t.F:109-111)
   bool want_doubles = true;
   // contracted tiles of the current row, concatenated along K when the row ends (engine.h Segment)
@@ -226,7 +226,7 @@ struct NativeSink {
   bool row_fire[9] = {false, false, false, false, false, false, false, false, false};
   void push(const OperandView& t, const OperandView& v, double sign, Integer K, const bool fire[9]) {
     Segment sg;
-    sg.K = (int)K; sg.t = t; sg.v = v; sg.tscale = sign * (lam ? yscale : 1.0);
+    sg.K = (int)K; sg.t = t; sg.v = v; sg.tscale = sign;
     segs.push_back(sg);
     for (int k = 0; k < 9; k++) row_fire[k] = fire[k];
   }
@@ -234,7 +234,7 @@ struct NativeSink {
     if (!segs.empty()) {
       std::vector<GroupPanel> tc, vc;   // kernels fired by the same operand list (diagonal tuples) share panels
       for (int k = 0; k < 9; k++)
-        if (row_fire[k]) e.add_contraction_group(family, k, segs.data(), (int)segs.size(), &tc, &vc);
+        if (row_fire[k]) e.add_contraction_group(family, k, segs.data(), (int)segs.size(), &tc, &vc, side);
     }
     segs.clear();
   }
@@ -336,11 +336,11 @@ void emit_tuple(nwc_triples_ctx* c, const Integer t[6], long long item_lo = 0, l
   c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
 }
 
-// Lambda-CCSD(T), one of the two polarisation runs of a tuple (yscale = +1 / -1):
-//   doubles tile D = Td + yscale * Yd,  singles tile S = Ys,
-// Td = ccsd_t_doubles(T2,V2) (lambda_ccsd_t.F:109-111), Ys = y1*v (lambda_ccsd_t_left_1), Yd = y2*f (left_2, the
-// doubles-bound outer products) - sum_h7 y2*v (left_3) - sum_p7 y2*v (left_4).
-void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale, long long item_lo = 0, long long item_hi = -1) {
+// Lambda-CCSD(T): a two-sided tuple.  Side 0 = Td = ccsd_t_doubles(T2,V2) (lambda_ccsd_t.F:109-111); side 1 = the
+// left-hand doubles Yd = y2*f (left_2, doubles-bound outer products) - sum_h7 y2*v (left_3) - sum_p7 y2*v (left_4);
+// singles tile = Ys = y1*v (left_1).  The kernel accumulates Td, parks it in a second canonical tile, accumulates Yd,
+// and the energy pass forms sum f Td Yd/Delta and sum f Td (Ys+Yd)/Delta -- neither tile ever exists in HBM.
+void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], long long item_lo = 0, long long item_hi = -1) {
   const HostState& S = c->S;
   int R[6];
   tuple_ranges(S, t, R);
@@ -350,10 +350,11 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale, lo
     rhs.want_singles = false;
     walk_doubles(S, t, rhs);
   }
-  {   // left-hand contractions (into the same doubles tile, signed) and left-hand singles
+  c->eng->set_two_sided();
+  {   // left-hand contractions (side 1) and left-hand singles
     NativeSink lhs{c, *c->eng, S};
     lhs.lam = true;
-    lhs.yscale = yscale;
+    lhs.side = 1;
     walk_singles(S, t, lhs);
     walk_doubles(S, t, lhs);
   }
@@ -380,7 +381,7 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], double yscale, lo
       sa[ppos[a]] = 1; sa[hpos[b]] = (int)S.rg(Pa);                       // f block (h6,p3), p3 fastest
       sb[ppos[v]] = 1; sb[ppos[u]] = (int)S.rg(Pv);                       // y2 block (h4,h5,p1,p2), p2 fastest
       sb[hpos[y]] = (int)(S.rg(Pu) * S.rg(Pv)); sb[hpos[x]] = (int)(S.rg(Hy) * S.rg(Pu) * S.rg(Pv));
-      const bool neg = ((a == 1) != (b == 1)) != (yscale < 0);
+      const bool neg = (a == 1) != (b == 1);
       c->eng->add_outer_product(fblk, sa, yblk, sb, neg, /*to_doubles=*/true);
     }
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
@@ -942,27 +943,16 @@ static int run_lambda_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, c
                           double energy[2], double* per_task) {
   NWC_TRY(cudaSetDevice(c->eng->device()));
   if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_run_lambda: call nwc_triples_set_lambda first"; return 1; }
-  const size_t cnt = ids.size();
-  std::vector<double> raw(4 * cnt + 4, 0.0);   // per task: (E, E+ES) of the + run, then of the - run
-  double dummy[2] = {0.0, 0.0};
-  Pipeline pipe(c, dummy, raw.data());
-  for (size_t i = 0; i < cnt; i++) {
+  energy[0] = energy[1] = 0.0;
+  if (per_task) for (size_t i = 0; i < 2 * ids.size(); i++) per_task[i] = 0.0;
+  Pipeline pipe(c, energy, per_task);
+  for (size_t i = 0; i < ids.size(); i++) {
     const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
     if (ranges && b <= a) continue;
-    emit_tuple_lambda(c, &c->klist[7 * (size_t)ids[i]], +1.0, a, b);
-    pipe.emitted((Integer)(2 * i));
-    emit_tuple_lambda(c, &c->klist[7 * (size_t)ids[i]], -1.0, a, b);
-    pipe.emitted((Integer)(2 * i + 1));
+    emit_tuple_lambda(c, &c->klist[7 * (size_t)ids[i]], a, b);
+    pipe.emitted((Integer)i);
   }
   pipe.finish();
-  energy[0] = energy[1] = 0.0;
-  for (size_t i = 0; i < cnt; i++) {
-    const double ep = raw[4 * i], sp_ = raw[4 * i + 1] - raw[4 * i], em = raw[4 * i + 2], sm_ = raw[4 * i + 3] - raw[4 * i + 2];
-    const double e1 = 0.25 * (ep - em), e2 = e1 + 0.5 * (sp_ + sm_);
-    energy[0] += e1;
-    energy[1] += e2;
-    if (per_task) { per_task[2 * i] = e1; per_task[2 * i + 1] = e2; }
-  }
   return 0;
 }
 
@@ -977,8 +967,8 @@ int nwc_triples_run_lambda(nwc_triples_ctx* c, Integer first, Integer stride, In
   });
 }
 
-// Lambda-CCSD(T) over the static block partition of nwc_triples_run_partition (both polarisation runs of a tuple take
-// the same sub-tile range; the kernel's sums are additive over sub-tiles, so the rank sums add up exactly as for (T)).
+// Lambda-CCSD(T) over the static block partition of nwc_triples_run_partition (the sums are additive over sub-tiles,
+// so the rank sums add up exactly as for (T)).
 int nwc_triples_run_lambda_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
                                      double energy[2], double* per_task) {
   return guarded(c, [&]() {

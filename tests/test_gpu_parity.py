@@ -233,7 +233,7 @@ def test_2eorb_storage_native(oracle, shape, ts, restricted):
 def test_sharded_v2_two_contexts_one_gpu(oracle, h2o_c2v):
     """Sharded V2 addressing (block i -> rank i % 2, compacted shards, peer pointers): two contexts on one GPU stand
     in for two ranks; each runs its half of the task list reading the other's shard.  The IPC/NVLink flavour of the
-    same path is exercised by tools/nccl_smoke.py --sharded on a multi-GPU box."""
+    same path is tests/test_gpu_multi.py (needs two GPUs)."""
     st = h2o_c2v
     ref = oracle.ccsd_t(st)
     ctx = []

@@ -84,7 +84,7 @@ def test_lambda_left_tiles_are_the_t_tiles_of_the_transposed_amplitudes(oracle):
 @pytest.mark.parametrize("shape,ts,restricted,intorb", [("small", 2, True, False), ("small", 3, True, True),
                                                          ("small", 2, False, False), ("h2o", 20, True, False)])
 def test_lambda_ccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, intorb):
-    """nwc_triples_run_lambda (two polarisation runs of the unmodified fused kernel per tuple) against the oracle's
+    """nwc_triples_run_lambda (two-sided tuples through the LAMBDA instantiation of the fused kernel) against the oracle's
     sorted reading, per task and in total; spin-orbital and `2eorb` V2 storage."""
     from nwchem_b200 import capi
     if shape == "small":
@@ -113,8 +113,8 @@ def test_lambda_ccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, intorb)
 
 @pytest.mark.gpu
 def test_lambda_block_partition_sums_to_total(oracle):
-    """nwc_triples_run_lambda_partition: the polarisation sums are additive over sub-tiles, so rank pieces (tuples on a
-    boundary shared at sub-tile granularity) add up to the single-rank energies, and those match the oracle."""
+    """nwc_triples_run_lambda_partition: the two sums are additive over sub-tiles, so rank pieces (tuples on a boundary
+    shared at sub-tile granularity) add up to the single-rank energies, and those match the oracle."""
     from nwchem_b200 import capi
     import dataclasses
     t = synth.shape_tiling("h2o_ccpvdz_c2v")
