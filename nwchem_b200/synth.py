@@ -114,11 +114,10 @@ def random_orbital(t: tl.Tiling, seed: int = 20240229, scale: float = 0.1) -> Or
     return OrbitalV2(a, tab, rng.uniform(-1, 1, size) * scale)
 
 
-def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = False) -> BlockStores:
-    """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts.
-    With an unrestricted tiling (t.restricted False) the same closed-shell tensors are expanded into every spin
-    block (beta tiles are their own owners), so E[T]/E(T) must equal the restricted result: a check of the
-    `restricted` factor-2 / k_alpha logic (ccsd_t_dot.F:52-56, tce_restricted.F)."""
+def physical_dense(t: tl.Tiling, seed: int = 20240229, naux: int = 12):
+    """The dense closed-shell spatial tensors behind `physical`: (no, nv, t1s[a,i], t2s[a,b,i,j], eri[p,q,r,s] = (pq|rs)).
+    Drawn in a tiling-independent order, so different tilesizes (and the dense spin-orbital checks of the oracle) see
+    identical tensors."""
     no = int(sum(t.range[i] for i in range(t.noab) if t.spin[i] == 1))
     nv = int(sum(t.range[i] for i in range(t.noab, t.noab + t.nvab) if t.spin[i] == 1))
     n = no + nv
@@ -143,6 +142,15 @@ def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = 
     t1s[(iv[:, None] ^ io[None, :]) != 0] = 0.0
     m = iv[:, None, None, None] ^ iv[None, :, None, None] ^ io[None, None, :, None] ^ io[None, None, None, :]
     t2s[m != 0] = 0.0
+    return no, nv, t1s, t2s, eri
+
+
+def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = False) -> BlockStores:
+    """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts.
+    With an unrestricted tiling (t.restricted False) the same closed-shell tensors are expanded into every spin
+    block (beta tiles are their own owners), so E[T]/E(T) must equal the restricted result: a check of the
+    `restricted` factor-2 / k_alpha logic (ccsd_t_dot.F:52-56, tce_restricted.F)."""
+    no, nv, t1s, t2s, eri = physical_dense(t, seed, naux)
 
     def so(b):  # spatial ids and spin of tile b (1-based)
         return t.members[b - 1], int(t.spin[b - 1])

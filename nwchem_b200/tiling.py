@@ -223,6 +223,68 @@ def f1_hp_offset(t: Tiling, irrep: int = 0):
     return _hash(keys, sizes)
 
 
+# ---- CR-CCSD(T) intermediates (src/tce/ccsd_t/cr_ccsd_t_N.F, cr_ccsd_t_E.F): the three block stores the per-tuple
+#      routines cr_ccsd_t_N_1 / _N_2 / _E_2 read (the reference can also load them from files: read_in3, gr1_1/gr1_2/ei1_2)
+def cr_n1_offset(t: Tiling, irrep_v: int = 0):
+    """i1(h11 p4 h1 h2) of cr_ccsd_t_N_1, stored (p4b, h11b, h1b<=h2b), h2 fastest; key
+    h2b-1 + noab*(h1b-1 + noab*(h11b-1 + noab*(p4b-noab-1)))  (OFFSET_cr_ccsd_t_N_1_1, cr_ccsd_t_N.F:773-841)."""
+    keys, sizes = [], []
+    sp, sy = t.spin, t.sym
+    for p4b in range(t.noab + 1, t.noab + t.nvab + 1):
+        for h11b in range(1, t.noab + 1):
+            for h1b in range(1, t.noab + 1):
+                for h2b in range(h1b, t.noab + 1):
+                    if sp[h11b - 1] + sp[p4b - 1] != sp[h1b - 1] + sp[h2b - 1]:
+                        continue
+                    if (sy[h11b - 1] ^ sy[p4b - 1] ^ sy[h1b - 1] ^ sy[h2b - 1]) != irrep_v:
+                        continue
+                    if t.restricted and sp[h11b - 1] + sp[p4b - 1] + sp[h1b - 1] + sp[h2b - 1] == 8:
+                        continue
+                    keys.append(h2b - 1 + t.noab * (h1b - 1 + t.noab * (h11b - 1 + t.noab * (p4b - t.noab - 1))))
+                    sizes.append(t.r(p4b) * t.r(h11b) * t.r(h1b) * t.r(h2b))
+    return _hash(keys, sizes)
+
+
+def cr_n2_offset(t: Tiling, irrep_v: int = 0):
+    """i1(p4 p5 h1 p12) of cr_ccsd_t_N_2, stored (p4b<=p5b, h1b, p12b), p12 fastest; key
+    p12b-noab-1 + nvab*(h1b-1 + noab*(p5b-noab-1 + nvab*(p4b-noab-1)))  (OFFSET_cr_ccsd_t_N_2_1, cr_ccsd_t_N.F:4011-4079)."""
+    keys, sizes = [], []
+    sp, sy = t.spin, t.sym
+    for p4b in range(t.noab + 1, t.noab + t.nvab + 1):
+        for p5b in range(p4b, t.noab + t.nvab + 1):
+            for h1b in range(1, t.noab + 1):
+                for p12b in range(t.noab + 1, t.noab + t.nvab + 1):
+                    if sp[p4b - 1] + sp[p5b - 1] != sp[h1b - 1] + sp[p12b - 1]:
+                        continue
+                    if (sy[p4b - 1] ^ sy[p5b - 1] ^ sy[h1b - 1] ^ sy[p12b - 1]) != irrep_v:
+                        continue
+                    if t.restricted and sp[p4b - 1] + sp[p5b - 1] + sp[h1b - 1] + sp[p12b - 1] == 8:
+                        continue
+                    keys.append(p12b - t.noab - 1 + t.nvab * (h1b - 1 + t.noab * (p5b - t.noab - 1 + t.nvab * (p4b - t.noab - 1))))
+                    sizes.append(t.r(p4b) * t.r(p5b) * t.r(h1b) * t.r(p12b))
+    return _hash(keys, sizes)
+
+
+def cr_e2_offset(t: Tiling):
+    """i1(p4 p5 h1 h2)_tt of cr_ccsd_t_E_2: the T2 block structure with target irrep irrep_t xor irrep_t = 0
+    (OFFSET_cr_ccsd_t_E_2_1, cr_ccsd_t_E.F:907-960)."""
+    return t2_offset(t, 0)
+
+
+def decode_cr_n1_key(t: Tiling, key: int):
+    h2b = key % t.noab + 1; key //= t.noab
+    h1b = key % t.noab + 1; key //= t.noab
+    h11b = key % t.noab + 1; key //= t.noab
+    return key + t.noab + 1, h11b, h1b, h2b  # (p4b,h11b,h1b,h2b)
+
+
+def decode_cr_n2_key(t: Tiling, key: int):
+    p12b = key % t.nvab + t.noab + 1; key //= t.nvab
+    h1b = key % t.noab + 1; key //= t.noab
+    p5b = key % t.nvab + t.noab + 1; key //= t.nvab
+    return key + t.noab + 1, p5b, h1b, p12b  # (p4b,p5b,h1b,p12b)
+
+
 def decode_t1_key(t: Tiling, key: int):
     return key // t.noab + t.noab + 1, key % t.noab + 1  # (p5b, h6b)
 

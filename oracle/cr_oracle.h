@@ -1,0 +1,386 @@
+/*
+ * oracle/cr_oracle.h -- TEST INFRASTRUCTURE ONLY (included at the end of triples_oracle.c).
+ *
+ * CR-CCSD(T), the per-tuple half: src/tce/ccsd_t/cr_ccsd_t.F:88-258 with
+ *   cr_ccsd_t_N_1 (cr_ccsd_t_N.F:296-664)   M += -P(9) Sum(h11) t(p4 p5 h1 h11) i1(h11 p6 h2 h3)   kernels sd_t_cr1_K  :6207-6457
+ *   cr_ccsd_t_N_2 (cr_ccsd_t_N.F:3540-3902) M += -P(9) Sum(p12) t(p4 p12 h1 h2) i1(p5 p6 h3 p12)   kernels sd_t_d2cp_K :6464-6717
+ *   cr_ccsd_t_E_1 (cr_ccsd_t_E.F:74-407)    E += P(9) t(p4 p5 h1 h2) t(p6 h3)                      kernels sd_E_K      :982-1204
+ *   cr_ccsd_t_E_2 (cr_ccsd_t_E.F:408-742)   E += -2/3 P(9) t(p4 h1) i1(p5 p6 h2 h3)                kernels sd_E2_K     :1209-1441
+ * and the (T) tiles S = ccsd_t_singles_l, D = ccsd_t_doubles_l (cr_ccsd_t.F:139-144) restated in triples_oracle.c.
+ * The three intermediates (d_i1_1, d_i1_2 of cr_ccsd_t_N, d_i1_2 of cr_ccsd_t_E) are INPUTS here, as they are for the
+ * reference's tuple loop (built once with toggle 1 or read from files, cr_ccsd_t_N.F:57-63); tests obtain them from
+ * oracle/cr_dense.py.
+ *
+ * PARITY PIN STATUS: no QA test of the reference exercises cr-ccsd(t) at the tile level and the Fortran cannot be built
+ * here; this restatement is pinned by (i) line-by-line fidelity (tables below cite their lines), (ii) agreement of the
+ * four sums with an untiled dense evaluation of the same tensor expressions (cr_dense.Dense.dense_reference),
+ * (iii) tile-size invariance, restricted == unrestricted.
+ */
+
+typedef struct {
+  const Integer *n1_hash; const double *n1; /* d_i1_1 / k_i1_offset_1: OFFSET_cr_ccsd_t_N_1_1, cr_ccsd_t_N.F:773 */
+  const Integer *n2_hash; const double *n2; /* d_i1_2 / k_i1_offset_2: OFFSET_cr_ccsd_t_N_2_1, cr_ccsd_t_N.F:4011 */
+  const Integer *e2_hash; const double *e2; /* d_i1_3 / k_i1_offset_3: OFFSET_cr_ccsd_t_E_2_1, cr_ccsd_t_E.F:907 */
+} ora_cr;
+
+/* sd_t_cr1_K (cr_ccsd_t_N.F:6207-6457): the layouts and signs of sd_t_d1_K, but the intermediate is stored
+ * (p6,h7,h2,h3), i.e. v2sub(h3,h2,h7,p6) instead of v2sub(h3,h2,p6,h7) */
+#define DEF_CR1(K, A, B, C, D, E, F, SGN)                                                      \
+  static void ora_sd_t_cr1_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,\
+                               Integer p4d, Integer h7d, double *RESTRICT triplesx,            \
+                               const double *RESTRICT t2sub, const double *RESTRICT v2sub) {   \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                for (Integer h7 = 0; h7 < h7d; h7++)                                          \
+                  triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##=         \
+                      t2sub[h7 + h7d * (p4 + p4d * (p5 + p5d * h1))] *                        \
+                      v2sub[h3 + h3d * (h2 + h2d * (h7 + h7d * p6))];                         \
+  }
+DEF_CR1(1, h3, h2, h1, p6, p5, p4, -) /* :6213,:6223 */
+DEF_CR1(2, h3, h1, h2, p6, p5, p4, +) /* :6241,:6251 */
+DEF_CR1(3, h1, h3, h2, p6, p5, p4, -) /* :6269,:6279 */
+DEF_CR1(4, h3, h2, h1, p5, p4, p6, -) /* :6297,:6307 */
+DEF_CR1(5, h3, h1, h2, p5, p4, p6, +) /* :6325,:6335 */
+DEF_CR1(6, h1, h3, h2, p5, p4, p6, -) /* :6353,:6363 */
+DEF_CR1(7, h3, h2, h1, p5, p6, p4, +) /* :6381,:6391 */
+DEF_CR1(8, h3, h1, h2, p5, p6, p4, -) /* :6409,:6419 */
+DEF_CR1(9, h1, h3, h2, p5, p6, p4, +) /* :6437,:6447 */
+static const d_fn CR1[9] = {ora_sd_t_cr1_1, ora_sd_t_cr1_2, ora_sd_t_cr1_3, ora_sd_t_cr1_4, ora_sd_t_cr1_5,
+                            ora_sd_t_cr1_6, ora_sd_t_cr1_7, ora_sd_t_cr1_8, ora_sd_t_cr1_9};
+
+/* sd_t_d2cp_K (cr_ccsd_t_N.F:6464-6717): declarations, operand layouts and signs identical to sd_t_d2_K
+ * (t2sub(p7,p4,h1,h2), v2sub(p7,h3,p6,p5)); written out again because the reference does */
+#define DEF_D2CP(K, A, B, C, D, E, F, SGN)                                                     \
+  static void ora_sd_t_d2cp_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,\
+                                Integer p4d, Integer p7d, double *RESTRICT triplesx,           \
+                                const double *RESTRICT t2sub, const double *RESTRICT v2sub) {  \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                for (Integer p7 = 0; p7 < p7d; p7++)                                          \
+                  triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##=         \
+                      t2sub[p7 + p7d * (p4 + p4d * (h1 + h1d * h2))] *                        \
+                      v2sub[p7 + p7d * (h3 + h3d * (p6 + p6d * p5))];                         \
+  }
+DEF_D2CP(1, h3, h2, h1, p6, p5, p4, -) /* :6472,:6482 */
+DEF_D2CP(2, h2, h1, h3, p6, p5, p4, -) /* :6500,:6510 */
+DEF_D2CP(3, h2, h3, h1, p6, p5, p4, +) /* :6528,:6538 */
+DEF_D2CP(4, h3, h2, h1, p6, p4, p5, +) /* :6556,:6566 */
+DEF_D2CP(5, h2, h1, h3, p6, p4, p5, +) /* :6584,:6594 */
+DEF_D2CP(6, h2, h3, h1, p6, p4, p5, -) /* :6612,:6622 */
+DEF_D2CP(7, h3, h2, h1, p4, p6, p5, -) /* :6640,:6650 */
+DEF_D2CP(8, h2, h1, h3, p4, p6, p5, -) /* :6668,:6678 */
+DEF_D2CP(9, h2, h3, h1, p4, p6, p5, +) /* :6696,:6706 */
+static const d_fn D2CP[9] = {ora_sd_t_d2cp_1, ora_sd_t_d2cp_2, ora_sd_t_d2cp_3, ora_sd_t_d2cp_4, ora_sd_t_d2cp_5,
+                             ora_sd_t_d2cp_6, ora_sd_t_d2cp_7, ora_sd_t_d2cp_8, ora_sd_t_d2cp_9};
+
+/* sd_E_K (cr_ccsd_t_E.F:982-1204): triplesx(A..F) SGN= t1sub(p6,h3) * t2sub(p4,p5,h1,h2) */
+#define DEF_E1(K, A, B, C, D, E, F, SGN)                                                       \
+  static void ora_sd_E_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,   \
+                           Integer p4d, double *RESTRICT triplesx, const double *RESTRICT t2sub,\
+                           const double *RESTRICT t1sub) {                                     \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] SGN##=           \
+                    t1sub[p6 + p6d * h3] * t2sub[p4 + p4d * (p5 + p5d * (h1 + h1d * h2))];    \
+  }
+DEF_E1(1, h3, h2, h1, p6, p5, p4, +)
+DEF_E1(2, h2, h1, h3, p6, p5, p4, +)
+DEF_E1(3, h2, h3, h1, p6, p5, p4, -)
+DEF_E1(4, h3, h2, h1, p5, p4, p6, +)
+DEF_E1(5, h2, h1, h3, p5, p4, p6, +)
+DEF_E1(6, h2, h3, h1, p5, p4, p6, -)
+DEF_E1(7, h3, h2, h1, p5, p6, p4, -)
+DEF_E1(8, h2, h1, h3, p5, p6, p4, -)
+DEF_E1(9, h2, h3, h1, p5, p6, p4, +)
+typedef void (*e1_fn)(Integer, Integer, Integer, Integer, Integer, Integer, double *, const double *, const double *);
+static const e1_fn E1K[9] = {ora_sd_E_1, ora_sd_E_2, ora_sd_E_3, ora_sd_E_4, ora_sd_E_5, ora_sd_E_6, ora_sd_E_7, ora_sd_E_8, ora_sd_E_9};
+
+/* sd_E2_K (cr_ccsd_t_E.F:1209-1441): triplesx(A..F) += twot * t1sub(p4,h1) * v2sub(h3,h2,p6,p5); the nine layouts are
+ * those of sd_t_s1_K */
+#define DEF_E2(K, A, B, C, D, E, F)                                                            \
+  static void ora_sd_E2_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,  \
+                            Integer p4d, double *RESTRICT triplesx, const double *RESTRICT t1sub,\
+                            const double *RESTRICT v2sub, double twot) {                       \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] +=               \
+                    twot * t1sub[p4 + p4d * h1] * v2sub[h3 + h3d * (h2 + h2d * (p6 + p6d * p5))];\
+  }
+DEF_E2(1, h3, h2, h1, p6, p5, p4)
+DEF_E2(2, h3, h1, h2, p6, p5, p4)
+DEF_E2(3, h1, h3, h2, p6, p5, p4)
+DEF_E2(4, h3, h2, h1, p6, p4, p5)
+DEF_E2(5, h3, h1, h2, p6, p4, p5)
+DEF_E2(6, h1, h3, h2, p6, p4, p5)
+DEF_E2(7, h3, h2, h1, p4, p6, p5)
+DEF_E2(8, h3, h1, h2, p4, p6, p5)
+DEF_E2(9, h1, h3, h2, p4, p6, p5)
+typedef void (*e2_fn)(Integer, Integer, Integer, Integer, Integer, Integer, double *, const double *, const double *, double);
+static const e2_fn E2K[9] = {ora_sd_E2_1, ora_sd_E2_2, ora_sd_E2_3, ora_sd_E2_4, ora_sd_E2_5, ora_sd_E2_6, ora_sd_E2_7, ora_sd_E2_8, ora_sd_E2_9};
+
+static void cr_rows(Integer a3[9][6], const Integer tp[3], const Integer th[3], const int P[3][3], const int H[3][3]) {
+  for (int ip = 0; ip < 3; ip++)
+    for (int ih = 0; ih < 3; ih++) {
+      Integer *r = a3[ip * 3 + ih];
+      r[0] = tp[P[ip][0]]; r[1] = tp[P[ip][1]]; r[2] = tp[P[ip][2]];
+      r[3] = th[H[ih][0]]; r[4] = th[H[ih][1]]; r[5] = th[H[ih][2]];
+    }
+  dedup_rows(a3);
+}
+static int cr_test(const Integer tp[3], const Integer th[3], const Integer rp[3], const Integer rh[3], const int TPk[3], const int THk[3]) {
+  return tp[0] == rp[TPk[0]] && tp[1] == rp[TPk[1]] && tp[2] == rp[TPk[2]] && th[0] == rh[THk[0]] && th[1] == rh[THk[1]] &&
+         th[2] == rh[THk[2]];
+}
+
+/* cr_ccsd_t_N_1 (cr_ccsd_t_N.F:296-664) */
+void ora_cr_ccsd_t_N_1(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer t_p4b, Integer t_p5b, Integer t_p6b,
+                       Integer t_h1b, Integer t_h2b, Integer t_h3b) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  const Integer noab = c->noab, nvab = c->nvab;
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :364-425: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
+  static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (h1,h2,h3),(h2,h1,h3),(h3,h1,h2) */
+  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* tests :531,:564,:597: ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
+  static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==h1,h2,h3; ==h2,h1,h3; ==h2,h3,h1 */
+  Integer a3[9][6];
+  cr_rows(a3, tp, th, P, H);
+  for (int ia6 = 0; ia6 < 9; ia6++) { /* :445 */
+    const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+    if (!(p4b <= p5b && h2b <= h3b && p4b != 0)) continue;            /* :452 */
+    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :455-463 */
+    const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+    for (Integer h7b = 1; h7b <= noab; h7b++) {                        /* :470 (h11b) */
+      if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h7b)) continue;   /* :471 */
+      if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h7b)) != c->irrep_t) continue; /* :473 */
+      Integer p4b_1, p5b_1, h1b_1, h7b_1, p6b_2, h7b_2, h2b_2, h3b_2;
+      restricted_4(c, p4b, p5b, h1b, h7b, &p4b_1, &p5b_1, &h1b_1, &h7b_1); /* :475 */
+      restricted_4(c, p6b, h7b, h2b, h3b, &p6b_2, &h7b_2, &h2b_2, &h3b_2); /* :476 */
+      const Integer dim_common = RANGE(h7b);
+      const Integer dima = dim_common * RANGE(p4b) * RANGE(p5b) * RANGE(h1b);
+      const Integer dimb = dim_common * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
+      if (!(dima > 0 && dimb > 0)) continue;
+      double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
+      double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
+      if (h7b < h1b) { /* :489-495 */
+        get_hash_block(c->t2, k_a, dima, c->t2_hash, h1b_1 - 1 + noab * (h7b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+        ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h7b), RANGE(h1b), 4, 2, 1, 3, -1.0);
+      }
+      if (h1b <= h7b) { /* :497-503 */
+        get_hash_block(c->t2, k_a, dima, c->t2_hash, h7b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+        ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h7b), 3, 2, 1, 4, 1.0);
+      }
+      /* the intermediate block as stored, no sort (:510-513) */
+      get_hash_block(cr->n1, k_b_sort, dimb, cr->n1_hash, h3b_2 - 1 + noab * (h2b_2 - 1 + noab * (h7b_2 - 1 + noab * (p6b_2 - noab - 1))));
+      for (int kp = 0; kp < 3; kp++)
+        for (int kh = 0; kh < 3; kh++)
+          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :531-:640 */
+            CR1[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b), a_c, k_a_sort, k_b_sort);
+      free(k_a); free(k_a_sort); free(k_b_sort);
+    }
+  }
+}
+
+/* cr_ccsd_t_N_2 (cr_ccsd_t_N.F:3540-3902) */
+void ora_cr_ccsd_t_N_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer t_p4b, Integer t_p5b, Integer t_p6b,
+                       Integer t_h1b, Integer t_h2b, Integer t_h3b) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  const Integer noab = c->noab, nvab = c->nvab;
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :3608-3669: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
+  static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (h1,h2,h3),(h2,h3,h1),(h1,h3,h2) */
+  static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==p4,p5,p6; ==p5,p4,p6; ==p5,p6,p4 */
+  static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==h1,h2,h3; ==h3,h1,h2; ==h1,h3,h2 */
+  Integer a3[9][6];
+  cr_rows(a3, tp, th, P, H);
+  for (int ia6 = 0; ia6 < 9; ia6++) {
+    const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+    if (!(p5b <= p6b && h1b <= h2b && p4b != 0)) continue;            /* :3696 */
+    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :3699-3707 */
+    const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+    for (Integer p7b = noab + 1; p7b <= noab + nvab; p7b++) {          /* :3714 (p12b) */
+      if (SPIN(p4b) + SPIN(p7b) != SPIN(h1b) + SPIN(h2b)) continue;
+      if ((SYM(p4b) ^ SYM(p7b) ^ SYM(h1b) ^ SYM(h2b)) != c->irrep_t) continue;
+      Integer p4b_1, p7b_1, h1b_1, h2b_1, p5b_2, p6b_2, h3b_2, p7b_2;
+      restricted_4(c, p4b, p7b, h1b, h2b, &p4b_1, &p7b_1, &h1b_1, &h2b_1); /* :3719 */
+      restricted_4(c, p5b, p6b, h3b, p7b, &p5b_2, &p6b_2, &h3b_2, &p7b_2); /* :3720 */
+      const Integer dim_common = RANGE(p7b);
+      const Integer dima = dim_common * RANGE(p4b) * RANGE(h1b) * RANGE(h2b);
+      const Integer dimb = dim_common * RANGE(p5b) * RANGE(p6b) * RANGE(h3b);
+      if (!(dima > 0 && dimb > 0)) continue;
+      double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
+      double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
+      if (p7b < p4b) { /* :3733-3739 */
+        get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p4b_1 - noab - 1 + nvab * (p7b_1 - noab - 1))));
+        ora_tce_sort_4(k_a, k_a_sort, RANGE(p7b), RANGE(p4b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, -1.0);
+      }
+      if (p4b <= p7b) { /* :3741-3747 */
+        get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p7b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
+        ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p7b), RANGE(h1b), RANGE(h2b), 4, 3, 1, 2, 1.0);
+      }
+      /* :3754-3757: the intermediate block as stored */
+      get_hash_block(cr->n2, k_b_sort, dimb, cr->n2_hash, p7b_2 - noab - 1 + nvab * (h3b_2 - 1 + noab * (p6b_2 - noab - 1 + nvab * (p5b_2 - noab - 1))));
+      for (int kp = 0; kp < 3; kp++)
+        for (int kh = 0; kh < 3; kh++)
+          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :3775-:3880 */
+            D2CP[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b), a_c, k_a_sort, k_b_sort);
+      free(k_a); free(k_a_sort); free(k_b_sort);
+    }
+  }
+}
+
+/* the tuple-level filters of the E routines: as row_allowed, with the irrep targets written there */
+static int cr_row_allowed(const ora_ctx *c, Integer p4b, Integer p5b, Integer p6b, Integer h1b, Integer h2b, Integer h3b, Integer target) {
+  Integer ssum = SPIN(p4b) + SPIN(p5b) + SPIN(p6b) + SPIN(h1b) + SPIN(h2b) + SPIN(h3b);
+  if (c->restricted && ssum == 12) return 0;
+  if (SPIN(p4b) + SPIN(p5b) + SPIN(p6b) != SPIN(h1b) + SPIN(h2b) + SPIN(h3b)) return 0;
+  return (SYM(p4b) ^ SYM(p5b) ^ SYM(p6b) ^ SYM(h1b) ^ SYM(h2b) ^ SYM(h3b)) == target;
+}
+
+/* cr_ccsd_t_E_1 (cr_ccsd_t_E.F:74-407): d_a = T2, d_b = the local T1 copy */
+void ora_cr_ccsd_t_E_1(const ora_ctx *c, double *a_c, Integer t_p4b, Integer t_p5b, Integer t_p6b, Integer t_h1b,
+                       Integer t_h2b, Integer t_h3b) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  const Integer noab = c->noab, nvab = c->nvab;
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :142-203: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
+  static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (h1,h2,h3),(h2,h3,h1),(h1,h3,h2) */
+  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
+  static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==h1,h2,h3; ==h3,h1,h2; ==h1,h3,h2 */
+  Integer a3[9][6];
+  cr_rows(a3, tp, th, P, H);
+  for (int ia6 = 0; ia6 < 9; ia6++) {
+    const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+    if (!(p4b <= p5b && h1b <= h2b && p4b != 0)) continue;                                    /* :230 */
+    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t)) continue;  /* :233-241 */
+    if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h2b)) continue;                             /* :248 */
+    if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h2b)) != c->irrep_t) continue;                  /* :250 */
+    Integer p4b_1, p5b_1, h1b_1, h2b_1, p6b_2, h3b_2;
+    restricted_4(c, p4b, p5b, h1b, h2b, &p4b_1, &p5b_1, &h1b_1, &h2b_1);                      /* :252 */
+    restricted_2(c, p6b, h3b, &p6b_2, &h3b_2);                                                /* :253 */
+    const Integer dima = RANGE(p4b) * RANGE(p5b) * RANGE(h1b) * RANGE(h2b), dimb = RANGE(p6b) * RANGE(h3b);
+    if (!(dima > 0 && dimb > 0)) continue;
+    double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
+    double *k_b = (double *)malloc(sizeof(double) * dimb), *k_b_sort = (double *)malloc(sizeof(double) * dimb);
+    get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1)))); /* :265 */
+    ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, 1.0); /* :268 */
+    get_hash_block(c->t1, k_b, dimb, c->t1_hash, h3b_2 - 1 + noab * (p6b_2 - noab - 1));      /* :276 (GET_HASH_BLOCK_MA) */
+    ora_tce_sort_2(k_b, k_b_sort, RANGE(p6b), RANGE(h3b), 2, 1, 1.0);                         /* :279 */
+    const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+    for (int kp = 0; kp < 3; kp++)
+      for (int kh = 0; kh < 3; kh++)
+        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :292-:388 */
+          E1K[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort);
+    free(k_a); free(k_a_sort); free(k_b); free(k_b_sort);
+  }
+}
+
+/* cr_ccsd_t_E_2 (cr_ccsd_t_E.F:408-742): d_a = the local T1 copy, d_b = i1(p4 p5 h1 h2)_tt */
+void ora_cr_ccsd_t_E_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer t_p4b, Integer t_p5b, Integer t_p6b,
+                       Integer t_h1b, Integer t_h2b, Integer t_h3b) {
+  const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
+  const Integer noab = c->noab, nvab = c->nvab;
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :476-537: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
+  static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (h1,h2,h3),(h2,h1,h3),(h3,h1,h2) */
+  static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==p4,p5,p6; ==p5,p4,p6; ==p5,p6,p4 */
+  static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==h1,h2,h3; ==h2,h1,h3; ==h2,h3,h1 */
+  static const double TWOT[9] = {-2.0 / 3.0, 2.0 / 3.0, -2.0 / 3.0, 2.0 / 3.0, -2.0 / 3.0, 2.0 / 3.0, -2.0 / 3.0, 2.0 / 3.0, -2.0 / 3.0};
+  Integer a3[9][6];
+  cr_rows(a3, tp, th, P, H);
+  for (int ia6 = 0; ia6 < 9; ia6++) {
+    const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
+    if (!(p5b <= p6b && h2b <= h3b && p4b != 0)) continue;                                            /* :564 */
+    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t ^ c->irrep_t)) continue; /* :567-576 */
+    if (SPIN(p4b) != SPIN(h1b)) continue;                                                             /* :580 */
+    if ((SYM(p4b) ^ SYM(h1b)) != c->irrep_t) continue;                                                /* :581 */
+    Integer p4b_1, h1b_1, p5b_2, p6b_2, h2b_2, h3b_2;
+    restricted_2(c, p4b, h1b, &p4b_1, &h1b_1);                                                        /* :583 */
+    restricted_4(c, p5b, p6b, h2b, h3b, &p5b_2, &p6b_2, &h2b_2, &h3b_2);                              /* :584 */
+    const Integer dima = RANGE(p4b) * RANGE(h1b), dimb = RANGE(p5b) * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
+    if (!(dima > 0 && dimb > 0)) continue;
+    double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
+    double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
+    get_hash_block(c->t1, k_a, dima, c->t1_hash, h1b_1 - 1 + noab * (p4b_1 - noab - 1));             /* :596 */
+    ora_tce_sort_2(k_a, k_a_sort, RANGE(p4b), RANGE(h1b), 2, 1, 1.0);                                 /* :599 */
+    get_hash_block(cr->e2, k_b_sort, dimb, cr->e2_hash, h3b_2 - 1 + noab * (h2b_2 - 1 + noab * (p6b_2 - noab - 1 + nvab * (p5b_2 - noab - 1)))); /* :604 */
+    const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
+    for (int kp = 0; kp < 3; kp++)
+      for (int kh = 0; kh < 3; kh++)
+        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :608-:680; twot alternates -2/3, +2/3 */
+          E2K[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort, TWOT[kp * 3 + kh]);
+    free(k_a); free(k_a_sort); free(k_b_sort);
+  }
+}
+
+/* One tuple of cr_ccsd_t.F:88-222.  tuple = (p4b,p5b,p6b,h1b,h2b,h3b); sums[4] += (num1, num2, den1, den2).
+ * Optional outputs (prod(ranges) doubles each, indexed [p4,p5,p6,h1,h2,h3]): the `moment 2,3` tile and the `denominator` tile. */
+void ora_cr_ccsd_t_tuple(const ora_ctx *c, const ora_cr *cr, const Integer *tuple, double *sums, double *right_out, double *den_out) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2], t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  double *k_singles = (double *)calloc(size + 1, sizeof(double)), *k_doubles = (double *)calloc(size + 1, sizeof(double));
+  double *k_right = (double *)calloc(size + 1, sizeof(double)), *k_den = (double *)calloc(size + 1, sizeof(double)); /* :127-138 */
+  ora_ccsd_t_singles_l(c, k_singles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL); /* :139 */
+  ora_ccsd_t_doubles_l(c, k_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL); /* :142 */
+  ora_cr_ccsd_t_N_1(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /* :145 (toggle 2, cr_ccsd_t_N.F:176) */
+  ora_cr_ccsd_t_N_2(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /*      (cr_ccsd_t_N.F:293) */
+  ora_cr_ccsd_t_E_1(c, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);                 /* :150 (cr_ccsd_t_E.F:41) */
+  ora_cr_ccsd_t_E_2(c, cr, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);             /*      (cr_ccsd_t_E.F:70) */
+  const double factor = ora_ccsd_t_factor((int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* :153-167 */
+  const double *e4 = c->evl_sorted + c->offset[t_p4b - 1], *e5 = c->evl_sorted + c->offset[t_p5b - 1];
+  const double *e6 = c->evl_sorted + c->offset[t_p6b - 1], *e1 = c->evl_sorted + c->offset[t_h1b - 1];
+  const double *e2 = c->evl_sorted + c->offset[t_h2b - 1], *e3 = c->evl_sorted + c->offset[t_h3b - 1];
+  double num1 = 0.0, num2 = 0.0, den1 = 0.0, den2 = 0.0;
+  size_t i = 0;
+  for (Integer p4 = 0; p4 < R[0]; p4++)
+    for (Integer p5 = 0; p5 < R[1]; p5++)
+      for (Integer p6 = 0; p6 < R[2]; p6++)
+        for (Integer h1 = 0; h1 < R[3]; h1++)
+          for (Integer h2 = 0; h2 < R[4]; h2++)
+            for (Integer h3 = 0; h3 < R[5]; h3++, i++) {
+              const double d = -e4[p4] - e5[p5] - e6[p6] + e1[h1] + e2[h2] + e3[h3];
+              num1 += factor * k_right[i] * k_doubles[i] / d;                  /* :176-183 */
+              num2 += factor * k_right[i] * (k_singles[i] + k_doubles[i]) / d; /* :184-191 */
+              den1 += factor * k_den[i] * k_doubles[i] / d;                    /* :192-199 */
+              den2 += factor * k_den[i] * (k_singles[i] + k_doubles[i]) / d;   /* :200-207 */
+            }
+  sums[0] += num1; sums[1] += num2; sums[2] += den1; sums[3] += den2;
+  if (right_out) memcpy(right_out, k_right, sizeof(double) * size);
+  if (den_out) memcpy(den_out, k_den, sizeof(double) * size);
+  free(k_singles); free(k_doubles); free(k_right); free(k_den);
+}
+
+/* cr_ccsd_t: all tuples in the loop order of cr_ccsd_t.F:95-100 (nxtask and the ga_acc sums are identity on one rank);
+ * sums[4] = (num1, num2, den1, den2) WITHOUT den0 (:253-254 add it); per_task (optional) 4 doubles per tuple */
+Integer ora_cr_ccsd_t(const ora_ctx *c, const ora_cr *cr, double *sums, double *per_task) {
+  Integer count = 0;
+  sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+  const Integer n0 = c->noab, n1 = c->noab + c->nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue; /* :102-121 */
+              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+              double s[4] = {0.0, 0.0, 0.0, 0.0};
+              ora_cr_ccsd_t_tuple(c, cr, t, s, NULL, NULL);
+              if (per_task) for (int q = 0; q < 4; q++) per_task[4 * count + q] = s[q];
+              for (int q = 0; q < 4; q++) sums[q] += s[q];
+              count++;
+            }
+  return count;
+}

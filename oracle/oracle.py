@@ -303,3 +303,46 @@ def tile_group(n, isize):
 
 def num_threads():
     return int(lib().ora_num_threads())
+
+
+class CR(C.Structure):   # ora_cr (cr_oracle.h)
+    _fields_ = [("n1_hash", PL), ("n1", PD), ("n2_hash", PL), ("n2", PD), ("e2_hash", PL), ("e2", PD)]
+
+
+def make_cr(cr):
+    k = dict(n1h=np.ascontiguousarray(cr.n1_hash, np.int64), n1=np.ascontiguousarray(cr.n1, np.float64),
+             n2h=np.ascontiguousarray(cr.n2_hash, np.int64), n2=np.ascontiguousarray(cr.n2, np.float64),
+             e2h=np.ascontiguousarray(cr.e2_hash, np.int64), e2=np.ascontiguousarray(cr.e2, np.float64))
+    return CR(_pl(k["n1h"]), _pd(k["n1"]), _pl(k["n2h"]), _pd(k["n2"]), _pl(k["e2h"]), _pd(k["e2"])), k
+
+
+def cr_ccsd_t(st, cr):
+    """CR-CCSD(T) tuple loop on the CPU (cr_ccsd_t.F:88-258 restated, cr_oracle.h).  `cr` = cr_dense.CRStores (the three
+    intermediates + den0).  Returns dict(sums = (num1,num2,den1,den2) without den0, per_task[n,4] in the loop order of
+    cr_ccsd_t.F:95-100, tasks[n,6], e1, e2 = the CR-CCSD[T] / CR-CCSD(T) corrections :257-258)."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_cr(cr)
+    n = len(task_list(st.t))
+    s = np.zeros(4); pt = np.zeros((max(n, 1), 4))
+    l.ora_cr_ccsd_t.restype = L
+    cnt = l.ora_cr_ccsd_t(C.byref(c), C.byref(y), _pd(s), _pd(pt))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    den0 = float(getattr(cr, "den0", 0.0))
+    return dict(sums=s.copy(), per_task=pt[:cnt], e1=float(s[0] / (1.0 + s[2] + den0)), e2=float(s[1] / (1.0 + s[3] + den0)))
+
+
+def cr_tuple(st, cr, tup):
+    """One tuple: (sums[4], moment tile, denominator tile), tiles indexed [p4,p5,p6,h1,h2,h3]."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_cr(cr)
+    dims = [st.t.r(int(b)) for b in tup[:6]]
+    n = int(np.prod(dims))
+    s = np.zeros(4); m = np.zeros(n); e = np.zeros(n)
+    tt = np.array(tup[:6], np.int64)
+    l.ora_cr_ccsd_t_tuple(C.byref(c), C.byref(y), _pl(tt), _pd(s), _pd(m), _pd(e))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return s, m.reshape(dims), e.reshape(dims)

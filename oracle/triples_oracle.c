@@ -1366,3 +1366,4 @@ Integer ora_lambda_ccsd_t(const ora_ctx *c, const ora_lambda *y, int sorted, dou
             }
   return count;
 }
+#include "cr_oracle.h"

@@ -1,0 +1,167 @@
+"""CR-CCSD(T) (src/tce/ccsd_t/cr_ccsd_t.F): the oracle's restatement of the tuple loop and the library's
+nwc_triples_run_cr against it.
+
+The tuple loop needs four t3-sized tiles per tuple -- the (T) singles S and doubles D, the moment M (cr_ccsd_t_N_1/_N_2:
+the (T) doubles contractions with V2 replaced by two dressed intermediates) and the denominator tile E (cr_ccsd_t_E_1/_E_2:
+outer products of t1 with t2 and with a t1*t1 intermediate) -- and forms four sums, M.D, M.(S+D), E.D, E.(S+D), each over
+f/Delta.  The intermediates are inputs of the loop (the reference builds them once, or reads them from files); the tests
+take them from a dense spin-orbital evaluation of the TCE expressions (oracle/cr_dense.py).
+
+CPU tests pin the restatement: (i) the tiled sums equal an untiled dense evaluation of the same algebra to 1e-16;
+(ii) tile-size invariance and restricted == unrestricted; (iii) M -> D as the amplitudes go to zero (the dressed
+intermediates reduce to V2), which ties the conventions of the dense intermediates to the line-by-line (T) oracle.
+(File name: sorts last, so the driver's `pytest -x` reaches every older GPU test first.)"""
+import dataclasses
+import numpy as np
+import pytest
+from nwchem_b200 import synth, tiling as tl
+
+OCC, VIRT = [2, 1], [3, 2]     # two irreps, 3 occupied / 5 virtual alpha orbitals
+
+
+def _inputs(ts, restricted=True, shape=None):
+    from oracle import cr_dense
+    if shape is None:
+        t = tl.make_tiling(OCC, VIRT, ts, restricted)
+    else:
+        t = synth.shape_tiling(shape, tilesize=ts, restricted=restricted)
+    d = cr_dense.Dense(t)
+    return synth.physical(t, intorb=True), d.stores(), d
+
+
+def test_cr_offset_tables_have_the_block_structure_of_the_v2_classes_they_dress():
+    """OFFSET_cr_ccsd_t_N_1_1 / _N_2_1 enumerate the same tile quadruples as the <hp||hh> / <pp||hp> classes of V2
+    (the intermediates start as copies of those blocks, cr_ccsd_t_N.F:669,:3907), in their own key order."""
+    t = synth.shape_tiling("h2o_ccpvdz_c2v")
+    n1h, n1 = tl.cr_n1_offset(t); n2h, n2 = tl.cr_n2_offset(t); e2h, e2 = tl.cr_e2_offset(t)
+    v2h, _ = tl.v2_offset(t)
+    hphh = set(); pphp = set()
+    for i in range(int(v2h[0])):
+        g3, g4, g1, g2 = tl.decode_v2_key(t, int(v2h[1 + i]))
+        cls = tuple(b > t.noab for b in (g3, g4, g1, g2))
+        if cls == (False, True, False, False): hphh.add((g3, g4, g1, g2))
+        if cls == (True, True, False, True): pphp.add((g3, g4, g1, g2))
+    got1 = set()
+    for i in range(int(n1h[0])):
+        p4b, h11b, h1b, h2b = tl.decode_cr_n1_key(t, int(n1h[1 + i]))
+        got1.add((h11b, p4b, h1b, h2b))
+    got2 = {tl.decode_cr_n2_key(t, int(n2h[1 + i])) for i in range(int(n2h[0]))}
+    assert got1 == hphh and got2 == pphp
+    t2h, t2n = tl.t2_offset(t)
+    assert np.array_equal(e2h, t2h) and e2 == t2n
+
+
+def test_cr_tiled_oracle_equals_the_untiled_dense_evaluation(oracle):
+    ref = None
+    for ts, restricted in ((1, True), (2, True), (3, True), (8, True), (2, False)):
+        st, cr, d = _inputs(ts, restricted)
+        r = oracle.cr_ccsd_t(st, cr)
+        dense = np.array(d.dense_reference()[:4])
+        assert np.max(np.abs(r["sums"] - dense)) <= 1e-16, (ts, restricted, r["sums"], dense)
+        if ref is None:
+            ref = r
+            assert abs(ref["sums"][0]) > 1e-6 and abs(ref["sums"][2]) > 1e-7 and abs(ref["sums"][1] - ref["sums"][0]) > 1e-6
+            assert abs(cr.den0) > 1e-3
+        assert np.max(np.abs(r["sums"] - ref["sums"])) <= 1e-16                 # tile-size / spin-adaptation invariance
+        assert abs(r["e1"] - ref["e1"]) <= 1e-16 and abs(r["e2"] - ref["e2"]) <= 1e-16
+
+
+def test_cr_moment_tile_is_antisymmetric_dense_tensor_and_reduces_to_the_t_doubles(oracle):
+    """Tile by tile: the oracle's `moment 2,3` and `denominator` tiles are the corresponding blocks of the dense
+    antisymmetric tensors; with amplitudes scaled by s the moment differs from the (T) doubles tile by O(s) relative."""
+    from oracle import cr_dense
+    t = tl.make_tiling(OCC, VIRT, 2)
+    st, cr, d = _inputs(2)
+    S, D, M, E = d.six_index()
+    checked = 0
+    for tup in oracle.task_list(t)[::7]:
+        tup = [int(x) for x in tup[:6]]
+        _, m, e = oracle.cr_tuple(st, cr, tup)
+        s_ref, d_ref = oracle.tuple_tiles(st, tup)[:2]
+        ix = np.ix_(d._pidx(tup[0]), d._pidx(tup[1]), d._pidx(tup[2]), d._hidx(tup[3]), d._hidx(tup[4]), d._hidx(tup[5]))
+        assert np.max(np.abs(m - M[ix])) <= 1e-16 and np.max(np.abs(e - E[ix])) <= 1e-16
+        assert np.max(np.abs(d_ref - D[ix])) <= 1e-16 and np.max(np.abs(s_ref - S[ix])) <= 1e-16
+        checked += 1
+    assert checked >= 5
+    rel = []
+    for sc in (1e-2, 1e-3):
+        dd = cr_dense.Dense(t, t_scale=sc)
+        _, D2, M2, _ = dd.six_index()
+        rel.append(np.max(np.abs(M2 - D2)) / np.max(np.abs(D2)))
+    assert rel[0] < 1e-2 and 8.0 < rel[0] / rel[1] < 12.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU: nwc_triples_set_cr / nwc_triples_run_cr (two passes of two-sided tuples through the LAMBDA instantiation of the
+# fused kernel: numerators with the moment contractions as the right-hand side, denominators with the E outer
+# products bound to the right-hand tile)
+# ------------------------------------------------------------------------------------------------------------------
+def _sorted_rows(tr, pt):
+    order = sorted(range(len(pt)), key=lambda i: tuple(int(x) for x in tr.task_list()[i][:6]))
+    return pt[order]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ts,restricted,intorb", [(None, 2, True, False), (None, 3, True, True),
+                                                         (None, 2, False, False), ("h2o_ccpvdz_c2v", 20, True, False)])
+def test_cr_ccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, intorb):
+    from nwchem_b200 import capi
+    st, cr, d = _inputs(ts, restricted, shape)
+    ref = oracle.cr_ccsd_t(st, cr)
+    tr = capi.Triples(0)
+    if intorb:
+        tr.set_state_2eorb(st)
+    else:
+        tr.set_state(dataclasses.replace(st, orb=None))
+    tr.set_cr(cr)
+    sums, pt = tr.run_cr(per_task=True)
+    got = _sorted_rows(tr, pt)
+    e1, e2 = tr.cr_energies(sums, cr.den0)
+    tr.close()
+    scale = np.max(np.abs(ref["sums"]))
+    assert np.max(np.abs(sums - ref["sums"])) <= 1e-12 * max(1.0, scale / 1e-3), (sums, ref["sums"])
+    assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-10
+    assert np.max(np.abs(got - ref["per_task"])) <= 1e-13
+    assert abs(e1 - ref["e1"]) <= 1e-12 and abs(e2 - ref["e2"]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_cr_block_partition_sums_to_total(oracle):
+    from nwchem_b200 import capi
+    st, cr, d = _inputs(20, True, "h2o_ccpvdz_c2v")
+    ref = oracle.cr_ccsd_t(st, cr)
+    tr = capi.Triples(0)
+    tr.set_state(dataclasses.replace(st, orb=None))
+    tr.set_cr(cr)
+    sums, pt = tr.run_cr(per_task=True)
+    parts = [tr.run_cr_partition(r, 3, per_task=True) for r in range(3)]
+    again, _ = tr.run_cr(per_task=True)
+    tr.close()
+    assert np.max(np.abs(sums - ref["sums"])) <= 1e-12
+    assert np.array_equal(sums, again)                                            # bitwise reproducible
+    assert np.max(np.abs(sum(p[0] for p in parts) - sums)) <= 1e-14
+    assert np.max(np.abs(sum(p[1] for p in parts) - pt)) <= 1e-15
+
+
+@pytest.mark.gpu
+def test_cr_ragged_and_random_blocks(oracle):
+    """Stores without any permutational symmetry (every block iid) on a ragged tiling: the library must follow the
+    reference block by block (which block, which element order, which sign), not merely the antisymmetric algebra."""
+    from nwchem_b200 import capi
+    t = tl.make_tiling([5], [11], 6)             # tiles 5 | 5,6 per spin: ragged against the 4-wide sub-tiles
+    st = synth.random_blocks(t, seed=11)
+    rng = np.random.default_rng(5)
+    from oracle import cr_dense
+    n1h, n1 = tl.cr_n1_offset(t); n2h, n2 = tl.cr_n2_offset(t); e2h, e2 = tl.cr_e2_offset(t)
+    cr = cr_dense.CRStores(n1h, rng.uniform(-1, 1, n1) * 0.1, n2h, rng.uniform(-1, 1, n2) * 0.1, e2h,
+                           rng.uniform(-1, 1, e2) * 0.02, 0.0)
+    ref = oracle.cr_ccsd_t(st, cr)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    tr.set_cr(cr)
+    sums, pt = tr.run_cr(per_task=True)
+    got = _sorted_rows(tr, pt)
+    tr.close()
+    assert np.max(np.abs(ref["per_task"])) > 1e-8
+    assert np.max(np.abs(got - ref["per_task"])) <= 1e-12 * max(1.0, np.max(np.abs(ref["per_task"])))
+    assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-10
