@@ -156,6 +156,34 @@ typedef struct {
 const char *nwc_triples_last_error(void);
 int nwc_triples_create(nwc_triples_ctx **out, int device);
 int nwc_triples_destroy(nwc_triples_ctx *ctx);
+/* Host-only TRACE context: no device, no arithmetic, nothing executes.  The host driver logic of the native tier (which
+ * blocks a tuple reads, through which strides, into which kernel and with which sign: the restatement of
+ * ccsd_t_singles_gpu.F / ccsd_t_doubles_gpu.F / lambda_ccsd_t_left.F / cr_ccsd_t_N.F / cr_ccsd_t_E.F in
+ * csrc/host_driver.h + csrc/native_abi.cu) runs exactly as it does in front of the GPU, but the operand descriptors it
+ * hands to the engine are recorded instead of being packed and launched.  set_state (replicated spin-orbital stores
+ * only), set_lambda and set_cr keep the caller's host arrays by reference; trace_tuple records one tuple
+ * (method 0: (T), 1: Lambda-CCSD(T), 2 / 3: CR-CCSD(T) numerator / denominator pass); trace_take hands the records
+ * out.  Every compute entry point fails on a trace context.  It exists so the CPU test-suite can check the driver half
+ * against the oracle's tiles without a GPU (tests/test_trace.py); the pointers in the records are the caller's. */
+typedef struct {
+  Integer kind;        /* 0 sd_t_s1_K, 1 sd_t_d1_K, 2 sd_t_d2_K (one contracted tile), 3 outer product, 9 end of tuple */
+  Integer k0;          /* K - 1 (kinds 0-2) */
+  Integer side;        /* kinds 1,2: 0 = the tuple's doubles tile, 1 = the second tile of a two-sided tuple;
+                          kind 3: 0 = singles tile, 1 = side-1 tile, 2 = side-0 tile */
+  Integer K;           /* contracted range (kinds 1,2); kind 9: 1 if the tuple is two-sided */
+  Integer neg;         /* kind 3: 1 = subtract */
+  const double *a;     /* kinds 0-2: t1sub / t2sub source; kind 3: the two-index operand */
+  const double *b;     /* kinds 0-2: v2sub source; kind 3: the four-index operand */
+  long long sa[6];     /* element strides: kinds 0-2 per PERMUTED name (h1,h2,h3,p4,p5,p6); kind 3 per physical
+                          position (h3,h2,h1,p6,p5,p4); kind 9: sa = the ranges by physical position */
+  long long sb[6];
+  long long ka, kb;    /* strides of the contracted index */
+  double scale;        /* kinds 1,2: factor of the T2 sort (tce_hashnsort.F); kind 9: the tuple factor */
+} nwc_trace_rec;
+int nwc_triples_create_trace(nwc_triples_ctx **out);
+int nwc_triples_trace_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], int method);
+/* copies up to cap records to out, clears the trace, *n = number of records there were */
+int nwc_triples_trace_take(nwc_triples_ctx *ctx, nwc_trace_rec *out, size_t cap, size_t *n);
 /* copies the tiling tables and uploads the three block stores into HBM (replicated per GPU).  In every set_state*
  * variant a NULL data pointer (st->t1, st->t2, st->v2, orb->v2orb) means "allocate the store, do not upload": the
  * caller fills it on the device (nwc_triples_synth_fill).  A new set_state* call releases whatever the previous one
@@ -266,6 +294,26 @@ int nwc_triples_run_lambda(nwc_triples_ctx *ctx, Integer first, Integer stride, 
 /* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_energy) */
 int nwc_triples_run_lambda_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task,
                                      Integer ntasks, double energy[2], double *per_task);
+/* CR-CCSD(T) (src/tce/ccsd_t/cr_ccsd_t.F, tce_energy.F `cr-ccsd(t)`): the tuple loop cr_ccsd_t.F:88-222.  Per tuple it
+ * needs the (T) tiles S (ccsd_t_singles_l) and D (ccsd_t_doubles_l), the moment M (cr_ccsd_t_N_1/_N_2, cr_ccsd_t_N.F:296,
+ * :3540 -- the doubles contractions with V2 replaced by dressed intermediates) and the denominator tile E
+ * (cr_ccsd_t_E_1/_E_2, cr_ccsd_t_E.F:74,:408 -- outer products), and forms num1 = sum f M D/Delta, num2 = sum f M (S+D)/Delta,
+ * den1 = sum f E D/Delta, den2 = sum f E (S+D)/Delta (:176-207).  set_cr uploads the three intermediates the loop reads
+ * -- what cr_ccsd_t_N(...,toggle 1) / cr_ccsd_t_E(...,toggle 1) leave in d_i1_1, d_i1_2 and d_i1_3, or the files
+ * gr1_1 / gr1_2 / ei1_2 of read_in3 (cr_ccsd_t_N.F:57-63) -- in the reference's block layout with their offset tables:
+ *   n1: i1(h11 p4 h1 h2), blocks (p4b, h11b, h1b<=h2b), key h2b-1+noab*(h1b-1+noab*(h11b-1+noab*(p4b-noab-1)))      (cr_ccsd_t_N.F:773-841)
+ *   n2: i1(p4 p5 h1 p12), blocks (p4b<=p5b, h1b, p12b), key p12b-noab-1+nvab*(h1b-1+noab*(p5b-noab-1+nvab*(p4b-noab-1))) (:4011-4079)
+ *   e2: i1(p4 p5 h1 h2)_tt, the T2 block structure and key                                                       (cr_ccsd_t_E.F:907-960)
+ * run_cr returns sums[4] = (num1, num2, den1, den2) over tasks first, first+stride, ... of the heaviest-first list,
+ * per_task (optional) 4 doubles per task run.  The caller adds den0 (the scalar of cr_ccsd_t_D, cr_ccsd_t.F:67-70) after
+ * the sum over ranks and forms CR-CCSD[T] = num1/(1+den1+den0), CR-CCSD(T) = num2/(1+den2+den0) (:253-258). */
+int nwc_triples_set_cr(nwc_triples_ctx *ctx, const Integer *n1_hash, const double *n1, const Integer *n2_hash,
+                       const double *n2, const Integer *e2_hash, const double *e2);
+int nwc_triples_run_cr(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double sums[4],
+                       double *per_task);
+/* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_sum, n = 4) */
+int nwc_triples_run_cr_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                                 double sums[4], double *per_task);
 /* one tuple, optionally materialising the t3 tiles (validation only) */
 int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                           double *host_doubles, double *host_singles);

@@ -319,6 +319,29 @@ module nwc_triples_mod
       real(c_double), intent(out) :: energy(2)       ! Lambda-CCSD[T], Lambda-CCSD(T) corrections of this rank
       type(c_ptr), value :: per_task
     end function
+    ! CR-CCSD(T) (cr_ccsd_t.F): the three intermediates of the tuple loop -- d_i1_1 / d_i1_2 of cr_ccsd_t_N (toggle 1)
+    ! and d_i1_3 of cr_ccsd_t_E (toggle 1), fetched with get_block into local arrays -- with int_mb(k_i1_offset_1..3)
+    integer(c_int) function nwc_triples_set_cr(ctx, n1_hash, n1, n2_hash, n2, e2_hash, e2) &
+        bind(C, name='nwc_triples_set_cr')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), intent(in) :: n1_hash(*), n2_hash(*), e2_hash(*)
+      real(c_double), intent(in) :: n1(*), n2(*), e2(*)
+    end function
+    integer(c_int) function nwc_triples_run_cr_partition(ctx, rank, nranks, first_task, ntasks, sums, per_task) &
+        bind(C, name='nwc_triples_run_cr_partition')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), value :: rank, nranks, first_task, ntasks
+      real(c_double), intent(out) :: sums(4)         ! num1, num2, den1, den2 of this rank (cr_ccsd_t.F:176-207), without den0
+      type(c_ptr), value :: per_task
+    end function
+    integer(c_int) function nwc_triples_allreduce_sum(ctx, buf, n) bind(C, name='nwc_triples_allreduce_sum')
+      import :: c_int, c_ptr, c_double, c_size_t
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: buf(*)
+      integer(c_size_t), value :: n
+    end function
     integer(c_int) function nwc_triples_nccl_unique_id(id) bind(C, name='nwc_triples_nccl_unique_id')
       import :: c_int, c_char
       character(kind=c_char) :: id(128)

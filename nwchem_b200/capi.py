@@ -26,6 +26,12 @@ class OrbState(C.Structure):  # nwc_tce_orb_state
                 ("v2orb_hash", PL), ("v2orb", PD)]
 
 
+class TraceRec(C.Structure):  # nwc_trace_rec
+    _fields_ = [("kind", L), ("k0", L), ("side", L), ("K", L), ("neg", L), ("a", C.c_void_p), ("b", C.c_void_p),
+                ("sa", C.c_longlong * 6), ("sb", C.c_longlong * 6), ("ka", C.c_longlong), ("kb", C.c_longlong),
+                ("scale", C.c_double)]
+
+
 class Stats(C.Structure):  # nwc_triples_stats
     _fields_ = [("fused_ms", C.c_double), ("repack_ms", C.c_double), ("fused_launches", C.c_longlong),
                 ("repack_launches", C.c_longlong), ("reduce_launches", C.c_longlong), ("work_items", C.c_longlong),
@@ -191,10 +197,34 @@ def ccsd_t_gpu_tuple(st, tup, dump=False):
 class Triples:
     """Native tier: block stores resident in HBM; static task partition; optional NCCL reduction."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, trace: bool = False):
+        """trace=True: host-only trace context (nwc_triples_create_trace): records the driver's operand descriptors,
+        executes nothing; the arrays handed to set_state / set_lambda / set_cr are kept by reference."""
         self._h = C.c_void_p()
-        _check(lib().nwc_triples_create(C.byref(self._h), device), "nwc_triples_create")
+        self._keep = []
+        self.is_trace = bool(trace)
+        if trace:
+            lib().nwc_triples_create_trace.argtypes = [C.POINTER(C.c_void_p)]
+            _check(lib().nwc_triples_create_trace(C.byref(self._h)), "nwc_triples_create_trace")
+        else:
+            _check(lib().nwc_triples_create(C.byref(self._h), device), "nwc_triples_create")
         self.t = None
+
+    def trace_tuple(self, tup, method: int):
+        """Records of one tuple (method 0 (T), 1 Lambda-CCSD(T), 2 / 3 CR-CCSD(T) numerator / denominator pass) as a
+        list of TraceRec; see include/nwc_triples.h nwc_trace_rec."""
+        l = lib()
+        l.nwc_triples_trace_tuple.argtypes = [C.c_void_p, PL, C.c_int]
+        l.nwc_triples_trace_take.argtypes = [C.c_void_p, C.POINTER(TraceRec), C.c_size_t, C.POINTER(C.c_size_t)]
+        tt = np.array([int(x) for x in tup[:6]], np.int64)
+        _check(l.nwc_triples_trace_tuple(self._h, _pl(tt), int(method)), "nwc_triples_trace_tuple")
+        cap = 4096
+        buf = (TraceRec * cap)()
+        n = C.c_size_t(0)
+        _check(l.nwc_triples_trace_take(self._h, buf, cap, C.byref(n)), "nwc_triples_trace_take")
+        if n.value > cap:
+            raise RuntimeError("trace buffer too small")
+        return [buf[i] for i in range(n.value)], buf
 
     def close(self):
         if self._h:
@@ -211,6 +241,8 @@ class Triples:
         s, keep = make_state(st)
         _check(lib().nwc_triples_set_state(self._h, C.byref(s)), "nwc_triples_set_state")
         self.t = st.t
+        if self.is_trace:
+            self._keep.append(keep)
 
     def set_state_2eorb(self, st, rank: int = 0, world: int = 1):
         """`2eorb` storage: V2 is read from st.orb (synth.OrbitalV2), never from st.v2.  world > 1: the orbital
@@ -271,6 +303,8 @@ class Triples:
         l.nwc_triples_set_lambda.argtypes = [C.c_void_p, PL, PD, PL, PD, PL, PD]
         _check(l.nwc_triples_set_lambda(self._h, _pl(k[0]), _pd(k[1]), _pl(k[2]), _pd(k[3]), _pl(k[4]), _pd(k[5])),
                "nwc_triples_set_lambda")
+        if self.is_trace:
+            self._keep.append(k)
 
     def run_lambda(self, first=0, stride=1, max_tasks=0, per_task=False):
         """Lambda-CCSD[T] / Lambda-CCSD(T) correction energies (lambda_ccsd_t.F), tasks first, first+stride, ..."""
@@ -294,6 +328,46 @@ class Triples:
         _check(l.nwc_triples_run_lambda_partition(self._h, rank, world, first_task, ntasks, _pd(e), _pd(pt) if per_task else None),
                "nwc_triples_run_lambda_partition")
         return (float(e[0]), float(e[1]), pt[:n]) if per_task else (float(e[0]), float(e[1]))
+
+    def set_cr(self, cr):
+        """cr: the three CR-CCSD(T) intermediates with their offset tables (attributes n1_hash, n1, n2_hash, n2, e2_hash,
+        e2 -- tiling.cr_n1_offset / cr_n2_offset / cr_e2_offset layouts; cr_ccsd_t_N.F / cr_ccsd_t_E.F toggle 1)."""
+        k = [np.ascontiguousarray(a, np.int64 if i % 2 == 0 else np.float64)
+             for i, a in enumerate((cr.n1_hash, cr.n1, cr.n2_hash, cr.n2, cr.e2_hash, cr.e2))]
+        l = lib()
+        l.nwc_triples_set_cr.argtypes = [C.c_void_p, PL, PD, PL, PD, PL, PD]
+        _check(l.nwc_triples_set_cr(self._h, _pl(k[0]), _pd(k[1]), _pl(k[2]), _pd(k[3]), _pl(k[4]), _pd(k[5])),
+               "nwc_triples_set_cr")
+        if self.is_trace:
+            self._keep.append(k)
+
+    def run_cr(self, first=0, stride=1, max_tasks=0, per_task=False):
+        """CR-CCSD(T) tuple loop (cr_ccsd_t.F:88-222): sums = (num1, num2, den1, den2) without den0 [, per_task[n,4]]."""
+        s = np.zeros(4)
+        cnt = len(range(first, self.num_tasks, stride))
+        if max_tasks and max_tasks > 0:
+            cnt = min(cnt, max_tasks)
+        pt = np.zeros((max(cnt, 1), 4)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_cr.argtypes = [C.c_void_p, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_cr(self._h, first, stride, max_tasks, _pd(s), _pd(pt) if per_task else None),
+               "nwc_triples_run_cr")
+        return (s, pt[:cnt]) if per_task else s
+
+    def run_cr_partition(self, rank: int, world: int, first_task: int = 0, ntasks: int = 0, per_task=False):
+        s = np.zeros(4)
+        n = self.num_tasks - first_task if ntasks <= 0 else min(ntasks, self.num_tasks - first_task)
+        pt = np.zeros((max(n, 1), 4)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_cr_partition.argtypes = [C.c_void_p, L, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_cr_partition(self._h, rank, world, first_task, ntasks, _pd(s), _pd(pt) if per_task else None),
+               "nwc_triples_run_cr_partition")
+        return (s, pt[:n]) if per_task else s
+
+    @staticmethod
+    def cr_energies(sums, den0):
+        """cr_ccsd_t.F:253-258: (CR-CCSD[T], CR-CCSD(T)) corrections from the four sums and the scalar of cr_ccsd_t_D."""
+        return float(sums[0] / (1.0 + sums[2] + den0)), float(sums[1] / (1.0 + sums[3] + den0))
 
     def tuple_items(self, tup) -> int:
         tt = np.array(tup, np.int64)

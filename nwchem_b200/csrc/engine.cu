@@ -65,6 +65,7 @@ size_t Arena::capacity() const {
 
 // ------------------------------------------------------------------------------------------------
 Engine::Engine(int device) : device_(device) {
+  if (trace_only()) { stream_ = nullptr; evt0_ = evt1_ = nullptr; return; }
   NWC_CUDA(cudaSetDevice(device_));
   NWC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   NWC_CUDA(cudaEventCreate(&evt0_));
@@ -83,6 +84,7 @@ double Engine::timer_stop_ms() {
   return ms;
 }
 Engine::~Engine() {
+  if (trace_only()) return;
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
   for (Slot& s : slots_) {
@@ -100,6 +102,7 @@ Engine::~Engine() {
 
 void Engine::trim() {
   abort();
+  if (trace_only()) return;
   for (Slot& s : slots_) {
     s.arena.release();
     if (s.d_meta) { cudaFree(s.d_meta); s.d_meta = nullptr; s.d_meta_cap = 0; }
@@ -107,8 +110,11 @@ void Engine::trim() {
 }
 
 void Engine::abort() {
-  cudaStreamSynchronize(stream_);
-  cudaGetLastError();
+  if (!trace_only()) {
+    cudaStreamSynchronize(stream_);
+    cudaGetLastError();
+  }
+  trace.clear();
   open_ = false;
   tuples_.clear(); descs_.clear(); sdescs_.clear(); jobs_.clear(); ajobs_.clear(); cjobs_.clear();
   items_ = 0; max_chunks_ = 1; max_ablock_ = max_panel_ = max_copy_ = 0;
@@ -160,6 +166,7 @@ void Engine::begin_tuple(const int R_phys[6]) {
   two_sided_ = false;
   cur_sd_singles_.clear();
   cur_sd_doubles_.clear();
+  cur_sd_side0_.clear();
   open_ = true;
 }
 
@@ -179,6 +186,16 @@ void Engine::add_contraction_group(int family, int k0, const Segment* segs, int 
                                    std::vector<GroupPanel>* v_cache, int side) {
   if (!open_ || (family != 1 && family != 2) || k0 < 0 || k0 > 8 || side < 0 || side > 1) throw Error("nwc_triples: bad add_contraction");
   if (side == 1) two_sided_ = true;
+  if (trace_only()) {
+    for (int i = 0; i < nseg; i++) {
+      nwc_trace_rec r{};
+      r.kind = family; r.k0 = k0; r.side = side; r.K = segs[i].K; r.a = segs[i].t.base; r.b = segs[i].v.base;
+      for (int q = 0; q < 6; q++) { r.sa[q] = segs[i].t.stride[q]; r.sb[q] = segs[i].v.stride[q]; }
+      r.ka = segs[i].t.kstride; r.kb = segs[i].v.kstride; r.scale = segs[i].tscale;
+      trace.push_back(r);
+    }
+    return;
+  }
   // which operand is the G1 (one particle + two holes) one, and the singleton names
   const bool t_is_g1 = (family == 2);
   const int pa = pos_of(family, k0, family == 2 ? N_P4 : N_P6);
@@ -242,6 +259,13 @@ void Engine::add_contraction_group(int family, int k0, const Segment* segs, int 
 
 void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub) {
   if (!open_ || k0 < 0 || k0 > 8) throw Error("nwc_triples: bad add_singles");
+  if (trace_only()) {
+    nwc_trace_rec r{};
+    r.kind = 0; r.k0 = k0; r.a = t1sub.base; r.b = v2sub.base; r.scale = 1.0;
+    for (int q = 0; q < 6; q++) { r.sa[q] = t1sub.stride[q]; r.sb[q] = v2sub.stride[q]; }
+    trace.push_back(r);
+    return;
+  }
   SinglesDesc d;
   memset(&d, 0, sizeof(d));
   d.t1 = t1sub.base;
@@ -256,8 +280,9 @@ void Engine::add_singles(int k0, const OperandView& t1sub, const OperandView& v2
   cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R);
 }
 
-void Engine::add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, bool to_doubles) {
+void Engine::add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, int target) {
   if (!open_) throw Error("nwc_triples: add_outer_product outside a tuple");
+  if (target != OP_SINGLES && target != OP_SIDE1 && target != OP_SIDE0) throw Error("nwc_triples: bad outer-product target");
   SinglesDesc d;
   memset(&d, 0, sizeof(d));
   d.t1 = a;
@@ -272,12 +297,28 @@ void Engine::add_outer_product(const double* a, const int sa[6], const double* b
   // (a stride may legitimately be 0 only for an index the operand lacks; ranges of 1 still carry stride >= 1)
   if (na != 2 || nb != 4) throw Error("nwc_triples: outer product needs a 2-index and a 4-index operand");
   d.neg = negative ? 1 : 0;
-  (to_doubles ? cur_sd_doubles_ : cur_sd_singles_).push_back(d);
+  if (trace_only()) {
+    nwc_trace_rec r{};
+    r.kind = 3; r.side = target; r.neg = d.neg; r.a = a; r.b = b; r.scale = 1.0;
+    for (int q = 0; q < 6; q++) { r.sa[q] = sa[q]; r.sb[q] = sb[q]; }
+    trace.push_back(r);
+    return;
+  }
+  (target == OP_SIDE0 ? cur_sd_side0_ : target == OP_SIDE1 ? cur_sd_doubles_ : cur_sd_singles_).push_back(d);
   cur_hdr_.factor += 2.0 * prodR(cur_hdr_.R);
 }
 
 void Engine::end_tuple(const double* const eps[6], double factor, long long item_lo, long long item_hi) {
   if (!open_) throw Error("nwc_triples: end_tuple without begin_tuple");
+  if (trace_only()) {
+    nwc_trace_rec r{};
+    r.kind = 9; r.K = two_sided_ ? 1 : 0; r.scale = factor;
+    for (int q = 0; q < 6; q++) r.sa[q] = cur_hdr_.R[q];
+    r.sb[0] = item_lo; r.sb[1] = item_hi;
+    trace.push_back(r);
+    open_ = false;
+    return;
+  }
   // reference argument order (h1,h2,h3,p4,p5,p6) -> physical positions
   cur_hdr_.eps[POS_H1] = eps[0]; cur_hdr_.eps[POS_H2] = eps[1]; cur_hdr_.eps[POS_H3] = eps[2];
   cur_hdr_.eps[POS_P4] = eps[3]; cur_hdr_.eps[POS_P5] = eps[4]; cur_hdr_.eps[POS_P6] = eps[5];
@@ -296,15 +337,18 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
     n += (int)cur_descs_[1][s].size();
   }
   cur_hdr_.desc2_begin[9] = n;
-  cur_hdr_.two_sided = two_sided_ ? 1 : 0;
+  if (!two_sided_ && !cur_sd_side0_.empty()) { open_ = false; throw Error("nwc_triples: side-0 outer products need a two-sided tuple"); }
+  cur_hdr_.two_sided = two_sided_ ? 1 + (int)cur_sd_side0_.size() : 0;   // kernels.cuh TupleHdr
   cur_hdr_.sdesc_begin = (int)sdescs_.size();
+  sdescs_.insert(sdescs_.end(), cur_sd_side0_.begin(), cur_sd_side0_.end());
   sdescs_.insert(sdescs_.end(), cur_sd_doubles_.begin(), cur_sd_doubles_.end());
   cur_hdr_.sdesc_mid = (int)sdescs_.size();
   sdescs_.insert(sdescs_.end(), cur_sd_singles_.begin(), cur_sd_singles_.end());
   cur_hdr_.sdesc_end = (int)sdescs_.size();
   open_ = false;
-  if (cur_hdr_.sdesc_end - cur_hdr_.sdesc_begin > MAX_SINGLES_TERMS)
-    throw Error("nwc_triples: more than " + std::to_string(MAX_SINGLES_TERMS) + " outer-product terms in one tuple");
+  const int max_terms = two_sided_ ? MAX_SINGLES_TERMS_2S : MAX_SINGLES_TERMS;
+  if (cur_hdr_.sdesc_end - cur_hdr_.sdesc_begin > max_terms)
+    throw Error("nwc_triples: more than " + std::to_string(max_terms) + " outer-product terms in one tuple");
   const long long all = tuple_items(cur_hdr_.R);
   if (item_hi < 0 || item_hi > all) item_hi = all;
   if (item_lo < 0) item_lo = 0;
@@ -394,6 +438,7 @@ void Engine::flush_prep() {
 
 int Engine::submit(double* dump_doubles, double* dump_singles) {
   if (open_) throw Error("nwc_triples: submit with an open tuple");
+  if (trace_only()) throw Error("nwc_triples: a trace context cannot execute anything (there is no CPU fallback)");
   const int nt = (int)tuples_.size();
   if (nt == 0) return -1;
   Slot& S = slots_[cur_];

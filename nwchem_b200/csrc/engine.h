@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include "kernels.cuh"
 #include "tables.h"
+#include "../../include/nwc_triples.h"
 
 namespace nwc {
 
@@ -82,9 +83,12 @@ struct EngineStats {
 
 class Engine {
  public:
-  explicit Engine(int device);
+  explicit Engine(int device);   // device < 0: host-only trace engine (include/nwc_triples.h nwc_triples_create_trace)
   ~Engine();
   int device() const { return device_; }
+  // trace engine: the add_* calls record their operand descriptors here instead of building panels; nothing launches
+  bool trace_only() const { return device_ < 0; }
+  std::vector<nwc_trace_rec> trace;
   cudaStream_t stream() const { return stream_; }
   Arena& arena() { return slots_[cur_].arena; }   // arena of the batch being built
   int current_slot() const { return cur_; }
@@ -116,9 +120,11 @@ class Engine {
   }
   void add_singles(int k0, const OperandView& t1sub, const OperandView& v2sub);
   // generic outer-product term  +-a[sum g*sa] * b[sum g*sb]  (element strides per PHYSICAL position h3,h2,h1,p6,p5,p4;
-  // `a` carries one hole and one particle index, `b` the other four).  to_doubles: the term belongs to the doubles
-  // tile (added before the energy pass) instead of the singles tile.
-  void add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, bool to_doubles);
+  // `a` carries one hole and one particle index, `b` the other four).  target: OP_SINGLES = the singles tile;
+  // OP_SIDE1 = the side-1 doubles tile of a two-sided tuple (Lambda-CCSD(T): y2*f); OP_SIDE0 = its side-0 tile
+  // (CR-CCSD(T): the denominator tile E).  Doubles-bound terms are added before the energy pass.
+  enum { OP_SINGLES = 0, OP_SIDE1 = 1, OP_SIDE0 = 2 };
+  void add_outer_product(const double* a, const int sa[6], const double* b, const int sb[6], bool negative, int target);
   // eps: six DEVICE vectors in reference argument order (h1,h2,h3,p4,p5,p6).  [item_lo, item_hi) restricts the launch
   // to a sub-range of the tuple's 4^6 sub-tiles (linear index, h3 block fastest, p4 block slowest; item_hi < 0 = all):
   // energies are additive over sub-tiles, so a tuple can be shared between GPUs or evaluated slab by slab.
@@ -176,7 +182,7 @@ class Engine {
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;
-  std::vector<SinglesDesc> cur_sd_singles_, cur_sd_doubles_;   // of the tuple being built
+  std::vector<SinglesDesc> cur_sd_singles_, cur_sd_doubles_, cur_sd_side0_;   // of the tuple being built
   std::vector<RepackJob> jobs_;
   std::vector<AntisymJob> ajobs_;
   std::vector<CopyJob> cjobs_;

@@ -195,12 +195,13 @@ inline int build_rows(const Integer t[6], const int P[3][3], const int H[3][3], 
   return n;
 }
 
-inline bool row_ok(const HostState& S, const Row& r) {
+inline bool row_ok_target(const HostState& S, const Row& r, Integer target) {
   const Integer ps = S.sp(r.p4b) + S.sp(r.p5b) + S.sp(r.p6b), hs = S.sp(r.h1b) + S.sp(r.h2b) + S.sp(r.h3b);
   if (S.restricted && ps + hs == 12) return false;
   if (ps != hs) return false;
-  return (S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.p6b) ^ S.sy(r.h1b) ^ S.sy(r.h2b) ^ S.sy(r.h3b)) == (S.irrep_v ^ S.irrep_t);
+  return (S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.p6b) ^ S.sy(r.h1b) ^ S.sy(r.h2b) ^ S.sy(r.h3b)) == target;
 }
+inline bool row_ok(const HostState& S, const Row& r) { return row_ok_target(S, r, S.irrep_v ^ S.irrep_t); }
 
 // which of the nine kernels fire for this row: kernel K=3*kp+kh fires iff the task tuple equals the row
 // permuted by TP[kp] (particles) and TH[kh] (holes)
@@ -218,8 +219,11 @@ inline int fired(const Integer t[6], const Row& r, const int TP[3][3], const int
 }
 
 // t = (t_p4b,t_p5b,t_p6b,t_h1b,t_h2b,t_h3b)
+// row_target < 0: the (T) filter (irrep_v xor irrep_t).  cr_ccsd_t_E_2 (cr_ccsd_t_E.F:408-742) is this same walk -- same
+// rows :476-537, row filter :564, t1 filter :580-581, restricted maps :583-584, dispatch tests :608-680 -- with the row
+// target irrep_t^irrep_t^irrep_t (:575) and the <pp||hh> block replaced by the i1(pphh)_tt intermediate.
 template <class Sink>
-void walk_singles(const HostState& S, const Integer t[6], Sink& sink) {
+void walk_singles(const HostState& S, const Integer t[6], Sink& sink, Integer row_target = -1) {
   static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};   // ccsd_t_singles_gpu.F:101-162
   static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
   static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}};  // tests :281,:370,:462
@@ -229,7 +233,7 @@ void walk_singles(const HostState& S, const Integer t[6], Sink& sink) {
   for (int i = 0; i < n; i++) {
     const Row& r = rows[i];
     if (!(r.p5b <= r.p6b && r.h2b <= r.h3b)) continue;                       // :200
-    if (!row_ok(S, r)) continue;                                             // :203-211
+    if (!(row_target < 0 ? row_ok(S, r) : row_ok_target(S, r, row_target))) continue;   // :203-211
     if (S.sp(r.p4b) != S.sp(r.h1b)) continue;                                // :218
     if ((S.sy(r.p4b) ^ S.sy(r.h1b)) != S.irrep_t) continue;                  // :219
     bool fire[9];
@@ -239,6 +243,32 @@ void walk_singles(const HostState& S, const Integer t[6], Sink& sink) {
     restricted_map(S, 2, a, am);                                             // :221
     restricted_map(S, 4, b, bm);                                             // :222
     sink.singles(r, am[0], am[1], bm[0], bm[1], bm[2], bm[3], fire);
+  }
+}
+
+// cr_ccsd_t_E_1 (cr_ccsd_t_E.F:74-407): E += P(9) t(p4 p5 h1 h2) t(p6 h3) -- nine outer products of a T2 block with a T1
+// block.  Reports (row, T2 block ids after tce_restricted_4, T1 block ids after tce_restricted_2, fired sd_E_K).
+template <class Sink>
+void walk_cr_e1(const HostState& S, const Integer t[6], Sink& sink) {
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};   // rows :142-203: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5)
+  static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};   //                (h1,h2,h3),(h2,h3,h1),(h1,h3,h2)
+  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :292,:325,:358
+  static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :292,:303,:314
+  Row rows[9];
+  const int n = build_rows(t, P, H, rows);
+  for (int i = 0; i < n; i++) {
+    const Row& r = rows[i];
+    if (!(r.p4b <= r.p5b && r.h1b <= r.h2b)) continue;                                  // :230
+    if (!row_ok_target(S, r, S.irrep_t ^ S.irrep_t)) continue;                          // :233-241
+    if (S.sp(r.p4b) + S.sp(r.p5b) != S.sp(r.h1b) + S.sp(r.h2b)) continue;               // :248
+    if ((S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.h1b) ^ S.sy(r.h2b)) != S.irrep_t) continue; // :250
+    bool fire[9];
+    if (!fired(t, r, TP, TH, fire)) continue;
+    const Integer a[4] = {r.p4b, r.p5b, r.h1b, r.h2b}, b[2] = {r.p6b, r.h3b};
+    Integer am[4], bm[2];
+    restricted_map(S, 4, a, am);                                                        // :252
+    restricted_map(S, 2, b, bm);                                                        // :253
+    sink.cr_e1(r, am, bm, fire);
   }
 }
 
@@ -320,6 +350,9 @@ struct CostSink {
   void d1_pair(const Row&, Integer h7b, const Integer*, const Integer*, const bool fire[9]) { pair(S.rg(h7b), fire); }
   void d2_pair(const Row&, Integer p7b, const Integer*, const Integer*, const bool fire[9]) { pair(S.rg(p7b), fire); }
   void row_end(int) { planes += rowfired * ((rowK + 3) / 4); rowK = 0; rowfired = 0; }
+  void cr_e1(const Row&, const Integer*, const Integer*, const bool fire[9]) {
+    for (int k = 0; k < 9; k++) if (fire[k]) planes += 1;
+  }
 };
 
 inline long long tuple_sub_tiles(const HostState& S, const Integer t[6]) {

@@ -297,10 +297,13 @@ struct __align__(16) FusedSmem {
 
 // Lambda-CCSD(T) launches append a second canonical tile: the right-hand doubles Td are parked there while the
 // left-hand tile Yd is accumulated in `canon` (2 CTAs/SM instead of 3)
+constexpr int MAX_SDESC2 = MAX_SINGLES_TERMS_2S - MAX_SDESC;   // outer-product terms beyond FusedSmem::st (two-sided tuples only)
 struct __align__(16) LambdaSmem {
   double canon2[SUBTILE];
   int desc2_begin[10];
-  int pad[2];
+  int nsd_mid0;                             // terms [0, nsd_mid0) are added to the SIDE-0 tile (canon2), [nsd_mid0, nsd_mid) to canon
+  int pad[1];
+  SinglesTerm st2[MAX_SDESC2];
 };
 
 int fused_smem_bytes() { return (int)sizeof(FusedSmem); }
@@ -578,9 +581,14 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
-    sm.nsd = nsd < MAX_SDESC ? nsd : MAX_SDESC;
+    constexpr int SD_CAP = LAMBDA ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC;
+    sm.nsd = nsd < SD_CAP ? nsd : SD_CAP;
     const int nmid = T.sdesc_mid - T.sdesc_begin;
     sm.nsd_mid = nmid < 0 ? 0 : (nmid < sm.nsd ? nmid : sm.nsd);
+    if (LAMBDA) {
+      const int n0 = T.two_sided - 1;
+      lm.nsd_mid0 = n0 < 0 ? 0 : (n0 < sm.nsd_mid ? n0 : sm.nsd_mid);
+    }
     sm.zero = 0;
   }
   if (tid < 10) sm.desc_begin[tid] = T.desc_begin[tid];
@@ -622,10 +630,11 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     if (lane < 24) sm.eps[q][i] = __ldg(T.eps[q] + g);
   }
   if (warp == 2) {  // one lane per singles term: staged-layout multipliers, source strides and sub-tile origin
-    const int nsd_l = min(T.sdesc_end - T.sdesc_begin, MAX_SDESC);
+    const int nsd_l = min(T.sdesc_end - T.sdesc_begin, LAMBDA ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC);
     const bool act = lane < nsd_l;
     const SinglesDesc* sd = act ? &sdescs[T.sdesc_begin + lane] : nullptr;
-    SinglesTerm& st = sm.st[lane < MAX_SDESC ? lane : 0];
+    SinglesTerm& st = (LAMBDA && lane >= MAX_SDESC) ? lm.st2[lane - MAX_SDESC < MAX_SDESC2 ? lane - MAX_SDESC : 0]
+                                                    : sm.st[lane < MAX_SDESC ? lane : 0];
     int mt = 0, mv = 0, edge = 0;
     int vbase = 0, tbase = 0;
 #pragma unroll
@@ -782,10 +791,16 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   // Two groups of outer-product terms: [0, nsd_mid) belong to the DOUBLES tile (Lambda-CCSD(T): y2 * f, lambda_ccsd_t_left_2)
   // and are added into the canonical tile before the energy pass; [nsd_mid, nsd) are the singles (sd_t_s1_K).  Plain
   // (T) has nsd_mid = 0.
+  // Two-sided tuples (LAMBDA) split the first group once more: [0, nsd_mid0) belong to the side-0 tile parked in canon2
+  // (CR-CCSD(T): the denominator tile E = t2*t1 - 2/3 t1*(t1 t1), cr_ccsd_t_E.F:7-8), [nsd_mid0, nsd_mid) to the side-1 tile.
   bool staged_before = false;
 #pragma unroll 1
-  for (int grp = LAMBDA ? 0 : 1; grp < 2; grp++) {
-    const int glo = (!LAMBDA || grp == 0) ? 0 : sm.nsd_mid, ghi = (LAMBDA && grp == 0) ? sm.nsd_mid : nsd;
+  for (int grp = LAMBDA ? -1 : 1; grp < 2; grp++) {
+    int glo, ghi;
+    if (!LAMBDA) { glo = 0; ghi = nsd; }
+    else if (grp < 0) { glo = 0; ghi = lm.nsd_mid0; }
+    else if (grp == 0) { glo = lm.nsd_mid0; ghi = sm.nsd_mid; }
+    else { glo = sm.nsd_mid; ghi = nsd; }
     if (ghi <= glo) continue;
     // stage the t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges;
     // all loads of a batch of nine terms are issued before the first store (one exposed L2 latency per batch)
@@ -799,7 +814,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
       for (int u = 0; u < SD_PER_PASS; u++) {
         v0[u] = v1[u] = vt[u] = 0.0;
         if (u < nt) {
-          const SinglesTerm& stt = sm.st[t0 + u];
+          const SinglesTerm& stt = (LAMBDA && t0 + u >= MAX_SDESC) ? lm.st2[t0 + u - MAX_SDESC] : sm.st[t0 + u];
           const int offv = stt.vbase + d0 * stt.vs[0] + d1 * stt.vs[1] + d2 * stt.vs[2] + d3 * stt.vs[3];
           const int offt = stt.tbase + d0 * stt.ts[0] + d1 * stt.ts[1];
           bool ok0 = true, ok1 = true, okt = true;
@@ -827,7 +842,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
       // DFMA that lands between two DMMAs costs about one DMMA slot.  So: pull the operands of a term into registers
       // first, then issue its 32 DFMAs back to back.
       for (int t = 0; t < nt; t++) {
-        const SinglesTerm stt = sm.st[t0 + t];
+        const SinglesTerm stt = (LAMBDA && t0 + t >= MAX_SDESC) ? lm.st2[t0 + t - MAX_SDESC] : sm.st[t0 + t];
         const double* t1s = sm.ring + t * SD_TERM;
         const double* v2s = t1s + SD_T1;
         const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + (2 * wo1) * stt.wt[5];
@@ -868,11 +883,12 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
         }
       }
     }
-    if (LAMBDA && grp == 0) {   // doubles-bound terms: fold them into this warp's quarter of the canonical tile, start the singles from 0
+    if (LAMBDA && grp < 1) {   // doubles-bound terms: fold them into this warp's quarter of their canonical tile, start the next group from 0
       const int Ad = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
+      double* tile = grp < 0 ? lm.canon2 : sm.canon;
 #pragma unroll
       for (int jj = 0; jj < 32; jj++) {
-        sm.canon[Ad ^ canon_swz(jj << 6)] += sing[jj];
+        tile[Ad ^ canon_swz(jj << 6)] += sing[jj];
         sing[jj] = 0.0;
       }
     }

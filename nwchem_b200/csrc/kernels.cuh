@@ -35,6 +35,8 @@ struct SinglesDesc {    // one fired sd_t_s1_K call:  S +-= t1[sum g*st1] * v2[s
   int pad;
 };
 constexpr int MAX_SINGLES_TERMS = 18;   // per tuple: nine sd_t_s1_K terms + nine doubles-bound outer products (Lambda-CCSD(T))
+constexpr int MAX_SINGLES_TERMS_2S = 32;   // two-sided tuples (the LAMBDA instantiation keeps the extra terms in its own shared
+                                           // memory): CR-CCSD(T)'s denominator pass has 9 + 9 + 9 outer-product terms
 
 struct TupleHdr {
   int R[6];             // ranges by physical position (h3,h2,h1,p6,p5,p4)
@@ -43,8 +45,10 @@ struct TupleHdr {
   double factor;        // ccsd_t_dot.F:52-66
   int desc_begin[10];   // split s owns descs [desc_begin[s], desc_begin[s+1])
   int sdesc_begin, sdesc_end;
-  int sdesc_mid;        // outer-product terms [sdesc_begin, sdesc_mid) are added to the DOUBLES tile, the rest are the singles
-  int two_sided;        // Lambda-CCSD(T): desc2_begin lists the LEFT-hand contractions, the energy pairs the two tiles
+  int sdesc_mid;        // outer-product terms [sdesc_begin, sdesc_mid) are added to the DOUBLES tiles, the rest are the singles
+  int two_sided;        // 0: plain (T).  1 + n0: two-sided tuple (Lambda-/CR-CCSD(T)): desc2_begin lists the side-1
+                        // contractions, the energy pairs the two tiles, and the first n0 outer-product terms
+                        // [sdesc_begin, sdesc_begin + n0) belong to the SIDE-0 tile, [.., sdesc_mid) to the side-1 tile
   int desc2_begin[10];  // split s of the left-hand side owns descs [desc2_begin[s], desc2_begin[s+1])
   long long item_begin; // first work item (sub-tile) of this tuple in the launch
   int nitems;            // work items of this launch (a sub-range when the tuple is split across GPUs)

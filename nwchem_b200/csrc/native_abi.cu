@@ -78,6 +78,11 @@ struct nwc_triples_ctx {
   double *d_y1 = nullptr, *d_y2 = nullptr, *d_f1 = nullptr;
   size_t n_y1 = 0, n_y2 = 0, n_f1 = 0;
   std::vector<Integer> y1_hash, y2_hash, f1_hash;
+  // CR-CCSD(T) inputs (nwc_triples_set_cr): the three intermediates of cr_ccsd_t.F's tuple loop, replicated
+  double *d_crn1 = nullptr, *d_crn2 = nullptr, *d_cre2 = nullptr;
+  size_t n_crn1 = 0, n_crn2 = 0, n_cre2 = 0;
+  std::vector<Integer> crn1_hash, crn2_hash, cre2_hash;
+  std::vector<double> cre2_scaled;          // trace contexts keep host data by reference: the 2/3-scaled copy lives here
   // per batch slot (engine.h): blocks that live in that slot's arena
   std::unordered_map<Integer, const double*> v2_built[2];   // spin-orbital key -> antisymmetrised block
   std::unordered_map<Integer, const double*> pulled[2];     // block index -> local copy of a remote block
@@ -86,6 +91,15 @@ struct nwc_triples_ctx {
 namespace {
 
 void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_state* variant
+  if (c->eng->trace_only()) {   // host-only trace context: every store pointer is borrowed from the caller
+    c->eng->abort();
+    c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = c->d_y1 = c->d_y2 = c->d_f1 = nullptr;
+    c->d_crn1 = c->d_crn2 = c->d_cre2 = nullptr;
+    c->y1_hash.clear(); c->y2_hash.clear(); c->f1_hash.clear();
+    c->crn1_hash.clear(); c->crn2_hash.clear(); c->cre2_hash.clear();
+    c->klist.clear();
+    return;
+  }
   cudaSetDevice(c->eng->device());
   c->eng->abort();
   for (size_t r = 0; r < c->v2_peer.size(); r++)
@@ -94,9 +108,12 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
   c->v2_nshards = 1; c->v2_rank = 0;
   cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl);
   cudaFree(c->d_y1); cudaFree(c->d_y2); cudaFree(c->d_f1);
+  cudaFree(c->d_crn1); cudaFree(c->d_crn2); cudaFree(c->d_cre2);
   c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = c->d_y1 = c->d_y2 = c->d_f1 = nullptr;
-  c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = c->n_y1 = c->n_y2 = c->n_f1 = 0;
+  c->d_crn1 = c->d_crn2 = c->d_cre2 = nullptr;
+  c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = c->n_y1 = c->n_y2 = c->n_f1 = c->n_crn1 = c->n_crn2 = c->n_cre2 = 0;
   c->y1_hash.clear(); c->y2_hash.clear(); c->f1_hash.clear();
+  c->crn1_hash.clear(); c->crn2_hash.clear(); c->cre2_hash.clear();
   for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
   c->S.intorb = false; c->S.orb_off.clear(); c->S.host_off.clear(); c->S.orb_runs.clear(); c->S.orb_blocks.clear();
   c->S.orb_index.clear(); c->S.orb_size = c->S.orb_host_size = 0;
@@ -221,6 +238,13 @@ struct NativeSink {
   int side = 0;              // 0: the tuple's doubles tile; 1: the left-hand doubles tile of a two-sided (Lambda) tuple
   bool want_singles = true;  // (T) right-hand side of Lambda-CCSD(T) uses the doubles only (lambda_ccsd_t.F:109-111)
   bool want_doubles = true;
+  // CR-CCSD(T) (cr_ccsd_t.F:139-152).  CR_MOMENT: the walk of the (T) doubles produces the moment tile -- cr_ccsd_t_N_1 /
+  // _N_2 are ccsd_t_doubles with the <hp||hh> / <pp||hp> blocks replaced by the dressed intermediates (same rows, filters,
+  // T2 fetches, dispatch tests and kernel layouts/signs; only the store, its key and, for N_1, the element order differ).
+  // CR_DENOM: the walk of the (T) singles produces cr_ccsd_t_E_2 (t1 x i1_tt, -2/3) and walk_cr_e1 produces cr_ccsd_t_E_1,
+  // both as outer products bound to the side-0 tile.
+  enum { CR_OFF = 0, CR_MOMENT = 1, CR_DENOM = 2 };
+  int cr = CR_OFF;
   // contracted tiles of the current row, concatenated along K when the row ends (engine.h Segment)
   std::vector<Segment> segs;
   bool row_fire[9] = {false, false, false, false, false, false, false, false, false};
@@ -265,11 +289,41 @@ struct NativeSink {
       t.stride[N_P4] = 1; t.stride[N_H1] = S.rg(r.p4b);
     }
     // V2 block <p5 p6||h2 h3> stored (p5,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,p5)
-    v.base = v2_operand(c, p5b_2, p6b_2, h2b_2, h3b_2, "v2(pphh)");
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.stride[N_P5] = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
+    if (cr == CR_DENOM) {
+      // cr_ccsd_t_E_2: i1(p5 p6 h2 h3)_tt block, same layout, key as a T2 block (cr_ccsd_t_E.F:604-607); sd_E2_K adds
+      // twot * t1sub * v2sub with twot = -2/3 * (sign of sd_t_s1_K) (:612-:680).  The store is resident pre-scaled by
+      // 2/3 (nwc_triples_set_cr), so only the sign is left.
+      v.base = c->d_cre2 + hash_lookup_or_die(c->cre2_hash, t2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "cr e2(pphh)");
+      for (int k = 0; k < 9; k++)
+        if (fire[k]) {
+          int sa[6], sb[6];
+          for (int q = 0; q < 6; q++) { sa[q] = (int)t.stride[DECL[0][k][q]]; sb[q] = (int)v.stride[DECL[0][k][q]]; }
+          e.add_outer_product(t.base, sa, v.base, sb, SIGN[0][k] > 0, Engine::OP_SIDE0);
+        }
+      return;
+    }
+    v.base = v2_operand(c, p5b_2, p6b_2, h2b_2, h3b_2, "v2(pphh)");
     for (int k = 0; k < 9; k++)
       if (fire[k]) e.add_singles(k, t, v);
+  }
+
+  // cr_ccsd_t_E_1 (cr_ccsd_t_E.F:265-281, kernels sd_E_K): t2sub(p4,p5,h1,h2) = the stored T2 block <p4 p5||h1 h2>
+  // (h2 fastest; the reference's TCE_SORT_4(4,3,2,1) only reverses the index order), t1sub(p6,h3) = the stored T1 block
+  void cr_e1(const Row& r, const Integer am[4], const Integer bm[2], const bool fire[9]) {
+    OperandView a, b;
+    a.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, bm[0], bm[1]), "t1");
+    a.stride[N_H3] = 1; a.stride[N_P6] = S.rg(r.h3b);
+    b.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
+    b.stride[N_H2] = 1; b.stride[N_H1] = S.rg(r.h2b); b.stride[N_P5] = S.rg(r.h1b) * S.rg(r.h2b);
+    b.stride[N_P4] = S.rg(r.p5b) * S.rg(r.h1b) * S.rg(r.h2b);
+    for (int k = 0; k < 9; k++)
+      if (fire[k]) {
+        int sa[6], sb[6];
+        for (int q = 0; q < 6; q++) { sa[q] = (int)a.stride[DECL_E1[k][q]]; sb[q] = (int)b.stride[DECL_E1[k][q]]; }
+        e.add_outer_product(a.base, sa, b.base, sb, SIGN_E1[k] < 0, Engine::OP_SIDE0);
+      }
   }
 
   void d1_pair(const Row& r, Integer h7b, const Integer am[4], const Integer bm[4], const bool fire[9]) {
@@ -287,10 +341,19 @@ struct NativeSink {
       t.stride[N_P4] = st[0]; t.stride[N_P5] = st[1]; t.stride[N_H1] = st[2]; t.kstride = st[3];
       sign = 1.0;
     }
-    // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
-    v.base = v2_operand(c, bm[1], bm[0], bm[2], bm[3], "v2(hphh)");
-    v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
-    v.kstride = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
+    if (cr == CR_MOMENT) {
+      // i1(h7 p6 h2 h3) of cr_ccsd_t_N_1, stored (p6,h7,h2,h3), h3 fastest == v2sub(h3,h2,h7,p6) of sd_t_cr1_K; key
+      // h3-1 + noab*(h2-1 + noab*(h7-1 + noab*(p6-noab-1))) (cr_ccsd_t_N.F:510-513)
+      const Integer key = bm[3] - 1 + S.noab * (bm[2] - 1 + S.noab * (bm[1] - 1 + S.noab * (bm[0] - S.noab - 1)));
+      v.base = c->d_crn1 + hash_lookup_or_die(c->crn1_hash, key, "cr n1(phhh)");
+      v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.kstride = S.rg(r.h3b) * S.rg(r.h2b);
+      v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b) * rh7;
+    } else {
+      // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
+      v.base = v2_operand(c, bm[1], bm[0], bm[2], bm[3], "v2(hphh)");
+      v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
+      v.kstride = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
+    }
     push(t, v, sign, rh7, fire);
   }
 
@@ -309,8 +372,12 @@ struct NativeSink {
       t.stride[N_P4] = st[0]; t.kstride = st[1]; t.stride[N_H1] = st[2]; t.stride[N_H2] = st[3];
       sign = 1.0;
     }
-    // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161)
-    v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
+    // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161); CR-CCSD(T): i1(p5 p6 h3 p7)
+    // of cr_ccsd_t_N_2, same layout, key p7-noab-1 + nvab*(h3-1 + noab*(p6-noab-1 + nvab*(p5-noab-1))) (cr_ccsd_t_N.F:3754-3757)
+    if (cr == CR_MOMENT)
+      v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, bm[3] - S.noab - 1 + S.nvab * (bm[2] - 1 + S.noab * (bm[1] - S.noab - 1 + S.nvab * (bm[0] - S.noab - 1))), "cr n2(pphp)");
+    else
+      v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
     v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
     push(t, v, sign, rp7, fire);
@@ -382,11 +449,46 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], long long item_lo
       sb[ppos[v]] = 1; sb[ppos[u]] = (int)S.rg(Pv);                       // y2 block (h4,h5,p1,p2), p2 fastest
       sb[hpos[y]] = (int)(S.rg(Pu) * S.rg(Pv)); sb[hpos[x]] = (int)(S.rg(Hy) * S.rg(Pu) * S.rg(Pv));
       const bool neg = (a == 1) != (b == 1);
-      c->eng->add_outer_product(fblk, sa, yblk, sb, neg, /*to_doubles=*/true);
+      c->eng->add_outer_product(fblk, sa, yblk, sb, neg, Engine::OP_SIDE1);
     }
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
   c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
+}
+
+// CR-CCSD(T) (cr_ccsd_t.F:127-207): per tuple four t3-sized tiles -- S, D of (T), the moment M and the denominator
+// tile E -- and four sums  num1 = <M,D>, num2 = <M,S+D>, den1 = <E,D>, den2 = <E,S+D>,  <A,B> = sum f A B / Delta.
+// Two two-sided tuples through the LAMBDA instantiation of the fused kernel (energy = (<T0,T1>, <T0,T1+Ts>)):
+//   pass 0 (numerators):   side 0 = M (contractions with the dressed intermediates), side 1 = D, singles tile = S
+//   pass 1 (denominators): side 0 = E (18 outer products, no contraction),           side 1 = D, singles tile = S
+// so D is contracted twice (1.5x the minimal FLOPs of this method: a one-pass variant needs four accumulators per
+// sub-tile in the epilogue).  None of the four tiles ever exists in HBM.
+void emit_tuple_cr(nwc_triples_ctx* c, const Integer t[6], int pass, long long item_lo = 0, long long item_hi = -1) {
+  const HostState& S = c->S;
+  int R[6];
+  tuple_ranges(S, t, R);
+  c->eng->begin_tuple(R);
+  if (pass == 0) {   // cr_ccsd_t_N toggle 2: _N_1 (Sum h11) and _N_2 (Sum p12)
+    NativeSink m{c, *c->eng, S};
+    m.cr = NativeSink::CR_MOMENT;
+    m.want_singles = false;
+    walk_doubles(S, t, m);
+  } else {           // cr_ccsd_t_E toggle 2: _E_1, _E_2
+    NativeSink d{c, *c->eng, S};
+    d.cr = NativeSink::CR_DENOM;
+    walk_cr_e1(S, t, d);
+    walk_singles(S, t, d, S.irrep_t ^ S.irrep_t ^ S.irrep_t);
+  }
+  c->eng->set_two_sided();
+  {   // ccsd_t_singles_l / ccsd_t_doubles_l (cr_ccsd_t.F:139-144)
+    NativeSink rhs{c, *c->eng, S};
+    rhs.side = 1;
+    walk_singles(S, t, rhs);
+    walk_doubles(S, t, rhs);
+  }
+  const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
+                          c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
+  c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);   // cr_ccsd_t.F:153-167 == ccsd_t_dot.F:52-66
 }
 
 // Double-buffered batch loop: while the GPU runs batch k the host walks the driver logic of batch k+1 into the other
@@ -428,6 +530,11 @@ struct Pipeline {
 };
 
 int upload(double** dst, size_t* n_out, const double* src, size_t n, Engine* e) {
+  if (e->trace_only()) {   // nothing is copied anywhere: the records will point into the caller's arrays
+    *dst = const_cast<double*>(src);
+    *n_out = n;
+    return 0;
+  }
   if (*dst) { cudaFree(*dst); *dst = nullptr; }
   NWC_TRY(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(double)));
   if (n && src) {
@@ -480,8 +587,22 @@ int nwc_triples_create(nwc_triples_ctx** out, int device) {
   });
 }
 
+int nwc_triples_create_trace(nwc_triples_ctx** out) {
+  return guarded(nullptr, [&]() {
+    nwc_triples_ctx* c = new nwc_triples_ctx();
+    c->eng = new Engine(-1);
+    *out = c;
+    return 0;
+  });
+}
+
 int nwc_triples_destroy(nwc_triples_ctx* c) {
   if (!c) return 0;
+  if (c->eng->trace_only()) {
+    delete c->eng;
+    delete c;
+    return 0;
+  }
   cudaSetDevice(c->eng->device());
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   free_stores(c);
@@ -540,7 +661,7 @@ static void build_shards(nwc_triples_ctx* c, Integer n, int rank, int nranks, Si
 extern "C" {
 int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
   return guarded(c, [&]() {
-    NWC_TRY(cudaSetDevice(c->eng->device()));
+    if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
     free_stores(c);
     c->S.load_tables(st);
     const HostState& S = c->S;
@@ -552,6 +673,7 @@ int nwc_triples_set_state(nwc_triples_ctx* c, const nwc_tce_state* st) {
 }
 
 static int set_state_orbital(nwc_triples_ctx* c, const nwc_tce_state* st, const nwc_tce_orb_state* orb, int rank, int nranks) {
+  if (c->eng->trace_only()) { g_err = "a trace context takes replicated spin-orbital stores only (nwc_triples_set_state)"; return 1; }
   if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
   NWC_TRY(cudaSetDevice(c->eng->device()));
   free_stores(c);
@@ -897,7 +1019,7 @@ int nwc_triples_run_restart(nwc_triples_ctx* c, Integer first, Integer stride, I
 int nwc_triples_set_lambda(nwc_triples_ctx* c, const Integer* y1_hash, const double* y1, const Integer* y2_hash,
                            const double* y2, const Integer* f1_hash, const double* f1) {
   return guarded(c, [&]() {
-    NWC_TRY(cudaSetDevice(c->eng->device()));
+    if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
     const HostState& S = c->S;
     auto load = [&](const Integer* h, const double* data, std::vector<Integer>& tab, double** d, size_t* n, int kind) -> int {
       const Integer nb = h[0];
@@ -934,11 +1056,8 @@ int nwc_triples_set_lambda(nwc_triples_ctx* c, const Integer* y1_hash, const dou
 // Lambda-CCSD[T] / Lambda-CCSD(T) correction energies of tasks first, first+stride, ... (lambda_ccsd_t.F:59-190):
 //   energy[0] = sum f Td Yd / Delta ,  energy[1] = sum f Td (Ys + Yd) / Delta ,
 // the left-hand tiles taken in T3 order (the sort lambda_ccsd_t.F:35-36 announces; see oracle/triples_oracle.c for the
-// literal reading of the file).  The t3-sized tiles never exist in HBM here either: every tuple goes through the
-// UNMODIFIED fused kernel twice, with doubles tile D+ = Td + Yd and D- = Td - Yd and singles tile Ys, and
-//   sum Td Yd / Delta = ( E[D+] - E[D-] ) / 4 ,   sum Td Ys / Delta = ( ES[D+] + ES[D-] ) / 2
-// (polarisation identity; E = the kernel's sum f D^2/Delta, ES = its sum f D S/Delta).  Costs twice the minimal
-// FLOPs of this sibling, in exchange for no second kernel.
+// literal reading of the file).  The t3-sized tiles never exist in HBM here either: every tuple is a two-sided tuple
+// (emit_tuple_lambda) of the LAMBDA instantiation of the fused kernel, at the minimal FLOP count of the method.
 static int run_lambda_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const std::vector<long long>* ranges,
                           double energy[2], double* per_task) {
   NWC_TRY(cudaSetDevice(c->eng->device()));
@@ -982,6 +1101,137 @@ int nwc_triples_run_lambda_partition(nwc_triples_ctx* c, Integer rank, Integer n
     if (!ids.empty()) block_partition(c->S, c->klist, rank, nranks, ids, ranges);
     return run_lambda_ids(c, ids, &ranges, energy, per_task);
   });
+}
+
+// ---- CR-CCSD(T) (src/tce/ccsd_t/cr_ccsd_t.F) ----
+// The three intermediates the reference's tuple loop reads, with their offset tables ([n, keys.., offsets..]):
+//   n1 = d_i1_1 of cr_ccsd_t_N: i1(h11 p4 h1 h2), blocks (p4b,h11b,h1b<=h2b), OFFSET_cr_ccsd_t_N_1_1 (cr_ccsd_t_N.F:773)
+//   n2 = d_i1_2 of cr_ccsd_t_N: i1(p4 p5 h1 p12), blocks (p4b<=p5b,h1b,p12b), OFFSET_cr_ccsd_t_N_2_1 (:4011)
+//   e2 = d_i1_2 of cr_ccsd_t_E: i1(p4 p5 h1 h2)_tt, the T2 block structure,   OFFSET_cr_ccsd_t_E_2_1 (cr_ccsd_t_E.F:907)
+// i.e. what cr_ccsd_t_N(...,1) / cr_ccsd_t_E(...,1) leave in GA, or the files gr1_1 / gr1_2 / ei1_2 of read_in3
+// (cr_ccsd_t_N.F:57-63).  Replicated in HBM.  Call after a set_state* variant.
+int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash, const double* n2,
+                       const Integer* e2_hash, const double* e2) {
+  return guarded(c, [&]() {
+    if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    auto total_of = [&](const Integer* h, int kind) -> size_t {
+      const Integer nb = h[0];
+      if (nb <= 0) return 0;
+      Integer key = h[nb], sz = 0;
+      if (key < 0) throw Error("nwc_triples: CR offset table does not belong to this tiling");
+      if (kind == 1) {          // h2 + noab*(h1 + noab*(h11 + noab*(p4-noab)))
+        const Integer h2 = key % S.noab + 1; key /= S.noab; const Integer h1 = key % S.noab + 1; key /= S.noab;
+        const Integer h11 = key % S.noab + 1; key /= S.noab;
+        if (key >= S.nvab) throw Error("nwc_triples: CR n1 offset table does not belong to this tiling");
+        sz = S.rg(key + S.noab + 1) * S.rg(h11) * S.rg(h1) * S.rg(h2);
+      } else if (kind == 2) {   // p12-noab + nvab*(h1 + noab*(p5-noab + nvab*(p4-noab)))
+        const Integer p12 = key % S.nvab + S.noab + 1; key /= S.nvab; const Integer h1 = key % S.noab + 1; key /= S.noab;
+        const Integer p5 = key % S.nvab + S.noab + 1; key /= S.nvab;
+        if (key >= S.nvab) throw Error("nwc_triples: CR n2 offset table does not belong to this tiling");
+        sz = S.rg(key + S.noab + 1) * S.rg(p5) * S.rg(h1) * S.rg(p12);
+      } else {                  // a T2 key
+        const Integer h2 = key % S.noab + 1; key /= S.noab; const Integer h1 = key % S.noab + 1; key /= S.noab;
+        const Integer p5 = key % S.nvab + S.noab + 1; key /= S.nvab;
+        if (key >= S.nvab) throw Error("nwc_triples: CR e2 offset table does not belong to this tiling");
+        sz = S.rg(key + S.noab + 1) * S.rg(p5) * S.rg(h1) * S.rg(h2);
+      }
+      return (size_t)(h[2 * nb] + sz);
+    };
+    c->crn1_hash.assign(n1_hash, n1_hash + 2 * n1_hash[0] + 1);
+    c->crn2_hash.assign(n2_hash, n2_hash + 2 * n2_hash[0] + 1);
+    c->cre2_hash.assign(e2_hash, e2_hash + 2 * e2_hash[0] + 1);
+    if (upload(&c->d_crn1, &c->n_crn1, n1, total_of(n1_hash, 1), c->eng)) return 1;
+    if (upload(&c->d_crn2, &c->n_crn2, n2, total_of(n2_hash, 2), c->eng)) return 1;
+    // sd_E2_K multiplies by +-2/3 (cr_ccsd_t_E.F:612-680): the factor is folded into the resident copy once
+    const size_t ne = total_of(e2_hash, 3);
+    std::vector<double>& scaled = c->cre2_scaled;
+    scaled.assign(e2 ? ne : 0, 0.0);
+    for (size_t i = 0; i < scaled.size(); i++) scaled[i] = (2.0 / 3.0) * e2[i];
+    if (upload(&c->d_cre2, &c->n_cre2, e2 ? scaled.data() : nullptr, ne, c->eng)) return 1;
+    if (!c->eng->trace_only()) { scaled.clear(); scaled.shrink_to_fit(); }
+    return 0;
+  });
+}
+
+// CR-CCSD(T) sums of tasks `ids` (cr_ccsd_t.F:176-207): sums[4] = (num1, num2, den1, den2) WITHOUT den0; the caller adds
+// the scalar of cr_ccsd_t_D and forms  E[T] = num1/(1+den1+den0),  E(T) = num2/(1+den2+den0)  (:253-258) after the sum over
+// ranks (nwc_triples_allreduce_sum with n = 4).  per_task (optional): 4 doubles per task.
+static int run_cr_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const std::vector<long long>* ranges,
+                      double sums[4], double* per_task) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_run_cr: call nwc_triples_set_cr first"; return 1; }
+  std::vector<double> rows(4 * ids.size() + 4, 0.0);   // row 2i = pass 0 of task i, row 2i+1 = pass 1
+  double dummy[2] = {0.0, 0.0};
+  Pipeline pipe(c, dummy, rows.data());
+  for (size_t i = 0; i < ids.size(); i++) {
+    const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
+    if (ranges && b <= a) continue;
+    for (int pass = 0; pass < 2; pass++) {
+      emit_tuple_cr(c, &c->klist[7 * (size_t)ids[i]], pass, a, b);
+      pipe.emitted((Integer)(2 * i + pass));
+    }
+  }
+  pipe.finish();
+  sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+  for (size_t i = 0; i < ids.size(); i++)
+    for (int q = 0; q < 4; q++) {
+      sums[q] += rows[4 * i + q];
+      if (per_task) per_task[4 * i + q] = rows[4 * i + q];
+    }
+  return 0;
+}
+
+int nwc_triples_run_cr(nwc_triples_ctx* c, Integer first, Integer stride, Integer max_tasks, double sums[4], double* per_task) {
+  return guarded(c, [&]() {
+    if (stride <= 0) stride = 1;
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    std::vector<Integer> ids;
+    for (Integer k = first < 0 ? 0 : first; k < nt && (max_tasks <= 0 || (Integer)ids.size() < max_tasks); k += stride) ids.push_back(k);
+    return run_cr_ids(c, ids, nullptr, sums, per_task);
+  });
+}
+
+// the same over the static block partition of nwc_triples_run_partition (all four sums are additive over sub-tiles)
+int nwc_triples_run_cr_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                                 double sums[4], double* per_task) {
+  return guarded(c, [&]() {
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+    if (first_task < 0) first_task = 0;
+    if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
+    std::vector<Integer> ids;
+    for (Integer i = 0; i < ntasks; i++) ids.push_back(first_task + i);
+    std::vector<long long> ranges;
+    if (!ids.empty()) block_partition(c->S, c->klist, rank, nranks, ids, ranges);
+    return run_cr_ids(c, ids, &ranges, sums, per_task);
+  });
+}
+
+// ---- host-only trace (include/nwc_triples.h): the driver logic above, recorded instead of executed ----
+int nwc_triples_trace_tuple(nwc_triples_ctx* c, const Integer t[6], int method) {
+  return guarded(c, [&]() {
+    if (!c->eng->trace_only()) { g_err = "nwc_triples_trace_tuple needs a context from nwc_triples_create_trace"; return 1; }
+    if (!c->d_t1 || !c->d_t2 || !c->d_v2) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_state first"; return 1; }
+    if (method == 0) emit_tuple(c, t);
+    else if (method == 1) {
+      if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_lambda first"; return 1; }
+      emit_tuple_lambda(c, t);
+    } else if (method == 2 || method == 3) {
+      if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_cr first"; return 1; }
+      emit_tuple_cr(c, t, method - 2);
+    } else { g_err = "nwc_triples_trace_tuple: method must be 0..3"; return 1; }
+    return 0;
+  });
+}
+
+int nwc_triples_trace_take(nwc_triples_ctx* c, nwc_trace_rec* out, size_t cap, size_t* n) {
+  std::vector<nwc_trace_rec>& tr = c->eng->trace;
+  *n = tr.size();
+  const size_t m = tr.size() < cap ? tr.size() : cap;
+  if (out && m) memcpy(out, tr.data(), m * sizeof(nwc_trace_rec));
+  tr.clear();
+  return 0;
 }
 
 int nwc_triples_run_tuple(nwc_triples_ctx* c, const Integer t[6], double energy[2], double* host_doubles,

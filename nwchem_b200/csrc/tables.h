@@ -45,6 +45,16 @@ static const int8_t SIGN[3][9] = {{+1, -1, +1, -1, +1, -1, +1, -1, +1},
                                   {-1, +1, -1, -1, +1, -1, +1, -1, +1},
                                   {-1, -1, +1, +1, +1, -1, -1, -1, +1}};
 
+// CR-CCSD(T), cr_ccsd_t_E_1: sd_E_K, triplesx(...) +-= t1sub(p6,h3) * t2sub(p4,p5,h1,h2)
+// (src/tce/ccsd_t/cr_ccsd_t_E.F: declarations :987..:1187, updates :1000..:1200).  The other three CR kernel families
+// reuse the (T) tables: sd_t_cr1_K == sd_t_d1_K, sd_t_d2cp_K == sd_t_d2_K (cr_ccsd_t_N.F:6207-6717), sd_E2_K == sd_t_s1_K
+// times -2/3 (cr_ccsd_t_E.F:1209-1441).
+static const int8_t DECL_E1[9][6] = {
+    {N_H3, N_H2, N_H1, N_P6, N_P5, N_P4}, {N_H2, N_H1, N_H3, N_P6, N_P5, N_P4}, {N_H2, N_H3, N_H1, N_P6, N_P5, N_P4},
+    {N_H3, N_H2, N_H1, N_P5, N_P4, N_P6}, {N_H2, N_H1, N_H3, N_P5, N_P4, N_P6}, {N_H2, N_H3, N_H1, N_P5, N_P4, N_P6},
+    {N_H3, N_H2, N_H1, N_P5, N_P6, N_P4}, {N_H2, N_H1, N_H3, N_P5, N_P6, N_P4}, {N_H2, N_H3, N_H1, N_P5, N_P6, N_P4}};
+static const int8_t SIGN_E1[9] = {+1, +1, -1, +1, +1, -1, -1, -1, +1};
+
 // position of a permuted name for kernel (family,k0)
 inline int pos_of(int family, int k0, int name) {
   for (int q = 0; q < 6; q++)

@@ -21,3 +21,12 @@ SIGN = ((+1, -1, +1, -1, +1, -1, +1, -1, +1),
         (-1, +1, -1, -1, +1, -1, +1, -1, +1),
         (-1, -1, +1, +1, +1, -1, -1, -1, +1))
 PHYS = ("h3", "h2", "h1", "p6", "p5", "p4")  # physical layout, fastest first
+
+# CR-CCSD(T): sd_E_K of cr_ccsd_t_E_1, triplesx(...) +-= t1sub(p6,h3) * t2sub(p4,p5,h1,h2)
+# (src/tce/ccsd_t/cr_ccsd_t_E.F: declarations :987..:1187, updates :1000..:1200).  The other CR kernel families carry
+# the (T) tables: sd_t_cr1_K == D1, sd_t_d2cp_K == D2 (cr_ccsd_t_N.F:6207-6717), sd_E2_K == S times -2/3.
+_E1 = ("h3 h2 h1 p6 p5 p4", "h2 h1 h3 p6 p5 p4", "h2 h3 h1 p6 p5 p4",
+       "h3 h2 h1 p5 p4 p6", "h2 h1 h3 p5 p4 p6", "h2 h3 h1 p5 p4 p6",
+       "h3 h2 h1 p5 p6 p4", "h2 h1 h3 p5 p6 p4", "h2 h3 h1 p5 p6 p4")
+DECL_E1 = tuple(tuple(s.split()) for s in _E1)
+SIGN_E1 = (+1, +1, -1, +1, +1, -1, -1, -1, +1)

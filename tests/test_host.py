@@ -30,14 +30,14 @@ def test_library_loads_and_exports_all_declared_symbols():
 
 
 def test_kernel_tables_match_between_python_and_c_header():
-    from nwchem_b200.kernel_tables import DECL, SIGN
+    from nwchem_b200.kernel_tables import DECL, SIGN, DECL_E1, SIGN_E1
     src = open(os.path.join(ROOT, "nwchem_b200", "csrc", "tables.h")).read()
     rows = re.findall(r"\{(N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d, N_[HP]\d)\}", src)
-    assert len(rows) == 27
+    assert len(rows) == 36          # 27 (T) entry points + the nine sd_E_K of CR-CCSD(T)
     flat = [tuple(x.strip()[2:].lower() for x in r.split(",")) for r in rows]
-    assert flat == [d for fam in DECL for d in fam]
+    assert flat == [d for fam in DECL for d in fam] + list(DECL_E1)
     signs = re.findall(r"\{([+-]1(?:, [+-]1){8})\}", src)
-    assert [tuple(int(x) for x in s.split(",")) for s in signs] == [tuple(s) for s in SIGN]
+    assert [tuple(int(x) for x in s.split(",")) for s in signs] == [tuple(s) for s in SIGN] + [tuple(SIGN_E1)]
 
 
 @pytest.mark.parametrize("shape,ts", [("h2o_ccpvdz_c2v", 20), ("h2o_ccpvdz_c2v", 5), ("h2o_ccpvdz_c1", 7),
