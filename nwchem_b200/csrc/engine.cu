@@ -164,6 +164,7 @@ void Engine::begin_tuple(const int R_phys[6]) {
   for (int side = 0; side < 2; side++)
     for (int s = 0; s < 9; s++) cur_descs_[side][s].clear();
   two_sided_ = false;
+  dual_ = false;
   cur_sd_singles_.clear();
   cur_sd_doubles_.clear();
   cur_sd_side0_.clear();
@@ -312,7 +313,7 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
   if (!open_) throw Error("nwc_triples: end_tuple without begin_tuple");
   if (trace_only()) {
     nwc_trace_rec r{};
-    r.kind = 9; r.K = two_sided_ ? 1 : 0; r.scale = factor;
+    r.kind = 9; r.K = two_sided_ ? (dual_ ? 2 : 1) : 0; r.scale = factor;
     for (int q = 0; q < 6; q++) r.sa[q] = cur_hdr_.R[q];
     r.sb[0] = item_lo; r.sb[1] = item_hi;
     trace.push_back(r);
@@ -339,6 +340,7 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
   cur_hdr_.desc2_begin[9] = n;
   if (!two_sided_ && !cur_sd_side0_.empty()) { open_ = false; throw Error("nwc_triples: side-0 outer products need a two-sided tuple"); }
   cur_hdr_.two_sided = two_sided_ ? 1 + (int)cur_sd_side0_.size() : 0;   // kernels.cuh TupleHdr
+  if (dual_) cur_hdr_.two_sided = -cur_hdr_.two_sided;
   cur_hdr_.sdesc_begin = (int)sdescs_.size();
   sdescs_.insert(sdescs_.end(), cur_sd_side0_.begin(), cur_sd_side0_.end());
   sdescs_.insert(sdescs_.end(), cur_sd_doubles_.begin(), cur_sd_doubles_.end());
@@ -444,27 +446,44 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   Slot& S = slots_[cur_];
   if (S.busy) throw Error("nwc_triples: batch slot still in flight");
   flush_prep();
+  // Dual-energy batch: every tuple gets a shadow header `items_` work items further on.  The fused kernel is launched over
+  // the real items only (it never sees the shadows) and writes each sub-tile's second energy pair into the shadow's
+  // partial slot; the reduction then treats 2*nt tuples alike.
+  bool dual = false, single = false;
+  for (const TupleHdr& t : tuples_) { dual = dual || t.two_sided < 0; single = single || t.two_sided >= 0; }
+  if (dual && single) throw Error("nwc_triples: a batch cannot mix dual-energy tuples with others");
+  if (dual && (dump_doubles || dump_singles)) throw Error("nwc_triples: the validation dump does not support dual-energy tuples");
+  const int ntot = dual ? 2 * nt : nt;
+  const long long slots = dual ? 2 * items_ : items_;
+  if (dual) {
+    tuples_.reserve((size_t)ntot);
+    for (int i = 0; i < nt; i++) {
+      TupleHdr sh = tuples_[(size_t)i];
+      sh.item_begin += items_;
+      tuples_.push_back(sh);
+    }
+  }
   // one metadata buffer per slot: tuples | descs | sdescs | energies | chunk sums | partials
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t o_t = 0, o_d = al(o_t + nt * sizeof(TupleHdr)), o_s = al(o_d + descs_.size() * sizeof(ContrDesc)),
-               o_e = al(o_s + sdescs_.size() * sizeof(SinglesDesc)), o_c = al(o_e + nt * sizeof(double2)),
-               o_p = al(o_c + (size_t)nt * max_chunks_ * sizeof(double2)),
-               total = al(o_p + (size_t)items_ * partials_per_item() * sizeof(double2));
+  const size_t o_t = 0, o_d = al(o_t + ntot * sizeof(TupleHdr)), o_s = al(o_d + descs_.size() * sizeof(ContrDesc)),
+               o_e = al(o_s + sdescs_.size() * sizeof(SinglesDesc)), o_c = al(o_e + ntot * sizeof(double2)),
+               o_p = al(o_c + (size_t)ntot * max_chunks_ * sizeof(double2)),
+               total = al(o_p + (size_t)slots * partials_per_item() * sizeof(double2));
   if (total > S.d_meta_cap) {
     if (S.d_meta) NWC_CUDA(cudaFree(S.d_meta));
     S.d_meta = nullptr; S.d_meta_cap = 0;
     NWC_CUDA(cudaMalloc(&S.d_meta, total + total / 4));
     S.d_meta_cap = total + total / 4;
   }
-  if ((size_t)nt > S.h_out_cap) {
+  if ((size_t)ntot > S.h_out_cap) {
     if (S.h_out) NWC_CUDA(cudaFreeHost(S.h_out));
     S.h_out = nullptr; S.h_out_cap = 0;
-    const size_t cap = std::max((size_t)nt * 2, (size_t)256);
+    const size_t cap = std::max((size_t)ntot * 2, (size_t)256);
     NWC_CUDA(cudaMallocHost((void**)&S.h_out, cap * sizeof(double2)));
     S.h_out_cap = cap;
   }
   char* dm = (char*)S.d_meta;
-  upload(dm + o_t, tuples_.data(), nt * sizeof(TupleHdr));
+  upload(dm + o_t, tuples_.data(), ntot * sizeof(TupleHdr));
   upload(dm + o_d, descs_.data(), descs_.size() * sizeof(ContrDesc));
   upload(dm + o_s, sdescs_.data(), sdescs_.size() * sizeof(SinglesDesc));
   S.timed[2] = timing;
@@ -489,14 +508,14 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
   }
   NWC_CUDA(cudaGetLastError());
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[5], stream_));
-  launch_reduce((const TupleHdr*)(dm + o_t), nt, (const double2*)(dm + o_p), (double2*)(dm + o_c), max_chunks_,
+  launch_reduce((const TupleHdr*)(dm + o_t), ntot, (const double2*)(dm + o_p), (double2*)(dm + o_c), max_chunks_,
                 (double2*)(dm + o_e), stream_);
   NWC_CUDA(cudaGetLastError());
-  NWC_CUDA(cudaMemcpyAsync(S.h_out, dm + o_e, nt * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+  NWC_CUDA(cudaMemcpyAsync(S.h_out, dm + o_e, ntot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   NWC_CUDA(cudaEventRecord(S.done, stream_));
-  S.ntuples = nt;
+  S.ntuples = ntot;
   S.busy = true;
-  stats.d2h_bytes += nt * sizeof(double2);
+  stats.d2h_bytes += ntot * sizeof(double2);
   stats.fused_launches += 1;
   stats.reduce_launches += 2;
   stats.work_items += items_;

@@ -112,6 +112,10 @@ class Engine {
   void add_contraction_group(int family, int k0, const Segment* segs, int nseg, std::vector<GroupPanel>* t_cache = nullptr,
                              std::vector<GroupPanel>* v_cache = nullptr, int side = 0);
   void set_two_sided() { two_sided_ = true; }   // even if no left-hand contraction fires (its tile is then the outer products)
+  // Dual-energy two-sided tuple (CR-CCSD(T) in one pass): the OP_SIDE0 outer products form a FOURTH tile E instead of
+  // being added to the side-0 tile M, and the kernel returns two energy pairs, (<M,D>, <M,D+S>) and (<E,D>, <E,D+S>).
+  // A batch holds only dual tuples or none; its results come out as [pair 0 of every tuple | pair 1 of every tuple].
+  void set_dual() { two_sided_ = true; dual_ = true; }
   // one contracted tile on its own (K7 = its range)
   void add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale = 1.0) {
     Segment sg;
@@ -140,7 +144,7 @@ class Engine {
   // wait for a submitted slot; energies_out[2*i..] = (E1,E2) of its tuple i.  Rewinds the slot's arena.
   // compact: also merge a fragmented arena into one chunk (only when nothing allocated from it is read afterwards)
   void collect(int slot, double* energies_out, bool compact = false);
-  int slot_tuples(int slot) const { return slots_[slot].ntuples; }
+  int slot_tuples(int slot) const { return slots_[slot].ntuples; }   // result pairs of the slot (2 per tuple for a dual batch)
   bool slot_busy(int slot) const { return slots_[slot].busy; }
   // synchronous convenience: submit + collect
   void run(double* energies_out, double* dump_doubles = nullptr, double* dump_singles = nullptr);
@@ -178,7 +182,7 @@ class Engine {
   bool open_ = false;
   TupleHdr cur_hdr_{};
   std::vector<ContrDesc> cur_descs_[2][9];
-  bool two_sided_ = false;
+  bool two_sided_ = false, dual_ = false;
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;

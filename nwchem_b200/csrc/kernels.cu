@@ -302,7 +302,7 @@ struct __align__(16) LambdaSmem {
   double canon2[SUBTILE];
   int desc2_begin[10];
   int nsd_mid0;                             // terms [0, nsd_mid0) are added to the SIDE-0 tile (canon2), [nsd_mid0, nsd_mid) to canon
-  int pad[1];
+  int dual;                                 // CR-CCSD(T) in one pass: terms [0, nsd_mid0) form a FOURTH tile with its own energy pass
   SinglesTerm st2[MAX_SDESC2];
 };
 
@@ -586,8 +586,10 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     const int nmid = T.sdesc_mid - T.sdesc_begin;
     sm.nsd_mid = nmid < 0 ? 0 : (nmid < sm.nsd ? nmid : sm.nsd);
     if (LAMBDA) {
-      const int n0 = T.two_sided - 1;
+      const int ts = T.two_sided;             // 1 + n0, negative for dual-energy tuples (kernels.cuh TupleHdr)
+      const int n0 = (ts < 0 ? -ts : ts) - 1;
       lm.nsd_mid0 = n0 < 0 ? 0 : (n0 < sm.nsd_mid ? n0 : sm.nsd_mid);
+      lm.dual = ts < 0 ? 1 : 0;
     }
     sm.zero = 0;
   }
@@ -798,91 +800,15 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   for (int grp = LAMBDA ? -1 : 1; grp < 2; grp++) {
     int glo, ghi;
     if (!LAMBDA) { glo = 0; ghi = nsd; }
-    else if (grp < 0) { glo = 0; ghi = lm.nsd_mid0; }
+    else if (grp < 0) { glo = 0; ghi = lm.dual ? 0 : lm.nsd_mid0; }   // dual tuples: these terms get their own pass below
     else if (grp == 0) { glo = lm.nsd_mid0; ghi = sm.nsd_mid; }
     else { glo = sm.nsd_mid; ghi = nsd; }
     if (ghi <= glo) continue;
-    // stage the t1 (4x4, sign folded in) and v2 (4^4) sub-blocks of each term, zero outside the tile ranges;
-    // all loads of a batch of nine terms are issued before the first store (one exposed L2 latency per batch)
-    for (int t0 = glo; t0 < ghi; t0 += SD_PER_PASS) {
-      const int nt = (ghi - t0) < SD_PER_PASS ? (ghi - t0) : SD_PER_PASS;
-      if (staged_before) asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");   // previous pass fully consumed
-      staged_before = true;
-      double v0[SD_PER_PASS], v1[SD_PER_PASS], vt[SD_PER_PASS];
-      const int d0 = tid & 3, d1 = (tid >> 2) & 3, d2 = (tid >> 4) & 3, d3 = (tid >> 6) & 3;   // staged v2 digits
-#pragma unroll
-      for (int u = 0; u < SD_PER_PASS; u++) {
-        v0[u] = v1[u] = vt[u] = 0.0;
-        if (u < nt) {
-          const SinglesTerm& stt = (LAMBDA && t0 + u >= MAX_SDESC) ? lm.st2[t0 + u - MAX_SDESC] : sm.st[t0 + u];
-          const int offv = stt.vbase + d0 * stt.vs[0] + d1 * stt.vs[1] + d2 * stt.vs[2] + d3 * stt.vs[3];
-          const int offt = stt.tbase + d0 * stt.ts[0] + d1 * stt.ts[1];
-          bool ok0 = true, ok1 = true, okt = true;
-          if (stt.edge) {
-            const bool lowok = d0 < stt.vn[0] && d1 < stt.vn[1] && d2 < stt.vn[2];
-            ok0 = lowok && d3 < stt.vn[3];
-            ok1 = lowok && d3 + 2 < stt.vn[3];
-            okt = d0 < stt.tn[0] && d1 < stt.tn[1];
-          }
-          if (ok0) v0[u] = __ldg(stt.v2 + offv);
-          if (ok1) v1[u] = __ldg(stt.v2 + offv + 2 * stt.vs[3]);   // element tid+128: fourth digit + 2
-          if (tid < SD_T1 && okt) { const double x = __ldg(stt.t1 + offt); vt[u] = stt.neg ? -x : x; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < SD_PER_PASS; u++)
-        if (u < nt) {
-          double* dst = sm.ring + u * SD_TERM;
-          dst[SD_T1 + tid] = v0[u];
-          dst[SD_T1 + tid + NCONSUMERS] = v1[u];
-          if (tid < SD_T1) dst[tid] = vt[u];
-        }
-      asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMERS) : "memory");
-      // FP64 ALU instructions share the pipe with the DMMAs of the other CTAs on this SM, and every isolated
-      // DFMA that lands between two DMMAs costs about one DMMA slot.  So: pull the operands of a term into registers
-      // first, then issue its 32 DFMAs back to back.
-      for (int t = 0; t < nt; t++) {
-        const SinglesTerm stt = (LAMBDA && t0 + t >= MAX_SDESC) ? lm.st2[t0 + t - MAX_SDESC] : sm.st[t0 + t];
-        const double* t1s = sm.ring + t * SD_TERM;
-        const double* v2s = t1s + SD_T1;
-        const int ft = i_h3 * stt.wt[0] + i_h2 * stt.wt[1] + i_h1 * stt.wt[2] + (2 * wo1) * stt.wt[5];
-        const int fv = i_h3 * stt.wv[0] + i_h2 * stt.wv[1] + i_h1 * stt.wv[2] + (2 * wo1) * stt.wv[5];
-        const int t6 = stt.wt[3], t5 = stt.wt[4], t4 = stt.wt[5];
-        const int v6 = stt.wv[3], v5 = stt.wv[4], v4 = stt.wv[5];
-        // t1 carries exactly one particle index: over (p6,p5,p4lo) it takes at most four values tv[k]
-        const int tstep = t6 | t5 | t4;
-        double tv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) tv[k] = t1s[ft + k * tstep];
-        // v2 lacks the particle index t1 carries, so a thread needs only 8 (or 16) distinct v2 values per term;
-        // all loads first, then the 32 DFMAs of the term as one burst
-        if (t6) {          // t1(p6,.): v2 over (p5, p4lo)
-          double v8[8];
-#pragma unroll
-          for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) v8[b + 4 * a] = v2s[fv + b * v5 + a * v4];
-#pragma unroll
-          for (int e = 0; e < 32; e++) sing[e] = fma(tv[e & 3], v8[((e >> 2) & 3) + 4 * (e >> 4)], sing[e]);
-        } else if (t5) {   // t1(p5,.): v2 over (p6, p4lo)
-          double v8[8];
-#pragma unroll
-          for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) v8[c + 4 * a] = v2s[fv + c * v6 + a * v4];
-#pragma unroll
-          for (int e = 0; e < 32; e++) sing[e] = fma(tv[(e >> 2) & 3], v8[(e & 3) + 4 * (e >> 4)], sing[e]);
-        } else {           // t1(p4,.): v2 over (p6, p5)
-          double vv[16];
-#pragma unroll
-          for (int b = 0; b < 4; b++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) vv[c + 4 * b] = v2s[fv + c * v6 + b * v5];
-#pragma unroll
-          for (int e = 0; e < 32; e++) sing[e] = fma(tv[e >> 4], vv[e & 15], sing[e]);
-        }
-      }
-    }
+#define NWC_OT_GLO glo
+#define NWC_OT_GHI ghi
+#include "outer_terms.inc"
+#undef NWC_OT_GLO
+#undef NWC_OT_GHI
     if (LAMBDA && grp < 1) {   // doubles-bound terms: fold them into this warp's quarter of their canonical tile, start the next group from 0
       const int Ad = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
       double* tile = grp < 0 ? lm.canon2 : sm.canon;
@@ -961,6 +887,58 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   // one partial per warp: no CTA-wide rendezvous at the end, every warp leaves as soon as it is done
   // (reduce_chunk_kernel adds the four in a fixed order)
   if (lane == 0) partials[item * (NCONSUMERS / 32) + warp] = make_double2(e1, e2);
+  if (LAMBDA) {
+    // Dual tuples (CR-CCSD(T) in one pass, cr_ccsd_t.F:176-207).  So far: canon2 = M, canon = D, sing = S and the two sums
+    // above are num1 = <M,D>, num2 = <M,S+D>.  M is no longer needed: S takes its place in canon2, the outer-product
+    // terms [0, nsd_mid0) -- the denominator tile E of cr_ccsd_t_E -- are accumulated in registers, and a second energy
+    // pass forms den1 = <E,D>, den2 = <E,S+D>.  They go to the partial slot `gridDim.x` work items further on: the host
+    // appends one shadow tuple per tuple there, so the reduction needs no special case.
+    if (lm.dual) {
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        lm.canon2[At ^ canon_swz(jj << 6)] = sing[jj];
+        sing[jj] = 0.0;
+      }
+      __syncwarp();
+      const int e_terms = lm.nsd_mid0;
+#define NWC_OT_GLO 0
+#define NWC_OT_GHI e_terms
+#include "outer_terms.inc"
+#undef NWC_OT_GLO
+#undef NWC_OT_GHI
+      double d1 = 0.0, d2s = 0.0;
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        double dd[8], rr[8], ss[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          dd[u] = sm.canon[At ^ canon_swz((j0 + u) << 6)];
+          ss[u] = lm.canon2[At ^ canon_swz((j0 + u) << 6)];
+          rr[u] = sm.dp[warp][j0 + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) rr[u] = eh + rr[u];
+#pragma unroll
+        for (int u = 0; u < 8; u++) rr[u] = fast_rcp(rr[u]);
+#pragma unroll
+        for (int u = 0; u < 8; u++) rr[u] = sing[j0 + u] * rr[u];           // w = E/Delta
+#pragma unroll
+        for (int u = 0; u < 8; u++) d1 = fma(rr[u], dd[u], d1);
+#pragma unroll
+        for (int u = 0; u < 8; u++) d2s = fma(rr[u], ss[u], d2s);
+      }
+      double d2 = d1 + d2s;
+      d1 *= T.factor;
+      d2 *= T.factor;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      }
+      if (lane == 0) partials[((long long)gridDim.x + item) * (NCONSUMERS / 32) + warp] = make_double2(d1, d2);
+    }
+  }
   if (TIMING && tid == 0 && g_phase_buf && item < g_phase_cap) {
     tph[6] = clock64();
     for (int i = 0; i < 8; i++) g_phase_buf[item * 8 + i] = tph[i];

@@ -461,24 +461,28 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], long long item_lo
 // Two two-sided tuples through the LAMBDA instantiation of the fused kernel (energy = (<T0,T1>, <T0,T1+Ts>)):
 //   pass 0 (numerators):   side 0 = M (contractions with the dressed intermediates), side 1 = D, singles tile = S
 //   pass 1 (denominators): side 0 = E (18 outer products, no contraction),           side 1 = D, singles tile = S
-// so D is contracted twice (1.5x the minimal FLOPs of this method: a one-pass variant needs four accumulators per
-// sub-tile in the epilogue).  None of the four tiles ever exists in HBM.
+// so D is contracted twice (1.5x the minimal FLOPs of the method).  pass 2 = both at once, the default: a DUAL tuple
+// (engine.h set_dual) with side 0 = M, side 1 = D, singles = S and E as a fourth tile that the kernel forms in
+// registers after M has been consumed (kernels.cu, "Dual tuples") -- M and D are contracted once each, the minimal FLOP
+// count.  None of the four tiles ever exists in HBM.
 void emit_tuple_cr(nwc_triples_ctx* c, const Integer t[6], int pass, long long item_lo = 0, long long item_hi = -1) {
   const HostState& S = c->S;
   int R[6];
   tuple_ranges(S, t, R);
   c->eng->begin_tuple(R);
-  if (pass == 0) {   // cr_ccsd_t_N toggle 2: _N_1 (Sum h11) and _N_2 (Sum p12)
+  if (pass == 0 || pass == 2) {   // cr_ccsd_t_N toggle 2: _N_1 (Sum h11) and _N_2 (Sum p12)
     NativeSink m{c, *c->eng, S};
     m.cr = NativeSink::CR_MOMENT;
     m.want_singles = false;
     walk_doubles(S, t, m);
-  } else {           // cr_ccsd_t_E toggle 2: _E_1, _E_2
+  }
+  if (pass == 1 || pass == 2) {   // cr_ccsd_t_E toggle 2: _E_1, _E_2
     NativeSink d{c, *c->eng, S};
     d.cr = NativeSink::CR_DENOM;
     walk_cr_e1(S, t, d);
     walk_singles(S, t, d, S.irrep_t ^ S.irrep_t ^ S.irrep_t);
   }
+  if (pass == 2) c->eng->set_dual();
   c->eng->set_two_sided();
   {   // ccsd_t_singles_l / ccsd_t_doubles_l (cr_ccsd_t.F:139-144)
     NativeSink rhs{c, *c->eng, S};
@@ -500,6 +504,7 @@ struct Pipeline {
   double* per_task;
   std::vector<Integer> cur_pos, prev_pos;   // per_task row of each tuple of the batch being built / in flight
   int prev = -1;
+  bool dual = false;   // dual-energy batches (engine.h set_dual): per_task rows hold four doubles, pair 0 then pair 1
   std::vector<double> eb;
   Pipeline(nwc_triples_ctx* c_, double* en, double* pt) : c(c_), e(*c_->eng), energy(en), per_task(pt) {}
   void emitted(Integer row) {
@@ -508,12 +513,19 @@ struct Pipeline {
   }
   void wait_prev() {
     if (prev < 0) return;
-    eb.assign(2 * prev_pos.size() + 2, 0.0);
+    const size_t n = prev_pos.size();
+    eb.assign((dual ? 4 : 2) * n + 2, 0.0);
     e.collect(prev, eb.data(), /*compact=*/true);
-    for (size_t i = 0; i < prev_pos.size(); i++) {
+    for (size_t i = 0; i < n; i++) {
       energy[0] += eb[2 * i];
       energy[1] += eb[2 * i + 1];
-      if (per_task && prev_pos[i] >= 0) { per_task[2 * prev_pos[i]] += eb[2 * i]; per_task[2 * prev_pos[i] + 1] += eb[2 * i + 1]; }
+      if (!per_task || prev_pos[i] < 0) continue;
+      if (!dual) { per_task[2 * prev_pos[i]] += eb[2 * i]; per_task[2 * prev_pos[i] + 1] += eb[2 * i + 1]; }
+      else
+        for (int q = 0; q < 2; q++) {
+          per_task[4 * prev_pos[i] + q] += eb[2 * i + q];             // pair 0 of tuple i
+          per_task[4 * prev_pos[i] + 2 + q] += eb[2 * (n + i) + q];   // pair 1: the shadow tuples follow the real ones
+        }
     }
     slot_done(c, prev);
     prev = -1;
@@ -1161,15 +1173,23 @@ static int run_cr_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const
                       double sums[4], double* per_task) {
   NWC_TRY(cudaSetDevice(c->eng->device()));
   if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_run_cr: call nwc_triples_set_cr first"; return 1; }
-  std::vector<double> rows(4 * ids.size() + 4, 0.0);   // row 2i = pass 0 of task i, row 2i+1 = pass 1
+  std::vector<double> rows(4 * ids.size() + 4, 0.0);   // four doubles per task
   double dummy[2] = {0.0, 0.0};
   Pipeline pipe(c, dummy, rows.data());
+  const char* tp = getenv("NWC_CR_TWO_PASS");   // A/B: the two-pass form (numerators, then denominators; D contracted twice)
+  const bool two_pass = tp && *tp == '1';
+  pipe.dual = !two_pass;
   for (size_t i = 0; i < ids.size(); i++) {
     const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
     if (ranges && b <= a) continue;
-    for (int pass = 0; pass < 2; pass++) {
-      emit_tuple_cr(c, &c->klist[7 * (size_t)ids[i]], pass, a, b);
-      pipe.emitted((Integer)(2 * i + pass));
+    if (!two_pass) {
+      emit_tuple_cr(c, &c->klist[7 * (size_t)ids[i]], 2, a, b);
+      pipe.emitted((Integer)i);
+    } else {
+      for (int pass = 0; pass < 2; pass++) {   // row 2i = pass 0 of task i, row 2i+1 = pass 1, two doubles each
+        emit_tuple_cr(c, &c->klist[7 * (size_t)ids[i]], pass, a, b);
+        pipe.emitted((Integer)(2 * i + pass));
+      }
     }
   }
   pipe.finish();
@@ -1217,10 +1237,10 @@ int nwc_triples_trace_tuple(nwc_triples_ctx* c, const Integer t[6], int method) 
     else if (method == 1) {
       if (!c->d_y2 || !c->d_y1 || !c->d_f1) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_lambda first"; return 1; }
       emit_tuple_lambda(c, t);
-    } else if (method == 2 || method == 3) {
+    } else if (method >= 2 && method <= 4) {
       if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_cr first"; return 1; }
       emit_tuple_cr(c, t, method - 2);
-    } else { g_err = "nwc_triples_trace_tuple: method must be 0..3"; return 1; }
+    } else { g_err = "nwc_triples_trace_tuple: method must be 0..4"; return 1; }
     return 0;
   });
 }

@@ -26,19 +26,21 @@ def _gather(ptr, offs):
 
 def evaluate(recs):
     """Records of ONE tuple -> (side-0 doubles tile, side-1 tile, singles tile, factor, two_sided), tiles indexed
-    [p4,p5,p6,h1,h2,h3] (C order == the physical T3(h3,h2,h1,p6,p5,p4))."""
+    [p4,p5,p6,h1,h2,h3] (C order == the physical T3(h3,h2,h1,p6,p5,p4)).  For a dual-energy tuple a sixth value follows:
+    the tile of the side-0 outer products, which the kernel keeps apart from the side-0 contractions."""
     end = recs[-1]
     assert end.kind == 9 and all(r.kind != 9 for r in recs[:-1])
+    dual = int(end.K) == 2
     R = [int(end.sa[q]) for q in range(6)]                                  # by physical position, h3 first
     shape = R[::-1]                                                         # numpy axes: p4,p5,p6,h1,h2,h3
     idx = [np.arange(R[q]).reshape([-1 if ax == 5 - q else 1 for ax in range(6)]) for q in range(6)]   # idx[q]: position q
-    tiles = [np.zeros(shape), np.zeros(shape), np.zeros(shape)]             # side 0, side 1, singles
+    tiles = [np.zeros(shape), np.zeros(shape), np.zeros(shape), np.zeros(shape)]   # side 0, side 1, singles, dual: fourth tile
     for r in recs[:-1]:
         if r.kind == 3:                                                     # strides per physical position
             oa = sum(idx[q] * int(r.sa[q]) for q in range(6))
             ob = sum(idx[q] * int(r.sb[q]) for q in range(6))
             val = _gather(r.a, np.broadcast_to(oa, shape)) * _gather(r.b, np.broadcast_to(ob, shape))
-            tiles[{0: 2, 1: 1, 2: 0}[int(r.side)]] += -val if r.neg else val
+            tiles[{0: 2, 1: 1, 2: 3 if dual else 0}[int(r.side)]] += -val if r.neg else val
             continue
         fam, k0 = int(r.kind), int(r.k0)
         decl = DECL[fam][k0]                                                # permuted name at each physical position
@@ -53,6 +55,8 @@ def evaluate(recs):
             for k in range(int(r.K)):
                 acc += _gather(r.a, oa + k * int(r.ka)) * _gather(r.b, ob + k * int(r.kb))
             tiles[int(r.side)] += SIGN[fam][k0] * r.scale * acc
+    if dual:
+        return tiles[0], tiles[1], tiles[2], float(end.scale), True, tiles[3]
     return tiles[0], tiles[1], tiles[2], float(end.scale), bool(end.K)
 
 
@@ -160,6 +164,10 @@ def test_cr_driver_trace_matches_oracle_tiles(oracle, ts, restricted, kind):
         den = _energies(t, tup, e, d, s, f)
         got = np.array([num[0], num[1], den[0], den[1]])
         assert np.max(np.abs(got - sums_ref)) <= 1e-13 * max(1.0, np.max(np.abs(sums_ref)))
+        # the one-pass form (the default of nwc_triples_run_cr): one dual tuple holding all four tiles
+        recs, keep = tr.trace_tuple(tup, 4)
+        m1, d1, s1, f1, two, e1 = evaluate(recs)
+        assert np.array_equal(m1, m) and np.array_equal(d1, d) and np.array_equal(s1, s) and np.array_equal(e1, e) and f1 == f
         n += 1
     tr.close()
     assert n >= 5

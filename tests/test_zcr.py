@@ -92,9 +92,9 @@ def test_cr_moment_tile_is_antisymmetric_dense_tensor_and_reduces_to_the_t_doubl
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# GPU: nwc_triples_set_cr / nwc_triples_run_cr (two passes of two-sided tuples through the LAMBDA instantiation of the
-# fused kernel: numerators with the moment contractions as the right-hand side, denominators with the E outer
-# products bound to the right-hand tile)
+# GPU: nwc_triples_set_cr / nwc_triples_run_cr.  Default: ONE dual-energy tuple per task through the LAMBDA instantiation
+# of the fused kernel (M and D contracted once each; E formed in registers after M has been consumed).  NWC_CR_TWO_PASS=1:
+# two two-sided tuples per task (numerators with M as the side-0 tile, denominators with the E outer products bound to it).
 # ------------------------------------------------------------------------------------------------------------------
 def _sorted_rows(tr, pt):
     order = sorted(range(len(pt)), key=lambda i: tuple(int(x) for x in tr.task_list()[i][:6]))
@@ -165,3 +165,36 @@ def test_cr_ragged_and_random_blocks(oracle):
     assert np.max(np.abs(ref["per_task"])) > 1e-8
     assert np.max(np.abs(got - ref["per_task"])) <= 1e-12 * max(1.0, np.max(np.abs(ref["per_task"])))
     assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_cr_one_pass_equals_two_pass(oracle, monkeypatch):
+    """The dual-tuple form against the two-pass form (same kernels as Lambda-CCSD(T), D contracted twice), per task, on the
+    H2O table and on a ragged tiling with unsymmetric blocks; partition pieces of the dual form add up."""
+    from nwchem_b200 import capi
+    from oracle import cr_dense
+    for which in ("h2o", "ragged"):
+        if which == "h2o":
+            st, cr, d = _inputs(20, True, "h2o_ccpvdz_c2v")
+            st = dataclasses.replace(st, orb=None)
+        else:
+            t = tl.make_tiling([5], [11], 6)
+            st = synth.random_blocks(t, seed=11)
+            rng = np.random.default_rng(5)
+            n1h, n1 = tl.cr_n1_offset(t); n2h, n2 = tl.cr_n2_offset(t); e2h, e2 = tl.cr_e2_offset(t)
+            cr = cr_dense.CRStores(n1h, rng.uniform(-1, 1, n1) * 0.1, n2h, rng.uniform(-1, 1, n2) * 0.1, e2h,
+                                   rng.uniform(-1, 1, e2) * 0.02, 0.0)
+        tr = capi.Triples(0)
+        tr.set_state(st)
+        tr.set_cr(cr)
+        monkeypatch.delenv("NWC_CR_TWO_PASS", raising=False)
+        s1, p1 = tr.run_cr(per_task=True)
+        parts = [tr.run_cr_partition(r, 2, per_task=True) for r in range(2)]
+        monkeypatch.setenv("NWC_CR_TWO_PASS", "1")
+        s2, p2 = tr.run_cr(per_task=True)
+        monkeypatch.delenv("NWC_CR_TWO_PASS", raising=False)
+        tr.close()
+        scale = max(1.0, np.max(np.abs(p2)))
+        assert np.max(np.abs(p1 - p2)) <= 1e-13 * scale, which
+        assert np.max(np.abs(s1 - s2)) <= 1e-12 * max(1.0, np.max(np.abs(s2)))
+        assert np.max(np.abs(sum(p[1] for p in parts) - p1)) <= 1e-13 * scale

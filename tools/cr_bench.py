@@ -1,6 +1,6 @@
 """Timing of nwc_triples_run_cr on a named shape with random intermediates:
 python tools/cr_bench.py [shape] [max_tasks] [out.json].  Reports the (T) run of the same tasks beside it.
-(The two CR passes contract M + D and D again: executed FLOPs = 1.5x the minimal count of the method.)"""
+(Default: one dual-energy tuple per task, M and D contracted once each; the two-pass form contracts D twice.)"""
 import json
 import os
 import sys
@@ -29,14 +29,23 @@ tr = capi.Triples(0)
 tr.set_state(st)
 tr.set_cr(cr)
 res = {}
-for name, fn in (("(T)", lambda: tr.run(max_tasks=max_tasks)), ("CR-(T)", lambda: tr.run_cr(max_tasks=max_tasks))):
+def two_pass():
+    os.environ["NWC_CR_TWO_PASS"] = "1"
+    try:
+        return tr.run_cr(max_tasks=max_tasks)
+    finally:
+        del os.environ["NWC_CR_TWO_PASS"]
+
+
+for name, fn in (("(T)", lambda: tr.run(max_tasks=max_tasks)), ("CR-(T)", lambda: tr.run_cr(max_tasks=max_tasks)),
+                 ("CR-(T) two-pass", two_pass)):
     fn(); fn()
     tr.set_timing(True); tr.stats(reset=True)
     t0 = time.time(); e = fn(); dt = time.time() - t0
     s = tr.stats()
     res[name] = dict(shape=shape, wall_s=dt, fused_ms=s["fused_ms"], flops=s["flops"], tflops=s["flops"] / dt * 1e-12,
                      launches=int(s["fused_launches"]), result=[float(x) for x in np.ravel(e)])
-    print(f"{name:7s} {shape}: {dt:.3f} s wall, fused {s['fused_ms']:.1f} ms, executed {s['flops']:.3e} FLOP = "
+    print(f"{name:15s} {shape}: {dt:.3f} s wall, fused {s['fused_ms']:.1f} ms, executed {s['flops']:.3e} FLOP = "
           f"{s['flops'] / dt * 1e-12:.2f} TFLOP/s, launches {int(s['fused_launches'])}, result {e}", flush=True)
 if out:
     json.dump(res, open(out, "w"), indent=1)
