@@ -494,17 +494,19 @@ int Engine::submit(double* dump_doubles, double* dump_singles) {
     launch_fused_dump((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
                       (double2*)(dm + o_p), items_, dump_doubles, dump_singles, order_, stream_);
   } else {
-    bool ragged = false, lambda = false, plain = false;
+    bool ragged = false, lambda = false, plain = false, crx = false;
     for (const TupleHdr& t : tuples_) {
       for (int q = 0; q < 6; q++) ragged = ragged || (t.R[q] % SB != 0);
       const bool l = t.two_sided != 0;
       if (!l && t.sdesc_mid > t.sdesc_begin) throw Error("nwc_triples: doubles-bound outer products need a two-sided tuple");
       lambda = lambda || l;
       plain = plain || !l;
+      // side-0-bound terms, more terms than FusedSmem holds, or a dual-energy tuple: the CR-CCSD(T) instantiation
+      crx = crx || (t.two_sided != 0 && t.two_sided != 1) || (t.sdesc_end - t.sdesc_begin > MAX_SINGLES_TERMS);
     }
     if (lambda && plain) throw Error("nwc_triples: a batch cannot mix (T) tuples and two-sided (Lambda) tuples");
     launch_fused((const TupleHdr*)(dm + o_t), nt, (const ContrDesc*)(dm + o_d), (const SinglesDesc*)(dm + o_s),
-                 (double2*)(dm + o_p), items_, ragged, order_, lambda, stream_);
+                 (double2*)(dm + o_p), items_, ragged, order_, lambda ? (crx ? 2 : 1) : 0, stream_);
   }
   NWC_CUDA(cudaGetLastError());
   if (timing) NWC_CUDA(cudaEventRecord(S.ev[5], stream_));

@@ -501,14 +501,17 @@ __device__ unsigned int g_phase_cap = 0;
 
 // RAGGED: the launch holds tuples whose tile ranges are not multiples of four; only that instantiation carries the
 // block-skipping K loops (their mere presence costs the aligned case ~3 %, so aligned launches use the plain kernel).
-// LAMBDA: the launch holds tuples with doubles-bound outer-product terms (Lambda-CCSD(T)); the plain (T) instantiations
-// do not carry that code (it costs registers in the epilogue).
-template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0, bool LAMBDA = false>
+// LAMBDA: the launch holds two-sided tuples with doubles-bound outer-product terms; the plain (T) instantiations do not
+// carry that code (it costs registers in the epilogue).  1 = Lambda-CCSD(T) (side-1-bound terms, <= 18 terms);
+// 2 = CR-CCSD(T) as well (side-0-bound terms, up to 32 terms, dual-energy tuples) -- a separate instantiation, so the
+// Lambda-CCSD(T) kernel is not slowed down by the CR code either (3 % when they shared one).
+template <bool DUMP, bool TIMING = false, bool RAGGED = true, int ORDER = 0, int LAMBDA = 0>
 __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     fused_kernel(const TupleHdr* __restrict__ tuples, int ntuples, const ContrDesc* __restrict__ descs,
                  const SinglesDesc* __restrict__ sdescs, double2* __restrict__ partials, double* __restrict__ dump_d,
                  double* __restrict__ dump_s) {
   unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr bool CRX = LAMBDA == 2;
   if (TIMING) tph[0] = clock64();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
@@ -581,11 +584,11 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int nsd = T.sdesc_end - T.sdesc_begin;
-    constexpr int SD_CAP = LAMBDA ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC;
+    constexpr int SD_CAP = CRX ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC;
     sm.nsd = nsd < SD_CAP ? nsd : SD_CAP;
     const int nmid = T.sdesc_mid - T.sdesc_begin;
     sm.nsd_mid = nmid < 0 ? 0 : (nmid < sm.nsd ? nmid : sm.nsd);
-    if (LAMBDA) {
+    if (CRX) {
       const int ts = T.two_sided;             // 1 + n0, negative for dual-energy tuples (kernels.cuh TupleHdr)
       const int n0 = (ts < 0 ? -ts : ts) - 1;
       lm.nsd_mid0 = n0 < 0 ? 0 : (n0 < sm.nsd_mid ? n0 : sm.nsd_mid);
@@ -632,10 +635,10 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     if (lane < 24) sm.eps[q][i] = __ldg(T.eps[q] + g);
   }
   if (warp == 2) {  // one lane per singles term: staged-layout multipliers, source strides and sub-tile origin
-    const int nsd_l = min(T.sdesc_end - T.sdesc_begin, LAMBDA ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC);
+    const int nsd_l = min(T.sdesc_end - T.sdesc_begin, CRX ? MAX_SDESC + MAX_SDESC2 : MAX_SDESC);
     const bool act = lane < nsd_l;
     const SinglesDesc* sd = act ? &sdescs[T.sdesc_begin + lane] : nullptr;
-    SinglesTerm& st = (LAMBDA && lane >= MAX_SDESC) ? lm.st2[lane - MAX_SDESC < MAX_SDESC2 ? lane - MAX_SDESC : 0]
+    SinglesTerm& st = (CRX && lane >= MAX_SDESC) ? lm.st2[lane - MAX_SDESC < MAX_SDESC2 ? lane - MAX_SDESC : 0]
                                                     : sm.st[lane < MAX_SDESC ? lane : 0];
     int mt = 0, mv = 0, edge = 0;
     int vbase = 0, tbase = 0;
@@ -797,9 +800,9 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   // (CR-CCSD(T): the denominator tile E = t2*t1 - 2/3 t1*(t1 t1), cr_ccsd_t_E.F:7-8), [nsd_mid0, nsd_mid) to the side-1 tile.
   bool staged_before = false;
 #pragma unroll 1
-  for (int grp = LAMBDA ? -1 : 1; grp < 2; grp++) {
+  for (int grp = CRX ? -1 : (LAMBDA ? 0 : 1); grp < 2; grp++) {
     int glo, ghi;
-    if (!LAMBDA) { glo = 0; ghi = nsd; }
+    if (!CRX) { glo = (!LAMBDA || grp == 0) ? 0 : sm.nsd_mid; ghi = (LAMBDA && grp == 0) ? sm.nsd_mid : nsd; }
     else if (grp < 0) { glo = 0; ghi = lm.dual ? 0 : lm.nsd_mid0; }   // dual tuples: these terms get their own pass below
     else if (grp == 0) { glo = lm.nsd_mid0; ghi = sm.nsd_mid; }
     else { glo = sm.nsd_mid; ghi = nsd; }
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
 #undef NWC_OT_GHI
     if (LAMBDA && grp < 1) {   // doubles-bound terms: fold them into this warp's quarter of their canonical tile, start the next group from 0
       const int Ad = canon_swz(lane | (wo0 << 5) | (wo1 << 11));
-      double* tile = grp < 0 ? lm.canon2 : sm.canon;
+      double* tile = (CRX && grp < 0) ? lm.canon2 : sm.canon;
 #pragma unroll
       for (int jj = 0; jj < 32; jj++) {
         tile[Ad ^ canon_swz(jj << 6)] += sing[jj];
@@ -887,7 +890,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   // one partial per warp: no CTA-wide rendezvous at the end, every warp leaves as soon as it is done
   // (reduce_chunk_kernel adds the four in a fixed order)
   if (lane == 0) partials[item * (NCONSUMERS / 32) + warp] = make_double2(e1, e2);
-  if (LAMBDA) {
+  if (CRX) {
     // Dual tuples (CR-CCSD(T) in one pass, cr_ccsd_t.F:176-207).  So far: canon2 = M, canon = D, sing = S and the two sums
     // above are num1 = <M,D>, num2 = <M,S+D>.  M is no longer needed: S takes its place in canon2, the outer-product
     // terms [0, nsd_mid0) -- the denominator tile E of cr_ccsd_t_E -- are accumulated in registers, and a second energy
@@ -952,7 +955,7 @@ void set_phase_timing(unsigned long long* d_buf, unsigned int cap_items) {
   g_phase_timing = d_buf != nullptr;
 }
 
-template <bool DUMP, bool TIMING, bool RAGGED, int ORDER, bool LAMBDA = false>
+template <bool DUMP, bool TIMING, bool RAGGED, int ORDER, int LAMBDA = 0>
 static void launch_one(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
                        double2* d_partials, long long total_items, double* dd, double* ds, cudaStream_t stream) {
   static bool attr_done = false;   // one flag per instantiation
@@ -969,11 +972,13 @@ static void launch_one(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d
 static_assert(NWC_CTAS_PER_SM * (sizeof(FusedSmem) + 1024) <= 228 * 1024, "FusedSmem too large for the intended CTAs/SM");
 // order: index order inside the panel blocks (tables.h make_split), the one the panels of this launch were built with
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, int order, bool lambda, cudaStream_t stream) {
+                  double2* d_partials, long long total_items, bool ragged, int order, int lambda, cudaStream_t stream) {
   if (total_items <= 0) return;
-  if (lambda) {   // the general (ragged-capable) kernel with the doubles-bound outer-product group
-    if (order) launch_one<false, false, true, 1, true>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream);
-    else launch_one<false, false, true, 0, true>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream);
+  if (lambda) {   // the general (ragged-capable) kernel with the doubles-bound outer-product groups: 1 Lambda-CCSD(T), 2 CR-CCSD(T)
+#define NWC_LL(O, M) launch_one<false, false, true, O, M>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream)
+    if (lambda == 2) { if (order) NWC_LL(1, 2); else NWC_LL(0, 2); }
+    else { if (order) NWC_LL(1, 1); else NWC_LL(0, 1); }
+#undef NWC_LL
     return;
   }
 #define NWC_L(D, T, R, O) launch_one<D, T, R, O>(d_tuples, ntuples, d_descs, d_sdescs, d_partials, total_items, nullptr, nullptr, stream)

@@ -98,8 +98,10 @@ void launch_synth_fill(const FillJob* d_jobs, int njobs, long long max_doubles, 
 void launch_repack(const RepackJob* d_jobs, int njobs, long long max_panel_doubles, cudaStream_t stream);
 // ragged: some tuple of the launch has a tile range that is not a multiple of four (selects the block-skipping kernel)
 // order: index order inside the panel blocks (tables.h make_split) the launch's panels were built with
+// lambda: 0 plain (T) tuples; 1 two-sided tuples of Lambda-CCSD(T); 2 two-sided tuples that need the CR-CCSD(T) code
+//         (side-0-bound outer products, more than MAX_SINGLES_TERMS terms, dual-energy tuples)
 void launch_fused(const TupleHdr* d_tuples, int ntuples, const ContrDesc* d_descs, const SinglesDesc* d_sdescs,
-                  double2* d_partials, long long total_items, bool ragged, int order, bool lambda, cudaStream_t stream);
+                  double2* d_partials, long long total_items, bool ragged, int order, int lambda, cudaStream_t stream);
 // two-level deterministic reduction; d_chunk_sums holds ntuples * max_chunks double2 (max_chunks >= the largest
 // reduce_chunks(nitems) of the launch)
 int reduce_chunks(long long nitems);
