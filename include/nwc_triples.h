@@ -296,19 +296,19 @@ int nwc_triples_run_lambda(nwc_triples_ctx *ctx, Integer first, Integer stride, 
 /* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_energy) */
 int nwc_triples_run_lambda_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task,
                                      Integer ntasks, double energy[2], double *per_task);
-/* CR-CCSD(T) (src/tce/ccsd_t/cr_ccsd_t.F, tce_energy.F `cr-ccsd(t)`): the tuple loop cr_ccsd_t.F:88-222.  Per tuple it
+/* CR-CCSD(T) (src/tce/ccsd_t/cr_ccsd_t.F, tce_energy.F `cr-ccsd(t)`): the tuple loop cr_ccsd_t.F:93-233.  Per tuple it
  * needs the (T) tiles S (ccsd_t_singles_l) and D (ccsd_t_doubles_l), the moment M (cr_ccsd_t_N_1/_N_2, cr_ccsd_t_N.F:296,
  * :3540 -- the doubles contractions with V2 replaced by dressed intermediates) and the denominator tile E
  * (cr_ccsd_t_E_1/_E_2, cr_ccsd_t_E.F:74,:408 -- outer products), and forms num1 = sum f M D/Delta, num2 = sum f M (S+D)/Delta,
  * den1 = sum f E D/Delta, den2 = sum f E (S+D)/Delta (:176-207).  set_cr uploads the three intermediates the loop reads
  * -- what cr_ccsd_t_N(...,toggle 1) / cr_ccsd_t_E(...,toggle 1) leave in d_i1_1, d_i1_2 and d_i1_3, or the files
- * gr1_1 / gr1_2 / ei1_2 of read_in3 (cr_ccsd_t_N.F:57-63) -- in the reference's block layout with their offset tables:
+ * gr1_1 / gr1_2 / ei1_2 of read_in3 (cr_ccsd_t_N.F:98-104) -- in the reference's block layout with their offset tables:
  *   n1: i1(h11 p4 h1 h2), blocks (p4b, h11b, h1b<=h2b), key h2b-1+noab*(h1b-1+noab*(h11b-1+noab*(p4b-noab-1)))      (cr_ccsd_t_N.F:773-841)
  *   n2: i1(p4 p5 h1 p12), blocks (p4b<=p5b, h1b, p12b), key p12b-noab-1+nvab*(h1b-1+noab*(p5b-noab-1+nvab*(p4b-noab-1))) (:4011-4079)
  *   e2: i1(p4 p5 h1 h2)_tt, the T2 block structure and key                                                       (cr_ccsd_t_E.F:907-960)
  * run_cr returns sums[4] = (num1, num2, den1, den2) over tasks first, first+stride, ... of the heaviest-first list,
- * per_task (optional) 4 doubles per task run.  The caller adds den0 (the scalar of cr_ccsd_t_D, cr_ccsd_t.F:67-70) after
- * the sum over ranks and forms CR-CCSD[T] = num1/(1+den1+den0), CR-CCSD(T) = num2/(1+den2+den0) (:253-258). */
+ * per_task (optional) 4 doubles per task run.  The caller adds den0 (the scalar of cr_ccsd_t_D, cr_ccsd_t.F:66-69) after
+ * the sum over ranks and forms CR-CCSD[T] = num1/(1+den1+den0), CR-CCSD(T) = num2/(1+den2+den0) (:260-263). */
 int nwc_triples_set_cr(nwc_triples_ctx *ctx, const Integer *n1_hash, const double *n1, const Integer *n2_hash,
                        const double *n2, const Integer *e2_hash, const double *e2);
 int nwc_triples_run_cr(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double sums[4],

@@ -342,7 +342,7 @@ class Triples:
             self._keep.append(k)
 
     def run_cr(self, first=0, stride=1, max_tasks=0, per_task=False):
-        """CR-CCSD(T) tuple loop (cr_ccsd_t.F:88-222): sums = (num1, num2, den1, den2) without den0 [, per_task[n,4]]."""
+        """CR-CCSD(T) tuple loop (cr_ccsd_t.F:93-233): sums = (num1, num2, den1, den2) without den0 [, per_task[n,4]]."""
         s = np.zeros(4)
         cnt = len(range(first, self.num_tasks, stride))
         if max_tasks and max_tasks > 0:
@@ -366,7 +366,7 @@ class Triples:
 
     @staticmethod
     def cr_energies(sums, den0):
-        """cr_ccsd_t.F:253-258: (CR-CCSD[T], CR-CCSD(T)) corrections from the four sums and the scalar of cr_ccsd_t_D."""
+        """cr_ccsd_t.F:260-263: (CR-CCSD[T], CR-CCSD(T)) corrections from the four sums and the scalar of cr_ccsd_t_D."""
         return float(sums[0] / (1.0 + sums[2] + den0)), float(sums[1] / (1.0 + sums[3] + den0))
 
     def tuple_items(self, tup) -> int:

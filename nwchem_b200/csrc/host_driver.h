@@ -220,8 +220,8 @@ inline int fired(const Integer t[6], const Row& r, const int TP[3][3], const int
 
 // t = (t_p4b,t_p5b,t_p6b,t_h1b,t_h2b,t_h3b)
 // row_target < 0: the (T) filter (irrep_v xor irrep_t).  cr_ccsd_t_E_2 (cr_ccsd_t_E.F:408-742) is this same walk -- same
-// rows :476-537, row filter :564, t1 filter :580-581, restricted maps :583-584, dispatch tests :608-680 -- with the row
-// target irrep_t^irrep_t^irrep_t (:575) and the <pp||hh> block replaced by the i1(pphh)_tt intermediate.
+// rows :472-533, row filter :560, t1 filter :579-580, restricted maps :582-583, dispatch tests :625-721 -- with the row
+// target irrep_t^irrep_t^irrep_t (:571) and the <pp||hh> block replaced by the i1(pphh)_tt intermediate.
 template <class Sink>
 void walk_singles(const HostState& S, const Integer t[6], Sink& sink, Integer row_target = -1) {
   static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};   // ccsd_t_singles_gpu.F:101-162
@@ -250,24 +250,24 @@ void walk_singles(const HostState& S, const Integer t[6], Sink& sink, Integer ro
 // block.  Reports (row, T2 block ids after tce_restricted_4, T1 block ids after tce_restricted_2, fired sd_E_K).
 template <class Sink>
 void walk_cr_e1(const HostState& S, const Integer t[6], Sink& sink) {
-  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};   // rows :142-203: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5)
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};   // rows :138-199: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5)
   static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};   //                (h1,h2,h3),(h2,h3,h1),(h1,h3,h2)
-  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :292,:325,:358
-  static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :292,:303,:314
+  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :290,:323,:356
+  static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}};  // tests :290,:301,:312
   Row rows[9];
   const int n = build_rows(t, P, H, rows);
   for (int i = 0; i < n; i++) {
     const Row& r = rows[i];
-    if (!(r.p4b <= r.p5b && r.h1b <= r.h2b)) continue;                                  // :230
-    if (!row_ok_target(S, r, S.irrep_t ^ S.irrep_t)) continue;                          // :233-241
-    if (S.sp(r.p4b) + S.sp(r.p5b) != S.sp(r.h1b) + S.sp(r.h2b)) continue;               // :248
-    if ((S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.h1b) ^ S.sy(r.h2b)) != S.irrep_t) continue; // :250
+    if (!(r.p4b <= r.p5b && r.h1b <= r.h2b)) continue;                                  // :226
+    if (!row_ok_target(S, r, S.irrep_t ^ S.irrep_t)) continue;                          // :229-237
+    if (S.sp(r.p4b) + S.sp(r.p5b) != S.sp(r.h1b) + S.sp(r.h2b)) continue;               // :244
+    if ((S.sy(r.p4b) ^ S.sy(r.p5b) ^ S.sy(r.h1b) ^ S.sy(r.h2b)) != S.irrep_t) continue; // :246
     bool fire[9];
     if (!fired(t, r, TP, TH, fire)) continue;
     const Integer a[4] = {r.p4b, r.p5b, r.h1b, r.h2b}, b[2] = {r.p6b, r.h3b};
     Integer am[4], bm[2];
-    restricted_map(S, 4, a, am);                                                        // :252
-    restricted_map(S, 2, b, bm);                                                        // :253
+    restricted_map(S, 4, a, am);                                                        // :248
+    restricted_map(S, 2, b, bm);                                                        // :249
     sink.cr_e1(r, am, bm, fire);
   }
 }

@@ -292,8 +292,8 @@ struct NativeSink {
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.stride[N_P5] = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
     if (cr == CR_DENOM) {
-      // cr_ccsd_t_E_2: i1(p5 p6 h2 h3)_tt block, same layout, key as a T2 block (cr_ccsd_t_E.F:604-607); sd_E2_K adds
-      // twot * t1sub * v2sub with twot = -2/3 * (sign of sd_t_s1_K) (:612-:680).  The store is resident pre-scaled by
+      // cr_ccsd_t_E_2: i1(p5 p6 h2 h3)_tt block, same layout, key as a T2 block (cr_ccsd_t_E.F:605-608); sd_E2_K adds
+      // twot * t1sub * v2sub with twot = -2/3 * (sign of sd_t_s1_K) (:629-:721).  The store is resident pre-scaled by
       // 2/3 (nwc_triples_set_cr), so only the sign is left.
       v.base = c->d_cre2 + hash_lookup_or_die(c->cre2_hash, t2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "cr e2(pphh)");
       for (int k = 0; k < 9; k++)
@@ -309,7 +309,7 @@ struct NativeSink {
       if (fire[k]) e.add_singles(k, t, v);
   }
 
-  // cr_ccsd_t_E_1 (cr_ccsd_t_E.F:265-281, kernels sd_E_K): t2sub(p4,p5,h1,h2) = the stored T2 block <p4 p5||h1 h2>
+  // cr_ccsd_t_E_1 (cr_ccsd_t_E.F:261-277, kernels sd_E_K): t2sub(p4,p5,h1,h2) = the stored T2 block <p4 p5||h1 h2>
   // (h2 fastest; the reference's TCE_SORT_4(4,3,2,1) only reverses the index order), t1sub(p6,h3) = the stored T1 block
   void cr_e1(const Row& r, const Integer am[4], const Integer bm[2], const bool fire[9]) {
     OperandView a, b;
@@ -343,7 +343,7 @@ struct NativeSink {
     }
     if (cr == CR_MOMENT) {
       // i1(h7 p6 h2 h3) of cr_ccsd_t_N_1, stored (p6,h7,h2,h3), h3 fastest == v2sub(h3,h2,h7,p6) of sd_t_cr1_K; key
-      // h3-1 + noab*(h2-1 + noab*(h7-1 + noab*(p6-noab-1))) (cr_ccsd_t_N.F:510-513)
+      // h3-1 + noab*(h2-1 + noab*(h7-1 + noab*(p6-noab-1))) (cr_ccsd_t_N.F:509-512)
       const Integer key = bm[3] - 1 + S.noab * (bm[2] - 1 + S.noab * (bm[1] - 1 + S.noab * (bm[0] - S.noab - 1)));
       v.base = c->d_crn1 + hash_lookup_or_die(c->crn1_hash, key, "cr n1(phhh)");
       v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.kstride = S.rg(r.h3b) * S.rg(r.h2b);
@@ -373,7 +373,7 @@ struct NativeSink {
       sign = 1.0;
     }
     // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161); CR-CCSD(T): i1(p5 p6 h3 p7)
-    // of cr_ccsd_t_N_2, same layout, key p7-noab-1 + nvab*(h3-1 + noab*(p6-noab-1 + nvab*(p5-noab-1))) (cr_ccsd_t_N.F:3754-3757)
+    // of cr_ccsd_t_N_2, same layout, key p7-noab-1 + nvab*(h3-1 + noab*(p6-noab-1 + nvab*(p5-noab-1))) (cr_ccsd_t_N.F:3753-3756)
     if (cr == CR_MOMENT)
       v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, bm[3] - S.noab - 1 + S.nvab * (bm[2] - 1 + S.noab * (bm[1] - S.noab - 1 + S.nvab * (bm[0] - S.noab - 1))), "cr n2(pphp)");
     else
@@ -456,7 +456,7 @@ void emit_tuple_lambda(nwc_triples_ctx* c, const Integer t[6], long long item_lo
   c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);
 }
 
-// CR-CCSD(T) (cr_ccsd_t.F:127-207): per tuple four t3-sized tiles -- S, D of (T), the moment M and the denominator
+// CR-CCSD(T) (cr_ccsd_t.F:125-207): per tuple four t3-sized tiles -- S, D of (T), the moment M and the denominator
 // tile E -- and four sums  num1 = <M,D>, num2 = <M,S+D>, den1 = <E,D>, den2 = <E,S+D>,  <A,B> = sum f A B / Delta.
 // Two two-sided tuples through the LAMBDA instantiation of the fused kernel (energy = (<T0,T1>, <T0,T1+Ts>)):
 //   pass 0 (numerators):   side 0 = M (contractions with the dressed intermediates), side 1 = D, singles tile = S
@@ -1121,7 +1121,7 @@ int nwc_triples_run_lambda_partition(nwc_triples_ctx* c, Integer rank, Integer n
 //   n2 = d_i1_2 of cr_ccsd_t_N: i1(p4 p5 h1 p12), blocks (p4b<=p5b,h1b,p12b), OFFSET_cr_ccsd_t_N_2_1 (:4011)
 //   e2 = d_i1_2 of cr_ccsd_t_E: i1(p4 p5 h1 h2)_tt, the T2 block structure,   OFFSET_cr_ccsd_t_E_2_1 (cr_ccsd_t_E.F:907)
 // i.e. what cr_ccsd_t_N(...,1) / cr_ccsd_t_E(...,1) leave in GA, or the files gr1_1 / gr1_2 / ei1_2 of read_in3
-// (cr_ccsd_t_N.F:57-63).  Replicated in HBM.  Call after a set_state* variant.
+// (cr_ccsd_t_N.F:98-104).  Replicated in HBM.  Call after a set_state* variant.
 int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash, const double* n2,
                        const Integer* e2_hash, const double* e2) {
   return guarded(c, [&]() {
@@ -1155,7 +1155,7 @@ int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double*
     c->cre2_hash.assign(e2_hash, e2_hash + 2 * e2_hash[0] + 1);
     if (upload(&c->d_crn1, &c->n_crn1, n1, total_of(n1_hash, 1), c->eng)) return 1;
     if (upload(&c->d_crn2, &c->n_crn2, n2, total_of(n2_hash, 2), c->eng)) return 1;
-    // sd_E2_K multiplies by +-2/3 (cr_ccsd_t_E.F:612-680): the factor is folded into the resident copy once
+    // sd_E2_K multiplies by +-2/3 (cr_ccsd_t_E.F:629-721): the factor is folded into the resident copy once
     const size_t ne = total_of(e2_hash, 3);
     std::vector<double>& scaled = c->cre2_scaled;
     scaled.assign(e2 ? ne : 0, 0.0);
@@ -1167,7 +1167,7 @@ int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double*
 }
 
 // CR-CCSD(T) sums of tasks `ids` (cr_ccsd_t.F:176-207): sums[4] = (num1, num2, den1, den2) WITHOUT den0; the caller adds
-// the scalar of cr_ccsd_t_D and forms  E[T] = num1/(1+den1+den0),  E(T) = num2/(1+den2+den0)  (:253-258) after the sum over
+// the scalar of cr_ccsd_t_D and forms  E[T] = num1/(1+den1+den0),  E(T) = num2/(1+den2+den0)  (:260-263) after the sum over
 // ranks (nwc_triples_allreduce_sum with n = 4).  per_task (optional): 4 doubles per task.
 static int run_cr_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const std::vector<long long>* ranges,
                       double sums[4], double* per_task) {

@@ -1,9 +1,9 @@
 """CR-CCSD(T) intermediates and an untiled reference of the whole correction -- TEST INFRASTRUCTURE ONLY.
 
-The per-tuple half of CR-CCSD(T) (cr_ccsd_t.F:88-222: cr_ccsd_t_N_1 / _N_2 / _E_1 / _E_2 and the four energy sums) is
+The per-tuple half of CR-CCSD(T) (cr_ccsd_t.F:93-233: cr_ccsd_t_N_1 / _N_2 / _E_1 / _E_2 and the four energy sums) is
 restated line by line in triples_oracle.c.  Its inputs are three intermediate block stores the reference builds once,
 before the tuple loop, with ~25 TCE-generated block contraction routines (cr_ccsd_t_N.F:665-6200 with toggle 1,
-cr_ccsd_t_E.F:743-905) -- or loads from files (read_in3: gr1_1, gr1_2, ei1_2; cr_ccsd_t_N.F:57-63).  Those routines are
+cr_ccsd_t_E.F:743-905) -- or loads from files (read_in3: gr1_1, gr1_2, ei1_2; cr_ccsd_t_N.F:98-104).  Those routines are
 upstream of the hot path (SURVEY 8 f4 territory); here the tensors they produce are evaluated DENSELY in the spin-orbital
 basis straight from the tensor-contraction expressions the TCE printed at the top of each file (the specification the
 generated Fortran implements; cited per term below), and packed into the reference's block layouts
@@ -123,7 +123,7 @@ class Dense:
         x = np.einsum("ai,bj->abij", self.t1, self.t1)
         return -0.25 * (x - x.transpose(1, 0, 2, 3) - x.transpose(0, 1, 3, 2) + x.transpose(1, 0, 3, 2))
 
-    # ---- cr_ccsd_t_D.F:6-9 with c = t (cr_ccsd_t.F:67-68) ----
+    # ---- cr_ccsd_t_D.F:6-9 with c = t (cr_ccsd_t.F:66-67) ----
     def den0(self):
         t1, t2 = self.t1, self.t2
         i1 = t1.T + 0.5 * np.einsum("cami,cm->ia", t2, t1)       # i1(h6 p5) = c+(h6 p5) + 1/2 Sum(h4 p3) c+(h4 h6 p3 p5) t(p3 h4)
@@ -187,7 +187,7 @@ class Dense:
         a1 = np.zeros(s1); a2 = np.zeros(s2); a3 = np.zeros(s3)
         for key, off in synth._iter_hash(h1):
             p4b, h11b, h1b, h2b = tl.decode_cr_n1_key(t, key)
-            # stored (p4, h11, h1, h2), h2 fastest (the two TCE_SORT_4 of cr_ccsd_t_N_1_1, cr_ccsd_t_N.F:745-754)
+            # stored (p4, h11, h1, h2), h2 fastest (the two TCE_SORT_4 of cr_ccsd_t_N_1_1, cr_ccsd_t_N.F:740-750)
             blk = n1d[np.ix_(self._hidx(h11b), self._pidx(p4b), self._hidx(h1b), self._hidx(h2b))].transpose(1, 0, 2, 3)
             a1[off:off + blk.size] = blk.ravel()
         for key, off in synth._iter_hash(h2):
@@ -215,5 +215,5 @@ class Dense:
 
 
 def cr_energies(num1, num2, den1, den2, den0):
-    """cr_ccsd_t.F:255-258."""
+    """cr_ccsd_t.F:260-263."""
     return num1 / (1.0 + den1 + den0), num2 / (1.0 + den2 + den0)

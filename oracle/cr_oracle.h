@@ -1,14 +1,14 @@
 /*
  * oracle/cr_oracle.h -- TEST INFRASTRUCTURE ONLY (included at the end of triples_oracle.c).
  *
- * CR-CCSD(T), the per-tuple half: src/tce/ccsd_t/cr_ccsd_t.F:88-258 with
+ * CR-CCSD(T), the per-tuple half: src/tce/ccsd_t/cr_ccsd_t.F:93-263 with
  *   cr_ccsd_t_N_1 (cr_ccsd_t_N.F:296-664)   M += -P(9) Sum(h11) t(p4 p5 h1 h11) i1(h11 p6 h2 h3)   kernels sd_t_cr1_K  :6207-6457
  *   cr_ccsd_t_N_2 (cr_ccsd_t_N.F:3540-3902) M += -P(9) Sum(p12) t(p4 p12 h1 h2) i1(p5 p6 h3 p12)   kernels sd_t_d2cp_K :6464-6717
  *   cr_ccsd_t_E_1 (cr_ccsd_t_E.F:74-407)    E += P(9) t(p4 p5 h1 h2) t(p6 h3)                      kernels sd_E_K      :982-1204
  *   cr_ccsd_t_E_2 (cr_ccsd_t_E.F:408-742)   E += -2/3 P(9) t(p4 h1) i1(p5 p6 h2 h3)                kernels sd_E2_K     :1209-1441
  * and the (T) tiles S = ccsd_t_singles_l, D = ccsd_t_doubles_l (cr_ccsd_t.F:139-144) restated in triples_oracle.c.
  * The three intermediates (d_i1_1, d_i1_2 of cr_ccsd_t_N, d_i1_2 of cr_ccsd_t_E) are INPUTS here, as they are for the
- * reference's tuple loop (built once with toggle 1 or read from files, cr_ccsd_t_N.F:57-63); tests obtain them from
+ * reference's tuple loop (built once with toggle 1 or read from files, cr_ccsd_t_N.F:98-104); tests obtain them from
  * oracle/cr_dense.py.
  *
  * PARITY PIN STATUS: no QA test of the reference exercises cr-ccsd(t) at the tile level and the Fortran cannot be built
@@ -153,42 +153,42 @@ void ora_cr_ccsd_t_N_1(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer 
                        Integer t_h1b, Integer t_h2b, Integer t_h3b) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   const Integer noab = c->noab, nvab = c->nvab;
-  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :364-425: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :363-424: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
   static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (h1,h2,h3),(h2,h1,h3),(h3,h1,h2) */
-  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* tests :531,:564,:597: ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
+  static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* tests :529,:565,:601: ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
   static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==h1,h2,h3; ==h2,h1,h3; ==h2,h3,h1 */
   Integer a3[9][6];
   cr_rows(a3, tp, th, P, H);
-  for (int ia6 = 0; ia6 < 9; ia6++) { /* :445 */
+  for (int ia6 = 0; ia6 < 9; ia6++) { /* :444 */
     const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
-    if (!(p4b <= p5b && h2b <= h3b && p4b != 0)) continue;            /* :452 */
-    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :455-463 */
+    if (!(p4b <= p5b && h2b <= h3b && p4b != 0)) continue;            /* :451 */
+    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :454-462 */
     const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
-    for (Integer h7b = 1; h7b <= noab; h7b++) {                        /* :470 (h11b) */
-      if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h7b)) continue;   /* :471 */
-      if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h7b)) != c->irrep_t) continue; /* :473 */
+    for (Integer h7b = 1; h7b <= noab; h7b++) {                        /* :469 (h11b) */
+      if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h7b)) continue;   /* :470 */
+      if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h7b)) != c->irrep_t) continue; /* :472 */
       Integer p4b_1, p5b_1, h1b_1, h7b_1, p6b_2, h7b_2, h2b_2, h3b_2;
-      restricted_4(c, p4b, p5b, h1b, h7b, &p4b_1, &p5b_1, &h1b_1, &h7b_1); /* :475 */
-      restricted_4(c, p6b, h7b, h2b, h3b, &p6b_2, &h7b_2, &h2b_2, &h3b_2); /* :476 */
+      restricted_4(c, p4b, p5b, h1b, h7b, &p4b_1, &p5b_1, &h1b_1, &h7b_1); /* :474 */
+      restricted_4(c, p6b, h7b, h2b, h3b, &p6b_2, &h7b_2, &h2b_2, &h3b_2); /* :475 */
       const Integer dim_common = RANGE(h7b);
       const Integer dima = dim_common * RANGE(p4b) * RANGE(p5b) * RANGE(h1b);
       const Integer dimb = dim_common * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
       if (!(dima > 0 && dimb > 0)) continue;
       double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
       double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
-      if (h7b < h1b) { /* :489-495 */
+      if (h7b < h1b) { /* :488-494 */
         get_hash_block(c->t2, k_a, dima, c->t2_hash, h1b_1 - 1 + noab * (h7b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
         ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h7b), RANGE(h1b), 4, 2, 1, 3, -1.0);
       }
-      if (h1b <= h7b) { /* :497-503 */
+      if (h1b <= h7b) { /* :496-502 */
         get_hash_block(c->t2, k_a, dima, c->t2_hash, h7b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
         ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h7b), 3, 2, 1, 4, 1.0);
       }
-      /* the intermediate block as stored, no sort (:510-513) */
+      /* the intermediate block as stored, no sort (:509-512) */
       get_hash_block(cr->n1, k_b_sort, dimb, cr->n1_hash, h3b_2 - 1 + noab * (h2b_2 - 1 + noab * (h7b_2 - 1 + noab * (p6b_2 - noab - 1))));
       for (int kp = 0; kp < 3; kp++)
         for (int kh = 0; kh < 3; kh++)
-          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :531-:640 */
+          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :529-:631 */
             CR1[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(h7b), a_c, k_a_sort, k_b_sort);
       free(k_a); free(k_a_sort); free(k_b_sort);
     }
@@ -200,7 +200,7 @@ void ora_cr_ccsd_t_N_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer 
                        Integer t_h1b, Integer t_h2b, Integer t_h3b) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   const Integer noab = c->noab, nvab = c->nvab;
-  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :3608-3669: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :3607-3668: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
   static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (h1,h2,h3),(h2,h3,h1),(h1,h3,h2) */
   static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==p4,p5,p6; ==p5,p4,p6; ==p5,p6,p4 */
   static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==h1,h2,h3; ==h3,h1,h2; ==h1,h3,h2 */
@@ -208,34 +208,34 @@ void ora_cr_ccsd_t_N_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer 
   cr_rows(a3, tp, th, P, H);
   for (int ia6 = 0; ia6 < 9; ia6++) {
     const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
-    if (!(p5b <= p6b && h1b <= h2b && p4b != 0)) continue;            /* :3696 */
-    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :3699-3707 */
+    if (!(p5b <= p6b && h1b <= h2b && p4b != 0)) continue;            /* :3695 */
+    if (!row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b)) continue;      /* :3698-3706 */
     const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
-    for (Integer p7b = noab + 1; p7b <= noab + nvab; p7b++) {          /* :3714 (p12b) */
+    for (Integer p7b = noab + 1; p7b <= noab + nvab; p7b++) {          /* :3713 (p12b) */
       if (SPIN(p4b) + SPIN(p7b) != SPIN(h1b) + SPIN(h2b)) continue;
       if ((SYM(p4b) ^ SYM(p7b) ^ SYM(h1b) ^ SYM(h2b)) != c->irrep_t) continue;
       Integer p4b_1, p7b_1, h1b_1, h2b_1, p5b_2, p6b_2, h3b_2, p7b_2;
-      restricted_4(c, p4b, p7b, h1b, h2b, &p4b_1, &p7b_1, &h1b_1, &h2b_1); /* :3719 */
-      restricted_4(c, p5b, p6b, h3b, p7b, &p5b_2, &p6b_2, &h3b_2, &p7b_2); /* :3720 */
+      restricted_4(c, p4b, p7b, h1b, h2b, &p4b_1, &p7b_1, &h1b_1, &h2b_1); /* :3718 */
+      restricted_4(c, p5b, p6b, h3b, p7b, &p5b_2, &p6b_2, &h3b_2, &p7b_2); /* :3719 */
       const Integer dim_common = RANGE(p7b);
       const Integer dima = dim_common * RANGE(p4b) * RANGE(h1b) * RANGE(h2b);
       const Integer dimb = dim_common * RANGE(p5b) * RANGE(p6b) * RANGE(h3b);
       if (!(dima > 0 && dimb > 0)) continue;
       double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
       double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
-      if (p7b < p4b) { /* :3733-3739 */
+      if (p7b < p4b) { /* :3732-3738 */
         get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p4b_1 - noab - 1 + nvab * (p7b_1 - noab - 1))));
         ora_tce_sort_4(k_a, k_a_sort, RANGE(p7b), RANGE(p4b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, -1.0);
       }
-      if (p4b <= p7b) { /* :3741-3747 */
+      if (p4b <= p7b) { /* :3740-3746 */
         get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p7b_1 - noab - 1 + nvab * (p4b_1 - noab - 1))));
         ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p7b), RANGE(h1b), RANGE(h2b), 4, 3, 1, 2, 1.0);
       }
-      /* :3754-3757: the intermediate block as stored */
+      /* :3753-3756: the intermediate block as stored */
       get_hash_block(cr->n2, k_b_sort, dimb, cr->n2_hash, p7b_2 - noab - 1 + nvab * (h3b_2 - 1 + noab * (p6b_2 - noab - 1 + nvab * (p5b_2 - noab - 1))));
       for (int kp = 0; kp < 3; kp++)
         for (int kh = 0; kh < 3; kh++)
-          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :3775-:3880 */
+          if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :3773-:3875 */
             D2CP[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), RANGE(p7b), a_c, k_a_sort, k_b_sort);
       free(k_a); free(k_a_sort); free(k_b_sort);
     }
@@ -255,7 +255,7 @@ void ora_cr_ccsd_t_E_1(const ora_ctx *c, double *a_c, Integer t_p4b, Integer t_p
                        Integer t_h2b, Integer t_h3b) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   const Integer noab = c->noab, nvab = c->nvab;
-  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :142-203: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
+  static const int P[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* a3 rows :138-199: (p4,p5,p6),(p5,p6,p4),(p4,p6,p5) */
   static const int H[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}}; /* (h1,h2,h3),(h2,h3,h1),(h1,h3,h2) */
   static const int TP[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==p4,p5,p6; ==p6,p4,p5; ==p4,p6,p5 */
   static const int TH[3][3] = {{0, 1, 2}, {2, 0, 1}, {0, 2, 1}}; /* ==h1,h2,h3; ==h3,h1,h2; ==h1,h3,h2 */
@@ -263,25 +263,25 @@ void ora_cr_ccsd_t_E_1(const ora_ctx *c, double *a_c, Integer t_p4b, Integer t_p
   cr_rows(a3, tp, th, P, H);
   for (int ia6 = 0; ia6 < 9; ia6++) {
     const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
-    if (!(p4b <= p5b && h1b <= h2b && p4b != 0)) continue;                                    /* :230 */
-    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t)) continue;  /* :233-241 */
-    if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h2b)) continue;                             /* :248 */
-    if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h2b)) != c->irrep_t) continue;                  /* :250 */
+    if (!(p4b <= p5b && h1b <= h2b && p4b != 0)) continue;                                    /* :226 */
+    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t)) continue;  /* :229-237 */
+    if (SPIN(p4b) + SPIN(p5b) != SPIN(h1b) + SPIN(h2b)) continue;                             /* :244 */
+    if ((SYM(p4b) ^ SYM(p5b) ^ SYM(h1b) ^ SYM(h2b)) != c->irrep_t) continue;                  /* :246 */
     Integer p4b_1, p5b_1, h1b_1, h2b_1, p6b_2, h3b_2;
-    restricted_4(c, p4b, p5b, h1b, h2b, &p4b_1, &p5b_1, &h1b_1, &h2b_1);                      /* :252 */
-    restricted_2(c, p6b, h3b, &p6b_2, &h3b_2);                                                /* :253 */
+    restricted_4(c, p4b, p5b, h1b, h2b, &p4b_1, &p5b_1, &h1b_1, &h2b_1);                      /* :248 */
+    restricted_2(c, p6b, h3b, &p6b_2, &h3b_2);                                                /* :249 */
     const Integer dima = RANGE(p4b) * RANGE(p5b) * RANGE(h1b) * RANGE(h2b), dimb = RANGE(p6b) * RANGE(h3b);
     if (!(dima > 0 && dimb > 0)) continue;
     double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
     double *k_b = (double *)malloc(sizeof(double) * dimb), *k_b_sort = (double *)malloc(sizeof(double) * dimb);
-    get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1)))); /* :265 */
-    ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, 1.0); /* :268 */
-    get_hash_block(c->t1, k_b, dimb, c->t1_hash, h3b_2 - 1 + noab * (p6b_2 - noab - 1));      /* :276 (GET_HASH_BLOCK_MA) */
-    ora_tce_sort_2(k_b, k_b_sort, RANGE(p6b), RANGE(h3b), 2, 1, 1.0);                         /* :279 */
+    get_hash_block(c->t2, k_a, dima, c->t2_hash, h2b_1 - 1 + noab * (h1b_1 - 1 + noab * (p5b_1 - noab - 1 + nvab * (p4b_1 - noab - 1)))); /* :261 */
+    ora_tce_sort_4(k_a, k_a_sort, RANGE(p4b), RANGE(p5b), RANGE(h1b), RANGE(h2b), 4, 3, 2, 1, 1.0); /* :264 */
+    get_hash_block(c->t1, k_b, dimb, c->t1_hash, h3b_2 - 1 + noab * (p6b_2 - noab - 1));      /* :272 (GET_HASH_BLOCK_MA) */
+    ora_tce_sort_2(k_b, k_b_sort, RANGE(p6b), RANGE(h3b), 2, 1, 1.0);                         /* :275 */
     const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
     for (int kp = 0; kp < 3; kp++)
       for (int kh = 0; kh < 3; kh++)
-        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :292-:388 */
+        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :290-:382 */
           E1K[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort);
     free(k_a); free(k_a_sort); free(k_b); free(k_b_sort);
   }
@@ -292,7 +292,7 @@ void ora_cr_ccsd_t_E_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer 
                        Integer t_h1b, Integer t_h2b, Integer t_h3b) {
   const Integer tp[3] = {t_p4b, t_p5b, t_p6b}, th[3] = {t_h1b, t_h2b, t_h3b};
   const Integer noab = c->noab, nvab = c->nvab;
-  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :476-537: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
+  static const int P[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* a3 rows :472-533: (p4,p5,p6),(p5,p4,p6),(p6,p4,p5) */
   static const int H[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}}; /* (h1,h2,h3),(h2,h1,h3),(h3,h1,h2) */
   static const int TP[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==p4,p5,p6; ==p5,p4,p6; ==p5,p6,p4 */
   static const int TH[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; /* ==h1,h2,h3; ==h2,h1,h3; ==h2,h3,h1 */
@@ -301,41 +301,41 @@ void ora_cr_ccsd_t_E_2(const ora_ctx *c, const ora_cr *cr, double *a_c, Integer 
   cr_rows(a3, tp, th, P, H);
   for (int ia6 = 0; ia6 < 9; ia6++) {
     const Integer p4b = a3[ia6][0], p5b = a3[ia6][1], p6b = a3[ia6][2], h1b = a3[ia6][3], h2b = a3[ia6][4], h3b = a3[ia6][5];
-    if (!(p5b <= p6b && h2b <= h3b && p4b != 0)) continue;                                            /* :564 */
-    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t ^ c->irrep_t)) continue; /* :567-576 */
-    if (SPIN(p4b) != SPIN(h1b)) continue;                                                             /* :580 */
-    if ((SYM(p4b) ^ SYM(h1b)) != c->irrep_t) continue;                                                /* :581 */
+    if (!(p5b <= p6b && h2b <= h3b && p4b != 0)) continue;                                            /* :560 */
+    if (!cr_row_allowed(c, p4b, p5b, p6b, h1b, h2b, h3b, c->irrep_t ^ c->irrep_t ^ c->irrep_t)) continue; /* :563-572 */
+    if (SPIN(p4b) != SPIN(h1b)) continue;                                                             /* :579 */
+    if ((SYM(p4b) ^ SYM(h1b)) != c->irrep_t) continue;                                                /* :580 */
     Integer p4b_1, h1b_1, p5b_2, p6b_2, h2b_2, h3b_2;
-    restricted_2(c, p4b, h1b, &p4b_1, &h1b_1);                                                        /* :583 */
-    restricted_4(c, p5b, p6b, h2b, h3b, &p5b_2, &p6b_2, &h2b_2, &h3b_2);                              /* :584 */
+    restricted_2(c, p4b, h1b, &p4b_1, &h1b_1);                                                        /* :582 */
+    restricted_4(c, p5b, p6b, h2b, h3b, &p5b_2, &p6b_2, &h2b_2, &h3b_2);                              /* :583 */
     const Integer dima = RANGE(p4b) * RANGE(h1b), dimb = RANGE(p5b) * RANGE(p6b) * RANGE(h2b) * RANGE(h3b);
     if (!(dima > 0 && dimb > 0)) continue;
     double *k_a = (double *)malloc(sizeof(double) * dima), *k_a_sort = (double *)malloc(sizeof(double) * dima);
     double *k_b_sort = (double *)malloc(sizeof(double) * dimb);
-    get_hash_block(c->t1, k_a, dima, c->t1_hash, h1b_1 - 1 + noab * (p4b_1 - noab - 1));             /* :596 */
-    ora_tce_sort_2(k_a, k_a_sort, RANGE(p4b), RANGE(h1b), 2, 1, 1.0);                                 /* :599 */
-    get_hash_block(cr->e2, k_b_sort, dimb, cr->e2_hash, h3b_2 - 1 + noab * (h2b_2 - 1 + noab * (p6b_2 - noab - 1 + nvab * (p5b_2 - noab - 1)))); /* :604 */
+    get_hash_block(c->t1, k_a, dima, c->t1_hash, h1b_1 - 1 + noab * (p4b_1 - noab - 1));             /* :595 */
+    ora_tce_sort_2(k_a, k_a_sort, RANGE(p4b), RANGE(h1b), 2, 1, 1.0);                                 /* :598 */
+    get_hash_block(cr->e2, k_b_sort, dimb, cr->e2_hash, h3b_2 - 1 + noab * (h2b_2 - 1 + noab * (p6b_2 - noab - 1 + nvab * (p5b_2 - noab - 1)))); /* :605 */
     const Integer rp[3] = {p4b, p5b, p6b}, rh[3] = {h1b, h2b, h3b};
     for (int kp = 0; kp < 3; kp++)
       for (int kh = 0; kh < 3; kh++)
-        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :608-:680; twot alternates -2/3, +2/3 */
+        if (cr_test(tp, th, rp, rh, TP[kp], TH[kh])) /* :625-:721; twot alternates -2/3, +2/3 */
           E2K[kp * 3 + kh](RANGE(h3b), RANGE(h2b), RANGE(h1b), RANGE(p6b), RANGE(p5b), RANGE(p4b), a_c, k_a_sort, k_b_sort, TWOT[kp * 3 + kh]);
     free(k_a); free(k_a_sort); free(k_b_sort);
   }
 }
 
-/* One tuple of cr_ccsd_t.F:88-222.  tuple = (p4b,p5b,p6b,h1b,h2b,h3b); sums[4] += (num1, num2, den1, den2).
+/* One tuple of cr_ccsd_t.F:93-233.  tuple = (p4b,p5b,p6b,h1b,h2b,h3b); sums[4] += (num1, num2, den1, den2).
  * Optional outputs (prod(ranges) doubles each, indexed [p4,p5,p6,h1,h2,h3]): the `moment 2,3` tile and the `denominator` tile. */
 void ora_cr_ccsd_t_tuple(const ora_ctx *c, const ora_cr *cr, const Integer *tuple, double *sums, double *right_out, double *den_out) {
   const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2], t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
   const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
   const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
   double *k_singles = (double *)calloc(size + 1, sizeof(double)), *k_doubles = (double *)calloc(size + 1, sizeof(double));
-  double *k_right = (double *)calloc(size + 1, sizeof(double)), *k_den = (double *)calloc(size + 1, sizeof(double)); /* :127-138 */
+  double *k_right = (double *)calloc(size + 1, sizeof(double)), *k_den = (double *)calloc(size + 1, sizeof(double)); /* :125-138 */
   ora_ccsd_t_singles_l(c, k_singles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL); /* :139 */
   ora_ccsd_t_doubles_l(c, k_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL); /* :142 */
-  ora_cr_ccsd_t_N_1(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /* :145 (toggle 2, cr_ccsd_t_N.F:176) */
-  ora_cr_ccsd_t_N_2(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /*      (cr_ccsd_t_N.F:293) */
+  ora_cr_ccsd_t_N_1(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /* :145 (toggle 2, cr_ccsd_t_N.F:206) */
+  ora_cr_ccsd_t_N_2(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);           /*      (cr_ccsd_t_N.F:292) */
   ora_cr_ccsd_t_E_1(c, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);                 /* :150 (cr_ccsd_t_E.F:41) */
   ora_cr_ccsd_t_E_2(c, cr, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);             /*      (cr_ccsd_t_E.F:70) */
   const double factor = ora_ccsd_t_factor((int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* :153-167 */
@@ -362,8 +362,8 @@ void ora_cr_ccsd_t_tuple(const ora_ctx *c, const ora_cr *cr, const Integer *tupl
   free(k_singles); free(k_doubles); free(k_right); free(k_den);
 }
 
-/* cr_ccsd_t: all tuples in the loop order of cr_ccsd_t.F:95-100 (nxtask and the ga_acc sums are identity on one rank);
- * sums[4] = (num1, num2, den1, den2) WITHOUT den0 (:253-254 add it); per_task (optional) 4 doubles per tuple */
+/* cr_ccsd_t: all tuples in the loop order of cr_ccsd_t.F:93-98 (nxtask and the ga_acc sums are identity on one rank);
+ * sums[4] = (num1, num2, den1, den2) WITHOUT den0 (:260-261 add it); per_task (optional) 4 doubles per tuple */
 Integer ora_cr_ccsd_t(const ora_ctx *c, const ora_cr *cr, double *sums, double *per_task) {
   Integer count = 0;
   sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
@@ -374,7 +374,7 @@ Integer ora_cr_ccsd_t(const ora_ctx *c, const ora_cr *cr, double *sums, double *
         for (Integer h1 = 1; h1 <= n0; h1++)
           for (Integer h2 = h1; h2 <= n0; h2++)
             for (Integer h3 = h2; h3 <= n0; h3++) {
-              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue; /* :102-121 */
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue; /* :100-119 */
               const Integer t[6] = {p4, p5, p6, h1, h2, h3};
               double s[4] = {0.0, 0.0, 0.0, 0.0};
               ora_cr_ccsd_t_tuple(c, cr, t, s, NULL, NULL);

@@ -317,9 +317,9 @@ def make_cr(cr):
 
 
 def cr_ccsd_t(st, cr):
-    """CR-CCSD(T) tuple loop on the CPU (cr_ccsd_t.F:88-258 restated, cr_oracle.h).  `cr` = cr_dense.CRStores (the three
+    """CR-CCSD(T) tuple loop on the CPU (cr_ccsd_t.F:93-263 restated, cr_oracle.h).  `cr` = cr_dense.CRStores (the three
     intermediates + den0).  Returns dict(sums = (num1,num2,den1,den2) without den0, per_task[n,4] in the loop order of
-    cr_ccsd_t.F:95-100, tasks[n,6], e1, e2 = the CR-CCSD[T] / CR-CCSD(T) corrections :257-258)."""
+    cr_ccsd_t.F:93-98, tasks[n,6], e1, e2 = the CR-CCSD[T] / CR-CCSD(T) corrections :262-263)."""
     l = lib()
     c, keep = make_ctx(st)
     y, keep2 = make_cr(cr)
