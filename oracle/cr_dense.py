@@ -214,6 +214,109 @@ class Dense:
         return fh, f1
 
 
+@dataclasses.dataclass
+class CREOMStores:
+    """Inputs of the CR-EOMCCSD(T) tuple loop beyond the ground-state ones (cr_eomccsd_t.F:262-288 builds them with toggle 1):
+    the right-hand amplitudes x1 / x2, the four intermediates of creomsd_t_n2_mem, the one of q3rexpt2, r0 and the
+    excitation energy."""
+    x1_hash: np.ndarray; x1: np.ndarray
+    x2_hash: np.ndarray; x2: np.ndarray
+    m1_hash: np.ndarray; m1: np.ndarray     # d_i2_1  i1(h12 p4 h1 h2)
+    m2_hash: np.ndarray; m2: np.ndarray     # d_i2_2  i1(p4 p5 h1 p12)
+    m3_hash: np.ndarray; m3: np.ndarray     # d_i2_3  i1(h12 p4 h1 h2)
+    m4_hash: np.ndarray; m4: np.ndarray     # d_i2_4  i1(p4 p5 h1 p10)
+    q2_hash: np.ndarray; q2: np.ndarray     # d_i3_1  i1(p4 p5 h1 h2)_xt
+    r0: float
+    excit: float
+
+
+class DenseEOM:
+    """Synthetic inputs of the CR-EOMCCSD(T) tuple loop with the right index structure, and the untiled evaluation of the
+    loop's four sums.  The EOM intermediates (creomccsd_t_n2_mem.F:9-90, ~80 TCE equations in f, v, t, x) are upstream of
+    the hot path and are NOT restated: for the loop they are inputs like the amplitudes themselves, so any tensors with
+    their symmetry do -- x1, x2 and the q3rexpt2 intermediate are the t1, t2, i1_tt of a second synthetic problem, the
+    four moment intermediates the dressed hphh / pphp tensors of a second and third one."""
+
+    def __init__(self, t: tl.Tiling, r0: float = 0.37, excit: float = 0.21, seeds=(20240229, 77, 78)):
+        self.g = Dense(t, seeds[0])
+        self.a = Dense(t, seeds[1], fock_seed=11)
+        self.b = Dense(t, seeds[2], fock_seed=12)
+        self.r0, self.excit = r0, excit
+        self.x1, self.x2 = self.a.t1, self.a.t2
+        self.m1, self.m2 = self.a.n1(), self.a.n2()
+        self.m3, self.m4 = self.b.n1(), self.b.n2()
+        self.q2 = self.a.e2()
+
+    def six_index(self):
+        """(right, left) of cr_eomccsd_t.F:377-419, indexed [p4,p5,p6,h1,h2,h3], from the TCE expressions
+        creomccsd_t_n2_mem.F:9,:35,:55,:73 and q3rexpt2.F:7-8."""
+        g = self.g
+        E = np.einsum
+        p9 = Dense._p9
+        S, D, M, Et = g.six_index()
+        lr0 = abs(self.r0) >= 1e-7
+        R = (self.r0 * M if lr0 else 0.0 * M)
+        R = R - p9(E("abim,mcjk->abcijk", g.t2, self.m1), 2, 0)          # :9   -P(9) Sum(h12) t(p4 p5 h1 h12) i1(h12 p6 h2 h3)
+        R = R + 2.0 * p9(E("aeij,bcke->abcijk", g.t2, self.m2), 0, 2)    # :35  +2 P(9) Sum(p12) t(p4 p12 h1 h2) i1(p5 p6 h3 p12)
+        R = R - p9(E("abim,mcjk->abcijk", self.x2, self.m3), 2, 0)       # :55  -P(9) Sum(h12) x(p4 p5 h1 h12) i1(h12 p6 h2 h3)
+        R = R - p9(E("aeij,bcke->abcijk", self.x2, self.m4), 0, 2)       # :73  -P(9) Sum(p10) x(p4 p10 h1 h2) i1(p5 p6 h3 p10)
+        Lt = (self.r0 * Et if lr0 else 0.0 * Et)
+        Lt = Lt + p9(E("abij,ck->abcijk", g.t2, self.x1), 2, 2)          # q3rexpt2.F:7  P(9) t(p4 p5 h1 h2) x(p6 h3)
+        Lt = Lt - 2.0 * p9(E("ai,bcjk->abcijk", g.t1, self.q2), 0, 0)    # :8  -2 P(9) t(p4 h1) i1(p5 p6 h2 h3)
+        return R, Lt
+
+    def dense_reference(self):
+        R, Lt = self.six_index()
+        g = self.g
+        ep, eh = g.eps[g.P], g.eps[g.H]
+        delta = (-ep[:, None, None, None, None, None] - ep[None, :, None, None, None, None] - ep[None, None, :, None, None, None]
+                 + eh[None, None, None, :, None, None] + eh[None, None, None, None, :, None] + eh[None, None, None, None, None, :])
+        denex = delta + self.excit
+        return (float(np.sum(R * R / denex) / 36.0), float(np.sum(Lt * R) / 36.0), float(np.sum(Lt * R / denex) / 36.0),
+                float(np.sum(Lt * Lt) / 36.0))
+
+    def _pack(self, d, dense, kind):
+        t = d.t
+        if kind == "n1":
+            h, n = tl.cr_n1_offset(t)
+            out = np.zeros(n)
+            for key, off in synth._iter_hash(h):
+                p4b, h11b, h1b, h2b = tl.decode_cr_n1_key(t, key)
+                blk = dense[np.ix_(d._hidx(h11b), d._pidx(p4b), d._hidx(h1b), d._hidx(h2b))].transpose(1, 0, 2, 3)
+                out[off:off + blk.size] = blk.ravel()
+        elif kind == "n2":
+            h, n = tl.cr_n2_offset(t)
+            out = np.zeros(n)
+            for key, off in synth._iter_hash(h):
+                p4b, p5b, h1b, p12b = tl.decode_cr_n2_key(t, key)
+                blk = dense[np.ix_(d._pidx(p4b), d._pidx(p5b), d._hidx(h1b), d._pidx(p12b))]
+                out[off:off + blk.size] = blk.ravel()
+        elif kind == "pphh":
+            h, n = tl.t2_offset(t)
+            out = np.zeros(n)
+            for key, off in synth._iter_hash(h):
+                p4b, p5b, h1b, h2b = tl.decode_t2_key(t, key)
+                blk = dense[np.ix_(d._pidx(p4b), d._pidx(p5b), d._hidx(h1b), d._hidx(h2b))]
+                out[off:off + blk.size] = blk.ravel()
+        else:   # "ph": the T1 block structure
+            h, n = tl.t1_offset(t)
+            out = np.zeros(n)
+            for key, off in synth._iter_hash(h):
+                p5b, h6b = tl.decode_t1_key(t, key)
+                blk = dense[np.ix_(d._pidx(p5b), d._hidx(h6b))]
+                out[off:off + blk.size] = blk.ravel()
+        return h, out
+
+    def stores(self):
+        """(CRStores of the ground-state problem, CREOMStores)"""
+        g = self.g
+        x1h, x1 = self._pack(g, self.x1, "ph"); x2h, x2 = self._pack(g, self.x2, "pphh")
+        m1h, m1 = self._pack(g, self.m1, "n1"); m2h, m2 = self._pack(g, self.m2, "n2")
+        m3h, m3 = self._pack(g, self.m3, "n1"); m4h, m4 = self._pack(g, self.m4, "n2")
+        q2h, q2 = self._pack(g, self.q2, "pphh")
+        return g.stores(), CREOMStores(x1h, x1, x2h, x2, m1h, m1, m2h, m2, m3h, m3, m4h, m4, q2h, q2, self.r0, self.excit)
+
+
 def cr_energies(num1, num2, den1, den2, den0):
     """cr_ccsd_t.F:260-263."""
     return num1 / (1.0 + den1 + den0), num2 / (1.0 + den2 + den0)

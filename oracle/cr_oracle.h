@@ -384,3 +384,184 @@ Integer ora_cr_ccsd_t(const ora_ctx *c, const ora_cr *cr, double *sums, double *
             }
   return count;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* CR-EOMCCSD(T), the per-tuple half: src/tce/cr-eomccsd_t/cr_eomccsd_t.F:325-493.                                      */
+/*                                                                                                                      */
+/* Its six per-tuple routines are, character for character (checked with a normalising diff), the four CR-CCSD(T)       */
+/* routines above with other operands, irrep bookkeeping (irrep_x for the x amplitudes) and constant factors:           */
+/*   creomsd_t_n2_mem_1 (creomccsd_t_n2_mem.F:674-1042)    == cr_ccsd_t_N_1 (t2, i1_1 of the EOM moment), kernels sd_t_cr1_K */
+/*   creomsd_t_n2_mem_2 (:5665-6027)                       == cr_ccsd_t_N_2 (t2, i1_2), kernels cre_t_K (:15579-15838) with   */
+/*                                                            factor (2,2,-2,-2,-2,2,2,2,-2) = -2 x the sd_t_d2cp_K signs     */
+/*   creomsd_t_n2_mem_3 (:9657-10025)                      == cr_ccsd_t_N_1 (x2, i1_3), kernels sd_t_cr1_K                    */
+/*   creomsd_t_n2_mem_4 (:12905-13267)                     == cr_ccsd_t_N_2 (x2, i1_4), kernels cre_t_K with factor           */
+/*                                                            (-1,-1,1,1,1,-1,-1,-1,1) = the sd_t_d2cp_K signs                */
+/*   q3rexpt2_1 (q3rexpt2.F:80-413)                        == cr_ccsd_t_E_1 (t2, x1), kernels sd_E_K                          */
+/*   q3rexpt2_2 (:414-748)                                 == cr_ccsd_t_E_2 (t1, i1 of q3rexpt2), twot = -+2 instead of -+2/3 */
+/* Per tuple (cr_eomccsd_t.F:377-419): right = r0*cr_ccsd_t_N (if lr0) + the four mem routines; left = r0*cr_ccsd_t_E    */
+/* (if lr0) + the two q3rexpt2 routines; with denex = Delta + excit (:447-454)                                          */
+/*   num1 += f*right*right/denex + f*left*right (:455-458),   den1 += f*left*right/denex + f*left*left (:461-464).       */
+/* All intermediates, r0 and the excitation energy are INPUTS of the loop (toggle 1 / read_in3 upstream).               */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const Integer *x1_hash; const double *x1;     /* d_x1: tce_x1_offset (the T1 block structure for irrep_x = 0) */
+  const Integer *x2_hash; const double *x2;     /* d_x2 */
+  const Integer *m1_hash; const double *m1;     /* d_i2_1: i1(h12 p4 h1 h2) of creomsd_t_n2_mem_1, OFFSET_creomsd_t_n2_mem_1_1 (:1198) */
+  const Integer *m2_hash; const double *m2;     /* d_i2_2: i1(p4 p5 h1 p12) of _2, OFFSET_..._2_1 (:6189) */
+  const Integer *m3_hash; const double *m3;     /* d_i2_3: i1(h12 p4 h1 h2) of _3, OFFSET_..._3_1 (:10134) */
+  const Integer *m4_hash; const double *m4;     /* d_i2_4: i1(p4 p5 h1 p10) of _4, OFFSET_..._4_1 (:13383) */
+  const Integer *q2_hash; const double *q2;     /* d_i3_1: i1(p4 p5 h1 h2)_xt of q3rexpt2_2, OFFSET_q3rexpt2_2_1 (q3rexpt2.F:915) */
+  double r0, excit;                             /* r0xx (cr_eomccsd_t.F:134-144), excit */
+  Integer lr0;                                  /* :146-147 */
+} ora_creom;
+
+/* cre_t_K (creomccsd_t_n2_mem.F:15579-15838): the layouts of sd_t_d2_K, triplesx += factor * t2sub * v2sub */
+#define DEF_CRET(K, A, B, C, D, E, F)                                                          \
+  static void ora_cre_t_##K(Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d,  \
+                            Integer p4d, Integer p7d, double *RESTRICT triplesx,               \
+                            const double *RESTRICT t2sub, const double *RESTRICT v2sub, double factor) { \
+    for (Integer p4 = 0; p4 < p4d; p4++)                                                      \
+      for (Integer p5 = 0; p5 < p5d; p5++)                                                    \
+        for (Integer p6 = 0; p6 < p6d; p6++)                                                  \
+          for (Integer h1 = 0; h1 < h1d; h1++)                                                \
+            for (Integer h2 = 0; h2 < h2d; h2++)                                              \
+              for (Integer h3 = 0; h3 < h3d; h3++)                                            \
+                for (Integer p7 = 0; p7 < p7d; p7++)                                          \
+                  triplesx[T6(A, B, C, D, E, F, A##d, B##d, C##d, D##d, E##d)] +=             \
+                      factor * t2sub[p7 + p7d * (p4 + p4d * (h1 + h1d * h2))] *               \
+                      v2sub[p7 + p7d * (h3 + h3d * (p6 + p6d * p5))];                         \
+  }
+DEF_CRET(1, h3, h2, h1, p6, p5, p4)
+DEF_CRET(2, h2, h1, h3, p6, p5, p4)
+DEF_CRET(3, h2, h3, h1, p6, p5, p4)
+DEF_CRET(4, h3, h2, h1, p6, p4, p5)
+DEF_CRET(5, h2, h1, h3, p6, p4, p5)
+DEF_CRET(6, h2, h3, h1, p6, p4, p5)
+DEF_CRET(7, h3, h2, h1, p4, p6, p5)
+DEF_CRET(8, h2, h1, h3, p4, p6, p5)
+DEF_CRET(9, h2, h3, h1, p4, p6, p5)
+typedef void (*cret_fn)(Integer, Integer, Integer, Integer, Integer, Integer, Integer, double *, const double *, const double *, double);
+static const cret_fn CRET[9] = {ora_cre_t_1, ora_cre_t_2, ora_cre_t_3, ora_cre_t_4, ora_cre_t_5, ora_cre_t_6, ora_cre_t_7, ora_cre_t_8, ora_cre_t_9};
+
+/* The routines above are pure functions of (amplitude store, intermediate store): the EOM routines call them with
+ * temporarily substituted stores.  A shallow copy of the context / ora_cr carries the substitution. */
+static void creom_right(const ora_ctx *c, const ora_cr *cr, const ora_creom *q, double *k_right, const Integer *t) {
+  const Integer t_p4b = t[0], t_p5b = t[1], t_p6b = t[2], t_h1b = t[3], t_h2b = t[4], t_h3b = t[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  if (q->lr0) { /* cr_eomccsd_t.F:377-386: cr_ccsd_t_N(...,2), then dscal by r0xx */
+    ora_cr_ccsd_t_N_1(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+    ora_cr_ccsd_t_N_2(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+    for (size_t i = 0; i < size; i++) k_right[i] *= q->r0;
+  }
+  /* creomsd_t_n2_mem(...,2), :390-395: _1 and _3 through cr_ccsd_t_N_1 with substituted stores */
+  ora_ctx cx = *c;          /* x amplitudes in the place of t */
+  cx.t2_hash = q->x2_hash; cx.t2 = q->x2;
+  ora_cr s1 = *cr, s3 = *cr;
+  s1.n1_hash = q->m1_hash; s1.n1 = q->m1;
+  s3.n1_hash = q->m3_hash; s3.n1 = q->m3;
+  ora_cr_ccsd_t_N_1(c, &s1, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);      /* _1: t2 x i1_1 */
+  /* _2 and _4: cr_ccsd_t_N_2 with the cre_t_K kernels and their literal factors.  Evaluate the N_2 form into a scratch
+   * tile (it carries the sd_t_d2cp_K signs) and add it with the ratio factor/sign: -2 for _2, +1 for _4. */
+  double *tmp = (double *)calloc(size + 1, sizeof(double));
+  ora_cr s2 = *cr, s4 = *cr;
+  s2.n2_hash = q->m2_hash; s2.n2 = q->m2;
+  s4.n2_hash = q->m4_hash; s4.n2 = q->m4;
+  ora_cr_ccsd_t_N_2(c, &s2, tmp, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);          /* _2: t2 x i1_2 */
+  for (size_t i = 0; i < size; i++) k_right[i] += -2.0 * tmp[i];
+  ora_cr_ccsd_t_N_1(&cx, &s3, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);    /* _3: x2 x i1_3 */
+  memset(tmp, 0, sizeof(double) * size);
+  ora_cr_ccsd_t_N_2(&cx, &s4, tmp, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);        /* _4: x2 x i1_4 */
+  for (size_t i = 0; i < size; i++) k_right[i] += tmp[i];
+  free(tmp);
+}
+
+/* one of the nine cre_t_K kernels on explicit operands: lets the tests check that cre_t_K with the literal factors of
+ * creomsd_t_n2_mem_2 / _4 is -2 x / +1 x sd_t_d2cp_K, which creom_right relies on */
+void ora_cre_t_vs_d2cp(Integer k0, Integer h3d, Integer h2d, Integer h1d, Integer p6d, Integer p5d, Integer p4d, Integer p7d,
+                       const double *t2sub, const double *v2sub, double *out_cret_mem2, double *out_cret_mem4, double *out_d2cp) {
+  static const double F2[9] = {2.0, 2.0, -2.0, -2.0, -2.0, 2.0, 2.0, 2.0, -2.0};    /* creomccsd_t_n2_mem.F:5909-6005 */
+  static const double F4[9] = {-1.0, -1.0, 1.0, 1.0, 1.0, -1.0, -1.0, -1.0, 1.0};   /* :13150-13246 */
+  CRET[k0](h3d, h2d, h1d, p6d, p5d, p4d, p7d, out_cret_mem2, t2sub, v2sub, F2[k0]);
+  CRET[k0](h3d, h2d, h1d, p6d, p5d, p4d, p7d, out_cret_mem4, t2sub, v2sub, F4[k0]);
+  D2CP[k0](h3d, h2d, h1d, p6d, p5d, p4d, p7d, out_d2cp, t2sub, v2sub);
+}
+
+static void creom_left(const ora_ctx *c, const ora_cr *cr, const ora_creom *q, double *k_left, const Integer *t) {
+  const Integer t_p4b = t[0], t_p5b = t[1], t_p6b = t[2], t_h1b = t[3], t_h2b = t[4], t_h3b = t[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  if (q->lr0) { /* :400-408: cr_ccsd_t_E(...,2), then dscal by r0xx */
+    ora_cr_ccsd_t_E_1(c, k_left, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+    ora_cr_ccsd_t_E_2(c, cr, k_left, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+    for (size_t i = 0; i < size; i++) k_left[i] *= q->r0;
+  }
+  /* q3rexpt2(...,2), :410-419: _1 = cr_ccsd_t_E_1 with x1 in the place of t1; _2 = cr_ccsd_t_E_2 with the q3rexpt2
+   * intermediate and twot = -+2 = 3 x (-+2/3) */
+  ora_ctx cx = *c;
+  cx.t1_hash = q->x1_hash; cx.t1 = q->x1;
+  ora_cr_ccsd_t_E_1(&cx, k_left, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+  double *tmp = (double *)calloc(size + 1, sizeof(double));
+  ora_cr s = *cr;
+  s.e2_hash = q->q2_hash; s.e2 = q->q2;
+  ora_cr_ccsd_t_E_2(c, &s, tmp, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+  for (size_t i = 0; i < size; i++) k_left[i] += 3.0 * tmp[i];
+  free(tmp);
+}
+
+/* One tuple of cr_eomccsd_t.F:325-493.  sums[4] += (sum f R R/denex, sum f L R, sum f L R/denex, sum f L L); the file
+ * adds the first two into num1 and the last two into den1.  Optional outputs: the right and left tiles [p4,p5,p6,h1,h2,h3]. */
+void ora_cr_eomccsd_t_tuple(const ora_ctx *c, const ora_cr *cr, const ora_creom *q, const Integer *tuple, double *sums,
+                            double *right_out, double *left_out) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2], t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  double *k_right = (double *)calloc(size + 1, sizeof(double)), *k_left = (double *)calloc(size + 1, sizeof(double)); /* :361-369 */
+  creom_right(c, cr, q, k_right, tuple);
+  creom_left(c, cr, q, k_left, tuple);
+  const double factor = ora_ccsd_t_factor((int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* :421-435 */
+  const double *e4 = c->evl_sorted + c->offset[t_p4b - 1], *e5 = c->evl_sorted + c->offset[t_p5b - 1];
+  const double *e6 = c->evl_sorted + c->offset[t_p6b - 1], *e1 = c->evl_sorted + c->offset[t_h1b - 1];
+  const double *e2 = c->evl_sorted + c->offset[t_h2b - 1], *e3 = c->evl_sorted + c->offset[t_h3b - 1];
+  double a = 0.0, b = 0.0, cc = 0.0, d = 0.0;
+  size_t i = 0;
+  for (Integer p4 = 0; p4 < R[0]; p4++)
+    for (Integer p5 = 0; p5 < R[1]; p5++)
+      for (Integer p6 = 0; p6 < R[2]; p6++)
+        for (Integer h1 = 0; h1 < R[3]; h1++)
+          for (Integer h2 = 0; h2 < R[4]; h2++)
+            for (Integer h3 = 0; h3 < R[5]; h3++, i++) {
+              const double denex = -e4[p4] - e5[p5] - e6[p6] + e1[h1] + e2[h2] + e3[h3] + q->excit; /* :447-454 */
+              a += factor * (k_right[i] * k_right[i]) / denex;  /* :455-456 */
+              b += factor * k_left[i] * k_right[i];             /* :457-458 */
+              cc += factor * (k_left[i] * k_right[i]) / denex;  /* :461-462 */
+              d += factor * (k_left[i] * k_left[i]);            /* :463-464 */
+            }
+  sums[0] += a; sums[1] += b; sums[2] += cc; sums[3] += d;
+  if (right_out) memcpy(right_out, k_right, sizeof(double) * size);
+  if (left_out) memcpy(left_out, k_left, sizeof(double) * size);
+  free(k_right); free(k_left);
+}
+
+/* all tuples in the loop order of cr_eomccsd_t.F:325-330 (tuple filter :331-350 with irrep_x = 0); per_task 4 doubles per tuple */
+Integer ora_cr_eomccsd_t(const ora_ctx *c, const ora_cr *cr, const ora_creom *q, double *sums, double *per_task) {
+  Integer count = 0;
+  sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+  const Integer n0 = c->noab, n1 = c->noab + c->nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue;
+              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+              double s[4] = {0.0, 0.0, 0.0, 0.0};
+              ora_cr_eomccsd_t_tuple(c, cr, q, t, s, NULL, NULL);
+              if (per_task) for (int k = 0; k < 4; k++) per_task[4 * count + k] = s[k];
+              for (int k = 0; k < 4; k++) sums[k] += s[k];
+              count++;
+            }
+  return count;
+}

@@ -346,3 +346,63 @@ def cr_tuple(st, cr, tup):
     if l.ora_error():
         raise RuntimeError("oracle: block key not found")
     return s, m.reshape(dims), e.reshape(dims)
+
+
+class CREOM(C.Structure):   # ora_creom (cr_oracle.h)
+    _fields_ = [("x1_hash", PL), ("x1", PD), ("x2_hash", PL), ("x2", PD), ("m1_hash", PL), ("m1", PD), ("m2_hash", PL), ("m2", PD),
+                ("m3_hash", PL), ("m3", PD), ("m4_hash", PL), ("m4", PD), ("q2_hash", PL), ("q2", PD),
+                ("r0", C.c_double), ("excit", C.c_double), ("lr0", L)]
+
+
+def make_creom(q):
+    names = ("x1", "x2", "m1", "m2", "m3", "m4", "q2")
+    k = {}
+    args = []
+    for n in names:
+        k[n + "h"] = np.ascontiguousarray(getattr(q, n + "_hash"), np.int64)
+        k[n] = np.ascontiguousarray(getattr(q, n), np.float64)
+        args += [_pl(k[n + "h"]), _pd(k[n])]
+    return CREOM(*args, float(q.r0), float(q.excit), int(abs(q.r0) >= 1e-7)), k
+
+
+def cr_eomccsd_t(st, cr, q):
+    """CR-EOMCCSD(T) tuple loop on the CPU (cr_eomccsd_t.F:325-493 restated, cr_oracle.h).  cr = cr_dense.CRStores (the
+    ground-state intermediates, read when r0 != 0), q = cr_dense.CREOMStores.  Returns dict(sums = (sum f R R/denex,
+    sum f L R, sum f L R/denex, sum f L L), per_task[n,4], num1, den1)."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_cr(cr)
+    z, keep3 = make_creom(q)
+    n = len(task_list(st.t))
+    s = np.zeros(4); pt = np.zeros((max(n, 1), 4))
+    l.ora_cr_eomccsd_t.restype = L
+    cnt = l.ora_cr_eomccsd_t(C.byref(c), C.byref(y), C.byref(z), _pd(s), _pd(pt))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return dict(sums=s.copy(), per_task=pt[:cnt], num1=float(s[0] + s[1]), den1=float(s[2] + s[3]))
+
+
+def cr_eom_tuple(st, cr, q, tup):
+    """One tuple: (sums[4], right tile, left tile), tiles indexed [p4,p5,p6,h1,h2,h3]."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_cr(cr)
+    z, keep3 = make_creom(q)
+    dims = [st.t.r(int(b)) for b in tup[:6]]
+    n = int(np.prod(dims))
+    s = np.zeros(4); r = np.zeros(n); le = np.zeros(n)
+    tt = np.array(tup[:6], np.int64)
+    l.ora_cr_eomccsd_t_tuple(C.byref(c), C.byref(y), C.byref(z), _pl(tt), _pd(s), _pd(r), _pd(le))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return s, r.reshape(dims), le.reshape(dims)
+
+
+def cre_t_vs_d2cp(k0, dims_perm, kd, t2sub, v2sub):
+    """(cre_t_K with the factor of creomsd_t_n2_mem_2, with the factor of _4, sd_t_d2cp_K) on the same operands."""
+    l = lib()
+    h3d, h2d, h1d, p6d, p5d, p4d = [int(x) for x in dims_perm]
+    n = h3d * h2d * h1d * p6d * p5d * p4d
+    a = np.zeros(n); b = np.zeros(n); d = np.zeros(n)
+    l.ora_cre_t_vs_d2cp(L(k0), L(h3d), L(h2d), L(h1d), L(p6d), L(p5d), L(p4d), L(int(kd)), _pd(t2sub), _pd(v2sub), _pd(a), _pd(b), _pd(d))
+    return a, b, d
