@@ -163,7 +163,7 @@ int nwc_triples_destroy(nwc_triples_ctx *ctx);
  * hands to the engine are recorded instead of being packed and launched.  set_state (replicated spin-orbital stores
  * only), set_lambda and set_cr keep the caller's host arrays by reference; trace_tuple records one tuple
  * (method 0: (T), 1: Lambda-CCSD(T), 2 / 3: CR-CCSD(T) numerator / denominator pass of the two-pass form, 4: the one-pass
- * dual tuple); trace_take hands the records
+ * dual tuple, 5 / 6 / 7: the three tuples of CR-EOMCCSD(T)); trace_take hands the records
  * out.  Every compute entry point fails on a trace context.  It exists so the CPU test-suite can check the driver half
  * against the oracle's tiles without a GPU (tests/test_trace.py); the pointers in the records are the caller's. */
 typedef struct {
@@ -177,7 +177,8 @@ typedef struct {
   const double *a;     /* kinds 0-2: t1sub / t2sub source; kind 3: the two-index operand */
   const double *b;     /* kinds 0-2: v2sub source; kind 3: the four-index operand */
   long long sa[6];     /* element strides: kinds 0-2 per PERMUTED name (h1,h2,h3,p4,p5,p6); kind 3 per physical
-                          position (h3,h2,h1,p6,p5,p4); kind 9: sa = the ranges by physical position */
+                          position (h3,h2,h1,p6,p5,p4); kind 9: sa = the ranges by physical position, a / b / sb[2..5] =
+                          the six orbital-energy vectors (h1,h2,h3,p4,p5,p6) as addresses, sb[0..1] the sub-tile range */
   long long sb[6];
   long long ka, kb;    /* strides of the contracted index */
   double scale;        /* kinds 1,2: factor of the T2 sort (tce_hashnsort.F); kind 9: the tuple factor */
@@ -316,6 +317,25 @@ int nwc_triples_run_cr(nwc_triples_ctx *ctx, Integer first, Integer stride, Inte
 /* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_sum, n = 4) */
 int nwc_triples_run_cr_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
                                  double sums[4], double *per_task);
+/* CR-EOMCCSD(T) (src/tce/cr-eomccsd_t/cr_eomccsd_t.F, tce_energy.F:8787-8798): the tuple loop :325-493.  Its six per-tuple
+ * routines are the CR-CCSD(T) ones with other operands and constant factors (creomsd_t_n2_mem_1..4 == cr_ccsd_t_N_1/_N_2 on
+ * (t2 | x2) x (d_i2_1..4), creomccsd_t_n2_mem.F:674,:5665,:9657,:12905; q3rexpt2_1/_2 == cr_ccsd_t_E_1/_E_2 on (t2, x1) and
+ * (t1, d_i3_1), q3rexpt2.F:80,:414).  Per tuple: right = r0*cr_ccsd_t_N + creomsd_t_n2_mem, left = r0*cr_ccsd_t_E + q3rexpt2,
+ * denex = Delta + excit, and  num1 += f*right^2/denex + f*left*right,  den1 += f*left*right/denex + f*left^2 (:455-464).
+ * set_creom takes what the loop reads beyond T1/T2 and the CR-CCSD(T) intermediates of nwc_triples_set_cr (needed when
+ * |r0| >= 1e-7, :146-147): x1 / x2 (offset tables equal to T1's / T2's: irrep_x = 0), d_i2_1..4 with their offset tables
+ * (the layouts of the CR ones: hphh stored (p,h,h<=h), pphp stored (p<=p,h,p)), d_i3_1 (the T2 block structure), r0 and
+ * the excitation energy -- all produced upstream with toggle 1, or read from files with read_in3.  run_creom returns
+ * sums[4] = (sum f R R/denex, sum f L R, sum f L R/denex, sum f L L); num1 = sums[0]+sums[1], den1 = sums[2]+sums[3],
+ * energy1 = num1/(r0^2 + d12 + den1) (:564) with the caller's d12. */
+int nwc_triples_set_creom(nwc_triples_ctx *ctx, const Integer *x1_hash, const double *x1, const Integer *x2_hash,
+                          const double *x2, const Integer *i2_1_hash, const double *i2_1, const Integer *i2_2_hash,
+                          const double *i2_2, const Integer *i2_3_hash, const double *i2_3, const Integer *i2_4_hash,
+                          const double *i2_4, const Integer *i3_1_hash, const double *i3_1, double r0, double excit);
+int nwc_triples_run_creom(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double sums[4],
+                          double *per_task);
+int nwc_triples_run_creom_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task,
+                                    Integer ntasks, double sums[4], double *per_task);
 /* one tuple, optionally materialising the t3 tiles (validation only) */
 int nwc_triples_run_tuple(nwc_triples_ctx *ctx, const Integer tuple_p4p5p6h1h2h3[6], double energy[2],
                           double *host_doubles, double *host_singles);

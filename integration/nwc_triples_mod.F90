@@ -336,6 +336,25 @@ module nwc_triples_mod
       real(c_double), intent(out) :: sums(4)         ! num1, num2, den1, den2 of this rank (cr_ccsd_t.F:176-207), without den0
       type(c_ptr), value :: per_task
     end function
+    ! CR-EOMCCSD(T) (cr_eomccsd_t.F): x1 / x2, the four intermediates of creomsd_t_n2_mem (toggle 1), the one of q3rexpt2,
+    ! r0xx and the excitation energy; call nwc_triples_set_cr first when |r0xx| >= 1d-7
+    integer(c_int) function nwc_triples_set_creom(ctx, x1_hash, x1, x2_hash, x2, i2_1_hash, i2_1, i2_2_hash, i2_2, &
+                                                  i2_3_hash, i2_3, i2_4_hash, i2_4, i3_1_hash, i3_1, r0, excit) &
+        bind(C, name='nwc_triples_set_creom')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), intent(in) :: x1_hash(*), x2_hash(*), i2_1_hash(*), i2_2_hash(*), i2_3_hash(*), i2_4_hash(*), i3_1_hash(*)
+      real(c_double), intent(in) :: x1(*), x2(*), i2_1(*), i2_2(*), i2_3(*), i2_4(*), i3_1(*)
+      real(c_double), value :: r0, excit
+    end function
+    integer(c_int) function nwc_triples_run_creom_partition(ctx, rank, nranks, first_task, ntasks, sums, per_task) &
+        bind(C, name='nwc_triples_run_creom_partition')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), value :: rank, nranks, first_task, ntasks
+      real(c_double), intent(out) :: sums(4)         ! sum f R R/denex, sum f L R, sum f L R/denex, sum f L L (cr_eomccsd_t.F:455-464)
+      type(c_ptr), value :: per_task
+    end function
     integer(c_int) function nwc_triples_allreduce_sum(ctx, buf, n) bind(C, name='nwc_triples_allreduce_sum')
       import :: c_int, c_ptr, c_double, c_size_t
       type(c_ptr), value :: ctx

@@ -369,6 +369,45 @@ class Triples:
         """cr_ccsd_t.F:260-263: (CR-CCSD[T], CR-CCSD(T)) corrections from the four sums and the scalar of cr_ccsd_t_D."""
         return float(sums[0] / (1.0 + sums[2] + den0)), float(sums[1] / (1.0 + sums[3] + den0))
 
+    def set_creom(self, q):
+        """q: the CR-EOMCCSD(T) inputs (attributes x1_hash, x1, x2_hash, x2, m1..m4 (+_hash) = d_i2_1..4, q2 (+_hash) = d_i3_1,
+        r0, excit); call set_cr first when r0 != 0."""
+        names = ("x1", "x2", "m1", "m2", "m3", "m4", "q2")
+        k = []
+        for n in names:
+            k += [np.ascontiguousarray(getattr(q, n + "_hash"), np.int64), np.ascontiguousarray(getattr(q, n), np.float64)]
+        l = lib()
+        l.nwc_triples_set_creom.argtypes = [C.c_void_p] + [PL, PD] * 7 + [C.c_double, C.c_double]
+        args = []
+        for i in range(7):
+            args += [_pl(k[2 * i]), _pd(k[2 * i + 1])]
+        _check(l.nwc_triples_set_creom(self._h, *args, float(q.r0), float(q.excit)), "nwc_triples_set_creom")
+        if self.is_trace:
+            self._keep.append(k)
+
+    def run_creom(self, first=0, stride=1, max_tasks=0, per_task=False):
+        """CR-EOMCCSD(T) tuple loop (cr_eomccsd_t.F:325-493): sums = (sum f R R/denex, sum f L R, sum f L R/denex, sum f L L)."""
+        s = np.zeros(4)
+        cnt = len(range(first, self.num_tasks, stride))
+        if max_tasks and max_tasks > 0:
+            cnt = min(cnt, max_tasks)
+        pt = np.zeros((max(cnt, 1), 4)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_creom.argtypes = [C.c_void_p, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_creom(self._h, first, stride, max_tasks, _pd(s), _pd(pt) if per_task else None),
+               "nwc_triples_run_creom")
+        return (s, pt[:cnt]) if per_task else s
+
+    def run_creom_partition(self, rank: int, world: int, first_task: int = 0, ntasks: int = 0, per_task=False):
+        s = np.zeros(4)
+        n = self.num_tasks - first_task if ntasks <= 0 else min(ntasks, self.num_tasks - first_task)
+        pt = np.zeros((max(n, 1), 4)) if per_task else None
+        l = lib()
+        l.nwc_triples_run_creom_partition.argtypes = [C.c_void_p, L, L, L, L, PD, PD]
+        _check(l.nwc_triples_run_creom_partition(self._h, rank, world, first_task, ntasks, _pd(s), _pd(pt) if per_task else None),
+               "nwc_triples_run_creom_partition")
+        return (s, pt[:n]) if per_task else s
+
     def tuple_items(self, tup) -> int:
         tt = np.array(tup, np.int64)
         return int(lib().nwc_triples_tuple_items(self._h, _pl(tt)))

@@ -316,6 +316,9 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
     r.kind = 9; r.K = two_sided_ ? (dual_ ? 2 : 1) : 0; r.scale = factor;
     for (int q = 0; q < 6; q++) r.sa[q] = cur_hdr_.R[q];
     r.sb[0] = item_lo; r.sb[1] = item_hi;
+    r.a = eps[0]; r.b = eps[1];                                   // orbital-energy vectors: h1, h2, ...
+    r.sb[2] = (long long)(uintptr_t)eps[2]; r.sb[3] = (long long)(uintptr_t)eps[3];   // ... h3, p4,
+    r.sb[4] = (long long)(uintptr_t)eps[4]; r.sb[5] = (long long)(uintptr_t)eps[5];   // p5, p6
     trace.push_back(r);
     open_ = false;
     return;

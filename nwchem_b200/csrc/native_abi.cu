@@ -83,6 +83,16 @@ struct nwc_triples_ctx {
   size_t n_crn1 = 0, n_crn2 = 0, n_cre2 = 0;
   std::vector<Integer> crn1_hash, crn2_hash, cre2_hash;
   std::vector<double> cre2_scaled;          // trace contexts keep host data by reference: the 2/3-scaled copy lives here
+  // CR-EOMCCSD(T) inputs (nwc_triples_set_creom): x amplitudes, the four moment intermediates, and two combined stores
+  // for the left-hand outer products (eomy1 = r0*t1 + x1, eomz = r0*(2/3)*i1_tt + 2*i1_xt); eps vectors for the shifted
+  // and the unit denominators
+  double *d_x2 = nullptr, *d_m1 = nullptr, *d_m2 = nullptr, *d_m3 = nullptr, *d_m4 = nullptr, *d_eomy1 = nullptr, *d_eomz = nullptr;
+  double *d_evl_shift = nullptr, *d_unit = nullptr, *d_zero = nullptr;
+  size_t n_x2 = 0, n_m1 = 0, n_m2 = 0, n_m3 = 0, n_m4 = 0, n_eomy1 = 0, n_eomz = 0, n_evl_shift = 0, n_unit = 0, n_zero = 0;
+  std::vector<Integer> x2_hash, m1_hash, m2_hash, m3_hash, m4_hash, eomz_hash;
+  std::vector<double> eom_host[5];          // trace contexts: combined stores and eps vectors live here
+  double eom_r0 = 0.0, eom_excit = 0.0;
+  bool eom_lr0 = false, eom_set = false;
   // per batch slot (engine.h): blocks that live in that slot's arena
   std::unordered_map<Integer, const double*> v2_built[2];   // spin-orbital key -> antisymmetrised block
   std::unordered_map<Integer, const double*> pulled[2];     // block index -> local copy of a remote block
@@ -95,6 +105,8 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
     c->eng->abort();
     c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = c->d_y1 = c->d_y2 = c->d_f1 = nullptr;
     c->d_crn1 = c->d_crn2 = c->d_cre2 = nullptr;
+    c->d_x2 = c->d_m1 = c->d_m2 = c->d_m3 = c->d_m4 = c->d_eomy1 = c->d_eomz = c->d_evl_shift = c->d_unit = c->d_zero = nullptr;
+    c->eom_set = false;
     c->y1_hash.clear(); c->y2_hash.clear(); c->f1_hash.clear();
     c->crn1_hash.clear(); c->crn2_hash.clear(); c->cre2_hash.clear();
     c->klist.clear();
@@ -109,6 +121,12 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
   cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl);
   cudaFree(c->d_y1); cudaFree(c->d_y2); cudaFree(c->d_f1);
   cudaFree(c->d_crn1); cudaFree(c->d_crn2); cudaFree(c->d_cre2);
+  cudaFree(c->d_x2); cudaFree(c->d_m1); cudaFree(c->d_m2); cudaFree(c->d_m3); cudaFree(c->d_m4); cudaFree(c->d_eomy1);
+  cudaFree(c->d_eomz); cudaFree(c->d_evl_shift); cudaFree(c->d_unit); cudaFree(c->d_zero);
+  c->d_x2 = c->d_m1 = c->d_m2 = c->d_m3 = c->d_m4 = c->d_eomy1 = c->d_eomz = c->d_evl_shift = c->d_unit = c->d_zero = nullptr;
+  c->n_x2 = c->n_m1 = c->n_m2 = c->n_m3 = c->n_m4 = c->n_eomy1 = c->n_eomz = c->n_evl_shift = c->n_unit = c->n_zero = 0;
+  c->x2_hash.clear(); c->m1_hash.clear(); c->m2_hash.clear(); c->m3_hash.clear(); c->m4_hash.clear();
+  c->eom_set = false;
   c->d_t1 = c->d_t2 = c->d_v2 = c->d_v2orb = c->d_evl = c->d_y1 = c->d_y2 = c->d_f1 = nullptr;
   c->d_crn1 = c->d_crn2 = c->d_cre2 = nullptr;
   c->n_t1 = c->n_t2 = c->n_v2 = c->n_v2orb = c->n_y1 = c->n_y2 = c->n_f1 = c->n_crn1 = c->n_crn2 = c->n_cre2 = 0;
@@ -243,8 +261,15 @@ struct NativeSink {
   // T2 fetches, dispatch tests and kernel layouts/signs; only the store, its key and, for N_1, the element order differ).
   // CR_DENOM: the walk of the (T) singles produces cr_ccsd_t_E_2 (t1 x i1_tt, -2/3) and walk_cr_e1 produces cr_ccsd_t_E_1,
   // both as outer products bound to the side-0 tile.
-  enum { CR_OFF = 0, CR_MOMENT = 1, CR_DENOM = 2 };
+  // CR_EOM_RIGHT / CR_EOM_LEFT: the tiles of CR-EOMCCSD(T) (cr_eomccsd_t.F:377-419).  Its per-tuple routines are the CR-CCSD(T)
+  // ones with other operands and constant factors (creomccsd_t_n2_mem.F:674,:5665,:9657,:12905; q3rexpt2.F:80,:414), so one
+  // walk of the (T) doubles emits, per contracted tile, the segments  r0*t2*i1 (if r0 != 0), f*t2*i2_{1|2}, x2*i2_{3|4}
+  // (f = 1 for the Sum(h) family, -2 for the Sum(p) family) -- concatenated along K in one panel pair -- and the left tile
+  // is t2 x (r0*t1 + x1) through walk_cr_e1 plus t1 x (r0*2/3*i1_tt + 2*i1_xt) through walk_singles.
+  enum { CR_OFF = 0, CR_MOMENT = 1, CR_DENOM = 2, CR_EOM_RIGHT = 3, CR_EOM_LEFT = 4 };
   int cr = CR_OFF;
+  int op_target = Engine::OP_SIDE0;   // where CR_DENOM / CR_EOM_LEFT outer products go
+  int op_mask = 3;                    // CR_EOM_LEFT: bit 0 = the walk_cr_e1 family, bit 1 = the walk_singles family
   // contracted tiles of the current row, concatenated along K when the row ends (engine.h Segment)
   std::vector<Segment> segs;
   bool row_fire[9] = {false, false, false, false, false, false, false, false, false};
@@ -291,16 +316,18 @@ struct NativeSink {
     // V2 block <p5 p6||h2 h3> stored (p5,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,p5)
     v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b);
     v.stride[N_P5] = S.rg(r.h3b) * S.rg(r.h2b) * S.rg(r.p6b);
-    if (cr == CR_DENOM) {
+    if (cr == CR_DENOM || cr == CR_EOM_LEFT) {
       // cr_ccsd_t_E_2: i1(p5 p6 h2 h3)_tt block, same layout, key as a T2 block (cr_ccsd_t_E.F:605-608); sd_E2_K adds
       // twot * t1sub * v2sub with twot = -2/3 * (sign of sd_t_s1_K) (:629-:721).  The store is resident pre-scaled by
-      // 2/3 (nwc_triples_set_cr), so only the sign is left.
-      v.base = c->d_cre2 + hash_lookup_or_die(c->cre2_hash, t2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "cr e2(pphh)");
+      // 2/3 (nwc_triples_set_cr), so only the sign is left.  CR-EOMCCSD(T): the combined store of nwc_triples_set_creom.
+      if (cr == CR_EOM_LEFT && !(op_mask & 2)) return;
+      const double* zstore = cr == CR_DENOM ? c->d_cre2 : c->d_eomz;
+      v.base = zstore + hash_lookup_or_die(cr == CR_DENOM ? c->cre2_hash : c->eomz_hash, t2_key(S, p5b_2, p6b_2, h2b_2, h3b_2), "cr e2(pphh)");
       for (int k = 0; k < 9; k++)
         if (fire[k]) {
           int sa[6], sb[6];
           for (int q = 0; q < 6; q++) { sa[q] = (int)t.stride[DECL[0][k][q]]; sb[q] = (int)v.stride[DECL[0][k][q]]; }
-          e.add_outer_product(t.base, sa, v.base, sb, SIGN[0][k] > 0, Engine::OP_SIDE0);
+          e.add_outer_product(t.base, sa, v.base, sb, SIGN[0][k] > 0, op_target);
         }
       return;
     }
@@ -312,8 +339,10 @@ struct NativeSink {
   // cr_ccsd_t_E_1 (cr_ccsd_t_E.F:261-277, kernels sd_E_K): t2sub(p4,p5,h1,h2) = the stored T2 block <p4 p5||h1 h2>
   // (h2 fastest; the reference's TCE_SORT_4(4,3,2,1) only reverses the index order), t1sub(p6,h3) = the stored T1 block
   void cr_e1(const Row& r, const Integer am[4], const Integer bm[2], const bool fire[9]) {
+    if (cr == CR_EOM_LEFT && !(op_mask & 1)) return;
     OperandView a, b;
-    a.base = c->d_t1 + hash_lookup_or_die(S.t1_hash, t1_key(S, bm[0], bm[1]), "t1");
+    // CR-EOMCCSD(T): r0 * cr_ccsd_t_E_1 (t2 x t1) + q3rexpt2_1 (t2 x x1) = t2 x (r0*t1 + x1), the combined T1-like store
+    a.base = (cr == CR_EOM_LEFT ? c->d_eomy1 : c->d_t1) + hash_lookup_or_die(S.t1_hash, t1_key(S, bm[0], bm[1]), "t1");
     a.stride[N_H3] = 1; a.stride[N_P6] = S.rg(r.h3b);
     b.base = c->d_t2 + hash_lookup_or_die(S.t2_hash, t2_key(S, am[0], am[1], am[2], am[3]), "t2");
     b.stride[N_H2] = 1; b.stride[N_H1] = S.rg(r.h2b); b.stride[N_P5] = S.rg(r.h1b) * S.rg(r.h2b);
@@ -322,7 +351,7 @@ struct NativeSink {
       if (fire[k]) {
         int sa[6], sb[6];
         for (int q = 0; q < 6; q++) { sa[q] = (int)a.stride[DECL_E1[k][q]]; sb[q] = (int)b.stride[DECL_E1[k][q]]; }
-        e.add_outer_product(a.base, sa, b.base, sb, SIGN_E1[k] < 0, Engine::OP_SIDE0);
+        e.add_outer_product(a.base, sa, b.base, sb, SIGN_E1[k] < 0, op_target);
       }
   }
 
@@ -341,13 +370,23 @@ struct NativeSink {
       t.stride[N_P4] = st[0]; t.stride[N_P5] = st[1]; t.stride[N_H1] = st[2]; t.kstride = st[3];
       sign = 1.0;
     }
-    if (cr == CR_MOMENT) {
+    if (cr == CR_MOMENT || cr == CR_EOM_RIGHT) {
       // i1(h7 p6 h2 h3) of cr_ccsd_t_N_1, stored (p6,h7,h2,h3), h3 fastest == v2sub(h3,h2,h7,p6) of sd_t_cr1_K; key
       // h3-1 + noab*(h2-1 + noab*(h7-1 + noab*(p6-noab-1))) (cr_ccsd_t_N.F:509-512)
       const Integer key = bm[3] - 1 + S.noab * (bm[2] - 1 + S.noab * (bm[1] - 1 + S.noab * (bm[0] - S.noab - 1)));
-      v.base = c->d_crn1 + hash_lookup_or_die(c->crn1_hash, key, "cr n1(phhh)");
       v.stride[N_H3] = 1; v.stride[N_H2] = S.rg(r.h3b); v.kstride = S.rg(r.h3b) * S.rg(r.h2b);
       v.stride[N_P6] = S.rg(r.h3b) * S.rg(r.h2b) * rh7;
+      if (cr == CR_EOM_RIGHT) {
+        // creomsd_t_n2_mem_1 (t2 x i2_1), _3 (x2 x i2_3), and r0 * cr_ccsd_t_N_1: same T2-type fetch (x2 has the T2 block
+        // structure), same intermediate layout and key
+        OperandView tx = t;
+        tx.base = c->d_x2 + (t.base - c->d_t2);   // same block, same offset: the x2 offset table is checked equal to T2's
+        if (c->eom_lr0) { v.base = c->d_crn1 + hash_lookup_or_die(c->crn1_hash, key, "cr n1(phhh)"); push(t, v, sign * c->eom_r0, rh7, fire); }
+        v.base = c->d_m1 + hash_lookup_or_die(c->m1_hash, key, "creom i2_1(phhh)"); push(t, v, sign, rh7, fire);
+        v.base = c->d_m3 + hash_lookup_or_die(c->m3_hash, key, "creom i2_3(phhh)"); push(tx, v, sign, rh7, fire);
+        return;
+      }
+      v.base = c->d_crn1 + hash_lookup_or_die(c->crn1_hash, key, "cr n1(phhh)");
     } else {
       // block <h7 p6||h2 h3> stored (h7,p6,h2,h3), h3 fastest == v2sub(h3,h2,p6,h7)  (:67-80)
       v.base = v2_operand(c, bm[1], bm[0], bm[2], bm[3], "v2(hphh)");
@@ -374,8 +413,21 @@ struct NativeSink {
     }
     // block <p5 p6||h3 p7> stored (p5,p6,h3,p7), p7 fastest == v2sub(p7,h3,p6,p5)  (:149-161); CR-CCSD(T): i1(p5 p6 h3 p7)
     // of cr_ccsd_t_N_2, same layout, key p7-noab-1 + nvab*(h3-1 + noab*(p6-noab-1 + nvab*(p5-noab-1))) (cr_ccsd_t_N.F:3753-3756)
+    const Integer ckey = bm[3] - S.noab - 1 + S.nvab * (bm[2] - 1 + S.noab * (bm[1] - S.noab - 1 + S.nvab * (bm[0] - S.noab - 1)));
+    if (cr == CR_EOM_RIGHT) {
+      // creomsd_t_n2_mem_2 (t2 x i2_2, cre_t_K factor = -2 x the sd_t_d2cp_K sign), _4 (x2 x i2_4, factor = the sign), and
+      // r0 * cr_ccsd_t_N_2
+      v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
+      v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
+      OperandView tx = t;
+      tx.base = c->d_x2 + (t.base - c->d_t2);
+      if (c->eom_lr0) { v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, ckey, "cr n2(pphp)"); push(t, v, sign * c->eom_r0, rp7, fire); }
+      v.base = c->d_m2 + hash_lookup_or_die(c->m2_hash, ckey, "creom i2_2(pphp)"); push(t, v, -2.0 * sign, rp7, fire);
+      v.base = c->d_m4 + hash_lookup_or_die(c->m4_hash, ckey, "creom i2_4(pphp)"); push(tx, v, sign, rp7, fire);
+      return;
+    }
     if (cr == CR_MOMENT)
-      v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, bm[3] - S.noab - 1 + S.nvab * (bm[2] - 1 + S.noab * (bm[1] - S.noab - 1 + S.nvab * (bm[0] - S.noab - 1))), "cr n2(pphp)");
+      v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, ckey, "cr n2(pphp)");
     else
       v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
@@ -493,6 +545,56 @@ void emit_tuple_cr(nwc_triples_ctx* c, const Integer t[6], int pass, long long i
   const double* eps[6] = {c->d_evl + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
   c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);   // cr_ccsd_t.F:153-167 == ccsd_t_dot.F:52-66
+}
+
+// CR-EOMCCSD(T) (cr_eomccsd_t.F:325-493): per tuple a right tile R (contractions only) and a left tile L (outer products
+// only) and four sums  A = sum f R R/denex,  B = sum f L R,  C = sum f L R/denex,  D = sum f L L  (denex = Delta + omega);
+// the file adds A + B into num1 and C + D into den1 (:455-464).  Composed from tuple forms the kernels already have:
+//   which 0 "X":  PLAIN (T)-type tuple, doubles = R, singles = L, orbital energies of the h1 slot shifted by omega
+//                 -> (A, A + C): the (T) formulas E[T] = <D,D>, E(T) = <D,D+S> with D = R, S = L
+//   which 1 "Y1": two-sided tuple with UNIT denominators (eps = 1 for the h1 slot, 0 elsewhere): side 0 = L (outer
+//                 products bound to it), side 1 = R, singles = the t2 x (r0 t1 + x1) half of L -> (B, B + <L,La>)
+//   which 2 "Y2": two-sided, unit denominators, no contraction: side 0 = L, singles = the other half of L -> (0, <L,Lb>)
+// so D = <L,La> + <L,Lb>.  R is contracted twice (once at the plain kernel's 3 CTAs/SM); a kernel with an undenominated
+// second energy pass would need it once.
+void emit_tuple_creom(nwc_triples_ctx* c, const Integer t[6], int which, long long item_lo = 0, long long item_hi = -1) {
+  const HostState& S = c->S;
+  int R[6];
+  tuple_ranges(S, t, R);
+  c->eng->begin_tuple(R);
+  if (which == 0 || which == 1) {   // R: r0 * cr_ccsd_t_N + creomsd_t_n2_mem_1..4 (cr_eomccsd_t.F:377-395)
+    NativeSink r{c, *c->eng, S};
+    r.cr = NativeSink::CR_EOM_RIGHT;
+    r.want_singles = false;
+    r.side = which == 0 ? 0 : 1;
+    walk_doubles(S, t, r);
+  }
+  {   // L: r0 * cr_ccsd_t_E + q3rexpt2_1, _2 (:400-419)
+    NativeSink l{c, *c->eng, S};
+    l.cr = NativeSink::CR_EOM_LEFT;
+    l.op_target = which == 0 ? Engine::OP_SINGLES : Engine::OP_SIDE0;
+    walk_cr_e1(S, t, l);
+    walk_singles(S, t, l, S.irrep_t ^ S.irrep_t ^ S.irrep_t);
+    if (which != 0) {
+      c->eng->set_two_sided();
+      NativeSink h{c, *c->eng, S};   // the half of L that plays the singles tile
+      h.cr = NativeSink::CR_EOM_LEFT;
+      h.op_target = Engine::OP_SINGLES;
+      h.op_mask = which == 1 ? 1 : 2;
+      walk_cr_e1(S, t, h);
+      walk_singles(S, t, h, S.irrep_t ^ S.irrep_t ^ S.irrep_t);
+    }
+  }
+  const double* eps[6];
+  if (which == 0) {
+    const double* e[6] = {c->d_evl_shift + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
+                          c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
+    for (int q = 0; q < 6; q++) eps[q] = e[q];
+  } else {
+    eps[0] = c->d_unit;
+    for (int q = 1; q < 6; q++) eps[q] = c->d_zero;
+  }
+  c->eng->end_tuple(eps, tuple_factor(S, t), item_lo, item_hi);   // cr_eomccsd_t.F:421-435 == ccsd_t_dot.F:52-66
 }
 
 // Double-buffered batch loop: while the GPU runs batch k the host walks the driver logic of batch k+1 into the other
@@ -1228,6 +1330,165 @@ int nwc_triples_run_cr_partition(nwc_triples_ctx* c, Integer rank, Integer nrank
   });
 }
 
+// ---- CR-EOMCCSD(T) (src/tce/cr-eomccsd_t/cr_eomccsd_t.F) ----
+// Inputs of the tuple loop :325-493 beyond T1/T2 and (when r0 != 0) the CR-CCSD(T) intermediates of nwc_triples_set_cr:
+// the right-hand amplitudes x1 / x2 (the T1 / T2 block structure), the four intermediates of creomsd_t_n2_mem (toggle 1:
+// d_i2_1..4; layouts of the CR ones: OFFSET_creomsd_t_n2_mem_{1,2,3,4}_1), the one of q3rexpt2 (d_i3_1, the T2 block
+// structure), r0 (r0xx, :134-141) and the excitation energy.  Call after set_state (and set_cr when |r0| >= 1e-7).
+static int fetch_host(nwc_triples_ctx* c, const double* dptr, size_t n, std::vector<double>& out) {
+  out.assign(n, 0.0);
+  if (!n) return 0;
+  if (c->eng->trace_only()) { memcpy(out.data(), dptr, n * sizeof(double)); return 0; }
+  NWC_TRY(cudaMemcpy(out.data(), dptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int nwc_triples_set_creom(nwc_triples_ctx* c, const Integer* x1_hash, const double* x1, const Integer* x2_hash, const double* x2,
+                          const Integer* m1_hash, const double* m1, const Integer* m2_hash, const double* m2,
+                          const Integer* m3_hash, const double* m3, const Integer* m4_hash, const double* m4,
+                          const Integer* q2_hash, const double* q2, double r0, double excit) {
+  return guarded(c, [&]() {
+    if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
+    const HostState& S = c->S;
+    if (!c->d_t1 || !c->d_t2) { g_err = "nwc_triples_set_creom: call nwc_triples_set_state first"; return 1; }
+    const bool lr0 = !(fabs(r0) < 1.0e-7);   // cr_eomccsd_t.F:146-147
+    if (lr0 && (!c->d_crn1 || !c->d_crn2 || !c->d_cre2)) { g_err = "nwc_triples_set_creom: r0 != 0 needs the CR-CCSD(T) intermediates (nwc_triples_set_cr)"; return 1; }
+    auto same = [](const Integer* h, const std::vector<Integer>& ref) {
+      if ((size_t)(2 * h[0] + 1) != ref.size()) return false;
+      for (size_t i = 0; i < ref.size(); i++) if (h[i] != ref[i]) return false;
+      return true;
+    };
+    if (!same(x1_hash, S.t1_hash) || !same(x2_hash, S.t2_hash) || !same(q2_hash, S.t2_hash))
+      throw Error("nwc_triples_set_creom: x1 / x2 / the q3rexpt2 intermediate must have the T1 / T2 / T2 block structure (irrep_x = 0)");
+    if (lr0 && !same(q2_hash, c->cre2_hash)) throw Error("nwc_triples_set_creom: the i1_tt and i1_xt offset tables differ");
+    c->eom_r0 = r0; c->eom_excit = excit; c->eom_lr0 = lr0;
+    c->x2_hash.assign(x2_hash, x2_hash + 2 * x2_hash[0] + 1);
+    c->m1_hash.assign(m1_hash, m1_hash + 2 * m1_hash[0] + 1); c->m2_hash.assign(m2_hash, m2_hash + 2 * m2_hash[0] + 1);
+    c->m3_hash.assign(m3_hash, m3_hash + 2 * m3_hash[0] + 1); c->m4_hash.assign(m4_hash, m4_hash + 2 * m4_hash[0] + 1);
+    c->eomz_hash.assign(q2_hash, q2_hash + 2 * q2_hash[0] + 1);
+    const size_t n1 = store_size(S.t1_hash.data(), S, 1), n2 = store_size(S.t2_hash.data(), S, 2);
+    // store sizes of the intermediates: same key decoding as nwc_triples_set_cr
+    auto cr_total = [&](const Integer* h, int kind) -> size_t {
+      const Integer nb = h[0];
+      if (nb <= 0) return 0;
+      Integer key = h[nb], sz = 0;
+      if (kind == 1) {
+        const Integer h2 = key % S.noab + 1; key /= S.noab; const Integer h1 = key % S.noab + 1; key /= S.noab;
+        const Integer h11 = key % S.noab + 1; key /= S.noab;
+        if (key < 0 || key >= S.nvab) throw Error("nwc_triples_set_creom: hphh offset table does not belong to this tiling");
+        sz = S.rg(key + S.noab + 1) * S.rg(h11) * S.rg(h1) * S.rg(h2);
+      } else {
+        const Integer p12 = key % S.nvab + S.noab + 1; key /= S.nvab; const Integer h1 = key % S.noab + 1; key /= S.noab;
+        const Integer p5 = key % S.nvab + S.noab + 1; key /= S.nvab;
+        if (key < 0 || key >= S.nvab) throw Error("nwc_triples_set_creom: pphp offset table does not belong to this tiling");
+        sz = S.rg(key + S.noab + 1) * S.rg(p5) * S.rg(h1) * S.rg(p12);
+      }
+      return (size_t)(h[2 * nb] + sz);
+    };
+    if (upload(&c->d_x2, &c->n_x2, x2, n2, c->eng)) return 1;
+    if (upload(&c->d_m1, &c->n_m1, m1, cr_total(m1_hash, 1), c->eng)) return 1;
+    if (upload(&c->d_m2, &c->n_m2, m2, cr_total(m2_hash, 2), c->eng)) return 1;
+    if (upload(&c->d_m3, &c->n_m3, m3, cr_total(m3_hash, 1), c->eng)) return 1;
+    if (upload(&c->d_m4, &c->n_m4, m4, cr_total(m4_hash, 2), c->eng)) return 1;
+    // left-hand outer products, combined once: r0*E_1(t2,t1) + q3rexpt2_1(t2,x1) = t2 x (r0*t1 + x1);
+    // r0*E_2 (twot = -+2/3, t1 x i1_tt) + q3rexpt2_2 (twot = -+2, t1 x i1_xt) = -+ t1 x (r0*(2/3)*i1_tt + 2*i1_xt)
+    std::vector<double>& y1 = c->eom_host[0];
+    std::vector<double>& z = c->eom_host[1];
+    std::vector<double> tmp;
+    y1.assign(x1, x1 + n1);
+    if (lr0) { if (fetch_host(c, c->d_t1, n1, tmp)) return 1; for (size_t i = 0; i < n1; i++) y1[i] += r0 * tmp[i]; }
+    z.assign(n2, 0.0);
+    for (size_t i = 0; i < n2; i++) z[i] = 2.0 * q2[i];
+    if (lr0) { if (fetch_host(c, c->d_cre2, n2, tmp)) return 1; for (size_t i = 0; i < n2; i++) z[i] += r0 * tmp[i]; }   // d_cre2 holds (2/3)*i1_tt
+    if (upload(&c->d_eomy1, &c->n_eomy1, y1.data(), n1, c->eng)) return 1;
+    if (upload(&c->d_eomz, &c->n_eomz, z.data(), n2, c->eng)) return 1;
+    // denominators: denex = Delta + omega (the h1 slot reads eps + omega), and unit denominators (1 for the h1 slot, 0 elsewhere)
+    std::vector<double>& es = c->eom_host[2];
+    std::vector<double>& un = c->eom_host[3];
+    std::vector<double>& ze = c->eom_host[4];
+    es = S.evl;
+    for (double& v : es) v += excit;
+    Integer maxr = 1;
+    for (Integer b = 1; b <= S.N(); b++) maxr = S.rg(b) > maxr ? S.rg(b) : maxr;
+    un.assign((size_t)maxr, 1.0);
+    ze.assign((size_t)maxr, 0.0);
+    if (upload(&c->d_evl_shift, &c->n_evl_shift, es.data(), es.size(), c->eng)) return 1;
+    if (upload(&c->d_unit, &c->n_unit, un.data(), un.size(), c->eng)) return 1;
+    if (upload(&c->d_zero, &c->n_zero, ze.data(), ze.size(), c->eng)) return 1;
+    if (!c->eng->trace_only()) for (auto& v : c->eom_host) { v.clear(); v.shrink_to_fit(); }
+    c->eom_set = true;
+    return 0;
+  });
+}
+
+// sums[4] = (A, B, C, D) = (sum f R R/denex, sum f L R, sum f L R/denex, sum f L L) over the tasks; the caller forms
+// num1 = A + B, den1 = C + D and energy1 = num1/(r0^2 + d12 + den1) (cr_eomccsd_t.F:455-464, :564) after the sum over ranks.
+static int run_creom_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, const std::vector<long long>* ranges,
+                         double sums[4], double* per_task) {
+  if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (!c->eom_set) { g_err = "nwc_triples_run_creom: call nwc_triples_set_creom first"; return 1; }
+  std::vector<double> ex(2 * ids.size() + 2, 0.0), ey(4 * ids.size() + 4, 0.0);
+  double dummy[2] = {0.0, 0.0};
+  {   // plain tuples: (A, A + C)
+    Pipeline pipe(c, dummy, ex.data());
+    for (size_t i = 0; i < ids.size(); i++) {
+      const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
+      if (ranges && b <= a) continue;
+      emit_tuple_creom(c, &c->klist[7 * (size_t)ids[i]], 0, a, b);
+      pipe.emitted((Integer)i);
+    }
+    pipe.finish();
+  }
+  {   // two-sided tuples with unit denominators: row 2i = Y1 -> (B, B + <L,La>), row 2i+1 = Y2 -> (0, <L,Lb>)
+    Pipeline pipe(c, dummy, ey.data());
+    for (size_t i = 0; i < ids.size(); i++) {
+      const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
+      if (ranges && b <= a) continue;
+      for (int w = 1; w <= 2; w++) {
+        emit_tuple_creom(c, &c->klist[7 * (size_t)ids[i]], w, a, b);
+        pipe.emitted((Integer)(2 * i + (w - 1)));
+      }
+    }
+    pipe.finish();
+  }
+  sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+  for (size_t i = 0; i < ids.size(); i++) {
+    const double A = ex[2 * i], C = ex[2 * i + 1] - ex[2 * i];
+    const double B = ey[4 * i], D = (ey[4 * i + 1] - ey[4 * i]) + ey[4 * i + 3];
+    const double row[4] = {A, B, C, D};
+    for (int q = 0; q < 4; q++) {
+      sums[q] += row[q];
+      if (per_task) per_task[4 * i + q] = row[q];
+    }
+  }
+  return 0;
+}
+
+int nwc_triples_run_creom(nwc_triples_ctx* c, Integer first, Integer stride, Integer max_tasks, double sums[4], double* per_task) {
+  return guarded(c, [&]() {
+    if (stride <= 0) stride = 1;
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    std::vector<Integer> ids;
+    for (Integer k = first < 0 ? 0 : first; k < nt && (max_tasks <= 0 || (Integer)ids.size() < max_tasks); k += stride) ids.push_back(k);
+    return run_creom_ids(c, ids, nullptr, sums, per_task);
+  });
+}
+
+int nwc_triples_run_creom_partition(nwc_triples_ctx* c, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
+                                    double sums[4], double* per_task) {
+  return guarded(c, [&]() {
+    const Integer nt = (Integer)(c->klist.size() / 7);
+    if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+    if (first_task < 0) first_task = 0;
+    if (ntasks <= 0 || first_task + ntasks > nt) ntasks = nt - first_task;
+    std::vector<Integer> ids;
+    for (Integer i = 0; i < ntasks; i++) ids.push_back(first_task + i);
+    std::vector<long long> ranges;
+    if (!ids.empty()) block_partition(c->S, c->klist, rank, nranks, ids, ranges);
+    return run_creom_ids(c, ids, &ranges, sums, per_task);
+  });
+}
+
 // ---- host-only trace (include/nwc_triples.h): the driver logic above, recorded instead of executed ----
 int nwc_triples_trace_tuple(nwc_triples_ctx* c, const Integer t[6], int method) {
   return guarded(c, [&]() {
@@ -1240,7 +1501,10 @@ int nwc_triples_trace_tuple(nwc_triples_ctx* c, const Integer t[6], int method) 
     } else if (method >= 2 && method <= 4) {
       if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_cr first"; return 1; }
       emit_tuple_cr(c, t, method - 2);
-    } else { g_err = "nwc_triples_trace_tuple: method must be 0..4"; return 1; }
+    } else if (method >= 5 && method <= 7) {
+      if (!c->eom_set) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_creom first"; return 1; }
+      emit_tuple_creom(c, t, method - 5);
+    } else { g_err = "nwc_triples_trace_tuple: method must be 0..7"; return 1; }
     return 0;
   });
 }

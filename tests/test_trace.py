@@ -60,9 +60,17 @@ def evaluate(recs):
     return tiles[0], tiles[1], tiles[2], float(end.scale), bool(end.K)
 
 
-def _energies(t, tup, w_tile, d_tile, s_tile, factor):
+def _eps_of(end, shape):
+    """the six orbital-energy vectors the tuple was emitted with (end record), in the order p4,p5,p6,h1,h2,h3"""
+    ptrs = [int(end.a), int(end.b), int(end.sb[2]), int(end.sb[3]), int(end.sb[4]), int(end.sb[5])]   # h1,h2,h3,p4,p5,p6
+    rng = {0: shape[3], 1: shape[4], 2: shape[5], 3: shape[0], 4: shape[1], 5: shape[2]}
+    v = [np.ctypeslib.as_array((C.c_double * rng[i]).from_address(ptrs[i])).copy() for i in range(6)]
+    return [v[3], v[4], v[5], v[0], v[1], v[2]]
+
+
+def _energies(t, tup, w_tile, d_tile, s_tile, factor, eps=None):
     """(sum f W D / Delta, sum f W (D + S) / Delta) as the fused kernel's energy pass forms them"""
-    e = [t.evl_sorted[t.offset[b - 1]:t.offset[b - 1] + t.range[b - 1]] for b in tup]
+    e = eps if eps is not None else [t.evl_sorted[t.offset[b - 1]:t.offset[b - 1] + t.range[b - 1]] for b in tup]
     delta = (-e[0][:, None, None, None, None, None] - e[1][None, :, None, None, None, None] - e[2][None, None, :, None, None, None]
              + e[3][None, None, None, :, None, None] + e[4][None, None, None, None, :, None] + e[5][None, None, None, None, None, :])
     return factor * np.sum(w_tile * d_tile / delta), factor * np.sum(w_tile * (d_tile + s_tile) / delta)
@@ -183,3 +191,45 @@ def test_trace_context_cannot_compute():
     with pytest.raises(RuntimeError):
         tr.set_state_2eorb(synth.physical(t, intorb=True))
     tr.close()
+
+
+@pytest.mark.parametrize("ts,restricted,r0", [(2, True, 0.37), (3, True, 0.0), (2, False, 0.37)])
+def test_creom_driver_trace_matches_oracle(oracle, ts, restricted, r0):
+    """CR-EOMCCSD(T): the three tuples the library emits per task (a plain tuple with shifted denominators, two two-sided
+    tuples with unit denominators), evaluated from the trace with the energy formulas of the kernel, give the four sums of
+    cr_eomccsd_t.F:455-464; the right / left tiles equal the oracle's."""
+    from oracle import cr_dense
+    t = tl.make_tiling(OCC, VIRT, ts, restricted)
+    st = synth.physical(t)
+    cr, q = cr_dense.DenseEOM(t, r0=r0).stores()
+    tr = capi.Triples(trace=True)
+    tr.set_state(st)
+    if abs(r0) >= 1e-7:
+        tr.set_cr(cr)
+    tr.set_creom(q)
+    n = 0
+    for tup in oracle.task_list(t)[::3]:
+        tup = [int(x) for x in tup[:6]]
+        sums_ref, r_ref, l_ref = oracle.cr_eom_tuple(st, cr, q, tup)
+        recs, keep = tr.trace_tuple(tup, 5)                         # X: plain, doubles = R, singles = L, denex
+        rt, _, lt, f, two = evaluate(recs)
+        assert not two and np.max(np.abs(rt - r_ref)) <= 1e-15 and np.max(np.abs(lt - l_ref)) <= 1e-15
+        eps = _eps_of(recs[-1], rt.shape)
+        ref_eps = [t.evl_sorted[t.offset[b - 1]:t.offset[b - 1] + t.range[b - 1]] for b in tup]
+        assert np.allclose(eps[3], ref_eps[3] + q.excit, rtol=0, atol=1e-15) and all(np.array_equal(eps[i], ref_eps[i]) for i in (0, 1, 2, 4, 5))
+        a, apc = _energies(t, tup, rt, rt, lt, f, eps)
+        recs, keep = tr.trace_tuple(tup, 6)                         # Y1: side 0 = L, side 1 = R, singles = La, unit denominators
+        l0, r1, la, f1, two = evaluate(recs)
+        eps1 = _eps_of(recs[-1], rt.shape)
+        assert two and np.array_equal(l0, lt) and np.array_equal(r1, rt) and f1 == f
+        assert all(np.all(eps1[i] == (1.0 if i == 3 else 0.0)) for i in range(6))
+        b, bpla = _energies(t, tup, l0, r1, la, f, eps1)
+        recs, keep = tr.trace_tuple(tup, 7)                         # Y2: side 0 = L, no contraction, singles = Lb
+        l2, z2, lb, f2, two = evaluate(recs)
+        assert two and np.array_equal(l2, lt) and not np.any(z2) and np.max(np.abs(la + lb - lt)) <= 1e-16
+        _, llb = _energies(t, tup, l2, z2, lb, f, _eps_of(recs[-1], rt.shape))
+        got = np.array([a, b, apc - a, (bpla - b) + llb])
+        assert np.max(np.abs(got - sums_ref)) <= 1e-13 * max(1.0, np.max(np.abs(sums_ref))), (got, sums_ref)
+        n += 1
+    tr.close()
+    assert n >= 5

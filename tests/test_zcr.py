@@ -198,3 +198,90 @@ def test_cr_one_pass_equals_two_pass(oracle, monkeypatch):
         assert np.max(np.abs(p1 - p2)) <= 1e-13 * scale, which
         assert np.max(np.abs(s1 - s2)) <= 1e-12 * max(1.0, np.max(np.abs(s2)))
         assert np.max(np.abs(sum(p[1] for p in parts) - p1)) <= 1e-13 * scale
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CR-EOMCCSD(T) (src/tce/cr-eomccsd_t/cr_eomccsd_t.F:325-493)
+# ------------------------------------------------------------------------------------------------------------------
+def test_creom_kernels_with_literal_factors_are_multiples_of_the_cr_kernels(oracle):
+    """cre_t_K with the factor lists of creomsd_t_n2_mem_2 / _4 == -2 x / +1 x sd_t_d2cp_K (what the oracle's and the
+    library's treatment of those routines as scaled cr_ccsd_t_N_2 rests on)."""
+    rng = np.random.default_rng(1)
+    dims = (3, 2, 4, 2, 3, 2)          # h3d,h2d,h1d,p6d,p5d,p4d
+    kd = 5
+    t2sub = rng.uniform(-1, 1, kd * dims[5] * dims[2] * dims[1])
+    v2sub = rng.uniform(-1, 1, kd * dims[0] * dims[3] * dims[4])
+    for k0 in range(9):
+        a, b, d = oracle.cre_t_vs_d2cp(k0, dims, kd, t2sub, v2sub)
+        assert np.max(np.abs(d)) > 0.1
+        assert np.max(np.abs(a + 2.0 * d)) <= 1e-14 and np.max(np.abs(b - d)) <= 1e-14
+
+
+def test_creom_tiled_oracle_equals_the_untiled_dense_evaluation(oracle):
+    from oracle import cr_dense
+    ref = {}
+    for ts, restricted, r0 in ((1, True, 0.37), (2, True, 0.37), (3, True, 0.0), (3, True, 0.37), (2, False, 0.37), (2, False, 0.0)):
+        t = tl.make_tiling(OCC, VIRT, ts, restricted)
+        st = synth.physical(t)
+        d = cr_dense.DenseEOM(t, r0=r0)
+        cr, q = d.stores()
+        r = oracle.cr_eomccsd_t(st, cr, q)
+        dense = np.array(d.dense_reference())
+        assert np.max(np.abs(r["sums"] - dense)) <= 1e-16, (ts, restricted, r0, r["sums"], dense)
+        assert np.min(np.abs(r["sums"])) > 1e-7
+        if r0 in ref:
+            assert np.max(np.abs(r["sums"] - ref[r0])) <= 1e-16
+        ref[r0] = r["sums"]
+    assert np.max(np.abs(ref[0.0] - ref[0.37])) > 1e-6          # the r0 terms matter
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ts,restricted,r0", [(None, 2, True, 0.37), (None, 3, True, 0.0), (None, 2, False, 0.37),
+                                                     ("h2o_ccpvdz_c2v", 20, True, 0.37)])
+def test_cr_eomccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, r0):
+    from nwchem_b200 import capi
+    from oracle import cr_dense
+    t = tl.make_tiling(OCC, VIRT, ts, restricted) if shape is None else synth.shape_tiling(shape, tilesize=ts, restricted=restricted)
+    st = synth.physical(t)
+    cr, q = cr_dense.DenseEOM(t, r0=r0).stores()
+    ref = oracle.cr_eomccsd_t(st, cr, q)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    if abs(r0) >= 1e-7:
+        tr.set_cr(cr)
+    tr.set_creom(q)
+    sums, pt = tr.run_creom(per_task=True)
+    got = _sorted_rows(tr, pt)
+    parts = [tr.run_creom_partition(r, 2, per_task=True) for r in range(2)]
+    tr.close()
+    scale = max(1.0, np.max(np.abs(ref["per_task"])))
+    assert np.max(np.abs(got - ref["per_task"])) <= 1e-12 * scale
+    assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-9
+    assert np.max(np.abs(sum(p[0] for p in parts) - sums)) <= 1e-13
+    assert np.max(np.abs(sum(p[1] for p in parts) - pt)) <= 1e-13 * scale
+
+
+@pytest.mark.gpu
+def test_cr_eomccsd_t_ragged_and_random_blocks(oracle):
+    from nwchem_b200 import capi
+    from oracle import cr_dense
+    t = tl.make_tiling([5], [11], 6)
+    st = synth.random_blocks(t, seed=11)
+    rng = np.random.default_rng(5)
+    n1h, n1 = tl.cr_n1_offset(t); n2h, n2 = tl.cr_n2_offset(t); e2h, e2 = tl.cr_e2_offset(t)
+    r = lambda n, s: rng.uniform(-1, 1, n) * s
+    cr = cr_dense.CRStores(n1h, r(n1, 0.1), n2h, r(n2, 0.1), e2h, r(e2, 0.02), 0.0)
+    q = cr_dense.CREOMStores(st.t1_hash, r(len(st.t1), 0.05), st.t2_hash, r(len(st.t2), 0.02), n1h, r(n1, 0.1), n2h, r(n2, 0.1),
+                             n1h, r(n1, 0.1), n2h, r(n2, 0.1), e2h, r(e2, 0.02), -0.6, 0.3)
+    ref = oracle.cr_eomccsd_t(st, cr, q)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    tr.set_cr(cr)
+    tr.set_creom(q)
+    sums, pt = tr.run_creom(per_task=True)
+    got = _sorted_rows(tr, pt)
+    tr.close()
+    scale = max(1.0, np.max(np.abs(ref["per_task"])))
+    assert np.max(np.abs(ref["per_task"])) > 1e-8
+    assert np.max(np.abs(got - ref["per_task"])) <= 1e-11 * scale
+    assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-9
