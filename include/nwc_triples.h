@@ -317,7 +317,7 @@ int nwc_triples_run_cr(nwc_triples_ctx *ctx, Integer first, Integer stride, Inte
 /* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_sum, n = 4) */
 int nwc_triples_run_cr_partition(nwc_triples_ctx *ctx, Integer rank, Integer nranks, Integer first_task, Integer ntasks,
                                  double sums[4], double *per_task);
-/* CR-EOMCCSD(T) (src/tce/cr-eomccsd_t/cr_eomccsd_t.F, tce_energy.F:8787-8798): the tuple loop :325-493.  Its six per-tuple
+/* CR-EOMCCSD(T) (src/tce/cr-eomccsd_t/cr_eomccsd_t.F, tce_energy.F:8775-8786): the tuple loop :325-493.  Its six per-tuple
  * routines are the CR-CCSD(T) ones with other operands and constant factors (creomsd_t_n2_mem_1..4 == cr_ccsd_t_N_1/_N_2 on
  * (t2 | x2) x (d_i2_1..4), creomccsd_t_n2_mem.F:674,:5665,:9657,:12905; q3rexpt2_1/_2 == cr_ccsd_t_E_1/_E_2 on (t2, x1) and
  * (t1, d_i3_1), q3rexpt2.F:80,:414).  Per tuple: right = r0*cr_ccsd_t_N + creomsd_t_n2_mem, left = r0*cr_ccsd_t_E + q3rexpt2,
