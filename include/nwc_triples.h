@@ -163,7 +163,7 @@ int nwc_triples_destroy(nwc_triples_ctx *ctx);
  * hands to the engine are recorded instead of being packed and launched.  set_state (replicated spin-orbital stores
  * only), set_lambda and set_cr keep the caller's host arrays by reference; trace_tuple records one tuple
  * (method 0: (T), 1: Lambda-CCSD(T), 2 / 3: CR-CCSD(T) numerator / denominator pass of the two-pass form, 4: the one-pass
- * dual tuple, 5 / 6 / 7: the three tuples of CR-EOMCCSD(T)); trace_take hands the records
+ * dual tuple, 5 / 6 / 7: the three tuples of the composed form of CR-EOMCCSD(T), 8: its one-tuple form); trace_take hands the records
  * out.  Every compute entry point fails on a trace context.  It exists so the CPU test-suite can check the driver half
  * against the oracle's tiles without a GPU (tests/test_trace.py); the pointers in the records are the caller's. */
 typedef struct {
@@ -172,7 +172,8 @@ typedef struct {
   Integer side;        /* kinds 1,2: 0 = the tuple's doubles tile, 1 = the second tile of a two-sided tuple;
                           kind 3: 0 = singles tile, 1 = side-1 tile, 2 = side-0 tile */
   Integer K;           /* contracted range (kinds 1,2); kind 9: 1 if the tuple is two-sided, 2 if it is a dual-energy
-                          tuple (the side-0 outer products form a fourth tile of their own) */
+                          tuple (the side-0 outer products form a fourth tile of their own), 3 for the CR-EOMCCSD(T)
+                          form of a dual tuple (side 1 = R, singles = L) */
   Integer neg;         /* kind 3: 1 = subtract */
   const double *a;     /* kinds 0-2: t1sub / t2sub source; kind 3: the two-index operand */
   const double *b;     /* kinds 0-2: v2sub source; kind 3: the four-index operand */

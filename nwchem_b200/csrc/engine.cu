@@ -165,6 +165,7 @@ void Engine::begin_tuple(const int R_phys[6]) {
     for (int s = 0; s < 9; s++) cur_descs_[side][s].clear();
   two_sided_ = false;
   dual_ = false;
+  eom_ = false;
   cur_sd_singles_.clear();
   cur_sd_doubles_.clear();
   cur_sd_side0_.clear();
@@ -313,7 +314,7 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
   if (!open_) throw Error("nwc_triples: end_tuple without begin_tuple");
   if (trace_only()) {
     nwc_trace_rec r{};
-    r.kind = 9; r.K = two_sided_ ? (dual_ ? 2 : 1) : 0; r.scale = factor;
+    r.kind = 9; r.K = two_sided_ ? (dual_ ? (eom_ ? 3 : 2) : 1) : 0; r.scale = factor;
     for (int q = 0; q < 6; q++) r.sa[q] = cur_hdr_.R[q];
     r.sb[0] = item_lo; r.sb[1] = item_hi;
     r.a = eps[0]; r.b = eps[1];                                   // orbital-energy vectors: h1, h2, ...
@@ -343,6 +344,10 @@ void Engine::end_tuple(const double* const eps[6], double factor, long long item
   cur_hdr_.desc2_begin[9] = n;
   if (!two_sided_ && !cur_sd_side0_.empty()) { open_ = false; throw Error("nwc_triples: side-0 outer products need a two-sided tuple"); }
   cur_hdr_.two_sided = two_sided_ ? 1 + (int)cur_sd_side0_.size() : 0;   // kernels.cuh TupleHdr
+  if (eom_) {
+    if (!cur_sd_side0_.empty() || !cur_sd_doubles_.empty()) { open_ = false; throw Error("nwc_triples: a CR-EOMCCSD(T) tuple takes its outer products in the singles tile"); }
+    cur_hdr_.two_sided += 64;
+  }
   if (dual_) cur_hdr_.two_sided = -cur_hdr_.two_sided;
   cur_hdr_.sdesc_begin = (int)sdescs_.size();
   sdescs_.insert(sdescs_.end(), cur_sd_side0_.begin(), cur_sd_side0_.end());

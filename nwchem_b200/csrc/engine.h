@@ -116,6 +116,9 @@ class Engine {
   // being added to the side-0 tile M, and the kernel returns two energy pairs, (<M,D>, <M,D+S>) and (<E,D>, <E,D+S>).
   // A batch holds only dual tuples or none; its results come out as [pair 0 of every tuple | pair 1 of every tuple].
   void set_dual() { two_sided_ = true; dual_ = true; }
+  // CR-EOMCCSD(T) form of a dual tuple: ONE contraction tile R (side 1) and the outer-product tile L (singles); pair 0 =
+  // (<R,R>, <R,R+L>) with the tuple's denominators, pair 1 = (sum f L R, sum f L (R+L)) without denominators
+  void set_dual_eom() { two_sided_ = true; dual_ = true; eom_ = true; }
   // one contracted tile on its own (K7 = its range)
   void add_contraction(int family, int k0, int K7, const OperandView& tsub, const OperandView& v2sub, double tscale = 1.0) {
     Segment sg;
@@ -182,7 +185,7 @@ class Engine {
   bool open_ = false;
   TupleHdr cur_hdr_{};
   std::vector<ContrDesc> cur_descs_[2][9];
-  bool two_sided_ = false, dual_ = false;
+  bool two_sided_ = false, dual_ = false, eom_ = false;
   std::vector<TupleHdr> tuples_;
   std::vector<ContrDesc> descs_;
   std::vector<SinglesDesc> sdescs_;

@@ -589,10 +589,11 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     const int nmid = T.sdesc_mid - T.sdesc_begin;
     sm.nsd_mid = nmid < 0 ? 0 : (nmid < sm.nsd ? nmid : sm.nsd);
     if (CRX) {
-      const int ts = T.two_sided;             // 1 + n0, negative for dual-energy tuples (kernels.cuh TupleHdr)
-      const int n0 = (ts < 0 ? -ts : ts) - 1;
+      const int ts = T.two_sided;             // +-(1 + n0 + 64*eom), negative for dual-energy tuples (kernels.cuh TupleHdr)
+      const int mag = (ts < 0 ? -ts : ts) - 1;
+      const int n0 = mag & 63;
       lm.nsd_mid0 = n0 < 0 ? 0 : (n0 < sm.nsd_mid ? n0 : sm.nsd_mid);
-      lm.dual = ts < 0 ? 1 : 0;
+      lm.dual = ts < 0 ? (1 + ((mag >> 6) & 1)) : 0;   // 1: CR-CCSD(T) dual tuple; 2: CR-EOMCCSD(T) tuple
     }
     sm.zero = 0;
   }
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
   for (int grp = CRX ? -1 : (LAMBDA ? 0 : 1); grp < 2; grp++) {
     int glo, ghi;
     if (!CRX) { glo = (!LAMBDA || grp == 0) ? 0 : sm.nsd_mid; ghi = (LAMBDA && grp == 0) ? sm.nsd_mid : nsd; }
-    else if (grp < 0) { glo = 0; ghi = lm.dual ? 0 : lm.nsd_mid0; }   // dual tuples: these terms get their own pass below
+    else if (grp < 0) { glo = 0; ghi = lm.dual == 1 ? 0 : lm.nsd_mid0; }   // dual tuples: these terms get their own pass below
     else if (grp == 0) { glo = lm.nsd_mid0; ghi = sm.nsd_mid; }
     else { glo = sm.nsd_mid; ghi = nsd; }
     if (ghi <= glo) continue;
@@ -844,6 +845,7 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     for (int u = 0; u < 8; u++) {
       dd[u] = sm.canon[At ^ canon_swz((j0 + u) << 6)];
       td[u] = LAMBDA ? lm.canon2[At ^ canon_swz((j0 + u) << 6)] : dd[u];   // Lambda-CCSD(T): w = f*Td/Delta, E1 += w*Yd
+      if (CRX && lm.dual == 2) td[u] = dd[u];   // CR-EOMCCSD(T): one contraction tile R on both sides, <R,R> and <R,R+L>
       rr[u] = sm.dp[warp][j0 + u];
     }
 #pragma unroll
@@ -896,7 +898,32 @@ __global__ void __launch_bounds__(NTHREADS, LAMBDA ? 2 : NWC_CTAS_PER_SM)
     // terms [0, nsd_mid0) -- the denominator tile E of cr_ccsd_t_E -- are accumulated in registers, and a second energy
     // pass forms den1 = <E,D>, den2 = <E,S+D>.  They go to the partial slot `gridDim.x` work items further on: the host
     // appends one shadow tuple per tuple there, so the reduction needs no special case.
-    if (lm.dual) {
+    // CR-EOMCCSD(T) tuples (dual == 2, cr_eomccsd_t.F:455-464): canon = the right tile R, sing = the left tile L, and
+    // the sums above are <R,R>/denex-type.  The second pair needs no further tile, only NO denominator:
+    // sum f L R and sum f L (R + L).
+    if (lm.dual == 2) {
+      double d1 = 0.0, d2s = 0.0;
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        double dd[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) dd[u] = sm.canon[At ^ canon_swz((j0 + u) << 6)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) d1 = fma(sing[j0 + u], dd[u], d1);
+#pragma unroll
+        for (int u = 0; u < 8; u++) d2s = fma(sing[j0 + u], sing[j0 + u], d2s);
+      }
+      double d2 = d1 + d2s;
+      d1 *= T.factor;
+      d2 *= T.factor;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      }
+      if (lane == 0) partials[((long long)gridDim.x + item) * (NCONSUMERS / 32) + warp] = make_double2(d1, d2);
+    }
+    if (lm.dual == 1) {
       __syncwarp();
 #pragma unroll
       for (int jj = 0; jj < 32; jj++) {

@@ -47,8 +47,11 @@ struct TupleHdr {
   int sdesc_begin, sdesc_end;
   int sdesc_mid;        // outer-product terms [sdesc_begin, sdesc_mid) are added to the DOUBLES tiles, the rest are the singles
   int two_sided;        // 0: plain (T).  1 + n0: two-sided tuple (Lambda-/CR-CCSD(T)): desc2_begin lists the side-1
-                        // contractions, the energy pairs the two tiles, and the first n0 outer-product terms
-                        // [sdesc_begin, sdesc_begin + n0) belong to the SIDE-0 tile, [.., sdesc_mid) to the side-1 tile
+                        // contractions, the energy pairs the two tiles, and the first n0 (< 64) outer-product terms
+                        // [sdesc_begin, sdesc_begin + n0) belong to the SIDE-0 tile, [.., sdesc_mid) to the side-1 tile.
+                        // Negative: dual-energy tuple, two energy pairs (engine.h set_dual); -(1 + n0 + 64): the
+                        // CR-EOMCCSD(T) form of it (one contraction tile R in side 1, L in the singles tile:
+                        // pair 0 = (<R,R>, <R,R+L>) over denex, pair 1 = (sum f L R, sum f L (R+L)) undenominated)
   int desc2_begin[10];  // split s of the left-hand side owns descs [desc2_begin[s], desc2_begin[s+1])
   long long item_begin; // first work item (sub-tile) of this tuple in the launch
   int nitems;            // work items of this launch (a sub-range when the tuple is split across GPUs)

@@ -555,14 +555,16 @@ void emit_tuple_cr(nwc_triples_ctx* c, const Integer t[6], int pass, long long i
 //   which 1 "Y1": two-sided tuple with UNIT denominators (eps = 1 for the h1 slot, 0 elsewhere): side 0 = L (outer
 //                 products bound to it), side 1 = R, singles = the t2 x (r0 t1 + x1) half of L -> (B, B + <L,La>)
 //   which 2 "Y2": two-sided, unit denominators, no contraction: side 0 = L, singles = the other half of L -> (0, <L,Lb>)
-// so D = <L,La> + <L,Lb>.  R is contracted twice (once at the plain kernel's 3 CTAs/SM); a kernel with an undenominated
-// second energy pass would need it once.
+// so D = <L,La> + <L,Lb>.  R is contracted twice (once at the plain kernel's 3 CTAs/SM): NWC_CREOM_COMPOSED=1.
+//   which 3, the default: ONE dual-energy tuple in its CR-EOMCCSD(T) form (engine.h set_dual_eom): side 1 = R, singles = L,
+//                 shifted orbital energies; the kernel returns (A, A + C) and, from an undenominated second energy pass
+//                 over the same two tiles, (B, B + D).  R is contracted once.
 void emit_tuple_creom(nwc_triples_ctx* c, const Integer t[6], int which, long long item_lo = 0, long long item_hi = -1) {
   const HostState& S = c->S;
   int R[6];
   tuple_ranges(S, t, R);
   c->eng->begin_tuple(R);
-  if (which == 0 || which == 1) {   // R: r0 * cr_ccsd_t_N + creomsd_t_n2_mem_1..4 (cr_eomccsd_t.F:377-395)
+  if (which == 0 || which == 1 || which == 3) {   // R: r0 * cr_ccsd_t_N + creomsd_t_n2_mem_1..4 (cr_eomccsd_t.F:377-395)
     NativeSink r{c, *c->eng, S};
     r.cr = NativeSink::CR_EOM_RIGHT;
     r.want_singles = false;
@@ -572,10 +574,11 @@ void emit_tuple_creom(nwc_triples_ctx* c, const Integer t[6], int which, long lo
   {   // L: r0 * cr_ccsd_t_E + q3rexpt2_1, _2 (:400-419)
     NativeSink l{c, *c->eng, S};
     l.cr = NativeSink::CR_EOM_LEFT;
-    l.op_target = which == 0 ? Engine::OP_SINGLES : Engine::OP_SIDE0;
+    l.op_target = (which == 0 || which == 3) ? Engine::OP_SINGLES : Engine::OP_SIDE0;
     walk_cr_e1(S, t, l);
     walk_singles(S, t, l, S.irrep_t ^ S.irrep_t ^ S.irrep_t);
-    if (which != 0) {
+    if (which == 3) c->eng->set_dual_eom();
+    if (which == 1 || which == 2) {
       c->eng->set_two_sided();
       NativeSink h{c, *c->eng, S};   // the half of L that plays the singles tile
       h.cr = NativeSink::CR_EOM_LEFT;
@@ -586,7 +589,7 @@ void emit_tuple_creom(nwc_triples_ctx* c, const Integer t[6], int which, long lo
     }
   }
   const double* eps[6];
-  if (which == 0) {
+  if (which == 0 || which == 3) {
     const double* e[6] = {c->d_evl_shift + S.offset[t[3] - 1], c->d_evl + S.offset[t[4] - 1], c->d_evl + S.offset[t[5] - 1],
                           c->d_evl + S.offset[t[0] - 1], c->d_evl + S.offset[t[1] - 1], c->d_evl + S.offset[t[2] - 1]};
     for (int q = 0; q < 6; q++) eps[q] = e[q];
@@ -1429,6 +1432,27 @@ static int run_creom_ids(nwc_triples_ctx* c, const std::vector<Integer>& ids, co
   if (!c->eom_set) { g_err = "nwc_triples_run_creom: call nwc_triples_set_creom first"; return 1; }
   std::vector<double> ex(2 * ids.size() + 2, 0.0), ey(4 * ids.size() + 4, 0.0);
   double dummy[2] = {0.0, 0.0};
+  const char* cm = getenv("NWC_CREOM_COMPOSED");
+  if (!(cm && *cm == '1')) {   // one dual-energy tuple per task: rows of four = (A, A + C, B, B + D)
+    Pipeline pipe(c, dummy, ey.data());
+    pipe.dual = true;
+    for (size_t i = 0; i < ids.size(); i++) {
+      const long long a = ranges ? (*ranges)[2 * i] : 0, b = ranges ? (*ranges)[2 * i + 1] : -1;
+      if (ranges && b <= a) continue;
+      emit_tuple_creom(c, &c->klist[7 * (size_t)ids[i]], 3, a, b);
+      pipe.emitted((Integer)i);
+    }
+    pipe.finish();
+    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    for (size_t i = 0; i < ids.size(); i++) {
+      const double row[4] = {ey[4 * i], ey[4 * i + 2], ey[4 * i + 1] - ey[4 * i], ey[4 * i + 3] - ey[4 * i + 2]};
+      for (int q = 0; q < 4; q++) {
+        sums[q] += row[q];
+        if (per_task) per_task[4 * i + q] = row[q];
+      }
+    }
+    return 0;
+  }
   {   // plain tuples: (A, A + C)
     Pipeline pipe(c, dummy, ex.data());
     for (size_t i = 0; i < ids.size(); i++) {
@@ -1501,10 +1525,10 @@ int nwc_triples_trace_tuple(nwc_triples_ctx* c, const Integer t[6], int method) 
     } else if (method >= 2 && method <= 4) {
       if (!c->d_crn1 || !c->d_crn2 || !c->d_cre2) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_cr first"; return 1; }
       emit_tuple_cr(c, t, method - 2);
-    } else if (method >= 5 && method <= 7) {
+    } else if (method >= 5 && method <= 8) {
       if (!c->eom_set) { g_err = "nwc_triples_trace_tuple: call nwc_triples_set_creom first"; return 1; }
       emit_tuple_creom(c, t, method - 5);
-    } else { g_err = "nwc_triples_trace_tuple: method must be 0..7"; return 1; }
+    } else { g_err = "nwc_triples_trace_tuple: method must be 0..8"; return 1; }
     return 0;
   });
 }

@@ -230,6 +230,17 @@ def test_creom_driver_trace_matches_oracle(oracle, ts, restricted, r0):
         _, llb = _energies(t, tup, l2, z2, lb, f, _eps_of(recs[-1], rt.shape))
         got = np.array([a, b, apc - a, (bpla - b) + llb])
         assert np.max(np.abs(got - sums_ref)) <= 1e-13 * max(1.0, np.max(np.abs(sums_ref))), (got, sums_ref)
+        # the one-tuple form (default of nwc_triples_run_creom): a dual-energy tuple, side 1 = R, singles = L, denex;
+        # the kernel's second pair is undenominated
+        recs, keep = tr.trace_tuple(tup, 8)
+        z0, r8, l8, f8, two = evaluate(recs)
+        assert int(recs[-1].K) == 3 and two and not np.any(z0) and np.array_equal(r8, rt) and np.array_equal(l8, lt) and f8 == f
+        eps8 = _eps_of(recs[-1], rt.shape)
+        assert all(np.array_equal(eps8[i], eps[i]) for i in range(6))
+        a8, apc8 = _energies(t, tup, r8, r8, l8, f, eps8)
+        b8, bpd8 = f * np.sum(l8 * r8), f * np.sum(l8 * (r8 + l8))
+        got8 = np.array([a8, b8, apc8 - a8, bpd8 - b8])
+        assert np.max(np.abs(got8 - sums_ref)) <= 1e-13 * max(1.0, np.max(np.abs(sums_ref)))
         n += 1
     tr.close()
     assert n >= 5

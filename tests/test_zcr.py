@@ -253,8 +253,15 @@ def test_cr_eomccsd_t_gpu_matches_oracle(oracle, shape, ts, restricted, r0):
     sums, pt = tr.run_creom(per_task=True)
     got = _sorted_rows(tr, pt)
     parts = [tr.run_creom_partition(r, 2, per_task=True) for r in range(2)]
+    import os
+    os.environ["NWC_CREOM_COMPOSED"] = "1"      # A/B: the form composed of a plain tuple and two unit-denominator tuples
+    try:
+        sums_c, pt_c = tr.run_creom(per_task=True)
+    finally:
+        del os.environ["NWC_CREOM_COMPOSED"]
     tr.close()
     scale = max(1.0, np.max(np.abs(ref["per_task"])))
+    assert np.max(np.abs(pt_c - pt)) <= 1e-12 * scale
     assert np.max(np.abs(got - ref["per_task"])) <= 1e-12 * scale
     assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-9
     assert np.max(np.abs(sum(p[0] for p in parts) - sums)) <= 1e-13

@@ -32,14 +32,23 @@ tr.set_state(st)
 tr.set_cr(cr)
 tr.set_creom(q)
 res = {}
-for name, fn in (("(T)", lambda: tr.run(max_tasks=max_tasks)), ("CR-EOM-(T)", lambda: tr.run_creom(max_tasks=max_tasks))):
+def composed():
+    os.environ["NWC_CREOM_COMPOSED"] = "1"
+    try:
+        return tr.run_creom(max_tasks=max_tasks)
+    finally:
+        del os.environ["NWC_CREOM_COMPOSED"]
+
+
+for name, fn in (("(T)", lambda: tr.run(max_tasks=max_tasks)), ("CR-EOM-(T)", lambda: tr.run_creom(max_tasks=max_tasks)),
+                 ("CR-EOM-(T) composed", composed)):
     fn()
     tr.set_timing(True); tr.stats(reset=True)
     t0 = time.time(); e = fn(); dt = time.time() - t0
     s = tr.stats()
     res[name] = dict(shape=shape, wall_s=dt, fused_ms=s["fused_ms"], flops=s["flops"], tflops=s["flops"] / dt * 1e-12,
                      launches=int(s["fused_launches"]), result=[float(x) for x in np.ravel(e)])
-    print(f"{name:11s} {shape}: {dt:.3f} s wall, fused {s['fused_ms']:.1f} ms, executed {s['flops']:.3e} FLOP = "
+    print(f"{name:19s} {shape}: {dt:.3f} s wall, fused {s['fused_ms']:.1f} ms, executed {s['flops']:.3e} FLOP = "
           f"{s['flops'] / dt * 1e-12:.2f} TFLOP/s, launches {int(s['fused_launches'])}, result {e}", flush=True)
 if out:
     json.dump(res, open(out, "w"), indent=1)
