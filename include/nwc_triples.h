@@ -313,6 +313,16 @@ int nwc_triples_run_lambda_partition(nwc_triples_ctx *ctx, Integer rank, Integer
  * the sum over ranks and forms CR-CCSD[T] = num1/(1+den1+den0), CR-CCSD(T) = num2/(1+den2+den0) (:260-263). */
 int nwc_triples_set_cr(nwc_triples_ctx *ctx, const Integer *n1_hash, const double *n1, const Integer *n2_hash,
                        const double *n2, const Integer *e2_hash, const double *e2);
+/* The pphp intermediate is as large as V2's <pp||hp> class (2.5*o*v^3 doubles), so like V2 it can be dealt over the GPUs:
+ * block i of its offset table lives on rank i % nranks and n2_shard holds THIS rank's blocks only (table order,
+ * compacted); the hphh and pphh intermediates stay replicated.  Then exchange the shards exactly as for a sharded V2:
+ * cr_ipc_handle (64 bytes) all-gathered + cr_open_peers, or inside one process cr_shard_ptr / cr_set_peer_ptr. */
+int nwc_triples_set_cr_sharded(nwc_triples_ctx *ctx, const Integer *n1_hash, const double *n1, const Integer *n2_hash,
+                               const double *n2_shard, const Integer *e2_hash, const double *e2, int rank, int nranks);
+int nwc_triples_cr_ipc_handle(nwc_triples_ctx *ctx, char handle64[64]);
+int nwc_triples_cr_open_peers(nwc_triples_ctx *ctx, const char *handles);
+void *nwc_triples_cr_shard_ptr(nwc_triples_ctx *ctx);
+int nwc_triples_cr_set_peer_ptr(nwc_triples_ctx *ctx, int rank, void *dev_ptr);
 int nwc_triples_run_cr(nwc_triples_ctx *ctx, Integer first, Integer stride, Integer max_tasks, double sums[4],
                        double *per_task);
 /* the same over the static block partition of nwc_triples_run_partition (combine with nwc_triples_allreduce_sum, n = 4) */

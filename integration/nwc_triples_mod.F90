@@ -328,6 +328,26 @@ module nwc_triples_mod
       integer(c_long), intent(in) :: n1_hash(*), n2_hash(*), e2_hash(*)
       real(c_double), intent(in) :: n1(*), n2(*), e2(*)
     end function
+    ! the same with the pphp intermediate d_i1_2 dealt over the ranks (block i of k_i1_offset_2 -> rank mod(i,nranks));
+    ! exchange the shards with nwc_triples_cr_ipc_handle / nwc_triples_cr_open_peers as for a sharded V2
+    integer(c_int) function nwc_triples_set_cr_sharded(ctx, n1_hash, n1, n2_hash, n2_shard, e2_hash, e2, rank, nranks) &
+        bind(C, name='nwc_triples_set_cr_sharded')
+      import :: c_int, c_ptr, c_long, c_double
+      type(c_ptr), value :: ctx
+      integer(c_long), intent(in) :: n1_hash(*), n2_hash(*), e2_hash(*)
+      real(c_double), intent(in) :: n1(*), n2_shard(*), e2(*)
+      integer(c_int), value :: rank, nranks
+    end function
+    integer(c_int) function nwc_triples_cr_ipc_handle(ctx, handle) bind(C, name='nwc_triples_cr_ipc_handle')
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char) :: handle(64)
+    end function
+    integer(c_int) function nwc_triples_cr_open_peers(ctx, handles) bind(C, name='nwc_triples_cr_open_peers')
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: handles(*)
+    end function
     integer(c_int) function nwc_triples_run_cr_partition(ctx, rank, nranks, first_task, ntasks, sums, per_task) &
         bind(C, name='nwc_triples_run_cr_partition')
       import :: c_int, c_ptr, c_long, c_double

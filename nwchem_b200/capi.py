@@ -341,6 +341,35 @@ class Triples:
         if self.is_trace:
             self._keep.append(k)
 
+    def set_cr_sharded(self, cr, rank: int, world: int):
+        """As set_cr, but cr.n2 holds only this rank's blocks of the pphp intermediate (synth.shard_store); afterwards
+        exchange cr_shard_ptr / cr_set_peer_ptr (one process) or cr_ipc_handle / cr_open_peers (one process per GPU)."""
+        k = [np.ascontiguousarray(a, np.int64 if i % 2 == 0 else np.float64)
+             for i, a in enumerate((cr.n1_hash, cr.n1, cr.n2_hash, cr.n2, cr.e2_hash, cr.e2))]
+        l = lib()
+        l.nwc_triples_set_cr_sharded.argtypes = [C.c_void_p, PL, PD, PL, PD, PL, PD, C.c_int, C.c_int]
+        _check(l.nwc_triples_set_cr_sharded(self._h, _pl(k[0]), _pd(k[1]), _pl(k[2]), _pd(k[3]), _pl(k[4]), _pd(k[5]), rank, world),
+               "nwc_triples_set_cr_sharded")
+
+    def cr_shard_ptr(self) -> int:
+        lib().nwc_triples_cr_shard_ptr.restype = C.c_void_p
+        lib().nwc_triples_cr_shard_ptr.argtypes = [C.c_void_p]
+        return int(lib().nwc_triples_cr_shard_ptr(self._h) or 0)
+
+    def cr_set_peer_ptr(self, rank: int, ptr: int):
+        lib().nwc_triples_cr_set_peer_ptr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _check(lib().nwc_triples_cr_set_peer_ptr(self._h, rank, C.c_void_p(ptr)), "nwc_triples_cr_set_peer_ptr")
+
+    def cr_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        lib().nwc_triples_cr_ipc_handle.argtypes = [C.c_void_p, C.c_char_p]
+        _check(lib().nwc_triples_cr_ipc_handle(self._h, buf), "nwc_triples_cr_ipc_handle")
+        return buf.raw
+
+    def cr_open_peers(self, handles: bytes):
+        lib().nwc_triples_cr_open_peers.argtypes = [C.c_void_p, C.c_char_p]
+        _check(lib().nwc_triples_cr_open_peers(self._h, handles), "nwc_triples_cr_open_peers")
+
     def run_cr(self, first=0, stride=1, max_tasks=0, per_task=False):
         """CR-CCSD(T) tuple loop (cr_ccsd_t.F:93-233): sums = (num1, num2, den1, den2) without den0 [, per_task[n,4]]."""
         s = np.zeros(4)

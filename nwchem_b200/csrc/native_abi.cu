@@ -52,6 +52,24 @@ struct Nccl {
 const int NCCL_DOUBLE = 8, NCCL_SUM = 0;  // ncclFloat64, ncclSum (nccl.h)
 }  // namespace
 
+// A block store dealt block-wise over the ranks: block i of its offset table lives on rank i % nshards, compacted in
+// table order; remote blocks are pulled whole into the batch arena (pull_kernel), cached per batch slot.  The V2 store
+// has its own, older copy of this bookkeeping in the context (v2_*); this one serves the CR-CCSD(T) pphp intermediate.
+struct PeerStore {
+  int nshards = 1, rank = 0;
+  std::vector<Integer> shard_off, block_n;
+  std::vector<double*> peer;
+  std::vector<char> opened;
+  std::unordered_map<Integer, const double*> pulled[2];
+  void reset() {
+    for (size_t r = 0; r < peer.size(); r++)
+      if (opened[r] && peer[r]) cudaIpcCloseMemHandle(peer[r]);
+    nshards = 1; rank = 0;
+    shard_off.clear(); block_n.clear(); peer.clear(); opened.clear();
+    pulled[0].clear(); pulled[1].clear();
+  }
+};
+
 struct nwc_triples_ctx {
   Engine* eng = nullptr;
   HostState S;
@@ -83,6 +101,7 @@ struct nwc_triples_ctx {
   size_t n_crn1 = 0, n_crn2 = 0, n_cre2 = 0;
   std::vector<Integer> crn1_hash, crn2_hash, cre2_hash;
   std::vector<double> cre2_scaled;          // trace contexts keep host data by reference: the 2/3-scaled copy lives here
+  PeerStore crn2s;                          // nwc_triples_set_cr_sharded: the pphp intermediate (the size of V2's <pp||hp> class) dealt over the ranks
   // CR-EOMCCSD(T) inputs (nwc_triples_set_creom): x amplitudes, the four moment intermediates, and two combined stores
   // for the left-hand outer products (eomy1 = r0*t1 + x1, eomz = r0*(2/3)*i1_tt + 2*i1_xt); eps vectors for the shifted
   // and the unit denominators
@@ -120,6 +139,7 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
   c->v2_nshards = 1; c->v2_rank = 0;
   cudaFree(c->d_t1); cudaFree(c->d_t2); cudaFree(c->d_v2); cudaFree(c->d_v2orb); cudaFree(c->d_evl);
   cudaFree(c->d_y1); cudaFree(c->d_y2); cudaFree(c->d_f1);
+  c->crn2s.reset();
   cudaFree(c->d_crn1); cudaFree(c->d_crn2); cudaFree(c->d_cre2);
   cudaFree(c->d_x2); cudaFree(c->d_m1); cudaFree(c->d_m2); cudaFree(c->d_m3); cudaFree(c->d_m4); cudaFree(c->d_eomy1);
   cudaFree(c->d_eomz); cudaFree(c->d_evl_shift); cudaFree(c->d_unit); cudaFree(c->d_zero);
@@ -143,7 +163,7 @@ void free_stores(nwc_triples_ctx* c) {   // one reset routine for every set_stat
 void recover(nwc_triples_ctx* c) {
   if (!c || !c->eng) return;
   c->eng->abort();
-  for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); }
+  for (int s = 0; s < 2; s++) { c->v2_built[s].clear(); c->pulled[s].clear(); c->crn2s.pulled[s].clear(); }
 }
 
 template <class F>
@@ -230,11 +250,34 @@ const double* v2_operand(nwc_triples_ctx* c, Integer g3b, Integer g4b, Integer g
   return v2_block(c, v2_key(c->S, g3b, g4b, g1b, g2b), what);
 }
 
+// block `key` of the CR-CCSD(T) pphp intermediate i1(p4 p5 h1 p12): replicated, or this rank's shard / a pulled copy
+const double* crn2_block(nwc_triples_ctx* c, Integer key) {
+  PeerStore& P = c->crn2s;
+  if (P.nshards <= 1) return c->d_crn2 + hash_lookup_or_die(c->crn2_hash, key, "cr n2(pphp)");
+  const Integer pos = hash_index(c->crn2_hash.data(), key);
+  if (pos < 0) throw Error("nwc_triples: cr n2(pphp): block key " + std::to_string(key) + " not found");
+  const Integer idx = pos - 1;
+  const int owner = (int)(idx % P.nshards);
+  const Integer off = P.shard_off[(size_t)idx];
+  if (owner == P.rank) return c->d_crn2 + off;
+  const double* base = P.peer[(size_t)owner];
+  if (!base) throw Error("nwc_triples: CR shard of rank " + std::to_string(owner) + " is not mapped (nwc_triples_cr_open_peers)");
+  auto& cache = P.pulled[c->eng->current_slot()];
+  auto hit = cache.find(idx);
+  if (hit != cache.end()) return hit->second;
+  const Integer n = P.block_n[(size_t)idx];
+  double* dst = (double*)c->eng->arena().alloc((size_t)n * sizeof(double));
+  c->eng->add_copy(CopyJob{base + off, dst, (long long)n});
+  cache[idx] = dst;
+  return dst;
+}
+
 // a batch slot has been collected: blocks built / pulled in its arena are gone
 void slot_done(nwc_triples_ctx* c, int slot) {
   if (slot < 0) return;
   c->v2_built[slot].clear();
   c->pulled[slot].clear();
+  c->crn2s.pulled[slot].clear();
 }
 
 // lambda_2 block key (h4b<=h5b, p1b<=p2b): lambda_ccsd_t_left.F:378-380
@@ -421,13 +464,13 @@ struct NativeSink {
       v.stride[N_P5] = rp7 * S.rg(r.h3b) * S.rg(r.p6b);
       OperandView tx = t;
       tx.base = c->d_x2 + (t.base - c->d_t2);
-      if (c->eom_lr0) { v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, ckey, "cr n2(pphp)"); push(t, v, sign * c->eom_r0, rp7, fire); }
+      if (c->eom_lr0) { v.base = crn2_block(c, ckey); push(t, v, sign * c->eom_r0, rp7, fire); }
       v.base = c->d_m2 + hash_lookup_or_die(c->m2_hash, ckey, "creom i2_2(pphp)"); push(t, v, -2.0 * sign, rp7, fire);
       v.base = c->d_m4 + hash_lookup_or_die(c->m4_hash, ckey, "creom i2_4(pphp)"); push(tx, v, sign, rp7, fire);
       return;
     }
     if (cr == CR_MOMENT)
-      v.base = c->d_crn2 + hash_lookup_or_die(c->crn2_hash, ckey, "cr n2(pphp)");
+      v.base = crn2_block(c, ckey);
     else
       v.base = v2_operand(c, bm[0], bm[1], bm[2], bm[3], "v2(pphp)");
     v.kstride = 1; v.stride[N_H3] = rp7; v.stride[N_P6] = rp7 * S.rg(r.h3b);
@@ -1227,8 +1270,53 @@ int nwc_triples_run_lambda_partition(nwc_triples_ctx* c, Integer rank, Integer n
 //   e2 = d_i1_2 of cr_ccsd_t_E: i1(p4 p5 h1 h2)_tt, the T2 block structure,   OFFSET_cr_ccsd_t_E_2_1 (cr_ccsd_t_E.F:907)
 // i.e. what cr_ccsd_t_N(...,1) / cr_ccsd_t_E(...,1) leave in GA, or the files gr1_1 / gr1_2 / ei1_2 of read_in3
 // (cr_ccsd_t_N.F:98-104).  Replicated in HBM.  Call after a set_state* variant.
+static int set_cr_impl(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash, const double* n2,
+                       const Integer* e2_hash, const double* e2, int rank, int nranks);
 int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash, const double* n2,
                        const Integer* e2_hash, const double* e2) {
+  return set_cr_impl(c, n1_hash, n1, n2_hash, n2, e2_hash, e2, 0, 1);
+}
+// The pphp intermediate is as large as V2's <pp||hp> class (2.5*o*v^3 doubles: 527 GB for (H2O)10), so like V2 it can be
+// dealt over the GPUs of the node: block i of its offset table lives on rank i % nranks and `n2` holds THIS rank's blocks
+// only (table order, compacted); the small hphh and pphh intermediates stay replicated.  Afterwards the ranks exchange
+// nwc_triples_cr_ipc_handle / nwc_triples_cr_open_peers (or, inside one process, cr_shard_ptr / cr_set_peer_ptr) exactly
+// as for a sharded V2; remote blocks are pulled over NVLink per batch.
+int nwc_triples_set_cr_sharded(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash,
+                               const double* n2_shard, const Integer* e2_hash, const double* e2, int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad rank/nranks"; return 1; }
+  if (c->eng->trace_only() && nranks > 1) { g_err = "a trace context takes replicated stores only"; return 1; }
+  return set_cr_impl(c, n1_hash, n1, n2_hash, n2_shard, e2_hash, e2, rank, nranks);
+}
+int nwc_triples_cr_ipc_handle(nwc_triples_ctx* c, char handle64[64]) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  if (!c->d_crn2) { g_err = "nwc_triples_cr_ipc_handle: call nwc_triples_set_cr_sharded first"; return 1; }
+  cudaIpcMemHandle_t h;
+  NWC_TRY(cudaIpcGetMemHandle(&h, c->d_crn2));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int nwc_triples_cr_open_peers(nwc_triples_ctx* c, const char* handles) {
+  NWC_TRY(cudaSetDevice(c->eng->device()));
+  PeerStore& P = c->crn2s;
+  for (int r = 0; r < P.nshards; r++) {
+    if (r == P.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    NWC_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    P.peer[(size_t)r] = (double*)p;
+    P.opened[(size_t)r] = 1;
+  }
+  return 0;
+}
+void* nwc_triples_cr_shard_ptr(nwc_triples_ctx* c) { return c->d_crn2; }
+int nwc_triples_cr_set_peer_ptr(nwc_triples_ctx* c, int rank, void* dev_ptr) {
+  if (rank < 0 || rank >= c->crn2s.nshards) { g_err = "bad peer rank"; return 1; }
+  c->crn2s.peer[(size_t)rank] = (double*)dev_ptr;
+  return 0;
+}
+static int set_cr_impl(nwc_triples_ctx* c, const Integer* n1_hash, const double* n1, const Integer* n2_hash, const double* n2,
+                       const Integer* e2_hash, const double* e2, int rank, int nranks) {
   return guarded(c, [&]() {
     if (!c->eng->trace_only()) NWC_TRY(cudaSetDevice(c->eng->device()));
     const HostState& S = c->S;
@@ -1259,7 +1347,27 @@ int nwc_triples_set_cr(nwc_triples_ctx* c, const Integer* n1_hash, const double*
     c->crn2_hash.assign(n2_hash, n2_hash + 2 * n2_hash[0] + 1);
     c->cre2_hash.assign(e2_hash, e2_hash + 2 * e2_hash[0] + 1);
     if (upload(&c->d_crn1, &c->n_crn1, n1, total_of(n1_hash, 1), c->eng)) return 1;
-    if (upload(&c->d_crn2, &c->n_crn2, n2, total_of(n2_hash, 2), c->eng)) return 1;
+    c->crn2s.reset();
+    if (nranks <= 1) {
+      if (upload(&c->d_crn2, &c->n_crn2, n2, total_of(n2_hash, 2), c->eng)) return 1;
+    } else {   // shard offsets of every block (all ranks compute the same table)
+      PeerStore& P = c->crn2s;
+      const Integer nb = n2_hash[0];
+      const Integer total = (Integer)total_of(n2_hash, 2);
+      P.nshards = nranks; P.rank = rank;
+      P.shard_off.assign((size_t)nb, 0); P.block_n.assign((size_t)nb, 0);
+      P.peer.assign((size_t)nranks, nullptr); P.opened.assign((size_t)nranks, 0);
+      std::vector<Integer> fill((size_t)nranks, 0);
+      for (Integer i = 0; i < nb; i++) {
+        const Integer off = n2_hash[nb + 1 + i], next = (i + 1 < nb) ? n2_hash[nb + 2 + i] : total;
+        const int owner = (int)(i % nranks);
+        P.shard_off[(size_t)i] = fill[(size_t)owner];
+        P.block_n[(size_t)i] = next - off;
+        fill[(size_t)owner] += next - off;
+      }
+      if (upload(&c->d_crn2, &c->n_crn2, n2, (size_t)fill[(size_t)rank], c->eng)) return 1;
+      P.peer[(size_t)rank] = c->d_crn2;
+    }
     // sd_E2_K multiplies by +-2/3 (cr_ccsd_t_E.F:629-721): the factor is folded into the resident copy once
     const size_t ne = total_of(e2_hash, 3);
     std::vector<double>& scaled = c->cre2_scaled;

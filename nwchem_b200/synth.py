@@ -293,3 +293,12 @@ def shard_v2(st: BlockStores, rank: int, world: int) -> BlockStores:
     parts = [st.v2[offs[i]:offs[i + 1]] for i in range(n) if i % world == rank]
     v2 = np.concatenate(parts) if parts else np.zeros(0)
     return BlockStores(st.t, st.t1_hash, st.t1, st.t2_hash, st.t2, st.v2_hash, np.ascontiguousarray(v2))
+
+
+def shard_store(hash_table, data, rank: int, world: int):
+    """The shard of `rank` of any block store: block i of the offset table belongs to rank i % world; the shard keeps its
+    blocks in table order, compacted (nwc_triples_set_cr_sharded for the CR-CCSD(T) pphp intermediate)."""
+    n = int(hash_table[0])
+    offs = [int(hash_table[1 + n + i]) for i in range(n)] + [len(data)]
+    parts = [data[offs[i]:offs[i + 1]] for i in range(n) if i % world == rank]
+    return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0)

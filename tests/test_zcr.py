@@ -292,3 +292,42 @@ def test_cr_eomccsd_t_ragged_and_random_blocks(oracle):
     assert np.max(np.abs(ref["per_task"])) > 1e-8
     assert np.max(np.abs(got - ref["per_task"])) <= 1e-11 * scale
     assert np.max(np.abs(sums - ref["sums"]) / np.abs(ref["sums"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_cr_sharded_pphp_intermediate_two_contexts_one_gpu(oracle):
+    """nwc_triples_set_cr_sharded: the pphp intermediate dealt block-wise over two "ranks" (two contexts on one GPU, peer
+    pointers exchanged in-process; remote blocks pulled into the batch arena).  Each runs its piece of the block
+    partition; the pieces add up to the replicated run bit for bit (a pulled block is a copy), which matches the oracle.
+    CR-EOMCCSD(T) reads the same sharded store for its r0 term."""
+    from nwchem_b200 import capi
+    from oracle import cr_dense
+    t = synth.shape_tiling("h2o_ccpvdz_c2v")
+    st = synth.physical(t)
+    cr, q = cr_dense.DenseEOM(t, r0=0.37).stores()
+    ref = oracle.cr_ccsd_t(st, cr)
+    ref_eom = oracle.cr_eomccsd_t(st, cr, q)
+    one = capi.Triples(0)
+    one.set_state(st)
+    one.set_cr(cr)
+    s1, p1 = one.run_cr(per_task=True)
+    one.close()
+    ctx = []
+    for r in range(2):
+        tr = capi.Triples(0)
+        tr.set_state(st)
+        tr.set_cr_sharded(dataclasses.replace(cr, n2=synth.shard_store(cr.n2_hash, cr.n2, r, 2)), r, 2)
+        ctx.append(tr)
+    ctx[0].cr_set_peer_ptr(1, ctx[1].cr_shard_ptr())
+    ctx[1].cr_set_peer_ptr(0, ctx[0].cr_shard_ptr())
+    parts = [ctx[r].run_cr_partition(r, 2, per_task=True) for r in range(2)]
+    for tr in ctx:
+        tr.set_creom(q)
+    eom = [ctx[r].run_creom_partition(r, 2, per_task=True) for r in range(2)]
+    for tr in ctx:
+        tr.close()
+    assert np.max(np.abs(s1 - ref["sums"])) <= 1e-12
+    assert np.max(np.abs(parts[0][1] + parts[1][1] - p1)) <= 1e-15
+    assert np.max(np.abs(parts[0][0] + parts[1][0] - ref["sums"])) <= 1e-12
+    tot = eom[0][0] + eom[1][0]
+    assert np.max(np.abs(tot - ref_eom["sums"]) / np.abs(ref_eom["sums"])) <= 1e-9
