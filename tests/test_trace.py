@@ -244,3 +244,41 @@ def test_creom_driver_trace_matches_oracle(oracle, ts, restricted, r0):
         n += 1
     tr.close()
     assert n >= 5
+
+
+def test_trace_context_error_paths():
+    """Status + message instead of a crash: intermediates from another tiling, CR-EOM without the ground-state
+    intermediates, x amplitudes with a foreign block structure, a method the context was not set up for."""
+    from oracle import cr_dense
+    t = tl.make_tiling(OCC, VIRT, 2)
+    t_other = tl.make_tiling([3, 1], [4, 2], 2)
+    st = synth.physical(t)
+    d = cr_dense.DenseEOM(t)
+    cr, q = d.stores()
+    cr_other = cr_dense.Dense(t_other).stores()
+    tr = capi.Triples(trace=True)
+    tr.set_state(st)
+    tup = [int(x) for x in oracle_task(t)]
+    with pytest.raises(RuntimeError):
+        tr.trace_tuple(tup, 2)                       # CR before set_cr
+    with pytest.raises(RuntimeError):
+        tr.set_creom(q)                              # r0 != 0 needs set_cr
+    with pytest.raises(RuntimeError):
+        tr.set_cr(cr_other)                          # offset tables of another tiling
+    tr.set_cr(cr)
+    bad = dataclasses.replace(q, x2_hash=cr.n1_hash)
+    with pytest.raises(RuntimeError):
+        tr.set_creom(bad)
+    tr.set_creom(q)
+    recs, keep = tr.trace_tuple(tup, 8)
+    assert recs[-1].kind == 9
+    with pytest.raises(RuntimeError):
+        tr.trace_tuple(tup, 99)
+    with pytest.raises(RuntimeError):
+        tr.run_cr()                                  # a trace context cannot compute
+    tr.close()
+
+
+def oracle_task(t):
+    from oracle import oracle as ora
+    return ora.task_list(t)[0][:6]
