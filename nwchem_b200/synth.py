@@ -145,12 +145,14 @@ def physical_dense(t: tl.Tiling, seed: int = 20240229, naux: int = 12):
     return no, nv, t1s, t2s, eri
 
 
-def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = False) -> BlockStores:
+def physical(t: tl.Tiling, seed: int = 20240229, naux: int = 12, intorb: bool = False, dense=None) -> BlockStores:
     """Dense spatial tensors -> spin-orbital antisymmetrised blocks.  Only for small orbital counts.
     With an unrestricted tiling (t.restricted False) the same closed-shell tensors are expanded into every spin
     block (beta tiles are their own owners), so E[T]/E(T) must equal the restricted result: a check of the
-    `restricted` factor-2 / k_alpha logic (ccsd_t_dot.F:52-56, tce_restricted.F)."""
-    no, nv, t1s, t2s, eri = physical_dense(t, seed, naux)
+    `restricted` factor-2 / k_alpha logic (ccsd_t_dot.F:52-56, tce_restricted.F).
+    dense = (no, nv, t1s[a,i], t2s[a,b,i,j], eri[p,q,r,s]) replaces the synthetic tensors (real CCSD amplitudes and MO
+    integrals: oracle/h2o_ccsd.py), in the spatial-orbital order of the tiling (occupied then virtual)."""
+    no, nv, t1s, t2s, eri = physical_dense(t, seed, naux) if dense is None else dense
 
     def so(b):  # spatial ids and spin of tile b (1-based)
         return t.members[b - 1], int(t.spin[b - 1])

@@ -1,0 +1,452 @@
+"""Real amplitudes for the reference's own QA case -- TEST INFRASTRUCTURE ONLY.
+
+QA/tests/tce_ccsd_t_h2o (tce_ccsd_t_h2o.nw: H2O, cc-pVDZ spherical, RHF, no frozen core, CCSD(T)) is the one golden
+vector set the reference ships for this path: tce_ccsd_t_h2o.out:390 (SCF), :734 (CCSD), :743 / :746 (the
+[T] and (T) corrections).  Nothing in the image can produce the converged CCSD amplitudes and MO integrals those numbers
+need (no Fortran, no quantum-chemistry package), so this module computes them from first principles in numpy:
+McMurchie-Davidson integrals over the cc-pVDZ basis (data: src/basis/libraries/cc-pvdz, "O_cc-pVDZ" / "H_cc-pVDZ"),
+RHF, spin-orbital CCSD.  Each stage is checked against the QA output's own intermediate energies (SCF total energy,
+CCSD correlation energy) before the amplitudes are handed to the oracle's (T); the oracle's E[T] / E(T) on them is then
+compared with the golden corrections (tests/test_qa_h2o.py).  `python -m oracle.h2o_ccsd` regenerates
+tests/golden/h2o_ccpvdz_ccsd.npz.
+
+Energies are invariant under any change of basis within the same span, so no care is taken to normalise the basis
+functions: a contracted function is sum_k c_k a_k^((2l+3)/4) x^i y^j z^k exp(-a_k r^2) (the library's coefficients refer
+to normalised primitives: only the exponent dependence of the normalisation matters), d shells are the five real solid
+harmonics 2zz-xx-yy, xx-yy, xy, xz, yz."""
+from __future__ import annotations
+import itertools
+import os
+import numpy as np
+from scipy import special
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURE = os.path.join(os.path.dirname(HERE), "tests", "golden", "h2o_ccpvdz_ccsd.npz")
+
+# tce_ccsd_t_h2o.nw:17-21 (bohr)
+GEOM = [("O", 8.0, (0.0, 0.0, 0.22138519)), ("H", 1.0, (0.0, -1.43013023, -0.88554075)), ("H", 1.0, (0.0, 1.43013023, -0.88554075))]
+# src/basis/libraries/cc-pvdz: basis "O_cc-pVDZ" SPHERICAL / "H_cc-pVDZ" SPHERICAL.  (l, exponents, contraction columns)
+BASIS = {
+    "O": [(0, [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013],
+           [[0.00071, 0.00547, 0.027837, 0.1048, 0.283062, 0.448719, 0.270952, 0.015458],
+            [-0.00016, -0.001263, -0.006267, -0.025716, -0.070924, -0.165411, -0.116955, 0.557368]]),
+          (0, [0.3023], [[1.0]]),
+          (1, [17.7, 3.854, 1.046], [[0.043018, 0.228913, 0.508728]]),
+          (1, [0.2753], [[1.0]]),
+          (2, [1.185], [[1.0]])],
+    "H": [(0, [13.01, 1.962, 0.4446], [[0.019685, 0.137977, 0.478148]]),
+          (0, [0.122], [[1.0]]),
+          (1, [0.727], [[1.0]])],
+}
+# tce_ccsd_t_h2o.out
+QA = dict(scf=-76.026807857236, ccsd_corr=-0.213269954065481, t_bracket=-0.003139909173705, t_paren=-0.003054718622142)
+
+CART = {0: [(0, 0, 0)], 1: [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
+        2: [(2, 0, 0), (0, 2, 0), (0, 0, 2), (1, 1, 0), (1, 0, 1), (0, 1, 1)]}
+# real solid harmonics of l = 2 over (xx, yy, zz, xy, xz, yz); unnormalised (see the module docstring)
+SPH_D = np.array([[-1.0, -1.0, 2.0, 0, 0, 0], [1.0, -1.0, 0, 0, 0, 0], [0, 0, 0, 1.0, 0, 0], [0, 0, 0, 0, 1.0, 0], [0, 0, 0, 0, 0, 1.0]])
+
+
+def check_basis_against_reference(path="/root/reference/src/basis/libraries/cc-pvdz"):
+    """The numbers above are the library's (only where the reference tree is mounted)."""
+    if not os.path.exists(path):
+        return None
+    txt = open(path).read()
+    for el in ("O", "H"):
+        blk = txt[txt.index(f'basis "{el}_cc-pVDZ"'):]
+        blk = blk[:blk.index("\nend")]
+        nums = [float(x) for line in blk.split("\n")[1:] for x in line.split() if x[0].isdigit() or x[0] == "-"]
+        mine = []
+        for l, exps, cols in BASIS[el]:
+            for k, a in enumerate(exps):
+                mine += [a] + [c[k] for c in cols]
+        assert np.allclose(sorted(nums), sorted(mine), rtol=0, atol=1e-12), el
+    return True
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# primitive Cartesian functions and the contraction to the 24 spherical basis functions
+# ------------------------------------------------------------------------------------------------------------------
+def build_basis():
+    prim = []      # (center, exponent, (i,j,k))
+    rows = []      # contraction: list of (basis function index, prim index, coefficient)
+    nbf = 0
+    for el, z, R in GEOM:
+        for l, exps, cols in BASIS[el]:
+            first = len(prim)
+            for a in exps:
+                for ijk in CART[l]:
+                    prim.append((np.array(R), a, ijk))
+            ncart = len(CART[l])
+            for col in cols:
+                comb = np.eye(ncart) if l < 2 else SPH_D
+                for f in range(comb.shape[0]):
+                    for k, a in enumerate(exps):
+                        w = col[k] * a ** ((2 * l + 3) / 4.0)
+                        for cidx in range(ncart):
+                            if comb[f, cidx] != 0.0:
+                                rows.append((nbf, first + k * ncart + cidx, w * comb[f, cidx]))
+                    nbf += 1
+    C = np.zeros((len(prim), nbf))
+    for bf, p, w in rows:
+        C[p, bf] += w
+    return prim, C
+
+
+def _e1d(i, j, a, b, Q):
+    """Hermite expansion coefficients E_t^{ij}, t = 0..i+j, of x_A^i x_B^j exp(-a x_A^2 - b x_B^2) (Q = A - B)."""
+    p = a + b
+    q = a * b / p
+    memo = {}
+
+    def E(i, j, t):
+        if t < 0 or t > i + j:
+            return 0.0
+        key = (i, j, t)
+        if key in memo:
+            return memo[key]
+        if i == 0 and j == 0:
+            v = np.exp(-q * Q * Q)
+        elif j == 0:
+            v = E(i - 1, j, t - 1) / (2 * p) - (q * Q / a) * E(i - 1, j, t) + (t + 1) * E(i - 1, j, t + 1)
+        else:
+            v = E(i, j - 1, t - 1) / (2 * p) + (q * Q / b) * E(i, j - 1, t) + (t + 1) * E(i, j - 1, t + 1)
+        memo[key] = v
+        return v
+    return [E(i, j, t) for t in range(i + j + 1)]
+
+
+HERM = [h for L in range(5) for h in itertools.product(range(L + 1), repeat=3) if sum(h) == L]      # t+u+v <= 4: 35 terms
+HIDX = {h: n for n, h in enumerate(HERM)}
+
+
+def boys(nmax, T):
+    """F_n(T), n = 0..nmax, for an array T >= 0: downward recursion from F_nmax (incomplete gamma function; series near 0)."""
+    T = np.asarray(T, dtype=np.float64)
+    out = np.zeros((nmax + 1,) + T.shape)
+    small = T < 1e-6
+    Ts = np.where(small, 1.0, T)
+    n = nmax
+    top = special.gammainc(n + 0.5, Ts) * special.gamma(n + 0.5) / (2.0 * Ts ** (n + 0.5))
+    top = np.where(small, 1.0 / (2 * n + 1) - T / (2 * n + 3) + T * T / (2 * (2 * n + 5)), top)
+    out[n] = top
+    eT = np.exp(-T)
+    for m in range(nmax - 1, -1, -1):
+        out[m] = (2.0 * T * out[m + 1] + eT) / (2 * m + 1)
+    return out
+
+
+def hermite_R(Lmax, alpha, X, Y, Z):
+    """R_{tuv} = R^0_{tuv}(alpha, (X,Y,Z)) for t+u+v <= Lmax, vectorised over the leading axis; returns dict (t,u,v) -> array."""
+    T = alpha * (X * X + Y * Y + Z * Z)
+    F = boys(Lmax, T)
+    R = {}
+    for n in range(Lmax + 1):
+        R[(0, 0, 0, n)] = (-2.0 * alpha) ** n * F[n]
+    for L in range(1, Lmax + 1):
+        for t, u, v in itertools.product(range(L + 1), repeat=3):
+            if t + u + v != L:
+                continue
+            for n in range(Lmax - L + 1):
+                if t > 0:
+                    val = X * R[(t - 1, u, v, n + 1)]
+                    if t > 1:
+                        val = val + (t - 1) * R[(t - 2, u, v, n + 1)]
+                elif u > 0:
+                    val = Y * R[(t, u - 1, v, n + 1)]
+                    if u > 1:
+                        val = val + (u - 1) * R[(t, u - 2, v, n + 1)]
+                else:
+                    val = Z * R[(t, u, v - 1, n + 1)]
+                    if v > 1:
+                        val = val + (v - 1) * R[(t, u, v - 2, n + 1)]
+                R[(t, u, v, n)] = val
+    return {k[:3]: v for k, v in R.items() if k[3] == 0}
+
+
+def integrals():
+    """(S, T, V, eri, Enuc) over the 24 contracted spherical functions; eri[p,q,r,s] = (pq|rs)."""
+    prim, C = build_basis()
+    n = len(prim)
+    pairs = [(i, j) for i in range(n) for j in range(i + 1)]
+    npair = len(pairs)
+    P = np.zeros((npair, 3)); pp = np.zeros(npair); EH = np.zeros((npair, len(HERM)))
+    S = np.zeros((n, n)); Tk = np.zeros((n, n)); V = np.zeros((n, n))
+    nuc = [(z, np.array(R)) for _, z, R in GEOM]
+    for k, (i, j) in enumerate(pairs):
+        A, a, la = prim[i]; B, b, lb = prim[j]
+        p = a + b
+        Pc = (a * A + b * B) / p
+        e = [_e1d(la[d], lb[d], a, b, A[d] - B[d]) for d in range(3)]
+        for (t, u, v), idx in HIDX.items():
+            if t <= la[0] + lb[0] and u <= la[1] + lb[1] and v <= la[2] + lb[2]:
+                EH[k, idx] = e[0][t] * e[1][u] * e[2][v]
+        P[k] = Pc; pp[k] = p
+        # overlap and kinetic energy from one-dimensional overlaps s_d(i,j) = E_0^{ij} sqrt(pi/p)
+        def s1(d, ii, jj):
+            if ii < 0 or jj < 0:
+                return 0.0
+            return _e1d(ii, jj, a, b, A[d] - B[d])[0] * np.sqrt(np.pi / p)
+        s = [s1(d, la[d], lb[d]) for d in range(3)]
+        t1 = [-2 * b * b * s1(d, la[d], lb[d] + 2) + b * (2 * lb[d] + 1) * s[d] - 0.5 * lb[d] * (lb[d] - 1) * s1(d, la[d], lb[d] - 2)
+              for d in range(3)]
+        S[i, j] = S[j, i] = s[0] * s[1] * s[2]
+        Tk[i, j] = Tk[j, i] = t1[0] * s[1] * s[2] + s[0] * t1[1] * s[2] + s[0] * s[1] * t1[2]
+        vv = 0.0
+        for z, Rc in nuc:
+            d = Pc - Rc
+            R = hermite_R(4, np.array([p]), np.array([d[0]]), np.array([d[1]]), np.array([d[2]]))
+            vv += -z * (2 * np.pi / p) * sum(EH[k, idx] * R[h][0] for h, idx in HIDX.items() if EH[k, idx] != 0.0)
+        V[i, j] = V[j, i] = vv
+    # two-electron integrals over primitive pairs, in chunks
+    nh = len(HERM)
+    sign = np.array([(-1.0) ** sum(h) for h in HERM])
+    keys = sorted({tuple(np.add(h, g)) for h in HERM for g in HERM})
+    kpos = {kk: m for m, kk in enumerate(keys)}
+    gather = np.array([[kpos[tuple(np.add(h, g))] for g in HERM] for h in HERM])
+    eri_pp = np.zeros((npair, npair))
+    chunk = 4000
+    idxA, idxB = np.tril_indices(npair)
+    for c0 in range(0, len(idxA), chunk):
+        ia = idxA[c0:c0 + chunk]; ib = idxB[c0:c0 + chunk]
+        p = pp[ia]; q = pp[ib]
+        alpha = p * q / (p + q)
+        d = P[ia] - P[ib]
+        R = hermite_R(8, alpha, d[:, 0], d[:, 1], d[:, 2])
+        Rm = np.stack([R[kk] for kk in keys], axis=1)                      # [chunk, nkeys]
+        G = Rm[:, gather]                                                 # [chunk, nh, nh]
+        val = np.einsum("bh,bhg,bg->b", EH[ia], G, EH[ib] * sign[None, :])
+        val *= 2.0 * np.pi ** 2.5 / (p * q * np.sqrt(p + q))
+        eri_pp[ia, ib] = val
+        eri_pp[ib, ia] = val
+    # unpack pairs and contract
+    pidx = np.zeros((n, n), dtype=np.int64)
+    for k, (i, j) in enumerate(pairs):
+        pidx[i, j] = pidx[j, i] = k
+    eri_prim = eri_pp[pidx.reshape(-1)][:, pidx.reshape(-1)].reshape(n, n, n, n)
+    eri = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri_prim, C, C, C, C, optimize=True)
+    Sc = C.T @ S @ C; Tc = C.T @ Tk @ C; Vc = C.T @ V @ C
+    enuc = sum(nuc[i][0] * nuc[j][0] / np.linalg.norm(nuc[i][1] - nuc[j][1]) for i in range(len(nuc)) for j in range(i))
+    return Sc, Tc, Vc, eri, float(enuc)
+
+
+def rhf(S, T, V, eri, enuc, nocc=5, tol=1e-12, maxit=200):
+    """Restricted Hartree-Fock with DIIS; returns (energy, orbital energies, MO coefficients)."""
+    from scipy import linalg
+    H = T + V
+    e, Cm = linalg.eigh(H, S)
+    D = Cm[:, :nocc] @ Cm[:, :nocc].T
+    fs, es = [], []
+    E = 0.0
+    for it in range(maxit):
+        J = np.einsum("pqrs,rs->pq", eri, D)
+        K = np.einsum("prqs,rs->pq", eri, D)
+        F = H + 2 * J - K
+        Enew = float(np.sum(D * (H + F))) + enuc
+        err = F @ D @ S - S @ D @ F
+        fs.append(F); es.append(err)
+        fs, es = fs[-8:], es[-8:]
+        if len(fs) > 1:
+            m = len(fs)
+            Bm = -np.ones((m + 1, m + 1)); Bm[m, m] = 0.0
+            for i in range(m):
+                for j in range(m):
+                    Bm[i, j] = np.sum(es[i] * es[j])
+            rhs = np.zeros(m + 1); rhs[m] = -1.0
+            c = np.linalg.solve(Bm, rhs)[:m]
+            F = sum(ci * fi for ci, fi in zip(c, fs))
+        e, Cm = linalg.eigh(F, S)
+        D = Cm[:, :nocc] @ Cm[:, :nocc].T
+        if abs(Enew - E) < tol and np.max(np.abs(err)) < 1e-9:
+            E = Enew
+            break
+        E = Enew
+    return E, e, Cm
+
+
+def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200):
+    """Spin-orbital CCSD (Stanton, Gauss, Watts, Bartlett, J. Chem. Phys. 94, 4334 (1991)) for a canonical closed-shell RHF
+    reference; returns (correlation energy, t1s[a,i], t2s[a,b,i,j]) -- the spatial amplitudes t_i^a, t_{ij}^{ab} (alpha-beta)."""
+    n = len(eps)
+    nso = 2 * n
+    # spin-orbital index = 2*spatial + spin
+    sp = np.arange(nso) // 2
+    spin = np.arange(nso) % 2
+    g = eri_mo[np.ix_(sp, sp, sp, sp)]                                     # (pq|rs) over spin orbitals, spatial part
+    dl = (spin[:, None] == spin[None, :]).astype(float)
+    # <pq||rs> = (pr|qs) d(p,r) d(q,s) - (ps|qr) d(p,s) d(q,r)
+    v = np.einsum("prqs,pr,qs->pqrs", g, dl, dl) - np.einsum("psqr,ps,qr->pqrs", g, dl, dl)
+    e = eps[sp]
+    no = 2 * nocc
+    o, vv = slice(0, no), slice(no, nso)
+    eo, ev = e[o], e[vv]
+    D1 = eo[:, None] - ev[None, :]
+    D2 = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
+    t1 = np.zeros((no, nso - no))
+    t2 = v[o, o, vv, vv] / D2
+    E = np.einsum
+
+    def energy(t1, t2):
+        return 0.25 * E("ijab,ijab->", v[o, o, vv, vv], t2) + 0.5 * E("ijab,ia,jb->", v[o, o, vv, vv], t1, t1)
+    t1s_l, t2s_l, err_l = [], [], []
+    Ecc = energy(t1, t2)
+    for it in range(maxit):
+        tau_t = t2 + 0.5 * (E("ia,jb->ijab", t1, t1) - E("ib,ja->ijab", t1, t1))
+        tau = t2 + E("ia,jb->ijab", t1, t1) - E("ib,ja->ijab", t1, t1)
+        Fae = (-0.5 * E("me,ma->ae", np.zeros_like(t1), t1) + E("mf,mafe->ae", t1, v[o, vv, vv, vv])
+               - 0.5 * E("mnaf,mnef->ae", tau_t, v[o, o, vv, vv]))
+        Fmi = (E("ne,mnie->mi", t1, v[o, o, o, vv]) + 0.5 * E("inef,mnef->mi", tau_t, v[o, o, vv, vv]))
+        Fme = E("nf,mnef->me", t1, v[o, o, vv, vv])
+        Wmnij = (v[o, o, o, o] + E("je,mnie->mnij", t1, v[o, o, o, vv]) - E("ie,mnje->mnij", t1, v[o, o, o, vv])
+                 + 0.25 * E("ijef,mnef->mnij", tau, v[o, o, vv, vv]))
+        Wabef = (v[vv, vv, vv, vv] - E("mb,amef->abef", t1, v[vv, o, vv, vv]) + E("ma,bmef->abef", t1, v[vv, o, vv, vv])
+                 + 0.25 * E("mnab,mnef->abef", tau, v[o, o, vv, vv]))
+        Wmbej = (v[o, vv, vv, o] + E("jf,mbef->mbej", t1, v[o, vv, vv, vv]) - E("nb,mnej->mbej", t1, v[o, o, vv, o])
+                 - E("jnfb,mnef->mbej", 0.5 * t2 + E("jf,nb->jnfb", t1, t1), v[o, o, vv, vv]))
+        # T1 (canonical orbitals: f_ia = 0, f diagonal)
+        r1 = (E("ie,ae->ia", t1, Fae) - E("ma,mi->ia", t1, Fmi) + E("imae,me->ia", t2, Fme)
+              - E("nf,naif->ia", t1, v[o, vv, o, vv]) - 0.5 * E("imef,maef->ia", t2, v[o, vv, vv, vv])
+              - 0.5 * E("mnae,nmei->ia", t2, v[o, o, vv, o]))
+        # T2
+        Fae2 = Fae - 0.5 * E("mb,me->be", t1, Fme)
+        Fmi2 = Fmi + 0.5 * E("je,me->mj", t1, Fme)
+        r2 = v[o, o, vv, vv].copy()
+        x = E("ijae,be->ijab", t2, Fae2); r2 += x - x.transpose(0, 1, 3, 2)
+        x = E("imab,mj->ijab", t2, Fmi2); r2 -= x - x.transpose(1, 0, 2, 3)
+        r2 += 0.5 * E("mnab,mnij->ijab", tau, Wmnij) + 0.5 * E("ijef,abef->ijab", tau, Wabef)
+        x = E("imae,mbej->ijab", t2, Wmbej) - E("ie,ma,mbej->ijab", t1, t1, v[o, vv, vv, o])
+        r2 += x - x.transpose(1, 0, 2, 3) - x.transpose(0, 1, 3, 2) + x.transpose(1, 0, 3, 2)
+        x = E("ie,abej->ijab", t1, v[vv, vv, vv, o]); r2 += x - x.transpose(1, 0, 2, 3)
+        x = E("ma,mbij->ijab", t1, v[o, vv, o, o]); r2 -= x - x.transpose(0, 1, 3, 2)
+        t1n = r1 / D1
+        t2n = r2 / D2
+        # DIIS on the amplitudes
+        t1s_l.append(t1n); t2s_l.append(t2n); err_l.append(np.concatenate([(t1n - t1).ravel(), (t2n - t2).ravel()]))
+        t1s_l, t2s_l, err_l = t1s_l[-8:], t2s_l[-8:], err_l[-8:]
+        if len(err_l) > 1:
+            m = len(err_l)
+            Bm = -np.ones((m + 1, m + 1)); Bm[m, m] = 0.0
+            for i in range(m):
+                for j in range(m):
+                    Bm[i, j] = err_l[i] @ err_l[j]
+            rhs = np.zeros(m + 1); rhs[m] = -1.0
+            c = np.linalg.solve(Bm, rhs)[:m]
+            t1n = sum(ci * x for ci, x in zip(c, t1s_l)); t2n = sum(ci * x for ci, x in zip(c, t2s_l))
+        dE = energy(t1n, t2n) - Ecc
+        rms = np.sqrt(err_l[-1] @ err_l[-1])
+        t1, t2 = t1n, t2n
+        Ecc += dE
+        if abs(dE) < tol and rms < 1e-10:
+            break
+    # spatial amplitudes: alpha = even spin orbitals
+    oa = np.arange(0, no, 2); ob = oa + 1
+    va = np.arange(0, nso - no, 2); vb = va + 1
+    t1s = t1[np.ix_(oa, va)].T.copy()                                       # [a,i]
+    t2s = t2[np.ix_(oa, ob, va, vb)].transpose(2, 3, 0, 1).copy()           # t_{i alpha j beta}^{a alpha b beta} -> [a,b,i,j]
+    return float(Ecc), t1s, t2s
+
+
+def mo_irreps(S, Cm):
+    """C2v irrep code (0 a1, 1 a2, 2 / 3 the two b irreps; XOR = direct product) of every MO from its parities under
+    x -> -x and y -> -y.  The molecule lies in the yz plane; y -> -y swaps the hydrogens.  Code 2 goes to the in-plane
+    antisymmetric irrep, the one with six virtual orbitals, as in the QA tile table (tce_ccsd_t_h2o.out:644-659)."""
+    labels = []       # per basis function: (atom, shell key, power of x, power of y)
+    for ia, (el, z, R) in enumerate(GEOM):
+        for ish, (l, exps, cols) in enumerate(BASIS[el]):
+            comps = {0: [(0, 0)], 1: [(1, 0), (0, 1), (0, 0)], 2: [(0, 0), (0, 0), (1, 1), (1, 0), (0, 1)]}[l]
+            for icol in range(len(cols)):
+                for ic, (px, py) in enumerate(comps):
+                    labels.append((ia, (ish, icol, ic), px, py))
+    n = len(labels)
+    Px = np.zeros((n, n)); Py = np.zeros((n, n))
+    swap = {0: 0, 1: 2, 2: 1}
+    for i, (ia, key, px, py) in enumerate(labels):
+        Px[i, i] = (-1.0) ** px
+        j = [k for k, (ja, kk, _, _) in enumerate(labels) if ja == swap[ia] and kk == key][0]
+        Py[j, i] = (-1.0) ** py
+    out = []
+    for m in range(Cm.shape[1]):
+        c = Cm[:, m]
+        ex = float(c @ S @ (Px @ c)); ey = float(c @ S @ (Py @ c))
+        assert abs(abs(ex) - 1.0) < 1e-6 and abs(abs(ey) - 1.0) < 1e-6, (m, ex, ey)
+        sx, sy = ex > 0, ey > 0
+        out.append(0 if (sx and sy) else 1 if (not sx and not sy) else 2 if (sx and not sy) else 3)
+    return np.array(out, dtype=np.int64)
+
+
+def generate(verbose=True):
+    check_basis_against_reference()
+    S, T, V, eri, enuc = integrals()
+    escf, eps, Cm = rhf(S, T, V, eri, enuc)
+    irrep = mo_irreps(S, Cm)
+    if verbose:
+        print(f"SCF   {escf:.12f}   QA {QA['scf']:.12f}   diff {escf - QA['scf']:.2e}", flush=True)
+    eri_mo = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri, Cm, Cm, Cm, Cm, optimize=True)
+    ecc, t1s, t2s = ccsd(eps, eri_mo)
+    if verbose:
+        print(f"CCSD  {ecc:.12f}   QA {QA['ccsd_corr']:.12f}   diff {ecc - QA['ccsd_corr']:.2e}", flush=True)
+    return dict(escf=escf, ecc=ecc, eps=eps, irrep=irrep, t1s=t1s, t2s=t2s, eri_mo=eri_mo)
+
+
+def _pack(eri):
+    """(pq|rs) -> the upper triangle of the (p>=q) x (r>=s) pair matrix (8-fold symmetry: 45 150 of 331 776 numbers)"""
+    n = eri.shape[0]
+    i, j = np.tril_indices(n)
+    m = eri[i, j][:, i, j]
+    a, b = np.triu_indices(len(i))
+    return m[a, b]
+
+
+def _unpack(packed, n):
+    i, j = np.tril_indices(n)
+    npair = len(i)
+    m = np.zeros((npair, npair))
+    a, b = np.triu_indices(npair)
+    m[a, b] = packed
+    m[b, a] = packed
+    pidx = np.zeros((n, n), dtype=np.int64)
+    pidx[i, j] = np.arange(npair); pidx[j, i] = np.arange(npair)
+    return m[pidx.reshape(-1)][:, pidx.reshape(-1)].reshape(n, n, n, n)
+
+
+def save(r, path=FIXTURE):
+    np.savez_compressed(path, escf=r["escf"], ecc=r["ecc"], eps=r["eps"], irrep=r["irrep"], t1s=r["t1s"], t2s=r["t2s"],
+                        eri_packed=_pack(r["eri_mo"]))
+
+
+def load(path=FIXTURE):
+    """The committed fixture (generated by this module): dict(escf, ecc, eps[24], irrep[24], t1s[19,5], t2s[19,19,5,5],
+    eri_mo[24,24,24,24] = (pq|rs) over the canonical RHF orbitals in energy order)."""
+    d = np.load(path)
+    out = {k: d[k] for k in d.files if k != "eri_packed"}
+    out["eri_mo"] = _unpack(d["eri_packed"], len(d["eps"]))
+    return out
+
+
+def qa_stores(r=None, tilesize=20, c2v=True, restricted=True, intorb=False):
+    """TCE block stores of the QA case from the real tensors.  c2v: the tiling of the QA run itself (the tile table of
+    tce_ccsd_t_h2o.out:644-659: occupied a1 3, b1 1, b2 1; virtual a1 8, a2 2, b1 6, b2 3 per spin); otherwise C1."""
+    from nwchem_b200 import synth, tiling as tl
+    r = load() if r is None else r
+    eps, irr = r["eps"], r["irrep"]
+    no, nv = 5, len(eps) - 5
+    if c2v:
+        occ = [int(np.sum(irr[:no] == g)) for g in range(4)]
+        virt = [int(np.sum(irr[no:] == g)) for g in range(4)]
+        oo = np.concatenate([np.where(irr[:no] == g)[0] for g in range(4)])          # occupied, grouped by irrep
+        vo = np.concatenate([np.where(irr[no:] == g)[0] for g in range(4)])          # virtual, grouped by irrep
+    else:
+        occ, virt = [no], [nv]
+        oo, vo = np.arange(no), np.arange(nv)
+    perm = np.concatenate([oo, no + vo])
+    t = tl.make_tiling(occ, virt, tilesize, restricted, evl=(eps[:no][oo], eps[no:][vo]))
+    t1s = r["t1s"][np.ix_(vo, oo)]
+    t2s = r["t2s"][np.ix_(vo, vo, oo, oo)]
+    eri = r["eri_mo"][np.ix_(perm, perm, perm, perm)]
+    return synth.physical(t, intorb=intorb, dense=(no, nv, t1s, t2s, eri))
+
+
+if __name__ == "__main__":
+    r = generate()
+    save(r)
+    print("wrote", FIXTURE, os.path.getsize(FIXTURE), "bytes")

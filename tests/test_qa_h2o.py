@@ -1,0 +1,135 @@
+"""The reference's own golden vectors for this path: QA/tests/tce_ccsd_t_h2o (H2O, cc-pVDZ, RHF, CCSD(T)).
+
+tce_ccsd_t_h2o.out holds the only numbers the reference ships that pin the (T) path end to end:
+    :390  Total SCF energy                 -76.026807857236
+    :734  CCSD correlation energy           -0.213269954065481
+    :743  CCSD[T] correction energy         -0.003139909173705
+    :746  CCSD(T) correction energy         -0.003054718622142
+(the input also quotes -0.21640986353 / -0.21632467284 from an independent code, tce_ccsd_t_h2o.nw:5-6: the correlation
+energies, which the two corrections above reproduce).  They need converged CCSD amplitudes and MO integrals.
+oracle/h2o_ccsd.py computes those from first principles in numpy (McMurchie-Davidson integrals over the library's
+cc-pVDZ data, RHF, spin-orbital CCSD) and reproduces the SCF and CCSD energies of the QA output to 5e-10 Eh; the fixture
+tests/golden/h2o_ccpvdz_ccsd.npz is its output.  Here the oracle's restatement of the reference's (T) driver, run on
+those amplitudes on the QA run's own tile table, must give the golden corrections -- which pins the oracle (tables,
+filters, restricted mapping, kernels, factors, energy expression) against the reference's test data; the CUDA library is
+then held to the same numbers.  The remaining 2-3e-10 Eh is the convergence of the QA run's CCSD (its threshold is 1e-7
+on the residual), not of the (T) step: every tiling of the same amplitudes agrees to 1e-15."""
+import dataclasses
+import json
+import os
+import numpy as np
+import pytest
+from nwchem_b200 import synth, tiling as tl
+
+TOL = 1.0e-9        # Eh: against the QA output (limited by the CCSD convergence of the QA run and of the fixture)
+
+
+@pytest.fixture(scope="module")
+def qa():
+    from oracle import h2o_ccsd
+    return h2o_ccsd, h2o_ccsd.load()
+
+
+def test_fixture_reproduces_the_qa_scf_and_ccsd_energies(qa):
+    h, r = qa
+    assert abs(float(r["escf"]) - h.QA["scf"]) <= TOL
+    assert abs(float(r["ecc"]) - h.QA["ccsd_corr"]) <= TOL
+    assert r["t1s"].shape == (19, 5) and r["t2s"].shape == (19, 19, 5, 5) and r["eri_mo"].shape == (24,) * 4
+    # the correlation energy recomputed from the stored amplitudes and integrals (closed-shell formula)
+    no = 5
+    g = r["eri_mo"][no:, :no, no:, :no]                                      # (ai|bj)
+    tau = r["t2s"] + np.einsum("ai,bj->abij", r["t1s"], r["t1s"])
+    e = np.einsum("aibj,abij->", 2.0 * g - g.transpose(2, 1, 0, 3), tau)
+    assert abs(e - h.QA["ccsd_corr"]) <= TOL
+
+
+def test_oracle_on_the_qa_tile_table_gives_the_golden_triples_corrections(oracle, qa):
+    h, r = qa
+    st = h.qa_stores(r, tilesize=20, c2v=True)
+    t = st.t
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "h2o_tile_table.json")))
+    # the tiling derived from the computed orbital symmetries IS the tile table of the QA output (:644-659)
+    assert t.noab == 6 and t.nvab == 8
+    assert [int(x) for x in t.range] == gold["size"] and [int(x) for x in t.sym] == gold["irrep"]
+    assert [int(x) for x in t.spin] == gold["spin"] and [int(x) for x in t.offset] == gold["offset"]
+    assert [int(x) for x in t.alpha] == gold["alpha"]
+    o = oracle.ccsd_t(st)
+    assert len(o["tasks"]) == 230
+    assert abs(o["e1"] - h.QA["t_bracket"]) <= TOL, (o["e1"], h.QA["t_bracket"])
+    assert abs(o["e2"] - h.QA["t_paren"]) <= TOL, (o["e2"], h.QA["t_paren"])
+    # the independent code's correlation energies quoted in the QA input (tce_ccsd_t_h2o.nw:5-6, 11 digits)
+    assert abs(h.QA["ccsd_corr"] + o["e2"] - (-0.21632467284)) <= 2e-9
+    assert abs(h.QA["ccsd_corr"] + o["e1"] - (-0.21640986353)) <= 2e-9
+    ref = (o["e1"], o["e2"])
+    for ts, c2v, restricted in ((20, False, True), (7, False, True), (3, True, True), (20, True, False)):
+        o2 = oracle.ccsd_t(h.qa_stores(r, tilesize=ts, c2v=c2v, restricted=restricted))
+        assert abs(o2["e1"] - ref[0]) <= 1e-15 and abs(o2["e2"] - ref[1]) <= 1e-15, (ts, c2v, restricted)
+    # the reference's second formulation (ccsd_t_restart.F runs the TCE-generated singles / doubles) on the same data
+    b, tab, te, done = oracle.ccsd_t_restart(st)
+    assert abs(te - ref[1]) <= 1e-15
+
+
+def test_2eorb_store_of_the_real_integrals(oracle, qa):
+    h, r = qa
+    st = h.qa_stores(r, tilesize=20, c2v=True, intorb=True)
+    o = oracle.ccsd_t(st)                                                     # V2 antisymmetrised block by block from the orbital store
+    assert abs(o["e1"] - h.QA["t_bracket"]) <= TOL and abs(o["e2"] - h.QA["t_paren"]) <= TOL
+
+
+def test_native_driver_trace_on_the_real_amplitudes(oracle, qa):
+    """the library's host driver (trace context, no GPU) on the real data: tiles == the oracle's, and the energies summed
+    from them over the whole QA task list == the golden corrections"""
+    from nwchem_b200 import capi
+    from test_trace import evaluate, _energies
+    h, r = qa
+    st = h.qa_stores(r, tilesize=20, c2v=True)
+    tr = capi.Triples(trace=True)
+    tr.set_state(st)
+    e1 = e2 = 0.0
+    for k, tup in enumerate(oracle.task_list(st.t)):
+        tup = [int(x) for x in tup[:6]]
+        recs, keep = tr.trace_tuple(tup, 0)
+        d, _, s, f, _ = evaluate(recs)
+        if k % 23 == 0:
+            s_ref, d_ref = oracle.tuple_tiles(st, tup)[:2]
+            assert np.max(np.abs(d - d_ref)) <= 1e-16 and np.max(np.abs(s - s_ref)) <= 1e-16
+        a, b = _energies(st.t, tup, d, d, s, f)
+        e1 += a; e2 += b
+    tr.close()
+    assert abs(e1 - h.QA["t_bracket"]) <= TOL and abs(e2 - h.QA["t_paren"]) <= TOL
+
+
+def test_fixture_is_reproducible_from_first_principles(qa):
+    """integrals -> RHF -> CCSD again, now (about 25 s): the committed fixture is this script's output, and each stage hits
+    the QA output's energy"""
+    h, r = qa
+    g = h.generate(verbose=False)
+    assert abs(g["escf"] - h.QA["scf"]) <= TOL and abs(g["ecc"] - h.QA["ccsd_corr"]) <= TOL
+    assert np.array_equal(g["irrep"], r["irrep"])
+    assert np.max(np.abs(g["eps"] - r["eps"])) <= 1e-9
+    # amplitudes are defined up to the signs of the orbitals; compare sign-invariant quantities
+    assert abs(np.linalg.norm(g["t2s"]) - np.linalg.norm(r["t2s"])) <= 1e-9
+    assert abs(np.linalg.norm(g["t1s"]) - np.linalg.norm(r["t1s"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_library_gives_the_golden_triples_corrections(oracle, qa):
+    """Both ABI tiers and the `2eorb` storage on the real amplitudes, on the QA run's tile table: against the QA output
+    (1e-9 Eh) and against the oracle per task (1e-13)."""
+    from nwchem_b200 import capi
+    h, r = qa
+    st = h.qa_stores(r, tilesize=20, c2v=True, intorb=True)
+    ref = oracle.ccsd_t(st)
+    plain = dataclasses.replace(st, orb=None)
+    tr = capi.Triples(0)
+    tr.set_state(plain)
+    e1, e2, pt = tr.run(per_task=True)
+    assert np.asarray(tr.task_list())[:, :6].tolist() == ref["tasks"][:, :6].tolist()
+    tr.set_state_2eorb(st)
+    f1, f2 = tr.run()
+    tr.close()
+    c1, c2, _ = capi.ccsd_t_gpu(plain)
+    for a, b in ((e1, e2), (f1, f2), (c1, c2)):
+        assert abs(a - h.QA["t_bracket"]) <= TOL and abs(b - h.QA["t_paren"]) <= TOL, (a, b)
+        assert abs(a - ref["e1"]) <= 1e-12 and abs(b - ref["e2"]) <= 1e-12
+    assert np.max(np.abs(pt - ref["per_task"])) <= 1e-13
