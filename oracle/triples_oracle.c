@@ -8,9 +8,15 @@
  * Every function cites the reference file:line (relative to /root/reference) it follows.
  * Arrays are Fortran column-major restated with explicit 0-based index arithmetic.
  *
- * PARITY PIN STATUS: the reference ships no kernel-level golden vectors for this path and
- * its Fortran cannot be compiled in this image (no Fortran compiler, no GA/MPI).  The
- * oracle is pinned by (i) the H2O/cc-pVDZ tile table of QA/tests/tce_ccsd_t_h2o
+ * PARITY PIN STATUS: PINNED against the reference's own golden vectors.  The end-to-end
+ * energies of QA/tests/tce_ccsd_t_h2o (tce_ccsd_t_h2o.out:743,:746: CCSD[T] correction
+ * -0.003139909173705, CCSD(T) correction -0.003054718622142) are reproduced to 3e-10 Eh by
+ * this restatement run on CCSD amplitudes and MO integrals computed from first principles
+ * (oracle/h2o_ccsd.py: integrals, RHF, CCSD in numpy, themselves matching the QA output's
+ * SCF and CCSD energies to 5e-10 Eh) on the QA run's own tile table (tests/test_qa_h2o.py).
+ * Further pins -- the reference ships no kernel-level golden vectors for this path and
+ * its Fortran cannot be compiled in this image (no Fortran compiler, no GA/MPI): (i) the
+ * H2O/cc-pVDZ tile table of QA/tests/tce_ccsd_t_h2o
  * (tce_ccsd_t_h2o.out:644-659), (ii) agreement of the 27 kernels + energy kernel with the
  * reference's own CUDA implementation (sd_t_total.cu + memory.cu compiled unmodified into
  * oracle/_ref, run on the GPU box), (iii) the reference's independent second formulation of
@@ -18,8 +24,7 @@
  * ccsd_t_singles.F / ccsd_t_doubles.F) on every tuple of the H2O table, (iv) tile-size
  * invariance of E[T]/E(T) on antisymmetric synthetic amplitudes, (v) for the `2eorb` path,
  * bit-exact reconstruction of every spin-orbital V2 block from an orbital-form store of the
- * same integrals.  End-to-end energies of the QA outputs need converged CCSD amplitudes
- * that nothing in scope can produce: that part is unpinned.
+ * same integrals.
  */
 #include <stdio.h>
 #include <stdlib.h>
