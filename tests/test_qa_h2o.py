@@ -57,6 +57,8 @@ def test_oracle_on_the_qa_tile_table_gives_the_golden_triples_corrections(oracle
     assert len(o["tasks"]) == 230
     assert abs(o["e1"] - h.QA["t_bracket"]) <= TOL, (o["e1"], h.QA["t_bracket"])
     assert abs(o["e2"] - h.QA["t_paren"]) <= TOL, (o["e2"], h.QA["t_paren"])
+    # QA/tests/tce_cuda: the same molecule through the reference's CUDA back-end (tce_cuda.out:748,:751)
+    assert abs(o["e1"] - (-0.003139909174016)) <= TOL and abs(o["e2"] - (-0.003054718621780)) <= TOL
     # the independent code's correlation energies quoted in the QA input (tce_ccsd_t_h2o.nw:5-6, 11 digits)
     assert abs(h.QA["ccsd_corr"] + o["e2"] - (-0.21632467284)) <= 2e-9
     assert abs(h.QA["ccsd_corr"] + o["e1"] - (-0.21640986353)) <= 2e-9
@@ -132,4 +134,5 @@ def test_gpu_library_gives_the_golden_triples_corrections(oracle, qa):
     for a, b in ((e1, e2), (f1, f2), (c1, c2)):
         assert abs(a - h.QA["t_bracket"]) <= TOL and abs(b - h.QA["t_paren"]) <= TOL, (a, b)
         assert abs(a - ref["e1"]) <= 1e-12 and abs(b - ref["e2"]) <= 1e-12
+        assert abs(a - (-0.003139909174016)) <= TOL and abs(b - (-0.003054718621780)) <= TOL      # tce_cuda.out:748,:751
     assert np.max(np.abs(pt - ref["per_task"])) <= 1e-13
