@@ -41,6 +41,23 @@ BASIS = {
 # tce_ccsd_t_h2o.out
 QA = dict(scf=-76.026807857236, ccsd_corr=-0.213269954065481, t_bracket=-0.003139909173705, t_paren=-0.003054718622142)
 
+# QA/tests/tce_ozone_2eorb (tce_ozone_2eorb.nw: O3, the inline [5s3p2d] basis, RHF, `freeze atomic`, `2eorb`, CCSD(T)) and
+# QA/tests/tce_ccsd_t_xmem (same molecule and basis, symmetry c1, the sliced (T) of ccsd_t_6dts.F under tce:xmem)
+OZONE_GEOM = [("O", 8.0, (0.0, 0.0, 0.0)), ("O", 8.0, (0.0, -2.0473224350, -1.2595211660)), ("O", 8.0, (0.0, 2.0473224350, -1.2595211660))]
+OZONE_BASIS = {
+    "O": [(0, [10662.285, 1599.7097, 364.72526, 103.65179, 33.905805], [[0.000799, 0.006153, 0.031157, 0.115596, 0.301552]]),
+          (0, [12.287469, 4.756805], [[0.44487, 0.243172]]),
+          (0, [1.004271], [[1.0]]), (0, [0.300686], [[1.0]]), (0, [0.09003], [[1.0]]),
+          (1, [34.856463, 7.843131, 2.306249, 0.723164], [[0.015648, 0.098197, 0.307768, 0.49247]]),
+          (1, [0.214882], [[1.0]]), (1, [0.06385], [[1.0]]),
+          (2, [2.3062, 0.7232], [[0.2027, 0.5791]]),
+          (2, [0.2149, 0.0639], [[0.78545, 0.53387]])],
+}
+# tce_ozone_2eorb.out:396,:898,:908,:911 ; tce_ccsd_t_xmem.out:378,:865,:876,:879
+QA_OZONE = dict(scf=-224.327430429177, ccsd_corr=-0.631946819284344, t_bracket=-0.039379872138382, t_paren=-0.036050224214312,
+                xmem=dict(scf=-224.327430428908, ccsd_corr=-0.631946818916447, t_bracket=-0.039379871636142, t_paren=-0.036050224479361))
+FIXTURE_OZONE = os.path.join(os.path.dirname(HERE), "tests", "golden", "ozone_ccsd.npz")
+
 CART = {0: [(0, 0, 0)], 1: [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
         2: [(2, 0, 0), (0, 2, 0), (0, 0, 2), (1, 1, 0), (1, 0, 1), (0, 1, 1)]}
 # real solid harmonics of l = 2 over (xx, yy, zz, xy, xz, yz); unnormalised (see the module docstring)
@@ -67,12 +84,14 @@ def check_basis_against_reference(path="/root/reference/src/basis/libraries/cc-p
 # ------------------------------------------------------------------------------------------------------------------
 # primitive Cartesian functions and the contraction to the 24 spherical basis functions
 # ------------------------------------------------------------------------------------------------------------------
-def build_basis():
+def build_basis(geom=None, basis=None):
+    geom = GEOM if geom is None else geom
+    basis = BASIS if basis is None else basis
     prim = []      # (center, exponent, (i,j,k))
     rows = []      # contraction: list of (basis function index, prim index, coefficient)
     nbf = 0
-    for el, z, R in GEOM:
-        for l, exps, cols in BASIS[el]:
+    for el, z, R in geom:
+        for l, exps, cols in basis[el]:
             first = len(prim)
             for a in exps:
                 for ijk in CART[l]:
@@ -164,15 +183,18 @@ def hermite_R(Lmax, alpha, X, Y, Z):
     return {k[:3]: v for k, v in R.items() if k[3] == 0}
 
 
-def integrals():
-    """(S, T, V, eri, Enuc) over the 24 contracted spherical functions; eri[p,q,r,s] = (pq|rs)."""
-    prim, C = build_basis()
+def integrals(geom=None, basis=None, screen=1e-16, chunk=16000, verbose=False):
+    """(S, T, V, eri, Enuc) over the contracted spherical functions; eri[p,q,r,s] = (pq|rs).  Primitive pairs whose
+    Hermite coefficients are all below `screen` (tight functions on different centres) are dropped."""
+    geom = GEOM if geom is None else geom
+    prim, C = build_basis(geom, basis)
     n = len(prim)
+    nbf = C.shape[1]
     pairs = [(i, j) for i in range(n) for j in range(i + 1)]
     npair = len(pairs)
     P = np.zeros((npair, 3)); pp = np.zeros(npair); EH = np.zeros((npair, len(HERM)))
-    S = np.zeros((n, n)); Tk = np.zeros((n, n)); V = np.zeros((n, n))
-    nuc = [(z, np.array(R)) for _, z, R in GEOM]
+    S = np.zeros((n, n)); Tk = np.zeros((n, n))
+    nuc = [(z, np.array(R)) for _, z, R in geom]
     for k, (i, j) in enumerate(pairs):
         A, a, la = prim[i]; B, b, lb = prim[j]
         p = a + b
@@ -192,39 +214,92 @@ def integrals():
               for d in range(3)]
         S[i, j] = S[j, i] = s[0] * s[1] * s[2]
         Tk[i, j] = Tk[j, i] = t1[0] * s[1] * s[2] + s[0] * t1[1] * s[2] + s[0] * s[1] * t1[2]
-        vv = 0.0
-        for z, Rc in nuc:
-            d = Pc - Rc
-            R = hermite_R(4, np.array([p]), np.array([d[0]]), np.array([d[1]]), np.array([d[2]]))
-            vv += -z * (2 * np.pi / p) * sum(EH[k, idx] * R[h][0] for h, idx in HIDX.items() if EH[k, idx] != 0.0)
-        V[i, j] = V[j, i] = vv
-    # two-electron integrals over primitive pairs, in chunks
-    nh = len(HERM)
-    sign = np.array([(-1.0) ** sum(h) for h in HERM])
-    keys = sorted({tuple(np.add(h, g)) for h in HERM for g in HERM})
-    kpos = {kk: m for m, kk in enumerate(keys)}
-    gather = np.array([[kpos[tuple(np.add(h, g))] for g in HERM] for h in HERM])
-    eri_pp = np.zeros((npair, npair))
-    chunk = 4000
-    idxA, idxB = np.tril_indices(npair)
-    for c0 in range(0, len(idxA), chunk):
-        ia = idxA[c0:c0 + chunk]; ib = idxB[c0:c0 + chunk]
-        p = pp[ia]; q = pp[ib]
-        alpha = p * q / (p + q)
-        d = P[ia] - P[ib]
-        R = hermite_R(8, alpha, d[:, 0], d[:, 1], d[:, 2])
-        Rm = np.stack([R[kk] for kk in keys], axis=1)                      # [chunk, nkeys]
-        G = Rm[:, gather]                                                 # [chunk, nh, nh]
-        val = np.einsum("bh,bhg,bg->b", EH[ia], G, EH[ib] * sign[None, :])
-        val *= 2.0 * np.pi ** 2.5 / (p * q * np.sqrt(p + q))
-        eri_pp[ia, ib] = val
-        eri_pp[ib, ia] = val
-    # unpack pairs and contract
-    pidx = np.zeros((n, n), dtype=np.int64)
+    # nuclear attraction, all pairs at once per nucleus: V_ij = -Z (2 pi / p) sum_tuv E_tuv R_tuv(p, P - C)
+    vpair = np.zeros(npair)
+    for z, Rc in nuc:
+        d = P - Rc[None, :]
+        R = hermite_R(4, pp, d[:, 0], d[:, 1], d[:, 2])
+        vpair += -z * (2 * np.pi / pp) * sum(EH[:, idx] * R[h] for h, idx in HIDX.items())
+    V = np.zeros((n, n))
     for k, (i, j) in enumerate(pairs):
-        pidx[i, j] = pidx[j, i] = k
-    eri_prim = eri_pp[pidx.reshape(-1)][:, pidx.reshape(-1)].reshape(n, n, n, n)
-    eri = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri_prim, C, C, C, C, optimize=True)
+        V[i, j] = V[j, i] = vpair[k]
+    # contraction of primitive pairs to contracted pairs: W[k, (a>=b)] so that (ab| = sum_k W[k,ab] (k|
+    ia, ib = np.tril_indices(nbf)
+    W = np.zeros((npair, len(ia)))
+    for k, (i, j) in enumerate(pairs):
+        w = C[i][ia] * C[j][ib]
+        if i != j:
+            w = w + C[j][ia] * C[i][ib]
+        W[k] = w
+    keep = np.where((np.max(np.abs(EH), axis=1) > screen) & (np.max(np.abs(W), axis=1) > 0))[0]
+    if verbose:
+        print(f"primitive functions {n}, pairs {npair}, kept {len(keep)}", flush=True)
+    # sort the kept pairs by total angular momentum: a pair of L needs only the (L+1)(L+2)(L+3)/6 leading Hermite terms
+    Lpair = np.array([sum(prim[i][2]) + sum(prim[j][2]) for (i, j) in pairs])[keep]
+    order = np.argsort(Lpair, kind="stable")
+    keep = keep[order]; Lpair = Lpair[order]
+    EHk, Pk, ppk, Wk = EH[keep], P[keep], pp[keep], W[keep]
+    nk = len(keep)
+    nherm = [(L + 1) * (L + 2) * (L + 3) // 6 for L in range(5)]
+    groups = [np.where(Lpair == L)[0] for L in range(5)]
+    sign = np.array([(-1.0) ** sum(h) for h in HERM])
+    EHs = EHk * sign[None, :]
+    npc = len(ia)
+    half = np.zeros((nk, npc))                                            # half[a, (cd)] = sum_b (a|b) W[b, cd]
+    tables = {}
+
+    def table(LA, LB):
+        if (LA, LB) not in tables:
+            hs, gs = HERM[:nherm[LA]], HERM[:nherm[LB]]
+            keys = sorted({tuple(np.add(h, g)) for h in hs for g in gs})
+            kpos = {kk: m for m, kk in enumerate(keys)}
+            tables[(LA, LB)] = (keys, np.array([[kpos[tuple(np.add(h, g))] for g in gs] for h in hs]))
+        return tables[(LA, LB)]
+
+    def block(ra, rb, LA, LB):
+        """(a|b) for every a in ra, b in rb (index arrays into the kept pairs): matrix [len(ra), len(rb)]"""
+        keys, gather = table(LA, LB)
+        A = np.repeat(ra, len(rb)); B = np.tile(rb, len(ra))
+        p = ppk[A]; q = ppk[B]
+        alpha = p * q / (p + q)
+        d = Pk[A] - Pk[B]
+        R = hermite_R(LA + LB, alpha, d[:, 0], d[:, 1], d[:, 2])
+        Rm = np.stack([R[kk] for kk in keys], axis=1)
+        val = np.einsum("bh,bhg,bg->b", EHk[A][:, :nherm[LA]], Rm[:, gather], EHs[B][:, :nherm[LB]], optimize=True)
+        val *= 2.0 * np.pi ** 2.5 / (p * q * np.sqrt(p + q))
+        return val.reshape(len(ra), len(rb))
+
+    done = 0
+    for LA in range(5):
+        for LB in range(LA + 1):
+            ga, gb = groups[LA], groups[LB]
+            if len(ga) == 0 or len(gb) == 0:
+                continue
+            per = max(1, int(chunk * 1500 / (len(gb) * nherm[LA] * nherm[LB])))   # ~ chunk * 1500 gathered R values per batch
+            for a0 in range(0, len(ga), per):
+                ra = ga[a0:a0 + per]
+                if LA == LB:
+                    rb = gb[:a0 + len(ra)]                                # lower triangle of the diagonal class block
+                else:
+                    rb = gb
+                val = block(ra, rb, LA, LB)
+                if LA == LB:
+                    # rows ra against columns rb (which end with ra itself): count the ra x ra part once
+                    nlow = a0
+                    half[ra] += val @ Wk[rb]
+                    if nlow:
+                        half[rb[:nlow]] += val[:, :nlow].T @ Wk[ra]
+                else:
+                    half[ra] += val @ Wk[rb]
+                    half[rb] += val.T @ Wk[ra]
+                done += val.size
+            if verbose:
+                print(f"  eri class ({LA},{LB}): {len(ga)} x {len(gb)} pairs", flush=True)
+    full = Wk.T @ half                                                    # [(ab), (cd)]
+    pidx = np.zeros((nbf, nbf), dtype=np.int64)
+    pidx[ia, ib] = np.arange(npc); pidx[ib, ia] = np.arange(npc)
+    eri = full[pidx.reshape(-1)][:, pidx.reshape(-1)].reshape(nbf, nbf, nbf, nbf)
+    eri = 0.5 * (eri + eri.transpose(2, 3, 0, 1))
     Sc = C.T @ S @ C; Tc = C.T @ Tk @ C; Vc = C.T @ V @ C
     enuc = sum(nuc[i][0] * nuc[j][0] / np.linalg.norm(nuc[i][1] - nuc[j][1]) for i in range(len(nuc)) for j in range(i))
     return Sc, Tc, Vc, eri, float(enuc)
@@ -264,7 +339,7 @@ def rhf(S, T, V, eri, enuc, nocc=5, tol=1e-12, maxit=200):
     return E, e, Cm
 
 
-def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200):
+def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200, rms_tol=1e-10):
     """Spin-orbital CCSD (Stanton, Gauss, Watts, Bartlett, J. Chem. Phys. 94, 4334 (1991)) for a canonical closed-shell RHF
     reference; returns (correlation energy, t1s[a,i], t2s[a,b,i,j]) -- the spatial amplitudes t_i^a, t_{ij}^{ab} (alpha-beta)."""
     n = len(eps)
@@ -284,7 +359,9 @@ def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200):
     D2 = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
     t1 = np.zeros((no, nso - no))
     t2 = v[o, o, vv, vv] / D2
-    E = np.einsum
+
+    def E(*a):
+        return np.einsum(*a, optimize=True)
 
     def energy(t1, t2):
         return 0.25 * E("ijab,ijab->", v[o, o, vv, vv], t2) + 0.5 * E("ijab,ia,jb->", v[o, o, vv, vv], t1, t1)
@@ -336,7 +413,7 @@ def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200):
         rms = np.sqrt(err_l[-1] @ err_l[-1])
         t1, t2 = t1n, t2n
         Ecc += dE
-        if abs(dE) < tol and rms < 1e-10:
+        if abs(dE) < tol and rms < rms_tol:
             break
     # spatial amplitudes: alpha = even spin orbitals
     oa = np.arange(0, no, 2); ob = oa + 1
@@ -346,20 +423,25 @@ def ccsd(eps, eri_mo, nocc=5, tol=1e-11, maxit=200):
     return float(Ecc), t1s, t2s
 
 
-def mo_irreps(S, Cm):
+def mo_irreps(S, Cm, geom=None, basis=None, inplane_code=2):
     """C2v irrep code (0 a1, 1 a2, 2 / 3 the two b irreps; XOR = direct product) of every MO from its parities under
-    x -> -x and y -> -y.  The molecule lies in the yz plane; y -> -y swaps the hydrogens.  Code 2 goes to the in-plane
-    antisymmetric irrep, the one with six virtual orbitals, as in the QA tile table (tce_ccsd_t_h2o.out:644-659)."""
+    x -> -x and y -> -y.  The molecule lies in the yz plane; y -> -y swaps the off-axis atoms.  `inplane_code` goes to the
+    in-plane antisymmetric irrep: 2 for H2O (the one with six virtual orbitals, b1 in the QA tile table
+    tce_ccsd_t_h2o.out:644-659), 3 for ozone (b2 in tce_ozone_2eorb.out)."""
+    geom = GEOM if geom is None else geom
+    basis = BASIS if basis is None else basis
     labels = []       # per basis function: (atom, shell key, power of x, power of y)
-    for ia, (el, z, R) in enumerate(GEOM):
-        for ish, (l, exps, cols) in enumerate(BASIS[el]):
+    for ia, (el, z, R) in enumerate(geom):
+        for ish, (l, exps, cols) in enumerate(basis[el]):
             comps = {0: [(0, 0)], 1: [(1, 0), (0, 1), (0, 0)], 2: [(0, 0), (0, 0), (1, 1), (1, 0), (0, 1)]}[l]
             for icol in range(len(cols)):
                 for ic, (px, py) in enumerate(comps):
                     labels.append((ia, (ish, icol, ic), px, py))
     n = len(labels)
     Px = np.zeros((n, n)); Py = np.zeros((n, n))
-    swap = {0: 0, 1: 2, 2: 1}
+    swap = {}         # image of every atom under y -> -y
+    for ia, (el, z, R) in enumerate(geom):
+        swap[ia] = [ja for ja, (_, _, Q) in enumerate(geom) if abs(Q[0] - R[0]) < 1e-9 and abs(Q[1] + R[1]) < 1e-9 and abs(Q[2] - R[2]) < 1e-9][0]
     for i, (ia, key, px, py) in enumerate(labels):
         Px[i, i] = (-1.0) ** px
         j = [k for k, (ja, kk, _, _) in enumerate(labels) if ja == swap[ia] and kk == key][0]
@@ -370,8 +452,28 @@ def mo_irreps(S, Cm):
         ex = float(c @ S @ (Px @ c)); ey = float(c @ S @ (Py @ c))
         assert abs(abs(ex) - 1.0) < 1e-6 and abs(abs(ey) - 1.0) < 1e-6, (m, ex, ey)
         sx, sy = ex > 0, ey > 0
-        out.append(0 if (sx and sy) else 1 if (not sx and not sy) else 2 if (sx and not sy) else 3)
+        inp, outp = inplane_code, 5 - inplane_code
+        out.append(0 if (sx and sy) else 1 if (not sx and not sy) else inp if (sx and not sy) else outp)
     return np.array(out, dtype=np.int64)
+
+
+def generate_ozone(verbose=True):
+    """The ozone case of QA/tests/tce_ozone_2eorb and tce_ccsd_t_xmem: 72 basis functions, 12 occupied orbitals of which the
+    three O 1s cores are frozen (`freeze atomic`), 60 virtuals.  About 15 minutes and 15 GB; the result is too large for a
+    committed fixture (the <pp||hp> class alone is 8 MB), so tests/test_qa_h2o.py runs it only when NWC_QA_OZONE=1 and
+    the log of that run is kept in profiles/."""
+    S, T, V, eri, enuc = integrals(OZONE_GEOM, OZONE_BASIS, verbose=verbose)
+    escf, eps, Cm = rhf(S, T, V, eri, enuc, nocc=12)
+    if verbose:
+        print(f"SCF   {escf:.12f}   QA {QA_OZONE['scf']:.12f}   diff {escf - QA_OZONE['scf']:.2e}", flush=True)
+    irrep = mo_irreps(S, Cm, OZONE_GEOM, OZONE_BASIS, inplane_code=3)
+    nfz = 3
+    Ca = Cm[:, nfz:]
+    eri_mo = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri, Ca, Ca, Ca, Ca, optimize=True)
+    ecc, t1s, t2s = ccsd(eps[nfz:], eri_mo, nocc=12 - nfz)
+    if verbose:
+        print(f"CCSD  {ecc:.12f}   QA {QA_OZONE['ccsd_corr']:.12f}   diff {ecc - QA_OZONE['ccsd_corr']:.2e}", flush=True)
+    return dict(escf=escf, ecc=ecc, eps=eps[nfz:], irrep=irrep[nfz:], t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=12 - nfz)
 
 
 def generate(verbose=True):
@@ -429,7 +531,8 @@ def qa_stores(r=None, tilesize=20, c2v=True, restricted=True, intorb=False):
     from nwchem_b200 import synth, tiling as tl
     r = load() if r is None else r
     eps, irr = r["eps"], r["irrep"]
-    no, nv = 5, len(eps) - 5
+    no = int(r["nocc"]) if "nocc" in r else 5
+    nv = len(eps) - no
     if c2v:
         occ = [int(np.sum(irr[:no] == g)) for g in range(4)]
         virt = [int(np.sum(irr[no:] == g)) for g in range(4)]
