@@ -31,8 +31,12 @@ class Dense:
     """Dense spin-orbital tensors of the closed-shell synthetic problem of synth.physical.  Spin-orbital g of spatial
     orbital x and spin s (0 alpha, 1 beta) is x + n*s; holes are the x < no, particles the x >= no."""
 
-    def __init__(self, t: tl.Tiling, seed: int = 20240229, fock_seed: int = 4242, t_scale: float = 1.0):
-        no, nv, t1s, t2s, eri = synth.physical_dense(t, seed)
+    def __init__(self, t: tl.Tiling, seed: int = 20240229, fock_seed: int = 4242, t_scale: float = 1.0, dense=None,
+                 fock_hp=None):
+        """dense = (no, nv, t1s, t2s, eri) replaces the synthetic tensors (real amplitudes: oracle/h2o_ccsd.py), in the
+        spatial-orbital order of the tiling; fock_hp[i,a] then gives the (hole, particle) Fock block (zero for canonical
+        Hartree-Fock orbitals)."""
+        no, nv, t1s, t2s, eri = synth.physical_dense(t, seed) if dense is None else dense
         t1s = t1s * t_scale; t2s = t2s * t_scale
         n = no + nv
         self.t, self.no, self.nv, self.n = t, no, nv, n
@@ -59,6 +63,8 @@ class Dense:
             if t.spin[b] == 1:
                 irr[t.members[b]] = t.sym[b]
         fs[(irr[:no, None] ^ irr[None, no:]) != 0] = 0.0
+        if dense is not None:
+            fs = np.zeros((no, nv)) if fock_hp is None else np.asarray(fock_hp, dtype=np.float64)
         self.fs = fs
         self.f_hp = fs[np.ix_(xi, xa)] * d_ph.T                                # f(h,p)
         eps = np.zeros(2 * n)

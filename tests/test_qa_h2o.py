@@ -164,3 +164,27 @@ def test_ozone_frozen_core_2eorb_golden_energies(oracle):
     assert abs(o["e1"] - q["xmem"]["t_bracket"]) <= OZ and abs(o["e2"] - q["xmem"]["t_paren"]) <= OZ
     o2 = oracle.ccsd_t(h.qa_stores(r, tilesize=30, c2v=False))  # C1, tilesize 30, spin-orbital V2: the xmem run's setting
     assert abs(o2["e1"] - o["e1"]) <= 1e-13 and abs(o2["e2"] - o["e2"]) <= 1e-13
+
+
+def test_cr_ccsd_t_on_the_real_amplitudes_is_physically_sensible(oracle, qa):
+    """No QA case exercises cr-ccsd(t), so this is a plausibility check, not a golden vector: with the real CCSD
+    amplitudes of H2O the CR-CCSD(T) intermediates (oracle/cr_dense.py, the TCE expressions of cr_ccsd_t_N.F evaluated
+    densely) give a moment M that is the (T) doubles tile D to within 10 % (it is D plus higher orders in T), a
+    denominator overlap den0 = <T|T>-like of a few percent, and a CR-CCSD(T) correction that is the well-known 10-15 %
+    smaller than the (T) correction near equilibrium -- a wrong term or sign in any of the ~30 intermediate equations
+    would show here.  The tiled restatement equals the untiled dense evaluation on the real data too."""
+    from oracle import cr_dense
+    h, r = qa
+    eps = r["eps"]; no, nv = 5, 19
+    t = tl.make_tiling([no], [nv], 20, True, evl=(eps[:no], eps[no:]))
+    dense = (no, nv, r["t1s"], r["t2s"], r["eri_mo"])
+    st = synth.physical(t, dense=dense)
+    d = cr_dense.Dense(t, dense=dense)
+    cr = d.stores()
+    o = oracle.ccsd_t(st)
+    c = oracle.cr_ccsd_t(st, cr)
+    assert np.max(np.abs(np.array(d.dense_reference()[:4]) - c["sums"])) <= 1e-15
+    S, D, M, E = d.six_index()
+    assert 0.03 < np.linalg.norm(M - D) / np.linalg.norm(D) < 0.15
+    assert 0.03 < cr.den0 < 0.09
+    assert 0.82 < c["e2"] / o["e2"] < 0.95 and 0.82 < c["e1"] / o["e1"] < 0.95, (c["e1"], c["e2"], o["e1"], o["e2"])
