@@ -188,3 +188,100 @@ def test_cr_ccsd_t_on_the_real_amplitudes_is_physically_sensible(oracle, qa):
     assert 0.03 < np.linalg.norm(M - D) / np.linalg.norm(D) < 0.15
     assert 0.03 < cr.den0 < 0.09
     assert 0.82 < c["e2"] / o["e2"] < 0.95 and 0.82 < c["e1"] / o["e1"] < 0.95, (c["e1"], c["e2"], o["e1"], o["e2"])
+
+
+def _lambda_from_t(st):
+    """lambda_1 := t1^T, lambda_2 := t2^T block by block, f := 0 (LambdaStores)"""
+    t = st.t
+    lam = synth.physical_lambda(t)
+    y1 = np.zeros_like(lam.y1); y2 = np.zeros_like(lam.y2)
+    n = int(lam.y1_hash[0])
+    t1off = {int(st.t1_hash[1 + i]): int(st.t1_hash[1 + int(st.t1_hash[0]) + i]) for i in range(int(st.t1_hash[0]))}
+    for i in range(n):
+        key, off = int(lam.y1_hash[1 + i]), int(lam.y1_hash[1 + n + i])
+        h4b, p1b = key // t.nvab + 1, key % t.nvab + t.noab + 1
+        src = t1off[h4b - 1 + t.noab * (p1b - t.noab - 1)]
+        blk = st.t1[src:src + t.r(p1b) * t.r(h4b)].reshape(t.r(p1b), t.r(h4b))
+        y1[off:off + blk.size] = blk.T.ravel()
+    n = int(lam.y2_hash[0])
+    t2off = {int(st.t2_hash[1 + i]): int(st.t2_hash[1 + int(st.t2_hash[0]) + i]) for i in range(int(st.t2_hash[0]))}
+    for i in range(n):
+        key, off = int(lam.y2_hash[1 + i]), int(lam.y2_hash[1 + n + i])
+        k = key
+        p2b = k % t.nvab + t.noab + 1; k //= t.nvab
+        p1b = k % t.nvab + t.noab + 1; k //= t.nvab
+        h5b = k % t.noab + 1; k //= t.noab
+        h4b = k + 1
+        src = t2off[h5b - 1 + t.noab * (h4b - 1 + t.noab * (p2b - t.noab - 1 + t.nvab * (p1b - t.noab - 1)))]
+        dims = (t.r(p1b), t.r(p2b), t.r(h4b), t.r(h5b))
+        blk = st.t2[src:src + int(np.prod(dims))].reshape(dims)
+        y2[off:off + blk.size] = blk.transpose(2, 3, 0, 1).ravel()
+    return dataclasses.replace(lam, y1=y1, y2=y2, f1=np.zeros_like(lam.f1))
+
+
+def _bare_cr_stores(h, r, st):
+    """CR-CCSD(T) intermediates in the limit of no dressing: i1(hphh) = v(hphh), i1(pphp) = v(pphp) -- the dense builder with
+    zero amplitudes -- so that the moment tile M equals the (T) doubles tile D"""
+    from oracle import cr_dense
+    no = 5
+    irr, eps = r["irrep"], r["eps"]
+    oo = np.concatenate([np.where(irr[:no] == g)[0] for g in range(4)])
+    vo = np.concatenate([np.where(irr[no:] == g)[0] for g in range(4)])
+    perm = np.concatenate([oo, no + vo])
+    eri = r["eri_mo"][np.ix_(perm, perm, perm, perm)]
+    z1 = np.zeros((19, no)); z2 = np.zeros((19, 19, no, no))
+    return cr_dense.Dense(st.t, dense=(no, 19, z1, z2, eri)).stores()
+
+
+def test_sibling_restatements_reduce_to_the_golden_t_corrections(oracle, qa):
+    """The sibling corrections have no QA case of their own, but each contains the (T) correction as a limit, and on the
+    real amplitudes that limit must be the golden number:
+      Lambda-CCSD(T) with lambda := T^+ and f = 0:  E1 = sum f Td Yd/Delta -> CCSD[T],  E2 -> CCSD(T)
+          (the 36 permutation / sign pairs and operand fetches of lambda_ccsd_t_left.F, on real data);
+      CR-CCSD(T) with undressed intermediates (i1 := v):  num1 -> CCSD[T],  num2 -> CCSD(T)
+          (cr_ccsd_t_N_1 / _N_2 and their kernels with the transposed hphh layout);
+      CR-EOMCCSD(T) with r0 = 1, omega = 0, x = 0 and no EOM intermediates:  sum f R R/denex -> CCSD[T].
+    The same limits are taken through the LIBRARY's host driver (trace context) for the Lambda and CR tuples."""
+    from oracle import cr_dense
+    from nwchem_b200 import capi
+    from test_trace import evaluate, _energies
+    h, r = qa
+    st = h.qa_stores(r, tilesize=20, c2v=True, intorb=True)
+    plain = dataclasses.replace(st, orb=None)
+    g1, g2 = h.QA["t_bracket"], h.QA["t_paren"]
+    lam = _lambda_from_t(plain)
+    lo = oracle.lambda_ccsd_t(st, lam, sorted=True)
+    assert abs(lo["e1"] - g1) <= TOL and abs(lo["e2"] - g2) <= TOL, (lo["e1"], lo["e2"])
+    cr = _bare_cr_stores(h, r, plain)
+    co = oracle.cr_ccsd_t(plain, cr)
+    assert abs(co["sums"][0] - g1) <= TOL and abs(co["sums"][1] - g2) <= TOL, co["sums"]
+    z = lambda a: np.zeros_like(a)
+    q = cr_dense.CREOMStores(plain.t1_hash, z(plain.t1), plain.t2_hash, z(plain.t2), cr.n1_hash, z(cr.n1), cr.n2_hash, z(cr.n2),
+                             cr.n1_hash, z(cr.n1), cr.n2_hash, z(cr.n2), cr.e2_hash, z(cr.e2), 1.0, 0.0)
+    eo = oracle.cr_eomccsd_t(plain, cr, q)
+    assert abs(eo["sums"][0] - g1) <= TOL, eo["sums"]
+    # the library's host driver on the same limits
+    tr = capi.Triples(trace=True)
+    tr.set_state(plain)
+    tr.set_lambda(lam)
+    tr.set_cr(cr)
+    tr.set_creom(q)
+    le1 = le2 = ce1 = ce2 = ee1 = 0.0
+    for tup in oracle.task_list(plain.t):
+        tup = [int(x) for x in tup[:6]]
+        recs, keep = tr.trace_tuple(tup, 1)                    # Lambda: (Td | Yd, Ys)
+        td, yd, ys, f, _ = evaluate(recs)
+        a, b = _energies(plain.t, tup, td, yd, ys, f)
+        le1 += a; le2 += b
+        recs, keep = tr.trace_tuple(tup, 4)                    # CR, dual tuple: (M | D, S; E)
+        m, d, s, f, _, e = evaluate(recs)
+        a, b = _energies(plain.t, tup, m, d, s, f)
+        ce1 += a; ce2 += b
+        recs, keep = tr.trace_tuple(tup, 8)                    # CR-EOM, one-tuple form: (R, L)
+        _, rr, ll, f, _ = evaluate(recs)
+        a, _ = _energies(plain.t, tup, rr, rr, ll, f)
+        ee1 += a
+    tr.close()
+    assert abs(le1 - g1) <= TOL and abs(le2 - g2) <= TOL
+    assert abs(ce1 - g1) <= TOL and abs(ce2 - g2) <= TOL
+    assert abs(ee1 - g1) <= TOL

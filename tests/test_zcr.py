@@ -331,3 +331,36 @@ def test_cr_sharded_pphp_intermediate_two_contexts_one_gpu(oracle):
     assert np.max(np.abs(parts[0][0] + parts[1][0] - ref["sums"])) <= 1e-12
     tot = eom[0][0] + eom[1][0]
     assert np.max(np.abs(tot - ref_eom["sums"]) / np.abs(ref_eom["sums"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_sibling_corrections_reduce_to_the_golden_t_corrections_on_the_gpu():
+    """The limits of tests/test_qa_h2o.py::test_sibling_restatements_reduce_to_the_golden_t_corrections through the CUDA
+    library: Lambda-CCSD(T) with lambda := T^+, CR-CCSD(T) with undressed intermediates and CR-EOMCCSD(T) with r0 = 1,
+    omega = 0 each contain the (T) correction, and on the first-principles amplitudes of the QA case that is the golden
+    CCSD[T] / CCSD(T) of QA/tests/tce_ccsd_t_h2o/tce_ccsd_t_h2o.out:3374,3376."""
+    from nwchem_b200 import capi
+    from oracle import h2o_ccsd as h, cr_dense
+    from test_qa_h2o import _lambda_from_t, _bare_cr_stores, TOL
+    r = h.load()
+    st = dataclasses.replace(h.qa_stores(r, tilesize=20, c2v=True, intorb=False), orb=None)
+    g1, g2 = h.QA["t_bracket"], h.QA["t_paren"]
+    lam = _lambda_from_t(st)
+    cr = _bare_cr_stores(h, r, st)
+    z = lambda a: np.zeros_like(a)
+    q = cr_dense.CREOMStores(st.t1_hash, z(st.t1), st.t2_hash, z(st.t2), cr.n1_hash, z(cr.n1), cr.n2_hash, z(cr.n2),
+                             cr.n1_hash, z(cr.n1), cr.n2_hash, z(cr.n2), cr.e2_hash, z(cr.e2), 1.0, 0.0)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    tr.set_lambda(lam)
+    le1, le2 = tr.run_lambda()[:2]
+    tr.set_cr(cr)
+    cs = tr.run_cr()
+    cs = cs[0] if isinstance(cs, tuple) else cs
+    tr.set_creom(q)
+    es = tr.run_creom()
+    es = es[0] if isinstance(es, tuple) else es
+    tr.close()
+    assert abs(le1 - g1) <= 2 * TOL and abs(le2 - g2) <= 2 * TOL, (le1, le2)
+    assert abs(cs[0] - g1) <= 2 * TOL and abs(cs[1] - g2) <= 2 * TOL, cs
+    assert abs(es[0] - g1) <= 2 * TOL, es
