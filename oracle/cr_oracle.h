@@ -565,3 +565,135 @@ Integer ora_cr_eomccsd_t(const ora_ctx *c, const ora_cr *cr, const ora_creom *q,
             }
   return count;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* LR-CCSD(T) (locally renormalised), src/tce/ccsd_t/lr_ccsd_t.F: the tuple loop of cr_ccsd_t.F with the same moment    */
+/* tile (cr_ccsd_t_N, :162-166), the (T) doubles tile (:160) and the t1 (x) t2 tile (cr_ccsd_t_E, :167-169), and an      */
+/* extra per-element weight over the three holes.  It exists in the oracle because QA/tests/tce_lr_ccsd_t is the one    */
+/* golden vector of the reference that depends on the DRESSED intermediates and on the E tile (tests/test_qa_lr.py);    */
+/* the library does not offer this method.                                                                              */
+/* ------------------------------------------------------------------------------------------------------------------ */
+
+/* tce_nu1 (lr_ccsd_t.F:425-502): nu(i) = sum_a t1(a,i)^2 over the tile-ordered active holes */
+void ora_tce_nu1(const ora_ctx *c, double *k_hole) {
+  for (Integer p1b = c->noab + 1; p1b <= c->noab + c->nvab; p1b++)
+    for (Integer h2b = 1; h2b <= c->noab; h2b++) {
+      if (SPIN(p1b) != SPIN(h2b)) continue;                                    /* :447 */
+      if ((SYM(p1b) ^ SYM(h2b)) != 0) continue;                                /* :449 */
+      const Integer spinsum = SPIN(p1b) + SPIN(h2b), size = RANGE(p1b) * RANGE(h2b);
+      Integer pp1b = p1b, hh2b = h2b;
+      if (c->restricted && spinsum == 4) { pp1b = c->alpha[p1b - 1]; hh2b = c->alpha[h2b - 1]; } /* :470-472 */
+      double *k_t1 = (double *)malloc(sizeof(double) * (size_t)size);
+      get_hash_block(c->t1, k_t1, size, c->t1_hash, (pp1b - c->noab - 1) * c->noab + hh2b - 1);   /* :454, :473 */
+      Integer i = 0;
+      for (Integer p1 = 0; p1 < RANGE(p1b); p1++)
+        for (Integer h2 = 0; h2 < RANGE(h2b); h2++, i++)
+          k_hole[c->offset[h2b - 1] + h2] += k_t1[i] * k_t1[i];                /* :460-462, :479-481 */
+      free(k_t1);
+    }
+}
+
+/* tce_mu2 (lr_ccsd_t.F:503-631): mu(i,j) = mu(j,i) = sum_{a<b} t2(a,b,i,j)^2, i < j in the tile-ordered spin-orbital list */
+void ora_tce_mu2(const ora_ctx *c, double *k_2hole, Integer hole_p_1) {
+  const Integer n0 = c->noab, n1 = c->noab + c->nvab;
+  for (Integer p1b = n0 + 1; p1b <= n1; p1b++)
+    for (Integer p2b = p1b; p2b <= n1; p2b++)
+      for (Integer h3b = 1; h3b <= n0; h3b++)
+        for (Integer h4b = h3b; h4b <= n0; h4b++) {
+          if (SPIN(p1b) + SPIN(p2b) != SPIN(h3b) + SPIN(h4b)) continue;                      /* :533-534 */
+          if ((SYM(p1b) ^ SYM(p2b) ^ SYM(h3b) ^ SYM(h4b)) != 0) continue;                    /* :537-539 */
+          const Integer spinsum = SPIN(p1b) + SPIN(p2b) + SPIN(h3b) + SPIN(h4b);
+          const Integer size = RANGE(p1b) * RANGE(p2b) * RANGE(h3b) * RANGE(h4b);
+          Integer q1 = p1b, q2 = p2b, g3 = h3b, g4 = h4b;
+          if (c->restricted && spinsum == 8) {                                               /* :579-583 */
+            q1 = c->alpha[p1b - 1]; q2 = c->alpha[p2b - 1]; g3 = c->alpha[h3b - 1]; g4 = c->alpha[h4b - 1];
+          }
+          double *k_t2 = (double *)malloc(sizeof(double) * (size_t)size);
+          get_hash_block(c->t2, k_t2, size, c->t2_hash,
+                         (((q1 - n0 - 1) * c->nvab + q2 - n0 - 1) * n0 + g3 - 1) * n0 + g4 - 1); /* :545-547, :584-586 */
+          Integer i = 0;
+          for (Integer p1 = 1; p1 <= RANGE(p1b); p1++)
+            for (Integer p2 = 1; p2 <= RANGE(p2b); p2++)
+              for (Integer h3 = 1; h3 <= RANGE(h3b); h3++)
+                for (Integer h4 = 1; h4 <= RANGE(h4b); h4++, i++) {
+                  const Integer ipa1 = c->offset[p1b - 1] + p1, ipa2 = c->offset[p2b - 1] + p2;
+                  const Integer iha3 = c->offset[h3b - 1] + h3, iha4 = c->offset[h4b - 1] + h4;   /* :554-557 */
+                  if (ipa1 < ipa2 && iha3 < iha4) {                                               /* :558 */
+                    k_2hole[hole_p_1 * (iha3 - 1) + iha4 - 1] += k_t2[i] * k_t2[i];               /* :559-562 */
+                    k_2hole[hole_p_1 * (iha4 - 1) + iha3 - 1] += k_t2[i] * k_t2[i];               /* :563-566 */
+                  }
+                }
+          free(k_t2);
+        }
+}
+
+/* one tuple of lr_ccsd_t.F:126-385: sums[6] += (num1, num2, den0, den1, den2, den3) = the corrections IA, IB, IIA, IIB,
+ * IIIA, IIIB (:408-413) */
+void ora_lr_ccsd_t_tuple(const ora_ctx *c, const ora_cr *cr, const double *k_hole, const double *k_2hole, Integer hole_p_1,
+                         const Integer *tuple, double *sums) {
+  const Integer t_p4b = tuple[0], t_p5b = tuple[1], t_p6b = tuple[2], t_h1b = tuple[3], t_h2b = tuple[4], t_h3b = tuple[5];
+  const Integer R[6] = {RANGE(t_p4b), RANGE(t_p5b), RANGE(t_p6b), RANGE(t_h1b), RANGE(t_h2b), RANGE(t_h3b)};
+  const size_t size = (size_t)(R[0] * R[1] * R[2] * R[3] * R[4] * R[5]);
+  double *k_doubles = (double *)calloc(size + 1, sizeof(double));                         /* :146-156 */
+  double *k_right = (double *)calloc(size + 1, sizeof(double)), *k_den = (double *)calloc(size + 1, sizeof(double));
+  ora_ccsd_t_doubles_l(c, k_doubles, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b, 0, NULL);  /* :160 */
+  ora_cr_ccsd_t_N_1(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);            /* :162-166 */
+  ora_cr_ccsd_t_N_2(c, cr, k_right, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+  ora_cr_ccsd_t_E_1(c, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);                  /* :167-169 */
+  ora_cr_ccsd_t_E_2(c, cr, k_den, t_p4b, t_p5b, t_p6b, t_h1b, t_h2b, t_h3b);
+  const double factor = ora_ccsd_t_factor((int)c->restricted, t_h1b, t_h2b, t_h3b, t_p4b, t_p5b, t_p6b); /* :170-184 */
+  const double *e4 = c->evl_sorted + c->offset[t_p4b - 1], *e5 = c->evl_sorted + c->offset[t_p5b - 1];
+  const double *e6 = c->evl_sorted + c->offset[t_p6b - 1], *e1 = c->evl_sorted + c->offset[t_h1b - 1];
+  const double *e2 = c->evl_sorted + c->offset[t_h2b - 1], *e3 = c->evl_sorted + c->offset[t_h3b - 1];
+  const Integer o1 = c->offset[t_h1b - 1], o2 = c->offset[t_h2b - 1], o3 = c->offset[t_h3b - 1];
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  size_t i = 0;
+  for (Integer p4 = 0; p4 < R[0]; p4++)
+    for (Integer p5 = 0; p5 < R[1]; p5++)
+      for (Integer p6 = 0; p6 < R[2]; p6++)
+        for (Integer h1 = 0; h1 < R[3]; h1++)
+          for (Integer h2 = 0; h2 < R[4]; h2++)
+            for (Integer h3 = 0; h3 < R[5]; h3++, i++) {
+              const double d = -e4[p4] - e5[p5] - e6[p6] + e1[h1] + e2[h2] + e3[h3];
+              const double w = 1.0 + k_hole[o1 + h1] + k_hole[o2 + h2] + k_hole[o3 + h3] +
+                               k_2hole[hole_p_1 * (o1 + h1) + o2 + h2] + k_2hole[hole_p_1 * (o1 + h1) + o3 + h3] +
+                               k_2hole[hole_p_1 * (o2 + h2) + o3 + h3];
+              const double mm = factor * k_right[i] * k_right[i] / (d * w), em = factor * k_den[i] * k_right[i] / w;
+              const double dm = factor * k_doubles[i] * k_right[i] / (d * w);
+              const double dd = factor * k_doubles[i] * k_doubles[i] / (d * w), ed = factor * k_den[i] * k_doubles[i] / w;
+              s[0] += mm;            /* :194-212 */
+              s[1] += mm + em;       /* :213-243 */
+              s[2] += dm;            /* :244-262 */
+              s[3] += dm + em;       /* :263-293 */
+              s[4] += dd;            /* :294-312 */
+              s[5] += dd + ed;       /* :313-343 */
+            }
+  for (int q = 0; q < 6; q++) sums[q] += s[q];
+  free(k_doubles); free(k_right); free(k_den);
+}
+
+/* lr_ccsd_t: nu, mu (:80-97), then all tuples in the loop order of :126-131 with the filter of :132-150 */
+Integer ora_lr_ccsd_t(const ora_ctx *c, const ora_cr *cr, double *sums) {
+  Integer hole_p_1 = 0, count = 0;
+  for (Integer h = 1; h <= c->noab; h++) hole_p_1 += RANGE(h);                              /* :82 */
+  double *k_hole = (double *)calloc((size_t)hole_p_1, sizeof(double));
+  double *k_2hole = (double *)calloc((size_t)(hole_p_1 * hole_p_1), sizeof(double));
+  ora_tce_nu1(c, k_hole);
+  ora_tce_mu2(c, k_2hole, hole_p_1);
+  for (int q = 0; q < 6; q++) sums[q] = 0.0;
+  const Integer n0 = c->noab, n1 = c->noab + c->nvab;
+  for (Integer p4 = n0 + 1; p4 <= n1; p4++)
+    for (Integer p5 = p4; p5 <= n1; p5++)
+      for (Integer p6 = p5; p6 <= n1; p6++)
+        for (Integer h1 = 1; h1 <= n0; h1++)
+          for (Integer h2 = h1; h2 <= n0; h2++)
+            for (Integer h3 = h2; h3 <= n0; h3++) {
+              if (!tuple_allowed((int)c->restricted, c->spin, c->sym, p4, p5, p6, h1, h2, h3)) continue;
+              const Integer t[6] = {p4, p5, p6, h1, h2, h3};
+              ora_lr_ccsd_t_tuple(c, cr, k_hole, k_2hole, hole_p_1, t, sums);
+              count++;
+            }
+  free(k_hole); free(k_2hole);
+  return count;
+}

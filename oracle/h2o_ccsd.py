@@ -58,6 +58,31 @@ QA_OZONE = dict(scf=-224.327430429177, ccsd_corr=-0.631946819284344, t_bracket=-
                 xmem=dict(scf=-224.327430428908, ccsd_corr=-0.631946818916447, t_bracket=-0.039379871636142, t_paren=-0.036050224479361))
 FIXTURE_OZONE = os.path.join(os.path.dirname(HERE), "tests", "golden", "ozone_ccsd.npz")
 
+# QA/tests/tce_lr_ccsd_t (tce_lr_ccsd_t.nw: glycine, STO-3G, RHF, `freeze atomic`, tilesize 10, lr-ccsd(t)): the one QA case
+# whose golden numbers depend on the DRESSED moment intermediates of cr_ccsd_t_N and on the t1 (x) t2 tile of cr_ccsd_t_E.
+GLYCINE_GEOM = [("O", 8.0, (-2.8770919486, 1.5073755650, 0.3989960497)), ("C", 6.0, (-0.9993929716, 0.2223265108, -0.0939400216)),
+                ("C", 6.0, (1.6330980507, 1.1263991128, -0.7236778647)), ("O", 8.0, (-1.3167079358, -2.3304840070, -0.1955378962)),
+                ("N", 7.0, (3.5887721300, -0.1900460352, 0.6355723246)), ("H", 1.0, (1.7384347574, 3.1922914768, -0.2011420479)),
+                ("H", 1.0, (1.8051078216, 0.9725472539, -2.8503867814)), ("H", 1.0, (3.3674278149, -2.0653924379, 0.5211399625)),
+                ("H", 1.0, (5.2887327108, 0.3011058554, -0.0285088728)), ("H", 1.0, (-3.0501350657, -2.7557071585, 0.2342441831))]
+_S3, _SP_S, _SP_P = [0.15432897, 0.53532814, 0.44463454], [-0.09996723, 0.39951283, 0.70011547], [0.15591627, 0.60768372, 0.39195739]
+
+
+def _sto3g(core, valence):
+    return [(0, core, [_S3]), (0, valence, [_SP_S]), (1, valence, [_SP_P])]
+
+
+# src/basis/libraries/sto-3g: "H_STO-3G", "C_STO-3G", "N_STO-3G", "O_STO-3G"
+STO3G = {"H": [(0, [3.42525091, 0.62391373, 0.16885540], [_S3])],
+         "C": _sto3g([71.6168370, 13.0450960, 3.5305122], [2.9412494, 0.6834831, 0.2222899]),
+         "N": _sto3g([99.1061690, 18.0523120, 4.8856602], [3.7804559, 0.8784966, 0.2857144]),
+         "O": _sto3g([130.7093200, 23.8088610, 6.4436083], [5.0331513, 1.1695961, 0.3803890])}
+# tce_lr_ccsd_t.out:440,:443,:916,:924-939 (correlation energies: CCSD + the LR correction)
+QA_GLYCINE = dict(scf=-279.104932121548, enuc=178.409233643692, ccsd_corr=-0.299493468934347,
+                  lr=dict(IA=-0.307053292111625, IB=-0.305197418406767, IIA=-0.307599613508071,
+                          IIB=-0.305743739803214, IIIA=-0.308248545881664, IIIB=-0.306276971454144))
+FIXTURE_GLYCINE = os.path.join(os.path.dirname(HERE), "tests", "golden", "glycine_sto3g_ccsd.npz")
+
 CART = {0: [(0, 0, 0)], 1: [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
         2: [(2, 0, 0), (0, 2, 0), (0, 0, 2), (1, 1, 0), (1, 0, 1), (0, 1, 1)]}
 # real solid harmonics of l = 2 over (xx, yy, zz, xy, xz, yz); unnormalised (see the module docstring)
@@ -476,6 +501,23 @@ def generate_ozone(verbose=True):
     return dict(escf=escf, ecc=ecc, eps=eps[nfz:], irrep=irrep[nfz:], t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=12 - nfz)
 
 
+def generate_glycine(verbose=True):
+    """The glycine / STO-3G case of QA/tests/tce_lr_ccsd_t: 30 basis functions, 20 occupied orbitals of which the five 1s
+    cores are frozen, 10 virtuals, no symmetry.  Seconds."""
+    S, T, V, eri, enuc = integrals(GLYCINE_GEOM, STO3G, verbose=False)
+    escf, eps, Cm = rhf(S, T, V, eri, enuc, nocc=20)
+    if verbose:
+        print(f"Enuc  {enuc:.12f}   QA {QA_GLYCINE['enuc']:.12f}   diff {enuc - QA_GLYCINE['enuc']:.2e}")
+        print(f"SCF   {escf:.12f}   QA {QA_GLYCINE['scf']:.12f}   diff {escf - QA_GLYCINE['scf']:.2e}", flush=True)
+    nfz = 5
+    Ca = Cm[:, nfz:]
+    eri_mo = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri, Ca, Ca, Ca, Ca, optimize=True)
+    ecc, t1s, t2s = ccsd(eps[nfz:], eri_mo, nocc=20 - nfz)
+    if verbose:
+        print(f"CCSD  {ecc:.12f}   QA {QA_GLYCINE['ccsd_corr']:.12f}   diff {ecc - QA_GLYCINE['ccsd_corr']:.2e}", flush=True)
+    return dict(escf=escf, ecc=ecc, eps=eps[nfz:], irrep=np.zeros(25, dtype=np.int64), t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=20 - nfz)
+
+
 def generate(verbose=True):
     check_basis_against_reference()
     S, T, V, eri, enuc = integrals()
@@ -512,8 +554,9 @@ def _unpack(packed, n):
 
 
 def save(r, path=FIXTURE):
+    extra = {"nocc": r["nocc"]} if "nocc" in r else {}
     np.savez_compressed(path, escf=r["escf"], ecc=r["ecc"], eps=r["eps"], irrep=r["irrep"], t1s=r["t1s"], t2s=r["t2s"],
-                        eri_packed=_pack(r["eri_mo"]))
+                        eri_packed=_pack(r["eri_mo"]), **extra)
 
 
 def load(path=FIXTURE):
@@ -550,6 +593,11 @@ def qa_stores(r=None, tilesize=20, c2v=True, restricted=True, intorb=False):
 
 
 if __name__ == "__main__":
-    r = generate()
-    save(r)
-    print("wrote", FIXTURE, os.path.getsize(FIXTURE), "bytes")
+    import sys
+    if "glycine" in sys.argv[1:]:
+        save(generate_glycine(), FIXTURE_GLYCINE)
+        print("wrote", FIXTURE_GLYCINE, os.path.getsize(FIXTURE_GLYCINE), "bytes")
+    else:
+        r = generate()
+        save(r)
+        print("wrote", FIXTURE, os.path.getsize(FIXTURE), "bytes")

@@ -333,6 +333,20 @@ def cr_ccsd_t(st, cr):
     return dict(sums=s.copy(), per_task=pt[:cnt], e1=float(s[0] / (1.0 + s[2] + den0)), e2=float(s[1] / (1.0 + s[3] + den0)))
 
 
+def lr_ccsd_t(st, cr):
+    """LR-CCSD(T) tuple loop on the CPU (lr_ccsd_t.F restated, cr_oracle.h): the six corrections (IA, IB, IIA, IIB, IIIA,
+    IIIB) of lr_ccsd_t.F:408-413.  Test infrastructure for the QA golden numbers of tce_lr_ccsd_t only."""
+    l = lib()
+    c, keep = make_ctx(st)
+    y, keep2 = make_cr(cr)
+    s = np.zeros(6)
+    l.ora_lr_ccsd_t.restype = L
+    l.ora_lr_ccsd_t(C.byref(c), C.byref(y), _pd(s))
+    if l.ora_error():
+        raise RuntimeError("oracle: block key not found")
+    return dict(zip(("IA", "IB", "IIA", "IIB", "IIIA", "IIIB"), (float(x) for x in s)))
+
+
 def cr_tuple(st, cr, tup):
     """One tuple: (sums[4], moment tile, denominator tile), tiles indexed [p4,p5,p6,h1,h2,h3]."""
     l = lib()

@@ -364,3 +364,26 @@ def test_sibling_corrections_reduce_to_the_golden_t_corrections_on_the_gpu():
     assert abs(le1 - g1) <= 2 * TOL and abs(le2 - g2) <= 2 * TOL, (le1, le2)
     assert abs(cs[0] - g1) <= 2 * TOL and abs(cs[1] - g2) <= 2 * TOL, cs
     assert abs(es[0] - g1) <= 2 * TOL, es
+
+
+@pytest.mark.gpu
+def test_cr_ccsd_t_gpu_on_the_glycine_qa_case(oracle):
+    """CR-CCSD(T) through the CUDA library on the inputs of QA/tests/tce_lr_ccsd_t (glycine / STO-3G, ragged 7 + 8 hole
+    tiles), whose moment and t1 (x) t2 tiles the oracle reproduces the reference's golden LR-CCSD(T) energies with
+    (tests/test_qa_lr.py): per tuple and in total against that oracle."""
+    from nwchem_b200 import capi
+    from oracle import h2o_ccsd as h, cr_dense
+    r = h.load(h.FIXTURE_GLYCINE)
+    st = h.qa_stores(r, tilesize=10, c2v=False)
+    cr = cr_dense.Dense(st.t, dense=(15, 10, r["t1s"], r["t2s"], r["eri_mo"])).stores()
+    ref = oracle.cr_ccsd_t(st, cr)
+    tr = capi.Triples(0)
+    tr.set_state(st)
+    tr.set_cr(cr)
+    sums, pt = tr.run_cr(per_task=True)
+    got = _sorted_rows(tr, pt)
+    tr.close()
+    assert np.max(np.abs(got - ref["per_task"])) <= 1e-13
+    assert np.max(np.abs(sums - ref["sums"])) <= 1e-12
+    e1, e2 = capi.Triples.cr_energies(sums, cr.den0)
+    assert abs(e1 - ref["e1"]) <= 1e-12 and abs(e2 - ref["e2"]) <= 1e-12
