@@ -8,7 +8,9 @@ McMurchie-Davidson integrals over the cc-pVDZ basis (data: src/basis/libraries/c
 RHF, spin-orbital CCSD.  Each stage is checked against the QA output's own intermediate energies (SCF total energy,
 CCSD correlation energy) before the amplitudes are handed to the oracle's (T); the oracle's E[T] / E(T) on them is then
 compared with the golden corrections (tests/test_qa_h2o.py).  `python -m oracle.h2o_ccsd` regenerates
-tests/golden/h2o_ccpvdz_ccsd.npz.
+tests/golden/h2o_ccpvdz_ccsd.npz.  Two more QA cases are generated the same way: ozone (tce_ozone_2eorb / tce_ccsd_t_xmem;
+frozen core, `2eorb`; too large to commit, gated) and glycine / STO-3G (tce_lr_ccsd_t: the LR-CCSD(T) energies, which pin
+the CR-CCSD(T) tiles; `python -m oracle.h2o_ccsd glycine` -> tests/golden/glycine_sto3g_ccsd.npz, tests/test_qa_lr.py).
 
 Energies are invariant under any change of basis within the same span, so no care is taken to normalise the basis
 functions: a contracted function is sum_k c_k a_k^((2l+3)/4) x^i y^j z^k exp(-a_k r^2) (the library's coefficients refer
@@ -89,20 +91,23 @@ CART = {0: [(0, 0, 0)], 1: [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
 SPH_D = np.array([[-1.0, -1.0, 2.0, 0, 0, 0], [1.0, -1.0, 0, 0, 0, 0], [0, 0, 0, 1.0, 0, 0], [0, 0, 0, 0, 1.0, 0], [0, 0, 0, 0, 0, 1.0]])
 
 
-def check_basis_against_reference(path="/root/reference/src/basis/libraries/cc-pvdz"):
-    """The numbers above are the library's (only where the reference tree is mounted)."""
+def check_basis_against_reference(path="/root/reference/src/basis/libraries/cc-pvdz", name="cc-pVDZ", basis=None, elements=("O", "H")):
+    """The numbers above are the library's (only where the reference tree is mounted).  An SP shell of the library is two
+    entries here (s and p over the same exponents), so exponents are compared as sets and coefficients as multisets."""
     if not os.path.exists(path):
         return None
+    basis = BASIS if basis is None else basis
     txt = open(path).read()
-    for el in ("O", "H"):
-        blk = txt[txt.index(f'basis "{el}_cc-pVDZ"'):]
+    for el in elements:
+        blk = txt[txt.index(f'basis "{el}_{name}"'):]
         blk = blk[:blk.index("\nend")]
-        nums = [float(x) for line in blk.split("\n")[1:] for x in line.split() if x[0].isdigit() or x[0] == "-"]
-        mine = []
-        for l, exps, cols in BASIS[el]:
-            for k, a in enumerate(exps):
-                mine += [a] + [c[k] for c in cols]
-        assert np.allclose(sorted(nums), sorted(mine), rtol=0, atol=1e-12), el
+        rows = [[float(x) for x in line.split()] for line in blk.split("\n")[1:] if line.split() and (line.split()[0][0].isdigit() or line.split()[0][0] == "-")]
+        ref_exp = sorted({r[0] for r in rows})
+        ref_cof = sorted(c for r in rows for c in r[1:])
+        my_exp = sorted({a for l, exps, cols in basis[el] for a in exps})
+        my_cof = sorted(c[k] for l, exps, cols in basis[el] for k in range(len(exps)) for c in cols)
+        assert np.allclose(ref_exp, my_exp, rtol=0, atol=1e-12), el
+        assert np.allclose(ref_cof, my_cof, rtol=0, atol=1e-12), el
     return True
 
 
@@ -504,6 +509,7 @@ def generate_ozone(verbose=True):
 def generate_glycine(verbose=True):
     """The glycine / STO-3G case of QA/tests/tce_lr_ccsd_t: 30 basis functions, 20 occupied orbitals of which the five 1s
     cores are frozen, 10 virtuals, no symmetry.  Seconds."""
+    check_basis_against_reference("/root/reference/src/basis/libraries/sto-3g", "STO-3G", STO3G, ("H", "C", "N", "O"))
     S, T, V, eri, enuc = integrals(GLYCINE_GEOM, STO3G, verbose=False)
     escf, eps, Cm = rhf(S, T, V, eri, enuc, nocc=20)
     if verbose:
