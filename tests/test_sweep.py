@@ -105,3 +105,26 @@ def test_random_tilings_creom_and_block_partition(oracle):
                 cur = b
             assert cur == int(full[i, 1]), (t.range, world, i)
     assert ntup >= 50
+
+
+def test_random_tilings_2eorb_host_plan():
+    """the `2eorb` plan (which orbital-form block, strides, sign per half) rebuilds every stored spin-orbital V2 block bit
+    for bit on random tilings (tests/test_host.py does this on the H2O C2v table)"""
+    rng = np.random.default_rng(11)
+    nblk = 0
+    for t in _tilings(rng, 25, 6, 8):
+        st = synth.physical(t, intorb=True)
+        vo = st.orb.v2orb
+        for key, off in synth._iter_hash(st.v2_hash):
+            g3b, g4b, g1b, g2b = tl.decode_v2_key(t, key)
+            dims = [t.r(g3b), t.r(g4b), t.r(g1b), t.r(g2b)]
+            oa, ob, strides = capi.host_2eorb_plan(st, g3b, g4b, g1b, g2b)
+            idx = np.indices(dims).reshape(4, -1)
+            blk = np.zeros(idx.shape[1])
+            if oa >= 0:
+                blk += vo[oa + (idx * strides[0][:, None]).sum(0)]
+            if ob >= 0:
+                blk -= vo[ob + (idx * strides[1][:, None]).sum(0)]
+            assert np.array_equal(blk, st.v2[off:off + int(np.prod(dims))]), (t.range, g3b, g4b, g1b, g2b)
+            nblk += 1
+    assert nblk >= 1000
