@@ -252,6 +252,10 @@ def test_sibling_restatements_reduce_to_the_golden_t_corrections(oracle, qa):
     lam = _lambda_from_t(plain)
     lo = oracle.lambda_ccsd_t(st, lam, sorted=True)
     assert abs(lo["e1"] - g1) <= TOL and abs(lo["e2"] - g2) <= TOL, (lo["e1"], lo["e2"])
+    # the literal reading of lambda_ccsd_t.F (L3-ordered left tile multiplied index by index with the T3-ordered right tile,
+    # DESIGN 8 f3) does not have the (T) limit: this, besides tile-size invariance, is why the library implements the sorted one
+    ll = oracle.lambda_ccsd_t(st, lam, sorted=False)
+    assert abs(ll["e1"] - g1) > 1e-3 and abs(ll["e2"] - g2) > 1e-3
     cr = _bare_cr_stores(h, r, plain)
     co = oracle.cr_ccsd_t(plain, cr)
     assert abs(co["sums"][0] - g1) <= TOL and abs(co["sums"][1] - g2) <= TOL, co["sums"]
