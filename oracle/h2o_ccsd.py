@@ -101,6 +101,17 @@ H2O_DZ_LIT = {1.0: dict(scf=-76.009838, fci=-76.157866, ccsd=1.790, ccsd_t=0.574
               2.0: dict(scf=-75.595180, fci=-75.905247, ccsd=9.333, ccsd_t=-7.699, cr_ccsd_t=1.830)}
 
 
+# The HF / DZ full-CI benchmark of the same paper (R_e = 1.7328 bohr, stretched to 2 R_e and 3 R_e; "F_DZ (Dunning)"): full-CI
+# energies and the errors of CCSD, CCSD(T), CR-CCSD(T) in millihartree.  At 3 R_e CCSD(T) is 24.5 millihartree below full CI
+# and den0 = 0.98.
+DZ_BASIS["F"] = [(0, [9994.79, 1506.03, 350.269, 104.053, 34.8432, 4.3688], [[0.002017, 0.015295, 0.07311, 0.24642, 0.612593, 0.242489]]),
+                 (0, [12.2164], [[1.0]]), (0, [1.2078], [[1.0]]), (0, [0.3634], [[1.0]]),
+                 (1, [44.3555, 10.082, 2.9959, 0.9383], [[0.020868, 0.130092, 0.396219, 0.620368]]), (1, [0.2733], [[1.0]])]
+HF_DZ_LIT = {1.0: dict(fci=-100.160300, ccsd=1.634, ccsd_t=0.325, cr_ccsd_t=0.500),
+             2.0: dict(fci=-100.021733, ccsd=6.047, ccsd_t=0.038, cr_ccsd_t=2.031),
+             3.0: dict(fci=-99.985281, ccsd=11.596, ccsd_t=-24.480, cr_ccsd_t=2.100)}
+
+
 def h2o_dz_geometry(stretch=1.0, re=1.84345, angle=110.565):
     R, th = re * stretch, np.deg2rad(angle) / 2
     return [("O", 8.0, (0.0, 0.0, 0.0)), ("H", 1.0, (0.0, R * np.sin(th), R * np.cos(th))), ("H", 1.0, (0.0, -R * np.sin(th), R * np.cos(th)))]
@@ -545,13 +556,22 @@ def generate_glycine(verbose=True):
     return dict(escf=escf, ecc=ecc, eps=eps[nfz:], irrep=np.zeros(25, dtype=np.int64), t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=20 - nfz)
 
 
-def generate_h2o_dz(stretch=1.0):
-    """SCF + all-electron CCSD of the H2O / DZ benchmark at R = stretch * R_e (14 basis functions; under a second)."""
-    S, T, V, eri, enuc = integrals(h2o_dz_geometry(stretch), DZ_BASIS)
+def _generate_dz(geom):
+    S, T, V, eri, enuc = integrals(geom, DZ_BASIS)
     escf, eps, Cm = rhf(S, T, V, eri, enuc, nocc=5)
     eri_mo = np.einsum("pqrs,pa,qb,rc,sd->abcd", eri, Cm, Cm, Cm, Cm, optimize=True)
-    ecc, t1s, t2s = ccsd(eps, eri_mo, nocc=5, maxit=500)
-    return dict(escf=escf, ecc=ecc, eps=eps, irrep=np.zeros(14, dtype=np.int64), t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=5)
+    ecc, t1s, t2s = ccsd(eps, eri_mo, nocc=5, maxit=800)
+    return dict(escf=escf, ecc=ecc, eps=eps, irrep=np.zeros(len(eps), dtype=np.int64), t1s=t1s, t2s=t2s, eri_mo=eri_mo, nocc=5)
+
+
+def generate_h2o_dz(stretch=1.0):
+    """SCF + all-electron CCSD of the H2O / DZ benchmark at R = stretch * R_e (14 basis functions; under a second)."""
+    return _generate_dz(h2o_dz_geometry(stretch))
+
+
+def generate_hf_dz(stretch=1.0, re=1.7328):
+    """The same for hydrogen fluoride (12 basis functions)."""
+    return _generate_dz([("F", 9.0, (0.0, 0.0, 0.0)), ("H", 1.0, (0.0, 0.0, re * stretch))])
 
 
 def generate(verbose=True):
